@@ -1,0 +1,189 @@
+/* b200rt.h — C ABI of the B200-native render hot path (libb200rt.so).
+ *
+ * Drop-in boundary for the reference's `src/lib` render path (martingleich/RayTracingInAWeekend):
+ * a host layer flattens the reference scene graph into the POD arrays below and calls these entry
+ * points; everything behind them is hand-written sm_100a CUDA.  Plain pointers and sizes only.
+ *
+ * Reference interfaces replaced (file:line relative to the reference repo):
+ *   rt_scene_create   <- the data reachable from `World` (src/lib/rendering.rs:12-17): `Scene::new(root)`
+ *                        (src/lib/hittable.rs:125-128) with root = the flat `BoundingVolumeHierarchy`
+ *                        built by `BoundingVolumeHierarchy::new` (hittable.rs:360-380) from the element list of
+ *                        `NodeRef::finish` (src/app/worlds/world_builder.rs:273-328); `Camera` (src/lib/camera.rs:154-164),
+ *                        `BackgroundColor` (src/lib/background_color.rs:3-6), `WorldScatteringDistributionProvider::Rect`
+ *                        (src/lib/world_scattering_distribution.rs:4-9), `Material` (src/lib/material.rs:43-49),
+ *                        `Texture` (src/lib/texture.rs:4-20).
+ *   rt_trace          <- `Scene::hit(&self, &Ray, &Range<f32>, &mut TRng) -> Option<HitInteraction>` (hittable.rs:130-137)
+ *   rt_render         <- `render(image_size, thread_count, samples_per_pixel, max_depth, &World, RenderMode) -> Vec<Color>`
+ *                        (src/lib/rendering.rs:121-128)
+ *   rt_render_planes_device / rt_film_scale_device
+ *                     <- the per-thread planes + `merge_planes` of the same function (rendering.rs:161-210, 239-252),
+ *                        split so that one process per GPU renders a subset of the sample lanes and the film is
+ *                        combined with an NCCL all-reduce in between.
+ *   rt_to_rgb8_gamma2 <- `Color::to_rgb8_gamma2` (src/lib/color.rs:43-48), applied by the caller in src/app/main.rs:53-56.
+ *
+ * Every function returns 0 on success or a negative RT_E* code; rt_last_error() returns a thread-local
+ * message.  Nothing here ever falls back to a CPU implementation: without a CUDA device the calls fail.
+ */
+#ifndef B200RT_H
+#define B200RT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_OK 0
+#define RT_EINVAL (-1)  /* malformed scene / arguments                        */
+#define RT_ECUDA (-2)   /* CUDA runtime error (no device, launch failure ...) */
+#define RT_ENOMEM (-3)  /* host or device allocation failed                   */
+#define RT_EUNSUPPORTED (-4) /* scene element outside the hot-path scope       */
+
+#define RT_LEAF_BIT 0x80000000u /* BVH child reference: RT_LEAF_BIT | item index  (reference: usize::MAX - index) */
+#define RT_MISS 0xFFFFFFFFu     /* hit id of a ray that hit nothing                */
+
+/* Geometry kinds (reference enum `Geometry`, hittable.rs:104-110; AxisAlignedBox is out of scope) */
+enum { RT_GEO_SPHERE = 0, RT_GEO_RECT = 1, RT_GEO_TRIANGLE = 2 };
+/* RectPlane (rect_geometry.rs:8-22) */
+enum { RT_RECT_XY = 0, RT_RECT_XZ = 1, RT_RECT_YZ = 2 };
+/* Material kinds (material.rs:43-49; Isotropic is volume-only, out of scope) */
+enum { RT_MAT_LAMBERT = 0, RT_MAT_METAL = 1, RT_MAT_DIELECTRIC = 2, RT_MAT_DIFFUSE_LIGHT = 3 };
+/* Texture kinds (texture.rs:4-20; Checker/Marble out of scope) */
+enum { RT_TEX_SOLID = 0, RT_TEX_IMAGE = 1 };
+/* RenderMode (rendering.rs:94-98) */
+enum { RT_MODE_DEFAULT = 0, RT_MODE_NORMALS = 1 };
+
+/* One flattened scene element = SceneElement::SurfaceGeometry(geo, material).  Its index in the array is the
+ * "hit id" (position in `all_elements`, world_builder.rs:316).  `geom` holds, by kind:
+ *   sphere   : center xyz, radius                               (sphere_geometry.rs:6-9)
+ *   rect     : (float)plane, dist, r0.lo, r0.hi, r1.lo, r1.hi   (rect_geometry.rs:24-30)
+ *   triangle : positions[3] xyz, normals[3] xyz, texture_coords[3] uv   (triangle_geometry.rs:6-10) */
+typedef struct RtItem {
+    uint32_t kind;
+    uint32_t material;
+    float geom[24];
+} RtItem;
+
+/* BoundingVolumeNode (hittable.rs:345-351) in the reference's pre-order numbering. */
+typedef struct RtBvhNode {
+    float aabb_min[3];
+    float aabb_max[3];
+    uint32_t left;  /* node index, or RT_LEAF_BIT | item */
+    uint32_t right;
+    uint32_t axis_id;
+} RtBvhNode;
+
+typedef struct RtMaterial {
+    uint32_t kind;
+    uint32_t texture; /* albedo / emit; ignored for dielectric */
+    float param;      /* metal: fuzz; dielectric: index_of_refraction */
+} RtMaterial;
+
+typedef struct RtTexture {
+    uint32_t kind;
+    uint32_t image; /* RT_TEX_IMAGE: index into images */
+    float rgb[3];   /* RT_TEX_SOLID */
+} RtTexture;
+
+typedef struct RtImage {
+    uint32_t width, height;
+    const uint8_t* rgb8; /* row 0 = top, 3 bytes per texel (image::RgbImage) */
+} RtImage;
+
+typedef struct RtCamera { /* camera.rs:154-164, private fields included */
+    float position[3];
+    float upper_left_corner[3];
+    float unit_right[3];
+    float unit_up[3];
+    float scaled_right[3];
+    float scaled_up[3];
+    float lens_radius;
+    float time_start, time_end; /* accepted; ray time is unused without Animation leaves */
+    float shutter_pace[2];
+} RtCamera;
+
+typedef struct RtSceneDesc {
+    uint32_t n_items;
+    const RtItem* items;
+    uint32_t n_nodes;       /* n_items - 1 (0 for a single item) */
+    const RtBvhNode* nodes; /* reference topology; node 0 first */
+    uint32_t root;          /* initial_index: 0, or RT_LEAF_BIT|0 for a single item */
+    uint32_t n_materials;
+    const RtMaterial* materials;
+    uint32_t n_textures;
+    const RtTexture* textures;
+    uint32_t n_images;
+    const RtImage* images;
+    RtCamera camera;
+    uint32_t background_is_sky; /* BackgroundColor::Sky vs ::Solid */
+    float background_rgb[3];
+    uint32_t has_light;         /* Option<WorldScatteringDistributionProvider::Rect> */
+    uint32_t light_plane;
+    float light_dist, light_r0[2], light_r1[2];
+} RtSceneDesc;
+
+typedef struct RtRenderParams {
+    int32_t width, height;      /* Size2i */
+    uint64_t samples_per_pixel;
+    int32_t max_depth;
+    uint32_t thread_count;      /* reference: worker threads; here: sample lanes in flight per pixel.
+                                   Lane id gets spp/T (+1 if id < spp%T) samples — split_work_tasks, rendering.rs:222-237 */
+    uint32_t render_mode;       /* RT_MODE_* */
+    uint64_t seed;              /* Philox key (reference seeds from OS entropy, rendering.rs:160) */
+} RtRenderParams;
+
+typedef struct RtStats {
+    uint64_t ray_segments;   /* top-level closest-hit queries (rendering.rs:25) */
+    uint64_t paths;          /* camera samples generated */
+    uint64_t iterations;     /* wavefront iterations (extend+shade pairs) */
+    uint64_t kernel_launches;
+    double render_ms;        /* device time of the render loop (CUDA events), excluding upload/download */
+    double extend_ms;        /* device time spent in the extend (closest-hit) kernel, when profiling is on */
+    double shade_ms;
+} RtStats;
+
+typedef struct RtScene RtScene;
+
+const char* rt_last_error(void);
+int rt_device_count(int* out_count);
+
+/* Copies everything; the caller keeps ownership of its buffers.  `device` = CUDA ordinal. */
+int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene);
+void rt_scene_destroy(RtScene* scene);
+/* Device bytes held by the packed scene (nodes, primitives, shading records, tables, images). */
+int rt_scene_device_bytes(const RtScene* scene, uint64_t* out_bytes);
+
+/* Closest hit for n caller rays (host buffers).  org/dir: n*3 floats; outputs: hit_id n, t n, normal n*3,
+ * front_face n, uv n*2 (any output pointer may be NULL).  Half-open range [t_min, t_max). */
+int rt_trace(RtScene* scene, const float* org_xyz, const float* dir_xyz, uint64_t n, float t_min, float t_max,
+             uint32_t* hit_id, float* t, float* normal_xyz, uint8_t* front_face, float* uv);
+/* Same on device buffers (as allocated by the caller, e.g. a torch tensor's data_ptr) on `stream`. */
+int rt_trace_device(RtScene* scene, const float* d_org_xyz, const float* d_dir_xyz, uint64_t n, float t_min, float t_max,
+                    uint32_t* d_hit_id, float* d_t, float* d_normal_xyz, uint8_t* d_front_face, float* d_uv,
+                    void* cuda_stream);
+
+/* Whole render into a host buffer: out_rgb = width*height*3 floats, row 0 = top, linear RGB. */
+int rt_render(RtScene* scene, const RtRenderParams* params, float* out_rgb, RtStats* out_stats);
+/* Whole render into a device buffer (width*height*3 floats). */
+int rt_render_device(RtScene* scene, const RtRenderParams* params, float* d_out_rgb, void* cuda_stream,
+                     RtStats* out_stats);
+
+/* Multi-GPU split of render(): this rank renders sample lanes {lane_first, lane_first+lane_stride, ...} < T and
+ * writes  sum over its lanes of (lane plane / lane sample count)  into d_plane_sum (width*height*3 floats).
+ * After summing d_plane_sum over ranks (NCCL all-reduce), rt_film_scale_device multiplies by 1/T (merge_planes). */
+int rt_render_planes_device(RtScene* scene, const RtRenderParams* params, uint32_t lane_first, uint32_t lane_stride,
+                            float* d_plane_sum, void* cuda_stream, RtStats* out_stats);
+int rt_film_scale_device(float* d_rgb, uint64_t n_floats, float multiplier, void* cuda_stream);
+
+/* Color::to_rgb8_gamma2 on device data. */
+int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_out_rgb8, void* cuda_stream);
+
+/* Knobs (process-wide): traversal variant for A/B parity sweeps. 0 = reference node test only (exact, slow),
+ * 1 = reference test AND tight carried-interval cull (default). */
+int rt_set_option(const char* key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RT_H */

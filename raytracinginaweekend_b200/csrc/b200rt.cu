@@ -1,0 +1,642 @@
+// b200rt.cu — C ABI (include/b200rt.h) + host runtime of the B200 render hot path.
+//
+// Host side: validates the flattened reference scene, repacks it into the device layout of rt_device.cuh
+// (children-in-parent 64 B nodes, 64 B primitive / shading records), owns device buffers and drives the
+// wavefront loop.  There is NO CPU fallback: without a CUDA device every entry point returns RT_ECUDA.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo -O3 -Xcompiler -ffp-contract=off
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200rt.h"
+#include "rt_kernels.cuh"
+
+using namespace rt;
+
+namespace {
+
+thread_local std::string g_err;
+int g_opt_traversal = 1;      // 0 = reference node test only, 1 = + tight carried-interval cull
+int g_opt_profile = 0;        // 1 = time extend / shade separately with events (adds syncs)
+int g_opt_check_every = 8;    // host polls the live-path count every N iterations
+int g_opt_blocks_per_sm = 0;  // 0 = from occupancy query
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(expr)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess)                                                                            \
+            return fail(RT_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+}  // namespace
+
+struct RtScene {
+    int device = 0;
+    int sm_count = 0;
+    SceneDev dev{};
+    DevBuf<NodeDev> nodes;
+    DevBuf<PrimDev> prims;
+    DevBuf<ShadeDev> shade;
+    DevBuf<MaterialDev> materials;
+    DevBuf<TextureDev> textures;
+    std::vector<DevBuf<uint8_t>*> images;
+    uint64_t device_bytes = 0;
+    uint32_t depth = 0;
+    // render workspace (grown on demand, reused across renders)
+    DevBuf<float4> A[2], B[2], C[2], acc;
+    DevBuf<int32_t> D[2];
+    DevBuf<uint2> hits;
+    DevBuf<Counters> ctr;
+    DevBuf<float> film;
+    Counters* h_ctr = nullptr;  // pinned
+    size_t ws_slots = 0;
+    ~RtScene() {
+        for (auto* b : images) delete b;
+        if (h_ctr) cudaFreeHost(h_ctr);
+    }
+};
+
+namespace {
+
+struct Box {
+    float mn[3], mx[3];
+};
+
+// Geometry::bounding_box (hittable.rs:150-157) for leaf children; used only by the tight cull.
+Box leaf_box(const RtItem& it) {
+    Box b;
+    const float* g = it.geom;
+    if (it.kind == RT_GEO_SPHERE) {  // aabb.rs:20-25
+        for (int i = 0; i < 3; ++i) { b.mn[i] = g[i] - g[3]; b.mx[i] = g[i] + g[3]; }
+    } else if (it.kind == RT_GEO_RECT) {  // rect_geometry.rs:87-98, thickness 0.01
+        int plane = (int)g[0];
+        int p0 = plane == RT_RECT_YZ ? 1 : 0, p1 = plane == RT_RECT_XY ? 1 : 2, n = plane == RT_RECT_XY ? 2 : (plane == RT_RECT_XZ ? 1 : 0);
+        b.mn[p0] = g[2]; b.mx[p0] = g[3];
+        b.mn[p1] = g[4]; b.mx[p1] = g[5];
+        b.mn[n] = g[1] - 0.01f; b.mx[n] = g[1] + 0.01f;
+    } else {  // triangle_geometry.rs:47-49
+        for (int i = 0; i < 3; ++i) {
+            b.mn[i] = std::fmin(std::fmin(g[i], g[3 + i]), g[6 + i]);
+            b.mx[i] = std::fmax(std::fmax(g[i], g[3 + i]), g[6 + i]);
+        }
+    }
+    return b;
+}
+
+struct H3 {
+    float x, y, z;
+};
+inline H3 hsub(H3 a, H3 b) { return H3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline float hdot(H3 a, H3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline H3 hcross(H3 a, H3 b) { return H3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+// Per-triangle constants of TriangleGeometry::hit (triangle_geometry.rs:14-29), same op order, IEEE single.
+PrimDev pack_triangle(const float* g) {
+    H3 p0{g[0], g[1], g[2]}, p1{g[3], g[4], g[5]}, p2{g[6], g[7], g[8]};
+    H3 dir1 = hsub(p1, p0), dir2 = hsub(p2, p0);
+    H3 c = hcross(dir1, dir2);
+    float len = std::sqrt(hdot(c, c));
+    float s = 1.0f / len;  // Dir3::unit = self * (1.0 / length)
+    H3 n{c.x * s, c.y * s, c.z * s};
+    H3 vt1 = hcross(n, dir2);
+    float d1 = hdot(dir1, vt1);
+    H3 vt2 = hcross(n, dir1);
+    float d2 = hdot(dir2, vt2);
+    PrimDev p;
+    p.q0 = make_float4(p0.x, p0.y, p0.z, n.x);
+    p.q1 = make_float4(n.y, n.z, vt1.x, vt1.y);
+    p.q2 = make_float4(vt1.z, d1, vt2.x, vt2.y);
+    p.q3 = make_float4(vt2.z, d2, 0.0f, 0.0f);
+    return p;
+}
+
+inline float u2f(uint32_t u) {
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+int pack_scene(const RtSceneDesc& d, RtScene& sc) {
+    const uint32_t N = d.n_items;
+    if (N == 0) return fail(RT_EINVAL, "scene has no items (the reference BVH builder recurses forever on an empty list)");
+    if (N > RT_REF_ITEM_MASK) return fail(RT_EINVAL, "too many items");
+    if (!d.items) return fail(RT_EINVAL, "items is NULL");
+    if (d.n_nodes != N - 1) return fail(RT_EINVAL, "n_nodes must be n_items - 1 (reference BVH topology)");
+    if (d.n_nodes && !d.nodes) return fail(RT_EINVAL, "nodes is NULL");
+    if (d.n_materials == 0 || !d.materials) return fail(RT_EINVAL, "no materials");
+    for (uint32_t i = 0; i < d.n_materials; ++i) {
+        const RtMaterial& m = d.materials[i];
+        if (m.kind > RT_MAT_DIFFUSE_LIGHT) return fail(RT_EUNSUPPORTED, "material kind outside the hot-path scope (Isotropic is volume-only)");
+        if (m.kind != RT_MAT_DIELECTRIC && m.texture >= d.n_textures) return fail(RT_EINVAL, "material texture index out of range");
+    }
+    for (uint32_t i = 0; i < d.n_textures; ++i) {
+        const RtTexture& t = d.textures[i];
+        if (t.kind > RT_TEX_IMAGE) return fail(RT_EUNSUPPORTED, "texture kind outside the hot-path scope (Checker/Marble)");
+        if (t.kind == RT_TEX_IMAGE && (t.image >= d.n_images || !d.images[t.image].rgb8 || d.images[t.image].width == 0 || d.images[t.image].height == 0))
+            return fail(RT_EINVAL, "image texture refers to a missing image");
+    }
+    auto ref_of_item = [&](uint32_t item) { return RT_REF_LEAF | (d.items[item].kind << RT_REF_KIND_SHIFT) | item; };
+    auto conv_ref = [&](uint32_t r, uint32_t* out) -> bool {
+        if (r & RT_LEAF_BIT) {
+            uint32_t item = r & ~RT_LEAF_BIT;
+            if (item >= N) return false;
+            *out = ref_of_item(item);
+        } else {
+            if (r >= d.n_nodes) return false;
+            *out = r;
+        }
+        return true;
+    };
+
+    std::vector<PrimDev> prims(N);
+    std::vector<ShadeDev> shade(N);
+    std::vector<Box> lbox(N);
+    float r_min = INFINITY, r_max = 0.0f;
+    for (uint32_t i = 0; i < N; ++i) {
+        const RtItem& it = d.items[i];
+        if (it.kind > RT_GEO_TRIANGLE) return fail(RT_EUNSUPPORTED, "geometry kind outside the hot-path scope (AxisAlignedBox/volumes/transform wrappers)");
+        if (it.material >= d.n_materials) return fail(RT_EINVAL, "item material index out of range");
+        const float* g = it.geom;
+        PrimDev p;
+        p.q0 = p.q1 = p.q2 = p.q3 = make_float4(0, 0, 0, 0);
+        ShadeDev s;
+        s.q0 = s.q1 = s.q2 = s.q3 = make_float4(0, 0, 0, 0);
+        if (it.kind == RT_GEO_SPHERE) {
+            if (!(g[3] >= 0.0f)) return fail(RT_EINVAL, "sphere radius must be >= 0 (sphere_geometry.rs:13)");
+            p.q0 = make_float4(g[0], g[1], g[2], g[3]);
+            r_min = std::min(r_min, g[3]);
+            r_max = std::max(r_max, g[3]);
+        } else if (it.kind == RT_GEO_RECT) {
+            uint32_t plane = (uint32_t)g[0];
+            if (plane > RT_RECT_YZ) return fail(RT_EINVAL, "rect plane out of range");
+            p.q0 = make_float4(g[1], g[2], g[3], g[4]);
+            p.q1 = make_float4(g[5], u2f(plane), 0.0f, 0.0f);
+        } else {
+            p = pack_triangle(g);
+            s.q0 = make_float4(g[9], g[10], g[11], g[12]);
+            s.q1 = make_float4(g[13], g[14], g[15], g[16]);
+            s.q2 = make_float4(g[17], g[18], g[19], g[20]);
+            s.q3 = make_float4(g[21], g[22], g[23], 0.0f);
+        }
+        s.q3.w = u2f(it.material);
+        prims[i] = p;
+        shade[i] = s;
+        lbox[i] = leaf_box(it);
+    }
+
+    std::vector<NodeDev> nodes(d.n_nodes);
+    auto child_box = [&](uint32_t r) -> Box {
+        if (r & RT_LEAF_BIT) return lbox[r & ~RT_LEAF_BIT];
+        Box b;
+        for (int k = 0; k < 3; ++k) { b.mn[k] = d.nodes[r].aabb_min[k]; b.mx[k] = d.nodes[r].aabb_max[k]; }
+        return b;
+    };
+    for (uint32_t i = 0; i < d.n_nodes; ++i) {
+        const RtBvhNode& n = d.nodes[i];
+        uint32_t l, r;
+        if (!conv_ref(n.left, &l) || !conv_ref(n.right, &r)) return fail(RT_EINVAL, "BVH child reference out of range");
+        if (n.axis_id > 2) return fail(RT_EINVAL, "BVH axis_id out of range");
+        Box bl = child_box(n.left), br = child_box(n.right);
+        NodeDev nd;
+        nd.q0 = make_float4(bl.mn[0], bl.mn[1], bl.mn[2], bl.mx[0]);
+        nd.q1 = make_float4(bl.mx[1], bl.mx[2], br.mn[0], br.mn[1]);
+        nd.q2 = make_float4(br.mn[2], br.mx[0], br.mx[1], br.mx[2]);
+        nd.q3 = make_uint4(l, r, n.axis_id, 0u);
+        nodes[i] = nd;
+    }
+    // depth of the tree (iterative DFS; also rejects cycles by bounding the visit count)
+    uint32_t root;
+    if (!conv_ref(d.root, &root)) return fail(RT_EINVAL, "root reference out of range");
+    uint32_t depth = 0;
+    if (!(root & RT_REF_LEAF)) {
+        std::vector<std::pair<uint32_t, uint32_t>> st;
+        st.push_back({root, 1u});
+        size_t visited = 0;
+        while (!st.empty()) {
+            auto [nd, dep] = st.back();
+            st.pop_back();
+            if (++visited > (size_t)d.n_nodes) return fail(RT_EINVAL, "BVH is not a tree");
+            depth = std::max(depth, dep);
+            uint32_t ch[2] = {nodes[nd].q3.x, nodes[nd].q3.y};
+            for (uint32_t c : ch)
+                if (!(c & RT_REF_LEAF)) st.push_back({c, dep + 1});
+        }
+    }
+    sc.depth = depth;
+
+    SceneDev& S = sc.dev;
+    std::memset(&S, 0, sizeof(S));
+    S.root = root;
+    S.n_items = N;
+    float extent = 0.0f;
+    if (!(root & RT_REF_LEAF)) {
+        for (int k = 0; k < 3; ++k) {
+            S.root_min[k] = d.nodes[root].aabb_min[k];
+            S.root_max[k] = d.nodes[root].aabb_max[k];
+            extent = std::max(extent, std::max(std::fabs(S.root_min[k]), std::fabs(S.root_max[k])));
+        }
+    } else {
+        for (int k = 0; k < 3; ++k) extent = std::max(extent, std::max(std::fabs(lbox[0].mn[k]), std::fabs(lbox[0].mx[k])));
+    }
+    for (int k = 0; k < 3; ++k) extent = std::max(extent, std::fabs(d.camera.position[k]));
+    S.stack_cap = depth + 2;
+    // Guard band of the tight cull (DESIGN.md "Tight node test"): a primitive test can report a hit for a ray that
+    // misses the primitive's true AABB by the rounding slack of that test.  Spheres: |disc error| <~ 6 eps |oc|^2
+    // -> lateral slack <~ 3 eps (t^2 / r + r); triangles / rects: ~ eps * coordinate magnitude.
+    const float eps = 5.9604645e-8f, safety = 8.0f;
+    S.margin_a = safety * eps * (extent + 3.0f * r_max);
+    S.margin_b = 1e-5f;
+    S.margin_c = (r_min < INFINITY && r_min > 0.0f) ? safety * 3.0f * eps / r_min : 0.0f;
+
+    const RtCamera& c = d.camera;
+    S.cam.position = make_float3(c.position[0], c.position[1], c.position[2]);
+    S.cam.ulc = make_float3(c.upper_left_corner[0], c.upper_left_corner[1], c.upper_left_corner[2]);
+    S.cam.unit_right = make_float3(c.unit_right[0], c.unit_right[1], c.unit_right[2]);
+    S.cam.unit_up = make_float3(c.unit_up[0], c.unit_up[1], c.unit_up[2]);
+    S.cam.scaled_right = make_float3(c.scaled_right[0], c.scaled_right[1], c.scaled_right[2]);
+    S.cam.scaled_up = make_float3(c.scaled_up[0], c.scaled_up[1], c.scaled_up[2]);
+    S.cam.lens_radius = c.lens_radius;
+    S.bg_is_sky = d.background_is_sky ? 1u : 0u;
+    for (int k = 0; k < 3; ++k) S.bg[k] = d.background_rgb[k];
+    S.has_light = d.has_light ? 1u : 0u;
+    if (d.has_light && d.light_plane > RT_RECT_YZ) return fail(RT_EINVAL, "light plane out of range");
+    S.light_plane = d.light_plane;
+    S.light_dist = d.light_dist;
+    S.light_r0lo = d.light_r0[0]; S.light_r0hi = d.light_r0[1];
+    S.light_r1lo = d.light_r1[0]; S.light_r1hi = d.light_r1[1];
+
+    // upload
+    CU(cudaSetDevice(sc.device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, sc.device));
+    sc.sm_count = prop.multiProcessorCount;
+    CU(sc.nodes.alloc(std::max<size_t>(nodes.size(), 1)));
+    CU(sc.prims.alloc(N));
+    CU(sc.shade.alloc(N));
+    if (!nodes.empty()) CU(cudaMemcpy(sc.nodes.p, nodes.data(), nodes.size() * sizeof(NodeDev), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(sc.prims.p, prims.data(), N * sizeof(PrimDev), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(sc.shade.p, shade.data(), N * sizeof(ShadeDev), cudaMemcpyHostToDevice));
+    sc.device_bytes = nodes.size() * sizeof(NodeDev) + (uint64_t)N * (sizeof(PrimDev) + sizeof(ShadeDev));
+
+    std::vector<const uint8_t*> img_dev(d.n_images, nullptr);
+    for (uint32_t i = 0; i < d.n_images; ++i) {
+        size_t bytes = (size_t)d.images[i].width * d.images[i].height * 3;
+        auto* b = new DevBuf<uint8_t>();
+        sc.images.push_back(b);
+        CU(b->alloc(bytes));
+        CU(cudaMemcpy(b->p, d.images[i].rgb8, bytes, cudaMemcpyHostToDevice));
+        img_dev[i] = b->p;
+        sc.device_bytes += bytes;
+    }
+    std::vector<MaterialDev> mats(d.n_materials);
+    for (uint32_t i = 0; i < d.n_materials; ++i) mats[i] = MaterialDev{d.materials[i].kind, d.materials[i].kind == RT_MAT_DIELECTRIC ? 0u : d.materials[i].texture, d.materials[i].param, 0u};
+    std::vector<TextureDev> texs(std::max<uint32_t>(d.n_textures, 1));
+    std::memset(texs.data(), 0, texs.size() * sizeof(TextureDev));
+    for (uint32_t i = 0; i < d.n_textures; ++i) {
+        TextureDev t{};
+        t.kind = d.textures[i].kind;
+        t.r = d.textures[i].rgb[0]; t.g = d.textures[i].rgb[1]; t.b = d.textures[i].rgb[2];
+        if (t.kind == RT_TEX_IMAGE) {
+            t.width = d.images[d.textures[i].image].width;
+            t.height = d.images[d.textures[i].image].height;
+            t.texels = img_dev[d.textures[i].image];
+        }
+        texs[i] = t;
+    }
+    CU(sc.materials.alloc(mats.size()));
+    CU(sc.textures.alloc(texs.size()));
+    CU(cudaMemcpy(sc.materials.p, mats.data(), mats.size() * sizeof(MaterialDev), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(sc.textures.p, texs.data(), texs.size() * sizeof(TextureDev), cudaMemcpyHostToDevice));
+    sc.device_bytes += mats.size() * sizeof(MaterialDev) + texs.size() * sizeof(TextureDev);
+    S.nodes = sc.nodes.p;
+    S.prims = sc.prims.p;
+    S.shade = sc.shade.p;
+    S.materials = sc.materials.p;
+    S.textures = sc.textures.p;
+    return RT_OK;
+}
+
+size_t stack_smem_bytes(const RtScene& sc, int block) { return (size_t)sc.dev.stack_cap * block * 8; }
+
+template <class K>
+int persistent_grid(const RtScene& sc, K kernel, int block, size_t smem, int* out_grid) {
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+    if (per_sm < 1) return fail(RT_ECUDA, "kernel does not fit on an SM (BVH too deep for the shared-memory stack)");
+    if (g_opt_blocks_per_sm > 0) per_sm = std::min(per_sm, g_opt_blocks_per_sm);
+    *out_grid = per_sm * sc.sm_count;
+    return RT_OK;
+}
+
+int ensure_workspace(RtScene& sc, size_t slots, size_t npix) {
+    if (sc.ws_slots < slots) {
+        for (int q = 0; q < 2; ++q) {
+            CU(sc.A[q].alloc(slots));
+            CU(sc.B[q].alloc(slots));
+            CU(sc.C[q].alloc(slots));
+            CU(sc.D[q].alloc(slots));
+        }
+        CU(sc.hits.alloc(slots));
+        CU(sc.acc.alloc(slots));
+        sc.ws_slots = slots;
+    }
+    if (!sc.ctr.p) CU(sc.ctr.alloc(1));
+    if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, sizeof(Counters)));
+    if (sc.film.n < npix * 3) CU(sc.film.alloc(npix * 3));
+    return RT_OK;
+}
+
+// The wavefront loop.  Writes the (unscaled unless apply_scale) film into d_out.
+int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint32_t lane_stride, float* d_out, bool apply_scale,
+                cudaStream_t stream, RtStats* stats) {
+    if (P.width < 2 || P.height < 2) return fail(RT_EINVAL, "image must be at least 2x2 (reference divides by width-1 / height-1)");
+    if (P.samples_per_pixel == 0) return fail(RT_EINVAL, "samples_per_pixel must be >= 1");
+    if (P.thread_count == 0) return fail(RT_EINVAL, "thread_count must be >= 1");
+    if (P.render_mode > RT_MODE_NORMALS) return fail(RT_EINVAL, "unknown render mode");
+    if (lane_stride == 0) return fail(RT_EINVAL, "lane_stride must be >= 1");
+    const uint64_t T = P.thread_count;
+    const uint64_t n_tasks = std::min<uint64_t>(T, P.samples_per_pixel);
+    if (P.samples_per_pixel / T + 1 > 0xFFFFFFFFull) return fail(RT_EINVAL, "too many samples per lane");
+    const size_t npix = (size_t)P.width * P.height;
+    CU(cudaSetDevice(sc.device));
+    if (lane_first >= n_tasks) {  // this rank owns no lane: contributes zeros
+        CU(cudaMemsetAsync(d_out, 0, npix * 3 * sizeof(float), stream));
+        if (stats) std::memset(stats, 0, sizeof(*stats));
+        return RT_OK;
+    }
+    const uint32_t n_local = (uint32_t)((n_tasks - lane_first + lane_stride - 1) / lane_stride);
+    const size_t slots = (size_t)n_local * npix;
+    if (slots > 0xFFFFFFF0ull) return fail(RT_EINVAL, "width*height*lanes exceeds 2^32 path slots");
+    int rc = ensure_workspace(sc, slots, npix);
+    if (rc) return rc;
+
+    RenderDev R{};
+    for (int q = 0; q < 2; ++q) { R.A[q] = sc.A[q].p; R.B[q] = sc.B[q].p; R.C[q] = sc.C[q].p; R.D[q] = sc.D[q].p; }
+    R.hits = sc.hits.p;
+    R.acc = sc.acc.p;
+    R.ctr = sc.ctr.p;
+    R.npix = (uint32_t)npix; R.width = (uint32_t)P.width; R.height = (uint32_t)P.height;
+    R.max_depth = P.max_depth;
+    R.n_tasks = (uint32_t)n_tasks;
+    R.lane_first = lane_first; R.lane_stride = lane_stride; R.n_local_lanes = n_local;
+    R.spp_whole = (uint32_t)(P.samples_per_pixel / T);
+    R.spp_rem = (uint32_t)(P.samples_per_pixel % T);
+    R.seed0 = (uint32_t)P.seed; R.seed1 = (uint32_t)(P.seed >> 32);
+    R.sx = 1.0f / (float)(P.width - 1);
+    R.sy = 1.0f / (float)(P.height - 1);
+    R.mode = P.render_mode;
+
+    const int eblock = 128;
+    const size_t esmem = stack_smem_bytes(sc, eblock);
+    int egrid = 0, sgrid = 0;
+    const bool tight = g_opt_traversal != 0;
+    if (tight) rc = persistent_grid(sc, k_extend<true>, eblock, esmem, &egrid);
+    else rc = persistent_grid(sc, k_extend<false>, eblock, esmem, &egrid);
+    if (rc) return rc;
+    rc = persistent_grid(sc, k_shade, 128, 0, &sgrid);
+    if (rc) return rc;
+
+    cudaEvent_t ev0, ev1, eva, evb;
+    CU(cudaEventCreate(&ev0));
+    CU(cudaEventCreate(&ev1));
+    CU(cudaEventCreate(&eva));
+    CU(cudaEventCreate(&evb));
+    uint64_t launches = 0, iters = 0;
+    double extend_ms = 0.0, shade_ms = 0.0;
+    CU(cudaEventRecord(ev0, stream));
+    {
+        int ggrid = (int)std::min<size_t>((slots + 255) / 256, (size_t)sc.sm_count * 8);
+        k_generate<<<ggrid, 256, 0, stream>>>(sc.dev, R);
+        ++launches;
+    }
+    int q = 0;
+    const uint64_t max_iters = (uint64_t)(R.spp_whole + 1u) * (uint64_t)std::max(P.max_depth, 1) + 4;
+    bool done = false;
+    while (!done) {
+        for (int it = 0; it < g_opt_check_every; ++it) {
+            if (g_opt_profile) CU(cudaEventRecord(eva, stream));
+            if (tight) k_extend<true><<<egrid, eblock, esmem, stream>>>(sc.dev, R, q);
+            else k_extend<false><<<egrid, eblock, esmem, stream>>>(sc.dev, R, q);
+            if (g_opt_profile) {
+                CU(cudaEventRecord(evb, stream));
+                CU(cudaEventSynchronize(evb));
+                float ms;
+                CU(cudaEventElapsedTime(&ms, eva, evb));
+                extend_ms += ms;
+                CU(cudaEventRecord(eva, stream));
+            }
+            k_shade<<<sgrid, 128, 0, stream>>>(sc.dev, R, q);
+            if (g_opt_profile) {
+                CU(cudaEventRecord(evb, stream));
+                CU(cudaEventSynchronize(evb));
+                float ms;
+                CU(cudaEventElapsedTime(&ms, eva, evb));
+                shade_ms += ms;
+            }
+            launches += 2;
+            ++iters;
+            q ^= 1;
+        }
+        CU(cudaMemcpyAsync(sc.h_ctr, sc.ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        if (sc.h_ctr->n[q] == 0) done = true;
+        if (iters > max_iters) return fail(RT_ECUDA, "wavefront loop did not terminate");
+    }
+    {
+        int fgrid = (int)std::min<size_t>((npix + 255) / 256, (size_t)sc.sm_count * 8);
+        k_finalize<<<fgrid, 256, 0, stream>>>(R, d_out, 1.0f / (float)n_tasks, apply_scale ? 1 : 0);
+        ++launches;
+    }
+    CU(cudaEventRecord(ev1, stream));
+    CU(cudaEventSynchronize(ev1));
+    CU(cudaGetLastError());
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(eva); cudaEventDestroy(evb);
+    if (stats) {
+        stats->ray_segments = sc.h_ctr->rays;
+        stats->paths = sc.h_ctr->paths;
+        stats->iterations = iters;
+        stats->kernel_launches = launches;
+        stats->render_ms = ms;
+        stats->extend_ms = extend_ms;
+        stats->shade_ms = shade_ms;
+    }
+    return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rt_last_error(void) { return g_err.c_str(); }
+
+int rt_device_count(int* out_count) {
+    if (!out_count) return fail(RT_EINVAL, "out_count is NULL");
+    CU(cudaGetDeviceCount(out_count));
+    return RT_OK;
+}
+
+int rt_set_option(const char* key, int64_t value) {
+    if (!key) return fail(RT_EINVAL, "key is NULL");
+    std::string k(key);
+    if (k == "traversal") g_opt_traversal = (int)value;
+    else if (k == "profile") g_opt_profile = (int)value;
+    else if (k == "check_every") g_opt_check_every = std::max<int>(1, (int)value);
+    else if (k == "blocks_per_sm") g_opt_blocks_per_sm = (int)value;
+    else return fail(RT_EINVAL, "unknown option " + k);
+    return RT_OK;
+}
+
+int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene) {
+    if (!desc || !out_scene) return fail(RT_EINVAL, "NULL argument");
+    *out_scene = nullptr;
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(RT_ECUDA, "CUDA device ordinal out of range (no CPU fallback exists)");
+    RtScene* sc = new (std::nothrow) RtScene();
+    if (!sc) return fail(RT_ENOMEM, "out of host memory");
+    sc->device = device;
+    int rc = pack_scene(*desc, *sc);
+    if (rc != RT_OK) {
+        delete sc;
+        return rc;
+    }
+    *out_scene = sc;
+    return RT_OK;
+}
+
+void rt_scene_destroy(RtScene* scene) {
+    if (!scene) return;
+    cudaSetDevice(scene->device);
+    delete scene;
+}
+
+int rt_scene_device_bytes(const RtScene* scene, uint64_t* out_bytes) {
+    if (!scene || !out_bytes) return fail(RT_EINVAL, "NULL argument");
+    *out_bytes = scene->device_bytes;
+    return RT_OK;
+}
+
+int rt_trace_device(RtScene* scene, const float* d_org, const float* d_dir, uint64_t n, float t_min, float t_max,
+                    uint32_t* d_hit_id, float* d_t, float* d_normal, uint8_t* d_front_face, float* d_uv, void* cuda_stream) {
+    if (!scene) return fail(RT_EINVAL, "scene is NULL");
+    if (n == 0) return RT_OK;
+    if (!d_org || !d_dir) return fail(RT_EINVAL, "ray buffers are NULL");
+    CU(cudaSetDevice(scene->device));
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const int block = 128;
+    const size_t smem = stack_smem_bytes(*scene, block);
+    int grid = 0, rc;
+    const bool tight = g_opt_traversal != 0;
+    if (tight) rc = persistent_grid(*scene, k_trace<true>, block, smem, &grid);
+    else rc = persistent_grid(*scene, k_trace<false>, block, smem, &grid);
+    if (rc) return rc;
+    grid = (int)std::min<uint64_t>((n + block - 1) / block, (uint64_t)grid * 4);
+    if (tight) k_trace<true><<<grid, block, smem, stream>>>(scene->dev, d_org, d_dir, n, t_min, t_max, d_hit_id, d_t, d_normal, d_front_face, d_uv);
+    else k_trace<false><<<grid, block, smem, stream>>>(scene->dev, d_org, d_dir, n, t_min, t_max, d_hit_id, d_t, d_normal, d_front_face, d_uv);
+    CU(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_trace(RtScene* scene, const float* org, const float* dir, uint64_t n, float t_min, float t_max, uint32_t* hit_id,
+             float* t, float* normal, uint8_t* front_face, float* uv) {
+    if (!scene) return fail(RT_EINVAL, "scene is NULL");
+    if (n == 0) return RT_OK;
+    if (!org || !dir) return fail(RT_EINVAL, "ray buffers are NULL");
+    CU(cudaSetDevice(scene->device));
+    DevBuf<float> d_org, d_dir, d_t, d_n, d_uv;
+    DevBuf<uint32_t> d_id;
+    DevBuf<uint8_t> d_ff;
+    CU(d_org.alloc(n * 3));
+    CU(d_dir.alloc(n * 3));
+    CU(d_id.alloc(n));
+    CU(d_t.alloc(n));
+    CU(d_n.alloc(n * 3));
+    CU(d_ff.alloc(n));
+    CU(d_uv.alloc(n * 2));
+    CU(cudaMemcpy(d_org.p, org, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_dir.p, dir, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    int rc = rt_trace_device(scene, d_org.p, d_dir.p, n, t_min, t_max, d_id.p, d_t.p, d_n.p, d_ff.p, d_uv.p, nullptr);
+    if (rc) return rc;
+    CU(cudaDeviceSynchronize());
+    if (hit_id) CU(cudaMemcpy(hit_id, d_id.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (t) CU(cudaMemcpy(t, d_t.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (normal) CU(cudaMemcpy(normal, d_n.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (front_face) CU(cudaMemcpy(front_face, d_ff.p, n, cudaMemcpyDeviceToHost));
+    if (uv) CU(cudaMemcpy(uv, d_uv.p, n * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_render_planes_device(RtScene* scene, const RtRenderParams* params, uint32_t lane_first, uint32_t lane_stride,
+                            float* d_plane_sum, void* cuda_stream, RtStats* out_stats) {
+    if (!scene || !params || !d_plane_sum) return fail(RT_EINVAL, "NULL argument");
+    return render_core(*scene, *params, lane_first, lane_stride, d_plane_sum, false, (cudaStream_t)cuda_stream, out_stats);
+}
+
+int rt_render_device(RtScene* scene, const RtRenderParams* params, float* d_out_rgb, void* cuda_stream, RtStats* out_stats) {
+    if (!scene || !params || !d_out_rgb) return fail(RT_EINVAL, "NULL argument");
+    return render_core(*scene, *params, 0, 1, d_out_rgb, true, (cudaStream_t)cuda_stream, out_stats);
+}
+
+int rt_render(RtScene* scene, const RtRenderParams* params, float* out_rgb, RtStats* out_stats) {
+    if (!scene || !params || !out_rgb) return fail(RT_EINVAL, "NULL argument");
+    if (params->width < 2 || params->height < 2) return fail(RT_EINVAL, "image must be at least 2x2");
+    CU(cudaSetDevice(scene->device));
+    const size_t n = (size_t)params->width * params->height * 3;
+    if (scene->film.n < n) CU(scene->film.alloc(n));
+    int rc = render_core(*scene, *params, 0, 1, scene->film.p, true, nullptr, out_stats);
+    if (rc) return rc;
+    CU(cudaMemcpy(out_rgb, scene->film.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_film_scale_device(float* d_rgb, uint64_t n_floats, float multiplier, void* cuda_stream) {
+    if (!d_rgb) return fail(RT_EINVAL, "NULL argument");
+    if (n_floats == 0) return RT_OK;
+    int grid = (int)std::min<uint64_t>((n_floats + 255) / 256, 148 * 16);
+    k_scale<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_rgb, n_floats, multiplier);
+    CU(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_out, void* cuda_stream) {
+    if (!d_rgb || !d_out) return fail(RT_EINVAL, "NULL argument");
+    if (n_pixels == 0) return RT_OK;
+    uint64_t n = n_pixels * 3;
+    int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+    k_gamma2<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_rgb, n, d_out);
+    CU(cudaGetLastError());
+    return RT_OK;
+}
+
+}  // extern "C"

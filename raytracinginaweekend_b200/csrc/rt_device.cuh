@@ -1,0 +1,432 @@
+// rt_device.cuh — device data layout + device functions of the B200 render hot path.
+//
+// Everything in here is compiled with --fmad=false: the reference is Rust (never contracts a*b+c), so
+// every float op below is a single IEEE-rounded op in the reference's operand order.  Citations are
+// file:line in the reference repo (martingleich/RayTracingInAWeekend).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rt {
+
+// ------------------------------------------------------------------------------------------------
+// Device scene layout (HBM, all 16-byte aligned, fetched with 128-bit loads)
+// ------------------------------------------------------------------------------------------------
+// Child reference: bit31 = leaf, bits 30..29 = geometry kind, bits 28..0 = item index (= hit id).
+#define RT_REF_LEAF 0x80000000u
+#define RT_REF_KIND_SHIFT 29
+#define RT_REF_ITEM_MASK 0x1FFFFFFFu
+#define RT_NO_HIT 0xFFFFFFFFu
+
+// One internal BVH node = 64 B: the AABBs of BOTH children live in the parent ("children-in-parent"),
+// so one node visit is one 64-byte fetch (4 x LDG.128) and two independent box tests.
+//   q0 = Lmin.xyz Lmax.x | q1 = Lmax.yz Rmin.xy | q2 = Rmin.z Rmax.xyz | q3 = left, right, axis, 0
+struct __align__(16) NodeDev {
+    float4 q0, q1, q2;
+    uint4 q3;
+};
+// One primitive = 64 B intersection record, indexed by item id.
+//   sphere  : q0 = center.xyz, radius
+//   rect    : q0 = dist, r0.lo, r0.hi, r1.lo | q1 = r1.hi, bits(plane), 0, 0
+//   triangle: q0 = p0.xyz, n.x | q1 = n.yz, vt1.xy | q2 = vt1.z, d1, vt2.xy | q3 = vt2.z, d2, 0, 0
+//             n = unit(cross(dir1,dir2)), vt1 = cross(n,dir2), d1 = dot(dir1,vt1), vt2 = cross(n,dir1), d2 = dot(dir2,vt2)
+//             — the per-test constants of triangle_geometry.rs:14-29, hoisted to scene build with identical rounding.
+struct __align__(16) PrimDev {
+    float4 q0, q1, q2, q3;
+};
+// One shading record = 64 B, indexed by item id (read only for the final hit of a segment).
+//   q0 = n0.xyz n1.x | q1 = n1.yz n2.xy | q2 = n2.z uv0.xy uv1.x | q3 = uv1.y uv2.xy bits(material)
+struct __align__(16) ShadeDev {
+    float4 q0, q1, q2, q3;
+};
+struct MaterialDev {  // 16 B
+    uint32_t kind, texture;
+    float param;
+    uint32_t pad;
+};
+struct TextureDev {  // 32 B
+    uint32_t kind, width, height, pad;
+    float r, g, b;
+    uint32_t pad2;
+    const uint8_t* texels;  // RGB8, row 0 = top
+};
+
+struct CameraDev {
+    float3 position, ulc, unit_right, unit_up, scaled_right, scaled_up;
+    float lens_radius;
+};
+
+struct SceneDev {
+    const NodeDev* nodes;
+    const PrimDev* prims;
+    const ShadeDev* shade;
+    const MaterialDev* materials;
+    const TextureDev* textures;
+    uint32_t root;            // child reference of the BVH root
+    uint32_t n_items;
+    float root_min[3], root_max[3];
+    uint32_t stack_cap;       // traversal stack entries per thread
+    float margin_a, margin_b, margin_c;  // tight-cull guard band: m(t) = a + |t|*(b + c*|t|)
+    CameraDev cam;
+    uint32_t bg_is_sky;
+    float bg[3];
+    uint32_t has_light, light_plane;
+    float light_dist, light_r0lo, light_r0hi, light_r1lo, light_r1hi;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small vector helpers (component order and association exactly as src/lib/vec3.rs)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 add3(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 sub3(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 neg3(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 mul3(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 div3(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // vec3.rs:189-191
+__device__ __forceinline__ float len3(float3 a) { return sqrtf(dot3(a, a)); }
+__device__ __forceinline__ float3 with_length3(float3 a, float len) { return mul3(a, len / len3(a)); }  // vec3.rs:206-208
+__device__ __forceinline__ float3 unit3(float3 a) { return with_length3(a, 1.0f); }                      // vec3.rs:203-205
+__device__ __forceinline__ float comp3(float3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+// ------------------------------------------------------------------------------------------------
+// Aabb::hit_cond (src/lib/aabb.rs:65-78) + carried-interval bounds
+// ------------------------------------------------------------------------------------------------
+struct Slab {
+    bool ref_pass;  // the reference's per-axis-independent rule (Q1)
+    float tn;       // max_i max(t0_i, start)   — also the exact end-dependent part of the rule: reject iff end <= tn
+    float tf;       // min_i min(t1_i, end)
+};
+__device__ __forceinline__ void slab_axis(float mn, float mx, float o, float d, float& t0, float& t1) {
+    float a = (mn - o) / d;  // true IEEE division, as the reference (no precomputed reciprocal)
+    float b = (mx - o) / d;
+    bool lt = a < b;  // math.rs:35-41 minmax: NaN compares false -> (b, a)
+    t0 = lt ? a : b;
+    t1 = lt ? b : a;
+}
+__device__ __forceinline__ Slab slab_test(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float3 o,
+                                          float3 d, float start, float end) {
+    float t0x, t1x, t0y, t1y, t0z, t1z;
+    slab_axis(mnx, mxx, o.x, d.x, t0x, t1x);
+    slab_axis(mny, mxy, o.y, d.y, t0y, t1y);
+    slab_axis(mnz, mxz, o.z, d.z, t0z, t1z);
+    float nx = fmaxf(t0x, start), ny = fmaxf(t0y, start), nz = fmaxf(t0z, start);  // f32::max ignores NaN, like fmaxf
+    float fx = fminf(t1x, end), fy = fminf(t1y, end), fz = fminf(t1z, end);
+    Slab s;
+    s.ref_pass = !(fx <= nx) && !(fy <= ny) && !(fz <= nz);
+    s.tn = fmaxf(fmaxf(nx, ny), nz);
+    s.tf = fminf(fminf(fx, fy), fz);
+    return s;
+}
+__device__ __forceinline__ float cull_margin(const SceneDev& S, float t) {
+    float at = fabsf(t);
+    return S.margin_a + at * (S.margin_b + S.margin_c * at);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Primitive tests: return t (accepted iff start <= t < end, half-open like Range::contains) or NaN-free miss flag
+// ------------------------------------------------------------------------------------------------
+// SphereGeometry::hit, src/lib/hittable/sphere_geometry.rs:21-43 (t only; normal/uv are rebuilt for the final hit)
+__device__ __forceinline__ bool sphere_t(float4 s, float3 o, float3 d, float start, float end, float& t_out) {
+    float3 oc = sub3(o, f3(s.x, s.y, s.z));
+    float half_b = dot3(oc, d);
+    float c = dot3(oc, oc) - s.w * s.w;
+    float disc = half_b * half_b - c;
+    if (disc < 0.0f) return false;
+    float sqrtd = sqrtf(disc);
+    float root_small = -half_b - sqrtd;
+    if (start <= root_small && root_small < end) { t_out = root_small; return true; }
+    float root_large = -half_b + sqrtd;
+    if (start <= root_large && root_large < end) { t_out = root_large; return true; }
+    return false;
+}
+// RectGeometry::hit, src/lib/hittable/rect_geometry.rs:33-42
+__device__ __forceinline__ void rect_axes(uint32_t plane, int& p0, int& p1, int& n) {
+    if (plane == 0u) { p0 = 0; p1 = 1; n = 2; }
+    else if (plane == 1u) { p0 = 0; p1 = 2; n = 1; }
+    else { p0 = 1; p1 = 2; n = 0; }
+}
+__device__ __forceinline__ bool rect_t(uint32_t plane, float dist, float r0lo, float r0hi, float r1lo, float r1hi,
+                                       float3 o, float3 d, float start, float end, float& t_out) {
+    int p0, p1, n;
+    rect_axes(plane, p0, p1, n);
+    float t = (dist - comp3(o, n)) / comp3(d, n);
+    if (start <= t && t < end) {
+        float3 pos = add3(o, mul3(d, t));
+        float a = comp3(pos, p0), b = comp3(pos, p1);
+        if (a >= r0lo && a <= r0hi && b >= r1lo && b <= r1hi) { t_out = t; return true; }
+    }
+    return false;
+}
+// TriangleGeometry::hit, src/lib/hittable/triangle_geometry.rs:13-31 with the per-triangle constants precomputed
+__device__ __forceinline__ bool triangle_t(const PrimDev& p, float3 o, float3 d, float start, float end, float& t_out,
+                                           float& w1_out, float& w2_out) {
+    float3 p0 = f3(p.q0.x, p.q0.y, p.q0.z);
+    float3 n = f3(p.q0.w, p.q1.x, p.q1.y);
+    float denom = dot3(d, n);
+    if (fabsf(denom) > 0.0001f) {
+        float t = dot3(sub3(p0, o), n) / denom;
+        if (start <= t && t < end) {
+            float3 pos = add3(o, mul3(d, t));
+            float3 q = sub3(pos, p0);
+            float3 vt1 = f3(p.q1.z, p.q1.w, p.q2.x);
+            float w1 = dot3(q, vt1) / p.q2.y;
+            if (w1 > 0.0f && w1 < 1.0f) {
+                float3 vt2 = f3(p.q2.z, p.q2.w, p.q3.x);
+                float w2 = dot3(q, vt2) / p.q3.y;
+                float w0 = 1.0f - w1 - w2;
+                if (w2 > 0.0f && w0 > 0.0f) { t_out = t; w1_out = w1; w2_out = w2; return true; }
+            }
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ PrimDev load_prim(const PrimDev* p) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+    PrimDev r;
+    r.q0 = __ldg(q); r.q1 = __ldg(q + 1); r.q2 = __ldg(q + 2); r.q3 = __ldg(q + 3);
+    return r;
+}
+
+// Leaf test dispatch.  Returns true and shrinks `end` when the primitive is accepted.
+__device__ __forceinline__ bool leaf_test(const SceneDev& S, uint32_t ref, float3 o, float3 d, float start, float& end) {
+    uint32_t kind = (ref >> RT_REF_KIND_SHIFT) & 3u;
+    uint32_t item = ref & RT_REF_ITEM_MASK;
+    const float4* q = reinterpret_cast<const float4*>(S.prims + item);
+    float t;
+    bool hit;
+    if (kind == 0u) {
+        hit = sphere_t(__ldg(q), o, d, start, end, t);
+    } else if (kind == 2u) {
+        PrimDev p;
+        p.q0 = __ldg(q); p.q1 = __ldg(q + 1); p.q2 = __ldg(q + 2); p.q3 = __ldg(q + 3);
+        float w1, w2;
+        hit = triangle_t(p, o, d, start, end, t, w1, w2);
+    } else {
+        float4 a = __ldg(q), b = __ldg(q + 1);
+        hit = rect_t(__float_as_uint(b.y), a.x, a.y, a.z, a.w, b.x, o, d, start, end, t);
+    }
+    if (hit) end = t;
+    return hit;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BoundingVolumeHierarchy::hit (src/lib/hittable.rs:429-473) as an iterative, ordered DFS.
+//   * child order, the node test and the half-open acceptance are the reference's (Q13), so among equal-t
+//     candidates the first visited wins exactly as in the recursion;
+//   * the far child is pushed with tn; at pop the end-dependent part of hit_cond is re-evaluated exactly
+//     (reject iff end <= tn), which is what the recursion does when it reaches that child later;
+//   * TIGHT additionally culls a child when the carried slab interval is empty by more than a guard band
+//     (true-bound AABBs cannot contain an accepted hit then); TIGHT=false is the reference rule alone.
+// Stack: shared memory, [level][thread] so lanes never bank-conflict.
+// ------------------------------------------------------------------------------------------------
+struct HitRec {
+    uint32_t ref;  // child reference of the closest primitive, RT_NO_HIT if none
+    float t;
+};
+
+template <bool TIGHT>
+__device__ __forceinline__ HitRec traverse(const SceneDev& S, float3 o, float3 d, float start, float end_in,
+                                           uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride) {
+    HitRec best;
+    best.ref = RT_NO_HIT;
+    best.t = end_in;
+    float end = end_in;
+    uint32_t cur = S.root;
+    if (!(cur & RT_REF_LEAF)) {
+        Slab r = slab_test(S.root_min[0], S.root_min[1], S.root_min[2], S.root_max[0], S.root_max[1], S.root_max[2], o,
+                           d, start, end);
+        bool pass = r.ref_pass;
+        if (TIGHT) pass = pass && !(r.tn - r.tf > cull_margin(S, r.tn));
+        if (!pass) return best;
+    }
+    uint32_t sp = 0;
+    for (;;) {
+        if (cur & RT_REF_LEAF) {
+            if (leaf_test(S, cur, o, d, start, end)) { best.ref = cur; best.t = end; }
+        } else {
+            const float4* q = reinterpret_cast<const float4*>(S.nodes + cur);
+            float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+            uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));
+            Slab sl = slab_test(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, d, start, end);
+            Slab sr = slab_test(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, d, start, end);
+            bool left_first = comp3(d, (int)q3.z) > 0.0f;  // hittable.rs:441-445
+            uint32_t c1 = left_first ? q3.x : q3.y, c2 = left_first ? q3.y : q3.x;
+            Slab s1 = left_first ? sl : sr, s2 = left_first ? sr : sl;
+            // leaves are never box-tested by the reference (hittable.rs:436-437); internal children get hit_cond
+            bool p1 = (c1 & RT_REF_LEAF) ? true : s1.ref_pass;
+            bool p2 = (c2 & RT_REF_LEAF) ? true : s2.ref_pass;
+            if (TIGHT) {
+                p1 = p1 && !(s1.tn - s1.tf > cull_margin(S, s1.tn));
+                p2 = p2 && !(s2.tn - s2.tf > cull_margin(S, s2.tn));
+            }
+            if (p1) {
+                if (p2) {
+                    stk_ref[sp * stk_stride] = c2;
+                    stk_tn[sp * stk_stride] = s2.tn;
+                    ++sp;
+                }
+                cur = c1;
+                continue;
+            }
+            if (p2) { cur = c2; continue; }
+        }
+        // pop
+        for (;;) {
+            if (sp == 0) return best;
+            --sp;
+            cur = stk_ref[sp * stk_stride];
+            float tn = stk_tn[sp * stk_stride];
+            if (cur & RT_REF_LEAF) {
+                if (TIGHT && (tn - end > cull_margin(S, tn))) continue;
+                break;
+            }
+            if (end <= tn) continue;  // hit_cond's end-dependent part with the shrunken range
+            break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// HitInteraction for the final hit of a segment (src/lib/hittable.rs:24-54 + the three geometry files)
+// ------------------------------------------------------------------------------------------------
+struct Interaction {
+    float3 position, normal;
+    float u, v;
+    bool front_face;
+    uint32_t material;
+};
+// Dir3::to_radian -> sphere uv  (vec3.rs:241-249, sphere_geometry.rs:56-59)
+__device__ __forceinline__ void sphere_uv(float3 n, float& u, float& v) {
+    float theta = acosf(n.y);
+    float phi = atan2f(-n.z, n.x) + 3.14159265358979323846f;
+    u = phi / 6.28318530717958647692f;
+    v = theta / 3.14159265358979323846f;
+}
+__device__ __forceinline__ Interaction make_interaction(const SceneDev& S, uint32_t ref, float t, float3 o, float3 d,
+                                                        bool want_uv) {
+    Interaction hi;
+    uint32_t kind = (ref >> RT_REF_KIND_SHIFT) & 3u;
+    uint32_t item = ref & RT_REF_ITEM_MASK;
+    const float4* q = reinterpret_cast<const float4*>(S.prims + item);
+    const float4* sq = reinterpret_cast<const float4*>(S.shade + item);
+    float3 pos = add3(o, mul3(d, t));  // Ray::at, ray.rs:20-22
+    float3 sn;
+    hi.u = 0.0f; hi.v = 0.0f;
+    float4 s3 = __ldg(sq + 3);
+    hi.material = __float_as_uint(s3.w);
+    if (kind == 0u) {
+        float4 s = __ldg(q);
+        sn = div3(sub3(pos, f3(s.x, s.y, s.z)), s.w);  // sphere_geometry.rs:44
+        if (want_uv) sphere_uv(sn, hi.u, hi.v);
+    } else if (kind == 2u) {
+        PrimDev p;
+        p.q0 = __ldg(q); p.q1 = __ldg(q + 1); p.q2 = __ldg(q + 2); p.q3 = __ldg(q + 3);
+        float3 p0 = f3(p.q0.x, p.q0.y, p.q0.z);
+        float3 qq = sub3(pos, p0);
+        float w1 = dot3(qq, f3(p.q1.z, p.q1.w, p.q2.x)) / p.q2.y;
+        float w2 = dot3(qq, f3(p.q2.z, p.q2.w, p.q3.x)) / p.q3.y;
+        float w0 = 1.0f - w1 - w2;
+        float4 s0 = __ldg(sq), s1 = __ldg(sq + 1), s2 = __ldg(sq + 2);
+        // math::interpolate: v0*w0 + v1*w1 + v2*w2, NOT re-normalised (Q8)   triangle_geometry.rs:31-32
+        sn = f3(s0.x * w0 + s0.w * w1 + s1.z * w2, s0.y * w0 + s1.x * w1 + s1.w * w2, s0.z * w0 + s1.y * w1 + s2.x * w2);
+        hi.u = s2.y * w0 + s2.w * w1 + s3.y * w2;
+        hi.v = s2.z * w0 + s3.x * w1 + s3.z * w2;
+    } else {
+        float4 a = __ldg(q), b = __ldg(q + 1);
+        int p0, p1, n;
+        rect_axes(__float_as_uint(b.y), p0, p1, n);
+        // Q5: uv.y divides by (r0.hi - r1.lo)   rect_geometry.rs:43-46
+        hi.u = (comp3(pos, p0) - a.y) / (a.z - a.y);
+        hi.v = (comp3(pos, p1) - a.w) / (a.z - a.w);
+        sn = f3(n == 0 ? -1.0f : 0.0f, n == 1 ? -1.0f : 0.0f, n == 2 ? -1.0f : 0.0f);
+    }
+    hi.front_face = dot3(sn, d) < 0.0f;  // hittable.rs:41
+    hi.normal = hi.front_face ? sn : neg3(sn);
+    hi.position = pos;
+    return hi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Counter-based RNG + inversion samplers (must stay bit-identical to oracle/oracle_rng.hpp REPLAY mode)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
+                                               uint32_t c3) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float u01(uint32_t v) { return (float)(v >> 8) * 5.9604644775390625e-8f; }
+
+__device__ __forceinline__ void sincos_2pi(float u, float& s_out, float& c_out) {
+    float x = u * 4.0f;
+    int q = (int)x;
+    float f = x - (float)q;
+    float a = f * 1.57079632679489661923f;
+    float a2 = a * a;
+    float s = a * (1.0f + a2 * (-1.6666667163e-1f + a2 * (8.3333337680e-3f + a2 * (-1.9841270114e-4f +
+              a2 * (2.7557314297e-6f + a2 * (-2.5052107943e-8f))))));
+    float c = 1.0f + a2 * (-0.5f + a2 * (4.1666667908e-2f + a2 * (-1.3888889225e-3f + a2 * (2.4801587642e-5f +
+              a2 * (-2.7557319224e-7f + a2 * (2.0876755880e-9f))))));
+    switch (q & 3) {
+        case 0: c_out = c;  s_out = s;  break;
+        case 1: c_out = -s; s_out = c;  break;
+        case 2: c_out = -c; s_out = -s; break;
+        default: c_out = s; s_out = -c; break;
+    }
+}
+__device__ __forceinline__ float cbrt_unit(float u) {
+    if (!(u > 0.0f)) return 0.0f;
+    float y = __uint_as_float(__float_as_uint(u) / 3u + 709921077u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y = (2.0f * y + u / (y * y)) * 0.333333343267f;
+    return y;
+}
+__device__ __forceinline__ float3 sample_unit_sphere(float ua, float ub) {  // stands in for rand_distr::UnitSphere
+    float z = 1.0f - 2.0f * ua;
+    float r2 = 1.0f - z * z;
+    float r = sqrtf(r2 > 0.0f ? r2 : 0.0f);
+    float s, c;
+    sincos_2pi(ub, s, c);
+    return f3(r * c, r * s, z);
+}
+
+// Camera::ray (src/lib/camera.rs:175-200) for the sample whose Philox block 0 is `r`
+__device__ __forceinline__ void camera_ray(const CameraDev& C, float px, float py, uint4 r, float3& o, float3& d) {
+    float3 offset = f3(0.0f, 0.0f, 0.0f);
+    if (C.lens_radius > 0.0f) {
+        float rad = sqrtf(u01(r.z));  // stands in for rand_distr::UnitDisc
+        float s, c;
+        sincos_2pi(u01(r.w), s, c);
+        float rdx = rad * c, rdy = rad * s;
+        offset = mul3(add3(mul3(C.unit_right, rdx), mul3(C.unit_up, rdy)), C.lens_radius);
+    }
+    o = add3(C.position, offset);
+    d = unit3(sub3(sub3(add3(C.ulc, mul3(C.scaled_right, px)), mul3(C.scaled_up, py)), offset));
+}
+
+// Texture::sample (src/lib/texture.rs:23-43)
+__device__ __forceinline__ uint32_t sat_u32(float v) {  // Rust `as u32` (saturating, NaN -> 0)
+    if (!(v == v)) return 0u;
+    if (v <= 0.0f) return 0u;
+    if (v >= 4294967296.0f) return 0xFFFFFFFFu;
+    return (uint32_t)v;
+}
+__device__ __forceinline__ float3 texture_sample(const SceneDev& S, uint32_t tex, float u, float v) {
+    TextureDev t = S.textures[tex];
+    if (t.kind == 0u) return f3(t.r, t.g, t.b);
+    uint32_t pu = min(sat_u32(u * (float)t.width), t.width - 1u);
+    uint32_t pv = min(sat_u32(v * (float)t.height), t.height - 1u);
+    const uint8_t* px = t.texels + 3ull * ((size_t)pv * t.width + pu);
+    return f3((float)px[0] / 255.0f, (float)px[1] / 255.0f, (float)px[2] / 255.0f);  // color.rs:29-35
+}
+
+}  // namespace rt

@@ -1,0 +1,380 @@
+// rt_kernels.cuh — the wavefront path tracer kernels (sm_100a).
+//
+//   k_generate : Size2i::iterf + pixel jitter + Camera::ray   (size2i.rs:38-56, rendering.rs:174-175, camera.rs:175-200)
+//   k_extend   : Scene::hit -> BVH closest hit                 (hittable.rs:429-473)          [dominant kernel]
+//   k_shade    : one iteration of ray_color's loop + Material::scatter + regeneration + compaction
+//                                                             (rendering.rs:19-92, material.rs, texture.rs, background_color.rs)
+//   k_finalize : per-pixel mean + merge_planes                 (rendering.rs:178-179, 239-252)
+//   k_trace    : Scene::hit on caller rays (validation entry)
+#pragma once
+#include "rt_device.cuh"
+
+namespace rt {
+
+struct Counters {
+    uint32_t n[2];          // live paths in queue 0 / 1
+    uint32_t cursor_extend; // dynamic work fetch
+    uint32_t pad;
+    unsigned long long rays;   // closest-hit queries so far
+    unsigned long long paths;  // camera samples generated so far
+};
+
+struct RenderDev {
+    float4* A[2];   // origin.xyz, bits(slot)            slot = local_lane * npix + pixel
+    float4* B[2];   // direction.xyz, bits(sample k within the lane)
+    float4* C[2];   // throughput.rgb, primary direction.y (Q6)
+    int32_t* D[2];  // remaining depth
+    uint2* hits;    // (child ref of closest primitive | RT_NO_HIT, bits(t)) per queue position
+    float4* acc;    // [n_local_lanes * npix] running per-lane sums (exclusive owner: the slot's single live path)
+    Counters* ctr;
+    uint32_t npix, width, height;
+    int32_t max_depth;
+    uint32_t n_tasks;        // T' = lanes that got >= 1 sample (split_work_tasks)
+    uint32_t lane_first, lane_stride, n_local_lanes;
+    uint32_t spp_whole, spp_rem;  // lane id gets spp_whole + (id < spp_rem)
+    uint32_t seed0, seed1;
+    float sx, sy;            // 1/(w-1), 1/(h-1)   (size2i.rs:21-22; also the jitter scale, rendering.rs:132-138)
+    uint32_t mode;
+};
+
+__device__ __forceinline__ uint32_t lane_samples(const RenderDev& R, uint32_t lane_id) {
+    return R.spp_whole + (lane_id < R.spp_rem ? 1u : 0u);
+}
+
+// New camera path for (pixel, lane, sample k).
+__device__ __forceinline__ void generate_path(const SceneDev& S, const RenderDev& R, uint32_t pixel, uint32_t lane_id,
+                                              uint32_t k, float3& o, float3& d) {
+    uint32_t x = pixel % R.width, y = pixel / R.width;
+    uint32_t s_global = k * R.n_tasks + lane_id;
+    uint4 r = philox4x32_10(R.seed0, R.seed1, pixel, s_global, 0u, 0u);
+    float fx = (float)x * R.sx, fy = (float)y * R.sy;          // size2i.rs:52-55
+    float px = fx + (u01(r.x) * R.sx + 0.0f);                   // Uniform<Vec2f>: x then y (vec2.rs:77-82)
+    float py = fy + (u01(r.y) * R.sy + 0.0f);
+    camera_ray(S.cam, px, py, r, o, d);
+}
+
+__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R) {
+    uint32_t n_slots = R.n_local_lanes * R.npix;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += gridDim.x * blockDim.x) {
+        uint32_t pixel = slot % R.npix, local_lane = slot / R.npix;
+        uint32_t lane_id = R.lane_first + local_lane * R.lane_stride;
+        float3 o, d;
+        generate_path(S, R, pixel, lane_id, 0u, o, d);
+        R.A[0][slot] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
+        R.B[0][slot] = make_float4(d.x, d.y, d.z, __uint_as_float(0u));
+        R.C[0][slot] = make_float4(1.0f, 1.0f, 1.0f, d.y);
+        R.D[0][slot] = R.max_depth;
+        R.acc[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        R.ctr->n[0] = n_slots;
+        R.ctr->n[1] = 0;
+        R.ctr->cursor_extend = 0;
+        R.ctr->rays = 0;
+        R.ctr->paths = n_slots;
+    }
+}
+
+// Closest hit for every live path of queue `q`.  Persistent warps pull 32 rays at a time.
+template <bool TIGHT>
+__global__ void __launch_bounds__(128) k_extend(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* stk_ref = smem + threadIdx.x;
+    float* stk_tn = reinterpret_cast<float*>(smem + S.stack_cap * blockDim.x) + threadIdx.x;
+    const uint32_t n = R.ctr->n[q];
+    const uint32_t lane = threadIdx.x & 31u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) R.ctr->n[q ^ 1] = 0;  // next queue starts empty (nobody touches it during extend)
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&R.ctr->cursor_extend, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        if (i < n) {
+            float4 a = R.A[q][i], b = R.B[q][i];
+            HitRec h = traverse<TIGHT>(S, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), 0.001f, __int_as_float(0x7f800000),
+                                       stk_ref, stk_tn, blockDim.x);
+            R.hits[i] = make_uint2(h.ref, __float_as_uint(h.t));
+        }
+    }
+}
+
+// One bounce of ray_color for every live path of queue `q`; survivors (and regenerated paths) are compacted
+// into queue q^1 with one warp-aggregated atomic per warp.
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
+    const uint32_t n = R.ctr->n[q];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        R.ctr->cursor_extend = 0;
+        R.ctr->rays += n;
+    }
+    uint32_t new_paths = 0;
+    for (uint32_t base = warp_global * 32u; base < n; base += n_warps * 32u) {
+        uint32_t i = base + lane;
+        bool live = false;
+        float3 o = f3(0, 0, 0), d = f3(0, 0, 1), thr = f3(1, 1, 1);
+        float dy0 = 0.0f;
+        uint32_t slot = 0, k = 0;
+        int32_t depth = 0;
+        if (i < n) {
+            float4 a = R.A[q][i], b = R.B[q][i], c = R.C[q][i];
+            depth = R.D[q][i];
+            uint2 h = R.hits[i];
+            o = f3(a.x, a.y, a.z); d = f3(b.x, b.y, b.z); thr = f3(c.x, c.y, c.z);
+            dy0 = c.w;
+            slot = __float_as_uint(a.w);
+            k = __float_as_uint(b.w);
+            const uint32_t pixel = slot % R.npix, local_lane = slot / R.npix;
+            const uint32_t lane_id = R.lane_first + local_lane * R.lane_stride;
+            const float t = __uint_as_float(h.y);
+            float3 radiance = f3(0.0f, 0.0f, 0.0f);
+            bool terminated = true;
+            // background_color.rs:9-19, sampled with the PRIMARY ray (Q6)
+            float3 bgc;
+            if (S.bg_is_sky) {
+                float tt = 0.5f * (dy0 + 1.0f);
+                float omt = 1.0f - tt;
+                bgc = f3(1.0f * omt + 0.5f * tt, 1.0f * omt + 0.7f * tt, 1.0f * omt + 1.0f * tt);
+            } else {
+                bgc = f3(S.bg[0], S.bg[1], S.bg[2]);
+            }
+            if (R.mode == 1u) {  // RenderMode::Normals (rendering.rs:108-116)
+                if (h.x != RT_NO_HIT) {
+                    Interaction hi = make_interaction(S, h.x, t, o, d, false);
+                    radiance = f3((hi.normal.x + 1.0f) * 0.5f, (hi.normal.y + 1.0f) * 0.5f, (hi.normal.z + 1.0f) * 0.5f);
+                } else {
+                    radiance = bgc;
+                }
+            } else if (h.x == RT_NO_HIT) {
+                radiance = f3(0.0f + thr.x * bgc.x, 0.0f + thr.y * bgc.y, 0.0f + thr.z * bgc.z);  // rendering.rs:66-68
+            } else if (depth <= 1) {
+                radiance = f3(0.0f, 0.0f, 0.0f);  // Q7, rendering.rs:26-27
+            } else {
+                Interaction hi = make_interaction(S, h.x, t, o, d, false);
+                const MaterialDev m = S.materials[hi.material];
+                const uint32_t s_global = k * R.n_tasks + lane_id;
+                const uint4 rnd = philox4x32_10(R.seed0, R.seed1, pixel, s_global, 1u + (uint32_t)(R.max_depth - depth), 0u);
+                float3 att = f3(1.0f, 1.0f, 1.0f), ndir = f3(0, 0, 1);
+                float prob = 1.0f;
+                bool scattered = false;
+                float3 emitted = f3(0.0f, 0.0f, 0.0f);
+                // texture coordinates are only needed by image textures: sphere uv costs acos+atan2
+                float tu = hi.u, tv = hi.v;
+                if (m.kind != 2u && S.textures[m.texture].kind == 1u && ((h.x >> RT_REF_KIND_SHIFT) & 3u) == 0u) {
+                    float4 sph = __ldg(reinterpret_cast<const float4*>(S.prims + (h.x & RT_REF_ITEM_MASK)));
+                    float3 sn = div3(sub3(hi.position, f3(sph.x, sph.y, sph.z)), sph.w);
+                    sphere_uv(sn, tu, tv);
+                }
+                if (m.kind == 0u) {  // Lambert, material.rs:59-63 + rendering.rs:35-51
+                    att = texture_sample(S, m.texture, tu, tv);
+                    const float3 nrm = hi.normal;
+                    const float PI = 3.14159265358979323846f;
+                    float pdf;
+                    if (S.has_light) {  // sample_final_scattering_distribution, rendering.rs:73-86
+                        int p0, p1, pn;
+                        rect_axes(S.light_plane, p0, p1, pn);
+                        if (u01(rnd.x) < 0.5f) {  // gen_bool(0.5) -> RectGeometry::generate, rect_geometry.rs:60-67
+                            float e0 = S.light_r0lo + u01(rnd.y) * (S.light_r0hi - S.light_r0lo);
+                            float e1 = S.light_r1lo + u01(rnd.z) * (S.light_r1hi - S.light_r1lo);
+                            float ex = p0 == 0 ? e0 : (p1 == 0 ? e1 : S.light_dist);
+                            float ey = p0 == 1 ? e0 : (p1 == 1 ? e1 : S.light_dist);
+                            float ez = p0 == 2 ? e0 : (p1 == 2 ? e1 : S.light_dist);
+                            ndir = unit3(sub3(f3(ex, ey, ez), hi.position));
+                        } else {
+                            float3 sph = sample_unit_sphere(u01(rnd.y), u01(rnd.z));
+                            float3 v = add3(nrm, sph);
+                            float l2 = dot3(v, v);
+                            ndir = l2 > 1e-8f ? div3(v, sqrtf(l2)) : nrm;  // unit_or_else, vec3.rs:223-230
+                        }
+                        // RectGeometry::value, rect_geometry.rs:68-85
+                        float lv = 0.0f, lt;
+                        if (rect_t(S.light_plane, S.light_dist, S.light_r0lo, S.light_r0hi, S.light_r1lo, S.light_r1hi,
+                                   hi.position, ndir, 0.001f, __int_as_float(0x7f800000), lt)) {
+                            float area = (S.light_r0hi - S.light_r0lo) * (S.light_r1hi - S.light_r1lo);
+                            float cosine = fabsf(comp3(ndir, pn));
+                            lv = (lt * lt) / (cosine * area);
+                        }
+                        pdf = 0.5f * lv + 0.5f * (fmaxf(dot3(nrm, ndir), 0.0f) / PI);
+                    } else {
+                        float3 sph = sample_unit_sphere(u01(rnd.x), u01(rnd.y));
+                        float3 v = add3(nrm, sph);
+                        float l2 = dot3(v, v);
+                        ndir = l2 > 1e-8f ? div3(v, sqrtf(l2)) : nrm;
+                        pdf = fmaxf(dot3(nrm, ndir), 0.0f) / PI;
+                    }
+                    float scattering_pdf = fmaxf(dot3(nrm, ndir), 0.0f) / PI;  // material.rs:123-127
+                    prob = scattering_pdf / pdf;                                // Q9: 0/0 -> NaN
+                    scattered = true;
+                } else if (m.kind == 1u) {  // Metal, material.rs:65-79
+                    float3 fuzz_dir = f3(0.0f, 0.0f, 0.0f);
+                    if (m.param > 0.0f) {
+                        float3 sph = sample_unit_sphere(u01(rnd.x), u01(rnd.y));
+                        fuzz_dir = mul3(mul3(sph, cbrt_unit(u01(rnd.z))), m.param);
+                    }
+                    float3 refl = sub3(d, mul3(hi.normal, 2.0f * dot3(d, hi.normal)));  // reflect, vec3.rs:232-234
+                    float3 dir = add3(refl, fuzz_dir);
+                    if (dot3(dir, hi.normal) > 0.0f) {
+                        ndir = unit3(dir);
+                        att = texture_sample(S, m.texture, tu, tv);
+                        scattered = true;
+                    }
+                } else if (m.kind == 2u) {  // Dielectric, material.rs:80-105
+                    float ratio = hi.front_face ? 1.0f / m.param : m.param;
+                    float cos_theta = fminf(dot3(neg3(d), hi.normal), 1.0f);
+                    float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+                    bool cannot_refract = ratio * sin_theta > 1.0f;
+                    bool do_reflect = cannot_refract;
+                    if (!do_reflect) {
+                        float r0 = (1.0f - ratio) / (1.0f + ratio);
+                        float rs = r0 * r0;
+                        float x = 1.0f - cos_theta;
+                        float x2 = x * x;
+                        float x4 = x2 * x2;
+                        float refl = rs + (1.0f - rs) * (x * x4);  // powi(5)
+                        do_reflect = refl > u01(rnd.x);
+                    }
+                    float3 dir;
+                    if (do_reflect) {
+                        dir = sub3(d, mul3(hi.normal, 2.0f * dot3(d, hi.normal)));
+                    } else {  // refract, vec3.rs:235-240
+                        float ct = fminf(dot3(neg3(d), hi.normal), 1.0f);
+                        float3 perp = mul3(add3(d, mul3(hi.normal, ct)), ratio);
+                        float3 par = mul3(hi.normal, -sqrtf(fabsf(1.0f - dot3(perp, perp))));
+                        dir = add3(perp, par);
+                    }
+                    ndir = unit3(dir);
+                    scattered = true;
+                } else {  // DiffuseLight: never scatters, emits from both faces (Q14), material.rs:132-137
+                    emitted = texture_sample(S, m.texture, tu, tv);
+                }
+                if (scattered) {
+                    // rendering.rs:54-61.  accum_emitted stays 0 unless the throughput is non-finite, in which case
+                    // it turns NaN; folding that into the throughput (inf -> NaN) keeps every outcome identical.
+                    float3 nt = f3((thr.x * att.x) * prob, (thr.y * att.y) * prob, (thr.z * att.z) * prob);
+                    const float qnan = __int_as_float(0x7fc00000);
+                    if (isinf(thr.x)) nt.x = qnan;
+                    if (isinf(thr.y)) nt.y = qnan;
+                    if (isinf(thr.z)) nt.z = qnan;
+                    thr = nt;
+                    o = hi.position;
+                    d = ndir;
+                    depth -= 1;
+                    terminated = false;
+                    live = true;
+                } else {
+                    radiance = f3(0.0f + thr.x * emitted.x, 0.0f + thr.y * emitted.y, 0.0f + thr.z * emitted.z);  // :62-64
+                }
+            }
+            if (terminated) {
+                float4 s = R.acc[slot];  // sequential per-pixel sum in sample order (rendering.rs:172-178)
+                s.x += radiance.x; s.y += radiance.y; s.z += radiance.z;
+                R.acc[slot] = s;
+                if (k + 1u < lane_samples(R, lane_id)) {  // regenerate in place: next sample of this (pixel, lane)
+                    k += 1u;
+                    generate_path(S, R, pixel, lane_id, k, o, d);
+                    thr = f3(1.0f, 1.0f, 1.0f);
+                    dy0 = d.y;
+                    depth = R.max_depth;
+                    live = true;
+                    new_paths += 1u;
+                }
+            }
+        }
+        // warp-ballot compaction into the other queue
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, live);
+        if (mask) {
+            uint32_t pos = 0;
+            if (lane == 0) pos = atomicAdd(&R.ctr->n[q ^ 1], (uint32_t)__popc(mask));
+            pos = __shfl_sync(0xFFFFFFFFu, pos, 0) + __popc(mask & ((1u << lane) - 1u));
+            if (live) {
+                R.A[q ^ 1][pos] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
+                R.B[q ^ 1][pos] = make_float4(d.x, d.y, d.z, __uint_as_float(k));
+                R.C[q ^ 1][pos] = make_float4(thr.x, thr.y, thr.z, dy0);
+                R.D[q ^ 1][pos] = depth;
+            }
+        }
+    }
+    // one atomic per warp for the generated-paths counter
+    for (int off = 16; off > 0; off >>= 1) new_paths += __shfl_xor_sync(0xFFFFFFFFu, new_paths, off);
+    if (lane == 0 && new_paths) atomicAdd(&R.ctr->paths, (unsigned long long)new_paths);
+}
+
+// film[p] = sum over this rank's lanes, in merge_planes order (last plane first), of lane_sum / lane_samples; times `scale`.
+__global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ RenderDev R, float* __restrict__ out_rgb, float scale,
+                                                  int apply_scale) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < R.npix; p += gridDim.x * blockDim.x) {
+        float3 sum = f3(0, 0, 0);
+        bool first = true;
+        // order: lane T'-1 (if local), then ascending
+        for (uint32_t step = 0; step <= R.n_local_lanes; ++step) {
+            uint32_t local;
+            if (step == 0) {
+                uint32_t last_id = R.lane_first + (R.n_local_lanes - 1u) * R.lane_stride;
+                if (last_id != R.n_tasks - 1u) continue;
+                local = R.n_local_lanes - 1u;
+            } else {
+                local = step - 1u;
+                uint32_t id = R.lane_first + local * R.lane_stride;
+                if (id == R.n_tasks - 1u) continue;
+            }
+            uint32_t lane_id = R.lane_first + local * R.lane_stride;
+            float ns = (float)lane_samples(R, lane_id);
+            float4 a = R.acc[(size_t)local * R.npix + p];
+            float3 plane = f3(a.x / ns, a.y / ns, a.z / ns);  // `.sum::<Color>() / real_samples as f32`
+            if (first) { sum = plane; first = false; }
+            else sum = add3(sum, plane);
+        }
+        if (apply_scale) sum = mul3(sum, scale);
+        out_rgb[3ull * p + 0] = sum.x;
+        out_rgb[3ull * p + 1] = sum.y;
+        out_rgb[3ull * p + 2] = sum.z;
+    }
+}
+
+// Scene::hit on caller rays.
+template <bool TIGHT>
+__global__ void __launch_bounds__(128) k_trace(const __grid_constant__ SceneDev S, const float* __restrict__ org,
+                                               const float* __restrict__ dir, uint64_t n, float t_min, float t_max,
+                                               uint32_t* __restrict__ hit_id, float* __restrict__ t_out,
+                                               float* __restrict__ normal, uint8_t* __restrict__ front_face,
+                                               float* __restrict__ uv) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* stk_ref = smem + threadIdx.x;
+    float* stk_tn = reinterpret_cast<float*>(smem + S.stack_cap * blockDim.x) + threadIdx.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]);
+        float3 d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        HitRec h = traverse<TIGHT>(S, o, d, t_min, t_max, stk_ref, stk_tn, blockDim.x);
+        if (h.ref != RT_NO_HIT) {
+            Interaction hi = make_interaction(S, h.ref, h.t, o, d, true);
+            if (hit_id) hit_id[i] = h.ref & RT_REF_ITEM_MASK;
+            if (t_out) t_out[i] = h.t;
+            if (normal) { normal[3 * i] = hi.normal.x; normal[3 * i + 1] = hi.normal.y; normal[3 * i + 2] = hi.normal.z; }
+            if (front_face) front_face[i] = hi.front_face ? 1 : 0;
+            if (uv) { uv[2 * i] = hi.u; uv[2 * i + 1] = hi.v; }
+        } else {
+            if (hit_id) hit_id[i] = 0xFFFFFFFFu;
+            if (t_out) t_out[i] = __int_as_float(0x7f800000);
+            if (normal) { normal[3 * i] = 0.0f; normal[3 * i + 1] = 0.0f; normal[3 * i + 2] = 0.0f; }
+            if (front_face) front_face[i] = 0;
+            if (uv) { uv[2 * i] = 0.0f; uv[2 * i + 1] = 0.0f; }
+        }
+    }
+}
+
+__global__ void k_scale(float* __restrict__ x, uint64_t n, float m) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) x[i] = x[i] * m;
+}
+
+// Color::to_rgb8_gamma2 (color.rs:43-48): u8(clamp(0, 255, sqrt(c) * 256)), NaN -> 0
+__global__ void k_gamma2(const float* __restrict__ rgb, uint64_t n, uint8_t* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        float v = sqrtf(rgb[i]) * 256.0f;
+        float c = v > 255.0f ? 255.0f : (v < 0.0f ? 0.0f : v);  // math::clamp, math.rs:18-27 (NaN falls through)
+        out[i] = (c == c) ? (uint8_t)c : (uint8_t)0;
+    }
+}
+
+}  // namespace rt
