@@ -141,6 +141,8 @@ typedef struct RtStats {
     double render_ms;        /* device time of the render loop (CUDA events), excluding upload/download */
     double extend_ms;        /* device time spent in the extend (closest-hit) kernel, when profiling is on */
     double shade_ms;
+    uint64_t node_visits;    /* BVH node fetches (64 B each) — only with rt_set_option("count", 1) */
+    uint64_t prim_tests;     /* primitive intersection tests    — only with rt_set_option("count", 1) */
 } RtStats;
 
 typedef struct RtScene RtScene;

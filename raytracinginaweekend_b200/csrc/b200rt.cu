@@ -23,6 +23,7 @@ namespace {
 
 thread_local std::string g_err;
 int g_opt_traversal = 1;      // 0 = reference node test only, 1 = + tight carried-interval cull
+int g_opt_count = 0;        // 1 = COUNT kernel variant (node visits / primitive tests per ray)
 int g_opt_profile = 0;        // 1 = time extend / shade separately with events (adds syncs)
 int g_opt_check_every = 8;    // host polls the live-path count every N iterations
 int g_opt_blocks_per_sm = 0;  // 0 = from occupancy query
@@ -419,8 +420,9 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     const size_t esmem = stack_smem_bytes(sc, eblock);
     int egrid = 0, sgrid = 0;
     const bool tight = g_opt_traversal != 0;
-    if (tight) rc = persistent_grid(sc, k_extend<true>, eblock, esmem, &egrid);
-    else rc = persistent_grid(sc, k_extend<false>, eblock, esmem, &egrid);
+    void (*ext)(SceneDev, RenderDev, int) =
+        g_opt_count ? (tight ? k_extend<true, true> : k_extend<false, true>) : (tight ? k_extend<true, false> : k_extend<false, false>);
+    rc = persistent_grid(sc, ext, eblock, esmem, &egrid);
     if (rc) return rc;
     rc = persistent_grid(sc, k_shade, 128, 0, &sgrid);
     if (rc) return rc;
@@ -444,8 +446,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     while (!done) {
         for (int it = 0; it < g_opt_check_every; ++it) {
             if (g_opt_profile) CU(cudaEventRecord(eva, stream));
-            if (tight) k_extend<true><<<egrid, eblock, esmem, stream>>>(sc.dev, R, q);
-            else k_extend<false><<<egrid, eblock, esmem, stream>>>(sc.dev, R, q);
+            ext<<<egrid, eblock, esmem, stream>>>(sc.dev, R, q);
             if (g_opt_profile) {
                 CU(cudaEventRecord(evb, stream));
                 CU(cudaEventSynchronize(evb));
@@ -490,6 +491,8 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
         stats->render_ms = ms;
         stats->extend_ms = extend_ms;
         stats->shade_ms = shade_ms;
+        stats->node_visits = sc.h_ctr->node_visits;
+        stats->prim_tests = sc.h_ctr->prim_tests;
     }
     return RT_OK;
 }
@@ -511,6 +514,7 @@ int rt_set_option(const char* key, int64_t value) {
     std::string k(key);
     if (k == "traversal") g_opt_traversal = (int)value;
     else if (k == "profile") g_opt_profile = (int)value;
+    else if (k == "count") g_opt_count = (int)value;
     else if (k == "check_every") g_opt_check_every = std::max<int>(1, (int)value);
     else if (k == "blocks_per_sm") g_opt_blocks_per_sm = (int)value;
     else return fail(RT_EINVAL, "unknown option " + k);

@@ -226,9 +226,13 @@ struct HitRec {
     float t;
 };
 
-template <bool TIGHT>
+struct TravCount {
+    uint32_t nodes, prims;  // internal-node visits (64 B fetches), primitive tests
+};
+template <bool TIGHT, bool COUNT = false>
 __device__ __forceinline__ HitRec traverse(const SceneDev& S, float3 o, float3 d, float start, float end_in,
-                                           uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride) {
+                                           uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride,
+                                           TravCount* cnt = nullptr) {
     HitRec best;
     best.ref = RT_NO_HIT;
     best.t = end_in;
@@ -244,8 +248,10 @@ __device__ __forceinline__ HitRec traverse(const SceneDev& S, float3 o, float3 d
     uint32_t sp = 0;
     for (;;) {
         if (cur & RT_REF_LEAF) {
+            if (COUNT) cnt->prims++;
             if (leaf_test(S, cur, o, d, start, end)) { best.ref = cur; best.t = end; }
         } else {
+            if (COUNT) cnt->nodes++;
             const float4* q = reinterpret_cast<const float4*>(S.nodes + cur);
             float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
             uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));

@@ -17,6 +17,7 @@ struct Counters {
     uint32_t pad;
     unsigned long long rays;   // closest-hit queries so far
     unsigned long long paths;  // camera samples generated so far
+    unsigned long long node_visits, prim_tests;  // only maintained by the COUNT kernel variant
 };
 
 struct RenderDev {
@@ -72,11 +73,13 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
         R.ctr->cursor_extend = 0;
         R.ctr->rays = 0;
         R.ctr->paths = n_slots;
+        R.ctr->node_visits = 0;
+        R.ctr->prim_tests = 0;
     }
 }
 
 // Closest hit for every live path of queue `q`.  Persistent warps pull 32 rays at a time.
-template <bool TIGHT>
+template <bool TIGHT, bool COUNT>
 __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
     extern __shared__ uint32_t smem[];
     uint32_t* stk_ref = smem + threadIdx.x;
@@ -84,6 +87,8 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ SceneDev
     const uint32_t n = R.ctr->n[q];
     const uint32_t lane = threadIdx.x & 31u;
     if (blockIdx.x == 0 && threadIdx.x == 0) R.ctr->n[q ^ 1] = 0;  // next queue starts empty (nobody touches it during extend)
+    TravCount tc;
+    tc.nodes = 0; tc.prims = 0;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&R.ctr->cursor_extend, 32u);
@@ -92,9 +97,19 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ SceneDev
         uint32_t i = base + lane;
         if (i < n) {
             float4 a = R.A[q][i], b = R.B[q][i];
-            HitRec h = traverse<TIGHT>(S, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), 0.001f, __int_as_float(0x7f800000),
-                                       stk_ref, stk_tn, blockDim.x);
+            HitRec h = traverse<TIGHT, COUNT>(S, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), 0.001f, __int_as_float(0x7f800000),
+                                              stk_ref, stk_tn, blockDim.x, &tc);
             R.hits[i] = make_uint2(h.ref, __float_as_uint(h.t));
+        }
+    }
+    if (COUNT) {
+        for (int off = 16; off > 0; off >>= 1) {
+            tc.nodes += __shfl_xor_sync(0xFFFFFFFFu, tc.nodes, off);
+            tc.prims += __shfl_xor_sync(0xFFFFFFFFu, tc.prims, off);
+        }
+        if (lane == 0) {
+            atomicAdd(&R.ctr->node_visits, (unsigned long long)tc.nodes);
+            atomicAdd(&R.ctr->prim_tests, (unsigned long long)tc.prims);
         }
     }
 }
