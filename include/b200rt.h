@@ -143,6 +143,7 @@ typedef struct RtStats {
     double shade_ms;
     uint64_t node_visits;    /* BVH node fetches (64 B each) — only with rt_set_option("count", 1) */
     uint64_t prim_tests;     /* primitive intersection tests    — only with rt_set_option("count", 1) */
+    uint64_t exact_steps;    /* node steps that fell back to true divisions — only with rt_set_option("count", 1) */
 } RtStats;
 
 typedef struct RtScene RtScene;
@@ -181,8 +182,10 @@ int rt_film_scale_device(float* d_rgb, uint64_t n_floats, float multiplier, void
 /* Color::to_rgb8_gamma2 on device data. */
 int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_out_rgb8, void* cuda_stream);
 
-/* Knobs (process-wide): traversal variant for A/B parity sweeps. 0 = reference node test only (exact, slow),
- * 1 = reference test AND tight carried-interval cull (default). */
+/* Knobs (process-wide).  "traversal": 0 = reference node test only, true divisions (the reference's algorithm, for A/B
+ * parity sweeps); 1 = + tight carried-interval cull; 2 = + reciprocal fast path with exact fallback (default).
+ * "count": 1 = maintain node_visits / prim_tests / exact_steps.  "profile": 1 = time extend / shade separately.
+ * "refill": busy-lane threshold of the persistent extend warps.  "check_every": host polling period (iterations). */
 int rt_set_option(const char* key, int64_t value);
 
 #ifdef __cplusplus

@@ -22,7 +22,8 @@ using namespace rt;
 namespace {
 
 thread_local std::string g_err;
-int g_opt_traversal = 1;      // 0 = reference node test only, 1 = + tight carried-interval cull
+int g_opt_traversal = 2;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path
+int g_opt_refill = 20;        // extend refills idle lanes when fewer than this many of 32 are busy
 int g_opt_count = 0;        // 1 = COUNT kernel variant (node visits / primitive tests per ray)
 int g_opt_profile = 0;        // 1 = time extend / shade separately with events (adds syncs)
 int g_opt_check_every = 8;    // host polls the live-path count every N iterations
@@ -66,6 +67,7 @@ struct RtScene {
     DevBuf<NodeDev> nodes;
     DevBuf<PrimDev> prims;
     DevBuf<ShadeDev> shade;
+    DevBuf<float4> own_box;
     DevBuf<MaterialDev> materials;
     DevBuf<TextureDev> textures;
     std::vector<DevBuf<uint8_t>*> images;
@@ -180,7 +182,12 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     std::vector<PrimDev> prims(N);
     std::vector<ShadeDev> shade(N);
     std::vector<Box> lbox(N);
-    float r_min = INFINITY, r_max = 0.0f;
+    // Guard band of the tight cull (DESIGN.md "Tight node test"): a primitive test can report a hit for a ray that
+    // misses the primitive's true AABB by the rounding slack of that test.  m(t) = A + |t| (1e-5 + C |t|) with
+    //   triangles / rects: A = 8 eps max|coordinate|            (position = o + t d is rounded at coordinate scale)
+    //   spheres          : A = 8 eps (max|coordinate| + 3 r), C = 8 * 3 eps / r   (|disc error| <~ 11 eps |oc|^2)
+    std::vector<float> leafA(N), leafC(N);
+    const float eps = 5.9604645e-8f, safety = 8.0f;
     for (uint32_t i = 0; i < N; ++i) {
         const RtItem& it = d.items[i];
         if (it.kind > RT_GEO_TRIANGLE) return fail(RT_EUNSUPPORTED, "geometry kind outside the hot-path scope (AxisAlignedBox/volumes/transform wrappers)");
@@ -193,8 +200,6 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
         if (it.kind == RT_GEO_SPHERE) {
             if (!(g[3] >= 0.0f)) return fail(RT_EINVAL, "sphere radius must be >= 0 (sphere_geometry.rs:13)");
             p.q0 = make_float4(g[0], g[1], g[2], g[3]);
-            r_min = std::min(r_min, g[3]);
-            r_max = std::max(r_max, g[3]);
         } else if (it.kind == RT_GEO_RECT) {
             uint32_t plane = (uint32_t)g[0];
             if (plane > RT_RECT_YZ) return fail(RT_EINVAL, "rect plane out of range");
@@ -211,9 +216,56 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
         prims[i] = p;
         shade[i] = s;
         lbox[i] = leaf_box(it);
+        float maxabs = 0.0f;
+        for (int k = 0; k < 3; ++k) maxabs = std::max(maxabs, std::max(std::fabs(lbox[i].mn[k]), std::fabs(lbox[i].mx[k])));
+        if (it.kind == RT_GEO_SPHERE) {
+            leafA[i] = safety * eps * (maxabs + 3.0f * g[3]);
+            leafC[i] = g[3] > 0.0f ? safety * 3.0f * eps / g[3] : INFINITY;
+        } else {
+            leafA[i] = safety * eps * maxabs;
+            leafC[i] = 0.0f;
+        }
+    }
+    auto bf16_up = [](float v) -> uint32_t {  // smallest bf16 >= v (v >= 0)
+        uint32_t b;
+        std::memcpy(&b, &v, 4);
+        if (b & 0xFFFFu) b = (b | 0xFFFFu) + 1u;
+        return b >> 16;
+    };
+    auto pack_margin = [&](float a, float c) -> uint32_t { return (bf16_up(a) << 16) | bf16_up(c); };
+    // subtree maxima, bottom-up (children always have larger indices than their parent in the pre-order numbering;
+    // verified below, otherwise fall back to the global maximum)
+    std::vector<float> nodeA(d.n_nodes, 0.0f), nodeC(d.n_nodes, 0.0f);
+    {
+        bool preorder = true;
+        for (uint32_t i = 0; i < d.n_nodes && preorder; ++i)
+            for (uint32_t c : {d.nodes[i].left, d.nodes[i].right})
+                if (!(c & RT_LEAF_BIT) && c <= i) preorder = false;
+        if (preorder) {
+            for (uint32_t ii = d.n_nodes; ii-- > 0;) {
+                float a = 0.0f, c = 0.0f;
+                for (uint32_t ch : {d.nodes[ii].left, d.nodes[ii].right}) {
+                    if (ch & RT_LEAF_BIT) {
+                        uint32_t item = ch & ~RT_LEAF_BIT;
+                        if (item >= N) return fail(RT_EINVAL, "BVH child reference out of range");
+                        a = std::max(a, leafA[item]); c = std::max(c, leafC[item]);
+                    } else {
+                        if (ch >= d.n_nodes) return fail(RT_EINVAL, "BVH child reference out of range");
+                        a = std::max(a, nodeA[ch]); c = std::max(c, nodeC[ch]);
+                    }
+                }
+                nodeA[ii] = a; nodeC[ii] = c;
+            }
+        } else {
+            float a = 0.0f, c = 0.0f;
+            for (uint32_t i = 0; i < N; ++i) { a = std::max(a, leafA[i]); c = std::max(c, leafC[i]); }
+            std::fill(nodeA.begin(), nodeA.end(), a);
+            std::fill(nodeC.begin(), nodeC.end(), c);
+        }
     }
 
     std::vector<NodeDev> nodes(d.n_nodes);
+    std::vector<float4> own_box(2 * (size_t)d.n_nodes);
     auto child_box = [&](uint32_t r) -> Box {
         if (r & RT_LEAF_BIT) return lbox[r & ~RT_LEAF_BIT];
         Box b;
@@ -230,8 +282,10 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
         nd.q0 = make_float4(bl.mn[0], bl.mn[1], bl.mn[2], bl.mx[0]);
         nd.q1 = make_float4(bl.mx[1], bl.mx[2], br.mn[0], br.mn[1]);
         nd.q2 = make_float4(br.mn[2], br.mx[0], br.mx[1], br.mx[2]);
-        nd.q3 = make_uint4(l, r, n.axis_id, 0u);
+        nd.q3 = make_uint4(l, r, n.axis_id, pack_margin(nodeA[i], nodeC[i]));
         nodes[i] = nd;
+        own_box[2 * i] = make_float4(n.aabb_min[0], n.aabb_min[1], n.aabb_min[2], 0.0f);
+        own_box[2 * i + 1] = make_float4(n.aabb_max[0], n.aabb_max[1], n.aabb_max[2], 0.0f);
     }
     // depth of the tree (iterative DFS; also rejects cycles by bounding the visit count)
     uint32_t root;
@@ -257,25 +311,14 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     std::memset(&S, 0, sizeof(S));
     S.root = root;
     S.n_items = N;
-    float extent = 0.0f;
     if (!(root & RT_REF_LEAF)) {
         for (int k = 0; k < 3; ++k) {
             S.root_min[k] = d.nodes[root].aabb_min[k];
             S.root_max[k] = d.nodes[root].aabb_max[k];
-            extent = std::max(extent, std::max(std::fabs(S.root_min[k]), std::fabs(S.root_max[k])));
         }
-    } else {
-        for (int k = 0; k < 3; ++k) extent = std::max(extent, std::max(std::fabs(lbox[0].mn[k]), std::fabs(lbox[0].mx[k])));
+        S.root_margin = pack_margin(nodeA[root], nodeC[root]);
     }
-    for (int k = 0; k < 3; ++k) extent = std::max(extent, std::fabs(d.camera.position[k]));
     S.stack_cap = depth + 2;
-    // Guard band of the tight cull (DESIGN.md "Tight node test"): a primitive test can report a hit for a ray that
-    // misses the primitive's true AABB by the rounding slack of that test.  Spheres: |disc error| <~ 6 eps |oc|^2
-    // -> lateral slack <~ 3 eps (t^2 / r + r); triangles / rects: ~ eps * coordinate magnitude.
-    const float eps = 5.9604645e-8f, safety = 8.0f;
-    S.margin_a = safety * eps * (extent + 3.0f * r_max);
-    S.margin_b = 1e-5f;
-    S.margin_c = (r_min < INFINITY && r_min > 0.0f) ? safety * 3.0f * eps / r_min : 0.0f;
 
     const RtCamera& c = d.camera;
     S.cam.position = make_float3(c.position[0], c.position[1], c.position[2]);
@@ -302,10 +345,12 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     CU(sc.nodes.alloc(std::max<size_t>(nodes.size(), 1)));
     CU(sc.prims.alloc(N));
     CU(sc.shade.alloc(N));
+    CU(sc.own_box.alloc(std::max<size_t>(own_box.size(), 2)));
     if (!nodes.empty()) CU(cudaMemcpy(sc.nodes.p, nodes.data(), nodes.size() * sizeof(NodeDev), cudaMemcpyHostToDevice));
+    if (!nodes.empty()) CU(cudaMemcpy(sc.own_box.p, own_box.data(), own_box.size() * sizeof(float4), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(sc.prims.p, prims.data(), N * sizeof(PrimDev), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(sc.shade.p, shade.data(), N * sizeof(ShadeDev), cudaMemcpyHostToDevice));
-    sc.device_bytes = nodes.size() * sizeof(NodeDev) + (uint64_t)N * (sizeof(PrimDev) + sizeof(ShadeDev));
+    sc.device_bytes = nodes.size() * (sizeof(NodeDev) + 2 * sizeof(float4)) + (uint64_t)N * (sizeof(PrimDev) + sizeof(ShadeDev));
 
     std::vector<const uint8_t*> img_dev(d.n_images, nullptr);
     for (uint32_t i = 0; i < d.n_images; ++i) {
@@ -340,6 +385,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     S.nodes = sc.nodes.p;
     S.prims = sc.prims.p;
     S.shade = sc.shade.p;
+    S.own_box = sc.own_box.p;
     S.materials = sc.materials.p;
     S.textures = sc.textures.p;
     return RT_OK;
@@ -405,6 +451,8 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     R.hits = sc.hits.p;
     R.acc = sc.acc.p;
     R.ctr = sc.ctr.p;
+    R.cap = (uint32_t)slots;
+    R.refill_threshold = (uint32_t)std::min(32, std::max(1, g_opt_refill));
     R.npix = (uint32_t)npix; R.width = (uint32_t)P.width; R.height = (uint32_t)P.height;
     R.max_depth = P.max_depth;
     R.n_tasks = (uint32_t)n_tasks;
@@ -419,9 +467,10 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     const int eblock = 128;
     const size_t esmem = stack_smem_bytes(sc, eblock);
     int egrid = 0, sgrid = 0;
-    const bool tight = g_opt_traversal != 0;
+    const int mode = std::min(2, std::max(0, g_opt_traversal));
     void (*ext)(SceneDev, RenderDev, int) =
-        g_opt_count ? (tight ? k_extend<true, true> : k_extend<false, true>) : (tight ? k_extend<true, false> : k_extend<false, false>);
+        g_opt_count ? (mode == 2 ? k_extend<2, true> : (mode == 1 ? k_extend<1, true> : k_extend<0, true>))
+                    : (mode == 2 ? k_extend<2, false> : (mode == 1 ? k_extend<1, false> : k_extend<0, false>));
     rc = persistent_grid(sc, ext, eblock, esmem, &egrid);
     if (rc) return rc;
     rc = persistent_grid(sc, k_shade, 128, 0, &sgrid);
@@ -469,7 +518,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
         }
         CU(cudaMemcpyAsync(sc.h_ctr, sc.ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
-        if (sc.h_ctr->n[q] == 0) done = true;
+        if (sc.h_ctr->nb[q] + sc.h_ctr->nn[q] == 0) done = true;
         if (iters > max_iters) return fail(RT_ECUDA, "wavefront loop did not terminate");
     }
     {
@@ -493,6 +542,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
         stats->shade_ms = shade_ms;
         stats->node_visits = sc.h_ctr->node_visits;
         stats->prim_tests = sc.h_ctr->prim_tests;
+        stats->exact_steps = sc.h_ctr->exact_steps;
     }
     return RT_OK;
 }
@@ -515,6 +565,7 @@ int rt_set_option(const char* key, int64_t value) {
     if (k == "traversal") g_opt_traversal = (int)value;
     else if (k == "profile") g_opt_profile = (int)value;
     else if (k == "count") g_opt_count = (int)value;
+    else if (k == "refill") g_opt_refill = (int)value;
     else if (k == "check_every") g_opt_check_every = std::max<int>(1, (int)value);
     else if (k == "blocks_per_sm") g_opt_blocks_per_sm = (int)value;
     else return fail(RT_EINVAL, "unknown option " + k);
@@ -561,13 +612,12 @@ int rt_trace_device(RtScene* scene, const float* d_org, const float* d_dir, uint
     const int block = 128;
     const size_t smem = stack_smem_bytes(*scene, block);
     int grid = 0, rc;
-    const bool tight = g_opt_traversal != 0;
-    if (tight) rc = persistent_grid(*scene, k_trace<true>, block, smem, &grid);
-    else rc = persistent_grid(*scene, k_trace<false>, block, smem, &grid);
+    const int mode = std::min(2, std::max(0, g_opt_traversal));
+    auto trc = mode == 2 ? k_trace<2> : (mode == 1 ? k_trace<1> : k_trace<0>);
+    rc = persistent_grid(*scene, trc, block, smem, &grid);
     if (rc) return rc;
     grid = (int)std::min<uint64_t>((n + block - 1) / block, (uint64_t)grid * 4);
-    if (tight) k_trace<true><<<grid, block, smem, stream>>>(scene->dev, d_org, d_dir, n, t_min, t_max, d_hit_id, d_t, d_normal, d_front_face, d_uv);
-    else k_trace<false><<<grid, block, smem, stream>>>(scene->dev, d_org, d_dir, n, t_min, t_max, d_hit_id, d_t, d_normal, d_front_face, d_uv);
+    trc<<<grid, block, smem, stream>>>(scene->dev, d_org, d_dir, n, t_min, t_max, d_hit_id, d_t, d_normal, d_front_face, d_uv);
     CU(cudaGetLastError());
     return RT_OK;
 }

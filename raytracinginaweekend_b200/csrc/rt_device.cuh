@@ -20,7 +20,8 @@ namespace rt {
 
 // One internal BVH node = 64 B: the AABBs of BOTH children live in the parent ("children-in-parent"),
 // so one node visit is one 64-byte fetch (4 x LDG.128) and two independent box tests.
-//   q0 = Lmin.xyz Lmax.x | q1 = Lmax.yz Rmin.xy | q2 = Rmin.z Rmax.xyz | q3 = left, right, axis, 0
+//   q0 = Lmin.xyz Lmax.x | q1 = Lmax.yz Rmin.xy | q2 = Rmin.z Rmax.xyz | q3 = left, right, axis, guard band
+//   guard band = two bf16 (A << 16 | C): m(t) = A + |t| * (1e-5 + C |t|), the max over both child subtrees
 struct __align__(16) NodeDev {
     float4 q0, q1, q2;
     uint4 q3;
@@ -66,7 +67,8 @@ struct SceneDev {
     uint32_t n_items;
     float root_min[3], root_max[3];
     uint32_t stack_cap;       // traversal stack entries per thread
-    float margin_a, margin_b, margin_c;  // tight-cull guard band: m(t) = a + |t|*(b + c*|t|)
+    uint32_t root_margin;     // guard band of the root box test (packed like NodeDev.q3.w)
+    const float4* own_box;    // [2*n_nodes] each node's own AABB (min.xyz,0 | max.xyz,0): only read on exact-tie pops
     CameraDev cam;
     uint32_t bg_is_sky;
     float bg[3];
@@ -117,10 +119,6 @@ __device__ __forceinline__ Slab slab_test(float mnx, float mny, float mnz, float
     s.tn = fmaxf(fmaxf(nx, ny), nz);
     s.tf = fminf(fminf(fx, fy), fz);
     return s;
-}
-__device__ __forceinline__ float cull_margin(const SceneDev& S, float t) {
-    float at = fabsf(t);
-    return S.margin_a + at * (S.margin_b + S.margin_c * at);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -212,86 +210,166 @@ __device__ __forceinline__ bool leaf_test(const SceneDev& S, uint32_t ref, float
 }
 
 // ------------------------------------------------------------------------------------------------
-// BoundingVolumeHierarchy::hit (src/lib/hittable.rs:429-473) as an iterative, ordered DFS.
+// BoundingVolumeHierarchy::hit (src/lib/hittable.rs:429-473) as an iterative, ordered DFS, written as a
+// per-lane state machine (trav_begin / trav_step) so a persistent warp can refill finished lanes.
 //   * child order, the node test and the half-open acceptance are the reference's (Q13), so among equal-t
 //     candidates the first visited wins exactly as in the recursion;
-//   * the far child is pushed with tn; at pop the end-dependent part of hit_cond is re-evaluated exactly
+//   * the far child is pushed with tn; at pop the end-dependent part of hit_cond is re-evaluated
 //     (reject iff end <= tn), which is what the recursion does when it reaches that child later;
-//   * TIGHT additionally culls a child when the carried slab interval is empty by more than a guard band
-//     (true-bound AABBs cannot contain an accepted hit then); TIGHT=false is the reference rule alone.
+//   * MODE 0: the reference rule alone, true divisions (the reference's algorithm, for A/B sweeps);
+//     MODE 1: + tight cull: a child is skipped when the carried slab interval is empty by more than a per-node
+//             guard band (true-bound AABBs cannot contain an accepted hit then), true divisions;
+//     MODE 2: MODE 1 decisions, but evaluated with one reciprocal per ray and multiplies.  Whenever the
+//             approximate values cannot prove the decision (within RT_BAND relative, or the ray has a zero /
+//             denormal direction component) the exact MODE 1 code runs instead, so the visited set is identical.
 // Stack: shared memory, [level][thread] so lanes never bank-conflict.
 // ------------------------------------------------------------------------------------------------
 struct HitRec {
     uint32_t ref;  // child reference of the closest primitive, RT_NO_HIT if none
     float t;
 };
-
 struct TravCount {
-    uint32_t nodes, prims;  // internal-node visits (64 B fetches), primitive tests
+    uint32_t nodes, prims, exact;  // node visits (64 B fetches), primitive tests, exact-fallback node steps
 };
-template <bool TIGHT, bool COUNT = false>
-__device__ __forceinline__ HitRec traverse(const SceneDev& S, float3 o, float3 d, float start, float end_in,
-                                           uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride,
-                                           TravCount* cnt = nullptr) {
-    HitRec best;
-    best.ref = RT_NO_HIT;
-    best.t = end_in;
-    float end = end_in;
-    uint32_t cur = S.root;
-    if (!(cur & RT_REF_LEAF)) {
+struct Trav {
+    float3 o, d, inv;
+    float start, end;
+    uint32_t cur, sp, best;
+    bool exact_only;
+};
+#define RT_BAND 1e-6f  // >= 8 ulp: bound on |(x*rcp(d)) - rn(x/d)| is ~1.5 ulp
+
+// guard band m(t) = A + |t| * (1e-5 + C * |t|), A and C packed as two bf16 (rounded up): hi = A, lo = C
+__device__ __forceinline__ float node_margin(uint32_t packed, float t) {
+    float a = __uint_as_float(packed & 0xFFFF0000u), c = __uint_as_float(packed << 16);
+    float at = fabsf(t);
+    return a + at * (1e-5f + c * at);
+}
+
+template <int MODE>
+__device__ __forceinline__ bool trav_begin(const SceneDev& S, Trav& T, float3 o, float3 d, float start, float end) {
+    T.o = o; T.d = d; T.start = start; T.end = end;
+    T.best = RT_NO_HIT; T.sp = 0; T.cur = S.root;
+    T.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const float lo = 1e-18f, hi = 1e18f;  // NaN / inf / zero / denormal components -> exact path only
+    T.exact_only = !(fabsf(d.x) > lo && fabsf(d.x) < hi && fabsf(d.y) > lo && fabsf(d.y) < hi && fabsf(d.z) > lo && fabsf(d.z) < hi);
+    if (!(T.cur & RT_REF_LEAF)) {
         Slab r = slab_test(S.root_min[0], S.root_min[1], S.root_min[2], S.root_max[0], S.root_max[1], S.root_max[2], o,
                            d, start, end);
         bool pass = r.ref_pass;
-        if (TIGHT) pass = pass && !(r.tn - r.tf > cull_margin(S, r.tn));
-        if (!pass) return best;
+        if (MODE >= 1) pass = pass && !(r.tn - r.tf > node_margin(S.root_margin, r.tn));
+        return pass;
     }
-    uint32_t sp = 0;
-    for (;;) {
-        if (cur & RT_REF_LEAF) {
-            if (COUNT) cnt->prims++;
-            if (leaf_test(S, cur, o, d, start, end)) { best.ref = cur; best.t = end; }
+    return true;
+}
+
+__device__ __forceinline__ void approx_slab(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const Trav& T,
+                                            float& tn, float& tf) {
+    float ax = (mnx - T.o.x) * T.inv.x, bx = (mxx - T.o.x) * T.inv.x;
+    float ay = (mny - T.o.y) * T.inv.y, by = (mxy - T.o.y) * T.inv.y;
+    float az = (mnz - T.o.z) * T.inv.z, bz = (mxz - T.o.z) * T.inv.z;
+    tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), T.start));
+    tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), T.end));
+}
+
+// One node step or one leaf step (followed by the pops it triggers).  Returns false when the traversal is finished.
+template <int MODE, bool COUNT>
+__device__ __forceinline__ bool trav_step(const SceneDev& S, Trav& T, uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride,
+                                          TravCount* cnt) {
+    uint32_t cur = T.cur;
+    if (cur & RT_REF_LEAF) {
+        if (COUNT) cnt->prims++;
+        if (leaf_test(S, cur, T.o, T.d, T.start, T.end)) T.best = cur;
+    } else {
+        if (COUNT) cnt->nodes++;
+        const float4* q = reinterpret_cast<const float4*>(S.nodes + cur);
+        const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));
+        const bool leafL = (q3.x & RT_REF_LEAF) != 0u, leafR = (q3.y & RT_REF_LEAF) != 0u;
+        float tnL, tfL, tnR, tfR;
+        bool pL, pR, need_exact;
+        if (MODE == 2 && !T.exact_only) {
+            approx_slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T, tnL, tfL);
+            approx_slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, tnR, tfR);
+            const bool cullL = tnL - tfL > node_margin(q3.w, tnL), cullR = tnR - tfR > node_margin(q3.w, tnR);
+            // carried interval non-empty beyond rounding => the per-axis reference rule passes too
+            const bool sureL = leafL || (tfL - tnL > RT_BAND * (fabsf(tfL) + fabsf(tnL)));
+            const bool sureR = leafR || (tfR - tnR > RT_BAND * (fabsf(tfR) + fabsf(tnR)));
+            pL = !cullL && sureL;
+            pR = !cullR && sureR;
+            need_exact = (!cullL && !sureL) || (!cullR && !sureR);
         } else {
-            if (COUNT) cnt->nodes++;
-            const float4* q = reinterpret_cast<const float4*>(S.nodes + cur);
-            float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-            uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));
-            Slab sl = slab_test(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, d, start, end);
-            Slab sr = slab_test(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, d, start, end);
-            bool left_first = comp3(d, (int)q3.z) > 0.0f;  // hittable.rs:441-445
-            uint32_t c1 = left_first ? q3.x : q3.y, c2 = left_first ? q3.y : q3.x;
-            Slab s1 = left_first ? sl : sr, s2 = left_first ? sr : sl;
-            // leaves are never box-tested by the reference (hittable.rs:436-437); internal children get hit_cond
-            bool p1 = (c1 & RT_REF_LEAF) ? true : s1.ref_pass;
-            bool p2 = (c2 & RT_REF_LEAF) ? true : s2.ref_pass;
-            if (TIGHT) {
-                p1 = p1 && !(s1.tn - s1.tf > cull_margin(S, s1.tn));
-                p2 = p2 && !(s2.tn - s2.tf > cull_margin(S, s2.tn));
-            }
-            if (p1) {
-                if (p2) {
-                    stk_ref[sp * stk_stride] = c2;
-                    stk_tn[sp * stk_stride] = s2.tn;
-                    ++sp;
-                }
-                cur = c1;
-                continue;
-            }
-            if (p2) { cur = c2; continue; }
+            need_exact = true;
         }
-        // pop
-        for (;;) {
-            if (sp == 0) return best;
-            --sp;
-            cur = stk_ref[sp * stk_stride];
-            float tn = stk_tn[sp * stk_stride];
-            if (cur & RT_REF_LEAF) {
-                if (TIGHT && (tn - end > cull_margin(S, tn))) continue;
-                break;
+        if (need_exact) {
+            if (COUNT) cnt->exact++;
+            const Slab sl = slab_test(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T.o, T.d, T.start, T.end);
+            const Slab sr = slab_test(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T.o, T.d, T.start, T.end);
+            // leaves are never box-tested by the reference (hittable.rs:436-437); internal children get hit_cond
+            pL = leafL ? true : sl.ref_pass;
+            pR = leafR ? true : sr.ref_pass;
+            if (MODE >= 1) {
+                pL = pL && !(sl.tn - sl.tf > node_margin(q3.w, sl.tn));
+                pR = pR && !(sr.tn - sr.tf > node_margin(q3.w, sr.tn));
             }
-            if (end <= tn) continue;  // hit_cond's end-dependent part with the shrunken range
+            tnL = sl.tn; tnR = sr.tn;
+        }
+        const bool left_first = comp3(T.d, (int)q3.z) > 0.0f;  // hittable.rs:441-445
+        const uint32_t c1 = left_first ? q3.x : q3.y, c2 = left_first ? q3.y : q3.x;
+        const bool p1 = left_first ? pL : pR, p2 = left_first ? pR : pL;
+        if (p1) {
+            if (p2) {
+                float tn2 = left_first ? tnR : tnL;
+                // leaf entries carry their cull threshold (tn - guard band), internal entries carry tn
+                if (c2 & RT_REF_LEAF) tn2 = (MODE >= 1) ? tn2 - node_margin(q3.w, tn2) : -__int_as_float(0x7f800000);
+                stk_ref[T.sp * stk_stride] = c2;
+                stk_tn[T.sp * stk_stride] = tn2;
+                ++T.sp;
+            }
+            T.cur = c1;
+            return true;
+        }
+        if (p2) { T.cur = c2; return true; }
+    }
+    for (;;) {  // pop
+        if (T.sp == 0) return false;
+        --T.sp;
+        cur = stk_ref[T.sp * stk_stride];
+        const float tn = stk_tn[T.sp * stk_stride];
+        if (cur & RT_REF_LEAF) {
+            if (T.end < tn) continue;  // tight cull with the shrunken range (never taken in MODE 0: tn = -inf)
             break;
         }
+        // hit_cond's end-dependent part with the shrunken range: reject iff end <= tn (exact tn)
+        if (MODE == 2 && !T.exact_only) {
+            const float e = RT_BAND * fabsf(tn);
+            if (T.end > tn + e) break;
+            if (T.end < tn - e) continue;
+            const float4 b0 = __ldg(S.own_box + 2u * cur), b1 = __ldg(S.own_box + 2u * cur + 1u);
+            const Slab s = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, T.o, T.d, T.start, T.end);
+            if (T.end <= s.tn) continue;
+            break;
+        }
+        if (T.end <= tn) continue;
+        break;
     }
+    T.cur = cur;
+    return true;
+}
+
+template <int MODE, bool COUNT = false>
+__device__ __forceinline__ HitRec traverse(const SceneDev& S, float3 o, float3 d, float start, float end_in,
+                                           uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride,
+                                           TravCount* cnt = nullptr) {
+    Trav T;
+    HitRec best;
+    best.ref = RT_NO_HIT;
+    best.t = end_in;
+    if (!trav_begin<MODE>(S, T, o, d, start, end_in)) return best;
+    while (trav_step<MODE, COUNT>(S, T, stk_ref, stk_tn, stk_stride, cnt)) {}
+    best.ref = T.best;
+    best.t = T.end;
+    return best;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,12 +12,13 @@
 namespace rt {
 
 struct Counters {
-    uint32_t n[2];          // live paths in queue 0 / 1
+    uint32_t nb[2];         // live continuing (bounce) paths in queue 0 / 1: positions [0, nb)
+    uint32_t nn[2];         // live regenerated (primary) paths in queue 0 / 1: positions cap-1 .. cap-nn (descending)
     uint32_t cursor_extend; // dynamic work fetch
     uint32_t pad;
     unsigned long long rays;   // closest-hit queries so far
     unsigned long long paths;  // camera samples generated so far
-    unsigned long long node_visits, prim_tests;  // only maintained by the COUNT kernel variant
+    unsigned long long node_visits, prim_tests, exact_steps;  // only maintained by the COUNT kernel variant
 };
 
 struct RenderDev {
@@ -28,6 +29,8 @@ struct RenderDev {
     uint2* hits;    // (child ref of closest primitive | RT_NO_HIT, bits(t)) per queue position
     float4* acc;    // [n_local_lanes * npix] running per-lane sums (exclusive owner: the slot's single live path)
     Counters* ctr;
+    uint32_t cap;            // queue capacity = number of path slots
+    uint32_t refill_threshold;  // extend refills idle lanes when fewer than this many lanes are busy
     uint32_t npix, width, height;
     int32_t max_depth;
     uint32_t n_tasks;        // T' = lanes that got >= 1 sample (split_work_tasks)
@@ -68,48 +71,82 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
         R.acc[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        R.ctr->n[0] = n_slots;
-        R.ctr->n[1] = 0;
+        R.ctr->nb[0] = n_slots; R.ctr->nn[0] = 0;
+        R.ctr->nb[1] = 0; R.ctr->nn[1] = 0;
         R.ctr->cursor_extend = 0;
         R.ctr->rays = 0;
         R.ctr->paths = n_slots;
         R.ctr->node_visits = 0;
         R.ctr->prim_tests = 0;
+        R.ctr->exact_steps = 0;
     }
 }
 
-// Closest hit for every live path of queue `q`.  Persistent warps pull 32 rays at a time.
-template <bool TIGHT, bool COUNT>
+// Queue position of the i-th live path: continuing paths grow from 0, regenerated ones from the top.
+__device__ __forceinline__ uint32_t queue_pos(uint32_t i, uint32_t nb, uint32_t cap) { return i < nb ? i : cap - 1u - (i - nb); }
+
+// Closest hit for every live path of queue `q`.  Persistent warps: every lane owns one ray's traversal state and,
+// when fewer than `refill_threshold` lanes are still busy, the idle lanes pull fresh rays with one warp-aggregated
+// atomic — rays differ by 100x in node visits, so waiting for the slowest lane would idle most of the warp.
+template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
     extern __shared__ uint32_t smem[];
     uint32_t* stk_ref = smem + threadIdx.x;
     float* stk_tn = reinterpret_cast<float*>(smem + S.stack_cap * blockDim.x) + threadIdx.x;
-    const uint32_t n = R.ctr->n[q];
+    const uint32_t nb = R.ctr->nb[q], n = nb + R.ctr->nn[q];
     const uint32_t lane = threadIdx.x & 31u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) R.ctr->n[q ^ 1] = 0;  // next queue starts empty (nobody touches it during extend)
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const float INF = __int_as_float(0x7f800000);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { R.ctr->nb[q ^ 1] = 0; R.ctr->nn[q ^ 1] = 0; }  // nobody touches them during extend
     TravCount tc;
-    tc.nodes = 0; tc.prims = 0;
+    tc.nodes = 0; tc.prims = 0; tc.exact = 0;
+    Trav T;
+    bool active = false, exhausted = false;
+    uint32_t my_pos = 0;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&R.ctr->cursor_extend, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + lane;
-        if (i < n) {
-            float4 a = R.A[q][i], b = R.B[q][i];
-            HitRec h = traverse<TIGHT, COUNT>(S, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), 0.001f, __int_as_float(0x7f800000),
-                                              stk_ref, stk_tn, blockDim.x, &tc);
-            R.hits[i] = make_uint2(h.ref, __float_as_uint(h.t));
+        const uint32_t idle = __ballot_sync(FULL, !active);
+        if (idle && !exhausted) {
+            const uint32_t want = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&R.ctr->cursor_extend, want);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + want >= n) exhausted = true;
+            if (!active) {
+                const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n) {
+                    my_pos = queue_pos(i, nb, R.cap);
+                    const float4 a = R.A[q][my_pos], b = R.B[q][my_pos];
+                    active = trav_begin<MODE>(S, T, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), 0.001f, INF);
+                    if (!active) R.hits[my_pos] = make_uint2(RT_NO_HIT, __float_as_uint(INF));
+                }
+            }
         }
+        uint32_t busy = __popc(__ballot_sync(FULL, active));
+        if (busy == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        const uint32_t thresh = exhausted ? 1u : R.refill_threshold;
+        do {
+            if (active) {
+                if (!trav_step<MODE, COUNT>(S, T, stk_ref, stk_tn, blockDim.x, &tc)) {
+                    R.hits[my_pos] = make_uint2(T.best, __float_as_uint(T.end));
+                    active = false;
+                }
+            }
+            busy = __popc(__ballot_sync(FULL, active));
+        } while (busy >= thresh);
     }
     if (COUNT) {
         for (int off = 16; off > 0; off >>= 1) {
-            tc.nodes += __shfl_xor_sync(0xFFFFFFFFu, tc.nodes, off);
-            tc.prims += __shfl_xor_sync(0xFFFFFFFFu, tc.prims, off);
+            tc.nodes += __shfl_xor_sync(FULL, tc.nodes, off);
+            tc.prims += __shfl_xor_sync(FULL, tc.prims, off);
+            tc.exact += __shfl_xor_sync(FULL, tc.exact, off);
         }
         if (lane == 0) {
             atomicAdd(&R.ctr->node_visits, (unsigned long long)tc.nodes);
             atomicAdd(&R.ctr->prim_tests, (unsigned long long)tc.prims);
+            atomicAdd(&R.ctr->exact_steps, (unsigned long long)tc.exact);
         }
     }
 }
@@ -117,7 +154,7 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ SceneDev
 // One bounce of ray_color for every live path of queue `q`; survivors (and regenerated paths) are compacted
 // into queue q^1 with one warp-aggregated atomic per warp.
 __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
-    const uint32_t n = R.ctr->n[q];
+    const uint32_t nb = R.ctr->nb[q], n = nb + R.ctr->nn[q];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -127,16 +164,17 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
     }
     uint32_t new_paths = 0;
     for (uint32_t base = warp_global * 32u; base < n; base += n_warps * 32u) {
-        uint32_t i = base + lane;
-        bool live = false;
+        const uint32_t i = base + lane;
+        const uint32_t ipos = queue_pos(i, nb, R.cap);
+        bool live = false, fresh = false;
         float3 o = f3(0, 0, 0), d = f3(0, 0, 1), thr = f3(1, 1, 1);
         float dy0 = 0.0f;
         uint32_t slot = 0, k = 0;
         int32_t depth = 0;
         if (i < n) {
-            float4 a = R.A[q][i], b = R.B[q][i], c = R.C[q][i];
-            depth = R.D[q][i];
-            uint2 h = R.hits[i];
+            float4 a = R.A[q][ipos], b = R.B[q][ipos], c = R.C[q][ipos];
+            depth = R.D[q][ipos];
+            uint2 h = R.hits[ipos];
             o = f3(a.x, a.y, a.z); d = f3(b.x, b.y, b.z); thr = f3(c.x, c.y, c.z);
             dy0 = c.w;
             slot = __float_as_uint(a.w);
@@ -293,17 +331,26 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
                     dy0 = d.y;
                     depth = R.max_depth;
                     live = true;
+                    fresh = true;
                     new_paths += 1u;
                 }
             }
         }
-        // warp-ballot compaction into the other queue
-        uint32_t mask = __ballot_sync(0xFFFFFFFFu, live);
-        if (mask) {
-            uint32_t pos = 0;
-            if (lane == 0) pos = atomicAdd(&R.ctr->n[q ^ 1], (uint32_t)__popc(mask));
-            pos = __shfl_sync(0xFFFFFFFFu, pos, 0) + __popc(mask & ((1u << lane) - 1u));
+        // warp-ballot compaction into the other queue: continuing paths from the bottom, fresh camera paths from the
+        // top, so warps of the next extend hold either coherent primary rays or bounce rays, not a mix
+        const uint32_t mcont = __ballot_sync(0xFFFFFFFFu, live && !fresh);
+        const uint32_t mnew = __ballot_sync(0xFFFFFFFFu, live && fresh);
+        if (mcont | mnew) {
+            uint32_t bc = 0, bn = 0;
+            if (lane == 0) {
+                if (mcont) bc = atomicAdd(&R.ctr->nb[q ^ 1], (uint32_t)__popc(mcont));
+                if (mnew) bn = atomicAdd(&R.ctr->nn[q ^ 1], (uint32_t)__popc(mnew));
+            }
+            bc = __shfl_sync(0xFFFFFFFFu, bc, 0);
+            bn = __shfl_sync(0xFFFFFFFFu, bn, 0);
             if (live) {
+                const uint32_t below = (1u << lane) - 1u;
+                const uint32_t pos = fresh ? R.cap - 1u - (bn + __popc(mnew & below)) : bc + __popc(mcont & below);
                 R.A[q ^ 1][pos] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
                 R.B[q ^ 1][pos] = make_float4(d.x, d.y, d.z, __uint_as_float(k));
                 R.C[q ^ 1][pos] = make_float4(thr.x, thr.y, thr.z, dy0);
@@ -349,7 +396,7 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ Render
 }
 
 // Scene::hit on caller rays.
-template <bool TIGHT>
+template <int MODE>
 __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ SceneDev S, const float* __restrict__ org,
                                                const float* __restrict__ dir, uint64_t n, float t_min, float t_max,
                                                uint32_t* __restrict__ hit_id, float* __restrict__ t_out,
@@ -361,7 +408,7 @@ __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ SceneDev 
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]);
         float3 d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
-        HitRec h = traverse<TIGHT>(S, o, d, t_min, t_max, stk_ref, stk_tn, blockDim.x);
+        HitRec h = traverse<MODE>(S, o, d, t_min, t_max, stk_ref, stk_tn, blockDim.x);
         if (h.ref != RT_NO_HIT) {
             Interaction hi = make_interaction(S, h.ref, h.t, o, d, true);
             if (hit_id) hit_id[i] = h.ref & RT_REF_ITEM_MASK;

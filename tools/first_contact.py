@@ -8,7 +8,7 @@ from raytracinginaweekend_b200 import _cabi as rt
 def cmp_trace(name, W, S, org, dir, label):
     t0 = time.time(); ref = W.trace(org, dir); t1 = time.time()
     res = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         rt.set_option("traversal", mode)
         got = S.trace(org, dir)
         ids = int((got["hit_id"] != ref["hit_id"]).sum())
@@ -42,7 +42,7 @@ for name, (pw, ph) in {"config:c1": (300, 200), "config:c2": (320, 180), "config
     cmp_trace(name, W, S, org, dir, "primary")
     org, dir = rand_rays(fs, 60000, 42)
     cmp_trace(name, W, S, org, dir, "random")
-    rt.set_option("traversal", 1)
+    rt.set_option("traversal", 2)
     # replay render parity (bit-exact expected)
     for (w, h, spp, T) in [(64, 48, 4, 1), (64, 48, 5, 2)]:
         ref, st = W.render(w, h, spp, 50, T, 7, "replay")
@@ -56,22 +56,27 @@ for name, (pw, ph) in {"config:c1": (300, 200), "config:c2": (320, 180), "config
     S.close(); W.close()
 
 # timing
-for name, spp in [("config:c2", 64), ("config:c1", 10), ("config:c3", 64)]:
+for name, spp in [("config:c2", 16), ("config:c1", 10), ("config:c3", 32)]:
     W = ob.OracleWorld.named(name); fs = W.export(); w, h = fs.default_size
     S = rt.DeviceScene.from_flat(fs)
+    rt.set_option("traversal", 2)
+    S.render(w, h, 2, 50, 1, 3)
     for T in (1, 4):
-        for trav in (1, 0):
-            if trav == 0 and T != 1: continue
-            rt.set_option("traversal", trav)
-            S.render(w, h, min(spp, 2), 50, 1, 3)
+        for refill in (1, 12, 16, 20, 24, 28, 32):
+            rt.set_option("refill", refill)
             img, st = S.render(w, h, spp, 50, T, 3)
-            print(name, "T", T, "trav", trav, "ms %.1f" % st["render_ms"], "Mrays/s %.1f" % (st["ray_segments"] / st["render_ms"] / 1e3),
-                  "rays", st["ray_segments"], "paths", st["paths"], "iters", st["iterations"], flush=True)
-    rt.set_option("traversal", 1); rt.set_option("profile", 1)
+            print(name, "T", T, "refill", refill, "ms %.1f" % st["render_ms"], "Mrays/s %.1f" % (st["ray_segments"] / st["render_ms"] / 1e3),
+                  "rays", st["ray_segments"], "iters", st["iterations"], flush=True)
+    rt.set_option("refill", 20)
+    for trav in (1, 0):
+        rt.set_option("traversal", trav)
+        img, st = S.render(w, h, spp, 50, 4, 3)
+        print(name, "T 4 trav", trav, "ms %.1f" % st["render_ms"], "Mrays/s %.1f" % (st["ray_segments"] / st["render_ms"] / 1e3), flush=True)
+    rt.set_option("traversal", 2); rt.set_option("count", 1)
+    img, st = S.render(w, h, spp, 50, 4, 3)
+    print(name, "counts: nodes/ray %.2f prims/ray %.2f exact/node %.5f" % (st["node_visits"] / st["ray_segments"], st["prim_tests"] / st["ray_segments"], st["exact_steps"] / max(1, st["node_visits"])), flush=True)
+    rt.set_option("count", 0); rt.set_option("profile", 1)
     img, st = S.render(w, h, spp, 50, 4, 3)
     print(name, "profile T4: extend_ms %.1f shade_ms %.1f total %.1f" % (st["extend_ms"], st["shade_ms"], st["render_ms"]), flush=True)
     rt.set_option("profile", 0)
-    from PIL import Image
-    os.makedirs("gpurun_out", exist_ok=True)
-    Image.fromarray(ob.to_rgb8_gamma2(img)).save("gpurun_out/%s.png" % name.split(":")[1])
     S.close(); W.close()
