@@ -23,6 +23,7 @@ namespace {
 
 thread_local std::string g_err;
 int g_opt_traversal = 2;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path
+int g_opt_leaf_weight = 16;   // extend phase vote: leaf phase when n_leaf * w > n_node * 16
 int g_opt_refill = 20;        // extend refills idle lanes when fewer than this many of 32 are busy
 int g_opt_count = 0;        // 1 = COUNT kernel variant (node visits / primitive tests per ray)
 int g_opt_profile = 0;        // 1 = time extend / shade separately with events (adds syncs)
@@ -453,6 +454,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     R.ctr = sc.ctr.p;
     R.cap = (uint32_t)slots;
     R.refill_threshold = (uint32_t)std::min(32, std::max(1, g_opt_refill));
+    R.leaf_weight = (uint32_t)std::max(1, g_opt_leaf_weight);
     R.npix = (uint32_t)npix; R.width = (uint32_t)P.width; R.height = (uint32_t)P.height;
     R.max_depth = P.max_depth;
     R.n_tasks = (uint32_t)n_tasks;
@@ -566,6 +568,7 @@ int rt_set_option(const char* key, int64_t value) {
     else if (k == "profile") g_opt_profile = (int)value;
     else if (k == "count") g_opt_count = (int)value;
     else if (k == "refill") g_opt_refill = (int)value;
+    else if (k == "leaf_weight") g_opt_leaf_weight = (int)value;
     else if (k == "check_every") g_opt_check_every = std::max<int>(1, (int)value);
     else if (k == "blocks_per_sm") g_opt_blocks_per_sm = (int)value;
     else return fail(RT_EINVAL, "unknown option " + k);

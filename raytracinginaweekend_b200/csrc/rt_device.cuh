@@ -272,15 +272,24 @@ __device__ __forceinline__ void approx_slab(float mnx, float mny, float mnz, flo
     tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), T.end));
 }
 
-// One node step or one leaf step (followed by the pops it triggers).  Returns false when the traversal is finished.
+// One scheduling round of a lane: a node step (if `do_leaf` is false and the lane is at an internal node) or a leaf
+// step (if `do_leaf` is true and the lane is at a leaf), followed by the pops it triggers; lanes in the other state
+// simply wait.  The warp picks `do_leaf` by vote (k_extend), so each phase runs with most lanes enabled instead of
+// interleaving 17-lane node steps with 4-lane leaf tests.  Per-lane visit order is untouched.
+// Returns false when the lane's traversal is finished.
 template <int MODE, bool COUNT>
-__device__ __forceinline__ bool trav_step(const SceneDev& S, Trav& T, uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride,
-                                          TravCount* cnt) {
+__device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_leaf, uint32_t* stk_ref, float* stk_tn,
+                                           uint32_t stk_stride, TravCount* cnt) {
     uint32_t cur = T.cur;
-    if (cur & RT_REF_LEAF) {
-        if (COUNT) cnt->prims++;
-        if (leaf_test(S, cur, T.o, T.d, T.start, T.end)) T.best = cur;
-    } else {
+    const bool at_leaf = (cur & RT_REF_LEAF) != 0u;
+    bool need_pop = false;
+    if (do_leaf) {
+        if (at_leaf) {
+            if (COUNT) cnt->prims++;
+            if (leaf_test(S, cur, T.o, T.d, T.start, T.end)) T.best = cur;
+            need_pop = true;
+        }
+    } else if (!at_leaf) {
         if (COUNT) cnt->nodes++;
         const float4* q = reinterpret_cast<const float4*>(S.nodes + cur);
         const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
@@ -317,44 +326,50 @@ __device__ __forceinline__ bool trav_step(const SceneDev& S, Trav& T, uint32_t* 
         const bool left_first = comp3(T.d, (int)q3.z) > 0.0f;  // hittable.rs:441-445
         const uint32_t c1 = left_first ? q3.x : q3.y, c2 = left_first ? q3.y : q3.x;
         const bool p1 = left_first ? pL : pR, p2 = left_first ? pR : pL;
-        if (p1) {
-            if (p2) {
-                float tn2 = left_first ? tnR : tnL;
-                // leaf entries carry their cull threshold (tn - guard band), internal entries carry tn
-                if (c2 & RT_REF_LEAF) tn2 = (MODE >= 1) ? tn2 - node_margin(q3.w, tn2) : -__int_as_float(0x7f800000);
-                stk_ref[T.sp * stk_stride] = c2;
-                stk_tn[T.sp * stk_stride] = tn2;
-                ++T.sp;
+        if (p1 && p2) {
+            float tn2 = left_first ? tnR : tnL;
+            // leaf entries carry their cull threshold (tn - guard band), internal entries carry tn
+            if (c2 & RT_REF_LEAF) tn2 = (MODE >= 1) ? tn2 - node_margin(q3.w, tn2) : -__int_as_float(0x7f800000);
+            stk_ref[T.sp * stk_stride] = c2;
+            stk_tn[T.sp * stk_stride] = tn2;
+            ++T.sp;
+        }
+        if (p1) T.cur = c1;
+        else if (p2) T.cur = c2;
+        else need_pop = true;
+    }
+    if (need_pop) {
+        for (;;) {
+            if (T.sp == 0) return false;
+            --T.sp;
+            cur = stk_ref[T.sp * stk_stride];
+            const float tn = stk_tn[T.sp * stk_stride];
+            if (cur & RT_REF_LEAF) {
+                if (T.end < tn) continue;  // tight cull with the shrunken range (never taken in MODE 0: tn = -inf)
+                break;
             }
-            T.cur = c1;
-            return true;
-        }
-        if (p2) { T.cur = c2; return true; }
-    }
-    for (;;) {  // pop
-        if (T.sp == 0) return false;
-        --T.sp;
-        cur = stk_ref[T.sp * stk_stride];
-        const float tn = stk_tn[T.sp * stk_stride];
-        if (cur & RT_REF_LEAF) {
-            if (T.end < tn) continue;  // tight cull with the shrunken range (never taken in MODE 0: tn = -inf)
+            // hit_cond's end-dependent part with the shrunken range: reject iff end <= tn (exact tn)
+            if (MODE == 2 && !T.exact_only) {
+                const float e = RT_BAND * fabsf(tn);
+                if (T.end > tn + e) break;
+                if (T.end < tn - e) continue;
+                const float4 b0 = __ldg(S.own_box + 2u * cur), b1 = __ldg(S.own_box + 2u * cur + 1u);
+                const Slab s = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, T.o, T.d, T.start, T.end);
+                if (T.end <= s.tn) continue;
+                break;
+            }
+            if (T.end <= tn) continue;
             break;
         }
-        // hit_cond's end-dependent part with the shrunken range: reject iff end <= tn (exact tn)
-        if (MODE == 2 && !T.exact_only) {
-            const float e = RT_BAND * fabsf(tn);
-            if (T.end > tn + e) break;
-            if (T.end < tn - e) continue;
-            const float4 b0 = __ldg(S.own_box + 2u * cur), b1 = __ldg(S.own_box + 2u * cur + 1u);
-            const Slab s = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, T.o, T.d, T.start, T.end);
-            if (T.end <= s.tn) continue;
-            break;
-        }
-        if (T.end <= tn) continue;
-        break;
+        T.cur = cur;
     }
-    T.cur = cur;
     return true;
+}
+
+template <int MODE, bool COUNT>
+__device__ __forceinline__ bool trav_step(const SceneDev& S, Trav& T, uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride,
+                                          TravCount* cnt) {
+    return trav_round<MODE, COUNT>(S, T, (T.cur & RT_REF_LEAF) != 0u, stk_ref, stk_tn, stk_stride, cnt);
 }
 
 template <int MODE, bool COUNT = false>

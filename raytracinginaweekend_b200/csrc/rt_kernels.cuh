@@ -31,6 +31,7 @@ struct RenderDev {
     Counters* ctr;
     uint32_t cap;            // queue capacity = number of path slots
     uint32_t refill_threshold;  // extend refills idle lanes when fewer than this many lanes are busy
+    uint32_t leaf_weight;       // phase vote: leaf phase runs when n_leaf * leaf_weight > n_node * 16
     uint32_t npix, width, height;
     int32_t max_depth;
     uint32_t n_tasks;        // T' = lanes that got >= 1 sample (split_work_tasks)
@@ -128,8 +129,12 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ SceneDev
         }
         const uint32_t thresh = exhausted ? 1u : R.refill_threshold;
         do {
+            // phase vote: run the leaf phase when (weighted) more lanes wait at a leaf than at an internal node
+            const uint32_t at_leaf = __ballot_sync(FULL, active && (T.cur & RT_REF_LEAF));
+            const uint32_t n_leaf = __popc(at_leaf);
+            const bool do_leaf = n_leaf * R.leaf_weight > (busy - n_leaf) * 16u;
             if (active) {
-                if (!trav_step<MODE, COUNT>(S, T, stk_ref, stk_tn, blockDim.x, &tc)) {
+                if (!trav_round<MODE, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc)) {
                     R.hits[my_pos] = make_uint2(T.best, __float_as_uint(T.end));
                     active = false;
                 }
