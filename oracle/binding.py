@@ -52,11 +52,17 @@ def lib():
         L.orc_render.restype = C.c_double
         L.orc_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_int,
                                  C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_render_planes.restype = C.c_double
+        L.orc_render_planes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_int,
+                                        C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.orc_to_rgb8_gamma2.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.orc_aabb_hit_cond.restype = C.c_int
         L.orc_aabb_hit_cond.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float]
         L.orc_obj_load.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_rng_kat.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_probe_math.argtypes = [C.c_float, C.c_void_p]
+        L.orc_split_work_tasks.restype = C.c_int
+        L.orc_split_work_tasks.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
         L.orc_philox.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
         _lib = L
     return _lib
@@ -195,6 +201,18 @@ class OracleWorld:
                                 {"faithful": 0, "replay": 1}[mode], {"default": 0, "normals": 1}[render_mode],
                                 _p(out), _p(stats))
         return out, dict(seconds=secs, rays=int(stats[0]), node_tests=int(stats[1]), prim_tests=int(stats[2]))
+
+
+def _render_planes(self, width, height, spp, max_depth, threads, seed, mode, lane_first, lane_stride, render_mode="default"):
+    """Un-normalised sum of this rank's lane planes (multi-GPU split of render(); see rt_render_planes_device)."""
+    out = np.zeros((height, width, 3), np.float32)
+    stats = np.zeros(3, np.uint64)
+    secs = lib().orc_render_planes(self.h, width, height, spp, max_depth, threads, seed, {"faithful": 0, "replay": 1}[mode],
+                                   {"default": 0, "normals": 1}[render_mode], lane_first, lane_stride, _p(out), _p(stats))
+    return out, dict(seconds=secs, rays=int(stats[0]))
+
+
+OracleWorld.render_planes = _render_planes
 
 
 def to_rgb8_gamma2(rgb):

@@ -254,18 +254,23 @@ void orc_primary_rays(void* hp, int width, int height, float* org, float* dir) {
 // (Philox (seed, pixel, sample, block) + inversion samplers; global sample index = k * n_tasks + task id).
 // render_mode: 0 = Default, 1 = Normals.  stats: [0] ray segments, [1] node tests, [2] prim tests.  Returns seconds
 // (timing brackets = the reference's: thread spawn .. join, excluding merge).
-double orc_render(void* hp, int width, int height, uint64_t spp, int max_depth, uint64_t thread_count, uint64_t seed,
-                  int mode, int render_mode, float* out_rgb, uint64_t* stats) {
+// lane_first / lane_stride select the subset of worker tasks this call renders (multi-GPU split of the same
+// function); apply_scale = 0 returns the un-normalised plane sum (before the 1/len multiplier of merge_planes).
+static double render_impl(void* hp, int width, int height, uint64_t spp, int max_depth, uint64_t thread_count, uint64_t seed,
+                          int mode, int render_mode, uint32_t lane_first, uint32_t lane_stride, int apply_scale,
+                          float* out_rgb, uint64_t* stats) {
     const World& world = ((Handle*)hp)->bw->world;
     const size_t npix = (size_t)width * height;
     UniformF32 jx(0.0f, 1.0f / (float)(width - 1)), jy(0.0f, 1.0f / (float)(height - 1));  // :132-138
-    std::vector<std::pair<size_t, size_t>> tasks = split_work_tasks(spp, thread_count);
-    const size_t n_tasks = tasks.size();
-    std::vector<std::vector<Color>> planes(n_tasks);
-    std::vector<Counters> cnts(n_tasks);
+    std::vector<std::pair<size_t, size_t>> all_tasks = split_work_tasks(spp, thread_count);
+    const size_t n_tasks = all_tasks.size();
+    std::vector<std::pair<size_t, size_t>> tasks;
+    for (size_t i = lane_first; i < n_tasks; i += lane_stride) tasks.push_back(all_tasks[i]);
+    std::vector<std::vector<Color>> planes(tasks.size());
+    std::vector<Counters> cnts(tasks.size());
     auto t_start = std::chrono::steady_clock::now();
     std::vector<std::thread> threads;
-    for (size_t ti = 0; ti < n_tasks; ++ti) {
+    for (size_t ti = 0; ti < tasks.size(); ++ti) {
         threads.emplace_back([&, ti]() {
             const size_t id = tasks[ti].first, real_spp = tasks[ti].second;
             TRng rng = mode == 1 ? TRng::make_replay(seed) : TRng::from_u64(seed * 0x9E3779B97F4A7C15ull + id + 1);
@@ -300,19 +305,38 @@ double orc_render(void* hp, int width, int height, uint64_t spp, int max_depth, 
     }
     for (auto& th : threads) th.join();
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
-    // merge_planes :239-252
-    float multiplier = 1.0f / (float)planes.size();
-    std::vector<Color> pixels = std::move(planes.back());
-    planes.pop_back();
-    for (const auto& plane : planes)
-        for (size_t i = 0; i < npix; ++i) pixels[i] = pixels[i] + plane[i];
-    for (size_t i = 0; i < npix; ++i) pixels[i] = pixels[i] * multiplier;
+    std::vector<Color> pixels(npix);
+    if (!planes.empty()) {
+        // merge_planes :239-252 — the LAST plane is popped first; a rank that does not own the globally last task sums ascending
+        const bool owns_last = tasks.back().first == n_tasks - 1;
+        if (owns_last) {
+            pixels = std::move(planes.back());
+            planes.pop_back();
+        } else {
+            pixels = std::move(planes.front());
+            planes.erase(planes.begin());
+        }
+        for (const auto& plane : planes)
+            for (size_t i = 0; i < npix; ++i) pixels[i] = pixels[i] + plane[i];
+        if (apply_scale) {
+            float multiplier = 1.0f / (float)n_tasks;
+            for (size_t i = 0; i < npix; ++i) pixels[i] = pixels[i] * multiplier;
+        }
+    }
     for (size_t i = 0; i < npix; ++i) for (int k = 0; k < 3; ++k) out_rgb[3 * i + k] = pixels[i].e[k];
     if (stats) {
         stats[0] = stats[1] = stats[2] = 0;
         for (const Counters& c : cnts) { stats[0] += c.rays; stats[1] += c.node_tests; stats[2] += c.prim_tests; }
     }
     return secs;
+}
+double orc_render(void* hp, int width, int height, uint64_t spp, int max_depth, uint64_t thread_count, uint64_t seed,
+                  int mode, int render_mode, float* out_rgb, uint64_t* stats) {
+    return render_impl(hp, width, height, spp, max_depth, thread_count, seed, mode, render_mode, 0, 1, 1, out_rgb, stats);
+}
+double orc_render_planes(void* hp, int width, int height, uint64_t spp, int max_depth, uint64_t thread_count, uint64_t seed,
+                         int mode, int render_mode, uint32_t lane_first, uint32_t lane_stride, float* out_rgb, uint64_t* stats) {
+    return render_impl(hp, width, height, spp, max_depth, thread_count, seed, mode, render_mode, lane_first, lane_stride, 0, out_rgb, stats);
 }
 
 // Color::to_rgb8_gamma2 — src/lib/color.rs:43-48 (caller side, src/app/main.rs:53-56)
@@ -344,6 +368,15 @@ void orc_rng_kat(uint64_t* u64_out, float* f32_out) {  // first draws of the sce
     for (int i = 0; i < 4; ++i) u64_out[i] = r.next_u64();
     TRng r2 = scene_rng();
     for (int i = 0; i < 4; ++i) f32_out[i] = r2.gen_f32();
+}
+void orc_probe_math(float u, float* out3) {  // sincos_2pi / cbrt_unit of the REPLAY samplers
+    sincos_2pi(u, &out3[0], &out3[1]);
+    out3[2] = cbrt_unit(u);
+}
+int orc_split_work_tasks(uint64_t spp, uint64_t threads, uint64_t* out_counts, uint64_t cap) {
+    auto t = split_work_tasks(spp, threads);
+    for (size_t i = 0; i < t.size() && i < cap; ++i) out_counts[i] = t[i].second;
+    return (int)t.size();
 }
 void orc_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out) {
     philox4x32_10(k0, k1, c0, c1, c2, c3, out);

@@ -205,7 +205,17 @@ class DeviceScene:
         check(lib().rt_scene_create(C.byref(desc), device, C.byref(h)))
         self.h = h
         self.device = device
+        self.owned = True
         del keepalive  # rt_scene_create copies everything
+
+    @classmethod
+    def borrowed(cls, handle, device: int = 0) -> "DeviceScene":
+        """Wrap an RtScene* owned by someone else (the host mirror's World)."""
+        self = cls.__new__(cls)
+        self.h = handle
+        self.device = device
+        self.owned = False
+        return self
 
     @classmethod
     def from_flat(cls, fs, device: int = 0) -> "DeviceScene":
@@ -216,7 +226,8 @@ class DeviceScene:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().rt_scene_destroy(self.h)
+            if getattr(self, "owned", True):
+                lib().rt_scene_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -51,7 +51,9 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
 def build_host(force: bool = False) -> str:
     srcs = _sources(HOST, (".cpp", ".hpp")) + [os.path.join(ROOT, "include", "b200rt.h"), os.path.join(ROOT, "include", "rtiaw_host.h")]
     if force or _stale(LIB_HOST, srcs):
-        cmd = ["g++"] + GXX_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIB_HOST, os.path.join(HOST, "rtiaw_capi.cpp"), "-ldl"]
+        build_cuda()
+        cmd = ["g++"] + GXX_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIB_HOST, os.path.join(HOST, "rtiaw_capi.cpp"),
+               "-L", PKG, "-lb200rt", "-Wl,-rpath,$ORIGIN"]
         subprocess.check_call(cmd)
     return LIB_HOST
 

@@ -1,0 +1,180 @@
+// rtiaw_capi.cpp — C shim (include/rtiaw_host.h) over the C++ host mirror.
+#include "rtiaw_host.h"
+
+#include "rtiaw_app.hpp"
+
+using namespace rtiaw;
+
+struct RtwWorld {
+    std::unique_ptr<World> world;
+    Size2i default_size{0, 0};
+};
+
+namespace {
+thread_local std::string g_err;
+template <class F>
+int guard(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+const char* rtw_last_error(void) { return g_err.c_str(); }
+
+RtwWorld* rtw_world_create(const char* name, const char* suzanne, const char* cube, uint32_t ew, uint32_t eh, const uint8_t* ergb) {
+    RtwWorld* w = nullptr;
+    guard([&] {
+        Assets a;
+        a.suzanne_obj = suzanne ? suzanne : "";
+        a.cube_obj = cube ? cube : "";
+        a.earth_w = ew; a.earth_h = eh; a.earth_rgb8 = ergb;
+        NamedWorld nw = create_world(name ? name : "", a);
+        w = new RtwWorld{std::move(nw.world), nw.default_size};
+    });
+    return w;
+}
+
+RtwWorld* rtw_world_create_elements(uint32_t n, const uint32_t* kinds, const uint32_t* mat_of, const float* geom, uint32_t n_materials,
+                                    const RtMaterial* materials, uint32_t n_textures, const RtTexture* textures, uint32_t n_images,
+                                    const RtImage* images, const float* cam, const float* bg, const float* light) {
+    RtwWorld* w = nullptr;
+    guard([&] {
+        auto tables = std::make_shared<MaterialTable>();
+        for (uint32_t i = 0; i < n_images; ++i) {
+            ImageData im;
+            im.width = images[i].width; im.height = images[i].height;
+            im.rgb8.assign(images[i].rgb8, images[i].rgb8 + (size_t)im.width * im.height * 3);
+            tables->images.push_back(std::move(im));
+        }
+        tables->textures.assign(textures, textures + n_textures);
+        tables->materials.assign(materials, materials + n_materials);
+        std::vector<SurfaceGeometry> elems(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            const float* g = geom + 24 * (size_t)i;
+            Geometry geo;
+            if (kinds[i] == RT_GEO_SPHERE) {
+                geo = Geometry::Sphere({{g[0], g[1], g[2]}, g[3]});
+            } else if (kinds[i] == RT_GEO_RECT) {
+                RectGeometry r;
+                r.rect_plane = (RectPlane)(uint32_t)g[0]; r.dist = g[1];
+                r.r0[0] = g[2]; r.r0[1] = g[3]; r.r1[0] = g[4]; r.r1[1] = g[5];
+                geo = Geometry::Rect(r);
+            } else if (kinds[i] == RT_GEO_TRIANGLE) {
+                TriangleGeometry t;
+                for (int k = 0; k < 3; ++k) {
+                    t.positions[k] = {g[3 * k], g[3 * k + 1], g[3 * k + 2]};
+                    t.normals[k] = {g[9 + 3 * k], g[10 + 3 * k], g[11 + 3 * k]};
+                    t.texture_coords[k] = {g[18 + 2 * k], g[19 + 2 * k]};
+                }
+                geo = Geometry::Triangle(t);
+            } else {
+                throw std::invalid_argument("geometry kind outside the hot-path scope");
+            }
+            elems[i] = {geo, mat_of[i]};
+        }
+        auto world = std::make_unique<World>();
+        world->tables = tables;
+        world->hittable = std::make_shared<Scene>(std::move(elems));
+        Camera& c = world->camera;
+        c.position = {cam[0], cam[1], cam[2]};
+        c.upper_left_corner = {cam[3], cam[4], cam[5]};
+        c.unit_right = {cam[6], cam[7], cam[8]};
+        c.unit_up = {cam[9], cam[10], cam[11]};
+        c.scaled_right = {cam[12], cam[13], cam[14]};
+        c.scaled_up = {cam[15], cam[16], cam[17]};
+        c.lens_radius = cam[18];
+        c.time_interval = {cam[19], cam[20]};
+        c.shutter_pace = {cam[21], cam[22]};
+        world->background = bg[0] != 0.0f ? BackgroundColor::Sky() : BackgroundColor::Solid({bg[1], bg[2], bg[3]});
+        if (bg[0] != 0.0f) world->background.color = {bg[1], bg[2], bg[3]};
+        if (light && light[0] != 0.0f) {
+            world->has_scattering_distribution_provider = true;
+            RectGeometry& r = world->scattering_distribution_provider.rect;
+            r.rect_plane = (RectPlane)(uint32_t)light[1]; r.dist = light[2];
+            r.r0[0] = light[3]; r.r0[1] = light[4]; r.r1[0] = light[5]; r.r1[1] = light[6];
+        }
+        w = new RtwWorld{std::move(world), Size2i{0, 0}};
+    });
+    return w;
+}
+
+void rtw_world_destroy(RtwWorld* w) { delete w; }
+
+int rtw_world_info(const RtwWorld* w, uint64_t* info) {
+    return guard([&] {
+        const World& W = *w->world;
+        info[0] = W.hittable->elements.size();
+        info[1] = W.hittable->bvh.nodes.size();
+        info[2] = W.hittable->bvh.initial_index;
+        info[3] = W.hittable->bvh.depth;
+        info[4] = (uint64_t)w->default_size.width;
+        info[5] = (uint64_t)w->default_size.height;
+        info[6] = W.tables->materials.size();
+        info[7] = W.tables->textures.size();
+        info[8] = W.tables->images.size();
+        info[9] = W.has_scattering_distribution_provider ? 1 : 0;
+    });
+}
+
+int rtw_world_export(const RtwWorld* w, RtItem* items, RtBvhNode* nodes, RtMaterial* materials, RtTexture* textures,
+                     uint32_t* image_wh, float* cam, float* bg, float* light) {
+    return guard([&] {
+        const World& W = *w->world;
+        std::vector<RtItem> it;
+        std::vector<RtImage> im;
+        RtSceneDesc d = W.describe(it, im);
+        std::memcpy(items, d.items, sizeof(RtItem) * d.n_items);
+        if (d.n_nodes) std::memcpy(nodes, d.nodes, sizeof(RtBvhNode) * d.n_nodes);
+        std::memcpy(materials, d.materials, sizeof(RtMaterial) * d.n_materials);
+        if (d.n_textures) std::memcpy(textures, d.textures, sizeof(RtTexture) * d.n_textures);
+        for (uint32_t i = 0; i < d.n_images; ++i) { image_wh[2 * i] = d.images[i].width; image_wh[2 * i + 1] = d.images[i].height; }
+        std::memcpy(cam, &d.camera, sizeof(float) * 23);
+        bg[0] = d.background_is_sky ? 1.0f : 0.0f;
+        bg[1] = d.background_rgb[0]; bg[2] = d.background_rgb[1]; bg[3] = d.background_rgb[2];
+        light[0] = d.has_light ? 1.0f : 0.0f;
+        light[1] = (float)d.light_plane; light[2] = d.light_dist;
+        light[3] = d.light_r0[0]; light[4] = d.light_r0[1]; light[5] = d.light_r1[0]; light[6] = d.light_r1[1];
+    });
+}
+
+const uint8_t* rtw_world_image(const RtwWorld* w, uint32_t index) { return w->world->tables->images.at(index).rgb8.data(); }
+
+int rtw_world_device(RtwWorld* w, int device, RtScene** out_scene) {
+    return guard([&] { *out_scene = w->world->device(device); });
+}
+
+int rtw_render(RtwWorld* w, int32_t width, int32_t height, uint64_t thread_count, uint64_t spp, int32_t max_depth, uint32_t render_mode,
+               uint64_t seed, int device, float* out_rgb, RtStats* out_stats) {
+    return guard([&] {
+        std::vector<Color> px = render(Size2i{width, height}, thread_count, spp, max_depth, *w->world, (RenderMode)render_mode, seed, out_stats, device);
+        std::memcpy(out_rgb, px.data(), px.size() * sizeof(Color));
+    });
+}
+
+int rtw_hit(RtwWorld* w, uint64_t n, const float* org, const float* dirs, float t_min, float t_max, int device, uint32_t* hit_id,
+            float* t, float* normal, uint8_t* front_face, float* uv) {
+    return guard([&] {
+        if (rt_trace(w->world->device(device), org, dirs, n, t_min, t_max, hit_id, t, normal, front_face, uv) != RT_OK) throw_rt("rt_trace");
+    });
+}
+
+int rtw_load_obj(const char* path, uint64_t* n_tris, float* out24, uint64_t cap) {
+    return guard([&] {
+        std::vector<TriangleGeometry> tris = load_obj_file(path);
+        *n_tris = tris.size();
+        for (size_t i = 0; i < tris.size() && i < cap; ++i) {
+            RtItem it;
+            Geometry::Triangle(tris[i]).write(it);
+            std::memcpy(out24 + 24 * i, it.geom, sizeof(it.geom));
+        }
+    });
+}
+
+}  // extern "C"

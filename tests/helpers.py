@@ -1,0 +1,212 @@
+"""Shared test helpers: synthetic scenes, ray sets (primary / random / adversarial) and comparisons."""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+MISS = 0xFFFFFFFF
+
+
+def f2u(x):
+    return np.ascontiguousarray(x, F32).view(np.uint32)
+
+
+def unit_rows(v):
+    v = np.asarray(v, np.float64)
+    return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(F32)
+
+
+def simple_camera(pos=(0.0, 1.0, 6.0), at=(0.0, 0.0, 0.0), fov=50.0, aspect=0.75, lens_radius=0.0, focus=1.0):
+    """Camera fields as Camera::build()...build() computes them (float32 numpy restatement for test scenes)."""
+    pos, at = np.array(pos, F32), np.array(at, F32)
+    up = np.array([0, 1, 0], F32)
+    fwd = at - pos
+    h = F32(np.tan(F32(fov) * F32(np.pi / 180.0) * F32(0.5)))
+    vw, vh = F32(2.0) * h, F32(2.0) * h * F32(aspect)
+
+    def unit(a):
+        return a * (F32(1.0) / F32(np.sqrt(np.dot(a, a).astype(F32))))
+    right = unit(np.cross(fwd, up).astype(F32))
+    upv = unit(np.cross(right, fwd).astype(F32))
+    sfwd = fwd * (F32(focus) / F32(np.sqrt(np.dot(fwd, fwd).astype(F32))))
+    ulc = F32(focus) * (right * (vw * F32(-0.5)) + upv * (vh * F32(0.5))) + sfwd
+    cam = np.zeros(23, F32)
+    cam[0:3], cam[3:6], cam[6:9], cam[9:12] = pos, ulc, right, upv
+    cam[12:15], cam[15:18] = right * (F32(focus) * vw), upv * (F32(focus) * vh)
+    cam[18] = lens_radius
+    return cam
+
+
+def solid_tex(rgb):
+    return [0, MISS] + list(np.array(rgb, F32).view(np.uint32))
+
+
+def mat(kind, tex, param=0.0):
+    return [kind, tex, int(np.array([param], F32).view(np.uint32)[0])]
+
+
+def random_scene(seed, n_spheres=20, n_tris=30, n_rects=4, extent=4.0, with_light=False, image_tex=None):
+    """Random mixed scene in the flat element layout (kinds, item_mat, geom, mats, texs, images, cam, bg, light)."""
+    rng = np.random.default_rng(seed)
+    kinds, geom = [], []
+    for _ in range(n_spheres):
+        g = np.zeros(24, F32)
+        g[0:3] = rng.uniform(-extent, extent, 3)
+        g[3] = rng.uniform(0.1, 0.8)
+        kinds.append(0); geom.append(g)
+    for _ in range(n_rects):
+        g = np.zeros(24, F32)
+        g[0] = rng.integers(0, 3)
+        g[1] = rng.uniform(-extent, extent)
+        a, b = np.sort(rng.uniform(-extent, extent, 2)); c, d = np.sort(rng.uniform(-extent, extent, 2))
+        g[2:6] = [a, b + 0.1, c, d + 0.1]
+        kinds.append(1); geom.append(g)
+    for _ in range(n_tris):
+        g = np.zeros(24, F32)
+        p0 = rng.uniform(-extent, extent, 3)
+        g[0:3] = p0; g[3:6] = p0 + rng.uniform(-1, 1, 3); g[6:9] = p0 + rng.uniform(-1, 1, 3)
+        n = np.cross(g[3:6] - g[0:3], g[6:9] - g[0:3]); n = n / (np.linalg.norm(n) + 1e-20)
+        for k in range(3):
+            g[9 + 3 * k: 12 + 3 * k] = n + rng.normal(0, 0.1, 3)   # non-unit, varying vertex normals (Q8)
+        g[18:24] = rng.uniform(0, 1, 6)
+        kinds.append(2); geom.append(g)
+    order = rng.permutation(len(kinds))
+    kinds = np.array(kinds, np.uint32)[order]
+    geom = np.array(geom, F32)[order]
+    texs = [solid_tex(rng.uniform(0.2, 0.9, 3)) for _ in range(4)] + [solid_tex([4.0, 4.0, 4.0])]
+    images = []
+    if image_tex is not None:
+        texs.append([1, 0, 0, 0, 0]); images.append(image_tex)
+    mats = [mat(0, 0), mat(0, 1), mat(1, 2, 0.0), mat(1, 3, 0.3), mat(2, MISS, 1.5), mat(3, 4)]
+    if image_tex is not None:
+        mats.append(mat(0, 5))
+    item_mat = rng.integers(0, len(mats), len(kinds)).astype(np.uint32)
+    cam = simple_camera(pos=(0.5, 1.0, 3.0 * extent), at=(0, 0, 0), fov=50.0, aspect=0.75)
+    bg = np.array([1, 0, 0, 0], F32)
+    light = np.zeros(7, F32)
+    if with_light:
+        ridx = np.nonzero(kinds == 1)[0]
+        if len(ridx):
+            g = geom[ridx[0]]
+            item_mat[ridx[0]] = 5
+            light = np.array([1, g[0], g[1], g[2], g[3], g[4], g[5]], F32)
+    return dict(kinds=kinds, item_mat=item_mat, geom=geom, mats=np.array(mats, np.uint32), texs=np.array(texs, np.uint32),
+                images=images, cam=cam, bg=bg, light=light)
+
+
+def scene_bounds(fs):
+    if len(fs.nodes_box):
+        lo, hi = fs.nodes_box[0, :3].astype(np.float64), fs.nodes_box[0, 3:].astype(np.float64)
+    else:
+        lo, hi = np.array([-2.0, -2, -2]), np.array([2.0, 2, 2])
+    return np.maximum(lo, -60.0), np.minimum(hi, 60.0)
+
+
+def random_rays(fs, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = scene_bounds(fs)
+    pad = 0.25 * (hi - lo)
+    org = rng.uniform(lo - pad, hi + pad, size=(n, 3)).astype(F32)
+    return org, unit_rows(rng.normal(size=(n, 3)))
+
+
+def adversarial_rays(fs, n_per_class, seed):
+    """Rays aimed at the places where acceptance rules and ties are decided: triangle vertices / edges, sphere limbs,
+    rect borders and corners, exact axis-parallel directions (zero components -> inf / NaN slabs), origins lying exactly
+    on node-box planes, origins on surfaces."""
+    rng = np.random.default_rng(seed)
+    lo, hi = scene_bounds(fs)
+    pad = 0.5 * (hi - lo)
+    orgs, dirs = [], []
+
+    def aim(targets):
+        targets = np.asarray(targets, np.float64)
+        if len(targets) == 0:
+            return
+        idx = rng.integers(0, len(targets), n_per_class)
+        o = rng.uniform(lo - pad, hi + pad, size=(n_per_class, 3))
+        d = targets[idx] - o
+        ok = np.linalg.norm(d, axis=1) > 1e-6
+        orgs.append(o[ok].astype(F32)); dirs.append(unit_rows(d[ok]))
+
+    tri = fs.geom[fs.kinds == 2]
+    if len(tri):
+        p = tri[:, :9].reshape(-1, 3, 3).astype(np.float64)
+        aim(p.reshape(-1, 3))                                    # vertices
+        aim(0.5 * (p[:, 0] + p[:, 1])); aim(0.5 * (p[:, 1] + p[:, 2]))  # edge midpoints
+        w = rng.dirichlet([1, 1, 1], len(p))
+        aim((p * w[:, :, None]).sum(1))                          # interior
+    sph = fs.geom[fs.kinds == 0]
+    if len(sph):
+        c, r = sph[:, :3].astype(np.float64), sph[:, 3:4].astype(np.float64)
+        u = rng.normal(size=c.shape); u /= np.linalg.norm(u, axis=1, keepdims=True)
+        aim(c + r * u)                                           # surface points (limb for some origins)
+        # exact tangents: origin o, tangent point t with (t-c).(t-o) = 0
+        idx = rng.integers(0, len(c), n_per_class)
+        o = rng.uniform(lo - pad, hi + pad, size=(n_per_class, 3))
+        oc = o - c[idx]; dist = np.linalg.norm(oc, axis=1, keepdims=True)
+        ok = (dist[:, 0] > r[idx, 0] * 1.01)
+        w_ = oc / dist
+        v = np.cross(w_, rng.normal(size=w_.shape)); v /= np.linalg.norm(v, axis=1, keepdims=True) + 1e-30
+        cosb = r[idx] / dist
+        tpt = c[idx] + r[idx] * (cosb * w_ + np.sqrt(np.maximum(0, 1 - cosb ** 2)) * v)
+        d = tpt - o
+        orgs.append(o[ok].astype(F32)); dirs.append(unit_rows(d[ok]))
+    rect = fs.geom[fs.kinds == 1]
+    if len(rect):
+        pts = []
+        for g in rect:
+            plane = int(g[0]); a0, a1, n = [(0, 1, 2), (0, 2, 1), (1, 2, 0)][plane]
+            for u_ in (g[2], g[3], 0.5 * (g[2] + g[3])):
+                for v_ in (g[4], g[5], 0.5 * (g[4] + g[5])):
+                    q = np.zeros(3); q[a0], q[a1], q[n] = u_, v_, g[1]
+                    pts.append(q)
+        aim(pts)
+    # exact axis-parallel rays (zero direction components)
+    for ax in range(3):
+        for sgn in (-1.0, 1.0):
+            o = rng.uniform(lo - pad, hi + pad, size=(n_per_class // 4 + 1, 3)).astype(F32)
+            d = np.zeros_like(o); d[:, ax] = sgn
+            orgs.append(o); dirs.append(d.astype(F32))
+    # origins exactly on node-box planes with a zero direction component on that axis (0/0 = NaN slabs)
+    if len(fs.nodes_box):
+        m = n_per_class // 2 + 1
+        idx = rng.integers(0, len(fs.nodes_box), m)
+        ax = rng.integers(0, 3, m); side = rng.integers(0, 2, m)
+        o = rng.uniform(lo, hi, size=(m, 3)).astype(F32)
+        o[np.arange(m), ax] = fs.nodes_box[idx, ax + 3 * side]
+        d = rng.normal(size=(m, 3)); d[np.arange(m), ax] = 0.0
+        orgs.append(o); dirs.append(unit_rows(d + 1e-30))
+        dirs[-1][np.arange(m), ax] = 0.0
+    return np.concatenate(orgs), np.concatenate(dirs)
+
+
+def compare_hits(got, ref, rel_tol=1e-5):
+    """Hit ids bit-exact; t and normals within rel_tol relative (the north-star bound); returns a dict of counts."""
+    ids_bad = int((got["hit_id"] != ref["hit_id"]).sum())
+    both = (ref["hit_id"] != MISS) & (got["hit_id"] == ref["hit_id"])
+    t_bits = int((f2u(got["t"][both]) != f2u(ref["t"][both])).sum())
+    n_bits = int((f2u(got["normal"][both]) != f2u(ref["normal"][both])).any(axis=1).sum())
+    with np.errstate(invalid="ignore", divide="ignore"):
+        t_rel = np.abs(got["t"][both] - ref["t"][both]) / np.maximum(np.abs(ref["t"][both]), 1e-30)
+        nscale = np.maximum(np.linalg.norm(ref["normal"][both], axis=1, keepdims=True), 1e-30)
+        n_rel = np.abs(got["normal"][both] - ref["normal"][both]) / nscale
+    return dict(n=len(ref["hit_id"]), hits=int(both.sum()), id_mismatch=ids_bad, t_bit_mismatch=t_bits, normal_bit_mismatch=n_bits,
+                t_rel_max=float(t_rel.max()) if both.any() else 0.0, n_rel_max=float(n_rel.max()) if both.any() else 0.0,
+                ff_mismatch=int((got["front_face"][both] != ref["front_face"][both]).sum()),
+                uv_abs_max=float(np.abs(got["uv"][both] - ref["uv"][both]).max()) if both.any() else 0.0)
+
+
+def assert_hits_match(got, ref, rel_tol=1e-5):
+    r = compare_hits(got, ref, rel_tol)
+    assert r["id_mismatch"] == 0, r
+    assert r["t_rel_max"] <= rel_tol and r["n_rel_max"] <= rel_tol, r
+    assert r["ff_mismatch"] == 0, r
+    assert r["uv_abs_max"] <= 2e-6, r   # device acosf / atan2f vs glibc: a few ulp of uv in [0, 1]
+    return r
+
+
+def images_equal_bits(a, b):
+    a, b = np.ascontiguousarray(a, F32), np.ascontiguousarray(b, F32)
+    na, nb = np.isnan(a), np.isnan(b)
+    return bool(np.array_equal(na, nb) and np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb]))

@@ -1,0 +1,151 @@
+"""Host-side logic of the product (no GPU): the C++ mirror of the reference API must flatten scenes exactly like the
+oracle's literal restatement (element order = hit ids, baked transforms, BVH topology and boxes, tables, camera), and
+the C ABI must load, export every declared symbol and fail loudly without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import raytracinginaweekend_b200 as rb
+from raytracinginaweekend_b200 import _cabi, api, build, dist
+from helpers import F32, random_scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIELDS = ["kinds", "item_mat", "geom", "nodes_box", "nodes_lra", "mats", "texs", "cam", "bg", "light"]
+
+
+def same_flat(a, b):
+    for f in FIELDS:
+        x, y = getattr(a, f), getattr(b, f)
+        assert x.shape == y.shape, f
+        assert np.array_equal(np.ascontiguousarray(x).view(np.uint32), np.ascontiguousarray(y).view(np.uint32)), f
+    assert a.root == b.root and a.depth == b.depth
+    assert len(a.images) == len(b.images) and all(np.array_equal(i, j) for i, j in zip(a.images, b.images))
+
+
+WORLDS = ["demo:suzanne", "demo:final_scene1", "demo:simple_plane", "demo:earth_mapped", "demo:defocus_blur",
+          "config:c1", "config:c2", "config:c3", "config:c5"]
+
+
+@pytest.mark.parametrize("name", WORLDS)
+def test_world_flatten_matches_oracle(name, oracle_world):
+    w = rb.World.named(name)
+    same_flat(w.export(), oracle_world(name).export())
+    assert (w.default_size.width, w.default_size.height) == oracle_world(name).default_size
+
+
+def test_million_triangle_world_flatten_matches_oracle(oracle):
+    w = rb.World.named("config:c4")
+    o = oracle.OracleWorld.named("config:c4")
+    assert w.n_items == 999_945 and w.n_nodes == 999_944
+    same_flat(w.export(), o.export())
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_bvh_build_matches_oracle_on_random_scenes(seed, oracle):
+    sc = random_scene(seed, n_spheres=5 + 13 * seed, n_tris=40 * seed, n_rects=seed, with_light=seed % 2 == 1)
+    same_flat(rb.World.from_elements(**sc).export(), oracle.OracleWorld.from_flat(**sc).export())
+
+
+def test_bvh_ties_are_stable(oracle):
+    """Equal sort keys: the reference uses a stable sort, so ties keep element order (affects hit ids on coincident geometry)."""
+    sc = random_scene(1, n_spheres=40, n_tris=0, n_rects=0)
+    sc["geom"][:, 0] = 1.0
+    sc["geom"][::2, 1] = 2.0
+    sc["geom"][:, 3] = 0.5
+    same_flat(rb.World.from_elements(**sc).export(), oracle.OracleWorld.from_flat(**sc).export())
+
+
+def test_obj_loader_matches_oracle(oracle):
+    for name, n in (("suzanne.obj", 968), ("cube.obj", 12)):
+        tris = rb.load_obj_mesh(os.path.join(api.ASSETS, name))
+        cnt = np.zeros(1, np.uint64)
+        ref = np.zeros((n, 24), F32)
+        oracle.lib().orc_obj_load(os.path.join(api.ASSETS, name).encode(), oracle._p(cnt), oracle._p(ref), n)
+        assert tris.shape == (n, 24) and np.array_equal(tris.view(np.uint32), ref.view(np.uint32))
+
+
+def test_out_of_scope_worlds_are_rejected():
+    for name in ("demo:cornell_box", "demo:final_scene2", "demo:nope"):
+        with pytest.raises(RuntimeError):
+            rb.World.named(name)
+
+
+def test_gamma_matches_oracle(oracle):
+    rng = np.random.default_rng(0)
+    v = np.concatenate([rng.uniform(-0.5, 2.0, 3000), [np.nan, 0.0, 1.0, np.inf, -np.inf, 0.25]]).astype(F32).reshape(-1, 3)
+    assert np.array_equal(rb.to_rgb8_gamma2(v), oracle.to_rgb8_gamma2(v))
+
+
+# ---------------------------------------------------------------- C ABI surface
+def declared_symbols(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(rt_[a-z0-9_]+|rtw_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    L = _cabi.lib()
+    syms = declared_symbols("b200rt.h")
+    assert set(syms) == set(_cabi.EXPORTED), (syms, _cabi.EXPORTED)
+    for s in syms:
+        assert getattr(L, s) is not None
+    H = api.host_lib()
+    hs = declared_symbols("rtiaw_host.h")
+    assert len(hs) >= 10
+    for s in hs:
+        assert getattr(H, s) is not None
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_cabi.RtItem) == 104 and C.sizeof(_cabi.RtBvhNode) == 36
+    assert C.sizeof(_cabi.RtMaterial) == 12 and C.sizeof(_cabi.RtTexture) == 20
+    assert C.sizeof(_cabi.RtCamera) == 92 and C.sizeof(_cabi.RtRenderParams) == 40
+
+
+def test_native_libraries_are_in_tree():
+    assert os.path.dirname(build.LIB_CUDA) == os.path.join(ROOT, "raytracinginaweekend_b200")
+    assert os.path.exists(build.LIB_CUDA) and os.path.exists(build.LIB_HOST)
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a GPU every compute entry point must fail loudly (RT_ECUDA), never compute on the CPU."""
+    try:
+        n = _cabi.device_count()
+    except _cabi.B200RTError as e:
+        assert e.code == -2
+        n = 0
+    if n > 0:
+        pytest.skip("a CUDA device is present")
+    sc = random_scene(0)
+    w = rb.World.from_elements(**sc)
+    with pytest.raises(RuntimeError, match="rt_scene_create"):
+        rb.render(rb.Size2i(8, 8), 1, 1, 5, w)
+    with pytest.raises(RuntimeError):
+        w.hit(np.zeros((1, 3), F32), np.array([[0, 0, -1]], F32))
+    fs = w.export()
+    with pytest.raises(_cabi.B200RTError) as ei:
+        _cabi.DeviceScene.from_flat(fs)
+    assert ei.value.code == -2
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may import, include, link or load it."""
+    pkg = os.path.join(ROOT, "raytracinginaweekend_b200")
+    bad = re.compile(r"(^\s*(import|from)\s+oracle\b|#\s*include\s*[\"<][^\">]*oracle|liboracle|oracle/_build|oracle\.binding)", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not bad.search(txt), f
+
+
+# ---------------------------------------------------------------- lane split (rendering.rs:222-237)
+def test_lane_partition():
+    assert dist.n_tasks(8, 3) == 3 and dist.n_tasks(4, 64) == 4
+    lanes = [list(range(*dist.lane_partition(8, 64, r, 4)[:1], dist.n_tasks(8, 64), 4)) for r in range(4)]
+    assert sorted(sum(lanes, [])) == list(range(8))
+    assert [dist.lane_samples(4, 10, i) for i in range(4)] == [3, 3, 2, 2]
+    assert dist.lane_partition(2, 64, 3, 4)[2] == 0      # more ranks than lanes: this rank owns nothing

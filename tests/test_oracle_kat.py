@@ -1,0 +1,285 @@
+"""Known-answer tests that pin the ORACLE (the reference ships no tests: parity is otherwise unpinned).
+
+Analytic cases need no second implementation: closed-form ray/primitive answers, the acceptance rules quoted from the
+reference source, structural facts of the BVH builder and the OBJ loader, published Philox vectors.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from helpers import F32, MISS, mat, simple_camera, solid_tex
+
+INF = float("inf")
+
+
+def world_of(oracle, kinds, geoms, light=None):
+    geom = np.zeros((len(kinds), 24), F32)
+    for i, g in enumerate(geoms):
+        geom[i, :len(g)] = g
+    return oracle.OracleWorld.from_flat(np.array(kinds, np.uint32), np.zeros(len(kinds), np.uint32), geom, np.array([mat(0, 0)], np.uint32),
+                                        np.array([solid_tex([0.5, 0.5, 0.5])], np.uint32), [], simple_camera(), np.array([1, 0, 0, 0], F32),
+                                        np.zeros(7, F32) if light is None else light)
+
+
+def trace1(w, o, d, tmin=0.001, tmax=INF):
+    r = w.trace(np.array([o], F32), np.array([d], F32), tmin, tmax)
+    return {k: v[0] for k, v in r.items()}
+
+
+# ---------------------------------------------------------------- sphere (src/lib/hittable/sphere_geometry.rs:21-54)
+def test_sphere_front_inside_behind_tangent(oracle):
+    w = world_of(oracle, [0], [[0, 0, -5, 1]])
+    h = trace1(w, [0, 0, 0], [0, 0, -1])
+    assert h["hit_id"] == 0 and h["t"] == F32(4.0) and h["front_face"] == 1 and tuple(h["normal"]) == (0.0, 0.0, 1.0)
+    h = trace1(w, [0, 0, -5], [0, 0, -1])          # from the centre: near root < t_min, far root accepted, normal flipped
+    assert h["t"] == F32(1.0) and h["front_face"] == 0 and tuple(h["normal"]) == (-0.0, -0.0, 1.0)
+    assert trace1(w, [0, 0, 0], [0, 0, 1])["hit_id"] == MISS   # sphere behind the ray
+    h = trace1(w, [1, 0, 0], [0, 0, -1])            # exact tangent: disc == 0 is accepted (`disc < 0` rejects)
+    assert h["hit_id"] == 0 and h["t"] == F32(5.0)
+    assert trace1(w, [1.001, 0, 0], [0, 0, -1])["hit_id"] == MISS
+    # "phantom" hit: this ray passes OUTSIDE the sphere's AABB (x = 1.0000002 > 1), but |oc|^2 rounds to 26 in f32, disc == 0 and
+    # the reference accepts it.  A tighter node test must keep such rays (the guard band of the GPU's tight cull exists for this).
+    assert trace1(w, [1.0000002, 0, 0], [0, 0, -1])["hit_id"] == 0
+    # half-open range [t_min, t_max): t == t_max is rejected, t == t_min accepted
+    assert trace1(w, [0, 0, 0], [0, 0, -1], 0.001, 4.0)["hit_id"] == MISS
+    assert trace1(w, [0, 0, 0], [0, 0, -1], 4.0, 5.0)["t"] == F32(4.0)
+
+
+def test_sphere_uv_matches_to_radian(oracle):
+    w = world_of(oracle, [0], [[0, 0, 0, 2]])
+    h = trace1(w, [0, 0, 5], [0, 0, -1])           # hits (0,0,2): n = (0,0,1): theta = acos(0), phi = atan2(-1, 0) + pi
+    assert abs(h["uv"][0] - (math.atan2(-1.0, 0.0) + math.pi) / (2 * math.pi)) < 1e-6
+    assert abs(h["uv"][1] - 0.5) < 1e-6
+
+
+# ---------------------------------------------------------------- rect (rect_geometry.rs:33-59)
+def test_rect_closed_borders_and_uv_quirk(oracle):
+    w = world_of(oracle, [1], [[0, -3, -1, 1, -2, 3]])     # XY plane z=-3, x in [-1,1], y in [-2,3]
+    h = trace1(w, [1, 3, 0], [0, 0, -1])                   # exactly on the corner: closed interval test accepts
+    assert h["hit_id"] == 0 and h["t"] == F32(3.0)
+    assert trace1(w, [1.0000001, 3, 0], [0, 0, -1])["hit_id"] == MISS
+    h = trace1(w, [0.5, 0.5, 0], [0, 0, -1])
+    assert h["uv"][0] == F32((0.5 + 1) / 2.0)
+    assert h["uv"][1] == F32(F32(0.5 + 2) / F32(1 - (-2)))      # Q5: divides by (r0.hi - r1.lo), not (r1.hi - r1.lo)
+    assert tuple(h["normal"]) == (0.0, 0.0, 1.0) and h["front_face"] == 0   # raw normal is -axis; seen from +z it is flipped
+    h = trace1(w, [0.5, 0.5, -6], [0, 0, 1])
+    assert tuple(h["normal"]) == (0.0, 0.0, -1.0) and h["front_face"] == 1
+    assert trace1(w, [0, 0, 0], [1, 0, 0])["hit_id"] == MISS   # parallel: t = -3/0 = -inf
+
+
+# ---------------------------------------------------------------- triangle (triangle_geometry.rs:13-45)
+def test_triangle_open_barycentrics_and_blended_normal(oracle):
+    tri = [0, 0, -2, 2, 0, -2, 0, 2, -2,   0, 0, 1, 0, 0, 2, 0, 0, 4,   0, 0, 1, 0, 0, 1]
+    w = world_of(oracle, [2], [tri])
+    h = trace1(w, [0.5, 0.5, 0], [0, 0, -1])
+    assert h["hit_id"] == 0 and h["t"] == F32(2.0)
+    w1, w2 = 0.25, 0.25
+    assert abs(h["normal"][2] - ((1 - w1 - w2) * 1 + w1 * 2 + w2 * 4)) < 1e-6   # Q8: blended, NOT re-normalised
+    assert abs(h["uv"][0] - w1) < 1e-6 and abs(h["uv"][1] - w2) < 1e-6
+    for o in ([0, 0, 0], [2, 0, 0], [0, 2, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]):      # vertices and edges: strict 0<w<1 rejects
+        assert trace1(w, o, [0, 0, -1])["hit_id"] == MISS, o
+    d = np.array([1.0, 0.0, -0.00009]); d /= np.linalg.norm(d)                       # |d.n| <= 1e-4: treated as parallel
+    assert trace1(w, [-5, 0.5, -2 + 5 * 0.00009], d)["hit_id"] == MISS
+
+
+# ---------------------------------------------------------------- Aabb::hit_cond (aabb.rs:65-78)
+def test_hit_cond_is_per_axis_independent(oracle):
+    L = oracle.lib()
+    box = np.array([0, 0, 0, 1, 1, 1], F32)
+
+    def hc(b, o, d, t0=0.001, t1=INF):
+        return L.orc_aabb_hit_cond(oracle._p(np.array(b, F32)), oracle._p(np.array(o, F32)), oracle._p(np.array(d, F32)), t0, t1)
+    s = 1 / math.sqrt(2)
+    assert hc(box, [0.5, 0.5, 5], [0, 0, -1]) == 1
+    assert hc(box, [-1, 4, 0.5], [s, -s, 0]) == 1      # Q1: true slab test misses (x and y intervals are disjoint), the reference passes
+    assert hc(box, [0.5, 0.5, 5], [0, 0, 1]) == 0      # behind
+    assert hc([0, 0, 0, 1, 0, 1], [0.5, 1, 0.5], [0, -1, 0]) == 0   # zero-thickness box is never entered (t_max <= t_min)
+    assert hc(box, [0.5, 0.5, 5], [0, 0, -1], 0.001, 4.0) == 0      # range end <= entry distance
+    # origin exactly on a slab plane with a zero direction component: 0/0 = NaN meets minmax's `a < b` (false -> swapped) and
+    # NaN-ignoring max/min; hand-evaluated from aabb.rs:65-78:
+    assert hc(box, [0, 0.5, 5], [0, 0, -1]) == 0       # (NaN, +inf) -> t0 = +inf, t1 = NaN -> t_max = end = inf <= t_min = inf
+    assert hc(box, [1, 0.5, 5], [0, 0, -1]) == 0       # (-inf, NaN) -> t0 = NaN, t1 = -inf -> t_max = -inf
+    assert hc(box, [0, 0.5, 5], [-0.0, 0, -1]) == 1    # (NaN, -inf) -> t0 = -inf, t1 = NaN -> [t_min, end) survives
+    assert hc(box, [0.5, 0.5, 5], [0.0, 0, -1]) == 1   # strictly inside the slab: (-inf, +inf)
+
+
+# ---------------------------------------------------------------- BVH builder (hittable.rs:360-427)
+def test_bvh_topology(oracle):
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 7, 64, 257):
+        g = np.zeros((n, 24), F32)
+        g[:, :3] = rng.uniform(-5, 5, (n, 3)); g[:, 3] = 0.3
+        w = world_of(oracle, [0] * n, list(g))
+        fs = w.export()
+        assert len(fs.nodes_lra) == n - 1
+        if n == 1:
+            assert fs.root == (0x80000000 | 0)
+            continue
+        assert fs.root == 0
+        # pre-order numbering, axis of a child = (parent axis + child size) % 3, leaves partition the items
+        seen = []
+
+        def walk(ref, axis_expected, size_expected):
+            if ref & 0x80000000:
+                seen.append(ref & 0x7FFFFFFF)
+                return 1
+            l, r, axis = fs.nodes_lra[ref]
+            assert axis == axis_expected
+            sizes = []
+            for c in (l, r):
+                if not (c & 0x80000000):
+                    assert c > ref
+            nl = count(l); nr = count(r)
+            assert nl == (nl + nr) // 2
+            walk(l, (axis + nl) % 3, nl); walk(r, (axis + nr) % 3, nr)
+            return nl + nr
+
+        def count(ref):
+            if ref & 0x80000000:
+                return 1
+            return count(fs.nodes_lra[ref][0]) + count(fs.nodes_lra[ref][1])
+        walk(0, 0, n)
+        assert sorted(seen) == list(range(n))
+        # node boxes are the union of the leaf boxes below them
+        def box(ref):
+            if ref & 0x80000000:
+                c = g[ref & 0x7FFFFFFF]
+                return c[:3] - c[3], c[:3] + c[3]
+            (a0, a1), (b0, b1) = box(fs.nodes_lra[ref][0]), box(fs.nodes_lra[ref][1])
+            lo, hi = np.minimum(a0, b0), np.maximum(a1, b1)
+            assert np.array_equal(fs.nodes_box[ref, :3], lo) and np.array_equal(fs.nodes_box[ref, 3:], hi)
+            return lo, hi
+        box(0)
+
+
+def test_closest_hit_and_tie_rule(oracle):
+    # two coincident spheres: equal t -> the FIRST VISITED wins (half-open range), visit order = child order by sign of d[axis]
+    w = world_of(oracle, [0, 0], [[0, 0, -5, 1], [0, 0, -5, 1]])
+    assert trace1(w, [0, 0, 0], [0, 0, -1])["hit_id"] == 1     # d.x == 0 -> not > 0 -> right child (item 1) first
+    d = np.array([1e-3, 0, -1.0]); d /= np.linalg.norm(d)
+    assert trace1(w, [-5e-3, 0, 0], d)["hit_id"] == 0          # d.x > 0 -> left child (item 0) first
+    # nearer of two separated spheres regardless of order
+    w = world_of(oracle, [0, 0], [[0, 0, -9, 1], [0, 0, -5, 1]])
+    assert trace1(w, [0, 0, 0], [0, 0, -1])["hit_id"] == 1
+    assert trace1(w, [0, 0, -20], [0, 0, 1])["hit_id"] == 0
+
+
+# ---------------------------------------------------------------- RNG restatements
+def _xoroshiro128pp(s0, s1):
+    M = (1 << 64) - 1
+    rotl = lambda x, k: ((x << k) | (x >> (64 - k))) & M
+    while True:
+        r = (rotl((s0 + s1) & M, 17) + s0) & M
+        s1 ^= s0
+        s0 = rotl(s0, 49) ^ s1 ^ ((s1 << 21) & M)
+        s1 = rotl(s1, 28)
+        yield r
+
+
+def test_scene_rng_matches_published_xoroshiro128pp(oracle):
+    u = np.zeros(4, np.uint64); f = np.zeros(4, F32)
+    oracle.lib().orc_rng_kat(oracle._p(u), oracle._p(f))
+    g = _xoroshiro128pp(0x0807060504030201, 0x100F0E0D0C0B0A09)   # seed bytes 1..16, little endian (src/app/main.rs:24)
+    exp = [next(g) for _ in range(4)]
+    assert [int(x) for x in u] == exp
+    assert [float(x) for x in f] == [((e & 0xFFFFFFFF) >> 8) * 2.0 ** -24 for e in exp]
+
+
+def test_philox_known_answers(oracle):
+    # Random123 kat_vectors, philox4x32 with 10 rounds
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in kat:
+        out = np.zeros(4, np.uint32)
+        oracle.lib().orc_philox(key[0], key[1], ctr[0], ctr[1], ctr[2], ctr[3], oracle._p(out))
+        assert tuple(int(x) for x in out) == exp
+
+
+def test_replay_sampler_math_accuracy(oracle):
+    out = np.zeros(3, F32)
+    for u in np.linspace(0, 0.999999, 997):
+        oracle.lib().orc_probe_math(float(F32(u)), oracle._p(out))
+        assert abs(out[0] - math.sin(2 * math.pi * float(F32(u)))) < 4e-7
+        assert abs(out[1] - math.cos(2 * math.pi * float(F32(u)))) < 4e-7
+        assert abs(out[2] - float(F32(u)) ** (1 / 3)) < 3e-7
+
+
+# ---------------------------------------------------------------- OBJ ingest (src/app/obj_loader.rs, Q4)
+def test_obj_loader_fan_quirk(oracle):
+    def load(name):
+        n = np.zeros(1, np.uint64)
+        path = os.path.join(oracle.ASSETS, name).encode()
+        oracle.lib().orc_obj_load(path, oracle._p(n), None, 0)
+        out = np.zeros((int(n[0]), 24), F32)
+        oracle.lib().orc_obj_load(path, oracle._p(n), oracle._p(out), int(n[0]))
+        return out
+    suz = load("suzanne.obj")
+    assert len(suz) == 968                                     # 32 triangles + 468 quads -> 32 + 2*468
+    broken = np.all(suz[:, 3:6] == 0, axis=1) & np.all(suz[:, 12:15] == 0, axis=1)
+    assert int(broken.sum()) == 500                            # first triangle of every face: vertex 1 = ORIGIN, normal 1 = 0
+    cube = load("cube.obj")
+    assert len(cube) == 12 and int((np.all(cube[:, 3:6] == 0, axis=1)).sum()) == 6
+    assert np.all(cube[:, 18:24] == 0)                         # a//c references carry no uv
+    # first face "f 1//1 2//1 4//1 3//1": triangles (v1, ORIGIN, v4) and (v1, v4, v3)
+    assert tuple(cube[0, 0:3]) == (-1, -1, 1) and tuple(cube[0, 6:9]) == (-1, 1, -1)
+    assert tuple(cube[1, 0:3]) == (-1, -1, 1) and tuple(cube[1, 3:6]) == (-1, 1, -1) and tuple(cube[1, 6:9]) == (-1, -1, -1)
+
+
+# ---------------------------------------------------------------- render driver (src/lib/rendering.rs)
+def test_split_work_tasks(oracle):
+    def split(spp, t):
+        out = np.zeros(64, np.uint64)
+        n = oracle.lib().orc_split_work_tasks(spp, t, oracle._p(out), 64)
+        return [int(x) for x in out[:n]]
+    assert split(10, 4) == [3, 3, 2, 2]
+    assert split(8, 8) == [1] * 8
+    assert split(3, 8) == [1, 1, 1]          # tasks with zero samples are dropped
+    assert split(7, 1) == [7]
+
+
+def test_merge_planes_order_and_weights(oracle, oracle_world):
+    w = oracle_world("demo:defocus_blur")
+    full, _ = w.render(24, 16, 7, 50, 3, 11, "replay")
+    planes = [w.render_planes(24, 16, 7, 50, 3, 11, "replay", i, 3)[0] for i in range(3)]
+    # merge_planes (rendering.rs:239-252): last plane first, then ascending, then * 1/len — equal weights although the lanes
+    # got 3, 2, 2 samples (Q12)
+    exp = ((planes[2] + planes[0]) + planes[1]) * F32(1.0 / 3.0)
+    assert np.array_equal(exp.view(np.uint32), full.view(np.uint32))
+
+
+def test_gamma_quantisation(oracle):
+    v = np.array([[0.0, 1.0, 0.25], [np.nan, -1.0, 4.0], [0.999, 1e-6, 0.5]], F32)
+    out = oracle.to_rgb8_gamma2(v)
+    assert out.tolist() == [[0, 255, 128], [0, 0, 255], [int(math.sqrt(F32(0.999)) * 256), 0, 181]]
+
+
+def test_white_furnace(oracle):
+    """Lambert albedo 1 inside a uniform white environment: every sample is exactly 1 (pdf ratio 1) — any energy bug shows."""
+    geom = np.zeros((2, 24), F32); geom[0, :4] = [0, 0, 0, 1]; geom[1, :4] = [2.5, 0.2, 0.3, 0.7]   # disjoint: a path that gets inside a closed Lambert shell never escapes
+    w = oracle.OracleWorld.from_flat(np.array([0, 0], np.uint32), np.zeros(2, np.uint32), geom, np.array([mat(0, 0)], np.uint32),
+                                     np.array([solid_tex([1, 1, 1])], np.uint32), [], simple_camera(pos=(0, 0.5, 5)),
+                                     np.array([0, 1, 1, 1], F32), np.zeros(7, F32))
+    for mode in ("faithful", "replay"):
+        img, _ = w.render(40, 30, 8, 50, 2, 3, mode)
+        fin = img[~np.isnan(img)]
+        assert fin.size > 0.999 * img.size and np.all(np.abs(fin - 1.0) < 1e-5), mode
+
+
+def test_replay_samplers_are_distribution_equivalent(oracle):
+    """REPLAY (Philox + inversion) and FAITHFUL (Xoroshiro + rejection) must estimate the same image."""
+    from helpers import random_scene
+    sc = random_scene(3, n_spheres=12, n_tris=10, n_rects=3, with_light=True)
+    w = oracle.OracleWorld.from_flat(**sc)
+    n = 192
+    a, _ = w.render(32, 24, n, 16, 4, 1, "faithful")
+    b, _ = w.render(32, 24, n, 16, 4, 2, "faithful")
+    r, _ = w.render(32, 24, n, 16, 4, 1, "replay")
+    ok = ~(np.isnan(a) | np.isnan(b) | np.isnan(r))
+    clip = lambda x: np.minimum(x, 10.0)   # fireflies from the light-sampling pdf: compare clipped estimators
+    noise = math.sqrt(np.mean((clip(a[ok]) - clip(b[ok])) ** 2))
+    err = math.sqrt(np.mean((clip(a[ok]) - clip(r[ok])) ** 2))
+    assert err <= 1.3 * noise + 1e-3, (err, noise)
+    assert abs(np.mean(clip(a[ok])) - np.mean(clip(r[ok]))) <= 4 * noise / math.sqrt(ok.sum() / 3) + 2e-3
