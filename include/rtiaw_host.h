@@ -47,6 +47,10 @@ const uint8_t* rtw_world_image(const RtwWorld* w, uint32_t index);
 
 /* The device-resident scene (created on first use; owned by the world). */
 int rtw_world_device(RtwWorld* w, int device, RtScene** out_scene);
+/* Drop the device copy (the next use uploads the scene again: lets callers time the host->device hand-off). */
+int rtw_world_release_device(RtwWorld* w);
+/* Host bytes that rt_scene_create copies for this world (items, nodes, tables, images). */
+int rtw_world_upload_bytes(const RtwWorld* w, uint64_t* out_bytes);
 
 int rtw_render(RtwWorld* w, int32_t width, int32_t height, uint64_t thread_count, uint64_t samples_per_pixel,
                int32_t max_depth, uint32_t render_mode, uint64_t seed, int device, float* out_rgb, RtStats* out_stats);

@@ -81,6 +81,8 @@ def host_lib():
         L.rtw_world_image.restype = C.c_void_p
         L.rtw_world_image.argtypes = [C.c_void_p, C.c_uint32]
         L.rtw_world_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.rtw_world_release_device.argtypes = [C.c_void_p]
+        L.rtw_world_upload_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.rtw_render.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint32,
                                  C.c_uint64, C.c_int, C.c_void_p, C.POINTER(_cabi.RtStats)]
         L.rtw_hit.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int] + [C.c_void_p] * 5
@@ -201,6 +203,15 @@ class World:
         h = C.c_void_p()
         _check(host_lib().rtw_world_device(self.h, device, C.byref(h)))
         return _cabi.DeviceScene.borrowed(h, device)
+
+    def release_device(self):
+        """Drop the device copy; the next render / hit uploads the scene again."""
+        _check(host_lib().rtw_world_release_device(self.h))
+
+    def upload_bytes(self) -> int:
+        b = C.c_uint64(0)
+        _check(host_lib().rtw_world_upload_bytes(self.h, C.byref(b)))
+        return b.value
 
     def hit(self, org, dir, t_range=(0.001, float("inf")), device: int = 0):
         org = np.ascontiguousarray(org, np.float32).reshape(-1, 3)

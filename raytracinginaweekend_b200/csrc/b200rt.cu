@@ -26,7 +26,7 @@ int g_opt_traversal = 2;      // 0 = reference node test only (exact), 1 = + tig
 int g_opt_leaf_weight = 16;   // extend phase vote: leaf phase when n_leaf * w > n_node * 16
 int g_opt_refill = 20;        // extend refills idle lanes when fewer than this many of 32 are busy
 int g_opt_count = 0;        // 1 = COUNT kernel variant (node visits / primitive tests per ray)
-int g_opt_profile = 0;        // 1 = time extend / shade separately with events (adds syncs)
+int g_opt_profile = 0;        // 1 = time every extend / shade launch with CUDA events on the launching stream (no extra syncs)
 int g_opt_check_every = 8;    // host polls the live-path count every N iterations
 int g_opt_blocks_per_sm = 0;  // 0 = from occupancy query
 
@@ -80,11 +80,15 @@ struct RtScene {
     DevBuf<uint2> hits;
     DevBuf<Counters> ctr;
     DevBuf<float> film;
-    Counters* h_ctr = nullptr;  // pinned
+    Counters* h_ctr = nullptr;  // pinned, 2 entries (double-buffered poll)
+    cudaEvent_t poll_event[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> prof_events;
     size_t ws_slots = 0;
     ~RtScene() {
         for (auto* b : images) delete b;
         if (h_ctr) cudaFreeHost(h_ctr);
+        for (auto e : poll_event) if (e) cudaEventDestroy(e);
+        for (auto e : prof_events) cudaEventDestroy(e);
     }
 };
 
@@ -418,7 +422,7 @@ int ensure_workspace(RtScene& sc, size_t slots, size_t npix) {
         sc.ws_slots = slots;
     }
     if (!sc.ctr.p) CU(sc.ctr.alloc(1));
-    if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, sizeof(Counters)));
+    if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, 2 * sizeof(Counters)));
     if (sc.film.n < npix * 3) CU(sc.film.alloc(npix * 3));
     return RT_OK;
 }
@@ -478,13 +482,22 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     rc = persistent_grid(sc, k_shade, 128, 0, &sgrid);
     if (rc) return rc;
 
-    cudaEvent_t ev0, ev1, eva, evb;
+    cudaEvent_t ev0, ev1;
     CU(cudaEventCreate(&ev0));
     CU(cudaEventCreate(&ev1));
-    CU(cudaEventCreate(&eva));
-    CU(cudaEventCreate(&evb));
     uint64_t launches = 0, iters = 0;
     double extend_ms = 0.0, shade_ms = 0.0;
+    const int chunk = g_opt_check_every;
+    // per-launch timing without extra synchronisation: 3 events per iteration, read back after the chunk's poll
+    if (g_opt_profile && sc.prof_events.size() < (size_t)(2 * 3 * chunk)) {
+        while (sc.prof_events.size() < (size_t)(2 * 3 * chunk)) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            sc.prof_events.push_back(e);
+        }
+    }
+    for (int b = 0; b < 2; ++b)
+        if (!sc.poll_event[b]) CU(cudaEventCreate(&sc.poll_event[b]));
     CU(cudaEventRecord(ev0, stream));
     {
         int ggrid = (int)std::min<size_t>((slots + 255) / 256, (size_t)sc.sm_count * 8);
@@ -492,35 +505,59 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
         ++launches;
     }
     int q = 0;
-    const uint64_t max_iters = (uint64_t)(R.spp_whole + 1u) * (uint64_t)std::max(P.max_depth, 1) + 4;
-    bool done = false;
-    while (!done) {
-        for (int it = 0; it < g_opt_check_every; ++it) {
-            if (g_opt_profile) CU(cudaEventRecord(eva, stream));
+    const uint64_t max_iters = (uint64_t)(R.spp_whole + 1u) * (uint64_t)std::max(P.max_depth, 1) + 4 + 2 * (uint64_t)chunk;
+    // The host never knows the live-path count of the iteration it is launching: kernels read it from device memory
+    // (grids are persistent, sized by the SM count).  Every `chunk` iterations the counters are copied to pinned memory;
+    // the host keeps one chunk in flight while it waits for the previous chunk's copy, so the GPU never idles on the poll.
+    int q_after[2] = {0, 0};
+    auto enqueue_chunk = [&](int buf) -> int {
+        for (int it = 0; it < chunk; ++it) {
+            cudaEvent_t* pe = g_opt_profile ? &sc.prof_events[(size_t)(buf * chunk + it) * 3] : nullptr;
+            if (pe) CU(cudaEventRecord(pe[0], stream));
             ext<<<egrid, eblock, esmem, stream>>>(sc.dev, R, q);
-            if (g_opt_profile) {
-                CU(cudaEventRecord(evb, stream));
-                CU(cudaEventSynchronize(evb));
-                float ms;
-                CU(cudaEventElapsedTime(&ms, eva, evb));
-                extend_ms += ms;
-                CU(cudaEventRecord(eva, stream));
-            }
+            if (pe) CU(cudaEventRecord(pe[1], stream));
             k_shade<<<sgrid, 128, 0, stream>>>(sc.dev, R, q);
-            if (g_opt_profile) {
-                CU(cudaEventRecord(evb, stream));
-                CU(cudaEventSynchronize(evb));
-                float ms;
-                CU(cudaEventElapsedTime(&ms, eva, evb));
-                shade_ms += ms;
-            }
+            if (pe) CU(cudaEventRecord(pe[2], stream));
             launches += 2;
             ++iters;
             q ^= 1;
         }
-        CU(cudaMemcpyAsync(sc.h_ctr, sc.ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-        CU(cudaStreamSynchronize(stream));
-        if (sc.h_ctr->nb[q] + sc.h_ctr->nn[q] == 0) done = true;
+        CU(cudaMemcpyAsync(&sc.h_ctr[buf], sc.ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+        CU(cudaEventRecord(sc.poll_event[buf], stream));
+        q_after[buf] = q;  // the queue the next iteration would read
+        return RT_OK;
+    };
+    auto harvest = [&](int buf) -> int {
+        if (!g_opt_profile) return RT_OK;
+        for (int it = 0; it < chunk; ++it) {
+            cudaEvent_t* pe = &sc.prof_events[(size_t)(buf * chunk + it) * 3];
+            float a = 0.0f, b2 = 0.0f;
+            CU(cudaEventElapsedTime(&a, pe[0], pe[1]));
+            CU(cudaEventElapsedTime(&b2, pe[1], pe[2]));
+            extend_ms += a;
+            shade_ms += b2;
+        }
+        return RT_OK;
+    };
+    int buf = 0;
+    rc = enqueue_chunk(buf);
+    if (rc) return rc;
+    const Counters* final_ctr = nullptr;
+    for (;;) {
+        rc = enqueue_chunk(buf ^ 1);
+        if (rc) return rc;
+        CU(cudaEventSynchronize(sc.poll_event[buf]));
+        rc = harvest(buf);
+        if (rc) return rc;
+        const bool drained = sc.h_ctr[buf].nb[q_after[buf]] + sc.h_ctr[buf].nn[q_after[buf]] == 0;
+        buf ^= 1;
+        if (drained) {  // the chunk already in flight only runs empty iterations
+            CU(cudaEventSynchronize(sc.poll_event[buf]));
+            rc = harvest(buf);
+            if (rc) return rc;
+            final_ctr = &sc.h_ctr[buf];
+            break;
+        }
         if (iters > max_iters) return fail(RT_ECUDA, "wavefront loop did not terminate");
     }
     {
@@ -533,18 +570,18 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     CU(cudaGetLastError());
     float ms = 0.0f;
     CU(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(eva); cudaEventDestroy(evb);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (stats) {
-        stats->ray_segments = sc.h_ctr->rays;
-        stats->paths = sc.h_ctr->paths;
+        stats->ray_segments = final_ctr->rays;
+        stats->paths = final_ctr->paths;
         stats->iterations = iters;
         stats->kernel_launches = launches;
         stats->render_ms = ms;
         stats->extend_ms = extend_ms;
         stats->shade_ms = shade_ms;
-        stats->node_visits = sc.h_ctr->node_visits;
-        stats->prim_tests = sc.h_ctr->prim_tests;
-        stats->exact_steps = sc.h_ctr->exact_steps;
+        stats->node_visits = final_ctr->node_visits;
+        stats->prim_tests = final_ctr->prim_tests;
+        stats->exact_steps = final_ctr->exact_steps;
     }
     return RT_OK;
 }

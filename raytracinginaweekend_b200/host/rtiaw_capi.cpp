@@ -150,6 +150,20 @@ int rtw_world_device(RtwWorld* w, int device, RtScene** out_scene) {
     return guard([&] { *out_scene = w->world->device(device); });
 }
 
+int rtw_world_release_device(RtwWorld* w) {
+    return guard([&] { w->world->release_device(); });
+}
+
+int rtw_world_upload_bytes(const RtwWorld* w, uint64_t* out_bytes) {
+    return guard([&] {
+        const World& W = *w->world;
+        uint64_t b = W.hittable->elements.size() * sizeof(RtItem) + W.hittable->bvh.nodes.size() * sizeof(RtBvhNode) +
+                     W.tables->materials.size() * sizeof(RtMaterial) + W.tables->textures.size() * sizeof(RtTexture) + sizeof(RtSceneDesc);
+        for (const ImageData& im : W.tables->images) b += im.rgb8.size();
+        *out_bytes = b;
+    });
+}
+
 int rtw_render(RtwWorld* w, int32_t width, int32_t height, uint64_t thread_count, uint64_t spp, int32_t max_depth, uint32_t render_mode,
                uint64_t seed, int device, float* out_rgb, RtStats* out_stats) {
     return guard([&] {
