@@ -234,16 +234,22 @@ struct TravCount {
 struct Trav {
     float3 o, d, inv;
     float start, end;
+    float mscale;  // 2 * max_i |1 / d_i|: converts the lateral guard band into a gap in t
     uint32_t cur, sp, best;
     bool exact_only;
 };
 #define RT_BAND 1e-6f  // >= 8 ulp: bound on |(x*rcp(d)) - rn(x/d)| is ~1.5 ulp
 
-// guard band m(t) = A + |t| * (1e-5 + C * |t|), A and C packed as two bf16 (rounded up): hi = A, lo = C
-__device__ __forceinline__ float node_margin(uint32_t packed, float t) {
+// Guard band of the tight cull.  eps(t) = A + |t| * (1e-5 + C * |t|) is the LATERAL distance (space units) by which a ray
+// may miss a primitive's true AABB and still be accepted by the primitive's single-precision test (A and C are packed
+// as two bf16, rounded up: hi = A, lo = C).  A ray that misses a box laterally by delta on axis i opens a gap of
+// delta / |d_i| in t, so the gap that proves "misses the box padded by eps" is eps * (1/|d_j| + 1/|d_k|) <= eps * mscale
+// with mscale = 2 * max_i |1/d_i| (per ray).  Near-axis-parallel rays therefore (correctly) lose the tight cull:
+// they can slide along a box face within rounding distance of it.
+__device__ __forceinline__ float node_margin(uint32_t packed, float t, float mscale) {
     float a = __uint_as_float(packed & 0xFFFF0000u), c = __uint_as_float(packed << 16);
     float at = fabsf(t);
-    return a + at * (1e-5f + c * at);
+    return (a + at * (1e-5f + c * at)) * mscale;
 }
 
 template <int MODE>
@@ -251,13 +257,14 @@ __device__ __forceinline__ bool trav_begin(const SceneDev& S, Trav& T, float3 o,
     T.o = o; T.d = d; T.start = start; T.end = end;
     T.best = RT_NO_HIT; T.sp = 0; T.cur = S.root;
     T.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    T.mscale = 2.0f * fmaxf(fmaxf(fabsf(T.inv.x), fabsf(T.inv.y)), fabsf(T.inv.z));  // +inf for axis-parallel rays: no tight cull
     const float lo = 1e-18f, hi = 1e18f;  // NaN / inf / zero / denormal components -> exact path only
     T.exact_only = !(fabsf(d.x) > lo && fabsf(d.x) < hi && fabsf(d.y) > lo && fabsf(d.y) < hi && fabsf(d.z) > lo && fabsf(d.z) < hi);
     if (!(T.cur & RT_REF_LEAF)) {
         Slab r = slab_test(S.root_min[0], S.root_min[1], S.root_min[2], S.root_max[0], S.root_max[1], S.root_max[2], o,
                            d, start, end);
         bool pass = r.ref_pass;
-        if (MODE >= 1) pass = pass && !(r.tn - r.tf > node_margin(S.root_margin, r.tn));
+        if (MODE >= 1) pass = pass && !(r.tn - r.tf > node_margin(S.root_margin, r.tn, T.mscale));
         return pass;
     }
     return true;
@@ -300,7 +307,7 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
         if (MODE == 2 && !T.exact_only) {
             approx_slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T, tnL, tfL);
             approx_slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, tnR, tfR);
-            const bool cullL = tnL - tfL > node_margin(q3.w, tnL), cullR = tnR - tfR > node_margin(q3.w, tnR);
+            const bool cullL = tnL - tfL > node_margin(q3.w, tnL, T.mscale), cullR = tnR - tfR > node_margin(q3.w, tnR, T.mscale);
             // carried interval non-empty beyond rounding => the per-axis reference rule passes too
             const bool sureL = leafL || (tfL - tnL > RT_BAND * (fabsf(tfL) + fabsf(tnL)));
             const bool sureR = leafR || (tfR - tnR > RT_BAND * (fabsf(tfR) + fabsf(tnR)));
@@ -318,8 +325,8 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
             pL = leafL ? true : sl.ref_pass;
             pR = leafR ? true : sr.ref_pass;
             if (MODE >= 1) {
-                pL = pL && !(sl.tn - sl.tf > node_margin(q3.w, sl.tn));
-                pR = pR && !(sr.tn - sr.tf > node_margin(q3.w, sr.tn));
+                pL = pL && !(sl.tn - sl.tf > node_margin(q3.w, sl.tn, T.mscale));
+                pR = pR && !(sr.tn - sr.tf > node_margin(q3.w, sr.tn, T.mscale));
             }
             tnL = sl.tn; tnR = sr.tn;
         }
@@ -329,7 +336,7 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
         if (p1 && p2) {
             float tn2 = left_first ? tnR : tnL;
             // leaf entries carry their cull threshold (tn - guard band), internal entries carry tn
-            if (c2 & RT_REF_LEAF) tn2 = (MODE >= 1) ? tn2 - node_margin(q3.w, tn2) : -__int_as_float(0x7f800000);
+            if (c2 & RT_REF_LEAF) tn2 = (MODE >= 1) ? tn2 - node_margin(q3.w, tn2, T.mscale) : -__int_as_float(0x7f800000);
             stk_ref[T.sp * stk_stride] = c2;
             stk_tn[T.sp * stk_stride] = tn2;
             ++T.sp;

@@ -178,6 +178,32 @@ def adversarial_rays(fs, n_per_class, seed):
         d = rng.normal(size=(m, 3)); d[np.arange(m), ax] = 0.0
         orgs.append(o); dirs.append(unit_rows(d + 1e-30))
         dirs[-1][np.arange(m), ax] = 0.0
+    # rays sliding along slab / primitive boundaries: origin on a box plane, rect border or sphere-AABB face, with a zero or
+    # tiny direction component on that axis (the hit lands within rounding distance of the boundary: "phantom" accepts)
+    planes = []   # (axis, coordinate)
+    if len(fs.nodes_box):
+        for ax in range(3):
+            planes += [(ax, v) for v in fs.nodes_box[:, ax]] + [(ax, v) for v in fs.nodes_box[:, 3 + ax]]
+    for g in rect:
+        plane = int(g[0]); a0, a1, n = [(0, 1, 2), (0, 2, 1), (1, 2, 0)][plane]
+        planes += [(a0, g[2]), (a0, g[3]), (a1, g[4]), (a1, g[5]), (n, g[1])]
+    for g in sph[:200]:
+        for ax in range(3):
+            planes += [(ax, g[ax] - g[3]), (ax, g[ax] + g[3])]
+    if planes:
+        m = n_per_class
+        pick = rng.integers(0, len(planes), m)
+        o = rng.uniform(lo, hi, size=(m, 3)).astype(F32)
+        d = rng.normal(size=(m, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        tiny = rng.choice([0.0, 1e-12, -1e-12, 1e-9, -1e-9, 1e-7, -1e-7, 1e-5, -1e-5, 1e-3, -1e-3], m)
+        for i in range(m):
+            ax, v = planes[pick[i]]
+            o[i, ax] = v
+            d[i, ax] = 0.0
+            d[i] /= max(np.linalg.norm(d[i]), 1e-30)
+            d[i, ax] = tiny[i]
+        orgs.append(o); dirs.append(d.astype(F32))
     return np.concatenate(orgs), np.concatenate(dirs)
 
 
