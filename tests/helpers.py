@@ -207,6 +207,16 @@ def adversarial_rays(fs, n_per_class, seed):
     return np.concatenate(orgs), np.concatenate(dirs)
 
 
+def _uv_diff(a, b):
+    """max |a-b| over finite entries; inf when the NaN masks differ (acos of a rounded |n.y| > 1 is NaN on both sides)."""
+    if a.size == 0:
+        return 0.0
+    na, nb = np.isnan(a), np.isnan(b)
+    if not np.array_equal(na, nb):
+        return float("inf")
+    return float(np.abs(a[~na] - b[~nb]).max()) if (~na).any() else 0.0
+
+
 def compare_hits(got, ref, rel_tol=1e-5):
     """Hit ids bit-exact; t and normals within rel_tol relative (the north-star bound); returns a dict of counts."""
     ids_bad = int((got["hit_id"] != ref["hit_id"]).sum())
@@ -220,7 +230,7 @@ def compare_hits(got, ref, rel_tol=1e-5):
     return dict(n=len(ref["hit_id"]), hits=int(both.sum()), id_mismatch=ids_bad, t_bit_mismatch=t_bits, normal_bit_mismatch=n_bits,
                 t_rel_max=float(t_rel.max()) if both.any() else 0.0, n_rel_max=float(n_rel.max()) if both.any() else 0.0,
                 ff_mismatch=int((got["front_face"][both] != ref["front_face"][both]).sum()),
-                uv_abs_max=float(np.abs(got["uv"][both] - ref["uv"][both]).max()) if both.any() else 0.0)
+                uv_abs_max=_uv_diff(got["uv"][both], ref["uv"][both]))
 
 
 def assert_hits_match(got, ref, rel_tol=1e-5):

@@ -191,14 +191,18 @@ def test_render_statistics_vs_faithful_oracle(oracle_world):
         assert abs(np.mean(a[..., c][m]) - np.mean(g[..., c][m])) <= 4 * noise / math.sqrt(m.sum()) + 1e-4
 
 
-def test_white_furnace_gpu():
+def test_white_furnace_gpu(oracle):
+    """Lambert albedo 1 in a white environment: every escaping sample is exactly 1.  (A few paths get trapped inside a sphere
+    after a grazing bounce and die black at depth exhaustion — the reference does the same, so the oracle is the judge.)"""
     geom = np.zeros((2, 24), F32); geom[0, :4] = [0, 0, 0, 1]; geom[1, :4] = [2.5, 0.2, 0.3, 0.7]
-    w = rb.World.from_elements(np.array([0, 0], np.uint32), np.zeros(2, np.uint32), geom, np.array([mat(0, 0)], np.uint32),
-                               np.array([solid_tex([1, 1, 1])], np.uint32), [], simple_camera(pos=(0, 0.5, 5)),
-                               np.array([0, 1, 1, 1], F32), np.zeros(7, F32))
+    args = (np.array([0, 0], np.uint32), np.zeros(2, np.uint32), geom, np.array([mat(0, 0)], np.uint32),
+            np.array([solid_tex([1, 1, 1])], np.uint32), [], simple_camera(pos=(0, 0.5, 5)), np.array([0, 1, 1, 1], F32), np.zeros(7, F32))
+    w = rb.World.from_elements(*args)
     img = rb.render(rb.Size2i(160, 120), 4, 32, 50, w, seed=5)
     fin = img[~np.isnan(img)]
-    assert fin.size > 0.999 * img.size and np.all(np.abs(fin - 1.0) < 1e-5)
+    assert fin.size > 0.999 * img.size and np.mean(np.abs(fin - 1.0) < 1e-5) > 0.999 and abs(fin.mean() - 1.0) < 1e-3
+    ref, _ = oracle.OracleWorld.from_flat(*args).render(160, 120, 32, 50, 4, 5, "replay")
+    assert images_equal_bits(img, ref)
 
 
 def test_render_is_deterministic_and_seed_sensitive():
