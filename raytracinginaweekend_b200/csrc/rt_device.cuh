@@ -232,10 +232,14 @@ struct TravCount {
     uint32_t nodes, prims, exact;  // node visits (64 B fetches), primitive tests, exact-fallback node steps
 };
 struct Trav {
-    float3 o, d, inv;
+    float3 o, d;
+    float3 inv, oinv;  // 1/d and -o/d: the fast path evaluates a slab plane as fma(b, inv, oinv)
     float start, end;
     float mscale;  // 2 * max_i |1 / d_i|: converts the lateral guard band into a gap in t
+    float sB;      // 1e-5 * mscale
+    float oe;      // 2 x bound on the absolute error of an approximate slab distance: 1.2e-7 * max_i |o_i / d_i| (x2)
     uint32_t cur, sp, best;
+    uint32_t dpos;  // bit i = (d_i > 0): child order (hittable.rs:441)
     bool exact_only;
 };
 #define RT_BAND 1e-6f  // >= 8 ulp: bound on |(x*rcp(d)) - rn(x/d)| is ~1.5 ulp
@@ -257,9 +261,15 @@ __device__ __forceinline__ bool trav_begin(const SceneDev& S, Trav& T, float3 o,
     T.o = o; T.d = d; T.start = start; T.end = end;
     T.best = RT_NO_HIT; T.sp = 0; T.cur = S.root;
     T.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    T.oinv = f3(-o.x * T.inv.x, -o.y * T.inv.y, -o.z * T.inv.z);
     T.mscale = 2.0f * fmaxf(fmaxf(fabsf(T.inv.x), fabsf(T.inv.y)), fabsf(T.inv.z));  // +inf for axis-parallel rays: no tight cull
-    const float lo = 1e-18f, hi = 1e18f;  // NaN / inf / zero / denormal components -> exact path only
-    T.exact_only = !(fabsf(d.x) > lo && fabsf(d.x) < hi && fabsf(d.y) > lo && fabsf(d.y) < hi && fabsf(d.z) > lo && fabsf(d.z) < hi);
+    T.sB = 1e-5f * T.mscale;
+    // fma(b, inv, oinv) vs rn((b - o) / d): |err| <= 1.2e-7 |t| + 6e-8 |o_i / d_i|  (inv, oinv and the fma each round once)
+    T.oe = 2.4e-7f * fmaxf(fmaxf(fabsf(T.oinv.x), fabsf(T.oinv.y)), fabsf(T.oinv.z));
+    T.dpos = (d.x > 0.0f ? 1u : 0u) | (d.y > 0.0f ? 2u : 0u) | (d.z > 0.0f ? 4u : 0u);
+    const float lo = 1e-18f, hi = 1e18f;  // NaN / inf / zero / denormal components, or a negative range start -> exact path only
+    T.exact_only = !(fabsf(d.x) > lo && fabsf(d.x) < hi && fabsf(d.y) > lo && fabsf(d.y) < hi && fabsf(d.z) > lo && fabsf(d.z) < hi) ||
+                   !(start >= 0.0f) || !(T.oe < 1e30f);
     if (!(T.cur & RT_REF_LEAF)) {
         Slab r = slab_test(S.root_min[0], S.root_min[1], S.root_min[2], S.root_max[0], S.root_max[1], S.root_max[2], o,
                            d, start, end);
@@ -270,11 +280,13 @@ __device__ __forceinline__ bool trav_begin(const SceneDev& S, Trav& T, float3 o,
     return true;
 }
 
+// Approximate carried slab interval: 6 FFMA + 12 FMNMX.  FMA is deliberate here (this value only steers the cull /
+// sure-pass decision, never a result); its error bound is T.oe + 1.2e-7 |t|.
 __device__ __forceinline__ void approx_slab(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const Trav& T,
                                             float& tn, float& tf) {
-    float ax = (mnx - T.o.x) * T.inv.x, bx = (mxx - T.o.x) * T.inv.x;
-    float ay = (mny - T.o.y) * T.inv.y, by = (mxy - T.o.y) * T.inv.y;
-    float az = (mnz - T.o.z) * T.inv.z, bz = (mxz - T.o.z) * T.inv.z;
+    float ax = __fmaf_rn(mnx, T.inv.x, T.oinv.x), bx = __fmaf_rn(mxx, T.inv.x, T.oinv.x);
+    float ay = __fmaf_rn(mny, T.inv.y, T.oinv.y), by = __fmaf_rn(mxy, T.inv.y, T.oinv.y);
+    float az = __fmaf_rn(mnz, T.inv.z, T.oinv.z), bz = __fmaf_rn(mxz, T.inv.z, T.oinv.z);
     tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), T.start));
     tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), T.end));
 }
@@ -302,15 +314,19 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
         const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
         const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));
         const bool leafL = (q3.x & RT_REF_LEAF) != 0u, leafR = (q3.y & RT_REF_LEAF) != 0u;
-        float tnL, tfL, tnR, tfR;
+        float tnL, tfL, tnR, tfR, mgL = 0.0f, mgR = 0.0f;
         bool pL, pR, need_exact;
         if (MODE == 2 && !T.exact_only) {
             approx_slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T, tnL, tfL);
             approx_slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, tnR, tfR);
-            const bool cullL = tnL - tfL > node_margin(q3.w, tnL, T.mscale), cullR = tnR - tfR > node_margin(q3.w, tnR, T.mscale);
+            // guard band in t (tn >= start >= 0 here): (A + 1e-5 t + C t^2) * mscale, plus the approximation error
+            const float sA = __fmaf_rn(__uint_as_float(q3.w & 0xFFFF0000u), T.mscale, T.oe), sC = __uint_as_float(q3.w << 16) * T.mscale;
+            mgL = __fmaf_rn(tnL, __fmaf_rn(sC, tnL, T.sB), sA);
+            mgR = __fmaf_rn(tnR, __fmaf_rn(sC, tnR, T.sB), sA);
+            const bool cullL = tnL - tfL > mgL, cullR = tnR - tfR > mgR;
             // carried interval non-empty beyond rounding => the per-axis reference rule passes too
-            const bool sureL = leafL || (tfL - tnL > RT_BAND * (fabsf(tfL) + fabsf(tnL)));
-            const bool sureR = leafR || (tfR - tnR > RT_BAND * (fabsf(tfR) + fabsf(tnR)));
+            const bool sureL = leafL || (tfL - tnL > __fmaf_rn(RT_BAND, tfL + tnL, T.oe));
+            const bool sureR = leafR || (tfR - tnR > __fmaf_rn(RT_BAND, tfR + tnR, T.oe));
             pL = !cullL && sureL;
             pR = !cullR && sureR;
             need_exact = (!cullL && !sureL) || (!cullR && !sureR);
@@ -329,14 +345,15 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
                 pR = pR && !(sr.tn - sr.tf > node_margin(q3.w, sr.tn, T.mscale));
             }
             tnL = sl.tn; tnR = sr.tn;
+            if (MODE >= 1) { mgL = node_margin(q3.w, tnL, T.mscale); mgR = node_margin(q3.w, tnR, T.mscale); }
         }
-        const bool left_first = comp3(T.d, (int)q3.z) > 0.0f;  // hittable.rs:441-445
+        const bool left_first = ((T.dpos >> q3.z) & 1u) != 0u;  // dir[axis_id] > 0, hittable.rs:441-445
         const uint32_t c1 = left_first ? q3.x : q3.y, c2 = left_first ? q3.y : q3.x;
         const bool p1 = left_first ? pL : pR, p2 = left_first ? pR : pL;
         if (p1 && p2) {
             float tn2 = left_first ? tnR : tnL;
             // leaf entries carry their cull threshold (tn - guard band), internal entries carry tn
-            if (c2 & RT_REF_LEAF) tn2 = (MODE >= 1) ? tn2 - node_margin(q3.w, tn2, T.mscale) : -__int_as_float(0x7f800000);
+            if (c2 & RT_REF_LEAF) tn2 = (MODE >= 1) ? tn2 - (left_first ? mgR : mgL) : -__int_as_float(0x7f800000);
             stk_ref[T.sp * stk_stride] = c2;
             stk_tn[T.sp * stk_stride] = tn2;
             ++T.sp;

@@ -104,43 +104,48 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ SceneDev
     Trav T;
     bool active = false, exhausted = false;
     uint32_t my_pos = 0;
+    uint32_t batch_next = 0, batch_end = 0;  // warp-uniform: ray indices [batch_next, batch_end) already claimed by this warp
+    uint32_t busy = 0;
     for (;;) {
+        // refill: idle lanes take rays from the warp's claimed batch (one atomic per 32 rays)
         const uint32_t idle = __ballot_sync(FULL, !active);
-        if (idle && !exhausted) {
-            const uint32_t want = __popc(idle);
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&R.ctr->cursor_extend, want);
-            base = __shfl_sync(FULL, base, 0);
-            if (base + want >= n) exhausted = true;
-            if (!active) {
-                const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
-                if (i < n) {
-                    my_pos = queue_pos(i, nb, R.cap);
-                    const float4 a = R.A[q][my_pos], b = R.B[q][my_pos];
-                    active = trav_begin<MODE>(S, T, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), 0.001f, INF);
-                    if (!active) R.hits[my_pos] = make_uint2(RT_NO_HIT, __float_as_uint(INF));
-                }
+        if (idle && !(exhausted && batch_next == batch_end) && busy < R.refill_threshold) {
+            if (batch_next == batch_end && !exhausted) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&R.ctr->cursor_extend, 32u);
+                base = __shfl_sync(FULL, base, 0);
+                batch_next = min(base, n);
+                batch_end = min(base + 32u, n);
+                if (base + 32u >= n) exhausted = true;
             }
+            const uint32_t avail = batch_end - batch_next;
+            const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+            if (!active && rank < avail) {
+                const uint32_t i = batch_next + rank;
+                my_pos = queue_pos(i, nb, R.cap);
+                const float4 a = R.A[q][my_pos], b = R.B[q][my_pos];
+                active = trav_begin<MODE>(S, T, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), 0.001f, INF);
+                if (!active) R.hits[my_pos] = make_uint2(RT_NO_HIT, __float_as_uint(INF));
+            }
+            batch_next += min(avail, (uint32_t)__popc(idle));
         }
-        uint32_t busy = __popc(__ballot_sync(FULL, active));
+        busy = __popc(__ballot_sync(FULL, active));
         if (busy == 0) {
-            if (exhausted) break;
+            if (exhausted && batch_next == batch_end) break;
             continue;
         }
-        const uint32_t thresh = exhausted ? 1u : R.refill_threshold;
-        do {
-            // phase vote: run the leaf phase when (weighted) more lanes wait at a leaf than at an internal node
-            const uint32_t at_leaf = __ballot_sync(FULL, active && (T.cur & RT_REF_LEAF));
-            const uint32_t n_leaf = __popc(at_leaf);
-            const bool do_leaf = n_leaf * R.leaf_weight > (busy - n_leaf) * 16u;
-            if (active) {
-                if (!trav_round<MODE, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc)) {
-                    R.hits[my_pos] = make_uint2(T.best, __float_as_uint(T.end));
-                    active = false;
-                }
+        // phase vote: run the leaf phase when (weighted) more lanes wait at a leaf than at an internal node
+        const uint32_t at_leaf = __ballot_sync(FULL, active && (T.cur & RT_REF_LEAF));
+        const uint32_t n_leaf = __popc(at_leaf);
+        const bool do_leaf = n_leaf * R.leaf_weight > (busy - n_leaf) * 16u;
+        if (active) {
+            if (!trav_round<MODE, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc)) {
+                R.hits[my_pos] = make_uint2(T.best, __float_as_uint(T.end));
+                active = false;
+                busy -= 1u;  // (per-lane view; only used as a hint for the refill threshold)
             }
-            busy = __popc(__ballot_sync(FULL, active));
-        } while (busy >= thresh);
+        }
+        busy = __popc(__ballot_sync(FULL, active));
     }
     if (COUNT) {
         for (int off = 16; off > 0; off >>= 1) {
