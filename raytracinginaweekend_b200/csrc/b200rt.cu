@@ -437,7 +437,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     if (lane_stride == 0) return fail(RT_EINVAL, "lane_stride must be >= 1");
     const uint64_t T = P.thread_count;
     const uint64_t n_tasks = std::min<uint64_t>(T, P.samples_per_pixel);
-    if (P.samples_per_pixel / T + 1 > 0xFFFFFFFFull) return fail(RT_EINVAL, "too many samples per lane");
+    if (P.samples_per_pixel / T + 1 > 0x7FFFFFFFull) return fail(RT_EINVAL, "too many samples per lane");
     const size_t npix = (size_t)P.width * P.height;
     CU(cudaSetDevice(sc.device));
     if (lane_first >= n_tasks) {  // this rank owns no lane: contributes zeros
@@ -469,6 +469,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     R.sx = 1.0f / (float)(P.width - 1);
     R.sy = 1.0f / (float)(P.height - 1);
     R.mode = P.render_mode;
+    R.ref_only = g_opt_traversal == 0 ? 1u : 0u;
 
     const int eblock = 128;
     const size_t esmem = stack_smem_bytes(sc, eblock);

@@ -256,11 +256,25 @@ __device__ __forceinline__ float node_margin(uint32_t packed, float t, float msc
     return (a + at * (1e-5f + c * at)) * mscale;
 }
 
-template <int MODE>
-__device__ __forceinline__ bool trav_begin(const SceneDev& S, Trav& T, float3 o, float3 d, float start, float end) {
+// Root box test of BoundingVolumeHierarchy::hit (hittable.rs:472 -> hit_recursive(initial_index)): the reference rule, plus the
+// tight cull unless ref_only.  Producers of rays (k_generate / k_shade, all 32 lanes busy) evaluate it once per ray so the
+// persistent extend warps do not run 6 IEEE divisions with one or two lanes enabled.
+__device__ __forceinline__ bool root_gate(const SceneDev& S, float3 o, float3 d, float start, float end, bool ref_only) {
+    if (S.root & RT_REF_LEAF) return true;
+    const Slab r = slab_test(S.root_min[0], S.root_min[1], S.root_min[2], S.root_max[0], S.root_max[1], S.root_max[2], o, d, start, end);
+    bool pass = r.ref_pass;
+    if (!ref_only) {
+        const float mscale = 2.0f * fmaxf(fmaxf(fabsf(1.0f / d.x), fabsf(1.0f / d.y)), fabsf(1.0f / d.z));
+        pass = pass && !(r.tn - r.tf > node_margin(S.root_margin, r.tn, mscale));
+    }
+    return pass;
+}
+
+// Per-ray traversal setup (the root box has already been tested: root_gate).
+__device__ __forceinline__ void trav_setup(const SceneDev& S, Trav& T, float3 o, float3 d, float start, float end) {
     T.o = o; T.d = d; T.start = start; T.end = end;
     T.best = RT_NO_HIT; T.sp = 0; T.cur = S.root;
-    T.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    T.inv = f3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));  // correctly rounded 1/d
     T.oinv = f3(-o.x * T.inv.x, -o.y * T.inv.y, -o.z * T.inv.z);
     T.mscale = 2.0f * fmaxf(fmaxf(fabsf(T.inv.x), fabsf(T.inv.y)), fabsf(T.inv.z));  // +inf for axis-parallel rays: no tight cull
     T.sB = 1e-5f * T.mscale;
@@ -270,14 +284,12 @@ __device__ __forceinline__ bool trav_begin(const SceneDev& S, Trav& T, float3 o,
     const float lo = 1e-18f, hi = 1e18f;  // NaN / inf / zero / denormal components, or a negative range start -> exact path only
     T.exact_only = !(fabsf(d.x) > lo && fabsf(d.x) < hi && fabsf(d.y) > lo && fabsf(d.y) < hi && fabsf(d.z) > lo && fabsf(d.z) < hi) ||
                    !(start >= 0.0f) || !(T.oe < 1e30f);
-    if (!(T.cur & RT_REF_LEAF)) {
-        Slab r = slab_test(S.root_min[0], S.root_min[1], S.root_min[2], S.root_max[0], S.root_max[1], S.root_max[2], o,
-                           d, start, end);
-        bool pass = r.ref_pass;
-        if (MODE >= 1) pass = pass && !(r.tn - r.tf > node_margin(S.root_margin, r.tn, T.mscale));
-        return pass;
-    }
-    return true;
+}
+
+template <int MODE>
+__device__ __forceinline__ bool trav_begin(const SceneDev& S, Trav& T, float3 o, float3 d, float start, float end) {
+    trav_setup(S, T, o, d, start, end);
+    return root_gate(S, o, d, start, end, MODE == 0);
 }
 
 // Approximate carried slab interval: 6 FFMA + 12 FMNMX.  FMA is deliberate here (this value only steers the cull /

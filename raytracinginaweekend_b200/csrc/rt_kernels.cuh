@@ -40,7 +40,10 @@ struct RenderDev {
     uint32_t seed0, seed1;
     float sx, sy;            // 1/(w-1), 1/(h-1)   (size2i.rs:21-22; also the jitter scale, rendering.rs:132-138)
     uint32_t mode;
+    uint32_t ref_only;       // traversal MODE 0: the root gate must not apply the tight cull either
 };
+
+#define RT_ROOT_MISS 0x80000000u  // top bit of the per-path sample index: the ray fails the BVH root test (producer-side)
 
 __device__ __forceinline__ uint32_t lane_samples(const RenderDev& R, uint32_t lane_id) {
     return R.spp_whole + (lane_id < R.spp_rem ? 1u : 0u);
@@ -66,7 +69,8 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
         float3 o, d;
         generate_path(S, R, pixel, lane_id, 0u, o, d);
         R.A[0][slot] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
-        R.B[0][slot] = make_float4(d.x, d.y, d.z, __uint_as_float(0u));
+        const uint32_t miss = root_gate(S, o, d, 0.001f, __int_as_float(0x7f800000), R.ref_only != 0u) ? 0u : RT_ROOT_MISS;
+        R.B[0][slot] = make_float4(d.x, d.y, d.z, __uint_as_float(miss));
         R.C[0][slot] = make_float4(1.0f, 1.0f, 1.0f, d.y);
         R.D[0][slot] = R.max_depth;
         R.acc[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -90,7 +94,7 @@ __device__ __forceinline__ uint32_t queue_pos(uint32_t i, uint32_t nb, uint32_t 
 // when fewer than `refill_threshold` lanes are still busy, the idle lanes pull fresh rays with one warp-aggregated
 // atomic — rays differ by 100x in node visits, so waiting for the slowest lane would idle most of the warp.
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
+__global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
     extern __shared__ uint32_t smem[];
     uint32_t* stk_ref = smem + threadIdx.x;
     float* stk_tn = reinterpret_cast<float*>(smem + S.stack_cap * blockDim.x) + threadIdx.x;
@@ -105,12 +109,11 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ SceneDev
     bool active = false, exhausted = false;
     uint32_t my_pos = 0;
     uint32_t batch_next = 0, batch_end = 0;  // warp-uniform: ray indices [batch_next, batch_end) already claimed by this warp
-    uint32_t busy = 0;
+    uint32_t act_mask = 0;                   // warp-uniform ballot of `active`
     for (;;) {
         // refill: idle lanes take rays from the warp's claimed batch (one atomic per 32 rays)
-        const uint32_t idle = __ballot_sync(FULL, !active);
-        if (idle && !(exhausted && batch_next == batch_end) && busy < R.refill_threshold) {
-            if (batch_next == batch_end && !exhausted) {
+        if (act_mask != FULL && !(exhausted && batch_next == batch_end) && (uint32_t)__popc(act_mask) < R.refill_threshold) {
+            if (batch_next == batch_end) {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(&R.ctr->cursor_extend, 32u);
                 base = __shfl_sync(FULL, base, 0);
@@ -118,34 +121,36 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ SceneDev
                 batch_end = min(base + 32u, n);
                 if (base + 32u >= n) exhausted = true;
             }
+            const uint32_t idle = ~act_mask;
             const uint32_t avail = batch_end - batch_next;
             const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
             if (!active && rank < avail) {
-                const uint32_t i = batch_next + rank;
-                my_pos = queue_pos(i, nb, R.cap);
+                my_pos = queue_pos(batch_next + rank, nb, R.cap);
                 const float4 a = R.A[q][my_pos], b = R.B[q][my_pos];
-                active = trav_begin<MODE>(S, T, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), 0.001f, INF);
-                if (!active) R.hits[my_pos] = make_uint2(RT_NO_HIT, __float_as_uint(INF));
+                if (__float_as_uint(b.w) & RT_ROOT_MISS) {
+                    R.hits[my_pos] = make_uint2(RT_NO_HIT, __float_as_uint(INF));
+                } else {
+                    trav_setup(S, T, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), 0.001f, INF);
+                    active = true;
+                }
             }
             batch_next += min(avail, (uint32_t)__popc(idle));
+            act_mask = __ballot_sync(FULL, active);
         }
-        busy = __popc(__ballot_sync(FULL, active));
-        if (busy == 0) {
+        if (act_mask == 0u) {
             if (exhausted && batch_next == batch_end) break;
             continue;
         }
         // phase vote: run the leaf phase when (weighted) more lanes wait at a leaf than at an internal node
-        const uint32_t at_leaf = __ballot_sync(FULL, active && (T.cur & RT_REF_LEAF));
-        const uint32_t n_leaf = __popc(at_leaf);
-        const bool do_leaf = n_leaf * R.leaf_weight > (busy - n_leaf) * 16u;
+        const uint32_t n_leaf = __popc(__ballot_sync(FULL, active && (T.cur & RT_REF_LEAF)));
+        const bool do_leaf = n_leaf * R.leaf_weight > ((uint32_t)__popc(act_mask) - n_leaf) * 16u;
         if (active) {
             if (!trav_round<MODE, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc)) {
                 R.hits[my_pos] = make_uint2(T.best, __float_as_uint(T.end));
                 active = false;
-                busy -= 1u;  // (per-lane view; only used as a hint for the refill threshold)
             }
         }
-        busy = __popc(__ballot_sync(FULL, active));
+        act_mask = __ballot_sync(FULL, active);
     }
     if (COUNT) {
         for (int off = 16; off > 0; off >>= 1) {
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
             o = f3(a.x, a.y, a.z); d = f3(b.x, b.y, b.z); thr = f3(c.x, c.y, c.z);
             dy0 = c.w;
             slot = __float_as_uint(a.w);
-            k = __float_as_uint(b.w);
+            k = __float_as_uint(b.w) & ~RT_ROOT_MISS;
             const uint32_t pixel = slot % R.npix, local_lane = slot / R.npix;
             const uint32_t lane_id = R.lane_first + local_lane * R.lane_stride;
             const float t = __uint_as_float(h.y);
@@ -359,10 +364,11 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
             bc = __shfl_sync(0xFFFFFFFFu, bc, 0);
             bn = __shfl_sync(0xFFFFFFFFu, bn, 0);
             if (live) {
+                const uint32_t miss = root_gate(S, o, d, 0.001f, __int_as_float(0x7f800000), R.ref_only != 0u) ? 0u : RT_ROOT_MISS;
                 const uint32_t below = (1u << lane) - 1u;
                 const uint32_t pos = fresh ? R.cap - 1u - (bn + __popc(mnew & below)) : bc + __popc(mcont & below);
                 R.A[q ^ 1][pos] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
-                R.B[q ^ 1][pos] = make_float4(d.x, d.y, d.z, __uint_as_float(k));
+                R.B[q ^ 1][pos] = make_float4(d.x, d.y, d.z, __uint_as_float(k | miss));
                 R.C[q ^ 1][pos] = make_float4(thr.x, thr.y, thr.z, dy0);
                 R.D[q ^ 1][pos] = depth;
             }
