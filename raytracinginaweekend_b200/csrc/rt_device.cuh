@@ -187,18 +187,23 @@ __device__ __forceinline__ PrimDev load_prim(const PrimDev* p) {
     return r;
 }
 
-// Leaf test dispatch on a record that is already in registers.  Returns true and shrinks `end` when the primitive is accepted.
-__device__ __forceinline__ bool leaf_test(uint32_t ref, const PrimDev& p, float3 o, float3 d, float start, float& end) {
-    const uint32_t kind = (ref >> RT_REF_KIND_SHIFT) & 3u;
+// Leaf test dispatch.  Returns true and shrinks `end` when the primitive is accepted.
+__device__ __forceinline__ bool leaf_test(const SceneDev& S, uint32_t ref, float3 o, float3 d, float start, float& end) {
+    uint32_t kind = (ref >> RT_REF_KIND_SHIFT) & 3u;
+    uint32_t item = ref & RT_REF_ITEM_MASK;
+    const float4* q = reinterpret_cast<const float4*>(S.prims + item);
     float t;
     bool hit;
     if (kind == 0u) {
-        hit = sphere_t(p.q0, o, d, start, end, t);
+        hit = sphere_t(__ldg(q), o, d, start, end, t);
     } else if (kind == 2u) {
+        PrimDev p;
+        p.q0 = __ldg(q); p.q1 = __ldg(q + 1); p.q2 = __ldg(q + 2); p.q3 = __ldg(q + 3);
         float w1, w2;
         hit = triangle_t(p, o, d, start, end, t, w1, w2);
     } else {
-        hit = rect_t(__float_as_uint(p.q1.y), p.q0.x, p.q0.y, p.q0.z, p.q0.w, p.q1.x, o, d, start, end, t);
+        float4 a = __ldg(q), b = __ldg(q + 1);
+        hit = rect_t(__float_as_uint(b.y), a.x, a.y, a.z, a.w, b.x, o, d, start, end, t);
     }
     if (hit) end = t;
     return hit;
@@ -236,25 +241,7 @@ struct Trav {
     uint32_t cur, sp, best;
     uint32_t dpos;  // bit i = (d_i > 0): child order (hittable.rs:441)
     bool exact_only;
-    PrimDev rec;    // the 64-byte record of `cur` (node or primitive), fetched one round ahead of its use
 };
-
-// Software-pipelined fetch: issued as soon as the next `cur` is known (end of a round / refill); the consumer is the next
-// round the lane takes part in, i.e. after the warp's phase vote — the L1/L2 latency overlaps that control work and the
-// other lanes' steps instead of stalling at the top of the step (long-scoreboard was the #1 stall reason).
-__device__ __forceinline__ void trav_fetch(const SceneDev& S, Trav& T) {
-    const uint32_t cur = T.cur;
-    if (cur & RT_REF_LEAF) {
-        const float4* q = reinterpret_cast<const float4*>(S.prims + (cur & RT_REF_ITEM_MASK));
-        const uint32_t kind = (cur >> RT_REF_KIND_SHIFT) & 3u;
-        T.rec.q0 = __ldg(q);
-        if (kind != 0u) T.rec.q1 = __ldg(q + 1);
-        if (kind == 2u) { T.rec.q2 = __ldg(q + 2); T.rec.q3 = __ldg(q + 3); }
-    } else {
-        const float4* q = reinterpret_cast<const float4*>(S.nodes + cur);
-        T.rec.q0 = __ldg(q); T.rec.q1 = __ldg(q + 1); T.rec.q2 = __ldg(q + 2); T.rec.q3 = __ldg(q + 3);
-    }
-}
 #define RT_BAND 1e-6f  // >= 8 ulp: bound on |(x*rcp(d)) - rn(x/d)| is ~1.5 ulp
 
 // Guard band of the tight cull.  eps(t) = A + |t| * (1e-5 + C * |t|) is the LATERAL distance (space units) by which a ray
@@ -297,7 +284,6 @@ __device__ __forceinline__ void trav_setup(const SceneDev& S, Trav& T, float3 o,
     const float lo = 1e-18f, hi = 1e18f;  // NaN / inf / zero / denormal components, or a negative range start -> exact path only
     T.exact_only = !(fabsf(d.x) > lo && fabsf(d.x) < hi && fabsf(d.y) > lo && fabsf(d.y) < hi && fabsf(d.z) > lo && fabsf(d.z) < hi) ||
                    !(start >= 0.0f) || !(T.oe < 1e30f);
-    trav_fetch(S, T);
 }
 
 template <int MODE>
@@ -331,13 +317,14 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
     if (do_leaf) {
         if (at_leaf) {
             if (COUNT) cnt->prims++;
-            if (leaf_test(cur, T.rec, T.o, T.d, T.start, T.end)) T.best = cur;
+            if (leaf_test(S, cur, T.o, T.d, T.start, T.end)) T.best = cur;
             need_pop = true;
         }
     } else if (!at_leaf) {
         if (COUNT) cnt->nodes++;
-        const float4 q0 = T.rec.q0, q1 = T.rec.q1, q2 = T.rec.q2;
-        const uint4 q3 = make_uint4(__float_as_uint(T.rec.q3.x), __float_as_uint(T.rec.q3.y), __float_as_uint(T.rec.q3.z), __float_as_uint(T.rec.q3.w));
+        const float4* q = reinterpret_cast<const float4*>(S.nodes + cur);
+        const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));
         const bool leafL = (q3.x & RT_REF_LEAF) != 0u, leafR = (q3.y & RT_REF_LEAF) != 0u;
         float tnL, tfL, tnR, tfR, mgL = 0.0f, mgR = 0.0f;
         bool pL, pR, need_exact;
@@ -386,7 +373,6 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
         if (p1) T.cur = c1;
         else if (p2) T.cur = c2;
         else need_pop = true;
-        if (!need_pop) trav_fetch(S, T);
     }
     if (need_pop) {
         for (;;) {
@@ -412,7 +398,6 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
             break;
         }
         T.cur = cur;
-        trav_fetch(S, T);
     }
     return true;
 }
