@@ -11,6 +11,7 @@ CSRC = os.path.join(PKG, "csrc")
 HOST = os.path.join(PKG, "host")
 LIB_CUDA = os.path.join(PKG, "libb200rt.so")
 LIB_HOST = os.path.join(PKG, "librtiaw_host.so")
+APP = os.path.join(PKG, "rtiaw_app")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -58,7 +59,19 @@ def build_host(force: bool = False) -> str:
     return LIB_HOST
 
 
+def build_app(force: bool = False) -> str:
+    """The reference CLI (src/app/main.rs) over the host mirror."""
+    srcs = _sources(HOST, (".cpp", ".hpp")) + [os.path.join(ROOT, "include", "b200rt.h")]
+    if force or _stale(APP, srcs):
+        build_cuda()
+        flags = [f for f in GXX_FLAGS if f not in ("-shared", "-fPIC")]
+        cmd = ["g++"] + flags + ["-I", os.path.join(ROOT, "include"), "-o", APP, os.path.join(HOST, "main.cpp"),
+               "-L", PKG, "-lb200rt", "-Wl,-rpath,$ORIGIN"]
+        subprocess.check_call(cmd)
+    return APP
+
+
 def build_all(force: bool = False) -> None:
     build_cuda(force)
-    if os.path.exists(os.path.join(HOST, "rtiaw_capi.cpp")):
-        build_host(force)
+    build_host(force)
+    build_app(force)

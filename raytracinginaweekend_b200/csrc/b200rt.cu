@@ -11,6 +11,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -61,6 +63,30 @@ struct DevBuf {
 
 }  // namespace
 
+// Render workspace (path-state queues, accumulators, counters): one per device, shared by all scenes of the process and
+// reused across renders, so creating / destroying a scene never pays for gigabytes of cudaMalloc.  Renders on the same
+// device are serialised by `mu` (rt_render* stays blocking and thread-safe).
+struct Workspace {
+    std::mutex mu;
+    DevBuf<float4> A[2], B[2], C[2], acc;
+    DevBuf<int32_t> D[2];
+    DevBuf<uint2> hits;
+    DevBuf<Counters> ctr;
+    DevBuf<float> film;
+    Counters* h_ctr = nullptr;  // pinned, 2 entries (double-buffered poll)
+    cudaEvent_t poll_event[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> prof_events;
+    size_t ws_slots = 0;
+};
+static std::mutex g_ws_mu;
+static std::map<int, Workspace*> g_ws;  // never freed: lives as long as the process (the CUDA context may already be gone at exit)
+static Workspace& workspace_of(int device) {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    Workspace*& w = g_ws[device];
+    if (!w) w = new Workspace();
+    return *w;
+}
+
 struct RtScene {
     int device = 0;
     int sm_count = 0;
@@ -74,21 +100,8 @@ struct RtScene {
     std::vector<DevBuf<uint8_t>*> images;
     uint64_t device_bytes = 0;
     uint32_t depth = 0;
-    // render workspace (grown on demand, reused across renders)
-    DevBuf<float4> A[2], B[2], C[2], acc;
-    DevBuf<int32_t> D[2];
-    DevBuf<uint2> hits;
-    DevBuf<Counters> ctr;
-    DevBuf<float> film;
-    Counters* h_ctr = nullptr;  // pinned, 2 entries (double-buffered poll)
-    cudaEvent_t poll_event[2] = {nullptr, nullptr};
-    std::vector<cudaEvent_t> prof_events;
-    size_t ws_slots = 0;
     ~RtScene() {
         for (auto* b : images) delete b;
-        if (h_ctr) cudaFreeHost(h_ctr);
-        for (auto e : poll_event) if (e) cudaEventDestroy(e);
-        for (auto e : prof_events) cudaEventDestroy(e);
     }
 };
 
@@ -409,7 +422,7 @@ int persistent_grid(const RtScene& sc, K kernel, int block, size_t smem, int* ou
     return RT_OK;
 }
 
-int ensure_workspace(RtScene& sc, size_t slots, size_t npix) {
+int ensure_workspace(Workspace& sc, size_t slots, size_t npix) {
     if (sc.ws_slots < slots) {
         for (int q = 0; q < 2; ++q) {
             CU(sc.A[q].alloc(slots));
@@ -448,14 +461,16 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     const uint32_t n_local = (uint32_t)((n_tasks - lane_first + lane_stride - 1) / lane_stride);
     const size_t slots = (size_t)n_local * npix;
     if (slots > 0xFFFFFFF0ull) return fail(RT_EINVAL, "width*height*lanes exceeds 2^32 path slots");
-    int rc = ensure_workspace(sc, slots, npix);
+    Workspace& ws = workspace_of(sc.device);
+    std::lock_guard<std::mutex> ws_lock(ws.mu);
+    int rc = ensure_workspace(ws, slots, npix);
     if (rc) return rc;
 
     RenderDev R{};
-    for (int q = 0; q < 2; ++q) { R.A[q] = sc.A[q].p; R.B[q] = sc.B[q].p; R.C[q] = sc.C[q].p; R.D[q] = sc.D[q].p; }
-    R.hits = sc.hits.p;
-    R.acc = sc.acc.p;
-    R.ctr = sc.ctr.p;
+    for (int q = 0; q < 2; ++q) { R.A[q] = ws.A[q].p; R.B[q] = ws.B[q].p; R.C[q] = ws.C[q].p; R.D[q] = ws.D[q].p; }
+    R.hits = ws.hits.p;
+    R.acc = ws.acc.p;
+    R.ctr = ws.ctr.p;
     R.cap = (uint32_t)slots;
     R.refill_threshold = (uint32_t)std::min(32, std::max(1, g_opt_refill));
     R.leaf_weight = (uint32_t)std::max(1, g_opt_leaf_weight);
@@ -490,15 +505,15 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     double extend_ms = 0.0, shade_ms = 0.0;
     const int chunk = g_opt_check_every;
     // per-launch timing without extra synchronisation: 3 events per iteration, read back after the chunk's poll
-    if (g_opt_profile && sc.prof_events.size() < (size_t)(2 * 3 * chunk)) {
-        while (sc.prof_events.size() < (size_t)(2 * 3 * chunk)) {
+    if (g_opt_profile && ws.prof_events.size() < (size_t)(2 * 3 * chunk)) {
+        while (ws.prof_events.size() < (size_t)(2 * 3 * chunk)) {
             cudaEvent_t e;
             CU(cudaEventCreate(&e));
-            sc.prof_events.push_back(e);
+            ws.prof_events.push_back(e);
         }
     }
     for (int b = 0; b < 2; ++b)
-        if (!sc.poll_event[b]) CU(cudaEventCreate(&sc.poll_event[b]));
+        if (!ws.poll_event[b]) CU(cudaEventCreate(&ws.poll_event[b]));
     CU(cudaEventRecord(ev0, stream));
     {
         int ggrid = (int)std::min<size_t>((slots + 255) / 256, (size_t)sc.sm_count * 8);
@@ -513,7 +528,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     int q_after[2] = {0, 0};
     auto enqueue_chunk = [&](int buf) -> int {
         for (int it = 0; it < chunk; ++it) {
-            cudaEvent_t* pe = g_opt_profile ? &sc.prof_events[(size_t)(buf * chunk + it) * 3] : nullptr;
+            cudaEvent_t* pe = g_opt_profile ? &ws.prof_events[(size_t)(buf * chunk + it) * 3] : nullptr;
             if (pe) CU(cudaEventRecord(pe[0], stream));
             ext<<<egrid, eblock, esmem, stream>>>(sc.dev, R, q);
             if (pe) CU(cudaEventRecord(pe[1], stream));
@@ -523,15 +538,15 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
             ++iters;
             q ^= 1;
         }
-        CU(cudaMemcpyAsync(&sc.h_ctr[buf], sc.ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-        CU(cudaEventRecord(sc.poll_event[buf], stream));
+        CU(cudaMemcpyAsync(&ws.h_ctr[buf], ws.ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+        CU(cudaEventRecord(ws.poll_event[buf], stream));
         q_after[buf] = q;  // the queue the next iteration would read
         return RT_OK;
     };
     auto harvest = [&](int buf) -> int {
         if (!g_opt_profile) return RT_OK;
         for (int it = 0; it < chunk; ++it) {
-            cudaEvent_t* pe = &sc.prof_events[(size_t)(buf * chunk + it) * 3];
+            cudaEvent_t* pe = &ws.prof_events[(size_t)(buf * chunk + it) * 3];
             float a = 0.0f, b2 = 0.0f;
             CU(cudaEventElapsedTime(&a, pe[0], pe[1]));
             CU(cudaEventElapsedTime(&b2, pe[1], pe[2]));
@@ -547,16 +562,16 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     for (;;) {
         rc = enqueue_chunk(buf ^ 1);
         if (rc) return rc;
-        CU(cudaEventSynchronize(sc.poll_event[buf]));
+        CU(cudaEventSynchronize(ws.poll_event[buf]));
         rc = harvest(buf);
         if (rc) return rc;
-        const bool drained = sc.h_ctr[buf].nb[q_after[buf]] + sc.h_ctr[buf].nn[q_after[buf]] == 0;
+        const bool drained = ws.h_ctr[buf].nb[q_after[buf]] + ws.h_ctr[buf].nn[q_after[buf]] == 0;
         buf ^= 1;
         if (drained) {  // the chunk already in flight only runs empty iterations
-            CU(cudaEventSynchronize(sc.poll_event[buf]));
+            CU(cudaEventSynchronize(ws.poll_event[buf]));
             rc = harvest(buf);
             if (rc) return rc;
-            final_ctr = &sc.h_ctr[buf];
+            final_ctr = &ws.h_ctr[buf];
             break;
         }
         if (iters > max_iters) return fail(RT_ECUDA, "wavefront loop did not terminate");
@@ -708,10 +723,11 @@ int rt_render(RtScene* scene, const RtRenderParams* params, float* out_rgb, RtSt
     if (params->width < 2 || params->height < 2) return fail(RT_EINVAL, "image must be at least 2x2");
     CU(cudaSetDevice(scene->device));
     const size_t n = (size_t)params->width * params->height * 3;
-    if (scene->film.n < n) CU(scene->film.alloc(n));
-    int rc = render_core(*scene, *params, 0, 1, scene->film.p, true, nullptr, out_stats);
+    DevBuf<float> film;  // 25 MB at 1080p: cheap next to the render; the big buffers live in the per-device workspace
+    CU(film.alloc(n));
+    int rc = render_core(*scene, *params, 0, 1, film.p, true, nullptr, out_stats);
     if (rc) return rc;
-    CU(cudaMemcpy(out_rgb, scene->film.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_rgb, film.p, n * sizeof(float), cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 
