@@ -212,6 +212,9 @@ def main():
         step_ms.append(e0.elapsed_time(e1))
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    per_rank = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(n_gpus)]
+    if n_gpus > 1:
+        dist.all_gather(per_rank, torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev))
     t_local = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     rays_local = torch.tensor([float(sum(s["ray_segments"] for s in stats))], dtype=torch.float64, device=dev)
     if n_gpus > 1:
@@ -271,7 +274,8 @@ def main():
                        "spp_total": spp_total, "max_depth": MAX_DEPTH, "sample_lanes_per_gpu": wl["lanes"],
                        "parallelism": f"sample-lane sharding x{n_gpus}, NCCL all-reduce of the film",
                        "l2": "256 MB flush between steps; path-state working set %.1f GB > L2" % (wl["lanes"] * size.count() * 136 / 1e9),
-                       "ray_segments_per_step": total_rays / args.steps},
+                       "ray_segments_per_step": total_rays / args.steps,
+                       "per_rank_ms_per_step": [float(t.item()) / args.steps for t in per_rank] if n_gpus > 1 else [total_ms / args.steps]},
             "roofline": {"kernel": "k_extend", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                          "bytes_per_ray": EXTEND_BYTES_PER_RAY, "launches": n_ext, "avg_launch_ms": ext_ms / max(1, n_ext),
