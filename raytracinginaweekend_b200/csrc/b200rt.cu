@@ -25,8 +25,9 @@ namespace {
 
 thread_local std::string g_err;
 int g_opt_traversal = 2;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path
-int g_opt_leaf_weight = 16;   // extend phase vote: leaf phase when n_leaf * w > n_node * 16
-int g_opt_refill = 20;        // extend refills idle lanes when fewer than this many of 32 are busy
+int g_opt_pipes = 2;         // independent wavefront pipelines (streams) per render: one pipeline's extend tail overlaps the other's work
+int g_opt_leaf_weight = 24;   // extend phase vote: leaf phase when n_leaf * w > n_node * 16
+int g_opt_refill = 28;        // extend refills idle lanes when fewer than this many of 32 are busy
 int g_opt_count = 0;        // 1 = COUNT kernel variant (node visits / primitive tests per ray)
 int g_opt_profile = 0;        // 1 = time every extend / shade launch with CUDA events on the launching stream (no extra syncs)
 int g_opt_check_every = 8;    // host polls the live-path count every N iterations
@@ -73,9 +74,12 @@ struct Workspace {
     DevBuf<uint2> hits;
     DevBuf<Counters> ctr;
     DevBuf<float> film;
-    Counters* h_ctr = nullptr;  // pinned, 2 entries (double-buffered poll)
-    cudaEvent_t poll_event[2] = {nullptr, nullptr};
-    std::vector<cudaEvent_t> prof_events;
+    static const int MAX_PIPES = 8;
+    Counters* h_ctr = nullptr;  // pinned, MAX_PIPES x 2 entries (double-buffered poll per pipeline)
+    cudaEvent_t poll_event[MAX_PIPES][2] = {};
+    cudaStream_t pipe_stream[MAX_PIPES] = {};
+    cudaEvent_t fork_event = nullptr, join_event[MAX_PIPES] = {};
+    std::vector<cudaEvent_t> prof_events[MAX_PIPES];
     size_t ws_slots = 0;
 };
 static std::mutex g_ws_mu;
@@ -434,8 +438,16 @@ int ensure_workspace(Workspace& sc, size_t slots, size_t npix) {
         CU(sc.acc.alloc(slots));
         sc.ws_slots = slots;
     }
-    if (!sc.ctr.p) CU(sc.ctr.alloc(1));
-    if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, 2 * sizeof(Counters)));
+    if (!sc.ctr.p) CU(sc.ctr.alloc(Workspace::MAX_PIPES));
+    if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, Workspace::MAX_PIPES * 2 * sizeof(Counters)));
+    if (!sc.fork_event) {
+        CU(cudaEventCreateWithFlags(&sc.fork_event, cudaEventDisableTiming));
+        for (int p = 0; p < Workspace::MAX_PIPES; ++p) {
+            CU(cudaStreamCreateWithFlags(&sc.pipe_stream[p], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&sc.join_event[p], cudaEventDisableTiming));
+            for (int b = 0; b < 2; ++b) CU(cudaEventCreate(&sc.poll_event[p][b]));
+        }
+    }
     if (sc.film.n < npix * 3) CU(sc.film.alloc(npix * 3));
     return RT_OK;
 }
@@ -466,14 +478,8 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     int rc = ensure_workspace(ws, slots, npix);
     if (rc) return rc;
 
-    RenderDev R{};
-    for (int q = 0; q < 2; ++q) { R.A[q] = ws.A[q].p; R.B[q] = ws.B[q].p; R.C[q] = ws.C[q].p; R.D[q] = ws.D[q].p; }
-    R.hits = ws.hits.p;
+    RenderDev R{};   // rank-level description (k_finalize uses it as is)
     R.acc = ws.acc.p;
-    R.ctr = ws.ctr.p;
-    R.cap = (uint32_t)slots;
-    R.refill_threshold = (uint32_t)std::min(32, std::max(1, g_opt_refill));
-    R.leaf_weight = (uint32_t)std::max(1, g_opt_leaf_weight);
     R.npix = (uint32_t)npix; R.width = (uint32_t)P.width; R.height = (uint32_t)P.height;
     R.max_depth = P.max_depth;
     R.n_tasks = (uint32_t)n_tasks;
@@ -485,6 +491,37 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     R.sy = 1.0f / (float)(P.height - 1);
     R.mode = P.render_mode;
     R.ref_only = g_opt_traversal == 0 ? 1u : 0u;
+    R.refill_threshold = (uint32_t)std::min(32, std::max(1, g_opt_refill));
+    R.leaf_weight = (uint32_t)std::max(1, g_opt_leaf_weight);
+
+    // Split the rank's lanes over G independent wavefront pipelines, each on its own stream with its own queues and
+    // counters.  A persistent extend launch ends with a tail in which a few very long rays keep a few warps busy; with two
+    // pipelines in flight the other pipeline's blocks backfill the SMs during that tail (and during shade / launch gaps).
+    const int G = (int)std::min<uint32_t>((uint32_t)std::max(1, std::min(g_opt_pipes, (int)Workspace::MAX_PIPES)), n_local);
+    struct Pipe {
+        RenderDev R;
+        cudaStream_t st;
+        int q = 0, buf = 0, q_after[2] = {0, 0};
+        bool done = false;
+        uint64_t iters = 0;
+        const Counters* final_ctr = nullptr;
+    };
+    std::vector<Pipe> pipes(G);
+    {
+        size_t off = 0;
+        for (int p = 0; p < G; ++p) {
+            Pipe& pp = pipes[p];
+            const uint32_t lanes_p = (n_local - (uint32_t)p + (uint32_t)G - 1u) / (uint32_t)G;
+            pp.R = R;
+            pp.R.pipe = (uint32_t)p; pp.R.n_pipes = (uint32_t)G;
+            pp.R.cap = (uint32_t)((size_t)lanes_p * npix);
+            for (int q = 0; q < 2; ++q) { pp.R.A[q] = ws.A[q].p + off; pp.R.B[q] = ws.B[q].p + off; pp.R.C[q] = ws.C[q].p + off; pp.R.D[q] = ws.D[q].p + off; }
+            pp.R.hits = ws.hits.p + off;
+            pp.R.ctr = ws.ctr.p + p;
+            pp.st = ws.pipe_stream[p];
+            off += pp.R.cap;
+        }
+    }
 
     const int eblock = 128;
     const size_t esmem = stack_smem_bytes(sc, eblock);
@@ -501,80 +538,90 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     cudaEvent_t ev0, ev1;
     CU(cudaEventCreate(&ev0));
     CU(cudaEventCreate(&ev1));
-    uint64_t launches = 0, iters = 0;
+    uint64_t launches = 0;
     double extend_ms = 0.0, shade_ms = 0.0;
     const int chunk = g_opt_check_every;
     // per-launch timing without extra synchronisation: 3 events per iteration, read back after the chunk's poll
-    if (g_opt_profile && ws.prof_events.size() < (size_t)(2 * 3 * chunk)) {
-        while (ws.prof_events.size() < (size_t)(2 * 3 * chunk)) {
-            cudaEvent_t e;
-            CU(cudaEventCreate(&e));
-            ws.prof_events.push_back(e);
-        }
+    if (g_opt_profile) {
+        for (int p = 0; p < G; ++p)
+            while (ws.prof_events[p].size() < (size_t)(2 * 3 * chunk)) {
+                cudaEvent_t e;
+                CU(cudaEventCreate(&e));
+                ws.prof_events[p].push_back(e);
+            }
     }
-    for (int b = 0; b < 2; ++b)
-        if (!ws.poll_event[b]) CU(cudaEventCreate(&ws.poll_event[b]));
     CU(cudaEventRecord(ev0, stream));
-    {
-        int ggrid = (int)std::min<size_t>((slots + 255) / 256, (size_t)sc.sm_count * 8);
-        k_generate<<<ggrid, 256, 0, stream>>>(sc.dev, R);
+    CU(cudaEventRecord(ws.fork_event, stream));
+    for (int p = 0; p < G; ++p) {
+        Pipe& pp = pipes[p];
+        CU(cudaStreamWaitEvent(pp.st, ws.fork_event, 0));
+        int ggrid = (int)std::min<size_t>(((size_t)pp.R.cap + 255) / 256, (size_t)sc.sm_count * 8);
+        k_generate<<<ggrid, 256, 0, pp.st>>>(sc.dev, pp.R);
         ++launches;
     }
-    int q = 0;
     const uint64_t max_iters = (uint64_t)(R.spp_whole + 1u) * (uint64_t)std::max(P.max_depth, 1) + 4 + 2 * (uint64_t)chunk;
     // The host never knows the live-path count of the iteration it is launching: kernels read it from device memory
     // (grids are persistent, sized by the SM count).  Every `chunk` iterations the counters are copied to pinned memory;
-    // the host keeps one chunk in flight while it waits for the previous chunk's copy, so the GPU never idles on the poll.
-    int q_after[2] = {0, 0};
-    auto enqueue_chunk = [&](int buf) -> int {
+    // the host keeps one chunk in flight per pipeline while it waits for the previous chunk's copy.
+    auto enqueue_chunk = [&](int p, int buf) -> int {
+        Pipe& pp = pipes[p];
         for (int it = 0; it < chunk; ++it) {
-            cudaEvent_t* pe = g_opt_profile ? &ws.prof_events[(size_t)(buf * chunk + it) * 3] : nullptr;
-            if (pe) CU(cudaEventRecord(pe[0], stream));
-            ext<<<egrid, eblock, esmem, stream>>>(sc.dev, R, q);
-            if (pe) CU(cudaEventRecord(pe[1], stream));
-            k_shade<<<sgrid, 128, 0, stream>>>(sc.dev, R, q);
-            if (pe) CU(cudaEventRecord(pe[2], stream));
+            cudaEvent_t* pe = g_opt_profile ? &ws.prof_events[p][(size_t)(buf * chunk + it) * 3] : nullptr;
+            if (pe) CU(cudaEventRecord(pe[0], pp.st));
+            ext<<<egrid, eblock, esmem, pp.st>>>(sc.dev, pp.R, pp.q);
+            if (pe) CU(cudaEventRecord(pe[1], pp.st));
+            k_shade<<<sgrid, 128, 0, pp.st>>>(sc.dev, pp.R, pp.q);
+            if (pe) CU(cudaEventRecord(pe[2], pp.st));
             launches += 2;
-            ++iters;
-            q ^= 1;
+            ++pp.iters;
+            pp.q ^= 1;
         }
-        CU(cudaMemcpyAsync(&ws.h_ctr[buf], ws.ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-        CU(cudaEventRecord(ws.poll_event[buf], stream));
-        q_after[buf] = q;  // the queue the next iteration would read
+        CU(cudaMemcpyAsync(&ws.h_ctr[p * 2 + buf], pp.R.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, pp.st));
+        CU(cudaEventRecord(ws.poll_event[p][buf], pp.st));
+        pp.q_after[buf] = pp.q;  // the queue the next iteration would read
         return RT_OK;
     };
-    auto harvest = [&](int buf) -> int {
+    auto harvest = [&](int p, int buf) -> int {
         if (!g_opt_profile) return RT_OK;
         for (int it = 0; it < chunk; ++it) {
-            cudaEvent_t* pe = &ws.prof_events[(size_t)(buf * chunk + it) * 3];
+            cudaEvent_t* pe = &ws.prof_events[p][(size_t)(buf * chunk + it) * 3];
             float a = 0.0f, b2 = 0.0f;
             CU(cudaEventElapsedTime(&a, pe[0], pe[1]));
             CU(cudaEventElapsedTime(&b2, pe[1], pe[2]));
-            extend_ms += a;
+            extend_ms += a;   // with G > 1 the pipelines overlap: these are per-kernel device times, not wall time
             shade_ms += b2;
         }
         return RT_OK;
     };
-    int buf = 0;
-    rc = enqueue_chunk(buf);
-    if (rc) return rc;
-    const Counters* final_ctr = nullptr;
-    for (;;) {
-        rc = enqueue_chunk(buf ^ 1);
+    for (int p = 0; p < G; ++p) {
+        rc = enqueue_chunk(p, 0);
         if (rc) return rc;
-        CU(cudaEventSynchronize(ws.poll_event[buf]));
-        rc = harvest(buf);
-        if (rc) return rc;
-        const bool drained = ws.h_ctr[buf].nb[q_after[buf]] + ws.h_ctr[buf].nn[q_after[buf]] == 0;
-        buf ^= 1;
-        if (drained) {  // the chunk already in flight only runs empty iterations
-            CU(cudaEventSynchronize(ws.poll_event[buf]));
-            rc = harvest(buf);
+    }
+    int live = G;
+    while (live > 0) {
+        for (int p = 0; p < G; ++p) {
+            Pipe& pp = pipes[p];
+            if (pp.done) continue;
+            rc = enqueue_chunk(p, pp.buf ^ 1);
             if (rc) return rc;
-            final_ctr = &ws.h_ctr[buf];
-            break;
+            CU(cudaEventSynchronize(ws.poll_event[p][pp.buf]));
+            rc = harvest(p, pp.buf);
+            if (rc) return rc;
+            const Counters& hc = ws.h_ctr[p * 2 + pp.buf];
+            const bool drained = hc.nb[pp.q_after[pp.buf]] + hc.nn[pp.q_after[pp.buf]] == 0;
+            pp.buf ^= 1;
+            if (drained) {  // the chunk already in flight only runs empty iterations
+                CU(cudaEventSynchronize(ws.poll_event[p][pp.buf]));
+                rc = harvest(p, pp.buf);
+                if (rc) return rc;
+                pp.final_ctr = &ws.h_ctr[p * 2 + pp.buf];
+                pp.done = true;
+                --live;
+                CU(cudaEventRecord(ws.join_event[p], pp.st));
+                CU(cudaStreamWaitEvent(stream, ws.join_event[p], 0));
+            }
+            if (pp.iters > max_iters) return fail(RT_ECUDA, "wavefront loop did not terminate");
         }
-        if (iters > max_iters) return fail(RT_ECUDA, "wavefront loop did not terminate");
     }
     {
         int fgrid = (int)std::min<size_t>((npix + 255) / 256, (size_t)sc.sm_count * 8);
@@ -587,6 +634,14 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     float ms = 0.0f;
     CU(cudaEventElapsedTime(&ms, ev0, ev1));
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    Counters total{};
+    uint64_t iters = 0;
+    for (const Pipe& pp : pipes) {
+        total.rays += pp.final_ctr->rays; total.paths += pp.final_ctr->paths;
+        total.node_visits += pp.final_ctr->node_visits; total.prim_tests += pp.final_ctr->prim_tests; total.exact_steps += pp.final_ctr->exact_steps;
+        iters = std::max(iters, pp.iters);
+    }
+    const Counters* final_ctr = &total;
     if (stats) {
         stats->ray_segments = final_ctr->rays;
         stats->paths = final_ctr->paths;
@@ -622,6 +677,7 @@ int rt_set_option(const char* key, int64_t value) {
     else if (k == "count") g_opt_count = (int)value;
     else if (k == "refill") g_opt_refill = (int)value;
     else if (k == "leaf_weight") g_opt_leaf_weight = (int)value;
+    else if (k == "pipes") g_opt_pipes = (int)value;
     else if (k == "check_every") g_opt_check_every = std::max<int>(1, (int)value);
     else if (k == "blocks_per_sm") g_opt_blocks_per_sm = (int)value;
     else return fail(RT_EINVAL, "unknown option " + k);

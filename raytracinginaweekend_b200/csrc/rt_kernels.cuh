@@ -29,7 +29,8 @@ struct RenderDev {
     uint2* hits;    // (child ref of closest primitive | RT_NO_HIT, bits(t)) per queue position
     float4* acc;    // [n_local_lanes * npix] running per-lane sums (exclusive owner: the slot's single live path)
     Counters* ctr;
-    uint32_t cap;            // queue capacity = number of path slots
+    uint32_t cap;            // queue capacity = number of path slots of THIS pipeline
+    uint32_t pipe, n_pipes;  // rank-local lanes are dealt round-robin to n_pipes independent wavefront pipelines (streams)
     uint32_t refill_threshold;  // extend refills idle lanes when fewer than this many lanes are busy
     uint32_t leaf_weight;       // phase vote: leaf phase runs when n_leaf * leaf_weight > n_node * 16
     uint32_t npix, width, height;
@@ -62,17 +63,18 @@ __device__ __forceinline__ void generate_path(const SceneDev& S, const RenderDev
 }
 
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R) {
-    uint32_t n_slots = R.n_local_lanes * R.npix;
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += gridDim.x * blockDim.x) {
-        uint32_t pixel = slot % R.npix, local_lane = slot / R.npix;
-        uint32_t lane_id = R.lane_first + local_lane * R.lane_stride;
+    const uint32_t n_slots = R.cap;  // this pipeline's lanes: rank-local lane = pipe + n_pipes * m
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_slots; j += gridDim.x * blockDim.x) {
+        const uint32_t pixel = j % R.npix, local_lane = R.pipe + R.n_pipes * (j / R.npix);
+        const uint32_t slot = local_lane * R.npix + pixel;  // accumulator index, unique across pipelines
+        const uint32_t lane_id = R.lane_first + local_lane * R.lane_stride;
         float3 o, d;
         generate_path(S, R, pixel, lane_id, 0u, o, d);
-        R.A[0][slot] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
+        R.A[0][j] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
         const uint32_t miss = root_gate(S, o, d, 0.001f, __int_as_float(0x7f800000), R.ref_only != 0u) ? 0u : RT_ROOT_MISS;
-        R.B[0][slot] = make_float4(d.x, d.y, d.z, __uint_as_float(miss));
-        R.C[0][slot] = make_float4(1.0f, 1.0f, 1.0f, d.y);
-        R.D[0][slot] = R.max_depth;
+        R.B[0][j] = make_float4(d.x, d.y, d.z, __uint_as_float(miss));
+        R.C[0][j] = make_float4(1.0f, 1.0f, 1.0f, d.y);
+        R.D[0][j] = R.max_depth;
         R.acc[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
