@@ -8,8 +8,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -25,7 +27,7 @@ namespace {
 
 thread_local std::string g_err;
 int g_opt_traversal = 2;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path
-int g_opt_pipes = 2;         // independent wavefront pipelines (streams) per render: one pipeline's extend tail overlaps the other's work
+int g_opt_pipes = 1;         // independent wavefront pipelines (streams) per render: one pipeline's extend tail overlaps the other's work
 int g_opt_leaf_weight = 24;   // extend phase vote: leaf phase when n_leaf * w > n_node * 16
 int g_opt_refill = 28;        // extend refills idle lanes when fewer than this many of 32 are busy
 int g_opt_count = 0;        // 1 = COUNT kernel variant (node visits / primitive tests per ray)
@@ -80,6 +82,8 @@ struct Workspace {
     cudaStream_t pipe_stream[MAX_PIPES] = {};
     cudaEvent_t fork_event = nullptr, join_event[MAX_PIPES] = {};
     std::vector<cudaEvent_t> prof_events[MAX_PIPES];
+    DevBuf<uint32_t> iter_log;  // [MAX_PIPES][ITER_LOG_CAP], only with RT_ITER_LOG set
+    static const int ITER_LOG_CAP = 16384;
     size_t ws_slots = 0;
 };
 static std::mutex g_ws_mu;
@@ -497,6 +501,9 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     // Split the rank's lanes over G independent wavefront pipelines, each on its own stream with its own queues and
     // counters.  A persistent extend launch ends with a tail in which a few very long rays keep a few warps busy; with two
     // pipelines in flight the other pipeline's blocks backfill the SMs during that tail (and during shade / launch gaps).
+    const char* iter_log_path = std::getenv("RT_ITER_LOG");  // debug: dump (pipe, iteration, live paths, extend ms, shade ms)
+    if (iter_log_path && !ws.iter_log.p) CU(ws.iter_log.alloc((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP));
+    std::vector<std::array<float, 2>> iter_ms[Workspace::MAX_PIPES];
     const int G = (int)std::min<uint32_t>((uint32_t)std::max(1, std::min(g_opt_pipes, (int)Workspace::MAX_PIPES)), n_local);
     struct Pipe {
         RenderDev R;
@@ -519,6 +526,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
             pp.R.hits = ws.hits.p + off;
             pp.R.ctr = ws.ctr.p + p;
             pp.st = ws.pipe_stream[p];
+            pp.R.iter_log = iter_log_path ? ws.iter_log.p + (size_t)p * Workspace::ITER_LOG_CAP : nullptr;
             off += pp.R.cap;
         }
     }
@@ -568,6 +576,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
         for (int it = 0; it < chunk; ++it) {
             cudaEvent_t* pe = g_opt_profile ? &ws.prof_events[p][(size_t)(buf * chunk + it) * 3] : nullptr;
             if (pe) CU(cudaEventRecord(pe[0], pp.st));
+            pp.R.iter = (uint32_t)std::min<uint64_t>(pp.iters, Workspace::ITER_LOG_CAP - 1);
             ext<<<egrid, eblock, esmem, pp.st>>>(sc.dev, pp.R, pp.q);
             if (pe) CU(cudaEventRecord(pe[1], pp.st));
             k_shade<<<sgrid, 128, 0, pp.st>>>(sc.dev, pp.R, pp.q);
@@ -590,6 +599,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
             CU(cudaEventElapsedTime(&b2, pe[1], pe[2]));
             extend_ms += a;   // with G > 1 the pipelines overlap: these are per-kernel device times, not wall time
             shade_ms += b2;
+            if (iter_log_path) iter_ms[p].push_back({a, b2});
         }
         return RT_OK;
     };
@@ -634,6 +644,18 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     float ms = 0.0f;
     CU(cudaEventElapsedTime(&ms, ev0, ev1));
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (iter_log_path) {
+        std::vector<uint32_t> lg((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP);
+        CU(cudaMemcpy(lg.data(), ws.iter_log.p, lg.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (FILE* f = std::fopen(iter_log_path, "w")) {
+            std::fprintf(f, "pipe,iter,rays,extend_ms,shade_ms\n");
+            for (int p = 0; p < G; ++p)
+                for (size_t i = 0; i < pipes[p].iters && i < (size_t)Workspace::ITER_LOG_CAP; ++i)
+                    std::fprintf(f, "%d,%zu,%u,%.4f,%.4f\n", p, i, lg[(size_t)p * Workspace::ITER_LOG_CAP + i],
+                                 i < iter_ms[p].size() ? iter_ms[p][i][0] : -1.0f, i < iter_ms[p].size() ? iter_ms[p][i][1] : -1.0f);
+            std::fclose(f);
+        }
+    }
     Counters total{};
     uint64_t iters = 0;
     for (const Pipe& pp : pipes) {

@@ -30,6 +30,8 @@ struct RenderDev {
     float4* acc;    // [n_local_lanes * npix] running per-lane sums (exclusive owner: the slot's single live path)
     Counters* ctr;
     uint32_t cap;            // queue capacity = number of path slots of THIS pipeline
+    uint32_t* iter_log;      // optional [max_iters]: live paths of each iteration (debug / per-launch accounting)
+    uint32_t iter;           // iteration index of this launch (only used with iter_log)
     uint32_t pipe, n_pipes;  // rank-local lanes are dealt round-robin to n_pipes independent wavefront pipelines (streams)
     uint32_t refill_threshold;  // extend refills idle lanes when fewer than this many lanes are busy
     uint32_t leaf_weight;       // phase vote: leaf phase runs when n_leaf * leaf_weight > n_node * 16
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         R.ctr->cursor_extend = 0;
         R.ctr->rays += n;
+        if (R.iter_log) R.iter_log[R.iter] = n;
     }
     uint32_t new_paths = 0;
     for (uint32_t base = warp_global * 32u; base < n; base += n_warps * 32u) {
