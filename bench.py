@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {  # BASELINE.json configs (DESIGN.md "Workload definitions")
     "c1": dict(world="config:c1", width=1200, height=800, spp=10, lanes=10, cpu_sample=(300, 200, 4)),
-    "c2": dict(world="config:c2", width=1920, height=1080, spp=64, lanes=32, cpu_sample=(320, 180, 4)),
+    "c2": dict(world="config:c2", width=1920, height=1080, spp=64, lanes=64, cpu_sample=(320, 180, 4)),
     "c3": dict(world="config:c3", width=1024, height=1024, spp=256, lanes=32, cpu_sample=(256, 256, 16)),
     "c4": dict(world="config:c4", width=3840, height=2160, spp=16, lanes=1, cpu_sample=(240, 135, 2)),
     "c5": dict(world="config:c5", width=3840, height=2160, spp=4096, lanes=8, cpu_sample=(240, 135, 2)),

@@ -185,7 +185,10 @@ int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_o
 /* Knobs (process-wide).  "traversal": 0 = reference node test only, true divisions (the reference's algorithm, for A/B
  * parity sweeps); 1 = + tight carried-interval cull; 2 = + reciprocal fast path with exact fallback (default).
  * "count": 1 = maintain node_visits / prim_tests / exact_steps.  "profile": 1 = time extend / shade separately.
- * "refill": busy-lane threshold of the persistent extend warps.  "check_every": host polling period (iterations). */
+ * "refill": busy-lane threshold of the persistent extend warps.  "leaf_weight": phase-vote weight.  "check_every": host
+ * polling period (iterations).  "pipes": independent wavefront pipelines (streams) per render (default 1).
+ * "blocks_per_sm": cap on resident blocks of the persistent kernels.
+ * Environment: RT_ITER_LOG=<path> dumps (pipe, iteration, live paths, extend ms, shade ms) of the last render as CSV. */
 int rt_set_option(const char* key, int64_t value);
 
 #ifdef __cplusplus
