@@ -502,7 +502,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     // counters.  A persistent extend launch ends with a tail in which a few very long rays keep a few warps busy; with two
     // pipelines in flight the other pipeline's blocks backfill the SMs during that tail (and during shade / launch gaps).
     const char* iter_log_path = std::getenv("RT_ITER_LOG");  // debug: dump (pipe, iteration, live paths, extend ms, shade ms)
-    if (iter_log_path && !ws.iter_log.p) CU(ws.iter_log.alloc((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP));
+    if (iter_log_path && !ws.iter_log.p) CU(ws.iter_log.alloc((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP * 8));
     std::vector<std::array<float, 2>> iter_ms[Workspace::MAX_PIPES];
     const int G = (int)std::min<uint32_t>((uint32_t)std::max(1, std::min(g_opt_pipes, (int)Workspace::MAX_PIPES)), n_local);
     struct Pipe {
@@ -526,7 +526,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
             pp.R.hits = ws.hits.p + off;
             pp.R.ctr = ws.ctr.p + p;
             pp.st = ws.pipe_stream[p];
-            pp.R.iter_log = iter_log_path ? ws.iter_log.p + (size_t)p * Workspace::ITER_LOG_CAP : nullptr;
+            pp.R.iter_log = iter_log_path ? ws.iter_log.p + (size_t)p * Workspace::ITER_LOG_CAP * 8 : nullptr;
             off += pp.R.cap;
         }
     }
@@ -645,14 +645,18 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     CU(cudaEventElapsedTime(&ms, ev0, ev1));
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (iter_log_path) {
-        std::vector<uint32_t> lg((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP);
+        std::vector<uint32_t> lg((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP * 8);
         CU(cudaMemcpy(lg.data(), ws.iter_log.p, lg.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         if (FILE* f = std::fopen(iter_log_path, "w")) {
-            std::fprintf(f, "pipe,iter,rays,extend_ms,shade_ms\n");
+            std::fprintf(f, "pipe,iter,rays,extend_ms,shade_ms,cum_nodes_div64,cum_prims_div64,cum_rounds_div16,cum_busy_div256,cum_trounds_div16,cum_tbusy_div256\n");
             for (int p = 0; p < G; ++p)
-                for (size_t i = 0; i < pipes[p].iters && i < (size_t)Workspace::ITER_LOG_CAP; ++i)
-                    std::fprintf(f, "%d,%zu,%u,%.4f,%.4f\n", p, i, lg[(size_t)p * Workspace::ITER_LOG_CAP + i],
-                                 i < iter_ms[p].size() ? iter_ms[p][i][0] : -1.0f, i < iter_ms[p].size() ? iter_ms[p][i][1] : -1.0f);
+                for (size_t i = 0; i < pipes[p].iters && i < (size_t)Workspace::ITER_LOG_CAP; ++i) {
+                    const uint32_t* L = &lg[(size_t)p * Workspace::ITER_LOG_CAP * 8];
+                    std::fprintf(f, "%d,%zu,%u,%.4f,%.4f,%u,%u,%u,%u,%u,%u\n", p, i, L[i],
+                                 i < iter_ms[p].size() ? iter_ms[p][i][0] : -1.0f, i < iter_ms[p].size() ? iter_ms[p][i][1] : -1.0f,
+                                 L[Workspace::ITER_LOG_CAP + i], L[2 * Workspace::ITER_LOG_CAP + i], L[4 * Workspace::ITER_LOG_CAP + i],
+                                 L[5 * Workspace::ITER_LOG_CAP + i], L[6 * Workspace::ITER_LOG_CAP + i], L[7 * Workspace::ITER_LOG_CAP + i]);
+                }
             std::fclose(f);
         }
     }

@@ -371,8 +371,14 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
             pR = !cullR && sureR;
             need_exact = (!cullL && !sureL) || (!cullR && !sureR);
             if (PLANE && !need_exact) {
-                if (pL && (q3.x >> RT_REF_KIND_SHIFT) == 6u) pL = !tri_plane_reject(S, T, q3.x, tnL, tfL, mgL);  // 6 = leaf bit | triangle
-                if (pR && (q3.y >> RT_REF_KIND_SHIFT) == 6u) pR = !tri_plane_reject(S, T, q3.y, tnR, tfR, mgR);
+                // one shared code path for both children (6 = leaf bit | triangle kind): lanes with a pending child run the
+                // body together instead of serialising a "left" and a "right" copy with a handful of lanes each
+                bool wantL = pL && (q3.x >> RT_REF_KIND_SHIFT) == 6u, wantR = pR && (q3.y >> RT_REF_KIND_SHIFT) == 6u;
+                while (wantL || wantR) {
+                    const bool useL = wantL;
+                    const bool rej = tri_plane_reject(S, T, useL ? q3.x : q3.y, useL ? tnL : tnR, useL ? tfL : tfR, useL ? mgL : mgR);
+                    if (useL) { pL = !rej; wantL = false; } else { pR = !rej; wantR = false; }
+                }
             }
         } else {
             need_exact = true;

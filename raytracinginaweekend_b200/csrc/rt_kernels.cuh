@@ -19,6 +19,7 @@ struct Counters {
     unsigned long long rays;   // closest-hit queries so far
     unsigned long long paths;  // camera samples generated so far
     unsigned long long node_visits, prim_tests, exact_steps;  // only maintained by the COUNT kernel variant
+    unsigned long long rounds, busy_lanes, tail_rounds, tail_busy_lanes;  // COUNT: warp rounds / busy lanes, overall and after the queue ran dry
 };
 
 struct RenderDev {
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
         R.ctr->node_visits = 0;
         R.ctr->prim_tests = 0;
         R.ctr->exact_steps = 0;
+        R.ctr->rounds = 0; R.ctr->busy_lanes = 0; R.ctr->tail_rounds = 0; R.ctr->tail_busy_lanes = 0;
     }
 }
 
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
     uint32_t my_pos = 0;
     uint32_t batch_next = 0, batch_end = 0;  // warp-uniform: ray indices [batch_next, batch_end) already claimed by this warp
     uint32_t act_mask = 0;                   // warp-uniform ballot of `active`
+    unsigned long long rounds_c = 0, busy_c = 0, trounds_c = 0, tbusy_c = 0;
     for (;;) {
         // refill: idle lanes take rays from the warp's claimed batch (one atomic per 32 rays)
         if (act_mask != FULL && !(exhausted && batch_next == batch_end) && (uint32_t)__popc(act_mask) < R.refill_threshold) {
@@ -145,6 +148,10 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
             if (exhausted && batch_next == batch_end) break;
             continue;
         }
+        if (COUNT && lane == 0) {
+            rounds_c += 1u; busy_c += __popc(act_mask);
+            if (exhausted && batch_next == batch_end) { trounds_c += 1u; tbusy_c += __popc(act_mask); }
+        }
         // phase vote: run the leaf phase when (weighted) more lanes wait at a leaf than at an internal node
         const uint32_t n_leaf = __popc(__ballot_sync(FULL, active && (T.cur & RT_REF_LEAF)));
         const bool do_leaf = n_leaf * R.leaf_weight > ((uint32_t)__popc(act_mask) - n_leaf) * 16u;
@@ -166,6 +173,8 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
             atomicAdd(&R.ctr->node_visits, (unsigned long long)tc.nodes);
             atomicAdd(&R.ctr->prim_tests, (unsigned long long)tc.prims);
             atomicAdd(&R.ctr->exact_steps, (unsigned long long)tc.exact);
+            atomicAdd(&R.ctr->rounds, rounds_c); atomicAdd(&R.ctr->busy_lanes, busy_c);
+            atomicAdd(&R.ctr->tail_rounds, trounds_c); atomicAdd(&R.ctr->tail_busy_lanes, tbusy_c);
         }
     }
 }
@@ -180,7 +189,15 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         R.ctr->cursor_extend = 0;
         R.ctr->rays += n;
-        if (R.iter_log) R.iter_log[R.iter] = n;
+        if (R.iter_log) {  // [iter] live paths, [CAP + 2 iter] cumulative node visits (lo/hi), [3 CAP + 2 iter] cumulative prim tests
+            R.iter_log[R.iter] = n;
+            R.iter_log[16384u + R.iter] = (uint32_t)(R.ctr->node_visits >> 6);
+            R.iter_log[32768u + R.iter] = (uint32_t)(R.ctr->prim_tests >> 6);
+            R.iter_log[4u * 16384u + R.iter] = (uint32_t)(R.ctr->rounds >> 4);
+            R.iter_log[5u * 16384u + R.iter] = (uint32_t)(R.ctr->busy_lanes >> 8);
+            R.iter_log[6u * 16384u + R.iter] = (uint32_t)(R.ctr->tail_rounds >> 4);
+            R.iter_log[7u * 16384u + R.iter] = (uint32_t)(R.ctr->tail_busy_lanes >> 8);
+        }
     }
     uint32_t new_paths = 0;
     for (uint32_t base = warp_global * 32u; base < n; base += n_warps * 32u) {
