@@ -303,42 +303,14 @@ __device__ __forceinline__ void approx_slab(float mnx, float mny, float mnz, flo
     tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), T.end));
 }
 
-// Conservative plane pre-test for a TRIANGLE leaf child, evaluated inside the node step (fast path only).
-// The exact test (triangle_geometry.rs:13-45) can only accept when the ray crosses the triangle's plane inside the
-// triangle's AABB and inside [start, end).  With the approximate crossing distance tp = (p0 - o).n / (d.n) this rejects
-// the leaf when tp lies outside the leaf box's clipped interval [tn, tf] by more than the guard band plus the bound on
-// |tp - t_exact| — OBJ slivers have huge AABBs that most rays cross far away from the plane crossing.  Rejected leaves never
-// reach the (poorly populated) leaf phase; everything not provably rejected is left to the exact test.
-__device__ __forceinline__ bool tri_plane_reject(const SceneDev& S, const Trav& T, uint32_t ref, float tn, float tf, float mg) {
-    const float4* q = reinterpret_cast<const float4*>(S.prims + (ref & RT_REF_ITEM_MASK));
-    const float4 q0 = __ldg(q), q1 = __ldg(q + 1);  // p0.xyz n.x | n.yz ..
-    const float nx = q0.w, ny = q1.x, nz = q1.y;
-    const float px = q0.x - T.o.x, py = q0.y - T.o.y, pz = q0.z - T.o.z;
-    const float denom = __fmaf_rn(T.d.x, nx, __fmaf_rn(T.d.y, ny, T.d.z * nz));
-    const float num = __fmaf_rn(px, nx, __fmaf_rn(py, ny, pz * nz));
-    const float mag = __fmaf_rn(fabsf(px), fabsf(nx), __fmaf_rn(fabsf(py), fabsf(ny), fabsf(pz * nz)));  // cancellation-free size of num
-    const float ad = fabsf(denom);
-    if (ad < 0.9e-4f) return true;         // |d.n| <= 1e-4: the exact test treats the ray as parallel (margin 10 %)
-    if (!(ad > 1.1e-4f)) return false;     // too close to the threshold (or NaN): let the exact test decide
-    float rcp;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(denom));
-    const float tp = num * rcp;
-    const float band = 2e-6f * __fmaf_rn(2.0f, fabsf(tp), mag * fabsf(rcp)) + mg;
-    return (tp < tn - band) || (tp > tf + band);
-}
-
 // One scheduling round of a lane: a node step (if `do_leaf` is false and the lane is at an internal node) or a leaf
 // step (if `do_leaf` is true and the lane is at a leaf), followed by the pops it triggers; lanes in the other state
 // simply wait.  The warp picks `do_leaf` by vote (k_extend), so each phase runs with most lanes enabled instead of
 // interleaving 17-lane node steps with 4-lane leaf tests.  Per-lane visit order is untouched.
 // Returns false when the lane's traversal is finished.
-#ifndef RT_PLANE_PRETEST
-#define RT_PLANE_PRETEST 1
-#endif
 template <int MODE, bool COUNT>
 __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_leaf, uint32_t* stk_ref, float* stk_tn,
                                            uint32_t stk_stride, TravCount* cnt) {
-    constexpr bool PLANE = RT_PLANE_PRETEST != 0;
     uint32_t cur = T.cur;
     const bool at_leaf = (cur & RT_REF_LEAF) != 0u;
     bool need_pop = false;
@@ -370,16 +342,6 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
             pL = !cullL && sureL;
             pR = !cullR && sureR;
             need_exact = (!cullL && !sureL) || (!cullR && !sureR);
-            if (PLANE && !need_exact) {
-                // one shared code path for both children (6 = leaf bit | triangle kind): lanes with a pending child run the
-                // body together instead of serialising a "left" and a "right" copy with a handful of lanes each
-                bool wantL = pL && (q3.x >> RT_REF_KIND_SHIFT) == 6u, wantR = pR && (q3.y >> RT_REF_KIND_SHIFT) == 6u;
-                while (wantL || wantR) {
-                    const bool useL = wantL;
-                    const bool rej = tri_plane_reject(S, T, useL ? q3.x : q3.y, useL ? tnL : tnR, useL ? tfL : tfR, useL ? mgL : mgR);
-                    if (useL) { pL = !rej; wantL = false; } else { pR = !rej; wantR = false; }
-                }
-            }
         } else {
             need_exact = true;
         }
