@@ -43,14 +43,17 @@ extern "C" {
 #define RT_LEAF_BIT 0x80000000u /* BVH child reference: RT_LEAF_BIT | item index  (reference: usize::MAX - index) */
 #define RT_MISS 0xFFFFFFFFu     /* hit id of a ray that hit nothing                */
 
-/* Geometry kinds (reference enum `Geometry`, hittable.rs:104-110; AxisAlignedBox is out of scope) */
-enum { RT_GEO_SPHERE = 0, RT_GEO_RECT = 1, RT_GEO_TRIANGLE = 2 };
+/* Geometry kinds (reference enum `Geometry`, hittable.rs:104-110) */
+enum { RT_GEO_SPHERE = 0, RT_GEO_RECT = 1, RT_GEO_TRIANGLE = 2, RT_GEO_BOX = 3 };
+/* Run-time wrappers of a scene element (SceneElement::Transformation / ::Animation, hittable.rs:117-118), applied in the
+ * order NodeRef::finish nests them: Animation(Transformation(SurfaceGeometry))  (world_builder.rs:310-315) */
+enum { RT_WRAP_TRANSFORMATION = 1, RT_WRAP_ANIMATION = 2 };
 /* RectPlane (rect_geometry.rs:8-22) */
 enum { RT_RECT_XY = 0, RT_RECT_XZ = 1, RT_RECT_YZ = 2 };
 /* Material kinds (material.rs:43-49; Isotropic is volume-only, out of scope) */
 enum { RT_MAT_LAMBERT = 0, RT_MAT_METAL = 1, RT_MAT_DIELECTRIC = 2, RT_MAT_DIFFUSE_LIGHT = 3 };
-/* Texture kinds (texture.rs:4-20; Checker/Marble out of scope) */
-enum { RT_TEX_SOLID = 0, RT_TEX_IMAGE = 1 };
+/* Texture kinds (texture.rs:4-20; Marble/Perlin out of scope) */
+enum { RT_TEX_SOLID = 0, RT_TEX_IMAGE = 1, RT_TEX_CHECKER = 2 };
 /* RenderMode (rendering.rs:94-98) */
 enum { RT_MODE_DEFAULT = 0, RT_MODE_NORMALS = 1 };
 
@@ -58,11 +61,17 @@ enum { RT_MODE_DEFAULT = 0, RT_MODE_NORMALS = 1 };
  * "hit id" (position in `all_elements`, world_builder.rs:316).  `geom` holds, by kind:
  *   sphere   : center xyz, radius                               (sphere_geometry.rs:6-9)
  *   rect     : (float)plane, dist, r0.lo, r0.hi, r1.lo, r1.hi   (rect_geometry.rs:24-30)
- *   triangle : positions[3] xyz, normals[3] xyz, texture_coords[3] uv   (triangle_geometry.rs:6-10) */
+ *   triangle : positions[3] xyz, normals[3] xyz, texture_coords[3] uv   (triangle_geometry.rs:6-10)
+ *   box      : min xyz, max xyz                                 (Geometry::AxisAlignedBox(Aabb), aabb.rs:10-13)
+ * wrap_flags / transform / velocity describe the optional run-time wrappers: Transformation{offset, y_sine, y_cosine}
+ * (transformations.rs:4-8) and Animation(velocity) (hittable.rs:117). */
 typedef struct RtItem {
     uint32_t kind;
     uint32_t material;
     float geom[24];
+    uint32_t wrap_flags;  /* RT_WRAP_* bits */
+    float transform[5];   /* offset xyz, y_sine, y_cosine */
+    float velocity[3];
 } RtItem;
 
 /* BoundingVolumeNode (hittable.rs:345-351) in the reference's pre-order numbering. */
@@ -82,8 +91,10 @@ typedef struct RtMaterial {
 
 typedef struct RtTexture {
     uint32_t kind;
-    uint32_t image; /* RT_TEX_IMAGE: index into images */
-    float rgb[3];   /* RT_TEX_SOLID */
+    uint32_t image;      /* RT_TEX_IMAGE: index into images */
+    float rgb[3];        /* RT_TEX_SOLID */
+    float inv_frequency; /* RT_TEX_CHECKER (texture.rs:8-12) */
+    uint32_t even, odd;  /* RT_TEX_CHECKER: texture indices (may themselves be checkers, nesting <= 8) */
 } RtTexture;
 
 typedef struct RtImage {
@@ -99,7 +110,7 @@ typedef struct RtCamera { /* camera.rs:154-164, private fields included */
     float scaled_right[3];
     float scaled_up[3];
     float lens_radius;
-    float time_start, time_end; /* accepted; ray time is unused without Animation leaves */
+    float time_start, time_end; /* motion_blur(start, end): ray.time = U[start, end) per camera sample (camera.rs:185-190) */
     float shutter_pace[2];
 } RtCamera;
 
@@ -161,6 +172,8 @@ int rt_scene_device_bytes(const RtScene* scene, uint64_t* out_bytes);
  * front_face n, uv n*2 (any output pointer may be NULL).  Half-open range [t_min, t_max). */
 int rt_trace(RtScene* scene, const float* org_xyz, const float* dir_xyz, uint64_t n, float t_min, float t_max,
              uint32_t* hit_id, float* t, float* normal_xyz, uint8_t* front_face, float* uv);
+/* Ray::time of the rays handed to rt_trace / rt_trace_device (only Animation leaves look at it; default 0). */
+int rt_scene_set_ray_time(RtScene* scene, float time);
 /* Same on device buffers (as allocated by the caller, e.g. a torch tensor's data_ptr) on `stream`. */
 int rt_trace_device(RtScene* scene, const float* d_org_xyz, const float* d_dir_xyz, uint64_t n, float t_min, float t_max,
                     uint32_t* d_hit_id, float* d_t, float* d_normal_xyz, uint8_t* d_front_face, float* d_uv,

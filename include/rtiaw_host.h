@@ -31,11 +31,12 @@ const char* rtw_last_error(void);
 RtwWorld* rtw_world_create(const char* name, const char* suzanne_obj_path, const char* cube_obj_path, uint32_t earth_w,
                            uint32_t earth_h, const uint8_t* earth_rgb8);
 /* geom: 24 floats per element (layout of RtItem.geom); cam: position, look-at basis as the 23 floats of RtCamera in order;
- * bg: is_sky, r, g, b; light: has, plane, dist, r0lo, r0hi, r1lo, r1hi. */
+ * bg: is_sky, r, g, b; light: has, plane, dist, r0lo, r0hi, r1lo, r1hi;
+ * wrap9 (optional): per element flags (RT_WRAP_*), offset xyz, y_sine, y_cosine, velocity xyz. */
 RtwWorld* rtw_world_create_elements(uint32_t n, const uint32_t* kinds, const uint32_t* materials_of, const float* geom,
                                     uint32_t n_materials, const RtMaterial* materials, uint32_t n_textures,
                                     const RtTexture* textures, uint32_t n_images, const RtImage* images, const float* cam23,
-                                    const float* bg4, const float* light7);
+                                    const float* bg4, const float* light7, const float* wrap9 /* may be NULL */);
 void rtw_world_destroy(RtwWorld* w);
 
 /* info[10]: n_items, n_nodes, root, depth, default_w, default_h, n_materials, n_textures, n_images, has_light */

@@ -40,10 +40,11 @@ def lib():
         L.orc_world_create_flat.restype = C.c_void_p
         L.orc_world_create_flat.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                             C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                            C.c_void_p, C.c_void_p]
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_set_trace_time.argtypes = [C.c_float]
         L.orc_world_destroy.argtypes = [C.c_void_p]
         L.orc_world_info.argtypes = [C.c_void_p, C.c_void_p]
-        L.orc_world_export.argtypes = [C.c_void_p] + [C.c_void_p] * 11
+        L.orc_world_export.argtypes = [C.c_void_p] + [C.c_void_p] * 12
         L.orc_world_image.restype = C.c_void_p
         L.orc_world_image.argtypes = [C.c_void_p, C.c_uint32]
         L.orc_trace.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
@@ -96,7 +97,8 @@ class FlatScene:
     root: int
     depth: int
     mats: np.ndarray           # u32 [M,3]  kind, texture, param bits
-    texs: np.ndarray           # u32 [T,5]  kind, image, rgb bits
+    texs: np.ndarray           # u32 [T,8]  kind, image, rgb bits, inv_frequency bits, even, odd
+    wrap: np.ndarray = None    # f32 [N,9]  flags (1 Transformation, 2 Animation), offset xyz, y_sine, y_cosine, velocity xyz
     images: list = field(default_factory=list)   # list of u8 [h,w,3]
     cam: np.ndarray = None     # f32 [23]
     bg: np.ndarray = None      # f32 [4]
@@ -125,7 +127,7 @@ class OracleWorld:
         return w
 
     @classmethod
-    def from_flat(cls, kinds, item_mat, geom, mats, texs, images, cam, bg, light) -> "OracleWorld":
+    def from_flat(cls, kinds, item_mat, geom, mats, texs, images, cam, bg, light, wrap=None) -> "OracleWorld":
         kinds = np.ascontiguousarray(kinds, dtype=np.uint32)
         item_mat = np.ascontiguousarray(item_mat, dtype=np.uint32)
         geom = np.ascontiguousarray(geom, dtype=np.float32)
@@ -137,9 +139,11 @@ class OracleWorld:
         cam = np.ascontiguousarray(cam, dtype=np.float32)
         bg = np.ascontiguousarray(bg, dtype=np.float32)
         light = np.ascontiguousarray(light, dtype=np.float32)
+        wrap = None if wrap is None else np.ascontiguousarray(wrap, dtype=np.float32).reshape(len(kinds), 9)
+        texs = texs.reshape(-1, 8)
         return cls(lib().orc_world_create_flat(len(kinds), _p(kinds), _p(item_mat), _p(geom), len(mats), _p(mats),
                                                len(texs), _p(texs), len(images), _p(wh), ptrs, _p(cam), _p(bg),
-                                               _p(light)))
+                                               _p(light), _p(wrap)))
 
     def close(self):
         if self.h:
@@ -159,19 +163,20 @@ class OracleWorld:
             kinds=np.zeros(n, np.uint32), item_mat=np.zeros(n, np.uint32), geom=np.zeros((n, 24), np.float32),
             nodes_box=np.zeros((nn, 6), np.float32), nodes_lra=np.zeros((nn, 3), np.uint32),
             root=int(self.info[2]), depth=int(self.info[3]),
-            mats=np.zeros((nm, 3), np.uint32), texs=np.zeros((nt, 5), np.uint32),
+            mats=np.zeros((nm, 3), np.uint32), texs=np.zeros((nt, 8), np.uint32), wrap=np.zeros((n, 9), np.float32),
             cam=np.zeros(23, np.float32), bg=np.zeros(4, np.float32), light=np.zeros(7, np.float32),
             default_size=self.default_size)
         wh = np.zeros((max(ni, 1), 2), np.uint32)
         lib().orc_world_export(self.h, _p(fs.kinds), _p(fs.item_mat), _p(fs.geom), _p(fs.nodes_box), _p(fs.nodes_lra),
-                               _p(fs.mats), _p(fs.texs), _p(wh), _p(fs.cam), _p(fs.bg), _p(fs.light))
+                               _p(fs.mats), _p(fs.texs), _p(wh), _p(fs.cam), _p(fs.bg), _p(fs.light), _p(fs.wrap))
         for i in range(ni):
             w, h = int(wh[i, 0]), int(wh[i, 1])
             buf = (C.c_uint8 * (w * h * 3)).from_address(lib().orc_world_image(self.h, i))
             fs.images.append(np.frombuffer(buf, dtype=np.uint8).reshape(h, w, 3).copy())
         return fs
 
-    def trace(self, org, dir, t_min=0.001, t_max=np.inf, counters=False):
+    def trace(self, org, dir, t_min=0.001, t_max=np.inf, counters=False, time=0.0):
+        lib().orc_set_trace_time(time)
         org = np.ascontiguousarray(org, dtype=np.float32).reshape(-1, 3)
         dir = np.ascontiguousarray(dir, dtype=np.float32).reshape(-1, 3)
         n = org.shape[0]

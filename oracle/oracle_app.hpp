@@ -149,6 +149,7 @@ struct GeoEntry {
 struct Node {  // :194-199
     std::vector<GeoEntry> geo;
     Transformation transformation;
+    Dir3 moving_animation;
     std::vector<std::shared_ptr<Node>> children;
 };
 typedef std::shared_ptr<Node> NodeRef;
@@ -167,6 +168,11 @@ struct WorldBuilder {
         Image im; im.width = w; im.height = h; im.rgb.assign(rgb, rgb + (size_t)w * h * 3);
         images.push_back(std::move(im));
         Texture t; t.kind = Texture::Image_; t.image = &images.back();
+        textures.push_back(t);
+        return &textures.back();
+    }
+    const Texture* texture_checker(float inv_frequency, const Texture* even, const Texture* odd) {  // world_builder.rs:38-40
+        Texture t; t.kind = Texture::Checker; t.inv_frequency = inv_frequency; t.even = even; t.odd = odd;
         textures.push_back(t);
         return &textures.back();
     }
@@ -191,6 +197,12 @@ struct WorldBuilder {
         g.rect.r1[0] = center.e[a1] - s1 * 0.5f; g.rect.r1[1] = center.e[a1] + s1 * 0.5f;
         return g;
     }
+    static Geometry geo_box(float width, float height, float depth) {  // :88-93
+        Geometry g; g.kind = Geometry::AxisAlignedBox;
+        g.box.min = Point3(0, 0, 0); g.box.max = Point3(width, height, depth);
+        return g;
+    }
+    static NodeRef new_obj_box(float w, float h, float d, const Material* m) { return new_obj(geo_box(w, h, d), m); }
     static Geometry geo_sphere(float radius) {  // :94-99
         Geometry g; g.kind = Geometry::Sphere;
         g.sphere.center = Point3(0, 0, 0); g.sphere.radius = radius;
@@ -218,19 +230,26 @@ struct WorldBuilder {
 static inline NodeRef translate(NodeRef n, Dir3 o) { n->transformation = n->transformation.translate(o); return n; }
 static inline NodeRef rotate_up(NodeRef n, float deg) { n->transformation = n->transformation.rotate_around_up_deg(deg); return n; }
 static inline NodeRef set_poi(NodeRef n) { for (auto& g : n->geo) g.is_poi = true; return n; }
+static inline NodeRef animate_moving(NodeRef n, Dir3 v) { n->moving_animation = n->moving_animation + v; return n; }
 
-// NodeRef::finish / finish_internal  (:272-329).  Only fully-bakeable leaves are in scope (sphere,
-// triangle, untransformed rect): a rect under a non-zero transform would need a run-time
-// Transformation wrapper and is rejected.
+// NodeRef::finish / finish_internal  (:272-329): bake what can be baked, wrap the remainder as a run-time Transformation,
+// wrap moving nodes as Animation, first POI rect WITHOUT a remainder becomes the light-sampling provider.
 static inline void finish_internal(const Node& node, const Transformation& parent, std::vector<SceneItem>& result,
                                    bool* has_light, RectGeometry* light) {
     Transformation full = parent.then(node.transformation);
     for (const GeoEntry& ge : node.geo) {
         bool has_rest = false;
-        Geometry real = ge.geo.partial_apply_transformation(full, &has_rest);
-        if (has_rest) throw std::runtime_error("oracle: transformed rect leaves are out of scope (row f2)");
-        result.push_back(SceneItem{real, ge.material});
-        if (ge.is_poi && !*has_light && real.kind == Geometry::Rect) { *has_light = true; *light = real.rect; }
+        Transformation rest;
+        Geometry real = ge.geo.partial_apply_transformation(full, &has_rest, &rest);
+        SceneItem it;
+        it.geo = real;
+        it.material = ge.material;
+        it.has_transform = has_rest;
+        it.transform = rest;
+        it.has_animation = node.moving_animation != Dir3(0, 0, 0);
+        it.velocity = node.moving_animation;
+        result.push_back(it);
+        if (ge.is_poi && !has_rest && !*has_light && real.kind == Geometry::Rect) { *has_light = true; *light = real.rect; }
     }
     for (const NodeRef& c : node.children) finish_internal(*c, full, result, has_light, light);
 }
@@ -341,6 +360,29 @@ static inline std::unique_ptr<BuiltWorld> build_world(const std::string& name, c
         add_random_sphere_field(wb, rng, scene, 11);
         finish(*bw, scene, bg_sky(), cb.build());
         bw->default_width = 1200; bw->default_height = (name == "config:c1") ? 800 : 675;
+    } else if (name == "demo:cornell_box") {  // demo_worlds.rs:266-296
+        float hsize = 278.0f;
+        Camera cam = cam_lookat(40.0f, 1.0f, Point3(hsize, hsize, -800.0f), Point3(hsize, hsize, 0.0f));
+        const Material* white = wb.material_lambert_solid(Color(0.73f, 0.73f, 0.73f));
+        scene->children.push_back(cornell_box_node(wb, 130.0f));
+        scene->children.push_back(translate(rotate_up(WorldBuilder::new_obj_box(165.0f, 330.0f, 165.0f, white), 15.0f), Dir3(265.0f, 0.0f, 295.0f)));
+        scene->children.push_back(translate(rotate_up(WorldBuilder::new_obj_box(165.0f, 165.0f, 165.0f, white), -18.0f), Dir3(130.0f, 0.0f, 65.0f)));
+        finish(*bw, scene, bg_solid(Color(0, 0, 0)), cam);
+        bw->default_width = 600; bw->default_height = 600;
+    } else if (name == "demo:moving_spheres") {  // demo_worlds.rs:351-393
+        CameraBuilder cb;
+        cb.vertical_fov(60.0f, 16.0f / 19.0f).set_position(Point3(0.0f, 2.0f, 10.0f)).look_at(DIR_UP, Point3(0.0f, 2.0f, 0.0f)).motion_blur(0.0f, 0.5f);
+        const Texture* tex_black = wb.texture_solid(Color(0.0f, 0.0f, 0.0f));
+        const Texture* tex_white = wb.texture_solid(Color(1.0f, 1.0f, 1.0f));
+        const Texture* tex_ground = wb.texture_checker(10.0f, tex_black, tex_white);
+        const Material* mat_ground = wb.material_lambert(tex_ground);
+        const Material* mat_red = wb.material_lambert_solid(Color(0.6f, 0.2f, 0.2f));
+        const Material* mat_blue = wb.material_lambert_solid(Color(0.2f, 0.2f, 0.6f));
+        scene->children.push_back(translate(WorldBuilder::new_obj_sphere(100.0f, mat_ground), Dir3(0.0f, -100.0f, 0.0f)));
+        scene->children.push_back(animate_moving(translate(WorldBuilder::new_obj_sphere(0.5f, mat_red), Dir3(-2.0f, 1.5f, 0.0f)), Dir3(2.0f, 0.0f, 0.0f)));
+        scene->children.push_back(animate_moving(translate(WorldBuilder::new_obj_sphere(0.5f, mat_blue), Dir3(0.0f, 0.5f, 0.0f)), Dir3(0.0f, 1.0f, 0.0f)));
+        finish(*bw, scene, bg_sky(), cb.build());
+        bw->default_width = 380; bw->default_height = 320;
     } else if (name == "demo:simple_plane") {  // demo_worlds.rs:298-324
         Camera cam = cam_lookat(60.0f, 9.0f / 16.0f, Point3(0.0f, 6.0f, 10.0f), Point3(0, 0, 0));
         const Material* mat_emit = wb.material_diffuse_light_solid(100.0f * Color(1.0f, 1.0f, 1.0f));

@@ -44,13 +44,14 @@ void* orc_world_create(const char* name, const char* suzanne_obj, const char* cu
 
 // Build a world from flat arrays (random / adversarial test scenes authored in Python).
 // geom: 24 floats per item — sphere: cx cy cz r | rect: plane dist r0lo r0hi r1lo r1hi | tri: 9 pos, 9 nrm, 6 uv.
-// mats: (kind, texture, param-as-float-bits) u32 triples.  texs: (kind, image, r, g, b as float bits) u32 x5.
+// mats: (kind, texture, param-as-float-bits) u32 triples.  texs: (kind, image, r, g, b, inv_frequency as float bits, even, odd) u32 x8.
+// wrap (optional, may be NULL): 9 floats per item — flags (bit0 Transformation, bit1 Animation), offset xyz, y_sine, y_cosine, velocity xyz.
 // cam: position3 ulc3 unit_right3 unit_up3 scaled_right3 scaled_up3 lens_radius t0 t1 pace2 (23 floats).
 // bg: sky-flag r g b.  light: has plane dist r0lo r0hi r1lo r1hi (7 floats, has==0 -> none).
 void* orc_world_create_flat(uint32_t n_items, const uint32_t* kinds, const uint32_t* item_mat, const float* geom,
                             uint32_t n_mats, const uint32_t* mats, uint32_t n_texs, const uint32_t* texs,
                             uint32_t n_images, const uint32_t* image_wh, const uint8_t* const* image_rgb,
-                            const float* cam, const float* bg, const float* light) {
+                            const float* cam, const float* bg, const float* light, const float* wrap) {
     try {
         if (n_items == 0) throw std::runtime_error("empty scene (reference recurses forever)");
         Handle* h = new Handle();
@@ -65,12 +66,18 @@ void* orc_world_create_flat(uint32_t n_items, const uint32_t* kinds, const uint3
         std::vector<const Texture*> tptr;
         for (uint32_t i = 0; i < n_texs; ++i) {
             Texture t;
-            t.kind = texs[5 * i] == 0 ? Texture::Solid : Texture::Image_;
-            t.color = Color(bits_to_f32(texs[5 * i + 2]), bits_to_f32(texs[5 * i + 3]), bits_to_f32(texs[5 * i + 4]));
-            if (t.kind == Texture::Image_) t.image = &wb.images[texs[5 * i + 1]];
+            t.kind = (Texture::Kind)texs[8 * i];
+            t.color = Color(bits_to_f32(texs[8 * i + 2]), bits_to_f32(texs[8 * i + 3]), bits_to_f32(texs[8 * i + 4]));
+            if (t.kind == Texture::Image_) t.image = &wb.images[texs[8 * i + 1]];
+            t.inv_frequency = bits_to_f32(texs[8 * i + 5]);
             wb.textures.push_back(t);
             tptr.push_back(&wb.textures.back());
         }
+        for (uint32_t i = 0; i < n_texs; ++i)
+            if (texs[8 * i] == Texture::Checker) {
+                wb.textures[i].even = tptr.at(texs[8 * i + 6]);
+                wb.textures[i].odd = tptr.at(texs[8 * i + 7]);
+            }
         std::vector<const Material*> mptr;
         for (uint32_t i = 0; i < n_mats; ++i) {
             uint32_t k = mats[3 * i];
@@ -88,6 +95,9 @@ void* orc_world_create_flat(uint32_t n_items, const uint32_t* kinds, const uint3
                 geo.kind = Geometry::Rect;
                 geo.rect.rect_plane = (int)g[0]; geo.rect.dist = g[1];
                 geo.rect.r0[0] = g[2]; geo.rect.r0[1] = g[3]; geo.rect.r1[0] = g[4]; geo.rect.r1[1] = g[5];
+            } else if (kinds[i] == 3) {
+                geo.kind = Geometry::AxisAlignedBox;
+                geo.box.min = Point3(g[0], g[1], g[2]); geo.box.max = Point3(g[3], g[4], g[5]);
             } else {
                 geo.kind = Geometry::Triangle;
                 for (int v = 0; v < 3; ++v) {
@@ -96,7 +106,18 @@ void* orc_world_create_flat(uint32_t n_items, const uint32_t* kinds, const uint3
                     geo.tri.texture_coords[v] = Vec2f(g[18 + 2 * v], g[19 + 2 * v]);
                 }
             }
-            w.scene.items.push_back(SceneItem{geo, mptr.at(item_mat[i])});
+            SceneItem it;
+            it.geo = geo;
+            it.material = mptr.at(item_mat[i]);
+            if (wrap) {
+                const float* wv = wrap + 9 * (size_t)i;
+                uint32_t fl = (uint32_t)wv[0];
+                it.has_transform = (fl & 1u) != 0;
+                it.transform.offset = Dir3(wv[1], wv[2], wv[3]); it.transform.y_sine = wv[4]; it.transform.y_cosine = wv[5];
+                it.has_animation = (fl & 2u) != 0;
+                it.velocity = Dir3(wv[6], wv[7], wv[8]);
+            }
+            w.scene.items.push_back(it);
         }
         w.scene.build();
         Camera& c = w.camera;
@@ -142,7 +163,7 @@ void orc_world_info(void* hp, uint64_t* info) {
 
 // Flat export; array layouts as in orc_world_create_flat.  nodes_box: 6 floats (min, max); nodes_lra: left, right, axis.
 void orc_world_export(void* hp, uint32_t* kinds, uint32_t* item_mat, float* geom, float* nodes_box, uint32_t* nodes_lra,
-                      uint32_t* mats, uint32_t* texs, uint32_t* image_wh, float* cam, float* bg, float* light) {
+                      uint32_t* mats, uint32_t* texs, uint32_t* image_wh, float* cam, float* bg, float* light, float* wrap) {
     Handle* h = (Handle*)hp;
     const World& w = h->bw->world;
     const WorldBuilder& wb = *h->bw->wb;
@@ -167,12 +188,20 @@ void orc_world_export(void* hp, uint32_t* kinds, uint32_t* item_mat, float* geom
         kinds[i] = (uint32_t)it.geo.kind;
         if (it.material != last_m) { last_m = it.material; last_i = mat_index(it.material); }
         item_mat[i] = last_i;
+        if (wrap) {
+            float* wv = wrap + 9 * i;
+            wv[0] = (float)((it.has_transform ? 1 : 0) | (it.has_animation ? 2 : 0));
+            for (int k = 0; k < 3; ++k) { wv[1 + k] = it.transform.offset.e[k]; wv[6 + k] = it.velocity.e[k]; }
+            wv[4] = it.transform.y_sine; wv[5] = it.transform.y_cosine;
+        }
         if (it.geo.kind == Geometry::Sphere) {
             g[0] = it.geo.sphere.center.e[0]; g[1] = it.geo.sphere.center.e[1]; g[2] = it.geo.sphere.center.e[2];
             g[3] = it.geo.sphere.radius;
         } else if (it.geo.kind == Geometry::Rect) {
             g[0] = (float)it.geo.rect.rect_plane; g[1] = it.geo.rect.dist;
             g[2] = it.geo.rect.r0[0]; g[3] = it.geo.rect.r0[1]; g[4] = it.geo.rect.r1[0]; g[5] = it.geo.rect.r1[1];
+        } else if (it.geo.kind == Geometry::AxisAlignedBox) {
+            for (int k = 0; k < 3; ++k) { g[k] = it.geo.box.min.e[k]; g[3 + k] = it.geo.box.max.e[k]; }
         } else {
             for (int v = 0; v < 3; ++v) {
                 for (int k = 0; k < 3; ++k) { g[3 * v + k] = it.geo.tri.positions[v].e[k]; g[9 + 3 * v + k] = it.geo.tri.normals[v].e[k]; }
@@ -193,9 +222,12 @@ void orc_world_export(void* hp, uint32_t* kinds, uint32_t* item_mat, float* geom
         mats[3 * i + 2] = f32_to_bits(wb.materials[i].param);
     }
     for (size_t i = 0; i < wb.textures.size(); ++i) {
-        texs[5 * i] = (uint32_t)wb.textures[i].kind;
-        texs[5 * i + 1] = wb.textures[i].image ? img_index(wb.textures[i].image) : 0xFFFFFFFFu;
-        for (int k = 0; k < 3; ++k) texs[5 * i + 2 + k] = f32_to_bits(wb.textures[i].color.e[k]);
+        texs[8 * i] = (uint32_t)wb.textures[i].kind;
+        texs[8 * i + 1] = wb.textures[i].image ? img_index(wb.textures[i].image) : 0xFFFFFFFFu;
+        for (int k = 0; k < 3; ++k) texs[8 * i + 2 + k] = f32_to_bits(wb.textures[i].color.e[k]);
+        texs[8 * i + 5] = f32_to_bits(wb.textures[i].inv_frequency);
+        texs[8 * i + 6] = wb.textures[i].even ? tex_index(wb.textures[i].even) : 0xFFFFFFFFu;
+        texs[8 * i + 7] = wb.textures[i].odd ? tex_index(wb.textures[i].odd) : 0xFFFFFFFFu;
     }
     for (size_t i = 0; i < wb.images.size(); ++i) { image_wh[2 * i] = wb.images[i].width; image_wh[2 * i + 1] = wb.images[i].height; }
     const Camera& c = w.camera;
@@ -211,12 +243,14 @@ void orc_world_export(void* hp, uint32_t* kinds, uint32_t* item_mat, float* geom
 const uint8_t* orc_world_image(void* hp, uint32_t i) { return ((Handle*)hp)->bw->wb->images[i].rgb.data(); }
 
 // Scene::hit on caller rays.  hit_id = flattened item index, 0xFFFFFFFF = miss.  counters (optional): node_tests, prim_tests.
+static float g_trace_time = 0.0f;
+void orc_set_trace_time(float t) { g_trace_time = t; }  // Ray::time of the rays handed to orc_trace (Animation leaves)
 void orc_trace(void* hp, uint64_t n, const float* org, const float* dir, float t_min, float t_max, uint32_t* hit_id,
                float* t, float* normal, uint8_t* front_face, float* uv, uint64_t* counters) {
     const World& w = ((Handle*)hp)->bw->world;
     Counters cnt;
     for (uint64_t i = 0; i < n; ++i) {
-        Ray r{Point3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), Dir3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), 0.0f};
+        Ray r{Point3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), Dir3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), g_trace_time};
         Range tr{t_min, t_max};
         HitInteraction hi;
         if (w.scene.hit(r, tr, &hi, &cnt)) {

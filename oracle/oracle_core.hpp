@@ -25,6 +25,11 @@ namespace orc {
 static const float PI_F = 3.14159265358979323846f;
 static const float TAU_F = 6.28318530717958647692f;
 static const float INF_F = std::numeric_limits<float>::infinity();
+// libm calls the reference makes at RUN time (f32::tan / sin_cos -> the platform libm).  `volatile` keeps the compiler from
+// folding them at compile time with a differently-rounded (MPFR) result.
+static inline float rt_tanf(float x) { volatile float v = x; return std::tan(v); }
+static inline float rt_sinf(float x) { volatile float v = x; return std::sin(v); }
+static inline float rt_cosf(float x) { volatile float v = x; return std::cos(v); }
 
 // ---------------------------------------------------------------- src/lib/vec3.rs:1-306
 struct V3 {
@@ -169,6 +174,53 @@ static inline GeoHit geo_hit_from_ray(const Ray& ray, Point3 position, Dir3 surf
     g.t = t;
     g.uv = uv;
     return g;
+}
+
+// ---------------------------------------------------------------- src/lib/aabb.rs:80-192 (AABB as a primitive; row f2)
+static inline float signum_f32(float v) {  // f32::signum: 1.0 for +0.0 and positives, -1.0 for -0.0 and negatives, NaN for NaN
+    if (v != v) return v;
+    return std::signbit(v) ? -1.0f : 1.0f;
+}
+static inline bool aabb_intersections_line(const Aabb& b, Point3 origin, Dir3 direction, float* near_t, int* near_plane,
+                                           float* far_t, int* far_plane) {  // :103-167
+    Dir3 mn = b.min - origin, mx = b.max - origin;
+    float near = -INF_F, far = INF_F;
+    int np = 0, fp = 0;
+    for (int i = 0; i < 3; ++i) {
+        float t1 = mn.e[i] / direction.e[i];
+        float t2 = mx.e[i] / direction.e[i];
+        float t_min = std::fmin(t1, t2);
+        float t_max = std::fmax(t1, t2);
+        if (t_min > near) { near = t_min; np = i; }
+        if (t_max < far) { far = t_max; fp = i; }
+        if (near > far || far < 0.0f) return false;
+    }
+    *near_t = near; *near_plane = np; *far_t = far; *far_plane = fp;
+    return true;
+}
+static inline bool aabb_prim_hit(const Aabb& b, const Ray& ray, const Range& t_range, GeoHit* out) {  // :80-102
+    float near_t, far_t;
+    int near_plane, far_plane;
+    if (!aabb_intersections_line(b, ray.origin, ray.direction, &near_t, &near_plane, &far_t, &far_plane)) return false;
+    float t;
+    int plane;
+    if (t_range.contains(near_t)) { t = near_t; plane = near_plane; }
+    else if (t_range.contains(far_t)) { t = far_t; plane = far_plane; }
+    else return false;
+    Point3 position = ray.origin + t * ray.direction;
+    float center = (b.max.e[plane] + b.min.e[plane]) * 0.5f;
+    Dir3 surface_normal(0, 0, 0);
+    surface_normal.e[plane] = signum_f32(position.e[plane] - center);
+    *out = geo_hit_from_ray(ray, position, surface_normal, t, Vec2f(0, 0));
+    return true;
+}
+// Aabb::corners (:178-192) + Transformation::apply_aabb (hittable.rs:285-291).  Q2: the loop mutates COPIES of the corners
+// (`for mut c in corners`), so the result is the bounding box of the UNTRANSFORMED corners — which can still differ from
+// the input by one rounding (min + (max - min) != max).
+static inline Aabb aabb_apply_transform_q2(const Aabb& a) {
+    Dir3 right(a.max.e[0] - a.min.e[0], 0.0f, 0.0f), up(0.0f, a.max.e[1] - a.min.e[1], 0.0f), fwd(0.0f, 0.0f, a.max.e[2] - a.min.e[2]);
+    Point3 c[8] = {a.min, a.min + right, a.min + up, a.min + fwd, a.max, a.max - right, a.max - up, a.max - fwd};
+    return aabb_surrounding_points(c, 8);
 }
 
 // ---------------------------------------------------------------- src/lib/hittable/sphere_geometry.rs
@@ -323,7 +375,7 @@ struct Transformation {
     Transformation rotate_around_up_deg(float angle) const {  // :26-36
         Transformation r = *this;
         float rad = angle * (PI_F / 180.0f);  // f32::to_radians
-        float s = std::sin(rad), c = std::cos(rad);
+        float s = rt_sinf(rad), c = rt_cosf(rad);
         rotate_around_up(c, s, r.offset);
         V3 v(y_sine, 0.0f, y_cosine);
         rotate_around_up(c, s, v);
@@ -365,9 +417,11 @@ struct Image {
 };
 struct HitInteraction;
 struct Texture {
-    enum Kind { Solid = 0, Image_ = 1 } kind = Solid;
+    enum Kind { Solid = 0, Image_ = 1, Checker = 2 } kind = Solid;
     Color color;
     const Image* image = nullptr;
+    float inv_frequency = 0.0f;              // Checker (texture.rs:8-12)
+    const Texture *even = nullptr, *odd = nullptr;
     Color sample(const HitInteraction& hi) const;
 };
 struct Material {
@@ -392,6 +446,11 @@ static inline uint32_t sat_u32(float v) {  // Rust `as u32`
 }
 inline Color Texture::sample(const HitInteraction& hi) const {  // texture.rs:23-43
     if (kind == Solid) return color;
+    if (kind == Checker) {  // :26-35
+        Dir3 sp = (hi.position - Point3(0, 0, 0)) * inv_frequency;
+        float sines = std::sin(sp.e[0]) * std::sin(sp.e[1]) * std::sin(sp.e[2]);
+        return (sines < 0.0f ? even : odd)->sample(hi);
+    }
     uint32_t pu = std::min(sat_u32(hi.uv.x * (float)image->width), image->width - 1);
     uint32_t pv = std::min(sat_u32(hi.uv.y * (float)image->height), image->height - 1);
     return new_rgb8(&image->rgb[3 * ((size_t)pv * image->width + pu)]);
@@ -473,14 +532,16 @@ static inline Color material_emit(const Material& m, const HitInteraction& hi) {
 
 // ---------------------------------------------------------------- src/lib/hittable.rs:104-482
 struct Geometry {
-    enum Kind { Sphere = 0, Rect = 1, Triangle = 2 } kind;
+    enum Kind { Sphere = 0, Rect = 1, Triangle = 2, AxisAlignedBox = 3 } kind;
     SphereGeometry sphere;
     RectGeometry rect;
     TriangleGeometry tri;
+    Aabb box;
     bool hit(const Ray& ray, const Range& tr, GeoHit* out) const {  // :141-148
         switch (kind) {
             case Sphere: return sphere_hit(sphere, ray, tr, out);
             case Rect: return rect_hit(rect, ray, tr, out);
+            case AxisAlignedBox: return aabb_prim_hit(box, ray, tr, out);
             default: return triangle_hit(tri, ray, tr, out);
         }
     }
@@ -488,11 +549,12 @@ struct Geometry {
         switch (kind) {
             case Sphere: return sphere_bounding_box(sphere);
             case Rect: return rect_bounding_box(rect, 0.01f);
+            case AxisAlignedBox: return box;
             default: return triangle_bounding_box(tri);
         }
     }
-    // :165-208; returns true when a remainder transformation is left over (Rect only)
-    Geometry partial_apply_transformation(const Transformation& t, bool* has_rest) const {
+    // :165-208; *rest receives the transformation that must stay as a run-time SceneElement::Transformation wrapper
+    Geometry partial_apply_transformation(const Transformation& t, bool* has_rest, Transformation* rest) const {
         Geometry g = *this;
         *has_rest = false;
         if (kind == Sphere) {
@@ -502,8 +564,16 @@ struct Geometry {
                 g.tri.positions[i] = t.apply_point(tri.positions[i]);
                 g.tri.normals[i] = t.apply_normal(tri.normals[i]);
             }
+        } else if (kind == AxisAlignedBox) {  // Q3: the translation is baked, the rotation-only remainder is applied afterwards
+            g.box.min = box.min + t.offset;
+            g.box.max = box.max + t.offset;
+            Transformation rem = t;
+            rem.offset = Dir3(0, 0, 0);
+            *has_rest = !rem.is_zero();
+            *rest = rem;
         } else {
             *has_rest = !t.is_zero();
+            *rest = t;
         }
         return g;
     }
@@ -519,9 +589,42 @@ struct BvhNode {  // :345-351
 };
 static const size_t USIZE_MAX = ~(size_t)0;
 
-struct SceneItem {  // SceneElement::SurfaceGeometry(geo, material)  (:115)
+// SceneElement::SurfaceGeometry(geo, material) (:115), optionally wrapped as Transformation(..) (:118) and then Animation(..)
+// (:117) exactly in the order NodeRef::finish applies them (world_builder.rs:310-315).
+struct SceneItem {
     Geometry geo;
     const Material* material;
+    bool has_transform = false;
+    Transformation transform;
+    bool has_animation = false;
+    Dir3 velocity;
+
+    Aabb bounding_box() const {  // SceneElement::bounding_box :249-267 (Q2: wrappers do not move / extend the box)
+        Aabb b = geo.bounding_box();
+        if (has_transform) b = aabb_apply_transform_q2(b);
+        if (has_animation) {
+            Aabb s = aabb_apply_transform_q2(b), e = aabb_apply_transform_q2(b);
+            b = aabb_surrounding(s, e);
+        }
+        return b;
+    }
+    bool hit(const Ray& ray_in, const Range& tr, GeoHit* out) const {  // SceneElement::hit :230-244
+        Ray ray = ray_in;
+        Transformation anim;
+        if (has_animation) {
+            anim = Transformation().translate(velocity * ray.time);
+            ray.origin = anim.reverse_point(ray.origin);
+            ray.direction = anim.reverse_normal(ray.direction);
+        }
+        if (has_transform) {
+            ray.origin = transform.reverse_point(ray.origin);
+            ray.direction = transform.reverse_normal(ray.direction);
+        }
+        if (!geo.hit(ray, tr, out)) return false;
+        if (has_transform) { out->position = transform.apply_point(out->position); out->normal = transform.apply_normal(out->normal); }
+        if (has_animation) { out->position = anim.apply_point(out->position); out->normal = anim.apply_normal(out->normal); }
+        return true;
+    }
 };
 
 struct Bvh {  // :352-482
@@ -532,7 +635,7 @@ struct Bvh {  // :352-482
 
     void build() {  // :360-380
         std::vector<std::pair<size_t, Aabb>> h(items.size());
-        for (size_t i = 0; i < items.size(); ++i) h[i] = {USIZE_MAX - i, items[i].geo.bounding_box()};
+        for (size_t i = 0; i < items.size(); ++i) h[i] = {USIZE_MAX - i, items[i].bounding_box()};
         nodes.clear();
         size_t d = 0;
         Aabb box;
@@ -584,7 +687,7 @@ struct Bvh {  // :352-482
             size_t item = USIZE_MAX - node;
             if (cnt) cnt->prim_tests++;
             GeoHit g;
-            if (items[item].geo.hit(ray, t_range, &g)) {  // leaf: NO AABB test (Q13)
+            if (items[item].hit(ray, t_range, &g)) {  // leaf: NO AABB test (Q13)
                 out->position = g.position; out->normal = g.normal; out->uv = g.uv; out->t = g.t;
                 out->front_face = g.front_face; out->material = items[item].material; out->item = (uint32_t)item;
                 return true;
@@ -648,7 +751,7 @@ struct CameraBuilder {  // :9-152
     float aperture = 0.0f, focus_distance = 1.0f;
     float t0 = 0, t1 = 0;
     CameraBuilder& vertical_fov(float fov_deg, float aspect_ratio) {  // :72-79 (Q10)
-        float h = std::tan((fov_deg * (PI_F / 180.0f)) * 0.5f);
+        float h = rt_tanf((fov_deg * (PI_F / 180.0f)) * 0.5f);
         viewport_width = 2.0f * h;
         viewport_height = 2.0f * h * aspect_ratio;
         return *this;

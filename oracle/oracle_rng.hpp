@@ -98,6 +98,7 @@ struct TRng {
     bool replay = false;
     uint32_t key0 = 0, key1 = 0, pixel = 0, sample = 0;
     uint32_t buf[4] = {0, 0, 0, 0};
+    uint32_t block_id = 0;
     int idx = 4;
 
     static TRng from_seed_bytes(const uint8_t seed[16]) {
@@ -131,6 +132,7 @@ struct TRng {
     void set_path(uint32_t pix, uint32_t smp) { pixel = pix; sample = smp; }
     void begin_block(uint32_t block) {
         if (!replay) return;
+        block_id = block;
         philox4x32_10(key0, key1, pixel, sample, block, 0u, buf);
         idx = 0;
     }
@@ -147,6 +149,7 @@ struct TRng {
     // uniform in [0,1) with 24 bits; in REPLAY mode this is the only primitive.
     float u01() {
         if (replay) {
+            if (idx > 0 && (idx & 3) == 0) philox4x32_10(key0, key1, pixel, sample, block_id, (uint32_t)(idx >> 2), buf);  // draws 4.. of a block
             uint32_t v = buf[idx & 3];
             ++idx;
             return (float)(v >> 8) * 5.9604644775390625e-8f;

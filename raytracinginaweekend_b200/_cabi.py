@@ -17,7 +17,8 @@ RT_MISS = 0xFFFFFFFF
 
 
 class RtItem(C.Structure):
-    _fields_ = [("kind", C.c_uint32), ("material", C.c_uint32), ("geom", C.c_float * 24)]
+    _fields_ = [("kind", C.c_uint32), ("material", C.c_uint32), ("geom", C.c_float * 24), ("wrap_flags", C.c_uint32),
+                ("transform", C.c_float * 5), ("velocity", C.c_float * 3)]
 
 
 class RtBvhNode(C.Structure):
@@ -30,7 +31,8 @@ class RtMaterial(C.Structure):
 
 
 class RtTexture(C.Structure):
-    _fields_ = [("kind", C.c_uint32), ("image", C.c_uint32), ("rgb", C.c_float * 3)]
+    _fields_ = [("kind", C.c_uint32), ("image", C.c_uint32), ("rgb", C.c_float * 3), ("inv_frequency", C.c_float),
+                ("even", C.c_uint32), ("odd", C.c_uint32)]
 
 
 class RtImage(C.Structure):
@@ -68,15 +70,17 @@ class RtStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-ITEM_DTYPE = np.dtype([("kind", "<u4"), ("material", "<u4"), ("geom", "<f4", (24,))])
+ITEM_DTYPE = np.dtype([("kind", "<u4"), ("material", "<u4"), ("geom", "<f4", (24,)), ("wrap_flags", "<u4"),
+                       ("transform", "<f4", (5,)), ("velocity", "<f4", (3,))])
 NODE_DTYPE = np.dtype([("aabb_min", "<f4", (3,)), ("aabb_max", "<f4", (3,)), ("left", "<u4"), ("right", "<u4"),
                        ("axis_id", "<u4")])
 MATERIAL_DTYPE = np.dtype([("kind", "<u4"), ("texture", "<u4"), ("param", "<f4")])
-TEXTURE_DTYPE = np.dtype([("kind", "<u4"), ("image", "<u4"), ("rgb", "<f4", (3,))])
+TEXTURE_DTYPE = np.dtype([("kind", "<u4"), ("image", "<u4"), ("rgb", "<f4", (3,)), ("inv_frequency", "<f4"), ("even", "<u4"),
+                          ("odd", "<u4")])
 assert ITEM_DTYPE.itemsize == C.sizeof(RtItem) and NODE_DTYPE.itemsize == C.sizeof(RtBvhNode)
 assert MATERIAL_DTYPE.itemsize == C.sizeof(RtMaterial) and TEXTURE_DTYPE.itemsize == C.sizeof(RtTexture)
 
-EXPORTED = ["rt_last_error", "rt_device_count", "rt_scene_create", "rt_scene_destroy", "rt_scene_device_bytes",
+EXPORTED = ["rt_last_error", "rt_device_count", "rt_scene_create", "rt_scene_destroy", "rt_scene_device_bytes", "rt_scene_set_ray_time",
             "rt_trace", "rt_trace_device", "rt_render", "rt_render_device", "rt_render_planes_device",
             "rt_film_scale_device", "rt_to_rgb8_gamma2_device", "rt_set_option"]
 
@@ -101,6 +105,7 @@ def lib():
         L.rt_scene_destroy.argtypes = [C.c_void_p]
         L.rt_scene_destroy.restype = None
         L.rt_scene_device_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.rt_scene_set_ray_time.argtypes = [C.c_void_p, C.c_float]
         L.rt_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_float] + [C.c_void_p] * 5
         L.rt_trace_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_float] + [C.c_void_p] * 6
         L.rt_render.argtypes = [C.c_void_p, C.POINTER(RtRenderParams), C.c_void_p, C.POINTER(RtStats)]
@@ -133,13 +138,35 @@ def device_count() -> int:
     return n.value
 
 
-def make_desc(kinds, item_mat, geom, nodes_box, nodes_lra, root, mats, texs, images, cam, bg, light):
-    """Assemble an RtSceneDesc from flat numpy arrays.  Returns (desc, keepalive)."""
+def textures_from_u32(texs):
+    """[T, 8] u32 rows (kind, image, r, g, b bits, inv_frequency bits, even, odd) -> RtTexture records."""
+    texs = np.asarray(texs, np.uint32).reshape(-1, 8)
+    t = np.zeros(len(texs), TEXTURE_DTYPE)
+    t["kind"], t["image"] = texs[:, 0], texs[:, 1]
+    t["rgb"] = texs[:, 2:5].copy().view(np.float32)
+    t["inv_frequency"] = texs[:, 5].copy().view(np.float32)
+    t["even"], t["odd"] = texs[:, 6], texs[:, 7]
+    return t
+
+
+def items_from_flat(kinds, item_mat, geom, wrap=None):
     n = len(kinds)
     items = np.zeros(n, ITEM_DTYPE)
     items["kind"] = kinds
     items["material"] = item_mat
     items["geom"] = np.asarray(geom, np.float32).reshape(n, 24)
+    if wrap is not None:
+        w = np.asarray(wrap, np.float32).reshape(n, 9)
+        items["wrap_flags"] = w[:, 0].astype(np.uint32)
+        items["transform"] = w[:, 1:6]
+        items["velocity"] = w[:, 6:9]
+    return items
+
+
+def make_desc(kinds, item_mat, geom, nodes_box, nodes_lra, root, mats, texs, images, cam, bg, light, wrap=None):
+    """Assemble an RtSceneDesc from flat numpy arrays.  Returns (desc, keepalive)."""
+    n = len(kinds)
+    items = items_from_flat(kinds, item_mat, geom, wrap)
     nn = len(nodes_lra)
     nodes = np.zeros(nn, NODE_DTYPE)
     if nn:
@@ -155,11 +182,7 @@ def make_desc(kinds, item_mat, geom, nodes_box, nodes_lra, root, mats, texs, ima
     m["kind"] = mats[:, 0]
     m["texture"] = mats[:, 1]
     m["param"] = mats[:, 2].copy().view(np.float32)
-    texs = np.asarray(texs, np.uint32).reshape(-1, 5)
-    t = np.zeros(len(texs), TEXTURE_DTYPE)
-    t["kind"] = texs[:, 0]
-    t["image"] = texs[:, 1]
-    t["rgb"] = texs[:, 2:5].copy().view(np.float32)
+    t = textures_from_u32(texs)
     images = [np.ascontiguousarray(im, np.uint8) for im in images]
     imgs = (RtImage * max(1, len(images)))()
     for i, im in enumerate(images):
@@ -221,7 +244,7 @@ class DeviceScene:
     def from_flat(cls, fs, device: int = 0) -> "DeviceScene":
         """fs: any object with the flat-scene attributes (kinds, item_mat, geom, nodes_box, nodes_lra, root, ...)."""
         desc, keep = make_desc(fs.kinds, fs.item_mat, fs.geom, fs.nodes_box, fs.nodes_lra, fs.root, fs.mats, fs.texs,
-                               fs.images, fs.cam, fs.bg, fs.light)
+                               fs.images, fs.cam, fs.bg, fs.light, getattr(fs, "wrap", None))
         return cls(desc, device, keep)
 
     def close(self):
@@ -240,6 +263,9 @@ class DeviceScene:
         b = C.c_uint64(0)
         check(lib().rt_scene_device_bytes(self.h, C.byref(b)))
         return b.value
+
+    def set_ray_time(self, time: float):
+        check(lib().rt_scene_set_ray_time(self.h, float(time)))
 
     def trace(self, org, dir, t_min=0.001, t_max=float("inf")):
         org = np.ascontiguousarray(org, np.float32).reshape(-1, 3)

@@ -51,6 +51,7 @@ class FlatScene:
     depth: int
     mats: np.ndarray
     texs: np.ndarray
+    wrap: np.ndarray = None
     images: list = field(default_factory=list)
     cam: np.ndarray = None
     bg: np.ndarray = None
@@ -73,7 +74,7 @@ def host_lib():
         L.rtw_world_create_elements.restype = C.c_void_p
         L.rtw_world_create_elements.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                                 C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                C.c_void_p]
+                                                C.c_void_p, C.c_void_p]
         L.rtw_world_destroy.argtypes = [C.c_void_p]
         L.rtw_world_destroy.restype = None
         L.rtw_world_info.argtypes = [C.c_void_p, C.c_void_p]
@@ -134,14 +135,14 @@ class World:
 
     @classmethod
     def named(cls, name: str) -> "World":
-        need_earth = name in ("demo:earth_mapped", "config:c3")
+        need_earth = name in ("demo:earth_mapped", "config:c3")  # JPEG decode is caller-side (image crate in the reference)
         e = earth_rgb8() if need_earth else None
         return cls(host_lib().rtw_world_create(name.encode(), os.path.join(ASSETS, "suzanne.obj").encode(),
                                                os.path.join(ASSETS, "cube.obj").encode(),
                                                e.shape[1] if need_earth else 0, e.shape[0] if need_earth else 0, _p(e)))
 
     @classmethod
-    def from_elements(cls, kinds, item_mat, geom, mats, texs, images, cam, bg, light) -> "World":
+    def from_elements(cls, kinds, item_mat, geom, mats, texs, images, cam, bg, light, wrap=None) -> "World":
         """Scene::new(BoundingVolumeHierarchy::new(elements)) from SurfaceGeometry arrays (flat layouts of b200rt.h)."""
         kinds = np.ascontiguousarray(kinds, np.uint32)
         item_mat = np.ascontiguousarray(item_mat, np.uint32)
@@ -149,9 +150,7 @@ class World:
         mats_u = np.asarray(mats, np.uint32).reshape(-1, 3)
         m = np.zeros(len(mats_u), _cabi.MATERIAL_DTYPE)
         m["kind"], m["texture"], m["param"] = mats_u[:, 0], mats_u[:, 1], mats_u[:, 2].copy().view(np.float32)
-        texs_u = np.asarray(texs, np.uint32).reshape(-1, 5)
-        t = np.zeros(len(texs_u), _cabi.TEXTURE_DTYPE)
-        t["kind"], t["image"], t["rgb"] = texs_u[:, 0], texs_u[:, 1], texs_u[:, 2:5].copy().view(np.float32)
+        t = _cabi.textures_from_u32(texs)
         images = [np.ascontiguousarray(im, np.uint8) for im in images]
         imgs = (_cabi.RtImage * max(1, len(images)))()
         for i, im in enumerate(images):
@@ -159,8 +158,10 @@ class World:
         cam = np.ascontiguousarray(cam, np.float32)
         bg = np.ascontiguousarray(bg, np.float32)
         light = np.ascontiguousarray(light, np.float32)
+        wrap = None if wrap is None else np.ascontiguousarray(wrap, np.float32).reshape(len(kinds), 9)
         return cls(host_lib().rtw_world_create_elements(len(kinds), _p(kinds), _p(item_mat), _p(geom), len(m), _p(m), len(t),
-                                                        _p(t), len(images), C.cast(imgs, C.c_void_p), _p(cam), _p(bg), _p(light)))
+                                                        _p(t), len(images), C.cast(imgs, C.c_void_p), _p(cam), _p(bg), _p(light),
+                                                        _p(wrap)))
 
     def close(self):
         if getattr(self, "h", None):
@@ -190,7 +191,9 @@ class World:
             nodes_lra=np.stack([nodes["left"], nodes["right"], nodes["axis_id"]], axis=1) if nn else np.zeros((0, 3), np.uint32),
             root=int(self.info[2]), depth=int(self.info[3]),
             mats=np.stack([m["kind"], m["texture"], m["param"].copy().view(np.uint32)], axis=1),
-            texs=np.concatenate([np.stack([t["kind"], t["image"]], axis=1), t["rgb"].copy().view(np.uint32)], axis=1) if nt else np.zeros((0, 5), np.uint32),
+            texs=np.concatenate([np.stack([t["kind"], t["image"]], axis=1), t["rgb"].copy().view(np.uint32),
+                                 t["inv_frequency"].copy().view(np.uint32)[:, None], np.stack([t["even"], t["odd"]], axis=1)], axis=1) if nt else np.zeros((0, 8), np.uint32),
+            wrap=np.concatenate([items["wrap_flags"].astype(np.float32)[:, None], items["transform"], items["velocity"]], axis=1),
             cam=cam, bg=bg, light=light, default_size=(self.default_size.width, self.default_size.height))
         for i in range(ni):
             w, h = int(wh[i, 0]), int(wh[i, 1])
@@ -213,7 +216,8 @@ class World:
         _check(host_lib().rtw_world_upload_bytes(self.h, C.byref(b)))
         return b.value
 
-    def hit(self, org, dir, t_range=(0.001, float("inf")), device: int = 0):
+    def hit(self, org, dir, t_range=(0.001, float("inf")), device: int = 0, time: float = 0.0):
+        self.device_scene(device).set_ray_time(time)
         org = np.ascontiguousarray(org, np.float32).reshape(-1, 3)
         dir = np.ascontiguousarray(dir, np.float32).reshape(-1, 3)
         n = org.shape[0]

@@ -73,6 +73,7 @@ struct Workspace {
     std::mutex mu;
     DevBuf<float4> A[2], B[2], C[2], acc;
     DevBuf<int32_t> D[2];
+    DevBuf<float> Tm[2];
     DevBuf<uint2> hits;
     DevBuf<Counters> ctr;
     DevBuf<float> film;
@@ -103,6 +104,8 @@ struct RtScene {
     DevBuf<PrimDev> prims;
     DevBuf<ShadeDev> shade;
     DevBuf<float4> own_box;
+    DevBuf<WrapDev> wraps;
+    bool has_animation = false;
     DevBuf<MaterialDev> materials;
     DevBuf<TextureDev> textures;
     std::vector<DevBuf<uint8_t>*> images;
@@ -131,6 +134,8 @@ Box leaf_box(const RtItem& it) {
         b.mn[p0] = g[2]; b.mx[p0] = g[3];
         b.mn[p1] = g[4]; b.mx[p1] = g[5];
         b.mn[n] = g[1] - 0.01f; b.mx[n] = g[1] + 0.01f;
+    } else if (it.kind == RT_GEO_BOX) {  // Geometry::AxisAlignedBox: the box itself (hittable.rs:154)
+        for (int i = 0; i < 3; ++i) { b.mn[i] = g[i]; b.mx[i] = g[3 + i]; }
     } else {  // triangle_geometry.rs:47-49
         for (int i = 0; i < 3; ++i) {
             b.mn[i] = std::fmin(std::fmin(g[i], g[3 + i]), g[6 + i]);
@@ -188,11 +193,14 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     }
     for (uint32_t i = 0; i < d.n_textures; ++i) {
         const RtTexture& t = d.textures[i];
-        if (t.kind > RT_TEX_IMAGE) return fail(RT_EUNSUPPORTED, "texture kind outside the hot-path scope (Checker/Marble)");
+        if (t.kind > RT_TEX_CHECKER) return fail(RT_EUNSUPPORTED, "texture kind outside the hot-path scope (Marble / Perlin)");
+        if (t.kind == RT_TEX_CHECKER && (t.even >= d.n_textures || t.odd >= d.n_textures)) return fail(RT_EINVAL, "checker texture child out of range");
         if (t.kind == RT_TEX_IMAGE && (t.image >= d.n_images || !d.images[t.image].rgb8 || d.images[t.image].width == 0 || d.images[t.image].height == 0))
             return fail(RT_EINVAL, "image texture refers to a missing image");
     }
-    auto ref_of_item = [&](uint32_t item) { return RT_REF_LEAF | (d.items[item].kind << RT_REF_KIND_SHIFT) | item; };
+    auto ref_of_item = [&](uint32_t item) {
+        return RT_REF_LEAF | (d.items[item].kind << RT_REF_KIND_SHIFT) | (d.items[item].wrap_flags ? RT_REF_WRAPPED : 0u) | item;
+    };
     auto conv_ref = [&](uint32_t r, uint32_t* out) -> bool {
         if (r & RT_LEAF_BIT) {
             uint32_t item = r & ~RT_LEAF_BIT;
@@ -213,10 +221,15 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     //   triangles / rects: A = 8 eps max|coordinate|            (position = o + t d is rounded at coordinate scale)
     //   spheres          : A = 8 eps (max|coordinate| + 3 r), C = 8 * 3 eps / r   (|disc error| <~ 11 eps |oc|^2)
     std::vector<float> leafA(N), leafC(N);
+    bool any_wrap = false;
+    std::vector<WrapDev> wraps(N);
     const float eps = 5.9604645e-8f, safety = 8.0f;
     for (uint32_t i = 0; i < N; ++i) {
         const RtItem& it = d.items[i];
-        if (it.kind > RT_GEO_TRIANGLE) return fail(RT_EUNSUPPORTED, "geometry kind outside the hot-path scope (AxisAlignedBox/volumes/transform wrappers)");
+        if (it.kind > RT_GEO_BOX) return fail(RT_EUNSUPPORTED, "geometry kind outside the hot-path scope (volumes)");
+        if (it.wrap_flags & ~3u) return fail(RT_EINVAL, "unknown wrapper flag");
+        any_wrap = any_wrap || it.wrap_flags != 0u;
+        sc.has_animation = sc.has_animation || (it.wrap_flags & RT_WRAP_ANIMATION) != 0u;
         if (it.material >= d.n_materials) return fail(RT_EINVAL, "item material index out of range");
         const float* g = it.geom;
         PrimDev p;
@@ -231,6 +244,9 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
             if (plane > RT_RECT_YZ) return fail(RT_EINVAL, "rect plane out of range");
             p.q0 = make_float4(g[1], g[2], g[3], g[4]);
             p.q1 = make_float4(g[5], u2f(plane), 0.0f, 0.0f);
+        } else if (it.kind == RT_GEO_BOX) {
+            p.q0 = make_float4(g[0], g[1], g[2], 0.0f);
+            p.q1 = make_float4(g[3], g[4], g[5], 0.0f);
         } else {
             p = pack_triangle(g);
             s.q0 = make_float4(g[9], g[10], g[11], g[12]);
@@ -251,6 +267,14 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
             leafA[i] = safety * eps * maxabs;
             leafC[i] = 0.0f;
         }
+        WrapDev w{};
+        w.a = make_float4(it.transform[0], it.transform[1], it.transform[2], it.transform[3]);
+        w.b = make_float4(it.transform[4], it.velocity[0], it.velocity[1], it.velocity[2]);
+        w.flags = it.wrap_flags;
+        wraps[i] = w;
+        // Q2: the reference does not transform / motion-extend the AABB of a wrapped element, so its box (and every ancestor's)
+        // is NOT a true bound: no tight cull there, the reference's weak per-axis rule alone decides (guard band = +inf)
+        if (it.wrap_flags) { leafA[i] = INFINITY; leafC[i] = 0.0f; }
     }
     auto bf16_up = [](float v) -> uint32_t {  // smallest bf16 >= v (v >= 0)
         uint32_t b;
@@ -354,6 +378,8 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     S.cam.scaled_right = make_float3(c.scaled_right[0], c.scaled_right[1], c.scaled_right[2]);
     S.cam.scaled_up = make_float3(c.scaled_up[0], c.scaled_up[1], c.scaled_up[2]);
     S.cam.lens_radius = c.lens_radius;
+    S.cam.time_start = c.time_start;
+    S.cam.time_end = c.time_end;
     S.bg_is_sky = d.background_is_sky ? 1u : 0u;
     for (int k = 0; k < 3; ++k) S.bg[k] = d.background_rgb[k];
     S.has_light = d.has_light ? 1u : 0u;
@@ -372,6 +398,11 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     CU(sc.prims.alloc(N));
     CU(sc.shade.alloc(N));
     CU(sc.own_box.alloc(std::max<size_t>(own_box.size(), 2)));
+    if (any_wrap) {
+        CU(sc.wraps.alloc(N));
+        CU(cudaMemcpy(sc.wraps.p, wraps.data(), N * sizeof(WrapDev), cudaMemcpyHostToDevice));
+        sc.device_bytes += (uint64_t)N * sizeof(WrapDev);
+    }
     if (!nodes.empty()) CU(cudaMemcpy(sc.nodes.p, nodes.data(), nodes.size() * sizeof(NodeDev), cudaMemcpyHostToDevice));
     if (!nodes.empty()) CU(cudaMemcpy(sc.own_box.p, own_box.data(), own_box.size() * sizeof(float4), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(sc.prims.p, prims.data(), N * sizeof(PrimDev), cudaMemcpyHostToDevice));
@@ -401,6 +432,11 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
             t.height = d.images[d.textures[i].image].height;
             t.texels = img_dev[d.textures[i].image];
         }
+        if (t.kind == RT_TEX_CHECKER) {
+            t.inv_frequency = d.textures[i].inv_frequency;
+            t.even = d.textures[i].even;
+            t.odd = d.textures[i].odd;
+        }
         texs[i] = t;
     }
     CU(sc.materials.alloc(mats.size()));
@@ -412,6 +448,8 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     S.prims = sc.prims.p;
     S.shade = sc.shade.p;
     S.own_box = sc.own_box.p;
+    S.wraps = sc.wraps.p;
+    S.trace_time = 0.0f;
     S.materials = sc.materials.p;
     S.textures = sc.textures.p;
     return RT_OK;
@@ -430,17 +468,22 @@ int persistent_grid(const RtScene& sc, K kernel, int block, size_t smem, int* ou
     return RT_OK;
 }
 
-int ensure_workspace(Workspace& sc, size_t slots, size_t npix) {
+int ensure_workspace(Workspace& sc, size_t slots, size_t npix, bool need_time) {
     if (sc.ws_slots < slots) {
         for (int q = 0; q < 2; ++q) {
             CU(sc.A[q].alloc(slots));
             CU(sc.B[q].alloc(slots));
             CU(sc.C[q].alloc(slots));
             CU(sc.D[q].alloc(slots));
+            sc.Tm[q].release();
         }
         CU(sc.hits.alloc(slots));
         CU(sc.acc.alloc(slots));
         sc.ws_slots = slots;
+    }
+    if (need_time && sc.Tm[0].n < sc.ws_slots) {
+        CU(sc.Tm[0].alloc(sc.ws_slots));
+        CU(sc.Tm[1].alloc(sc.ws_slots));
     }
     if (!sc.ctr.p) CU(sc.ctr.alloc(Workspace::MAX_PIPES));
     if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, Workspace::MAX_PIPES * 2 * sizeof(Counters)));
@@ -479,7 +522,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     if (slots > 0xFFFFFFF0ull) return fail(RT_EINVAL, "width*height*lanes exceeds 2^32 path slots");
     Workspace& ws = workspace_of(sc.device);
     std::lock_guard<std::mutex> ws_lock(ws.mu);
-    int rc = ensure_workspace(ws, slots, npix);
+    int rc = ensure_workspace(ws, slots, npix, sc.has_animation);
     if (rc) return rc;
 
     RenderDev R{};   // rank-level description (k_finalize uses it as is)
@@ -522,7 +565,10 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
             pp.R = R;
             pp.R.pipe = (uint32_t)p; pp.R.n_pipes = (uint32_t)G;
             pp.R.cap = (uint32_t)((size_t)lanes_p * npix);
-            for (int q = 0; q < 2; ++q) { pp.R.A[q] = ws.A[q].p + off; pp.R.B[q] = ws.B[q].p + off; pp.R.C[q] = ws.C[q].p + off; pp.R.D[q] = ws.D[q].p + off; }
+            for (int q = 0; q < 2; ++q) {
+                pp.R.A[q] = ws.A[q].p + off; pp.R.B[q] = ws.B[q].p + off; pp.R.C[q] = ws.C[q].p + off; pp.R.D[q] = ws.D[q].p + off;
+                pp.R.Tm[q] = sc.has_animation ? ws.Tm[q].p + off : nullptr;
+            }
             pp.R.hits = ws.hits.p + off;
             pp.R.ctr = ws.ctr.p + p;
             pp.st = ws.pipe_stream[p];
@@ -732,6 +778,12 @@ void rt_scene_destroy(RtScene* scene) {
     if (!scene) return;
     cudaSetDevice(scene->device);
     delete scene;
+}
+
+int rt_scene_set_ray_time(RtScene* scene, float time) {
+    if (!scene) return fail(RT_EINVAL, "scene is NULL");
+    scene->dev.trace_time = time;
+    return RT_OK;
 }
 
 int rt_scene_device_bytes(const RtScene* scene, uint64_t* out_bytes) {

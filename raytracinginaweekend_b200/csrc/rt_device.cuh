@@ -12,10 +12,12 @@ namespace rt {
 // ------------------------------------------------------------------------------------------------
 // Device scene layout (HBM, all 16-byte aligned, fetched with 128-bit loads)
 // ------------------------------------------------------------------------------------------------
-// Child reference: bit31 = leaf, bits 30..29 = geometry kind, bits 28..0 = item index (= hit id).
+// Child reference: bit31 = leaf, bits 30..29 = geometry kind, bit 28 = wrapped (run-time Transformation / Animation),
+// bits 27..0 = item index (= hit id).
 #define RT_REF_LEAF 0x80000000u
 #define RT_REF_KIND_SHIFT 29
-#define RT_REF_ITEM_MASK 0x1FFFFFFFu
+#define RT_REF_WRAPPED 0x10000000u
+#define RT_REF_ITEM_MASK 0x0FFFFFFFu
 #define RT_NO_HIT 0xFFFFFFFFu
 
 // One internal BVH node = 64 B: the AABBs of BOTH children live in the parent ("children-in-parent"),
@@ -29,6 +31,7 @@ struct __align__(16) NodeDev {
 // One primitive = 64 B intersection record, indexed by item id.
 //   sphere  : q0 = center.xyz, radius
 //   rect    : q0 = dist, r0.lo, r0.hi, r1.lo | q1 = r1.hi, bits(plane), 0, 0
+//   box     : q0 = min.xyz, 0 | q1 = max.xyz, 0
 //   triangle: q0 = p0.xyz, n.x | q1 = n.yz, vt1.xy | q2 = vt1.z, d1, vt2.xy | q3 = vt2.z, d2, 0, 0
 //             n = unit(cross(dir1,dir2)), vt1 = cross(n,dir2), d1 = dot(dir1,vt1), vt2 = cross(n,dir1), d2 = dot(dir2,vt2)
 //             — the per-test constants of triangle_geometry.rs:14-29, hoisted to scene build with identical rounding.
@@ -40,21 +43,30 @@ struct __align__(16) PrimDev {
 struct __align__(16) ShadeDev {
     float4 q0, q1, q2, q3;
 };
+// Run-time wrappers of an item (row f2): SceneElement::Transformation{offset, y_sine, y_cosine} and ::Animation(velocity).
+//   a = offset.xyz, y_sine | b = y_cosine, velocity.xyz | flags in the child reference (RT_REF_WRAPPED) + c.x
+struct __align__(16) WrapDev {
+    float4 a, b;
+    uint32_t flags, pad0, pad1, pad2;
+};
 struct MaterialDev {  // 16 B
     uint32_t kind, texture;
     float param;
     uint32_t pad;
 };
-struct TextureDev {  // 32 B
-    uint32_t kind, width, height, pad;
+struct TextureDev {  // 48 B
+    uint32_t kind, width, height, even;  // even / odd: RT_TEX_CHECKER children
     float r, g, b;
-    uint32_t pad2;
+    uint32_t odd;
     const uint8_t* texels;  // RGB8, row 0 = top
+    float inv_frequency;
+    uint32_t pad;
 };
 
 struct CameraDev {
     float3 position, ulc, unit_right, unit_up, scaled_right, scaled_up;
     float lens_radius;
+    float time_start, time_end;
 };
 
 struct SceneDev {
@@ -69,6 +81,8 @@ struct SceneDev {
     uint32_t stack_cap;       // traversal stack entries per thread
     uint32_t root_margin;     // guard band of the root box test (packed like NodeDev.q3.w)
     const float4* own_box;    // [2*n_nodes] each node's own AABB (min.xyz,0 | max.xyz,0): only read on exact-tie pops
+    const WrapDev* wraps;     // [n_items] or NULL when no item is wrapped
+    float trace_time;         // Ray::time of rt_trace rays
     CameraDev cam;
     uint32_t bg_is_sky;
     float bg[3];
@@ -187,11 +201,69 @@ __device__ __forceinline__ PrimDev load_prim(const PrimDev* p) {
     return r;
 }
 
-// Leaf test dispatch.  Returns true and shrinks `end` when the primitive is accepted.
-__device__ __forceinline__ bool leaf_test(const SceneDev& S, uint32_t ref, float3 o, float3 d, float start, float& end) {
+// Aabb::hit as a primitive (src/lib/aabb.rs:80-167): intersections_line + near/far choice.  plane_out = axis of the hit face.
+__device__ __forceinline__ bool box_t(float4 mn4, float4 mx4, float3 o, float3 d, float start, float end, float& t_out, int& plane_out) {
+    const float mn[3] = {mn4.x - o.x, mn4.y - o.y, mn4.z - o.z};
+    const float mx[3] = {mx4.x - o.x, mx4.y - o.y, mx4.z - o.z};
+    const float dd[3] = {d.x, d.y, d.z};
+    float near = -__int_as_float(0x7f800000), far = __int_as_float(0x7f800000);
+    int np = 0, fp = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float t1 = mn[i] / dd[i], t2 = mx[i] / dd[i];
+        const float t_min = fminf(t1, t2), t_max = fmaxf(t1, t2);
+        if (t_min > near) { near = t_min; np = i; }
+        if (t_max < far) { far = t_max; fp = i; }
+        if (near > far || far < 0.0f) return false;
+    }
+    if (start <= near && near < end) { t_out = near; plane_out = np; return true; }
+    if (start <= far && far < end) { t_out = far; plane_out = fp; return true; }
+    return false;
+}
+// rotate_around_up (transformations.rs:107-111)
+__device__ __forceinline__ float3 rot_y(float c, float s, float3 v) { return f3(c * v.x + s * v.z, v.y, -s * v.x + c * v.z); }
+// Ray seen by a wrapped element: Animation first (outer), then Transformation (hittable.rs:234-244, 270-277)
+__device__ __forceinline__ void wrap_reverse_ray(const WrapDev& w, float time, float3& o, float3& d) {
+    if (w.flags & 2u) {  // Animation: Transformation::ZERO.translate(velocity * time).reverse_ray
+        const float3 off = f3(w.b.y * time, w.b.z * time, w.b.w * time);
+        o = rot_y(1.0f, -0.0f, sub3(o, off));
+        d = rot_y(1.0f, -0.0f, d);
+    }
+    if (w.flags & 1u) {
+        o = rot_y(w.b.x, -w.a.w, sub3(o, f3(w.a.x, w.a.y, w.a.z)));
+        d = rot_y(w.b.x, -w.a.w, d);
+    }
+}
+// Transformation::apply_hit_interaction for both wrappers, inner first (hittable.rs:279-283)
+__device__ __forceinline__ void wrap_apply_hit(const WrapDev& w, float time, float3& pos, float3& nrm) {
+    if (w.flags & 1u) {
+        pos = add3(rot_y(w.b.x, w.a.w, pos), f3(w.a.x, w.a.y, w.a.z));
+        nrm = rot_y(w.b.x, w.a.w, nrm);
+    }
+    if (w.flags & 2u) {
+        pos = add3(rot_y(1.0f, 0.0f, pos), f3(w.b.y * time, w.b.z * time, w.b.w * time));
+        nrm = rot_y(1.0f, 0.0f, nrm);
+    }
+}
+__device__ __forceinline__ WrapDev load_wrap(const SceneDev& S, uint32_t item) {
+    const float4* q = reinterpret_cast<const float4*>(S.wraps + item);
+    WrapDev w;
+    w.a = __ldg(q); w.b = __ldg(q + 1);
+    w.flags = __float_as_uint(__ldg(q + 2).x);
+    w.pad0 = w.pad1 = w.pad2 = 0u;
+    return w;
+}
+
+// Leaf test dispatch (SceneElement::hit -> Geometry::hit, hittable.rs:141-148, 230-244).  Returns true and shrinks `end` when
+// the primitive is accepted.  `time` is Ray::time (only Animation wrappers use it).
+__device__ __forceinline__ bool leaf_test(const SceneDev& S, uint32_t ref, float3 o, float3 d, float time, float start, float& end) {
     uint32_t kind = (ref >> RT_REF_KIND_SHIFT) & 3u;
     uint32_t item = ref & RT_REF_ITEM_MASK;
     const float4* q = reinterpret_cast<const float4*>(S.prims + item);
+    if (ref & RT_REF_WRAPPED) {
+        const WrapDev w = load_wrap(S, item);
+        wrap_reverse_ray(w, time, o, d);
+    }
     float t;
     bool hit;
     if (kind == 0u) {
@@ -201,6 +273,9 @@ __device__ __forceinline__ bool leaf_test(const SceneDev& S, uint32_t ref, float
         p.q0 = __ldg(q); p.q1 = __ldg(q + 1); p.q2 = __ldg(q + 2); p.q3 = __ldg(q + 3);
         float w1, w2;
         hit = triangle_t(p, o, d, start, end, t, w1, w2);
+    } else if (kind == 3u) {
+        int plane;
+        hit = box_t(__ldg(q), __ldg(q + 1), o, d, start, end, t, plane);
     } else {
         float4 a = __ldg(q), b = __ldg(q + 1);
         hit = rect_t(__float_as_uint(b.y), a.x, a.y, a.z, a.w, b.x, o, d, start, end, t);
@@ -233,6 +308,7 @@ struct TravCount {
 };
 struct Trav {
     float3 o, d;
+    float time;        // Ray::time (Animation leaves)
     float3 inv, oinv;  // 1/d and -o/d: the fast path evaluates a slab plane as fma(b, inv, oinv)
     float start, end;
     float mscale;  // 2 * max_i |1 / d_i|: converts the lateral guard band into a gap in t
@@ -271,8 +347,8 @@ __device__ __forceinline__ bool root_gate(const SceneDev& S, float3 o, float3 d,
 }
 
 // Per-ray traversal setup (the root box has already been tested: root_gate).
-__device__ __forceinline__ void trav_setup(const SceneDev& S, Trav& T, float3 o, float3 d, float start, float end) {
-    T.o = o; T.d = d; T.start = start; T.end = end;
+__device__ __forceinline__ void trav_setup(const SceneDev& S, Trav& T, float3 o, float3 d, float time, float start, float end) {
+    T.o = o; T.d = d; T.time = time; T.start = start; T.end = end;
     T.best = RT_NO_HIT; T.sp = 0; T.cur = S.root;
     T.inv = f3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));  // correctly rounded 1/d
     T.oinv = f3(-o.x * T.inv.x, -o.y * T.inv.y, -o.z * T.inv.z);
@@ -287,8 +363,8 @@ __device__ __forceinline__ void trav_setup(const SceneDev& S, Trav& T, float3 o,
 }
 
 template <int MODE>
-__device__ __forceinline__ bool trav_begin(const SceneDev& S, Trav& T, float3 o, float3 d, float start, float end) {
-    trav_setup(S, T, o, d, start, end);
+__device__ __forceinline__ bool trav_begin(const SceneDev& S, Trav& T, float3 o, float3 d, float time, float start, float end) {
+    trav_setup(S, T, o, d, time, start, end);
     return root_gate(S, o, d, start, end, MODE == 0);
 }
 
@@ -317,7 +393,7 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
     if (do_leaf) {
         if (at_leaf) {
             if (COUNT) cnt->prims++;
-            if (leaf_test(S, cur, T.o, T.d, T.start, T.end)) T.best = cur;
+            if (leaf_test(S, cur, T.o, T.d, T.time, T.start, T.end)) T.best = cur;
             need_pop = true;
         }
     } else if (!at_leaf) {
@@ -409,14 +485,14 @@ __device__ __forceinline__ bool trav_step(const SceneDev& S, Trav& T, uint32_t* 
 }
 
 template <int MODE, bool COUNT = false>
-__device__ __forceinline__ HitRec traverse(const SceneDev& S, float3 o, float3 d, float start, float end_in,
+__device__ __forceinline__ HitRec traverse(const SceneDev& S, float3 o, float3 d, float time, float start, float end_in,
                                            uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride,
                                            TravCount* cnt = nullptr) {
     Trav T;
     HitRec best;
     best.ref = RT_NO_HIT;
     best.t = end_in;
-    if (!trav_begin<MODE>(S, T, o, d, start, end_in)) return best;
+    if (!trav_begin<MODE>(S, T, o, d, time, start, end_in)) return best;
     while (trav_step<MODE, COUNT>(S, T, stk_ref, stk_tn, stk_stride, cnt)) {}
     best.ref = T.best;
     best.t = T.end;
@@ -439,13 +515,19 @@ __device__ __forceinline__ void sphere_uv(float3 n, float& u, float& v) {
     u = phi / 6.28318530717958647692f;
     v = theta / 3.14159265358979323846f;
 }
-__device__ __forceinline__ Interaction make_interaction(const SceneDev& S, uint32_t ref, float t, float3 o, float3 d,
+__device__ __forceinline__ Interaction make_interaction(const SceneDev& S, uint32_t ref, float t, float3 o, float3 d, float time,
                                                         bool want_uv) {
     Interaction hi;
     uint32_t kind = (ref >> RT_REF_KIND_SHIFT) & 3u;
     uint32_t item = ref & RT_REF_ITEM_MASK;
     const float4* q = reinterpret_cast<const float4*>(S.prims + item);
     const float4* sq = reinterpret_cast<const float4*>(S.shade + item);
+    WrapDev wr;
+    const bool wrapped = (ref & RT_REF_WRAPPED) != 0u;
+    if (wrapped) {  // the element sees the reverse-transformed ray (hittable.rs:234-244)
+        wr = load_wrap(S, item);
+        wrap_reverse_ray(wr, time, o, d);
+    }
     float3 pos = add3(o, mul3(d, t));  // Ray::at, ray.rs:20-22
     float3 sn;
     hi.u = 0.0f; hi.v = 0.0f;
@@ -468,6 +550,26 @@ __device__ __forceinline__ Interaction make_interaction(const SceneDev& S, uint3
         sn = f3(s0.x * w0 + s0.w * w1 + s1.z * w2, s0.y * w0 + s1.x * w1 + s1.w * w2, s0.z * w0 + s1.y * w1 + s2.x * w2);
         hi.u = s2.y * w0 + s2.w * w1 + s3.y * w2;
         hi.v = s2.z * w0 + s3.x * w1 + s3.z * w2;
+    } else if (kind == 3u) {  // Aabb::hit, aabb.rs:92-101: face normal = signum(position - centre) on the hit plane's axis
+        int plane = 0;
+        const float4 mn = __ldg(q), mx = __ldg(q + 1);
+        {   // re-run intersections_line (same arithmetic as the accepted test) to recover which face produced t
+            const float mnv[3] = {mn.x - o.x, mn.y - o.y, mn.z - o.z}, mxv[3] = {mx.x - o.x, mx.y - o.y, mx.z - o.z}, dd[3] = {d.x, d.y, d.z};
+            float near = -__int_as_float(0x7f800000), far = __int_as_float(0x7f800000);
+            int np = 0, fp = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float t1 = mnv[i] / dd[i], t2 = mxv[i] / dd[i];
+                const float t_min = fminf(t1, t2), t_max = fmaxf(t1, t2);
+                if (t_min > near) { near = t_min; np = i; }
+                if (t_max < far) { far = t_max; fp = i; }
+            }
+            plane = (near == t) ? np : fp;
+        }
+        const float centre = (comp3(f3(mx.x, mx.y, mx.z), plane) + comp3(f3(mn.x, mn.y, mn.z), plane)) * 0.5f;
+        const float v = comp3(pos, plane) - centre;
+        const float sg = (v != v) ? v : (signbit(v) ? -1.0f : 1.0f);  // f32::signum
+        sn = f3(plane == 0 ? sg : 0.0f, plane == 1 ? sg : 0.0f, plane == 2 ? sg : 0.0f);
     } else {
         float4 a = __ldg(q), b = __ldg(q + 1);
         int p0, p1, n;
@@ -480,6 +582,7 @@ __device__ __forceinline__ Interaction make_interaction(const SceneDev& S, uint3
     hi.front_face = dot3(sn, d) < 0.0f;  // hittable.rs:41
     hi.normal = hi.front_face ? sn : neg3(sn);
     hi.position = pos;
+    if (wrapped) wrap_apply_hit(wr, time, hi.position, hi.normal);
     return hi;
 }
 
@@ -555,8 +658,20 @@ __device__ __forceinline__ uint32_t sat_u32(float v) {  // Rust `as u32` (satura
     if (v >= 4294967296.0f) return 0xFFFFFFFFu;
     return (uint32_t)v;
 }
-__device__ __forceinline__ float3 texture_sample(const SceneDev& S, uint32_t tex, float u, float v) {
+// does sampling this texture (through any checker nesting) read uv?
+__device__ __forceinline__ bool texture_needs_uv(const SceneDev& S, uint32_t tex) {
+    const TextureDev t = S.textures[tex];
+    if (t.kind == 1u) return true;
+    if (t.kind == 2u) return true;  // a checker may select an image texture: be conservative
+    return false;
+}
+__device__ __forceinline__ float3 texture_sample(const SceneDev& S, uint32_t tex, float u, float v, float3 position) {
     TextureDev t = S.textures[tex];
+    for (int depth = 0; depth < 8 && t.kind == 2u; ++depth) {  // Checker (texture.rs:26-35): pick even / odd by the sign of the sine product
+        const float sx = position.x * t.inv_frequency, sy = position.y * t.inv_frequency, sz = position.z * t.inv_frequency;
+        const float sines = sinf(sx) * sinf(sy) * sinf(sz);
+        t = S.textures[sines < 0.0f ? t.even : t.odd];
+    }
     if (t.kind == 0u) return f3(t.r, t.g, t.b);
     uint32_t pu = min(sat_u32(u * (float)t.width), t.width - 1u);
     uint32_t pv = min(sat_u32(v * (float)t.height), t.height - 1u);

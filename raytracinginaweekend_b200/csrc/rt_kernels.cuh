@@ -27,6 +27,7 @@ struct RenderDev {
     float4* B[2];   // direction.xyz, bits(sample k within the lane)
     float4* C[2];   // throughput.rgb, primary direction.y (Q6)
     int32_t* D[2];  // remaining depth
+    float* Tm[2];   // Ray::time of the path (camera.rs:185-190); NULL when the scene has no Animation leaf
     uint2* hits;    // (child ref of closest primitive | RT_NO_HIT, bits(t)) per queue position
     float4* acc;    // [n_local_lanes * npix] running per-lane sums (exclusive owner: the slot's single live path)
     Counters* ctr;
@@ -55,7 +56,7 @@ __device__ __forceinline__ uint32_t lane_samples(const RenderDev& R, uint32_t la
 
 // New camera path for (pixel, lane, sample k).
 __device__ __forceinline__ void generate_path(const SceneDev& S, const RenderDev& R, uint32_t pixel, uint32_t lane_id,
-                                              uint32_t k, float3& o, float3& d) {
+                                              uint32_t k, float3& o, float3& d, float& time) {
     uint32_t x = pixel % R.width, y = pixel / R.width;
     uint32_t s_global = k * R.n_tasks + lane_id;
     uint4 r = philox4x32_10(R.seed0, R.seed1, pixel, s_global, 0u, 0u);
@@ -63,6 +64,14 @@ __device__ __forceinline__ void generate_path(const SceneDev& S, const RenderDev
     float px = fx + (u01(r.x) * R.sx + 0.0f);                   // Uniform<Vec2f>: x then y (vec2.rs:77-82)
     float py = fy + (u01(r.y) * R.sy + 0.0f);
     camera_ray(S.cam, px, py, r, o, d);
+    // shutter time (camera.rs:185-190): the next draw of the camera block after the lens disc (draw #2 without a lens,
+    // draw #4 = first output of sub-block 1 with one); shutter_pace is always zero in the reference's builders
+    time = S.cam.time_start;
+    if (S.cam.time_start != S.cam.time_end) {
+        uint32_t bits = r.z;
+        if (S.cam.lens_radius > 0.0f) bits = philox4x32_10(R.seed0, R.seed1, pixel, s_global, 0u, 1u).x;
+        time = S.cam.time_start + u01(bits) * (S.cam.time_end - S.cam.time_start);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R) {
@@ -72,7 +81,9 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
         const uint32_t slot = local_lane * R.npix + pixel;  // accumulator index, unique across pipelines
         const uint32_t lane_id = R.lane_first + local_lane * R.lane_stride;
         float3 o, d;
-        generate_path(S, R, pixel, lane_id, 0u, o, d);
+        float time;
+        generate_path(S, R, pixel, lane_id, 0u, o, d, time);
+        if (R.Tm[0]) R.Tm[0][j] = time;
         R.A[0][j] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
         const uint32_t miss = root_gate(S, o, d, 0.001f, __int_as_float(0x7f800000), R.ref_only != 0u) ? 0u : RT_ROOT_MISS;
         R.B[0][j] = make_float4(d.x, d.y, d.z, __uint_as_float(miss));
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
                 if (__float_as_uint(b.w) & RT_ROOT_MISS) {
                     R.hits[my_pos] = make_uint2(RT_NO_HIT, __float_as_uint(INF));
                 } else {
-                    trav_setup(S, T, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), 0.001f, INF);
+                    trav_setup(S, T, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), R.Tm[q] ? R.Tm[q][my_pos] : 0.0f, 0.001f, INF);
                     active = true;
                 }
             }
@@ -205,12 +216,13 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
         const uint32_t ipos = queue_pos(i, nb, R.cap);
         bool live = false, fresh = false;
         float3 o = f3(0, 0, 0), d = f3(0, 0, 1), thr = f3(1, 1, 1);
-        float dy0 = 0.0f;
+        float dy0 = 0.0f, time = 0.0f;
         uint32_t slot = 0, k = 0;
         int32_t depth = 0;
         if (i < n) {
             float4 a = R.A[q][ipos], b = R.B[q][ipos], c = R.C[q][ipos];
             depth = R.D[q][ipos];
+            time = R.Tm[q] ? R.Tm[q][ipos] : 0.0f;
             uint2 h = R.hits[ipos];
             o = f3(a.x, a.y, a.z); d = f3(b.x, b.y, b.z); thr = f3(c.x, c.y, c.z);
             dy0 = c.w;
@@ -232,7 +244,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
             }
             if (R.mode == 1u) {  // RenderMode::Normals (rendering.rs:108-116)
                 if (h.x != RT_NO_HIT) {
-                    Interaction hi = make_interaction(S, h.x, t, o, d, false);
+                    Interaction hi = make_interaction(S, h.x, t, o, d, time, false);
                     radiance = f3((hi.normal.x + 1.0f) * 0.5f, (hi.normal.y + 1.0f) * 0.5f, (hi.normal.z + 1.0f) * 0.5f);
                 } else {
                     radiance = bgc;
@@ -242,7 +254,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
             } else if (depth <= 1) {
                 radiance = f3(0.0f, 0.0f, 0.0f);  // Q7, rendering.rs:26-27
             } else {
-                Interaction hi = make_interaction(S, h.x, t, o, d, false);
+                Interaction hi = make_interaction(S, h.x, t, o, d, time, false);
                 const MaterialDev m = S.materials[hi.material];
                 const uint32_t s_global = k * R.n_tasks + lane_id;
                 const uint4 rnd = philox4x32_10(R.seed0, R.seed1, pixel, s_global, 1u + (uint32_t)(R.max_depth - depth), 0u);
@@ -252,13 +264,12 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
                 float3 emitted = f3(0.0f, 0.0f, 0.0f);
                 // texture coordinates are only needed by image textures: sphere uv costs acos+atan2
                 float tu = hi.u, tv = hi.v;
-                if (m.kind != 2u && S.textures[m.texture].kind == 1u && ((h.x >> RT_REF_KIND_SHIFT) & 3u) == 0u) {
-                    float4 sph = __ldg(reinterpret_cast<const float4*>(S.prims + (h.x & RT_REF_ITEM_MASK)));
-                    float3 sn = div3(sub3(hi.position, f3(sph.x, sph.y, sph.z)), sph.w);
-                    sphere_uv(sn, tu, tv);
+                if (m.kind != 2u && ((h.x >> RT_REF_KIND_SHIFT) & 3u) == 0u && texture_needs_uv(S, m.texture)) {
+                    const Interaction hu = make_interaction(S, h.x, t, o, d, time, true);  // sphere uv costs acos + atan2: only on demand
+                    tu = hu.u; tv = hu.v;
                 }
                 if (m.kind == 0u) {  // Lambert, material.rs:59-63 + rendering.rs:35-51
-                    att = texture_sample(S, m.texture, tu, tv);
+                    att = texture_sample(S, m.texture, tu, tv, hi.position);
                     const float3 nrm = hi.normal;
                     const float PI = 3.14159265358979323846f;
                     float pdf;
@@ -307,7 +318,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
                     float3 dir = add3(refl, fuzz_dir);
                     if (dot3(dir, hi.normal) > 0.0f) {
                         ndir = unit3(dir);
-                        att = texture_sample(S, m.texture, tu, tv);
+                        att = texture_sample(S, m.texture, tu, tv, hi.position);
                         scattered = true;
                     }
                 } else if (m.kind == 2u) {  // Dielectric, material.rs:80-105
@@ -337,7 +348,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
                     ndir = unit3(dir);
                     scattered = true;
                 } else {  // DiffuseLight: never scatters, emits from both faces (Q14), material.rs:132-137
-                    emitted = texture_sample(S, m.texture, tu, tv);
+                    emitted = texture_sample(S, m.texture, tu, tv, hi.position);
                 }
                 if (scattered) {
                     // rendering.rs:54-61.  accum_emitted stays 0 unless the throughput is non-finite, in which case
@@ -363,7 +374,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
                 R.acc[slot] = s;
                 if (k + 1u < lane_samples(R, lane_id)) {  // regenerate in place: next sample of this (pixel, lane)
                     k += 1u;
-                    generate_path(S, R, pixel, lane_id, k, o, d);
+                    generate_path(S, R, pixel, lane_id, k, o, d, time);
                     thr = f3(1.0f, 1.0f, 1.0f);
                     dy0 = d.y;
                     depth = R.max_depth;
@@ -393,6 +404,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
                 R.B[q ^ 1][pos] = make_float4(d.x, d.y, d.z, __uint_as_float(k | miss));
                 R.C[q ^ 1][pos] = make_float4(thr.x, thr.y, thr.z, dy0);
                 R.D[q ^ 1][pos] = depth;
+                if (R.Tm[q ^ 1]) R.Tm[q ^ 1][pos] = time;
             }
         }
     }
@@ -446,9 +458,9 @@ __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ SceneDev 
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]);
         float3 d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
-        HitRec h = traverse<MODE>(S, o, d, t_min, t_max, stk_ref, stk_tn, blockDim.x);
+        HitRec h = traverse<MODE>(S, o, d, S.trace_time, t_min, t_max, stk_ref, stk_tn, blockDim.x);
         if (h.ref != RT_NO_HIT) {
-            Interaction hi = make_interaction(S, h.ref, h.t, o, d, true);
+            Interaction hi = make_interaction(S, h.ref, h.t, o, d, S.trace_time, true);
             if (hit_id) hit_id[i] = h.ref & RT_REF_ITEM_MASK;
             if (t_out) t_out[i] = h.t;
             if (normal) { normal[3 * i] = hi.normal.x; normal[3 * i + 1] = hi.normal.y; normal[3 * i + 2] = hi.normal.z; }

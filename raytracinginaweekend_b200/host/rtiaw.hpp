@@ -24,6 +24,12 @@
 
 namespace rtiaw {
 
+// libm calls the reference makes at RUN time (f32::tan / f32::sin_cos -> the platform libm); `volatile` stops the compiler
+// from folding them at compile time with a differently-rounded result.
+inline float libm_tan(float x) { volatile float v = x; return std::tan(v); }
+inline float libm_sin(float x) { volatile float v = x; return std::sin(v); }
+inline float libm_cos(float x) { volatile float v = x; return std::cos(v); }
+
 // ------------------------------------------------------------------ math types (src/lib/vec3.rs, vec2.rs, color.rs)
 struct Vec3 {
     float x = 0, y = 0, z = 0;
@@ -76,6 +82,16 @@ struct Aabb {
         return {{std::fmin(a.min.x, b.min.x), std::fmin(a.min.y, b.min.y), std::fmin(a.min.z, b.min.z)},
                 {std::fmax(a.max.x, b.max.x), std::fmax(a.max.y, b.max.y), std::fmax(a.max.z, b.max.z)}};
     }
+    // Transformation::apply_aabb (hittable.rs:285-291) as it actually behaves (Q2): `for mut c in corners` transforms COPIES, so
+    // the result is the bounding box of the eight UNtransformed corners (aabb.rs:178-192) — equal to *this up to one rounding
+    // of min + (max - min).
+    Aabb apply_aabb_as_reference() const {
+        const Dir3 right{max.x - min.x, 0.0f, 0.0f}, up{0.0f, max.y - min.y, 0.0f}, fwd{0.0f, 0.0f, max.z - min.z};
+        const Point3 c[8] = {min, min + right, min + up, min + fwd, max, max - right, max - up, max - fwd};
+        Aabb b{c[0], c[0]};
+        for (int k = 1; k < 8; ++k) b = surrounding(b, Aabb{c[k], c[k]});
+        return b;
+    }
 };
 
 // ------------------------------------------------------------------ src/lib/transformations.rs
@@ -97,7 +113,7 @@ public:
     Transformation rotate_around_up(float angle_deg) const {  // :26-36
         Transformation r = *this;
         const float rad = angle_deg * (3.14159265358979323846f / 180.0f);
-        const float s = std::sin(rad), c = std::cos(rad);
+        const float s = libm_sin(rad), c = libm_cos(rad);
         rotate_y(c, s, r.offset);
         Vec3 sc(y_sine, 0.0f, y_cosine);
         rotate_y(c, s, sc);
@@ -114,6 +130,12 @@ public:
         return d;
     }
     Dir3 apply_direction(Dir3 d) const { return apply_normal(d); }
+    // split_translation_remainder (:66-70): (offset, the same rotation without the offset)
+    Transformation rotation_remainder() const {
+        Transformation r = *this;
+        r.offset = dir::ZERO;
+        return r;
+    }
     Transformation then(const Transformation& next) const {  // :89-98
         Transformation r;
         r.offset = next.apply_direction(offset) + next.offset;
@@ -151,6 +173,8 @@ struct Geometry {
     SphereGeometry sphere;
     RectGeometry rect;
     TriangleGeometry triangle;
+    Aabb box;  // Geometry::AxisAlignedBox(Aabb)
+    static Geometry AxisAlignedBox(const Aabb& b) { Geometry g; g.kind = RT_GEO_BOX; g.box = b; return g; }
     static Geometry Sphere(SphereGeometry s) {
         if (!(s.radius >= 0.0f)) throw std::invalid_argument("assertion failed: radius >= 0.0 (sphere_geometry.rs:13)");
         Geometry g; g.kind = RT_GEO_SPHERE; g.sphere = s; return g;
@@ -171,14 +195,16 @@ struct Geometry {
             b.max.at(a0) = rect.r0[1]; b.max.at(a1) = rect.r1[1]; b.max.at(n) = rect.dist + 0.01f;
             return b;
         }
+        if (kind == RT_GEO_BOX) return box;
         Aabb b{triangle.positions[0], triangle.positions[0]};
         for (int k = 1; k < 3; ++k) b = Aabb::surrounding(b, Aabb{triangle.positions[k], triangle.positions[k]});
         return b;
     }
-    // hittable.rs:165-208.  Returns the baked geometry; *rest is set when a run-time Transformation would remain.
-    Geometry partial_apply_transformation(const Transformation& t, bool* rest) const {
+    // hittable.rs:165-208.  Returns the baked geometry; *has_rest / *rest describe the run-time Transformation that remains
+    // (rects: the whole transform; boxes: the rotation-only remainder after the translation was baked — Q3).
+    Geometry partial_apply_transformation(const Transformation& t, bool* has_rest, Transformation* rest) const {
         Geometry g = *this;
-        *rest = false;
+        *has_rest = false;
         if (kind == RT_GEO_SPHERE) {
             g.sphere.center = t.apply_point(sphere.center);
         } else if (kind == RT_GEO_TRIANGLE) {
@@ -186,8 +212,13 @@ struct Geometry {
                 g.triangle.positions[k] = t.apply_point(triangle.positions[k]);
                 g.triangle.normals[k] = t.apply_normal(triangle.normals[k]);
             }
+        } else if (kind == RT_GEO_BOX) {
+            g.box = Aabb{box.min + t.offset, box.max + t.offset};
+            *rest = t.rotation_remainder();
+            *has_rest = !rest->is_zero();
         } else {
-            *rest = !t.is_zero();
+            *rest = t;
+            *has_rest = !t.is_zero();
         }
         return g;
     }
@@ -200,6 +231,8 @@ struct Geometry {
         } else if (kind == RT_GEO_RECT) {
             g[0] = (float)(uint32_t)rect.rect_plane; g[1] = rect.dist;
             g[2] = rect.r0[0]; g[3] = rect.r0[1]; g[4] = rect.r1[0]; g[5] = rect.r1[1];
+        } else if (kind == RT_GEO_BOX) {
+            g[0] = box.min.x; g[1] = box.min.y; g[2] = box.min.z; g[3] = box.max.x; g[4] = box.max.y; g[5] = box.max.z;
         } else {
             for (int k = 0; k < 3; ++k) {
                 g[3 * k] = triangle.positions[k].x; g[3 * k + 1] = triangle.positions[k].y; g[3 * k + 2] = triangle.positions[k].z;
@@ -226,7 +259,7 @@ public:
     std::vector<ImageData> images;
     TextureId texture_solid(Color c) {  // Texture::Solid
         RtTexture t{};
-        t.kind = RT_TEX_SOLID; t.image = 0xFFFFFFFFu; t.rgb[0] = c.x; t.rgb[1] = c.y; t.rgb[2] = c.z;
+        t.kind = RT_TEX_SOLID; t.image = 0xFFFFFFFFu; t.even = t.odd = 0xFFFFFFFFu; t.rgb[0] = c.x; t.rgb[1] = c.y; t.rgb[2] = c.z;
         textures.push_back(t);
         return (TextureId)textures.size() - 1;
     }
@@ -235,7 +268,13 @@ public:
         im.width = w; im.height = h; im.rgb8.assign(rgb8, rgb8 + (size_t)w * h * 3);
         images.push_back(std::move(im));
         RtTexture t{};
-        t.kind = RT_TEX_IMAGE; t.image = (uint32_t)images.size() - 1;
+        t.kind = RT_TEX_IMAGE; t.image = (uint32_t)images.size() - 1; t.even = t.odd = 0xFFFFFFFFu;
+        textures.push_back(t);
+        return (TextureId)textures.size() - 1;
+    }
+    TextureId texture_checker(float inv_frequency, TextureId even, TextureId odd) {  // Texture::Checker
+        RtTexture t{};
+        t.kind = RT_TEX_CHECKER; t.image = 0xFFFFFFFFu; t.inv_frequency = inv_frequency; t.even = even; t.odd = odd;
         textures.push_back(t);
         return (TextureId)textures.size() - 1;
     }
@@ -250,9 +289,22 @@ public:
 };
 
 // ------------------------------------------------------------------ SceneElement / BVH / Scene (hittable.rs:112-138, 345-482)
-struct SurfaceGeometry {  // SceneElement::SurfaceGeometry(geo, material)
+// SceneElement::SurfaceGeometry(geo, material), optionally wrapped by SceneElement::Transformation and then
+// SceneElement::Animation — the nesting NodeRef::finish produces (world_builder.rs:305-315).
+struct SurfaceGeometry {
     Geometry geometry;
     MaterialId material = 0;
+    bool has_transformation = false;
+    Transformation transformation;
+    bool has_animation = false;
+    Dir3 velocity;
+    // SceneElement::bounding_box (hittable.rs:249-267) incl. Q2: wrappers neither move nor motion-extend the box
+    Aabb bounding_box() const {
+        Aabb b = geometry.bounding_box();
+        if (has_transformation) b = b.apply_aabb_as_reference();
+        if (has_animation) b = Aabb::surrounding(b.apply_aabb_as_reference(), b.apply_aabb_as_reference());
+        return b;
+    }
 };
 
 // BoundingVolumeHierarchy::new (hittable.rs:360-427): same topology as the reference — pre-order node numbering,
@@ -270,7 +322,7 @@ public:
         const size_t n = items.size();
         Builder b;
         b.boxes.resize(n);
-        for (size_t i = 0; i < n; ++i) b.boxes[i] = items[i].geometry.bounding_box();
+        for (size_t i = 0; i < n; ++i) b.boxes[i] = items[i].bounding_box();
         b.order.resize(n);
         std::iota(b.order.begin(), b.order.end(), 0u);
         b.out = &bvh.nodes;
@@ -334,7 +386,7 @@ public:
     public:
         Builder& viewport(float w, float h) { vw_ = w; vh_ = h; return *this; }
         Builder& vertical_fov(float fov_deg, float aspect_ratio) {  // :72-79 (sets the viewport WIDTH, Q10)
-            const float h = std::tan((fov_deg * (3.14159265358979323846f / 180.0f)) * 0.5f);
+            const float h = libm_tan((fov_deg * (3.14159265358979323846f / 180.0f)) * 0.5f);
             return viewport(2.0f * h, 2.0f * h * aspect_ratio);
         }
         Builder& position(Point3 p) { pos_ = p; return *this; }
@@ -418,8 +470,14 @@ public:
         const Scene& sc = *hittable;
         items_scratch.resize(sc.elements.size());
         for (size_t i = 0; i < sc.elements.size(); ++i) {
-            sc.elements[i].geometry.write(items_scratch[i]);
-            items_scratch[i].material = sc.elements[i].material;
+            const SurfaceGeometry& e = sc.elements[i];
+            RtItem& it = items_scratch[i];
+            e.geometry.write(it);
+            it.material = e.material;
+            it.wrap_flags = (e.has_transformation ? (uint32_t)RT_WRAP_TRANSFORMATION : 0u) | (e.has_animation ? (uint32_t)RT_WRAP_ANIMATION : 0u);
+            it.transform[0] = e.transformation.offset.x; it.transform[1] = e.transformation.offset.y; it.transform[2] = e.transformation.offset.z;
+            it.transform[3] = e.transformation.y_sine; it.transform[4] = e.transformation.y_cosine;
+            it.velocity[0] = e.velocity.x; it.velocity[1] = e.velocity.y; it.velocity[2] = e.velocity.z;
         }
         images_scratch.clear();
         for (const ImageData& im : tables->images) images_scratch.push_back(RtImage{im.width, im.height, im.rgb8.data()});

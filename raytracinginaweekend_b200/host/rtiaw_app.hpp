@@ -3,8 +3,8 @@
 //   * OBJ ingest           : src/app/obj_loader.rs, bug-compatible fan triangulation (Q4)
 //   * WorldBuilder / NodeBuilder / NodeRef::finish : src/app/worlds/world_builder.rs
 //   * worlds               : the in-scope demo worlds of src/app/worlds/demo_worlds.rs + the BASELINE.json configs C1..C5
-// Out of scope here (rejected with an error, never silently changed): boxes, volumes, moving/rotated rect leaves,
-// Checker / Marble textures.
+// Row f2 is in: boxes, run-time Transformation / Animation wrappers (Q2 / Q3 kept), motion blur, Checker textures.
+// Out of scope (rejected with an error, never silently changed): volumes / Isotropic, Marble / Perlin.
 #pragma once
 #include <fstream>
 #include <functional>
@@ -165,6 +165,7 @@ struct Node {
     };
     std::vector<Geo> geo;
     Transformation transformation;
+    Dir3 moving_animation;
     std::vector<NodeRef> children;
 };
 
@@ -177,6 +178,7 @@ public:
     NodeBuilder& set_all_geo_as_poi() { for (auto& g : n_->geo) g.is_poi = true; return *this; }
     NodeBuilder& rotate_around_up(float deg) { n_->transformation = n_->transformation.rotate_around_up(deg); return *this; }
     NodeBuilder& translate(Dir3 o) { n_->transformation = n_->transformation.translate(o); return *this; }
+    NodeBuilder& animate_moving(Dir3 velocity) { n_->moving_animation = n_->moving_animation + velocity; return *this; }
     NodeRef build() { return n_; }
 
 private:
@@ -188,6 +190,7 @@ public:
     std::shared_ptr<MaterialTable> tables = std::make_shared<MaterialTable>();
     TextureId texture_solid(Color c) { return tables->texture_solid(c); }
     TextureId texture_image(uint32_t w, uint32_t h, const uint8_t* rgb8) { return tables->texture_image(w, h, rgb8); }
+    TextureId texture_checker(float inv_frequency, TextureId even, TextureId odd) { return tables->texture_checker(inv_frequency, even, odd); }
     MaterialId material_lambert_solid(Color c) { return tables->lambert(texture_solid(c)); }
     MaterialId material_lambert(TextureId t) { return tables->lambert(t); }
     MaterialId material_metal_solid(Color c, float fuzz) { return tables->metal(texture_solid(c), fuzz); }
@@ -209,6 +212,9 @@ public:
         auto n = std::make_shared<Node>();
         n->geo.push_back({g, m, false});
         return NodeBuilder(n);
+    }
+    NodeBuilder new_obj_box(float width, float height, float depth, MaterialId m) const {  // geo_box, world_builder.rs:88-93
+        return new_obj(Geometry::AxisAlignedBox(Aabb{Point3{}, Point3{width, height, depth}}), m);
     }
     NodeBuilder new_obj_sphere(float radius, MaterialId m) const { return new_obj(Geometry::Sphere({Point3{}, radius}), m); }
     NodeBuilder new_obj_sphere_ground(float radius, float height, MaterialId m) const {
@@ -242,11 +248,14 @@ public:
         std::function<void(const Node&, const Transformation&)> walk = [&](const Node& node, const Transformation& parent) {
             const Transformation full = parent.then(node.transformation);
             for (const Node::Geo& g : node.geo) {
-                bool rest = false;
-                const Geometry baked = g.geometry.partial_apply_transformation(full, &rest);
-                if (rest) throw std::runtime_error("a rect under a non-zero transformation needs a run-time Transformation leaf (out of scope: SURVEY §8 f2)");
-                all.push_back({baked, g.material});
-                if (g.is_poi && baked.kind == RT_GEO_RECT && !world->has_scattering_distribution_provider) {
+                SurfaceGeometry e;
+                e.geometry = g.geometry.partial_apply_transformation(full, &e.has_transformation, &e.transformation);
+                e.material = g.material;
+                e.has_animation = !(node.moving_animation == dir::ZERO);
+                e.velocity = node.moving_animation;
+                const Geometry& baked = e.geometry;
+                all.push_back(e);
+                if (g.is_poi && !e.has_transformation && baked.kind == RT_GEO_RECT && !world->has_scattering_distribution_provider) {
                     world->has_scattering_distribution_provider = true;
                     world->scattering_distribution_provider.rect = baked.rect;
                 }
@@ -368,6 +377,28 @@ inline NamedWorld create_world(const std::string& name, const Assets& assets) {
         detail::sphere_field(wb, rng, scene, 11);
         out.world = wb.finish(scene.build(), sky, cam);
         out.default_size = {1200, c1 ? 800 : 675};
+    } else if (name == "demo:cornell_box") {  // demo_worlds.rs:266-296
+        const float h = 278.0f;
+        const Camera cam = Camera::build().vertical_fov(40.0f, 1.0f).position({h, h, -800.0f}).look_at(dir::UP, {h, h, 0.0f}).build();
+        const MaterialId white = wb.material_lambert_solid({0.73f, 0.73f, 0.73f});
+        scene.add(detail::cornell_box_node(wb, 130.0f));
+        scene.add(wb.new_obj_box(165.0f, 330.0f, 165.0f, white).rotate_around_up(15.0f).translate({265.0f, 0.0f, 295.0f}));
+        scene.add(wb.new_obj_box(165.0f, 165.0f, 165.0f, white).rotate_around_up(-18.0f).translate({130.0f, 0.0f, 65.0f}));
+        out.world = wb.finish(scene.build(), BackgroundColor::Solid({0, 0, 0}), cam);
+        out.default_size = {600, 600};
+    } else if (name == "demo:moving_spheres") {  // demo_worlds.rs:351-393
+        const Camera cam = Camera::build().vertical_fov(60.0f, 16.0f / 19.0f).position({0.0f, 2.0f, 10.0f}).look_at(dir::UP, {0.0f, 2.0f, 0.0f})
+                               .motion_blur(0.0f, 0.5f).build();
+        const TextureId tex_black = wb.texture_solid({0.0f, 0.0f, 0.0f});
+        const TextureId tex_white = wb.texture_solid({1.0f, 1.0f, 1.0f});
+        const MaterialId mat_ground = wb.material_lambert(wb.texture_checker(10.0f, tex_black, tex_white));
+        const MaterialId mat_red = wb.material_lambert_solid({0.6f, 0.2f, 0.2f});
+        const MaterialId mat_blue = wb.material_lambert_solid({0.2f, 0.2f, 0.6f});
+        scene.add(wb.new_obj_sphere(100.0f, mat_ground).translate({0.0f, -100.0f, 0.0f}));
+        scene.add(wb.new_obj_sphere(0.5f, mat_red).translate({-2.0f, 1.5f, 0.0f}).animate_moving({2.0f, 0.0f, 0.0f}));
+        scene.add(wb.new_obj_sphere(0.5f, mat_blue).translate({0.0f, 0.5f, 0.0f}).animate_moving({0.0f, 1.0f, 0.0f}));
+        out.world = wb.finish(scene.build(), sky, cam);
+        out.default_size = {380, 320};
     } else if (name == "demo:simple_plane") {  // demo_worlds.rs:298-324
         const Camera cam = Camera::build().vertical_fov(60.0f, 9.0f / 16.0f).position({0.0f, 6.0f, 10.0f}).look_at(dir::UP, {0, 0, 0}).build();
         const MaterialId mat_emit = wb.material_diffuse_light_solid(100.0f * Color{1.0f, 1.0f, 1.0f});
@@ -440,7 +471,7 @@ inline NamedWorld create_world(const std::string& name, const Assets& assets) {
         out.world = wb.finish(scene.build(), sky, cam);
         out.default_size = {3840, 2160};
     } else {
-        throw std::runtime_error("unknown world '" + name + "' (out-of-scope demo worlds: cornell_box, cornell_box_smoke, moving_spheres, perlin_spheres, final_scene2)");
+        throw std::runtime_error("unknown world '" + name + "' (out-of-scope demo worlds need volumes / Perlin: cornell_box_smoke, perlin_spheres, final_scene2)");
     }
     return out;
 }

@@ -43,7 +43,7 @@ RtwWorld* rtw_world_create(const char* name, const char* suzanne, const char* cu
 
 RtwWorld* rtw_world_create_elements(uint32_t n, const uint32_t* kinds, const uint32_t* mat_of, const float* geom, uint32_t n_materials,
                                     const RtMaterial* materials, uint32_t n_textures, const RtTexture* textures, uint32_t n_images,
-                                    const RtImage* images, const float* cam, const float* bg, const float* light) {
+                                    const RtImage* images, const float* cam, const float* bg, const float* light, const float* wrap) {
     RtwWorld* w = nullptr;
     guard([&] {
         auto tables = std::make_shared<MaterialTable>();
@@ -74,10 +74,24 @@ RtwWorld* rtw_world_create_elements(uint32_t n, const uint32_t* kinds, const uin
                     t.texture_coords[k] = {g[18 + 2 * k], g[19 + 2 * k]};
                 }
                 geo = Geometry::Triangle(t);
+            } else if (kinds[i] == RT_GEO_BOX) {
+                geo = Geometry::AxisAlignedBox(Aabb{{g[0], g[1], g[2]}, {g[3], g[4], g[5]}});
             } else {
                 throw std::invalid_argument("geometry kind outside the hot-path scope");
             }
-            elems[i] = {geo, mat_of[i]};
+            SurfaceGeometry e;
+            e.geometry = geo;
+            e.material = mat_of[i];
+            if (wrap) {  // flags, offset xyz, y_sine, y_cosine, velocity xyz
+                const float* wv = wrap + 9 * (size_t)i;
+                const uint32_t fl = (uint32_t)wv[0];
+                e.has_transformation = (fl & RT_WRAP_TRANSFORMATION) != 0;
+                e.transformation.offset = {wv[1], wv[2], wv[3]};
+                e.transformation.y_sine = wv[4]; e.transformation.y_cosine = wv[5];
+                e.has_animation = (fl & RT_WRAP_ANIMATION) != 0;
+                e.velocity = {wv[6], wv[7], wv[8]};
+            }
+            elems[i] = e;
         }
         auto world = std::make_unique<World>();
         world->tables = tables;

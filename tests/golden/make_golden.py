@@ -21,7 +21,9 @@ sys.path.insert(0, os.path.dirname(HERE))
 from helpers import adversarial_rays, random_rays  # noqa: E402
 from oracle import binding as ob  # noqa: E402
 
-SCENES = {"config:c1": (48, 32), "config:c2": (48, 27), "config:c3": (32, 32), "demo:defocus_blur": (40, 24), "demo:simple_plane": (40, 24)}
+SCENES = {"config:c1": (48, 32), "config:c2": (48, 27), "config:c3": (32, 32), "demo:defocus_blur": (40, 24), "demo:simple_plane": (40, 24),
+          "demo:cornell_box": (32, 32), "demo:moving_spheres": (38, 32)}
+TRACE_TIME = 0.3   # Ray::time of the traced rays (only demo:moving_spheres has Animation leaves)
 RENDER = dict(spp=4, max_depth=50, threads=2, seed=20261018)
 
 
@@ -33,7 +35,7 @@ def main():
         ro, rd = random_rays(fs, 1500, 42)
         ao, ad = adversarial_rays(fs, 120, 7)
         org = np.concatenate([po, ro, ao]); dir = np.concatenate([pd, rd, ad])
-        hit = W.trace(org, dir)
+        hit = W.trace(org, dir, time=TRACE_TIME)
         img, st = W.render(w, h, RENDER["spp"], RENDER["max_depth"], RENDER["threads"], RENDER["seed"], "replay")
         out = os.path.join(HERE, name.replace(":", "_") + ".npz")
         np.savez_compressed(out, org=org, dir=dir, hit_id=hit["hit_id"], t=hit["t"], normal=hit["normal"], front_face=hit["front_face"],

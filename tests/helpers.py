@@ -38,17 +38,30 @@ def simple_camera(pos=(0.0, 1.0, 6.0), at=(0.0, 0.0, 0.0), fov=50.0, aspect=0.75
 
 
 def solid_tex(rgb):
-    return [0, MISS] + list(np.array(rgb, F32).view(np.uint32))
+    """[kind, image, r, g, b bits, inv_frequency bits, even, odd]"""
+    return [0, MISS] + list(np.array(rgb, F32).view(np.uint32)) + [0, MISS, MISS]
+
+
+def checker_tex(inv_frequency, even, odd):
+    return [2, MISS, 0, 0, 0, int(np.array([inv_frequency], F32).view(np.uint32)[0]), even, odd]
 
 
 def mat(kind, tex, param=0.0):
     return [kind, tex, int(np.array([param], F32).view(np.uint32)[0])]
 
 
-def random_scene(seed, n_spheres=20, n_tris=30, n_rects=4, extent=4.0, with_light=False, image_tex=None):
-    """Random mixed scene in the flat element layout (kinds, item_mat, geom, mats, texs, images, cam, bg, light)."""
+def random_scene(seed, n_spheres=20, n_tris=30, n_rects=4, extent=4.0, with_light=False, image_tex=None, n_boxes=0, wrap_fraction=0.0,
+                 checker=False):
+    """Random mixed scene in the flat element layout (kinds, item_mat, geom, mats, texs, images, cam, bg, light[, wrap]).
+    n_boxes / wrap_fraction / checker exercise row f2: AxisAlignedBox primitives, run-time Transformation / Animation wrappers
+    (with the reference's untransformed bounding boxes, Q2) and Checker textures."""
     rng = np.random.default_rng(seed)
     kinds, geom = [], []
+    for _ in range(n_boxes):
+        g = np.zeros(24, F32)
+        lo = rng.uniform(-extent, extent, 3)
+        g[0:3] = lo; g[3:6] = lo + rng.uniform(0.2, 1.5, 3)
+        kinds.append(3); geom.append(g)
     for _ in range(n_spheres):
         g = np.zeros(24, F32)
         g[0:3] = rng.uniform(-extent, extent, 3)
@@ -76,12 +89,17 @@ def random_scene(seed, n_spheres=20, n_tris=30, n_rects=4, extent=4.0, with_ligh
     texs = [solid_tex(rng.uniform(0.2, 0.9, 3)) for _ in range(4)] + [solid_tex([4.0, 4.0, 4.0])]
     images = []
     if image_tex is not None:
-        texs.append([1, 0, 0, 0, 0]); images.append(image_tex)
+        texs.append([1, 0, 0, 0, 0, 0, MISS, MISS]); images.append(image_tex)
     mats = [mat(0, 0), mat(0, 1), mat(1, 2, 0.0), mat(1, 3, 0.3), mat(2, MISS, 1.5), mat(3, 4)]
     if image_tex is not None:
         mats.append(mat(0, 5))
+    if checker:
+        texs.append(checker_tex(2.5, 0, 1)); texs.append(checker_tex(0.7, len(texs) - 1, 2))   # nested checker
+        mats.append(mat(0, len(texs) - 1)); mats.append(mat(1, len(texs) - 2, 0.2))
     item_mat = rng.integers(0, len(mats), len(kinds)).astype(np.uint32)
     cam = simple_camera(pos=(0.5, 1.0, 3.0 * extent), at=(0, 0, 0), fov=50.0, aspect=0.75)
+    if wrap_fraction > 0:
+        cam[19], cam[20] = 0.0, 1.0      # motion_blur(0, 1)
     bg = np.array([1, 0, 0, 0], F32)
     light = np.zeros(7, F32)
     if with_light:
@@ -90,8 +108,27 @@ def random_scene(seed, n_spheres=20, n_tris=30, n_rects=4, extent=4.0, with_ligh
             g = geom[ridx[0]]
             item_mat[ridx[0]] = 5
             light = np.array([1, g[0], g[1], g[2], g[3], g[4], g[5]], F32)
-    return dict(kinds=kinds, item_mat=item_mat, geom=geom, mats=np.array(mats, np.uint32), texs=np.array(texs, np.uint32),
-                images=images, cam=cam, bg=bg, light=light)
+    out = dict(kinds=kinds, item_mat=item_mat, geom=geom, mats=np.array(mats, np.uint32), texs=np.array(texs, np.uint32),
+               images=images, cam=cam, bg=bg, light=light)
+    if wrap_fraction > 0:
+        n = len(kinds)
+        wrap = np.zeros((n, 9), F32)
+        wrap[:, 5] = 1.0                                   # y_cosine of the identity
+        sel = rng.uniform(size=n) < wrap_fraction
+        if with_light:
+            sel[np.nonzero(kinds == 1)[0][:1]] = False     # the light-sampling rect must stay un-wrapped (world_builder.rs:317)
+        for i in np.nonzero(sel)[0]:
+            fl = rng.integers(1, 4)
+            if kinds[i] == 2:
+                fl = 2                                     # triangles are always fully baked: only Animation can wrap them
+            ang = rng.uniform(-1.0, 1.0)
+            if fl & 1:
+                wrap[i, 1:4] = rng.uniform(-0.5, 0.5, 3); wrap[i, 4] = np.sin(ang); wrap[i, 5] = np.cos(ang)
+            if fl & 2:
+                wrap[i, 6:9] = rng.uniform(-0.8, 0.8, 3)
+            wrap[i, 0] = fl
+        out["wrap"] = wrap
+    return out
 
 
 def scene_bounds(fs):
