@@ -47,13 +47,14 @@ extern "C" {
 enum { RT_GEO_SPHERE = 0, RT_GEO_RECT = 1, RT_GEO_TRIANGLE = 2, RT_GEO_BOX = 3 };
 /* Run-time wrappers of a scene element (SceneElement::Transformation / ::Animation, hittable.rs:117-118), applied in the
  * order NodeRef::finish nests them: Animation(Transformation(SurfaceGeometry))  (world_builder.rs:310-315) */
-enum { RT_WRAP_TRANSFORMATION = 1, RT_WRAP_ANIMATION = 2 };
+enum { RT_WRAP_TRANSFORMATION = 1, RT_WRAP_ANIMATION = 2,
+       RT_WRAP_VOLUME = 4 /* SceneElement::VolumeGeometry (hittable.rs:116, 294-342): geom is the boundary, material the phase function */ };
 /* RectPlane (rect_geometry.rs:8-22) */
 enum { RT_RECT_XY = 0, RT_RECT_XZ = 1, RT_RECT_YZ = 2 };
-/* Material kinds (material.rs:43-49; Isotropic is volume-only, out of scope) */
-enum { RT_MAT_LAMBERT = 0, RT_MAT_METAL = 1, RT_MAT_DIELECTRIC = 2, RT_MAT_DIFFUSE_LIGHT = 3 };
-/* Texture kinds (texture.rs:4-20; Marble/Perlin out of scope) */
-enum { RT_TEX_SOLID = 0, RT_TEX_IMAGE = 1, RT_TEX_CHECKER = 2 };
+/* Material kinds (material.rs:43-49) */
+enum { RT_MAT_LAMBERT = 0, RT_MAT_METAL = 1, RT_MAT_DIELECTRIC = 2, RT_MAT_DIFFUSE_LIGHT = 3, RT_MAT_ISOTROPIC = 4 };
+/* Texture kinds (texture.rs:4-20) */
+enum { RT_TEX_SOLID = 0, RT_TEX_IMAGE = 1, RT_TEX_CHECKER = 2, RT_TEX_MARBLE = 3 };
 /* RenderMode (rendering.rs:94-98) */
 enum { RT_MODE_DEFAULT = 0, RT_MODE_NORMALS = 1 };
 
@@ -72,6 +73,7 @@ typedef struct RtItem {
     uint32_t wrap_flags;  /* RT_WRAP_* bits */
     float transform[5];   /* offset xyz, y_sine, y_cosine */
     float velocity[3];
+    float neg_inv_density; /* RT_WRAP_VOLUME: -1 / density (VolumeGeometry::new, hittable.rs:301-307) */
 } RtItem;
 
 /* BoundingVolumeNode (hittable.rs:345-351) in the reference's pre-order numbering. */
@@ -91,9 +93,9 @@ typedef struct RtMaterial {
 
 typedef struct RtTexture {
     uint32_t kind;
-    uint32_t image;      /* RT_TEX_IMAGE: index into images */
+    uint32_t image;      /* RT_TEX_IMAGE: index into images; RT_TEX_MARBLE: index into perlins */
     float rgb[3];        /* RT_TEX_SOLID */
-    float inv_frequency; /* RT_TEX_CHECKER (texture.rs:8-12) */
+    float inv_frequency; /* RT_TEX_CHECKER (texture.rs:8-12); RT_TEX_MARBLE: scale (texture.rs:13-16) */
     uint32_t even, odd;  /* RT_TEX_CHECKER: texture indices (may themselves be checkers, nesting <= 8) */
 } RtTexture;
 
@@ -101,6 +103,14 @@ typedef struct RtImage {
     uint32_t width, height;
     const uint8_t* rgb8; /* row 0 = top, 3 bytes per texel (image::RgbImage) */
 } RtImage;
+
+/* Perlin noise tables (perlin.rs:10-16) with bits = 8: 256 gradient vectors + three 256-entry permutations. */
+typedef struct RtPerlin {
+    const float* ranvec;   /* 256 * 3 */
+    const uint32_t* perm_x;
+    const uint32_t* perm_y;
+    const uint32_t* perm_z;
+} RtPerlin;
 
 typedef struct RtCamera { /* camera.rs:154-164, private fields included */
     float position[3];
@@ -126,6 +136,8 @@ typedef struct RtSceneDesc {
     const RtTexture* textures;
     uint32_t n_images;
     const RtImage* images;
+    uint32_t n_perlins;
+    const RtPerlin* perlins;
     RtCamera camera;
     uint32_t background_is_sky; /* BackgroundColor::Sky vs ::Solid */
     float background_rgb[3];
@@ -168,7 +180,8 @@ void rt_scene_destroy(RtScene* scene);
 /* Device bytes held by the packed scene (nodes, primitives, shading records, tables, images). */
 int rt_scene_device_bytes(const RtScene* scene, uint64_t* out_bytes);
 
-/* Closest hit for n caller rays (host buffers).  org/dir: n*3 floats; outputs: hit_id n, t n, normal n*3,
+/* Closest hit for n caller rays (host buffers).  Volumes draw one random number per tested volume element inside the traversal
+ * (the reference passes an rng into Scene::hit for this): rt_trace keys that draw by (ray index, element index), seed 0.  org/dir: n*3 floats; outputs: hit_id n, t n, normal n*3,
  * front_face n, uv n*2 (any output pointer may be NULL).  Half-open range [t_min, t_max). */
 int rt_trace(RtScene* scene, const float* org_xyz, const float* dir_xyz, uint64_t n, float t_min, float t_max,
              uint32_t* hit_id, float* t, float* normal_xyz, uint8_t* front_face, float* uv);

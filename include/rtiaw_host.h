@@ -32,19 +32,22 @@ RtwWorld* rtw_world_create(const char* name, const char* suzanne_obj_path, const
                            uint32_t earth_h, const uint8_t* earth_rgb8);
 /* geom: 24 floats per element (layout of RtItem.geom); cam: position, look-at basis as the 23 floats of RtCamera in order;
  * bg: is_sky, r, g, b; light: has, plane, dist, r0lo, r0hi, r1lo, r1hi;
- * wrap9 (optional): per element flags (RT_WRAP_*), offset xyz, y_sine, y_cosine, velocity xyz. */
+ * wrap10 (optional): per element flags (RT_WRAP_*), offset xyz, y_sine, y_cosine, velocity xyz, -1/density. */
 RtwWorld* rtw_world_create_elements(uint32_t n, const uint32_t* kinds, const uint32_t* materials_of, const float* geom,
                                     uint32_t n_materials, const RtMaterial* materials, uint32_t n_textures,
                                     const RtTexture* textures, uint32_t n_images, const RtImage* images, const float* cam23,
-                                    const float* bg4, const float* light7, const float* wrap9 /* may be NULL */);
+                                    const float* bg4, const float* light7, const float* wrap10 /* may be NULL */,
+                                    uint32_t n_perlins, const RtPerlin* perlins);
 void rtw_world_destroy(RtwWorld* w);
 
-/* info[10]: n_items, n_nodes, root, depth, default_w, default_h, n_materials, n_textures, n_images, has_light */
+/* info[11]: n_items, n_nodes, root, depth, default_w, default_h, n_materials, n_textures, n_images, has_light, n_perlins */
 int rtw_world_info(const RtwWorld* w, uint64_t* info);
 /* Copies the flattened scene into caller arrays sized from rtw_world_info (same layouts as RtItem / RtBvhNode / ...). */
 int rtw_world_export(const RtwWorld* w, RtItem* items, RtBvhNode* nodes, RtMaterial* materials, RtTexture* textures,
                      uint32_t* image_wh, float* cam23, float* bg4, float* light7);
 const uint8_t* rtw_world_image(const RtwWorld* w, uint32_t index);
+/* Perlin table `index`: 768 gradient floats, then perm_x | perm_y | perm_z (256 u32 each). */
+int rtw_world_perlin(const RtwWorld* w, uint32_t index, float* ranvec768, uint32_t* perm768);
 
 /* The device-resident scene (created on first use; owned by the world). */
 int rtw_world_device(RtwWorld* w, int device, RtScene** out_scene);

@@ -40,8 +40,9 @@ def lib():
         L.orc_world_create_flat.restype = C.c_void_p
         L.orc_world_create_flat.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                             C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                            C.c_void_p, C.c_void_p, C.c_void_p]
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_set_trace_time.argtypes = [C.c_float]
+        L.orc_world_perlin.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_world_destroy.argtypes = [C.c_void_p]
         L.orc_world_info.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_world_export.argtypes = [C.c_void_p] + [C.c_void_p] * 12
@@ -62,6 +63,8 @@ def lib():
         L.orc_obj_load.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_rng_kat.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_probe_math.argtypes = [C.c_float, C.c_void_p]
+        L.orc_probe_ln.argtypes = [C.c_float]
+        L.orc_probe_ln.restype = C.c_float
         L.orc_split_work_tasks.restype = C.c_int
         L.orc_split_work_tasks.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
         L.orc_philox.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
@@ -98,7 +101,8 @@ class FlatScene:
     depth: int
     mats: np.ndarray           # u32 [M,3]  kind, texture, param bits
     texs: np.ndarray           # u32 [T,8]  kind, image, rgb bits, inv_frequency bits, even, odd
-    wrap: np.ndarray = None    # f32 [N,9]  flags (1 Transformation, 2 Animation), offset xyz, y_sine, y_cosine, velocity xyz
+    wrap: np.ndarray = None    # f32 [N,10] flags (1 Transformation, 2 Animation, 4 Volume), offset xyz, y_sine, y_cosine, velocity xyz, -1/density
+    perlins: np.ndarray = None  # u32 [P,1536] 256 gradient vectors (float bits) + perm_x, perm_y, perm_z
     images: list = field(default_factory=list)   # list of u8 [h,w,3]
     cam: np.ndarray = None     # f32 [23]
     bg: np.ndarray = None      # f32 [4]
@@ -111,7 +115,7 @@ class OracleWorld:
         if not handle:
             raise RuntimeError("oracle: " + lib().orc_last_error().decode())
         self.h = handle
-        info = np.zeros(10, dtype=np.uint64)
+        info = np.zeros(11, dtype=np.uint64)
         lib().orc_world_info(self.h, _p(info))
         self.info = info
         self.n_items = int(info[0])
@@ -127,7 +131,7 @@ class OracleWorld:
         return w
 
     @classmethod
-    def from_flat(cls, kinds, item_mat, geom, mats, texs, images, cam, bg, light, wrap=None) -> "OracleWorld":
+    def from_flat(cls, kinds, item_mat, geom, mats, texs, images, cam, bg, light, wrap=None, perlins=None) -> "OracleWorld":
         kinds = np.ascontiguousarray(kinds, dtype=np.uint32)
         item_mat = np.ascontiguousarray(item_mat, dtype=np.uint32)
         geom = np.ascontiguousarray(geom, dtype=np.float32)
@@ -139,11 +143,12 @@ class OracleWorld:
         cam = np.ascontiguousarray(cam, dtype=np.float32)
         bg = np.ascontiguousarray(bg, dtype=np.float32)
         light = np.ascontiguousarray(light, dtype=np.float32)
-        wrap = None if wrap is None else np.ascontiguousarray(wrap, dtype=np.float32).reshape(len(kinds), 9)
+        wrap = None if wrap is None else np.ascontiguousarray(wrap, dtype=np.float32).reshape(len(kinds), 10)
+        perlins = np.zeros((0, 1536), np.uint32) if perlins is None else np.ascontiguousarray(perlins, dtype=np.uint32).reshape(-1, 1536)
         texs = texs.reshape(-1, 8)
         return cls(lib().orc_world_create_flat(len(kinds), _p(kinds), _p(item_mat), _p(geom), len(mats), _p(mats),
                                                len(texs), _p(texs), len(images), _p(wh), ptrs, _p(cam), _p(bg),
-                                               _p(light), _p(wrap)))
+                                               _p(light), _p(wrap), len(perlins), _p(perlins)))
 
     def close(self):
         if self.h:
@@ -163,12 +168,15 @@ class OracleWorld:
             kinds=np.zeros(n, np.uint32), item_mat=np.zeros(n, np.uint32), geom=np.zeros((n, 24), np.float32),
             nodes_box=np.zeros((nn, 6), np.float32), nodes_lra=np.zeros((nn, 3), np.uint32),
             root=int(self.info[2]), depth=int(self.info[3]),
-            mats=np.zeros((nm, 3), np.uint32), texs=np.zeros((nt, 8), np.uint32), wrap=np.zeros((n, 9), np.float32),
+            mats=np.zeros((nm, 3), np.uint32), texs=np.zeros((nt, 8), np.uint32), wrap=np.zeros((n, 10), np.float32),
+            perlins=np.zeros((int(self.info[10]), 1536), np.uint32),
             cam=np.zeros(23, np.float32), bg=np.zeros(4, np.float32), light=np.zeros(7, np.float32),
             default_size=self.default_size)
         wh = np.zeros((max(ni, 1), 2), np.uint32)
         lib().orc_world_export(self.h, _p(fs.kinds), _p(fs.item_mat), _p(fs.geom), _p(fs.nodes_box), _p(fs.nodes_lra),
                                _p(fs.mats), _p(fs.texs), _p(wh), _p(fs.cam), _p(fs.bg), _p(fs.light), _p(fs.wrap))
+        for i in range(len(fs.perlins)):
+            lib().orc_world_perlin(self.h, i, _p(fs.perlins[i]))
         for i in range(ni):
             w, h = int(wh[i, 0]), int(wh[i, 1])
             buf = (C.c_uint8 * (w * h * 3)).from_address(lib().orc_world_image(self.h, i))

@@ -145,6 +145,7 @@ struct GeoEntry {
     Geometry geo;
     const Material* material;
     bool is_poi;
+    float density = 1.0f;  // < 1: VolumeGeometry (world_builder.rs:305-309)
 };
 struct Node {  // :194-199
     std::vector<GeoEntry> geo;
@@ -158,6 +159,7 @@ struct WorldBuilder {
     std::deque<Texture> textures;
     std::deque<Material> materials;
     std::deque<Image> images;
+    std::deque<Perlin> perlins;
 
     const Texture* texture_solid(Color c) {
         Texture t; t.kind = Texture::Solid; t.color = c;
@@ -176,6 +178,13 @@ struct WorldBuilder {
         textures.push_back(t);
         return &textures.back();
     }
+    const Texture* texture_marble(float scale, TRng& rng) {  // world_builder.rs:32-37: Perlin::new(8, rng)
+        perlins.push_back(Perlin::make(8, rng));
+        Texture t; t.kind = Texture::Marble; t.scale = scale; t.noise = &perlins.back();
+        textures.push_back(t);
+        return &textures.back();
+    }
+    const Material* material_isotropic_solid(Color c) { return mk(Material::Isotropic, texture_solid(c), 0.0f); }
     const Material* mk(Material::Kind k, const Texture* tex, float p) {
         Material m; m.kind = k; m.tex = tex; m.param = p;
         materials.push_back(m);
@@ -230,6 +239,11 @@ struct WorldBuilder {
 static inline NodeRef translate(NodeRef n, Dir3 o) { n->transformation = n->transformation.translate(o); return n; }
 static inline NodeRef rotate_up(NodeRef n, float deg) { n->transformation = n->transformation.rotate_around_up_deg(deg); return n; }
 static inline NodeRef set_poi(NodeRef n) { for (auto& g : n->geo) g.is_poi = true; return n; }
+static inline NodeRef set_density(NodeRef n, float density) {  // set_all_geo_densitity :254-263
+    if (!(density >= 0.0f && density < 1.0f)) throw std::runtime_error("Invalid densitity");
+    for (auto& g : n->geo) g.density = density;
+    return n;
+}
 static inline NodeRef animate_moving(NodeRef n, Dir3 v) { n->moving_animation = n->moving_animation + v; return n; }
 
 // NodeRef::finish / finish_internal  (:272-329): bake what can be baked, wrap the remainder as a run-time Transformation,
@@ -248,6 +262,8 @@ static inline void finish_internal(const Node& node, const Transformation& paren
         it.transform = rest;
         it.has_animation = node.moving_animation != Dir3(0, 0, 0);
         it.velocity = node.moving_animation;
+        it.is_volume = ge.density < 1.0f;
+        if (it.is_volume) it.neg_inv_density = -1.0f / ge.density;  // VolumeGeometry::new :301-307
         result.push_back(it);
         if (ge.is_poi && !has_rest && !*has_light && real.kind == Geometry::Rect) { *has_light = true; *light = real.rect; }
     }
@@ -368,6 +384,77 @@ static inline std::unique_ptr<BuiltWorld> build_world(const std::string& name, c
         scene->children.push_back(translate(rotate_up(WorldBuilder::new_obj_box(165.0f, 330.0f, 165.0f, white), 15.0f), Dir3(265.0f, 0.0f, 295.0f)));
         scene->children.push_back(translate(rotate_up(WorldBuilder::new_obj_box(165.0f, 165.0f, 165.0f, white), -18.0f), Dir3(130.0f, 0.0f, 65.0f)));
         finish(*bw, scene, bg_solid(Color(0, 0, 0)), cam);
+        bw->default_width = 600; bw->default_height = 600;
+    } else if (name == "demo:cornell_box_smoke") {  // demo_worlds.rs:179-214
+        float hsize = 278.0f;
+        Camera cam = cam_lookat(40.0f, 1.0f, Point3(hsize, hsize, -800.0f), Point3(hsize, hsize, 0.0f));
+        const Material* smoke_black = wb.material_isotropic_solid(Color(0.0f, 0.0f, 0.0f));
+        const Material* smoke_white = wb.material_isotropic_solid(Color(1.0f, 1.0f, 1.0f));
+        scene->children.push_back(cornell_box_node(wb, 130.0f));
+        scene->children.push_back(set_density(translate(rotate_up(WorldBuilder::new_obj_box(165.0f, 330.0f, 165.0f, smoke_white), 15.0f), Dir3(265.0f, 0.0f, 295.0f)), 0.01f));
+        scene->children.push_back(set_density(translate(rotate_up(WorldBuilder::new_obj_box(165.0f, 165.0f, 165.0f, smoke_black), -18.0f), Dir3(130.0f, 0.0f, 65.0f)), 0.01f));
+        finish(*bw, scene, bg_solid(Color(0, 0, 0)), cam);
+        bw->default_width = 600; bw->default_height = 600;
+    } else if (name == "demo:perlin_spheres") {  // demo_worlds.rs:154-177
+        Camera cam = cam_lookat(40.0f, 3.0f / 4.0f, Point3(13.0f, 2.0f, 3.0f), Point3(0, 0, 0));
+        const Material* mat_noise = wb.material_lambert(wb.texture_marble(4.0f, rng));
+        scene->children.push_back(translate(WorldBuilder::new_obj_sphere(1000.0f, mat_noise), Dir3(0.0f, 0.0f - 1000.0f, 0.0f)));
+        scene->children.push_back(translate(WorldBuilder::new_obj_sphere(2.0f, mat_noise), Dir3(0.0f, 2.0f, 0.0f)));
+        finish(*bw, scene, bg_sky(), cam);
+        bw->default_width = 400; bw->default_height = 300;
+    } else if (name == "demo:final_scene2") {  // demo_worlds.rs:30-152
+        CameraBuilder cb;
+        cb.vertical_fov(40.0f, 1.0f).set_position(Point3(478.0f, 278.0f, -600.0f)).look_at(DIR_UP, Point3(278.0f, 278.0f, 0.0f)).motion_blur(0.0f, 1.0f);
+        const Material* mat_ground = wb.material_lambert_solid(Color(0.48f, 0.83f, 0.53f));
+        NodeRef ground = WorldBuilder::new_group();
+        {
+            const int boxes_per_side = 20;
+            Point3 rmin(-1000.0f, 0.0f, -1000.0f), rmax(1000.0f, 101.0f, 1000.0f);
+            float width = (rmax.e[0] - rmin.e[0]) / (float)boxes_per_side;
+            float height = rmax.e[1] - rmin.e[1];
+            float depth = (rmax.e[2] - rmin.e[2]) / (float)boxes_per_side;
+            for (int i = 0; i < boxes_per_side; ++i)
+                for (int j = 0; j < boxes_per_side; ++j) {
+                    Dir3 mn = rmin + Dir3((float)i * width, 0.0f, (float)j * depth) - Point3(0, 0, 0);
+                    ground->children.push_back(translate(WorldBuilder::new_obj_box(width, height * rng.gen_f32(), depth, mat_ground), mn));
+                }
+        }
+        const Material* mat_light = wb.material_diffuse_light_solid(Color(7.0f, 7.0f, 7.0f));
+        NodeRef light = WorldBuilder::new_obj_rect(RECT_XZ, Point3(273.0f, 554.0f, 279.0f), 300.0f, 300.0f, mat_light);
+        const Material* mat_glass = wb.material_dielectric(1.5f);
+        const Material* mat_metal = wb.material_metal_solid(Color(0.8f, 0.8f, 0.9f), 1.0f);
+        const Texture* tex_marble = wb.texture_marble(0.1f, rng);
+        const Material* mat_marble = wb.material_lambert(tex_marble);
+        const Material* mat_earth = wb.material_lambert(wb.texture_image(assets.earth_w, assets.earth_h, assets.earth_rgb));
+        const Material* mat_fog = wb.material_isotropic_solid(Color(0.2f, 0.4f, 0.9f));
+        const Material* mat_moving = wb.material_lambert_solid(Color(0.7f, 0.3f, 0.1f));
+        NodeRef floating = WorldBuilder::new_group();
+        floating->children.push_back(translate(WorldBuilder::new_obj_sphere(70.0f, mat_glass), Dir3(360.0f, 150.0f, 145.0f)));
+        floating->children.push_back(set_density(translate(WorldBuilder::new_obj_sphere(70.0f, mat_fog), Dir3(360.0f, 150.0f, 145.0f)), 0.2f));
+        floating->children.push_back(translate(WorldBuilder::new_obj_sphere(50.0f, mat_glass), Dir3(260.0f, 150.0f, 45.0f)));
+        floating->children.push_back(translate(WorldBuilder::new_obj_sphere(50.0f, mat_metal), Dir3(0.0f, 150.0f, 145.0f)));
+        floating->children.push_back(translate(WorldBuilder::new_obj_sphere(80.0f, mat_marble), Dir3(220.0f, 280.0f, 300.0f)));
+        floating->children.push_back(translate(WorldBuilder::new_obj_sphere(100.0f, mat_earth), Dir3(400.0f, 200.0f, 400.0f)));
+        floating->children.push_back(animate_moving(translate(WorldBuilder::new_obj_sphere(50.0f, mat_moving), Dir3(400.0f, 400.0f, 200.0f)), Dir3(30.0f, 0.0f, 0.0f)));
+        NodeRef sphere_cube = WorldBuilder::new_group();
+        {
+            const Material* material = wb.material_lambert_solid(Color(0.75f, 0.75f, 0.75f));
+            Transformation rot = Transformation().rotate_around_up_deg(15.0f);
+            Dir3 dir_1 = rot.apply_direction(Dir3(1, 0, 0)), dir_2 = rot.apply_direction(Dir3(0, 1, 0)), dir_3 = rot.apply_direction(Dir3(0, 0, -1));
+            Dir3 origin(-100.0f, 270.0f, 395.0f);
+            for (int i = 0; i < 1000; ++i) {
+                float r0 = rng.gen_f32(), r1 = rng.gen_f32(), r2 = rng.gen_f32();
+                Dir3 p = origin + 165.0f * (dir_1 * r0 + dir_2 * r1 + dir_3 * r2);
+                sphere_cube->children.push_back(translate(WorldBuilder::new_obj_sphere(10.0f, material), p));
+            }
+        }
+        NodeRef obj_fog = set_density(WorldBuilder::new_obj_sphere(5000.0f, wb.material_isotropic_solid(Color(1.0f, 1.0f, 1.0f))), 0.0001f);
+        scene->children.push_back(obj_fog);
+        scene->children.push_back(ground);
+        scene->children.push_back(sphere_cube);
+        scene->children.push_back(floating);
+        scene->children.push_back(light);
+        finish(*bw, scene, bg_solid(Color(0, 0, 0)), cb.build());
         bw->default_width = 600; bw->default_height = 600;
     } else if (name == "demo:moving_spheres") {  // demo_worlds.rs:351-393
         CameraBuilder cb;

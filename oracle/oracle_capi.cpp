@@ -45,13 +45,15 @@ void* orc_world_create(const char* name, const char* suzanne_obj, const char* cu
 // Build a world from flat arrays (random / adversarial test scenes authored in Python).
 // geom: 24 floats per item — sphere: cx cy cz r | rect: plane dist r0lo r0hi r1lo r1hi | tri: 9 pos, 9 nrm, 6 uv.
 // mats: (kind, texture, param-as-float-bits) u32 triples.  texs: (kind, image, r, g, b, inv_frequency as float bits, even, odd) u32 x8.
-// wrap (optional, may be NULL): 9 floats per item — flags (bit0 Transformation, bit1 Animation), offset xyz, y_sine, y_cosine, velocity xyz.
+// wrap (optional, may be NULL): 10 floats per item — flags (bit0 Transformation, bit1 Animation, bit2 Volume), offset xyz, y_sine, y_cosine, velocity xyz, neg_inv_density.
+// perlins: n_perlins tables of 256 gradient vectors (xyz) + 3 x 256 permutation entries, all as floats / u32 in one block of 256*3 + 768 words each.
 // cam: position3 ulc3 unit_right3 unit_up3 scaled_right3 scaled_up3 lens_radius t0 t1 pace2 (23 floats).
 // bg: sky-flag r g b.  light: has plane dist r0lo r0hi r1lo r1hi (7 floats, has==0 -> none).
 void* orc_world_create_flat(uint32_t n_items, const uint32_t* kinds, const uint32_t* item_mat, const float* geom,
                             uint32_t n_mats, const uint32_t* mats, uint32_t n_texs, const uint32_t* texs,
                             uint32_t n_images, const uint32_t* image_wh, const uint8_t* const* image_rgb,
-                            const float* cam, const float* bg, const float* light, const float* wrap) {
+                            const float* cam, const float* bg, const float* light, const float* wrap, uint32_t n_perlins,
+                            const uint32_t* perlin_words) {
     try {
         if (n_items == 0) throw std::runtime_error("empty scene (reference recurses forever)");
         Handle* h = new Handle();
@@ -63,10 +65,19 @@ void* orc_world_create_flat(uint32_t n_items, const uint32_t* kinds, const uint3
             im.rgb.assign(image_rgb[i], image_rgb[i] + (size_t)im.width * im.height * 3);
             wb.images.push_back(std::move(im));
         }
+        for (uint32_t i = 0; i < n_perlins; ++i) {
+            const uint32_t* pw = perlin_words + (size_t)i * 1536;
+            Perlin pn;
+            pn.bits = 8;
+            for (int k = 0; k < 256; ++k) pn.ranvec.push_back(Dir3(bits_to_f32(pw[3 * k]), bits_to_f32(pw[3 * k + 1]), bits_to_f32(pw[3 * k + 2])));
+            pn.perm_x.assign(pw + 768, pw + 1024); pn.perm_y.assign(pw + 1024, pw + 1280); pn.perm_z.assign(pw + 1280, pw + 1536);
+            wb.perlins.push_back(pn);
+        }
         std::vector<const Texture*> tptr;
         for (uint32_t i = 0; i < n_texs; ++i) {
             Texture t;
             t.kind = (Texture::Kind)texs[8 * i];
+            if (t.kind == Texture::Marble) { t.noise = &wb.perlins.at(texs[8 * i + 1]); t.scale = bits_to_f32(texs[8 * i + 5]); }
             t.color = Color(bits_to_f32(texs[8 * i + 2]), bits_to_f32(texs[8 * i + 3]), bits_to_f32(texs[8 * i + 4]));
             if (t.kind == Texture::Image_) t.image = &wb.images[texs[8 * i + 1]];
             t.inv_frequency = bits_to_f32(texs[8 * i + 5]);
@@ -110,12 +121,14 @@ void* orc_world_create_flat(uint32_t n_items, const uint32_t* kinds, const uint3
             it.geo = geo;
             it.material = mptr.at(item_mat[i]);
             if (wrap) {
-                const float* wv = wrap + 9 * (size_t)i;
+                const float* wv = wrap + 10 * (size_t)i;
                 uint32_t fl = (uint32_t)wv[0];
                 it.has_transform = (fl & 1u) != 0;
                 it.transform.offset = Dir3(wv[1], wv[2], wv[3]); it.transform.y_sine = wv[4]; it.transform.y_cosine = wv[5];
                 it.has_animation = (fl & 2u) != 0;
                 it.velocity = Dir3(wv[6], wv[7], wv[8]);
+                it.is_volume = (fl & 4u) != 0;
+                it.neg_inv_density = wv[9];
             }
             w.scene.items.push_back(it);
         }
@@ -159,6 +172,13 @@ void orc_world_info(void* hp, uint64_t* info) {
     info[7] = h->bw->wb->textures.size();
     info[8] = h->bw->wb->images.size();
     info[9] = w.has_light ? 1 : 0;
+    info[10] = h->bw->wb->perlins.size();
+}
+// 1536 words per table: 256 x (x, y, z) float bits, then perm_x, perm_y, perm_z (256 u32 each)
+void orc_world_perlin(void* hp, uint32_t index, uint32_t* words) {
+    const Perlin& p = ((Handle*)hp)->bw->wb->perlins.at(index);
+    for (int k = 0; k < 256; ++k) for (int c = 0; c < 3; ++c) words[3 * k + c] = f32_to_bits(p.ranvec[k].e[c]);
+    for (int k = 0; k < 256; ++k) { words[768 + k] = p.perm_x[k]; words[1024 + k] = p.perm_y[k]; words[1280 + k] = p.perm_z[k]; }
 }
 
 // Flat export; array layouts as in orc_world_create_flat.  nodes_box: 6 floats (min, max); nodes_lra: left, right, axis.
@@ -189,10 +209,11 @@ void orc_world_export(void* hp, uint32_t* kinds, uint32_t* item_mat, float* geom
         if (it.material != last_m) { last_m = it.material; last_i = mat_index(it.material); }
         item_mat[i] = last_i;
         if (wrap) {
-            float* wv = wrap + 9 * i;
-            wv[0] = (float)((it.has_transform ? 1 : 0) | (it.has_animation ? 2 : 0));
+            float* wv = wrap + 10 * i;
+            wv[0] = (float)((it.has_transform ? 1 : 0) | (it.has_animation ? 2 : 0) | (it.is_volume ? 4 : 0));
             for (int k = 0; k < 3; ++k) { wv[1 + k] = it.transform.offset.e[k]; wv[6 + k] = it.velocity.e[k]; }
             wv[4] = it.transform.y_sine; wv[5] = it.transform.y_cosine;
+            wv[9] = it.neg_inv_density;
         }
         if (it.geo.kind == Geometry::Sphere) {
             g[0] = it.geo.sphere.center.e[0]; g[1] = it.geo.sphere.center.e[1]; g[2] = it.geo.sphere.center.e[2];
@@ -225,7 +246,9 @@ void orc_world_export(void* hp, uint32_t* kinds, uint32_t* item_mat, float* geom
         texs[8 * i] = (uint32_t)wb.textures[i].kind;
         texs[8 * i + 1] = wb.textures[i].image ? img_index(wb.textures[i].image) : 0xFFFFFFFFu;
         for (int k = 0; k < 3; ++k) texs[8 * i + 2 + k] = f32_to_bits(wb.textures[i].color.e[k]);
-        texs[8 * i + 5] = f32_to_bits(wb.textures[i].inv_frequency);
+        texs[8 * i + 5] = f32_to_bits(wb.textures[i].kind == Texture::Marble ? wb.textures[i].scale : wb.textures[i].inv_frequency);
+        if (wb.textures[i].kind == Texture::Marble)
+            for (size_t k = 0; k < wb.perlins.size(); ++k) if (&wb.perlins[k] == wb.textures[i].noise) texs[8 * i + 1] = (uint32_t)k;
         texs[8 * i + 6] = wb.textures[i].even ? tex_index(wb.textures[i].even) : 0xFFFFFFFFu;
         texs[8 * i + 7] = wb.textures[i].odd ? tex_index(wb.textures[i].odd) : 0xFFFFFFFFu;
     }
@@ -253,7 +276,11 @@ void orc_trace(void* hp, uint64_t n, const float* org, const float* dir, float t
         Ray r{Point3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), Dir3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), g_trace_time};
         Range tr{t_min, t_max};
         HitInteraction hi;
-        if (w.scene.hit(r, tr, &hi, &cnt)) {
+        // Scene::hit takes an rng (volumes draw inside the traversal): rt_trace keys it by the ray index (REPLAY, seed 0)
+        TRng rng = TRng::make_replay(0);
+        rng.set_path((uint32_t)i, (uint32_t)(i >> 32));
+        rng.begin_block(0);
+        if (w.scene.hit(r, tr, rng, &hi, &cnt)) {
             hit_id[i] = hi.item; t[i] = hi.t;
             for (int k = 0; k < 3; ++k) normal[3 * i + k] = hi.normal.e[k];
             front_face[i] = hi.front_face ? 1 : 0;
@@ -326,9 +353,10 @@ static double render_impl(void* hp, int width, int height, uint64_t spp, int max
                         if (render_mode == 0) {
                             c = ray_color(ray, world, rng, max_depth, &cnt);
                         } else {  // RenderMode::Normals :108-116
+                            rng.begin_block(1);  // REPLAY bookkeeping: the first segment draws from block 1, as in ray_color
                             HitInteraction hi;
                             Range tr{0.001f, INF_F};
-                            if (world.scene.hit(ray, tr, &hi, &cnt)) c = (hi.normal + V3(1.0f, 1.0f, 1.0f)) * 0.5f;
+                            if (world.scene.hit(ray, tr, rng, &hi, &cnt)) c = (hi.normal + V3(1.0f, 1.0f, 1.0f)) * 0.5f;
                             else c = world.background.sample(ray);
                         }
                         sum = sum + c;
@@ -407,6 +435,7 @@ void orc_probe_math(float u, float* out3) {  // sincos_2pi / cbrt_unit of the RE
     sincos_2pi(u, &out3[0], &out3[1]);
     out3[2] = cbrt_unit(u);
 }
+float orc_probe_ln(float u) { return ln_unit(u); }  // free-flight ln of the REPLAY volume sampler
 int orc_split_work_tasks(uint64_t spp, uint64_t threads, uint64_t* out_counts, uint64_t cap) {
     auto t = split_work_tasks(spp, threads);
     for (size_t i = 0; i < t.size() && i < cap; ++i) out_counts[i] = t[i].second;

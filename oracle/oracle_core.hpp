@@ -410,6 +410,54 @@ struct Transformation {
     }
 };
 
+// ---------------------------------------------------------------- src/lib/perlin.rs
+struct Perlin {
+    std::vector<Dir3> ranvec;
+    std::vector<uint32_t> perm_x, perm_y, perm_z;
+    size_t bits = 0;
+    static Perlin make(size_t bits, TRng& rng) {  // :19-36  (scene-construction RNG: FAITHFUL stream)
+        Perlin p;
+        p.bits = bits;
+        const size_t n = (size_t)1 << bits;
+        for (size_t i = 0; i < n; ++i) { float s[3]; rng.unit_sphere(s); p.ranvec.push_back(Dir3(s[0], s[1], s[2])); }
+        auto gen = [&](std::vector<uint32_t>& v) {  // generate_per :93-97
+            v.resize(n);
+            for (size_t i = 0; i < n; ++i) v[i] = (uint32_t)i;
+            rng.shuffle(v.data(), n);
+        };
+        gen(p.perm_x); gen(p.perm_y); gen(p.perm_z);
+        return p;
+    }
+    float noise(Point3 p) const {  // :48-91
+        const int mask = (int)(((size_t)1 << bits) - 1);
+        float fx = std::floor(p.e[0]), fy = std::floor(p.e[1]), fz = std::floor(p.e[2]);
+        float u = p.e[0] - fx, v = p.e[1] - fy, w = p.e[2] - fz;
+        int i = (int)fx, j = (int)fy, k = (int)fz;
+        float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+        float accum = 0.0f;
+        for (int di = 0; di < 2; ++di)
+            for (int dj = 0; dj < 2; ++dj)
+                for (int dk = 0; dk < 2; ++dk) {
+                    uint32_t r = perm_x[(size_t)((i + di) & mask)] ^ perm_y[(size_t)((j + dj) & mask)] ^ perm_z[(size_t)((k + dk) & mask)];
+                    Dir3 c = ranvec[r];
+                    float fi = (float)di, fj = (float)dj, fk = (float)dk;
+                    Dir3 weight(u - (float)di, v - (float)dj, w - (float)dk);
+                    accum += (fi * uu + (1.0f - fi) * (1.0f - uu)) * (fj * vv + (1.0f - fj) * (1.0f - vv)) *
+                             (fk * ww + (1.0f - fk) * (1.0f - ww)) * dot(c, weight);
+                }
+        return accum;
+    }
+    float turbulence(Point3 p, int depth, float fall_off) const {  // :37-47
+        float accum = 0.0f, weight = 1.0f;
+        for (int d = 0; d < depth; ++d) {
+            accum += weight * noise(p);
+            weight *= fall_off;
+            p = p * 2.0f;
+        }
+        return std::fabs(accum);
+    }
+};
+
 // ---------------------------------------------------------------- src/lib/texture.rs + material.rs
 struct Image {
     uint32_t width = 0, height = 0;
@@ -417,7 +465,9 @@ struct Image {
 };
 struct HitInteraction;
 struct Texture {
-    enum Kind { Solid = 0, Image_ = 1, Checker = 2 } kind = Solid;
+    enum Kind { Solid = 0, Image_ = 1, Checker = 2, Marble = 3 } kind = Solid;
+    float scale = 0.0f;                      // Marble (texture.rs:13-16)
+    const Perlin* noise = nullptr;
     Color color;
     const Image* image = nullptr;
     float inv_frequency = 0.0f;              // Checker (texture.rs:8-12)
@@ -425,7 +475,7 @@ struct Texture {
     Color sample(const HitInteraction& hi) const;
 };
 struct Material {
-    enum Kind { Lambert = 0, Metal = 1, Dielectric = 2, DiffuseLight = 3 } kind = Lambert;
+    enum Kind { Lambert = 0, Metal = 1, Dielectric = 2, DiffuseLight = 3, Isotropic = 4 } kind = Lambert;
     const Texture* tex = nullptr;  // albedo / emit
     float param = 0.0f;            // fuzz / index_of_refraction
 };
@@ -446,6 +496,10 @@ static inline uint32_t sat_u32(float v) {  // Rust `as u32`
 }
 inline Color Texture::sample(const HitInteraction& hi) const {  // texture.rs:23-43
     if (kind == Solid) return color;
+    if (kind == Marble) {  // :44-51
+        float v = 0.5f * (1.0f + std::sin(hi.position.e[2] * scale + 10.0f * noise->turbulence(hi.position, 7, 0.5f)));
+        return Color(v, v, v);  // Color(1,1,1) * 0.5 * (1 + sin(..)): 1*0.5 is exact
+    }
     if (kind == Checker) {  // :26-35
         Dir3 sp = (hi.position - Point3(0, 0, 0)) * inv_frequency;
         float sines = std::sin(sp.e[0]) * std::sin(sp.e[1]) * std::sin(sp.e[2]);
@@ -512,6 +566,13 @@ static inline bool material_scatter(const Material& m, const Ray& ray, const Hit
                 direction = refract(ray.direction, hi.normal, refraction_ratio);
             *dist = ScatterDist{true, unit(direction)};
             *att = Color(1, 1, 1);
+            return true;
+        }
+        case Material::Isotropic: {  // :106-111
+            float sp[3];
+            rng.unit_sphere(sp);
+            *dist = ScatterDist{true, Dir3(sp[0], sp[1], sp[2])};
+            *att = m.tex->sample(hi);
             return true;
         }
         default:
@@ -598,6 +659,29 @@ struct SceneItem {
     Transformation transform;
     bool has_animation = false;
     Dir3 velocity;
+    bool is_volume = false;        // SceneElement::VolumeGeometry (:116, 294-342): `material` is the phase function
+    float neg_inv_density = 0.0f;  // -1 / density
+
+    // VolumeGeometry::hit :315-342.  Returns t via out->t; normal UP, uv ZERO, front_face false (all "arbitrary" in the reference).
+    bool volume_hit(const Ray& ray, const Range& t_range, TRng& rng, uint32_t item, GeoHit* out) const {
+        GeoHit b0, b1;
+        if (!geo.hit(ray, Range{-INF_F, INF_F}, &b0)) return false;
+        float start_boundary = b0.t;
+        float next = start_boundary + 0.001f;
+        if (!geo.hit(ray, Range{next, INF_F}, &b1)) return false;
+        float end_boundary = b1.t;
+        float start_medium = std::fmax(start_boundary, t_range.start);
+        float end_medium = std::fmin(end_boundary, t_range.end);
+        if (start_medium >= end_medium) return false;
+        float t = std::fmax(start_medium, 0.0f) + neg_inv_density * rng.volume_ln_u(item);
+        if (t > end_medium) return false;
+        out->position = ray.at(t);
+        out->normal = Dir3(0.0f, 1.0f, 0.0f);
+        out->uv = Vec2f(0, 0);
+        out->t = t;
+        out->front_face = false;
+        return true;
+    }
 
     Aabb bounding_box() const {  // SceneElement::bounding_box :249-267 (Q2: wrappers do not move / extend the box)
         Aabb b = geo.bounding_box();
@@ -608,7 +692,7 @@ struct SceneItem {
         }
         return b;
     }
-    bool hit(const Ray& ray_in, const Range& tr, GeoHit* out) const {  // SceneElement::hit :230-244
+    bool hit(const Ray& ray_in, const Range& tr, TRng& rng, uint32_t item, GeoHit* out) const {  // SceneElement::hit :230-244
         Ray ray = ray_in;
         Transformation anim;
         if (has_animation) {
@@ -620,7 +704,7 @@ struct SceneItem {
             ray.origin = transform.reverse_point(ray.origin);
             ray.direction = transform.reverse_normal(ray.direction);
         }
-        if (!geo.hit(ray, tr, out)) return false;
+        if (is_volume ? !volume_hit(ray, tr, rng, item, out) : !geo.hit(ray, tr, out)) return false;
         if (has_transform) { out->position = transform.apply_point(out->position); out->normal = transform.apply_normal(out->normal); }
         if (has_animation) { out->position = anim.apply_point(out->position); out->normal = anim.apply_normal(out->normal); }
         return true;
@@ -682,12 +766,12 @@ struct Bvh {  // :352-482
         return id;
     }
 
-    bool hit_recursive(size_t node, const Ray& ray, Range& t_range, HitInteraction* out, Counters* cnt) const {  // :429-451
+    bool hit_recursive(size_t node, const Ray& ray, Range& t_range, TRng& rng, HitInteraction* out, Counters* cnt) const {  // :429-451
         if (node > items.size()) {
             size_t item = USIZE_MAX - node;
             if (cnt) cnt->prim_tests++;
             GeoHit g;
-            if (items[item].hit(ray, t_range, &g)) {  // leaf: NO AABB test (Q13)
+            if (items[item].hit(ray, t_range, rng, (uint32_t)item, &g)) {  // leaf: NO AABB test (Q13)
                 out->position = g.position; out->normal = g.normal; out->uv = g.uv; out->t = g.t;
                 out->front_face = g.front_face; out->material = items[item].material; out->item = (uint32_t)item;
                 return true;
@@ -702,7 +786,7 @@ struct Bvh {  // :352-482
             bool any = false;  // hit_index_list :453-462
             for (int k = 0; k < 2; ++k) {
                 HitInteraction hi;
-                if (hit_recursive(order[k], ray, t_range, &hi, cnt)) {
+                if (hit_recursive(order[k], ray, t_range, rng, &hi, cnt)) {
                     t_range.end = hi.t;
                     *out = hi;
                     any = true;
@@ -712,10 +796,10 @@ struct Bvh {  // :352-482
         }
         return false;
     }
-    bool hit(const Ray& ray, const Range& t_range_in, HitInteraction* out, Counters* cnt) const {  // :464-473
+    bool hit(const Ray& ray, const Range& t_range_in, TRng& rng, HitInteraction* out, Counters* cnt) const {  // :464-473
         Range t_range = t_range_in;
         if (cnt) cnt->rays++;
-        return hit_recursive(initial_index, ray, t_range, out, cnt);
+        return hit_recursive(initial_index, ray, t_range, rng, out, cnt);
     }
 };
 
@@ -813,7 +897,7 @@ static inline Color ray_color(const Ray& ray, const World& world, TRng& rng, int
         ++bounce;
         HitInteraction hi;
         Range tr{0.001f, INF_F};
-        if (world.scene.hit(cur_ray, tr, &hi, cnt)) {
+        if (world.scene.hit(cur_ray, tr, rng, &hi, cnt)) {
             if (depth <= 1) return Color(0, 0, 0);  // Q7
             Color att;
             ScatterDist dist;

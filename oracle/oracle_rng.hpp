@@ -17,6 +17,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <limits>
+#include <utility>
 
 namespace orc {
 
@@ -76,6 +78,19 @@ static inline float cbrt_unit(float u) {
     float y = bits_to_f32(f32_to_bits(u) / 3u + 709921077u);
     for (int i = 0; i < 4; ++i) y = (2.0f * y + u / (y * y)) * 0.333333343267f;
     return y;
+}
+
+// Deterministic natural log on [0,1): exponent split + atanh series, IEEE ops only (same bits on CPU and GPU).
+static inline float ln_unit(float u) {
+    if (!(u > 0.0f)) return -std::numeric_limits<float>::infinity();
+    uint32_t b = f32_to_bits(u);
+    int e = (int)(b >> 23) - 127;
+    float m = bits_to_f32((b & 0x007FFFFFu) | 0x3F800000u);   // [1, 2)
+    if (m > 1.41421356f) { m = m * 0.5f; e += 1; }           // [0.707, 1.414)
+    float s = (m - 1.0f) / (m + 1.0f);                        // ln m = 2 atanh(s), |s| < 0.172
+    float s2 = s * s;
+    float p = 2.0f * s * (1.0f + s2 * (0.333333343f + s2 * (0.2f + s2 * (0.142857149f + s2 * 0.111111112f))));
+    return (float)e * 0.693147182f + p;
 }
 
 // rand 0.8.5 `UniformFloat<f32>::new(low, high)` (used for the pixel jitter via src/lib/vec2.rs:43-83
@@ -179,6 +194,32 @@ struct TRng {
             if (res < hi) return res;
             scale = bits_to_f32(f32_to_bits(scale) - 1);
         }
+    }
+    // rand 0.8.5 UniformInt<u32>::sample_single(0, n) (widening-multiply rejection with the leading-zeros zone); used by
+    // SliceRandom::shuffle -> gen_index (src/lib/perlin.rs:95).  Scene construction only (FAITHFUL stream).
+    uint32_t gen_index(uint32_t ubound) {
+        const uint32_t range = ubound;  // high - low with low = 0, exclusive upper bound
+        if (range == 0) return next_u32();
+        const uint32_t zone = (range << __builtin_clz(range)) - 1u;
+        for (;;) {
+            const uint64_t m = (uint64_t)next_u32() * range;
+            if ((uint32_t)m <= zone) return (uint32_t)(m >> 32);
+        }
+    }
+    template <class T>
+    void shuffle(T* v, size_t n) {  // rand::seq::SliceRandom::shuffle
+        for (size_t i = n - 1; i >= 1; --i) std::swap(v[i], v[gen_index((uint32_t)(i + 1))]);
+    }
+    // -ln(U) * (1/density) free-path draw of VolumeGeometry::hit (src/lib/hittable.rs:328): `rng.gen::<f32>().ln()`.
+    // REPLAY: the draw is keyed by the element index (a ray tests a leaf at most once), so it does not depend on visit order;
+    // ln is evaluated with ln_unit (IEEE ops only) so CPU and GPU agree bit for bit.  FAITHFUL: next sequential draw, libm logf.
+    float volume_ln_u(uint32_t item) {
+        if (replay) {
+            uint32_t o[4];
+            philox4x32_10(key0, key1, pixel, sample, block_id, 0x40000000u | item, o);
+            return ln_unit((float)(o[0] >> 8) * 5.9604644775390625e-8f);
+        }
+        return std::log(gen_f32());
     }
     // rand_distr 0.4.3 UnitSphere (Marsaglia 1972)  — src/lib/material.rs:21
     void unit_sphere(float out[3]) {

@@ -18,7 +18,7 @@ RT_MISS = 0xFFFFFFFF
 
 class RtItem(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("material", C.c_uint32), ("geom", C.c_float * 24), ("wrap_flags", C.c_uint32),
-                ("transform", C.c_float * 5), ("velocity", C.c_float * 3)]
+                ("transform", C.c_float * 5), ("velocity", C.c_float * 3), ("neg_inv_density", C.c_float)]
 
 
 class RtBvhNode(C.Structure):
@@ -39,6 +39,10 @@ class RtImage(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("rgb8", C.c_void_p)]
 
 
+class RtPerlin(C.Structure):
+    _fields_ = [("ranvec", C.c_void_p), ("perm_x", C.c_void_p), ("perm_y", C.c_void_p), ("perm_z", C.c_void_p)]
+
+
 class RtCamera(C.Structure):
     _fields_ = [("position", C.c_float * 3), ("upper_left_corner", C.c_float * 3), ("unit_right", C.c_float * 3),
                 ("unit_up", C.c_float * 3), ("scaled_right", C.c_float * 3), ("scaled_up", C.c_float * 3),
@@ -50,7 +54,7 @@ class RtSceneDesc(C.Structure):
     _fields_ = [("n_items", C.c_uint32), ("items", C.c_void_p), ("n_nodes", C.c_uint32), ("nodes", C.c_void_p),
                 ("root", C.c_uint32), ("n_materials", C.c_uint32), ("materials", C.c_void_p),
                 ("n_textures", C.c_uint32), ("textures", C.c_void_p), ("n_images", C.c_uint32), ("images", C.c_void_p),
-                ("camera", RtCamera), ("background_is_sky", C.c_uint32), ("background_rgb", C.c_float * 3),
+                ("n_perlins", C.c_uint32), ("perlins", C.c_void_p), ("camera", RtCamera), ("background_is_sky", C.c_uint32), ("background_rgb", C.c_float * 3),
                 ("has_light", C.c_uint32), ("light_plane", C.c_uint32), ("light_dist", C.c_float),
                 ("light_r0", C.c_float * 2), ("light_r1", C.c_float * 2)]
 
@@ -71,7 +75,7 @@ class RtStats(C.Structure):
 
 
 ITEM_DTYPE = np.dtype([("kind", "<u4"), ("material", "<u4"), ("geom", "<f4", (24,)), ("wrap_flags", "<u4"),
-                       ("transform", "<f4", (5,)), ("velocity", "<f4", (3,))])
+                       ("transform", "<f4", (5,)), ("velocity", "<f4", (3,)), ("neg_inv_density", "<f4")])
 NODE_DTYPE = np.dtype([("aabb_min", "<f4", (3,)), ("aabb_max", "<f4", (3,)), ("left", "<u4"), ("right", "<u4"),
                        ("axis_id", "<u4")])
 MATERIAL_DTYPE = np.dtype([("kind", "<u4"), ("texture", "<u4"), ("param", "<f4")])
@@ -156,14 +160,28 @@ def items_from_flat(kinds, item_mat, geom, wrap=None):
     items["material"] = item_mat
     items["geom"] = np.asarray(geom, np.float32).reshape(n, 24)
     if wrap is not None:
-        w = np.asarray(wrap, np.float32).reshape(n, 9)
+        w = np.asarray(wrap, np.float32).reshape(n, 10)
         items["wrap_flags"] = w[:, 0].astype(np.uint32)
         items["transform"] = w[:, 1:6]
         items["velocity"] = w[:, 6:9]
+        items["neg_inv_density"] = w[:, 9]
     return items
 
 
-def make_desc(kinds, item_mat, geom, nodes_box, nodes_lra, root, mats, texs, images, cam, bg, light, wrap=None):
+def perlins_to_c(perlins):
+    """[P, 1536] u32 rows (768 gradient float bits, perm_x | perm_y | perm_z) -> (RtPerlin array, keepalive)."""
+    perlins = np.ascontiguousarray(np.asarray(perlins if perlins is not None else [], np.uint32).reshape(-1, 1536))
+    arr = (RtPerlin * max(1, len(perlins)))()
+    for i in range(len(perlins)):
+        base = perlins.ctypes.data + i * 1536 * 4
+        arr[i].ranvec = base
+        arr[i].perm_x = base + 768 * 4
+        arr[i].perm_y = base + 1024 * 4
+        arr[i].perm_z = base + 1280 * 4
+    return arr, perlins
+
+
+def make_desc(kinds, item_mat, geom, nodes_box, nodes_lra, root, mats, texs, images, cam, bg, light, wrap=None, perlins=None):
     """Assemble an RtSceneDesc from flat numpy arrays.  Returns (desc, keepalive)."""
     n = len(kinds)
     items = items_from_flat(kinds, item_mat, geom, wrap)
@@ -201,6 +219,9 @@ def make_desc(kinds, item_mat, geom, nodes_box, nodes_lra, root, mats, texs, ima
     d.textures = t.ctypes.data if len(t) else None
     d.n_images = len(images)
     d.images = C.cast(imgs, C.c_void_p)
+    parr, pkeep = perlins_to_c(perlins)
+    d.n_perlins = len(pkeep)
+    d.perlins = C.cast(parr, C.c_void_p)
     cam = np.asarray(cam, np.float32)
     for i, name in enumerate(["position", "upper_left_corner", "unit_right", "unit_up", "scaled_right", "scaled_up"]):
         setattr(d.camera, name, (C.c_float * 3)(*cam[3 * i:3 * i + 3]))
@@ -217,7 +238,7 @@ def make_desc(kinds, item_mat, geom, nodes_box, nodes_lra, root, mats, texs, ima
     d.light_dist = float(light[2])
     d.light_r0 = (C.c_float * 2)(float(light[3]), float(light[4]))
     d.light_r1 = (C.c_float * 2)(float(light[5]), float(light[6]))
-    return d, (items, nodes, m, t, images, imgs)
+    return d, (items, nodes, m, t, images, imgs, parr, pkeep)
 
 
 class DeviceScene:
@@ -244,7 +265,7 @@ class DeviceScene:
     def from_flat(cls, fs, device: int = 0) -> "DeviceScene":
         """fs: any object with the flat-scene attributes (kinds, item_mat, geom, nodes_box, nodes_lra, root, ...)."""
         desc, keep = make_desc(fs.kinds, fs.item_mat, fs.geom, fs.nodes_box, fs.nodes_lra, fs.root, fs.mats, fs.texs,
-                               fs.images, fs.cam, fs.bg, fs.light, getattr(fs, "wrap", None))
+                               fs.images, fs.cam, fs.bg, fs.light, getattr(fs, "wrap", None), getattr(fs, "perlins", None))
         return cls(desc, device, keep)
 
     def close(self):

@@ -51,7 +51,8 @@ class FlatScene:
     depth: int
     mats: np.ndarray
     texs: np.ndarray
-    wrap: np.ndarray = None
+    wrap: np.ndarray = None      # [n, 10]: RT_WRAP_* flags, offset xyz, y_sine, y_cosine, velocity xyz, -1/density
+    perlins: np.ndarray = None   # [P, 1536] u32: 768 gradient float bits, perm_x | perm_y | perm_z
     images: list = field(default_factory=list)
     cam: np.ndarray = None
     bg: np.ndarray = None
@@ -74,7 +75,8 @@ def host_lib():
         L.rtw_world_create_elements.restype = C.c_void_p
         L.rtw_world_create_elements.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                                 C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                C.c_void_p, C.c_void_p]
+                                                C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.rtw_world_perlin.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.rtw_world_destroy.argtypes = [C.c_void_p]
         L.rtw_world_destroy.restype = None
         L.rtw_world_info.argtypes = [C.c_void_p, C.c_void_p]
@@ -127,7 +129,7 @@ class World:
         if not handle:
             raise RuntimeError("rtiaw host: " + host_lib().rtw_last_error().decode(errors="replace"))
         self.h = C.c_void_p(handle)
-        info = np.zeros(10, np.uint64)
+        info = np.zeros(11, np.uint64)
         _check(host_lib().rtw_world_info(self.h, _p(info)))
         self.info = info
         self.n_items, self.n_nodes = int(info[0]), int(info[1])
@@ -135,14 +137,14 @@ class World:
 
     @classmethod
     def named(cls, name: str) -> "World":
-        need_earth = name in ("demo:earth_mapped", "config:c3")  # JPEG decode is caller-side (image crate in the reference)
+        need_earth = name in ("demo:earth_mapped", "demo:final_scene2", "config:c3")  # JPEG decode is caller-side (image crate in the reference)
         e = earth_rgb8() if need_earth else None
         return cls(host_lib().rtw_world_create(name.encode(), os.path.join(ASSETS, "suzanne.obj").encode(),
                                                os.path.join(ASSETS, "cube.obj").encode(),
                                                e.shape[1] if need_earth else 0, e.shape[0] if need_earth else 0, _p(e)))
 
     @classmethod
-    def from_elements(cls, kinds, item_mat, geom, mats, texs, images, cam, bg, light, wrap=None) -> "World":
+    def from_elements(cls, kinds, item_mat, geom, mats, texs, images, cam, bg, light, wrap=None, perlins=None) -> "World":
         """Scene::new(BoundingVolumeHierarchy::new(elements)) from SurfaceGeometry arrays (flat layouts of b200rt.h)."""
         kinds = np.ascontiguousarray(kinds, np.uint32)
         item_mat = np.ascontiguousarray(item_mat, np.uint32)
@@ -158,10 +160,11 @@ class World:
         cam = np.ascontiguousarray(cam, np.float32)
         bg = np.ascontiguousarray(bg, np.float32)
         light = np.ascontiguousarray(light, np.float32)
-        wrap = None if wrap is None else np.ascontiguousarray(wrap, np.float32).reshape(len(kinds), 9)
+        wrap = None if wrap is None else np.ascontiguousarray(wrap, np.float32).reshape(len(kinds), 10)
+        parr, pkeep = _cabi.perlins_to_c(perlins)
         return cls(host_lib().rtw_world_create_elements(len(kinds), _p(kinds), _p(item_mat), _p(geom), len(m), _p(m), len(t),
                                                         _p(t), len(images), C.cast(imgs, C.c_void_p), _p(cam), _p(bg), _p(light),
-                                                        _p(wrap)))
+                                                        _p(wrap), len(pkeep), C.cast(parr, C.c_void_p)))
 
     def close(self):
         if getattr(self, "h", None):
@@ -193,12 +196,17 @@ class World:
             mats=np.stack([m["kind"], m["texture"], m["param"].copy().view(np.uint32)], axis=1),
             texs=np.concatenate([np.stack([t["kind"], t["image"]], axis=1), t["rgb"].copy().view(np.uint32),
                                  t["inv_frequency"].copy().view(np.uint32)[:, None], np.stack([t["even"], t["odd"]], axis=1)], axis=1) if nt else np.zeros((0, 8), np.uint32),
-            wrap=np.concatenate([items["wrap_flags"].astype(np.float32)[:, None], items["transform"], items["velocity"]], axis=1),
+            wrap=np.concatenate([items["wrap_flags"].astype(np.float32)[:, None], items["transform"], items["velocity"],
+                                 items["neg_inv_density"][:, None]], axis=1),
             cam=cam, bg=bg, light=light, default_size=(self.default_size.width, self.default_size.height))
         for i in range(ni):
             w, h = int(wh[i, 0]), int(wh[i, 1])
             buf = (C.c_uint8 * (w * h * 3)).from_address(host_lib().rtw_world_image(self.h, i))
             fs.images.append(np.frombuffer(buf, dtype=np.uint8).reshape(h, w, 3).copy())
+        n_perlins = int(self.info[10])
+        fs.perlins = np.zeros((n_perlins, 1536), np.uint32)
+        for i in range(n_perlins):
+            _check(host_lib().rtw_world_perlin(self.h, i, _p(fs.perlins[i, :768]), _p(fs.perlins[i, 768:])))
         return fs
 
     def device_scene(self, device: int = 0) -> "_cabi.DeviceScene":

@@ -106,6 +106,7 @@ struct RtScene {
     DevBuf<float4> own_box;
     DevBuf<WrapDev> wraps;
     bool has_animation = false;
+    bool has_wrapped = false, has_volume = false;  // pick the k_extend instantiation (plain / wrappers / wrappers + volumes)
     DevBuf<MaterialDev> materials;
     DevBuf<TextureDev> textures;
     std::vector<DevBuf<uint8_t>*> images;
@@ -188,12 +189,14 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     if (d.n_materials == 0 || !d.materials) return fail(RT_EINVAL, "no materials");
     for (uint32_t i = 0; i < d.n_materials; ++i) {
         const RtMaterial& m = d.materials[i];
-        if (m.kind > RT_MAT_DIFFUSE_LIGHT) return fail(RT_EUNSUPPORTED, "material kind outside the hot-path scope (Isotropic is volume-only)");
+        if (m.kind > RT_MAT_ISOTROPIC) return fail(RT_EINVAL, "unknown material kind");
         if (m.kind != RT_MAT_DIELECTRIC && m.texture >= d.n_textures) return fail(RT_EINVAL, "material texture index out of range");
     }
     for (uint32_t i = 0; i < d.n_textures; ++i) {
         const RtTexture& t = d.textures[i];
-        if (t.kind > RT_TEX_CHECKER) return fail(RT_EUNSUPPORTED, "texture kind outside the hot-path scope (Marble / Perlin)");
+        if (t.kind > RT_TEX_MARBLE) return fail(RT_EINVAL, "unknown texture kind");
+        if (t.kind == RT_TEX_MARBLE && (t.image >= d.n_perlins || !d.perlins[t.image].ranvec || !d.perlins[t.image].perm_x || !d.perlins[t.image].perm_y || !d.perlins[t.image].perm_z))
+            return fail(RT_EINVAL, "marble texture refers to a missing Perlin table");
         if (t.kind == RT_TEX_CHECKER && (t.even >= d.n_textures || t.odd >= d.n_textures)) return fail(RT_EINVAL, "checker texture child out of range");
         if (t.kind == RT_TEX_IMAGE && (t.image >= d.n_images || !d.images[t.image].rgb8 || d.images[t.image].width == 0 || d.images[t.image].height == 0))
             return fail(RT_EINVAL, "image texture refers to a missing image");
@@ -226,10 +229,12 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     const float eps = 5.9604645e-8f, safety = 8.0f;
     for (uint32_t i = 0; i < N; ++i) {
         const RtItem& it = d.items[i];
-        if (it.kind > RT_GEO_BOX) return fail(RT_EUNSUPPORTED, "geometry kind outside the hot-path scope (volumes)");
-        if (it.wrap_flags & ~3u) return fail(RT_EINVAL, "unknown wrapper flag");
+        if (it.kind > RT_GEO_BOX) return fail(RT_EINVAL, "unknown geometry kind");
+        if (it.wrap_flags & ~7u) return fail(RT_EINVAL, "unknown wrapper flag");
         any_wrap = any_wrap || it.wrap_flags != 0u;
         sc.has_animation = sc.has_animation || (it.wrap_flags & RT_WRAP_ANIMATION) != 0u;
+        sc.has_wrapped = sc.has_wrapped || it.wrap_flags != 0u;
+        sc.has_volume = sc.has_volume || (it.wrap_flags & RT_WRAP_VOLUME) != 0u;
         if (it.material >= d.n_materials) return fail(RT_EINVAL, "item material index out of range");
         const float* g = it.geom;
         PrimDev p;
@@ -271,10 +276,11 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
         w.a = make_float4(it.transform[0], it.transform[1], it.transform[2], it.transform[3]);
         w.b = make_float4(it.transform[4], it.velocity[0], it.velocity[1], it.velocity[2]);
         w.flags = it.wrap_flags;
+        w.neg_inv_density = it.neg_inv_density;
         wraps[i] = w;
         // Q2: the reference does not transform / motion-extend the AABB of a wrapped element, so its box (and every ancestor's)
         // is NOT a true bound: no tight cull there, the reference's weak per-axis rule alone decides (guard band = +inf)
-        if (it.wrap_flags) { leafA[i] = INFINITY; leafC[i] = 0.0f; }
+        if (it.wrap_flags & 3u) { leafA[i] = INFINITY; leafC[i] = 0.0f; }
     }
     auto bf16_up = [](float v) -> uint32_t {  // smallest bf16 >= v (v >= 0)
         uint32_t b;
@@ -419,6 +425,21 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
         img_dev[i] = b->p;
         sc.device_bytes += bytes;
     }
+    // Perlin tables: 768 floats (gradients) + 768 u32 (perm_x | perm_y | perm_z) per table, one device buffer each
+    std::vector<const float*> perlin_dev(d.n_perlins, nullptr);
+    for (uint32_t i = 0; i < d.n_perlins; ++i) {
+        std::vector<float> blk(1536);
+        std::memcpy(blk.data(), d.perlins[i].ranvec, 768 * sizeof(float));
+        std::memcpy(blk.data() + 768, d.perlins[i].perm_x, 256 * 4);
+        std::memcpy(blk.data() + 1024, d.perlins[i].perm_y, 256 * 4);
+        std::memcpy(blk.data() + 1280, d.perlins[i].perm_z, 256 * 4);
+        auto* b = new DevBuf<uint8_t>();
+        sc.images.push_back(b);
+        CU(b->alloc(1536 * 4));
+        CU(cudaMemcpy(b->p, blk.data(), 1536 * 4, cudaMemcpyHostToDevice));
+        perlin_dev[i] = reinterpret_cast<const float*>(b->p);
+        sc.device_bytes += 1536 * 4;
+    }
     std::vector<MaterialDev> mats(d.n_materials);
     for (uint32_t i = 0; i < d.n_materials; ++i) mats[i] = MaterialDev{d.materials[i].kind, d.materials[i].kind == RT_MAT_DIELECTRIC ? 0u : d.materials[i].texture, d.materials[i].param, 0u};
     std::vector<TextureDev> texs(std::max<uint32_t>(d.n_textures, 1));
@@ -436,6 +457,11 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
             t.inv_frequency = d.textures[i].inv_frequency;
             t.even = d.textures[i].even;
             t.odd = d.textures[i].odd;
+        }
+        if (t.kind == RT_TEX_MARBLE) {
+            t.inv_frequency = d.textures[i].inv_frequency;  // scale
+            t.ranvec = perlin_dev[d.textures[i].image];
+            t.perm = reinterpret_cast<const uint32_t*>(perlin_dev[d.textures[i].image] + 768);
         }
         texs[i] = t;
     }
@@ -500,6 +526,16 @@ int ensure_workspace(Workspace& sc, size_t slots, size_t npix, bool need_time) {
 }
 
 // The wavefront loop.  Writes the (unscaled unless apply_scale) film into d_out.
+using ExtendFn = void (*)(SceneDev, RenderDev, int);
+template <int FEAT>
+static ExtendFn pick_extend_feat(int mode, bool count) {
+    return count ? (mode == 2 ? k_extend<2, true, FEAT> : (mode == 1 ? k_extend<1, true, FEAT> : k_extend<0, true, FEAT>))
+                 : (mode == 2 ? k_extend<2, false, FEAT> : (mode == 1 ? k_extend<1, false, FEAT> : k_extend<0, false, FEAT>));
+}
+static ExtendFn pick_extend(int mode, bool count, int feat) {
+    return feat == 2 ? pick_extend_feat<2>(mode, count) : (feat == 1 ? pick_extend_feat<1>(mode, count) : pick_extend_feat<0>(mode, count));
+}
+
 int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint32_t lane_stride, float* d_out, bool apply_scale,
                 cudaStream_t stream, RtStats* stats) {
     if (P.width < 2 || P.height < 2) return fail(RT_EINVAL, "image must be at least 2x2 (reference divides by width-1 / height-1)");
@@ -581,9 +617,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     const size_t esmem = stack_smem_bytes(sc, eblock);
     int egrid = 0, sgrid = 0;
     const int mode = std::min(2, std::max(0, g_opt_traversal));
-    void (*ext)(SceneDev, RenderDev, int) =
-        g_opt_count ? (mode == 2 ? k_extend<2, true> : (mode == 1 ? k_extend<1, true> : k_extend<0, true>))
-                    : (mode == 2 ? k_extend<2, false> : (mode == 1 ? k_extend<1, false> : k_extend<0, false>));
+    void (*ext)(SceneDev, RenderDev, int) = pick_extend(mode, g_opt_count != 0, sc.has_volume ? 2 : (sc.has_wrapped ? 1 : 0));
     rc = persistent_grid(sc, ext, eblock, esmem, &egrid);
     if (rc) return rc;
     rc = persistent_grid(sc, k_shade, 128, 0, &sgrid);

@@ -47,20 +47,24 @@ struct __align__(16) ShadeDev {
 //   a = offset.xyz, y_sine | b = y_cosine, velocity.xyz | flags in the child reference (RT_REF_WRAPPED) + c.x
 struct __align__(16) WrapDev {
     float4 a, b;
-    uint32_t flags, pad0, pad1, pad2;
+    uint32_t flags;          // RT_WRAP_* bits (1 Transformation, 2 Animation, 4 Volume)
+    float neg_inv_density;   // Volume: -1 / density
+    uint32_t pad1, pad2;
 };
 struct MaterialDev {  // 16 B
     uint32_t kind, texture;
     float param;
     uint32_t pad;
 };
-struct TextureDev {  // 48 B
+struct TextureDev {  // 64 B
     uint32_t kind, width, height, even;  // even / odd: RT_TEX_CHECKER children
     float r, g, b;
     uint32_t odd;
     const uint8_t* texels;  // RGB8, row 0 = top
-    float inv_frequency;
+    float inv_frequency;    // checker; marble: scale
     uint32_t pad;
+    const float* ranvec;    // marble: 256 x 3 Perlin gradients
+    const uint32_t* perm;   // marble: perm_x | perm_y | perm_z (256 each)
 };
 
 struct CameraDev {
@@ -249,36 +253,86 @@ __device__ __forceinline__ WrapDev load_wrap(const SceneDev& S, uint32_t item) {
     const float4* q = reinterpret_cast<const float4*>(S.wraps + item);
     WrapDev w;
     w.a = __ldg(q); w.b = __ldg(q + 1);
-    w.flags = __float_as_uint(__ldg(q + 2).x);
-    w.pad0 = w.pad1 = w.pad2 = 0u;
+    const float4 c = __ldg(q + 2);
+    w.flags = __float_as_uint(c.x);
+    w.neg_inv_density = c.y;
+    w.pad1 = w.pad2 = 0u;
     return w;
 }
 
-// Leaf test dispatch (SceneElement::hit -> Geometry::hit, hittable.rs:141-148, 230-244).  Returns true and shrinks `end` when
-// the primitive is accepted.  `time` is Ray::time (only Animation wrappers use it).
-__device__ __forceinline__ bool leaf_test(const SceneDev& S, uint32_t ref, float3 o, float3 d, float time, float start, float& end) {
-    uint32_t kind = (ref >> RT_REF_KIND_SHIFT) & 3u;
-    uint32_t item = ref & RT_REF_ITEM_MASK;
-    const float4* q = reinterpret_cast<const float4*>(S.prims + item);
-    if (ref & RT_REF_WRAPPED) {
-        const WrapDev w = load_wrap(S, item);
-        wrap_reverse_ray(w, time, o, d);
-    }
-    float t;
-    bool hit;
-    if (kind == 0u) {
-        hit = sphere_t(__ldg(q), o, d, start, end, t);
-    } else if (kind == 2u) {
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3);
+__device__ __forceinline__ float u01(uint32_t v);
+__device__ __forceinline__ float ln_unit(float u);
+
+// Geometry::hit (hittable.rs:141-148): t of the accepted root in [start, end), by geometry kind.
+__device__ __forceinline__ bool prim_t(uint32_t kind, const float4* q, float3 o, float3 d, float start, float end, float& t) {
+    if (kind == 0u) return sphere_t(__ldg(q), o, d, start, end, t);
+    if (kind == 2u) {
         PrimDev p;
         p.q0 = __ldg(q); p.q1 = __ldg(q + 1); p.q2 = __ldg(q + 2); p.q3 = __ldg(q + 3);
         float w1, w2;
-        hit = triangle_t(p, o, d, start, end, t, w1, w2);
-    } else if (kind == 3u) {
+        return triangle_t(p, o, d, start, end, t, w1, w2);
+    }
+    if (kind == 3u) {
         int plane;
-        hit = box_t(__ldg(q), __ldg(q + 1), o, d, start, end, t, plane);
+        return box_t(__ldg(q), __ldg(q + 1), o, d, start, end, t, plane);
+    }
+    const float4 a = __ldg(q), b = __ldg(q + 1);
+    return rect_t(__float_as_uint(b.y), a.x, a.y, a.z, a.w, b.x, o, d, start, end, t);
+}
+
+// Key of the per-(path segment) Philox stream a volume draws its free path from (REPLAY layout of the oracle):
+// philox(k0, k1; c0, c1, c2, 0x40000000 | item).x — keyed by the element, so it does not depend on the visit order.
+struct VolKey {
+    uint32_t k0, k1, c0, c1, c2;
+};
+
+// VolumeGeometry::hit (hittable.rs:315-342): two boundary tests, then t = max(start_medium, 0) - ln(U) / density.
+template <class KEYFN>
+__device__ __forceinline__ bool volume_t(uint32_t kind, const float4* q, uint32_t item, float neg_inv_density, float3 o, float3 d,
+                                         float start, float end, const KEYFN& keyfn, float& t_out) {
+    const float INF = __int_as_float(0x7f800000);
+    float t0, t1;
+    if (!prim_t(kind, q, o, d, -INF, INF, t0)) return false;
+    const float next = t0 + 0.001f;
+    if (!prim_t(kind, q, o, d, next, INF, t1)) return false;
+    const float start_medium = fmaxf(t0, start), end_medium = fminf(t1, end);
+    if (start_medium >= end_medium) return false;
+    const VolKey k = keyfn();
+    const uint4 r = philox4x32_10(k.k0, k.k1, k.c0, k.c1, k.c2, 0x40000000u | item);
+    const float t = fmaxf(start_medium, 0.0f) + neg_inv_density * ln_unit(u01(r.x));
+    if (t > end_medium) return false;
+    t_out = t;
+    return true;
+}
+
+// Leaf test dispatch (SceneElement::hit -> Geometry::hit, hittable.rs:141-148, 230-244).  Returns true and shrinks `end` when
+// the element is accepted.  `time` is Ray::time (only Animation wrappers use it); keyfn supplies the volume draw key.
+template <class KEYFN>
+__device__ __forceinline__ bool leaf_test(const SceneDev& S, uint32_t ref, float3 o, float3 d, float time, float start, float& end,
+                                          const KEYFN& keyfn) {
+    const uint32_t kind = (ref >> RT_REF_KIND_SHIFT) & 3u;
+    const uint32_t item = ref & RT_REF_ITEM_MASK;
+    const float4* q = reinterpret_cast<const float4*>(S.prims + item);
+    float t;
+    bool hit;
+    // KEYFN::FEAT: 0 = the scene has no wrapped element, 1 = Transformation / Animation wrappers, 2 = + volumes
+    // (the launch picks the instantiation from the packed scene, so plain scenes do not carry the wrapper code)
+    if constexpr (KEYFN::FEAT >= 1) {
+        if (ref & RT_REF_WRAPPED) {
+            const WrapDev w = load_wrap(S, item);
+            wrap_reverse_ray(w, time, o, d);
+            if constexpr (KEYFN::FEAT >= 2) {
+                if (w.flags & 4u) hit = volume_t(kind, q, item, w.neg_inv_density, o, d, start, end, keyfn, t);
+                else hit = prim_t(kind, q, o, d, start, end, t);
+            } else {
+                hit = prim_t(kind, q, o, d, start, end, t);
+            }
+        } else {
+            hit = prim_t(kind, q, o, d, start, end, t);
+        }
     } else {
-        float4 a = __ldg(q), b = __ldg(q + 1);
-        hit = rect_t(__float_as_uint(b.y), a.x, a.y, a.z, a.w, b.x, o, d, start, end, t);
+        hit = prim_t(kind, q, o, d, start, end, t);
     }
     if (hit) end = t;
     return hit;
@@ -384,16 +438,16 @@ __device__ __forceinline__ void approx_slab(float mnx, float mny, float mnz, flo
 // simply wait.  The warp picks `do_leaf` by vote (k_extend), so each phase runs with most lanes enabled instead of
 // interleaving 17-lane node steps with 4-lane leaf tests.  Per-lane visit order is untouched.
 // Returns false when the lane's traversal is finished.
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, class KEYFN>
 __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_leaf, uint32_t* stk_ref, float* stk_tn,
-                                           uint32_t stk_stride, TravCount* cnt) {
+                                           uint32_t stk_stride, TravCount* cnt, const KEYFN& keyfn) {
     uint32_t cur = T.cur;
     const bool at_leaf = (cur & RT_REF_LEAF) != 0u;
     bool need_pop = false;
     if (do_leaf) {
         if (at_leaf) {
             if (COUNT) cnt->prims++;
-            if (leaf_test(S, cur, T.o, T.d, T.time, T.start, T.end)) T.best = cur;
+            if (leaf_test(S, cur, T.o, T.d, T.time, T.start, T.end, keyfn)) T.best = cur;
             need_pop = true;
         }
     } else if (!at_leaf) {
@@ -478,22 +532,22 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
     return true;
 }
 
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, class KEYFN>
 __device__ __forceinline__ bool trav_step(const SceneDev& S, Trav& T, uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride,
-                                          TravCount* cnt) {
-    return trav_round<MODE, COUNT>(S, T, (T.cur & RT_REF_LEAF) != 0u, stk_ref, stk_tn, stk_stride, cnt);
+                                          TravCount* cnt, const KEYFN& keyfn) {
+    return trav_round<MODE, COUNT>(S, T, (T.cur & RT_REF_LEAF) != 0u, stk_ref, stk_tn, stk_stride, cnt, keyfn);
 }
 
-template <int MODE, bool COUNT = false>
+template <int MODE, bool COUNT = false, class KEYFN>
 __device__ __forceinline__ HitRec traverse(const SceneDev& S, float3 o, float3 d, float time, float start, float end_in,
-                                           uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride,
+                                           uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride, const KEYFN& keyfn,
                                            TravCount* cnt = nullptr) {
     Trav T;
     HitRec best;
     best.ref = RT_NO_HIT;
     best.t = end_in;
     if (!trav_begin<MODE>(S, T, o, d, time, start, end_in)) return best;
-    while (trav_step<MODE, COUNT>(S, T, stk_ref, stk_tn, stk_stride, cnt)) {}
+    while (trav_step<MODE, COUNT>(S, T, stk_ref, stk_tn, stk_stride, cnt, keyfn)) {}
     best.ref = T.best;
     best.t = T.end;
     return best;
@@ -533,6 +587,13 @@ __device__ __forceinline__ Interaction make_interaction(const SceneDev& S, uint3
     hi.u = 0.0f; hi.v = 0.0f;
     float4 s3 = __ldg(sq + 3);
     hi.material = __float_as_uint(s3.w);
+    if (wrapped && (wr.flags & 4u)) {  // VolumeGeometry::hit :334-341: normal UP, uv ZERO, front_face false ("arbitrary")
+        hi.front_face = false;
+        hi.normal = f3(0.0f, 1.0f, 0.0f);
+        hi.position = pos;
+        wrap_apply_hit(wr, time, hi.position, hi.normal);
+        return hi;
+    }
     if (kind == 0u) {
         float4 s = __ldg(q);
         sn = div3(sub3(pos, f3(s.x, s.y, s.z)), s.w);  // sphere_geometry.rs:44
@@ -628,6 +689,18 @@ __device__ __forceinline__ float cbrt_unit(float u) {
     for (int i = 0; i < 4; ++i) y = (2.0f * y + u / (y * y)) * 0.333333343267f;
     return y;
 }
+// deterministic natural log on [0,1), IEEE ops only — bit-identical to oracle_rng.hpp ln_unit
+__device__ __forceinline__ float ln_unit(float u) {
+    if (!(u > 0.0f)) return -__int_as_float(0x7f800000);
+    uint32_t b = __float_as_uint(u);
+    int e = (int)(b >> 23) - 127;
+    float m = __uint_as_float((b & 0x007FFFFFu) | 0x3F800000u);
+    if (m > 1.41421356f) { m = m * 0.5f; e += 1; }
+    float s = (m - 1.0f) / (m + 1.0f);
+    float s2 = s * s;
+    float p = 2.0f * s * (1.0f + s2 * (0.333333343f + s2 * (0.2f + s2 * (0.142857149f + s2 * 0.111111112f))));
+    return (float)e * 0.693147182f + p;
+}
 __device__ __forceinline__ float3 sample_unit_sphere(float ua, float ub) {  // stands in for rand_distr::UnitSphere
     float z = 1.0f - 2.0f * ua;
     float r2 = 1.0f - z * z;
@@ -658,6 +731,37 @@ __device__ __forceinline__ uint32_t sat_u32(float v) {  // Rust `as u32` (satura
     if (v >= 4294967296.0f) return 0xFFFFFFFFu;
     return (uint32_t)v;
 }
+// Perlin::noise / ::turbulence (src/lib/perlin.rs:37-91), bits = 8
+__device__ __forceinline__ float perlin_noise(const TextureDev& t, float3 p) {
+    const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    const float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    const int i = (int)fx, j = (int)fy, k = (int)fz;
+    const float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+    float accum = 0.0f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                const uint32_t r = t.perm[(i + di) & 255] ^ t.perm[256 + ((j + dj) & 255)] ^ t.perm[512 + ((k + dk) & 255)];
+                const float3 c = f3(t.ranvec[3 * r], t.ranvec[3 * r + 1], t.ranvec[3 * r + 2]);
+                const float fi = (float)di, fj = (float)dj, fk = (float)dk;
+                const float3 weight = f3(u - fi, v - fj, w - fk);
+                accum += (fi * uu + (1.0f - fi) * (1.0f - uu)) * (fj * vv + (1.0f - fj) * (1.0f - vv)) * (fk * ww + (1.0f - fk) * (1.0f - ww)) *
+                         dot3(c, weight);
+            }
+    return accum;
+}
+__device__ __forceinline__ float perlin_turbulence(const TextureDev& t, float3 p, int depth, float fall_off) {
+    float accum = 0.0f, weight = 1.0f;
+    for (int d = 0; d < depth; ++d) {
+        accum += weight * perlin_noise(t, p);
+        weight *= fall_off;
+        p = mul3(p, 2.0f);
+    }
+    return fabsf(accum);
+}
 // does sampling this texture (through any checker nesting) read uv?
 __device__ __forceinline__ bool texture_needs_uv(const SceneDev& S, uint32_t tex) {
     const TextureDev t = S.textures[tex];
@@ -673,6 +777,10 @@ __device__ __forceinline__ float3 texture_sample(const SceneDev& S, uint32_t tex
         t = S.textures[sines < 0.0f ? t.even : t.odd];
     }
     if (t.kind == 0u) return f3(t.r, t.g, t.b);
+    if (t.kind == 3u) {  // Marble (texture.rs:44-51): 0.5 * (1 + sin(scale * z + 10 * turbulence(p, 7, 0.5)))
+        const float v = 0.5f * (1.0f + sinf(position.z * t.inv_frequency + 10.0f * perlin_turbulence(t, position, 7, 0.5f)));
+        return f3(v, v, v);
+    }
     uint32_t pu = min(sat_u32(u * (float)t.width), t.width - 1u);
     uint32_t pv = min(sat_u32(v * (float)t.height), t.height - 1u);
     const uint8_t* px = t.texels + 3ull * ((size_t)pv * t.width + pu);

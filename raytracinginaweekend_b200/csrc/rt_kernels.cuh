@@ -104,13 +104,34 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
     }
 }
 
+// Volume draw key of a path segment in the wavefront (computed on demand: only volume leaves ask for it)
+template <int FEAT_>
+struct ExtendKey {
+    static constexpr int FEAT = FEAT_;
+    const RenderDev* R;
+    int q;
+    uint32_t pos;
+    __device__ __forceinline__ VolKey operator()() const {
+        const uint32_t slot = __float_as_uint(R->A[q][pos].w), k = __float_as_uint(R->B[q][pos].w) & ~RT_ROOT_MISS;
+        const int32_t depth = R->D[q][pos];
+        const uint32_t pixel = slot % R->npix, lane_id = R->lane_first + (slot / R->npix) * R->lane_stride;
+        return VolKey{R->seed0, R->seed1, pixel, k * R->n_tasks + lane_id, 1u + (uint32_t)(R->max_depth - depth)};
+    }
+};
+// rt_trace: keyed by the ray index, seed 0, block 0
+struct TraceKey {
+    static constexpr int FEAT = 2;
+    uint64_t i;
+    __device__ __forceinline__ VolKey operator()() const { return VolKey{0u, 0u, (uint32_t)i, (uint32_t)(i >> 32), 0u}; }
+};
+
 // Queue position of the i-th live path: continuing paths grow from 0, regenerated ones from the top.
 __device__ __forceinline__ uint32_t queue_pos(uint32_t i, uint32_t nb, uint32_t cap) { return i < nb ? i : cap - 1u - (i - nb); }
 
 // Closest hit for every live path of queue `q`.  Persistent warps: every lane owns one ray's traversal state and,
 // when fewer than `refill_threshold` lanes are still busy, the idle lanes pull fresh rays with one warp-aggregated
 // atomic — rays differ by 100x in node visits, so waiting for the slowest lane would idle most of the warp.
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, int FEAT>
 __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
     extern __shared__ uint32_t smem[];
     uint32_t* stk_ref = smem + threadIdx.x;
@@ -167,7 +188,7 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
         const uint32_t n_leaf = __popc(__ballot_sync(FULL, active && (T.cur & RT_REF_LEAF)));
         const bool do_leaf = n_leaf * R.leaf_weight > ((uint32_t)__popc(act_mask) - n_leaf) * 16u;
         if (active) {
-            if (!trav_round<MODE, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc)) {
+            if (!trav_round<MODE, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos})) {
                 R.hits[my_pos] = make_uint2(T.best, __float_as_uint(T.end));
                 active = false;
             }
@@ -347,6 +368,10 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
                     }
                     ndir = unit3(dir);
                     scattered = true;
+                } else if (m.kind == 4u) {  // Isotropic (volume phase function), material.rs:106-111: Mirror(UnitSphere), not normalised
+                    ndir = sample_unit_sphere(u01(rnd.x), u01(rnd.y));
+                    att = texture_sample(S, m.texture, tu, tv, hi.position);
+                    scattered = true;
                 } else {  // DiffuseLight: never scatters, emits from both faces (Q14), material.rs:132-137
                     emitted = texture_sample(S, m.texture, tu, tv, hi.position);
                 }
@@ -458,7 +483,7 @@ __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ SceneDev 
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]);
         float3 d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
-        HitRec h = traverse<MODE>(S, o, d, S.trace_time, t_min, t_max, stk_ref, stk_tn, blockDim.x);
+        HitRec h = traverse<MODE, false>(S, o, d, S.trace_time, t_min, t_max, stk_ref, stk_tn, blockDim.x, TraceKey{i});
         if (h.ref != RT_NO_HIT) {
             Interaction hi = make_interaction(S, h.ref, h.t, o, d, S.trace_time, true);
             if (hit_id) hit_id[i] = h.ref & RT_REF_ITEM_MASK;

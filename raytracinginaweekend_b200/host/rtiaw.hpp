@@ -248,6 +248,10 @@ struct ImageData {
     uint32_t width = 0, height = 0;
     std::vector<uint8_t> rgb8;
 };
+struct PerlinData {  // Perlin (src/lib/perlin.rs:10-16) with bits = 8
+    std::vector<float> ranvec;  // 256 * 3
+    std::vector<uint32_t> perm_x, perm_y, perm_z;
+};
 using TextureId = uint32_t;
 using MaterialId = uint32_t;
 
@@ -257,6 +261,15 @@ public:
     std::vector<RtTexture> textures;
     std::vector<RtMaterial> materials;
     std::vector<ImageData> images;
+    std::vector<PerlinData> perlins;
+    TextureId texture_marble(float scale, PerlinData noise) {  // Texture::Marble { scale, noise }
+        perlins.push_back(std::move(noise));
+        RtTexture t{};
+        t.kind = RT_TEX_MARBLE; t.image = (uint32_t)perlins.size() - 1; t.inv_frequency = scale; t.even = t.odd = 0xFFFFFFFFu;
+        textures.push_back(t);
+        return (TextureId)textures.size() - 1;
+    }
+    MaterialId isotropic(TextureId albedo) { return add(RT_MAT_ISOTROPIC, albedo, 0.0f); }
     TextureId texture_solid(Color c) {  // Texture::Solid
         RtTexture t{};
         t.kind = RT_TEX_SOLID; t.image = 0xFFFFFFFFu; t.even = t.odd = 0xFFFFFFFFu; t.rgb[0] = c.x; t.rgb[1] = c.y; t.rgb[2] = c.z;
@@ -298,6 +311,8 @@ struct SurfaceGeometry {
     Transformation transformation;
     bool has_animation = false;
     Dir3 velocity;
+    bool is_volume = false;        // SceneElement::VolumeGeometry: `geometry` is the boundary, `material` the phase function
+    float neg_inv_density = 0.0f;  // VolumeGeometry::new (hittable.rs:301-307): -1.0 / density
     // SceneElement::bounding_box (hittable.rs:249-267) incl. Q2: wrappers neither move nor motion-extend the box
     Aabb bounding_box() const {
         Aabb b = geometry.bounding_box();
@@ -466,7 +481,7 @@ public:
     World& operator=(const World&) = delete;
 
     // Flatten into the C-ABI description (pointers stay valid while *this and `items_scratch` live).
-    RtSceneDesc describe(std::vector<RtItem>& items_scratch, std::vector<RtImage>& images_scratch) const {
+    RtSceneDesc describe(std::vector<RtItem>& items_scratch, std::vector<RtImage>& images_scratch, std::vector<RtPerlin>& perlins_scratch) const {
         const Scene& sc = *hittable;
         items_scratch.resize(sc.elements.size());
         for (size_t i = 0; i < sc.elements.size(); ++i) {
@@ -474,14 +489,20 @@ public:
             RtItem& it = items_scratch[i];
             e.geometry.write(it);
             it.material = e.material;
-            it.wrap_flags = (e.has_transformation ? (uint32_t)RT_WRAP_TRANSFORMATION : 0u) | (e.has_animation ? (uint32_t)RT_WRAP_ANIMATION : 0u);
+            it.wrap_flags = (e.has_transformation ? (uint32_t)RT_WRAP_TRANSFORMATION : 0u) | (e.has_animation ? (uint32_t)RT_WRAP_ANIMATION : 0u) |
+                            (e.is_volume ? (uint32_t)RT_WRAP_VOLUME : 0u);
+            it.neg_inv_density = e.neg_inv_density;
             it.transform[0] = e.transformation.offset.x; it.transform[1] = e.transformation.offset.y; it.transform[2] = e.transformation.offset.z;
             it.transform[3] = e.transformation.y_sine; it.transform[4] = e.transformation.y_cosine;
             it.velocity[0] = e.velocity.x; it.velocity[1] = e.velocity.y; it.velocity[2] = e.velocity.z;
         }
         images_scratch.clear();
         for (const ImageData& im : tables->images) images_scratch.push_back(RtImage{im.width, im.height, im.rgb8.data()});
+        perlins_scratch.clear();
+        for (const PerlinData& pn : tables->perlins) perlins_scratch.push_back(RtPerlin{pn.ranvec.data(), pn.perm_x.data(), pn.perm_y.data(), pn.perm_z.data()});
         RtSceneDesc d{};
+        d.n_perlins = (uint32_t)perlins_scratch.size();
+        d.perlins = perlins_scratch.data();
         d.n_items = (uint32_t)items_scratch.size();
         d.items = items_scratch.data();
         d.n_nodes = (uint32_t)sc.bvh.nodes.size();
@@ -521,7 +542,8 @@ public:
         release_device();
         std::vector<RtItem> items;
         std::vector<RtImage> images;
-        RtSceneDesc d = describe(items, images);
+        std::vector<RtPerlin> perlins;
+        RtSceneDesc d = describe(items, images, perlins);
         if (rt_scene_create(&d, device_ordinal, &dev_) != RT_OK) throw_rt("rt_scene_create");
         dev_ordinal_ = device_ordinal;
         return dev_;

@@ -3,11 +3,12 @@
 //   * OBJ ingest           : src/app/obj_loader.rs, bug-compatible fan triangulation (Q4)
 //   * WorldBuilder / NodeBuilder / NodeRef::finish : src/app/worlds/world_builder.rs
 //   * worlds               : the in-scope demo worlds of src/app/worlds/demo_worlds.rs + the BASELINE.json configs C1..C5
-// Row f2 is in: boxes, run-time Transformation / Animation wrappers (Q2 / Q3 kept), motion blur, Checker textures.
-// Out of scope (rejected with an error, never silently changed): volumes / Isotropic, Marble / Perlin.
+// Rows f2 and f3 are in: boxes, run-time Transformation / Animation wrappers (Q2 / Q3 kept), motion blur, Checker and
+// Marble (Perlin) textures, constant-density volumes with the Isotropic phase function — all ten demo worlds build.
 #pragma once
 #include <fstream>
 #include <functional>
+#include <numeric>
 #include <sstream>
 
 #include "rtiaw.hpp"
@@ -46,6 +47,49 @@ public:
             --sb;
             std::memcpy(&scale, &sb, 4);
         }
+    }
+
+    // rand Uniform::new(-1., 1.).sample (UniformFloat, scale nudged below the open upper bound) — used by rand_distr
+    float uniform_pm1() {
+        float scale = 2.0f;
+        const float max_rand = 1.0f - 1.1920929e-7f;
+        while (scale * max_rand + -1.0f >= 1.0f) { uint32_t sb; std::memcpy(&sb, &scale, 4); --sb; std::memcpy(&scale, &sb, 4); }
+        uint32_t bits = (next_u32() >> 9) | 0x3F800000u;
+        float v12;
+        std::memcpy(&v12, &bits, 4);
+        return (v12 - 1.0f) * scale + -1.0f;
+    }
+    Dir3 unit_sphere() {  // rand_distr::UnitSphere (Marsaglia)
+        for (;;) {
+            const float x1 = uniform_pm1(), x2 = uniform_pm1();
+            const float sum = x1 * x1 + x2 * x2;
+            if (sum >= 1.0f) continue;
+            const float factor = 2.0f * std::sqrt(1.0f - sum);
+            return {x1 * factor, x2 * factor, 1.0f - 2.0f * sum};
+        }
+    }
+    uint32_t gen_index(uint32_t ubound) {  // rand UniformInt<u32>::sample_single(0, ubound)
+        if (ubound == 0) return next_u32();
+        const uint32_t zone = (ubound << __builtin_clz(ubound)) - 1u;
+        for (;;) {
+            const uint64_t m = (uint64_t)next_u32() * ubound;
+            if ((uint32_t)m <= zone) return (uint32_t)(m >> 32);
+        }
+    }
+    template <class T>
+    void shuffle(std::vector<T>& v) {  // rand::seq::SliceRandom::shuffle
+        for (size_t i = v.size() - 1; i >= 1; --i) std::swap(v[i], v[gen_index((uint32_t)(i + 1))]);
+    }
+    PerlinData perlin(size_t bits) {  // Perlin::new (perlin.rs:19-36)
+        PerlinData p;
+        const size_t n = (size_t)1 << bits;
+        for (size_t i = 0; i < n; ++i) { const Dir3 g = unit_sphere(); p.ranvec.push_back(g.x); p.ranvec.push_back(g.y); p.ranvec.push_back(g.z); }
+        for (std::vector<uint32_t>* perm : {&p.perm_x, &p.perm_y, &p.perm_z}) {
+            perm->resize(n);
+            std::iota(perm->begin(), perm->end(), 0u);
+            shuffle(*perm);
+        }
+        return p;
     }
 
 private:
@@ -162,6 +206,7 @@ struct Node {
         Geometry geometry;
         MaterialId material;
         bool is_poi;
+        float density = 1.0f;  // < 1 -> VolumeGeometry (world_builder.rs:305-309)
     };
     std::vector<Geo> geo;
     Transformation transformation;
@@ -178,6 +223,11 @@ public:
     NodeBuilder& set_all_geo_as_poi() { for (auto& g : n_->geo) g.is_poi = true; return *this; }
     NodeBuilder& rotate_around_up(float deg) { n_->transformation = n_->transformation.rotate_around_up(deg); return *this; }
     NodeBuilder& translate(Dir3 o) { n_->transformation = n_->transformation.translate(o); return *this; }
+    NodeBuilder& set_all_geo_densitity(float density) {  // world_builder.rs:254-263 (spelling as in the reference)
+        if (!(density >= 0.0f && density < 1.0f)) throw std::invalid_argument("Invalid densitity");
+        for (auto& g : n_->geo) g.density = density;
+        return *this;
+    }
     NodeBuilder& animate_moving(Dir3 velocity) { n_->moving_animation = n_->moving_animation + velocity; return *this; }
     NodeRef build() { return n_; }
 
@@ -195,6 +245,8 @@ public:
     MaterialId material_lambert(TextureId t) { return tables->lambert(t); }
     MaterialId material_metal_solid(Color c, float fuzz) { return tables->metal(texture_solid(c), fuzz); }
     MaterialId material_dielectric(float ior) { return tables->dielectric(ior); }
+    MaterialId material_isotropic_solid(Color c) { return tables->isotropic(texture_solid(c)); }
+    TextureId texture_marble(float scale, SceneRng& rng) { return tables->texture_marble(scale, rng.perlin(8)); }  // world_builder.rs:32-37
     MaterialId material_diffuse_light_solid(Color c) { return tables->diffuse_light(texture_solid(c)); }
 
     static Geometry geo_rect(RectPlane plane, Point3 center, float s0, float s1) {  // world_builder.rs:77-86
@@ -210,7 +262,7 @@ public:
     NodeBuilder new_group() const { return NodeBuilder(std::make_shared<Node>()); }
     NodeBuilder new_obj(const Geometry& g, MaterialId m) const {
         auto n = std::make_shared<Node>();
-        n->geo.push_back({g, m, false});
+        n->geo.push_back({g, m, false, 1.0f});
         return NodeBuilder(n);
     }
     NodeBuilder new_obj_box(float width, float height, float depth, MaterialId m) const {  // geo_box, world_builder.rs:88-93
@@ -232,7 +284,7 @@ public:
         n->geo.reserve(tris.size());
         for (TriangleGeometry t : tris) {
             if (scale != 1.0f) for (auto& p : t.positions) p = p * scale;
-            n->geo.push_back({Geometry::Triangle(t), m, false});
+            n->geo.push_back({Geometry::Triangle(t), m, false, 1.0f});
         }
         return NodeBuilder(n);
     }
@@ -253,6 +305,8 @@ public:
                 e.material = g.material;
                 e.has_animation = !(node.moving_animation == dir::ZERO);
                 e.velocity = node.moving_animation;
+                e.is_volume = g.density < 1.0f;
+                if (e.is_volume) e.neg_inv_density = -1.0f / g.density;
                 const Geometry& baked = e.geometry;
                 all.push_back(e);
                 if (g.is_poi && !e.has_transformation && baked.kind == RT_GEO_RECT && !world->has_scattering_distribution_provider) {
@@ -386,6 +440,74 @@ inline NamedWorld create_world(const std::string& name, const Assets& assets) {
         scene.add(wb.new_obj_box(165.0f, 165.0f, 165.0f, white).rotate_around_up(-18.0f).translate({130.0f, 0.0f, 65.0f}));
         out.world = wb.finish(scene.build(), BackgroundColor::Solid({0, 0, 0}), cam);
         out.default_size = {600, 600};
+    } else if (name == "demo:cornell_box_smoke") {  // demo_worlds.rs:179-214
+        const float h = 278.0f;
+        const Camera cam = Camera::build().vertical_fov(40.0f, 1.0f).position({h, h, -800.0f}).look_at(dir::UP, {h, h, 0.0f}).build();
+        const MaterialId smoke_black = wb.material_isotropic_solid({0.0f, 0.0f, 0.0f});
+        const MaterialId smoke_white = wb.material_isotropic_solid({1.0f, 1.0f, 1.0f});
+        scene.add(detail::cornell_box_node(wb, 130.0f));
+        scene.add(wb.new_obj_box(165.0f, 330.0f, 165.0f, smoke_white).rotate_around_up(15.0f).translate({265.0f, 0.0f, 295.0f}).set_all_geo_densitity(0.01f));
+        scene.add(wb.new_obj_box(165.0f, 165.0f, 165.0f, smoke_black).rotate_around_up(-18.0f).translate({130.0f, 0.0f, 65.0f}).set_all_geo_densitity(0.01f));
+        out.world = wb.finish(scene.build(), BackgroundColor::Solid({0, 0, 0}), cam);
+        out.default_size = {600, 600};
+    } else if (name == "demo:perlin_spheres") {  // demo_worlds.rs:154-177
+        const Camera cam = Camera::build().vertical_fov(40.0f, 3.0f / 4.0f).position({13.0f, 2.0f, 3.0f}).look_at(dir::UP, {0, 0, 0}).build();
+        const MaterialId mat_noise = wb.material_lambert(wb.texture_marble(4.0f, rng));
+        scene.add(wb.new_obj_sphere_ground(1000.0f, 0.0f, mat_noise));
+        scene.add(wb.new_obj_sphere(2.0f, mat_noise).translate({0.0f, 2.0f, 0.0f}));
+        out.world = wb.finish(scene.build(), sky, cam);
+        out.default_size = {400, 300};
+    } else if (name == "demo:final_scene2") {  // demo_worlds.rs:30-152
+        const Camera cam = Camera::build().vertical_fov(40.0f, 1.0f).position({478.0f, 278.0f, -600.0f}).look_at(dir::UP, {278.0f, 278.0f, 0.0f})
+                               .motion_blur(0.0f, 1.0f).build();
+        const MaterialId mat_ground = wb.material_lambert_solid({0.48f, 0.83f, 0.53f});
+        NodeBuilder ground = wb.new_group();
+        {
+            const int boxes_per_side = 20;
+            const Point3 rmin{-1000.0f, 0.0f, -1000.0f}, rmax{1000.0f, 101.0f, 1000.0f};
+            const float width = (rmax.x - rmin.x) / (float)boxes_per_side;
+            const float height = rmax.y - rmin.y;
+            const float depth = (rmax.z - rmin.z) / (float)boxes_per_side;
+            for (int i = 0; i < boxes_per_side; ++i)
+                for (int j = 0; j < boxes_per_side; ++j) {
+                    const Dir3 mn = rmin + Dir3{(float)i * width, 0.0f, (float)j * depth} - Point3{};
+                    const float hbox = height * rng.gen_f32();
+                    ground.add(wb.new_obj_box(width, hbox, depth, mat_ground).translate(mn));
+                }
+        }
+        const MaterialId mat_light = wb.material_diffuse_light_solid({7.0f, 7.0f, 7.0f});
+        NodeBuilder light = wb.new_obj_rect_xz({273.0f, 554.0f, 279.0f}, 300.0f, 300.0f, mat_light);
+        const MaterialId mat_glass = wb.material_dielectric(1.5f);
+        const MaterialId mat_metal = wb.material_metal_solid({0.8f, 0.8f, 0.9f}, 1.0f);
+        const MaterialId mat_marble = wb.material_lambert(wb.texture_marble(0.1f, rng));
+        const MaterialId mat_earth = earth_material();
+        const MaterialId mat_fog = wb.material_isotropic_solid({0.2f, 0.4f, 0.9f});
+        const MaterialId mat_moving = wb.material_lambert_solid({0.7f, 0.3f, 0.1f});
+        NodeBuilder floating = wb.new_group();
+        floating.add(wb.new_obj_sphere(70.0f, mat_glass).translate({360.0f, 150.0f, 145.0f}));
+        floating.add(wb.new_obj_sphere(70.0f, mat_fog).translate({360.0f, 150.0f, 145.0f}).set_all_geo_densitity(0.2f));
+        floating.add(wb.new_obj_sphere(50.0f, mat_glass).translate({260.0f, 150.0f, 45.0f}));
+        floating.add(wb.new_obj_sphere(50.0f, mat_metal).translate({0.0f, 150.0f, 145.0f}));
+        floating.add(wb.new_obj_sphere(80.0f, mat_marble).translate({220.0f, 280.0f, 300.0f}));
+        floating.add(wb.new_obj_sphere(100.0f, mat_earth).translate({400.0f, 200.0f, 400.0f}));
+        floating.add(wb.new_obj_sphere(50.0f, mat_moving).translate({400.0f, 400.0f, 200.0f}).animate_moving({30.0f, 0.0f, 0.0f}));
+        NodeBuilder sphere_cube = wb.new_group();
+        {
+            const MaterialId material = wb.material_lambert_solid({0.75f, 0.75f, 0.75f});
+            const Transformation rot = Transformation().rotate_around_up(15.0f);
+            const Dir3 dir_1 = rot.apply_direction(dir::RIGHT), dir_2 = rot.apply_direction(dir::UP), dir_3 = rot.apply_direction(dir::FORWARD);
+            const Dir3 origin{-100.0f, 270.0f, 395.0f};
+            for (int i = 0; i < 1000; ++i) {
+                const float r0 = rng.gen_f32(), r1 = rng.gen_f32(), r2 = rng.gen_f32();
+                const Dir3 p = origin + 165.0f * (dir_1 * r0 + dir_2 * r1 + dir_3 * r2);
+                sphere_cube.add(wb.new_obj_sphere(10.0f, material).translate(p));
+            }
+        }
+        NodeBuilder obj_fog = wb.new_obj_sphere(5000.0f, wb.material_isotropic_solid({1.0f, 1.0f, 1.0f}));
+        obj_fog.set_all_geo_densitity(0.0001f);
+        scene.add(obj_fog).add(ground).add(sphere_cube).add(floating).add(light);
+        out.world = wb.finish(scene.build(), BackgroundColor::Solid({0, 0, 0}), cam);
+        out.default_size = {600, 600};
     } else if (name == "demo:moving_spheres") {  // demo_worlds.rs:351-393
         const Camera cam = Camera::build().vertical_fov(60.0f, 16.0f / 19.0f).position({0.0f, 2.0f, 10.0f}).look_at(dir::UP, {0.0f, 2.0f, 0.0f})
                                .motion_blur(0.0f, 0.5f).build();
@@ -471,7 +593,7 @@ inline NamedWorld create_world(const std::string& name, const Assets& assets) {
         out.world = wb.finish(scene.build(), sky, cam);
         out.default_size = {3840, 2160};
     } else {
-        throw std::runtime_error("unknown world '" + name + "' (out-of-scope demo worlds need volumes / Perlin: cornell_box_smoke, perlin_spheres, final_scene2)");
+        throw std::runtime_error("unknown world '" + name + "' (the ten reference demos and config:c1..c5 are available)");
     }
     return out;
 }

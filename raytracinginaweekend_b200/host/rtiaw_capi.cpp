@@ -43,7 +43,8 @@ RtwWorld* rtw_world_create(const char* name, const char* suzanne, const char* cu
 
 RtwWorld* rtw_world_create_elements(uint32_t n, const uint32_t* kinds, const uint32_t* mat_of, const float* geom, uint32_t n_materials,
                                     const RtMaterial* materials, uint32_t n_textures, const RtTexture* textures, uint32_t n_images,
-                                    const RtImage* images, const float* cam, const float* bg, const float* light, const float* wrap) {
+                                    const RtImage* images, const float* cam, const float* bg, const float* light, const float* wrap,
+                                    uint32_t n_perlins, const RtPerlin* perlins) {
     RtwWorld* w = nullptr;
     guard([&] {
         auto tables = std::make_shared<MaterialTable>();
@@ -52,6 +53,14 @@ RtwWorld* rtw_world_create_elements(uint32_t n, const uint32_t* kinds, const uin
             im.width = images[i].width; im.height = images[i].height;
             im.rgb8.assign(images[i].rgb8, images[i].rgb8 + (size_t)im.width * im.height * 3);
             tables->images.push_back(std::move(im));
+        }
+        for (uint32_t i = 0; i < n_perlins; ++i) {
+            PerlinData pn;
+            pn.ranvec.assign(perlins[i].ranvec, perlins[i].ranvec + 768);
+            pn.perm_x.assign(perlins[i].perm_x, perlins[i].perm_x + 256);
+            pn.perm_y.assign(perlins[i].perm_y, perlins[i].perm_y + 256);
+            pn.perm_z.assign(perlins[i].perm_z, perlins[i].perm_z + 256);
+            tables->perlins.push_back(std::move(pn));
         }
         tables->textures.assign(textures, textures + n_textures);
         tables->materials.assign(materials, materials + n_materials);
@@ -83,13 +92,15 @@ RtwWorld* rtw_world_create_elements(uint32_t n, const uint32_t* kinds, const uin
             e.geometry = geo;
             e.material = mat_of[i];
             if (wrap) {  // flags, offset xyz, y_sine, y_cosine, velocity xyz
-                const float* wv = wrap + 9 * (size_t)i;
+                const float* wv = wrap + 10 * (size_t)i;
                 const uint32_t fl = (uint32_t)wv[0];
                 e.has_transformation = (fl & RT_WRAP_TRANSFORMATION) != 0;
                 e.transformation.offset = {wv[1], wv[2], wv[3]};
                 e.transformation.y_sine = wv[4]; e.transformation.y_cosine = wv[5];
                 e.has_animation = (fl & RT_WRAP_ANIMATION) != 0;
                 e.velocity = {wv[6], wv[7], wv[8]};
+                e.is_volume = (fl & RT_WRAP_VOLUME) != 0;
+                e.neg_inv_density = wv[9];
             }
             elems[i] = e;
         }
@@ -134,6 +145,7 @@ int rtw_world_info(const RtwWorld* w, uint64_t* info) {
         info[7] = W.tables->textures.size();
         info[8] = W.tables->images.size();
         info[9] = W.has_scattering_distribution_provider ? 1 : 0;
+        info[10] = W.tables->perlins.size();
     });
 }
 
@@ -143,7 +155,8 @@ int rtw_world_export(const RtwWorld* w, RtItem* items, RtBvhNode* nodes, RtMater
         const World& W = *w->world;
         std::vector<RtItem> it;
         std::vector<RtImage> im;
-        RtSceneDesc d = W.describe(it, im);
+        std::vector<RtPerlin> pn;
+        RtSceneDesc d = W.describe(it, im, pn);
         std::memcpy(items, d.items, sizeof(RtItem) * d.n_items);
         if (d.n_nodes) std::memcpy(nodes, d.nodes, sizeof(RtBvhNode) * d.n_nodes);
         std::memcpy(materials, d.materials, sizeof(RtMaterial) * d.n_materials);
@@ -155,6 +168,16 @@ int rtw_world_export(const RtwWorld* w, RtItem* items, RtBvhNode* nodes, RtMater
         light[0] = d.has_light ? 1.0f : 0.0f;
         light[1] = (float)d.light_plane; light[2] = d.light_dist;
         light[3] = d.light_r0[0]; light[4] = d.light_r0[1]; light[5] = d.light_r1[0]; light[6] = d.light_r1[1];
+    });
+}
+
+int rtw_world_perlin(const RtwWorld* w, uint32_t index, float* ranvec768, uint32_t* perm768) {
+    return guard([&] {
+        const PerlinData& p = w->world->tables->perlins.at(index);
+        std::memcpy(ranvec768, p.ranvec.data(), 768 * sizeof(float));
+        std::memcpy(perm768, p.perm_x.data(), 256 * 4);
+        std::memcpy(perm768 + 256, p.perm_y.data(), 256 * 4);
+        std::memcpy(perm768 + 512, p.perm_z.data(), 256 * 4);
     });
 }
 

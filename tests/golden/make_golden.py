@@ -22,13 +22,17 @@ from helpers import adversarial_rays, random_rays  # noqa: E402
 from oracle import binding as ob  # noqa: E402
 
 SCENES = {"config:c1": (48, 32), "config:c2": (48, 27), "config:c3": (32, 32), "demo:defocus_blur": (40, 24), "demo:simple_plane": (40, 24),
-          "demo:cornell_box": (32, 32), "demo:moving_spheres": (38, 32)}
-TRACE_TIME = 0.3   # Ray::time of the traced rays (only demo:moving_spheres has Animation leaves)
+          "demo:cornell_box": (32, 32), "demo:moving_spheres": (38, 32), "demo:cornell_box_smoke": (32, 32), "demo:perlin_spheres": (40, 30),
+          "demo:final_scene2": (32, 32)}
+TRACE_TIME = 0.3   # Ray::time of the traced rays (only demo:moving_spheres / demo:final_scene2 have Animation leaves)
 RENDER = dict(spp=4, max_depth=50, threads=2, seed=20261018)
 
 
 def main():
+    only = sys.argv[1:]
     for name, (w, h) in SCENES.items():
+        if only and name not in only:
+            continue
         W = ob.OracleWorld.named(name)
         fs = W.export()
         po, pd = W.primary_rays(w, h)

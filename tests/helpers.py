@@ -46,15 +46,27 @@ def checker_tex(inv_frequency, even, odd):
     return [2, MISS, 0, 0, 0, int(np.array([inv_frequency], F32).view(np.uint32)[0]), even, odd]
 
 
+def marble_tex(scale, perlin):
+    return [3, perlin, 0, 0, 0, int(np.array([scale], F32).view(np.uint32)[0]), MISS, MISS]
+
+
+def random_perlin(rng):
+    """One Perlin table row: 256 unit gradients (float bits) + three permutations of 0..255 (perlin.rs:19-36)."""
+    g = rng.normal(size=(256, 3))
+    g = (g / np.linalg.norm(g, axis=1, keepdims=True)).astype(F32)
+    return np.concatenate([g.reshape(-1).view(np.uint32)] + [rng.permutation(256).astype(np.uint32) for _ in range(3)])
+
+
 def mat(kind, tex, param=0.0):
     return [kind, tex, int(np.array([param], F32).view(np.uint32)[0])]
 
 
 def random_scene(seed, n_spheres=20, n_tris=30, n_rects=4, extent=4.0, with_light=False, image_tex=None, n_boxes=0, wrap_fraction=0.0,
-                 checker=False):
-    """Random mixed scene in the flat element layout (kinds, item_mat, geom, mats, texs, images, cam, bg, light[, wrap]).
+                 checker=False, volume_fraction=0.0, marble=False):
+    """Random mixed scene in the flat element layout (kinds, item_mat, geom, mats, texs, images, cam, bg, light[, wrap, perlins]).
     n_boxes / wrap_fraction / checker exercise row f2: AxisAlignedBox primitives, run-time Transformation / Animation wrappers
-    (with the reference's untransformed bounding boxes, Q2) and Checker textures."""
+    (with the reference's untransformed bounding boxes, Q2) and Checker textures; volume_fraction / marble exercise row f3:
+    constant-density volumes (any boundary geometry, Isotropic and other phase functions) and Marble textures."""
     rng = np.random.default_rng(seed)
     kinds, geom = [], []
     for _ in range(n_boxes):
@@ -96,7 +108,18 @@ def random_scene(seed, n_spheres=20, n_tris=30, n_rects=4, extent=4.0, with_ligh
     if checker:
         texs.append(checker_tex(2.5, 0, 1)); texs.append(checker_tex(0.7, len(texs) - 1, 2))   # nested checker
         mats.append(mat(0, len(texs) - 1)); mats.append(mat(1, len(texs) - 2, 0.2))
+    perlins = []
+    if marble:
+        perlins = [random_perlin(rng), random_perlin(rng)]
+        texs.append(marble_tex(4.0, 0)); texs.append(marble_tex(0.6, 1))
+        mats.append(mat(0, len(texs) - 2)); mats.append(mat(1, len(texs) - 1, 0.1))
+        if checker:
+            texs.append(checker_tex(1.3, len(texs) - 1, 0)); mats.append(mat(0, len(texs) - 1))
     item_mat = rng.integers(0, len(mats), len(kinds)).astype(np.uint32)
+    iso = []
+    if volume_fraction > 0:
+        iso = [len(mats), len(mats) + 1]
+        mats.append(mat(4, 0)); mats.append(mat(4, len(texs) - 1))   # Isotropic over a solid and over the last texture
     cam = simple_camera(pos=(0.5, 1.0, 3.0 * extent), at=(0, 0, 0), fov=50.0, aspect=0.75)
     if wrap_fraction > 0:
         cam[19], cam[20] = 0.0, 1.0      # motion_blur(0, 1)
@@ -110,9 +133,11 @@ def random_scene(seed, n_spheres=20, n_tris=30, n_rects=4, extent=4.0, with_ligh
             light = np.array([1, g[0], g[1], g[2], g[3], g[4], g[5]], F32)
     out = dict(kinds=kinds, item_mat=item_mat, geom=geom, mats=np.array(mats, np.uint32), texs=np.array(texs, np.uint32),
                images=images, cam=cam, bg=bg, light=light)
-    if wrap_fraction > 0:
+    if marble:
+        out["perlins"] = np.array(perlins, np.uint32)
+    if wrap_fraction > 0 or volume_fraction > 0:
         n = len(kinds)
-        wrap = np.zeros((n, 9), F32)
+        wrap = np.zeros((n, 10), F32)
         wrap[:, 5] = 1.0                                   # y_cosine of the identity
         sel = rng.uniform(size=n) < wrap_fraction
         if with_light:
@@ -127,6 +152,14 @@ def random_scene(seed, n_spheres=20, n_tris=30, n_rects=4, extent=4.0, with_ligh
             if fl & 2:
                 wrap[i, 6:9] = rng.uniform(-0.8, 0.8, 3)
             wrap[i, 0] = fl
+        vol = rng.uniform(size=n) < volume_fraction
+        if with_light:
+            vol[np.nonzero(kinds == 1)[0][:1]] = False
+        for i in np.nonzero(vol)[0]:
+            wrap[i, 0] += 4                                # RT_WRAP_VOLUME: the geometry is the boundary of a constant medium
+            wrap[i, 9] = -1.0 / rng.uniform(0.2, 3.0)      # -1 / density
+            if rng.uniform() < 0.8:
+                item_mat[i] = iso[int(rng.integers(0, 2))] # mostly Isotropic; the rest keep an ordinary material as phase function
         out["wrap"] = wrap
     return out
 

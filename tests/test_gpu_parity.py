@@ -35,6 +35,16 @@ def default_options():
     yield
 
 
+def close_up_to_device_sinf(img, ref, rel=2e-5, max_bad=0):
+    """Marble / Checker evaluate sin() on the device (CUDA sinf) and with glibc in the oracle: <= 1-2 ulp apart, which moves a
+    texture colour by ~1e-7 relative and never changes a path.  NaN masks must still agree exactly."""
+    if not np.array_equal(np.isnan(ref), np.isnan(img)):
+        return False
+    nan = np.isnan(ref)
+    bad = (np.abs(ref - img) > rel * np.maximum(1.0, np.abs(ref))) & ~nan
+    return int(bad.any(axis=2).sum()) <= max_bad
+
+
 # ---------------------------------------------------------------- golden fixtures (no oracle in the loop)
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
 def test_golden_hits_and_replay_image(path):
@@ -46,17 +56,23 @@ def test_golden_hits_and_replay_image(path):
     assert r["t_bit_mismatch"] == 0 and r["normal_bit_mismatch"] == 0, r
     wd, ht = (int(x) for x in g["image_size"])
     img, st = rb.render(rb.Size2i(wd, ht), 2, 4, 50, w, rb.RenderMode.Default, seed=20261018, return_stats=True)
-    assert images_equal_bits(img, g["image"])
     assert st["ray_segments"] == int(g["rays"][0])
+    if "perlin" in path or "final_scene2" in path:
+        assert close_up_to_device_sinf(img, g["image"])      # Marble: device sinf vs glibc sinf, colour only (same paths)
+    else:
+        assert images_equal_bits(img, g["image"])
 
 
 # ---------------------------------------------------------------- Scene::hit parity, all traversal variants
 @pytest.mark.parametrize("mode", [0, 1, 2])
-@pytest.mark.parametrize("name", CONFIGS + ["demo:suzanne", "demo:earth_mapped", "demo:cornell_box", "demo:moving_spheres"])
+@pytest.mark.parametrize("name", CONFIGS + ["demo:suzanne", "demo:earth_mapped", "demo:cornell_box", "demo:moving_spheres",
+                                            "demo:cornell_box_smoke", "demo:perlin_spheres", "demo:final_scene2"])
 def test_trace_parity_vs_oracle(name, mode, oracle_world):
+    """Volume leaves (cornell_box_smoke, final_scene2) draw their free-flight distance from the per-ray replay stream inside
+    Scene::hit, so hit ids / t there also prove that the GPU consumes the same draws as the reference order of evaluation."""
     _cabi.set_option("traversal", mode)
     w, o = product_world(name), oracle_world(name)
-    if name == "demo:moving_spheres":
+    if name in ("demo:moving_spheres", "demo:final_scene2"):
         for tm in (0.0, 0.25, 0.49):
             org, dir = random_rays(o.export(), 20000, 3)
             r = assert_hits_match(w.hit(org, dir, time=tm), o.trace(org, dir, time=tm))
@@ -75,12 +91,13 @@ def test_trace_parity_vs_oracle(name, mode, oracle_world):
     assert r["t_bit_mismatch"] == 0 and r["normal_bit_mismatch"] == 0, r
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(16))
 def test_trace_parity_random_scenes(seed, oracle):
-    """seeds >= 8 add row f2: boxes, Transformation / Animation wrappers (ray time 0.37), checker textures."""
-    f2 = seed >= 8
+    """seeds >= 8 add row f2: boxes, Transformation / Animation wrappers (ray time 0.37), checker textures;
+    seeds >= 12 add row f3: constant-density volumes over every boundary kind (also wrapped ones) and marble textures."""
+    f2, f3 = seed >= 8, seed >= 12
     sc = random_scene(100 + seed, n_spheres=3 + 9 * (seed % 8), n_tris=25 * (seed % 8), n_rects=seed % 4, with_light=False,
-                      n_boxes=6 if f2 else 0, wrap_fraction=0.4 if f2 else 0.0, checker=f2)
+                      n_boxes=6 if f2 else 0, wrap_fraction=0.4 if f2 else 0.0, checker=f2, volume_fraction=0.35 if f3 else 0.0, marble=f3)
     w, o = rb.World.from_elements(**sc), oracle.OracleWorld.from_flat(**sc)
     fs = o.export()
     tm = 0.37 if f2 else 0.0
@@ -138,13 +155,17 @@ def test_flat_nodes_are_never_entered(oracle):
 # ---------------------------------------------------------------- render(): REPLAY bit-exactness
 @pytest.mark.parametrize("name,w,h,spp,T", [("config:c1", 96, 64, 6, 1), ("config:c1", 64, 40, 7, 3), ("config:c2", 96, 54, 4, 2),
                                             ("demo:cornell_box", 64, 64, 8, 4), ("demo:moving_spheres", 76, 64, 6, 3),
-                                            ("config:c3", 64, 64, 8, 4), ("demo:earth_mapped", 76, 64, 4, 2), ("demo:simple_plane", 64, 36, 9, 16)])
+                                            ("config:c3", 64, 64, 8, 4), ("demo:earth_mapped", 76, 64, 4, 2), ("demo:simple_plane", 64, 36, 9, 16),
+                                            ("demo:cornell_box_smoke", 64, 64, 8, 4), ("demo:perlin_spheres", 80, 60, 6, 3),
+                                            ("demo:final_scene2", 64, 64, 6, 3)])
 def test_render_replay_bit_exact(name, w, h, spp, T, oracle_world):
     ref, st = oracle_world(name).render(w, h, spp, 50, T, 77, "replay")
     img, gst = rb.render(rb.Size2i(w, h), T, spp, 50, product_world(name), rb.RenderMode.Default, seed=77, return_stats=True)
     assert gst["ray_segments"] == st["rays"]
     assert gst["paths"] == w * h * spp
-    if name in ("demo:earth_mapped", "config:c3", "demo:moving_spheres"):
+    if name == "demo:perlin_spheres":
+        assert close_up_to_device_sinf(img, ref)
+    elif name in ("demo:earth_mapped", "config:c3", "demo:moving_spheres", "demo:final_scene2"):
         # image texture: device acosf/atan2f may pick the neighbouring texel on a texel border (<= a few pixels)
         nan = np.isnan(ref) | np.isnan(img)
         bad = (np.abs(ref - img) > 1e-6) & ~nan
@@ -178,6 +199,30 @@ def test_render_random_f2_scene_bit_exact(oracle):
         nan = np.isnan(ref) | np.isnan(img)
         bad = (np.abs(ref - img) > 1e-6) & ~nan           # device sinf vs glibc at a checker zero crossing: a handful of pixels at most
         assert np.array_equal(np.isnan(ref), np.isnan(img)) and bad.any(axis=2).sum() <= 3
+
+
+def test_render_random_f3_scene(oracle):
+    """Row f3 on top of f2: volumes (Isotropic and ordinary phase functions, wrapped boundaries), marble textures, a light."""
+    sc = random_scene(47, n_spheres=10, n_tris=10, n_rects=4, with_light=True, n_boxes=6, wrap_fraction=0.4, checker=True,
+                      volume_fraction=0.4, marble=True)
+    w, o = rb.World.from_elements(**sc), oracle.OracleWorld.from_flat(**sc)
+    for T, spp in ((1, 5), (4, 6)):
+        ref, st = o.render(56, 42, spp, 20, T, 99, "replay")
+        img, gst = rb.render(rb.Size2i(56, 42), T, spp, 20, w, seed=99, return_stats=True)
+        assert gst["ray_segments"] == st["rays"]
+        assert close_up_to_device_sinf(img, ref, max_bad=3)   # checker zero crossings may flip a handful of pixels
+
+
+def test_render_volume_only_scene_bit_exact(oracle):
+    """Volumes with Isotropic over solid textures and no sin() anywhere: the film must be bit-identical."""
+    sc = random_scene(48, n_spheres=12, n_tris=0, n_rects=2, n_boxes=6, wrap_fraction=0.3, volume_fraction=0.5)
+    iso = np.nonzero(sc["mats"][:, 0] == 4)[0]
+    sc["mats"][iso, 1] = 1                                   # both Isotropic materials over solid textures
+    w, o = rb.World.from_elements(**sc), oracle.OracleWorld.from_flat(**sc)
+    ref, st = o.render(64, 48, 8, 30, 4, 5, "replay")
+    img, gst = rb.render(rb.Size2i(64, 48), 4, 8, 30, w, seed=5, return_stats=True)
+    assert gst["ray_segments"] == st["rays"]
+    assert images_equal_bits(img, ref)
 
 
 def test_render_random_scene_with_light_bit_exact(oracle):

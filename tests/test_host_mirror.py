@@ -13,7 +13,7 @@ from raytracinginaweekend_b200 import _cabi, api, build, dist
 from helpers import F32, random_scene
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FIELDS = ["kinds", "item_mat", "geom", "nodes_box", "nodes_lra", "mats", "texs", "cam", "bg", "light", "wrap"]
+FIELDS = ["kinds", "item_mat", "geom", "nodes_box", "nodes_lra", "mats", "texs", "cam", "bg", "light", "wrap", "perlins"]
 
 
 def same_flat(a, b):
@@ -26,6 +26,7 @@ def same_flat(a, b):
 
 
 WORLDS = ["demo:suzanne", "demo:final_scene1", "demo:simple_plane", "demo:earth_mapped", "demo:defocus_blur", "demo:cornell_box", "demo:moving_spheres",
+          "demo:cornell_box_smoke", "demo:perlin_spheres", "demo:final_scene2",
           "config:c1", "config:c2", "config:c3", "config:c5"]
 
 
@@ -46,7 +47,7 @@ def test_million_triangle_world_flatten_matches_oracle(oracle):
 @pytest.mark.parametrize("seed", range(6))
 def test_bvh_build_matches_oracle_on_random_scenes(seed, oracle):
     sc = random_scene(seed, n_spheres=5 + 13 * seed, n_tris=40 * seed, n_rects=seed, with_light=seed % 2 == 1, n_boxes=3 * (seed % 3),
-                      wrap_fraction=0.3 * (seed % 2), checker=seed % 3 == 0)
+                      wrap_fraction=0.3 * (seed % 2), checker=seed % 3 == 0, volume_fraction=0.2 * (seed >= 3), marble=seed >= 4)
     same_flat(rb.World.from_elements(**sc).export(), oracle.OracleWorld.from_flat(**sc).export())
 
 
@@ -68,8 +69,8 @@ def test_obj_loader_matches_oracle(oracle):
         assert tris.shape == (n, 24) and np.array_equal(tris.view(np.uint32), ref.view(np.uint32))
 
 
-def test_out_of_scope_worlds_are_rejected():
-    for name in ("demo:cornell_box_smoke", "demo:final_scene2", "demo:perlin_spheres", "demo:nope"):
+def test_unknown_worlds_are_rejected():
+    for name in ("demo:nope", "config:c9", ""):
         with pytest.raises(RuntimeError):
             rb.World.named(name)
 
@@ -101,7 +102,7 @@ def test_cabi_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_cabi.RtItem) == 140 and C.sizeof(_cabi.RtBvhNode) == 36
+    assert C.sizeof(_cabi.RtItem) == 144 and C.sizeof(_cabi.RtBvhNode) == 36
     assert C.sizeof(_cabi.RtMaterial) == 12 and C.sizeof(_cabi.RtTexture) == 32
     assert C.sizeof(_cabi.RtCamera) == 92 and C.sizeof(_cabi.RtRenderParams) == 40
 

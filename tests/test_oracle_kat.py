@@ -207,6 +207,73 @@ def test_replay_sampler_math_accuracy(oracle):
         assert abs(out[2] - float(F32(u)) ** (1 / 3)) < 3e-7
 
 
+def test_replay_ln_accuracy(oracle):
+    """ln_unit (free-flight sampling of volumes in REPLAY mode) against libm: <= 2e-7 relative on (0, 1)."""
+    for u in np.concatenate([np.linspace(1e-7, 0.999999, 1999), 2.0 ** -np.arange(1, 24)]):
+        uf = float(F32(u))
+        got, ref = oracle.lib().orc_probe_ln(uf), math.log(uf)
+        assert abs(got - ref) <= 3e-7 * max(1.0, abs(ref)), (uf, got, ref)
+    assert oracle.lib().orc_probe_ln(0.0) == -math.inf
+
+
+def _volume_sphere(oracle, density, kind=4):
+    geom = np.zeros((1, 24), F32); geom[0, :4] = [0, 0, -5, 1]
+    wrap = np.zeros((1, 10), F32); wrap[0, 0] = 4; wrap[0, 5] = 1; wrap[0, 9] = -1.0 / density
+    return oracle.OracleWorld.from_flat(np.array([0], np.uint32), np.zeros(1, np.uint32), geom, np.array([mat(kind, 0)], np.uint32),
+                                        np.array([solid_tex([1, 1, 1])], np.uint32), [], simple_camera(pos=(0, 0, 0), at=(0, 0, -5)),
+                                        np.array([0, 1, 1, 1], F32), np.zeros(7, F32), wrap=wrap)
+
+
+def test_volume_free_flight_is_exponential(oracle):
+    """VolumeGeometry::hit (hittable.rs:310-340): P(no collision along a chord of length L) = exp(-density * L); the collision
+    point lies inside the boundary, normal UP ('arbitrary'), front_face false, uv (0,0)."""
+    w = _volume_sphere(oracle, 0.7)
+    n = 40000
+    org = np.zeros((n, 3), F32); dir = np.tile(np.array([[0, 0, -1]], F32), (n, 1))
+    h = w.trace(org, dir)
+    hit = h["hit_id"] != MISS
+    assert abs((~hit).mean() - math.exp(-0.7 * 2.0)) < 4 * math.sqrt(0.25 / n)
+    assert np.all((h["t"][hit] >= 4.0) & (h["t"][hit] <= 6.0))
+    assert np.all(h["normal"][hit] == np.array([0, 1, 0], F32)) and np.all(h["front_face"][hit] == 0) and np.all(h["uv"][hit] == 0)
+    mean_depth = (h["t"][hit] - 4.0).mean()      # truncated exponential on [0, 2]
+    lam = 0.7
+    expect = 1 / lam - 2.0 * math.exp(-2 * lam) / (1 - math.exp(-2 * lam))
+    assert abs(mean_depth - expect) < 0.02
+    # a ray starting inside the medium: the boundary is entered at t < 0, clamped to t_min (hittable.rs:318-323)
+    org[:, 2] = -5.0
+    h = w.trace(org, dir)
+    assert abs((h["hit_id"] == MISS).mean() - math.exp(-0.7 * 1.0)) < 4 * math.sqrt(0.25 / n)
+    # chord ends before t_min / starts after t_max -> miss
+    assert np.all(w.trace(org[:64], dir[:64], 1.5, 1e30)["hit_id"] == MISS)
+    org[:, 2] = 0.0
+    assert np.all(w.trace(org[:64], dir[:64], 0.001, 3.9)["hit_id"] == MISS)
+
+
+def test_volume_replay_and_faithful_estimate_the_same_image(oracle, oracle_world):
+    w = oracle_world("demo:cornell_box_smoke")
+    n = 96
+    a, _ = w.render(24, 24, n, 20, 4, 1, "faithful")
+    b, _ = w.render(24, 24, n, 20, 4, 2, "faithful")
+    r, _ = w.render(24, 24, n, 20, 4, 1, "replay")
+    clip = lambda x: np.minimum(x, 10.0)
+    noise = math.sqrt(np.mean((clip(a) - clip(b)) ** 2))
+    err = math.sqrt(np.mean((clip(a) - clip(r)) ** 2))
+    assert err <= 1.3 * noise + 1e-3, (err, noise)
+    assert abs(clip(a).mean() - clip(r).mean()) <= 4 * noise / math.sqrt(a.size / 3) + 2e-3
+
+
+def test_perlin_noise_properties(oracle, oracle_world):
+    """Perlin::new (perlin.rs:19-36): 256 unit gradients and three permutations of 0..255; Marble is a lambert albedo in [0, 1]."""
+    fs = oracle_world("demo:perlin_spheres").export()
+    assert fs.perlins.shape == (1, 1536)
+    g = fs.perlins[0, :768].view(F32).reshape(256, 3)
+    assert np.allclose(np.linalg.norm(g, axis=1), 1.0, atol=1e-6)
+    for k in range(3):
+        assert sorted(fs.perlins[0, 768 + 256 * k: 1024 + 256 * k].tolist()) == list(range(256))
+    img, _ = oracle_world("demo:perlin_spheres").render(40, 30, 2, 2, 1, 1, "replay")   # depth 2: albedo * sky
+    assert np.isfinite(img).all() and img.min() >= 0.0 and img.max() <= 1.0 + 1e-6 and img.std() > 0.05
+
+
 # ---------------------------------------------------------------- OBJ ingest (src/app/obj_loader.rs, Q4)
 def test_obj_loader_fan_quirk(oracle):
     def load(name):
