@@ -167,6 +167,7 @@ typedef struct RtStats {
     uint64_t node_visits;    /* BVH node fetches (64 B each) — only with rt_set_option("count", 1) */
     uint64_t prim_tests;     /* primitive intersection tests    — only with rt_set_option("count", 1) */
     uint64_t exact_steps;    /* node steps that fell back to true divisions — only with rt_set_option("count", 1) */
+    uint64_t redo_rays;      /* traversal 3: rays the fast topology could not prove, traced again on the reference tree */
 } RtStats;
 
 typedef struct RtScene RtScene;
@@ -182,7 +183,9 @@ int rt_scene_device_bytes(const RtScene* scene, uint64_t* out_bytes);
 
 /* Closest hit for n caller rays (host buffers).  Volumes draw one random number per tested volume element inside the traversal
  * (the reference passes an rng into Scene::hit for this): rt_trace keys that draw by (ray index, element index), seed 0.  org/dir: n*3 floats; outputs: hit_id n, t n, normal n*3,
- * front_face n, uv n*2 (any output pointer may be NULL).  Half-open range [t_min, t_max). */
+ * front_face n, uv n*2 (any output pointer may be NULL).  Half-open range [t_min, t_max).  Directions should be unit vectors as
+ * Ray::new demands (ray.rs:13); a ray whose |dir|^2 is off by more than 1e-5 is still answered with the reference's arithmetic
+ * (which is not the geometric intersection for spheres then), using the reference node rule alone. */
 int rt_trace(RtScene* scene, const float* org_xyz, const float* dir_xyz, uint64_t n, float t_min, float t_max,
              uint32_t* hit_id, float* t, float* normal_xyz, uint8_t* front_face, float* uv);
 /* Ray::time of the rays handed to rt_trace / rt_trace_device (only Animation leaves look at it; default 0). */
@@ -209,7 +212,12 @@ int rt_film_scale_device(float* d_rgb, uint64_t n_floats, float multiplier, void
 int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_out_rgb8, void* cuda_stream);
 
 /* Knobs (process-wide).  "traversal": 0 = reference node test only, true divisions (the reference's algorithm, for A/B
- * parity sweeps); 1 = + tight carried-interval cull; 2 = + reciprocal fast path with exact fallback (default).
+ * parity sweeps); 1 = + tight carried-interval cull; 2 = + reciprocal fast path with exact fallback; 3 (default) = a
+ * rebuilt (SAH) topology over the same elements finds the closest accepted element, the result is kept only when the
+ * reference traversal provably returns the same element (unique minimum, hit point strictly inside the element's parent
+ * box of the reference tree), every other ray is traced again with 2 on the reference tree (RtStats.redo_rays); scenes with
+ * wrapped elements or volumes always use 2.  "rebuild": 0 = do not build the second topology at rt_scene_create.
+ * "rebuild_depth_extra": depth cap of the rebuilt tree above the reference depth (default 3).
  * "count": 1 = maintain node_visits / prim_tests / exact_steps.  "profile": 1 = time extend / shade separately.
  * "refill": busy-lane threshold of the persistent extend warps.  "leaf_weight": phase-vote weight.  "check_every": host
  * polling period (iterations).  "pipes": independent wavefront pipelines (streams) per render (default 1).

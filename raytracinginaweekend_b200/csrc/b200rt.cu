@@ -20,13 +20,17 @@
 
 #include "../../include/b200rt.h"
 #include "rt_kernels.cuh"
+#include "rt_rebuild.hpp"
 
 using namespace rt;
 
 namespace {
 
 thread_local std::string g_err;
-int g_opt_traversal = 2;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path
+int g_opt_traversal = 3;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path,
+                              // 3 = rebuilt topology + per-ray proof, unproven rays on the reference tree with 2 (plain scenes; else 2)
+int g_opt_rebuild = 1;        // build the second topology at rt_scene_create (0: traversal 3 behaves like 2)
+int g_opt_rebuild_depth_extra = 3;  // depth cap of the rebuilt tree = reference depth + this (the stack lives in shared memory)
 int g_opt_pipes = 1;         // independent wavefront pipelines (streams) per render: one pipeline's extend tail overlaps the other's work
 int g_opt_leaf_weight = 24;   // extend phase vote: leaf phase when n_leaf * w > n_node * 16
 int g_opt_refill = 28;        // extend refills idle lanes when fewer than this many of 32 are busy
@@ -75,6 +79,7 @@ struct Workspace {
     DevBuf<int32_t> D[2];
     DevBuf<float> Tm[2];
     DevBuf<uint2> hits;
+    DevBuf<uint32_t> redo;
     DevBuf<Counters> ctr;
     DevBuf<float> film;
     static const int MAX_PIPES = 8;
@@ -105,6 +110,9 @@ struct RtScene {
     DevBuf<ShadeDev> shade;
     DevBuf<float4> own_box;
     DevBuf<WrapDev> wraps;
+    DevBuf<NodeDev> nodes2;    // row f4: rebuilt topology (plain scenes only)
+    DevBuf<float4> vis_box;
+    uint32_t depth2 = 0;
     bool has_animation = false;
     bool has_wrapped = false, has_volume = false;  // pick the k_extend instantiation (plain / wrappers / wrappers + volumes)
     DevBuf<MaterialDev> materials;
@@ -363,6 +371,52 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     }
     sc.depth = depth;
 
+    // Row f4: second topology (SAH) over the same elements.  Plain scenes only: wrapped elements have boxes that are not
+    // true bounds (Q2) and volumes draw random numbers per tested element, so those scenes keep the reference tree alone.
+    std::vector<NodeDev> nodes2;
+    std::vector<float4> vis_box;
+    uint32_t root2 = 0;
+    if (!any_wrap && N >= 2 && g_opt_rebuild) {
+        std::vector<rt_rebuild::Box3> lb(N);
+        for (uint32_t i = 0; i < N; ++i)
+            for (int k = 0; k < 3; ++k) { lb[i].mn[k] = lbox[i].mn[k]; lb[i].mx[k] = lbox[i].mx[k]; }
+        rt_rebuild::Tree F;
+        rt_rebuild::build(lb, depth + (uint32_t)std::max(0, g_opt_rebuild_depth_extra), F);
+        const uint32_t n2 = (uint32_t)F.left.size();
+        std::vector<float> a2(n2, 0.0f), c2(n2, 0.0f);
+        for (uint32_t ii = n2; ii-- > 0;) {  // pre-order numbering: children have larger indices
+            float a = 0.0f, c = 0.0f;
+            for (uint32_t ch : {F.left[ii], F.right[ii]}) {
+                if (ch & RT_LEAF_BIT) { a = std::max(a, leafA[ch & ~RT_LEAF_BIT]); c = std::max(c, leafC[ch & ~RT_LEAF_BIT]); }
+                else { a = std::max(a, a2[ch]); c = std::max(c, c2[ch]); }
+            }
+            a2[ii] = a; c2[ii] = c;
+        }
+        nodes2.resize(n2);
+        auto box2 = [&](uint32_t r) -> rt_rebuild::Box3 { return (r & RT_LEAF_BIT) ? lb[r & ~RT_LEAF_BIT] : F.box[r]; };
+        auto ref2 = [&](uint32_t r) -> uint32_t { return (r & RT_LEAF_BIT) ? ref_of_item(r & ~RT_LEAF_BIT) : r; };
+        for (uint32_t i = 0; i < n2; ++i) {
+            const rt_rebuild::Box3 bl = box2(F.left[i]), br = box2(F.right[i]);
+            NodeDev nd;
+            nd.q0 = make_float4(bl.mn[0], bl.mn[1], bl.mn[2], bl.mx[0]);
+            nd.q1 = make_float4(bl.mx[1], bl.mx[2], br.mn[0], br.mn[1]);
+            nd.q2 = make_float4(br.mn[2], br.mx[0], br.mx[1], br.mx[2]);
+            nd.q3 = make_uint4(ref2(F.left[i]), ref2(F.right[i]), 0u, pack_margin(a2[i], c2[i]));
+            nodes2[i] = nd;
+        }
+        root2 = ref2(F.root);
+        sc.depth2 = F.depth;
+        // the reference parent's box of every element: the visibility proof of a fast-path hit (ref_visible)
+        vis_box.assign(2 * (size_t)N, make_float4(0, 0, 0, 0));
+        for (uint32_t i = 0; i < d.n_nodes; ++i)
+            for (uint32_t ch : {d.nodes[i].left, d.nodes[i].right})
+                if (ch & RT_LEAF_BIT) {
+                    const uint32_t item = ch & ~RT_LEAF_BIT;
+                    vis_box[2 * (size_t)item] = make_float4(d.nodes[i].aabb_min[0], d.nodes[i].aabb_min[1], d.nodes[i].aabb_min[2], 0.0f);
+                    vis_box[2 * (size_t)item + 1] = make_float4(d.nodes[i].aabb_max[0], d.nodes[i].aabb_max[1], d.nodes[i].aabb_max[2], 0.0f);
+                }
+    }
+
     SceneDev& S = sc.dev;
     std::memset(&S, 0, sizeof(S));
     S.root = root;
@@ -374,7 +428,8 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
         }
         S.root_margin = pack_margin(nodeA[root], nodeC[root]);
     }
-    S.stack_cap = depth + 2;
+    S.stack_cap = std::max(depth, sc.depth2) + 2;
+    S.root2 = root2;
 
     const RtCamera& c = d.camera;
     S.cam.position = make_float3(c.position[0], c.position[1], c.position[2]);
@@ -413,7 +468,14 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     if (!nodes.empty()) CU(cudaMemcpy(sc.own_box.p, own_box.data(), own_box.size() * sizeof(float4), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(sc.prims.p, prims.data(), N * sizeof(PrimDev), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(sc.shade.p, shade.data(), N * sizeof(ShadeDev), cudaMemcpyHostToDevice));
-    sc.device_bytes = nodes.size() * (sizeof(NodeDev) + 2 * sizeof(float4)) + (uint64_t)N * (sizeof(PrimDev) + sizeof(ShadeDev));
+    sc.device_bytes += nodes.size() * (sizeof(NodeDev) + 2 * sizeof(float4)) + (uint64_t)N * (sizeof(PrimDev) + sizeof(ShadeDev));
+    if (!nodes2.empty()) {
+        CU(sc.nodes2.alloc(nodes2.size()));
+        CU(sc.vis_box.alloc(vis_box.size()));
+        CU(cudaMemcpy(sc.nodes2.p, nodes2.data(), nodes2.size() * sizeof(NodeDev), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(sc.vis_box.p, vis_box.data(), vis_box.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        sc.device_bytes += nodes2.size() * sizeof(NodeDev) + vis_box.size() * sizeof(float4);
+    }
 
     std::vector<const uint8_t*> img_dev(d.n_images, nullptr);
     for (uint32_t i = 0; i < d.n_images; ++i) {
@@ -474,6 +536,8 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     S.prims = sc.prims.p;
     S.shade = sc.shade.p;
     S.own_box = sc.own_box.p;
+    S.nodes2 = sc.nodes2.p;
+    S.vis_box = sc.vis_box.p;
     S.wraps = sc.wraps.p;
     S.trace_time = 0.0f;
     S.materials = sc.materials.p;
@@ -504,6 +568,7 @@ int ensure_workspace(Workspace& sc, size_t slots, size_t npix, bool need_time) {
             sc.Tm[q].release();
         }
         CU(sc.hits.alloc(slots));
+        CU(sc.redo.alloc(slots));
         CU(sc.acc.alloc(slots));
         sc.ws_slots = slots;
     }
@@ -606,6 +671,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
                 pp.R.Tm[q] = sc.has_animation ? ws.Tm[q].p + off : nullptr;
             }
             pp.R.hits = ws.hits.p + off;
+            pp.R.redo = ws.redo.p + off;
             pp.R.ctr = ws.ctr.p + p;
             pp.st = ws.pipe_stream[p];
             pp.R.iter_log = iter_log_path ? ws.iter_log.p + (size_t)p * Workspace::ITER_LOG_CAP * 8 : nullptr;
@@ -616,10 +682,19 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     const int eblock = 128;
     const size_t esmem = stack_smem_bytes(sc, eblock);
     int egrid = 0, sgrid = 0;
-    const int mode = std::min(2, std::max(0, g_opt_traversal));
-    void (*ext)(SceneDev, RenderDev, int) = pick_extend(mode, g_opt_count != 0, sc.has_volume ? 2 : (sc.has_wrapped ? 1 : 0));
+    int mode = std::min(3, std::max(0, g_opt_traversal));
+    if (mode == 3 && !sc.nodes2.p) mode = 2;  // no rebuilt topology for this scene (wrapped elements, single element, rebuild off)
+    ExtendFn ext = mode == 3 ? (g_opt_count ? k_extend<3, true, 0> : k_extend<3, false, 0>)
+                             : pick_extend(mode, g_opt_count != 0, sc.has_volume ? 2 : (sc.has_wrapped ? 1 : 0));
+    ExtendFn ext_redo = g_opt_count ? k_extend<2, true, 0, true> : k_extend<2, false, 0, true>;
     rc = persistent_grid(sc, ext, eblock, esmem, &egrid);
     if (rc) return rc;
+    int rgrid = 0;
+    if (mode == 3) {
+        rc = persistent_grid(sc, ext_redo, eblock, esmem, &rgrid);
+        if (rc) return rc;
+        rgrid = std::max(1, rgrid / 4);  // the redo list is a small fraction of an iteration's rays
+    }
     rc = persistent_grid(sc, k_shade, 128, 0, &sgrid);
     if (rc) return rc;
 
@@ -658,6 +733,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
             if (pe) CU(cudaEventRecord(pe[0], pp.st));
             pp.R.iter = (uint32_t)std::min<uint64_t>(pp.iters, Workspace::ITER_LOG_CAP - 1);
             ext<<<egrid, eblock, esmem, pp.st>>>(sc.dev, pp.R, pp.q);
+            if (mode == 3) { ext_redo<<<rgrid, eblock, esmem, pp.st>>>(sc.dev, pp.R, pp.q); ++launches; }
             if (pe) CU(cudaEventRecord(pe[1], pp.st));
             k_shade<<<sgrid, 128, 0, pp.st>>>(sc.dev, pp.R, pp.q);
             if (pe) CU(cudaEventRecord(pe[2], pp.st));
@@ -745,6 +821,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     for (const Pipe& pp : pipes) {
         total.rays += pp.final_ctr->rays; total.paths += pp.final_ctr->paths;
         total.node_visits += pp.final_ctr->node_visits; total.prim_tests += pp.final_ctr->prim_tests; total.exact_steps += pp.final_ctr->exact_steps;
+        total.redo_total += pp.final_ctr->redo_total;
         iters = std::max(iters, pp.iters);
     }
     const Counters* final_ctr = &total;
@@ -759,6 +836,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
         stats->node_visits = final_ctr->node_visits;
         stats->prim_tests = final_ctr->prim_tests;
         stats->exact_steps = final_ctr->exact_steps;
+        stats->redo_rays = final_ctr->redo_total;
     }
     return RT_OK;
 }
@@ -779,6 +857,8 @@ int rt_set_option(const char* key, int64_t value) {
     if (!key) return fail(RT_EINVAL, "key is NULL");
     std::string k(key);
     if (k == "traversal") g_opt_traversal = (int)value;
+    else if (k == "rebuild") g_opt_rebuild = (int)value;
+    else if (k == "rebuild_depth_extra") g_opt_rebuild_depth_extra = (int)value;
     else if (k == "profile") g_opt_profile = (int)value;
     else if (k == "count") g_opt_count = (int)value;
     else if (k == "refill") g_opt_refill = (int)value;
@@ -836,8 +916,8 @@ int rt_trace_device(RtScene* scene, const float* d_org, const float* d_dir, uint
     const int block = 128;
     const size_t smem = stack_smem_bytes(*scene, block);
     int grid = 0, rc;
-    const int mode = std::min(2, std::max(0, g_opt_traversal));
-    auto trc = mode == 2 ? k_trace<2> : (mode == 1 ? k_trace<1> : k_trace<0>);
+    const int mode = std::min(3, std::max(0, g_opt_traversal));
+    auto trc = mode == 3 ? k_trace<3> : (mode == 2 ? k_trace<2> : (mode == 1 ? k_trace<1> : k_trace<0>));
     rc = persistent_grid(*scene, trc, block, smem, &grid);
     if (rc) return rc;
     grid = (int)std::min<uint64_t>((n + block - 1) / block, (uint64_t)grid * 4);

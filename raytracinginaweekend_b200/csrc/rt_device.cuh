@@ -86,6 +86,10 @@ struct SceneDev {
     uint32_t root_margin;     // guard band of the root box test (packed like NodeDev.q3.w)
     const float4* own_box;    // [2*n_nodes] each node's own AABB (min.xyz,0 | max.xyz,0): only read on exact-tie pops
     const WrapDev* wraps;     // [n_items] or NULL when no item is wrapped
+    // Row f4 (rt_rebuild.hpp): the rebuilt topology over the same elements; NULL when the scene has wrapped elements
+    const NodeDev* nodes2;    // same 64 B record; q3.z unused (children are visited near-first)
+    uint32_t root2;
+    const float4* vis_box;    // [2*n_items] box of the element's parent in the REFERENCE tree (min.xyz,0 | max.xyz,0)
     float trace_time;         // Ray::time of rt_trace rays
     CameraDev cam;
     uint32_t bg_is_sky;
@@ -532,6 +536,100 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row f4: traversal of the REBUILT topology (S.nodes2, plain scenes only).  It is an accelerator, not a definition:
+//   * it finds the smallest accepted t over ALL elements (every cull is conservative: a child is skipped only when the
+//     carried interval is empty by more than the guard band + the approximation error, and a popped entry only when
+//     end < tn - band, so even an element at exactly the current best t is still tested);
+//   * the leaf test runs with a CLOSED upper end once a best exists, so a second element at exactly the same t is seen
+//     and flagged (`tie`): which of two equal-t elements the reference returns depends on ITS visit order (Q13);
+//   * children are visited near-first (the reference orders by the sign of dir[axis_id]; irrelevant here).
+// The caller accepts the result only if !tie and ref_visible(); everything else is traced again on the reference tree.
+// ------------------------------------------------------------------------------------------------
+#define RT_TIE_BIT 8u  // kept in Trav::dpos (bits 0..2 are unused by the fast traversal)
+
+template <bool COUNT>
+__device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool do_leaf, uint32_t* stk_ref, float* stk_tn,
+                                                uint32_t stk_stride, TravCount* cnt) {
+    uint32_t cur = T.cur;
+    const bool at_leaf = (cur & RT_REF_LEAF) != 0u;
+    bool need_pop = false;
+    if (do_leaf) {
+        if (at_leaf) {
+            if (COUNT) cnt->prims++;
+            const uint32_t kind = (cur >> RT_REF_KIND_SHIFT) & 3u, item = cur & RT_REF_ITEM_MASK;
+            const bool have = T.best != RT_NO_HIT;
+            const float end_closed = have ? __uint_as_float(__float_as_uint(T.end + 0.0f) + 1u) : T.end;  // next float up (end >= 0, finite)
+            float t;
+            if (prim_t(kind, reinterpret_cast<const float4*>(S.prims + item), T.o, T.d, T.start, end_closed, t)) {
+                if (have && t == T.end) {
+                    T.dpos |= RT_TIE_BIT;
+                } else {
+                    T.best = cur; T.end = t; T.dpos &= ~RT_TIE_BIT;
+                }
+            }
+            need_pop = true;
+        }
+    } else if (!at_leaf) {
+        if (COUNT) cnt->nodes++;
+        const float4* q = reinterpret_cast<const float4*>(S.nodes2 + cur);
+        const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));
+        float tnL, tfL, tnR, tfR;
+        approx_slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T, tnL, tfL);
+        approx_slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, tnR, tfR);
+        const float sA = __fmaf_rn(__uint_as_float(q3.w & 0xFFFF0000u), T.mscale, T.oe), sC = __uint_as_float(q3.w << 16) * T.mscale;
+        const float mgL = __fmaf_rn(tnL, __fmaf_rn(sC, tnL, T.sB), sA);
+        const float mgR = __fmaf_rn(tnR, __fmaf_rn(sC, tnR, T.sB), sA);
+        const bool pL = !(tnL - tfL > mgL), pR = !(tnR - tfR > mgR);
+        const bool left_first = tnL <= tnR;
+        const uint32_t c1 = left_first ? q3.x : q3.y, c2 = left_first ? q3.y : q3.x;
+        const bool p1 = left_first ? pL : pR, p2 = left_first ? pR : pL;
+        if (p1 && p2) {
+            stk_ref[T.sp * stk_stride] = c2;
+            stk_tn[T.sp * stk_stride] = left_first ? tnR - mgR : tnL - mgL;  // cull threshold of the deferred child
+            ++T.sp;
+        }
+        if (p1) T.cur = c1;
+        else if (p2) T.cur = c2;
+        else need_pop = true;
+    }
+    if (need_pop) {
+        for (;;) {
+            if (T.sp == 0) return false;
+            --T.sp;
+            cur = stk_ref[T.sp * stk_stride];
+            if (T.end < stk_tn[T.sp * stk_stride]) continue;
+            break;
+        }
+        T.cur = cur;
+    }
+    return true;
+}
+
+// Can the fast traversal be used for this ray at all?  (finite, non-degenerate direction; see trav_setup)
+__device__ __forceinline__ bool fast_eligible(const SceneDev& S, const Trav& T) { return S.nodes2 != nullptr && !T.exact_only; }
+__device__ __forceinline__ void trav_setup_fast(const SceneDev& S, Trav& T) { T.cur = S.root2; T.dpos = 0u; }
+
+// Does the reference traversal provably return element `ref` at `t` (given that it is the UNIQUE minimum of all accepted
+// candidates)?  The reference reaches the element iff every ancestor A passes Aabb::hit_cond for the range [start, e) with
+// some e > t.  Per axis that holds when t lies strictly between the two slab distances the reference computes,
+// t0 = rn(rn(A.lo - o) / d) and t1 likewise: sufficient is that p = o + t d lies inside A by more than
+// 2^-22 (|A.lo| + |o| + |p|) on that axis (three roundings of 2^-24 each); we ask for 1e-6 (4x).
+// Ancestor boxes are nested (exact unions), and the margin grows slower than the distance when a face moves outward, so
+// the test against the PARENT's box covers the whole chain.  Flat parents (zero thickness, invisible in the reference,
+// aabb.rs:73) can never pass.  A failure proves nothing: the ray is simply traced on the reference tree.
+__device__ __forceinline__ bool ref_visible(const SceneDev& S, uint32_t ref, float3 o, float3 d, float t) {
+    const uint32_t item = ref & RT_REF_ITEM_MASK;
+    const float4 lo = __ldg(S.vis_box + 2u * item), hi = __ldg(S.vis_box + 2u * item + 1u);
+    const float c = 1e-6f;
+    const float px = o.x + t * d.x, py = o.y + t * d.y, pz = o.z + t * d.z;
+    const float mx = c * (fabsf(lo.x) + fabsf(hi.x) + fabsf(o.x) + fabsf(px));
+    const float my = c * (fabsf(lo.y) + fabsf(hi.y) + fabsf(o.y) + fabsf(py));
+    const float mz = c * (fabsf(lo.z) + fabsf(hi.z) + fabsf(o.z) + fabsf(pz));
+    return (px - lo.x > mx) && (hi.x - px > mx) && (py - lo.y > my) && (hi.y - py > my) && (pz - lo.z > mz) && (hi.z - pz > mz);
+}
+
 template <int MODE, bool COUNT, class KEYFN>
 __device__ __forceinline__ bool trav_step(const SceneDev& S, Trav& T, uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride,
                                           TravCount* cnt, const KEYFN& keyfn) {
@@ -550,6 +648,25 @@ __device__ __forceinline__ HitRec traverse(const SceneDev& S, float3 o, float3 d
     while (trav_step<MODE, COUNT>(S, T, stk_ref, stk_tn, stk_stride, cnt, keyfn)) {}
     best.ref = T.best;
     best.t = T.end;
+    return best;
+}
+
+// Whole-ray form of the fast path (rt_trace).  *proven = false -> the caller must trace the ray on the reference tree.
+__device__ __forceinline__ HitRec traverse_fast(const SceneDev& S, float3 o, float3 d, float start, float end_in, uint32_t* stk_ref,
+                                                float* stk_tn, uint32_t stk_stride, bool* proven) {
+    Trav T;
+    HitRec best;
+    best.ref = RT_NO_HIT;
+    best.t = end_in;
+    *proven = false;
+    trav_setup(S, T, o, d, 0.0f, start, end_in);
+    if (T.exact_only) return best;
+    if (!root_gate(S, o, d, start, end_in, false)) { *proven = true; return best; }  // the reference root test itself fails
+    trav_setup_fast(S, T);
+    while (trav_round_fast<false>(S, T, (T.cur & RT_REF_LEAF) != 0u, stk_ref, stk_tn, stk_stride, nullptr)) {}
+    best.ref = T.best;
+    best.t = T.end;
+    *proven = T.best == RT_NO_HIT || (!(T.dpos & RT_TIE_BIT) && ref_visible(S, T.best, o, d, T.end));
     return best;
 }
 

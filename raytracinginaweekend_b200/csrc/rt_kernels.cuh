@@ -20,6 +20,8 @@ struct Counters {
     unsigned long long paths;  // camera samples generated so far
     unsigned long long node_visits, prim_tests, exact_steps;  // only maintained by the COUNT kernel variant
     unsigned long long rounds, busy_lanes, tail_rounds, tail_busy_lanes;  // COUNT: warp rounds / busy lanes, overall and after the queue ran dry
+    uint32_t n_redo, cursor_redo;      // row f4: rays of this iteration the fast traversal could not prove -> reference traversal
+    unsigned long long redo_total;
 };
 
 struct RenderDev {
@@ -29,6 +31,7 @@ struct RenderDev {
     int32_t* D[2];  // remaining depth
     float* Tm[2];   // Ray::time of the path (camera.rs:185-190); NULL when the scene has no Animation leaf
     uint2* hits;    // (child ref of closest primitive | RT_NO_HIT, bits(t)) per queue position
+    uint32_t* redo; // [cap] queue positions to trace again on the reference tree (traversal MODE 3 only)
     float4* acc;    // [n_local_lanes * npix] running per-lane sums (exclusive owner: the slot's single live path)
     Counters* ctr;
     uint32_t cap;            // queue capacity = number of path slots of THIS pipeline
@@ -131,16 +134,18 @@ __device__ __forceinline__ uint32_t queue_pos(uint32_t i, uint32_t nb, uint32_t 
 // Closest hit for every live path of queue `q`.  Persistent warps: every lane owns one ray's traversal state and,
 // when fewer than `refill_threshold` lanes are still busy, the idle lanes pull fresh rays with one warp-aggregated
 // atomic — rays differ by 100x in node visits, so waiting for the slowest lane would idle most of the warp.
-template <int MODE, bool COUNT, int FEAT>
+// MODE 3 (row f4): fast traversal of the rebuilt topology + proof that the reference returns the same element; unproven rays
+// go to R.redo and a second launch (REDO = true: MODE 2 over that list) traces them on the reference tree.
+template <int MODE, bool COUNT, int FEAT, bool REDO = false>
 __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
     extern __shared__ uint32_t smem[];
     uint32_t* stk_ref = smem + threadIdx.x;
     float* stk_tn = reinterpret_cast<float*>(smem + S.stack_cap * blockDim.x) + threadIdx.x;
-    const uint32_t nb = R.ctr->nb[q], n = nb + R.ctr->nn[q];
+    const uint32_t nb = R.ctr->nb[q], n = REDO ? R.ctr->n_redo : nb + R.ctr->nn[q];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xFFFFFFFFu;
     const float INF = __int_as_float(0x7f800000);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { R.ctr->nb[q ^ 1] = 0; R.ctr->nn[q ^ 1] = 0; }  // nobody touches them during extend
+    if (!REDO && blockIdx.x == 0 && threadIdx.x == 0) { R.ctr->nb[q ^ 1] = 0; R.ctr->nn[q ^ 1] = 0; }  // nobody touches them during extend
     TravCount tc;
     tc.nodes = 0; tc.prims = 0; tc.exact = 0;
     Trav T;
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
         if (act_mask != FULL && !(exhausted && batch_next == batch_end) && (uint32_t)__popc(act_mask) < R.refill_threshold) {
             if (batch_next == batch_end) {
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&R.ctr->cursor_extend, 32u);
+                if (lane == 0) base = atomicAdd(REDO ? &R.ctr->cursor_redo : &R.ctr->cursor_extend, 32u);
                 base = __shfl_sync(FULL, base, 0);
                 batch_next = min(base, n);
                 batch_end = min(base + 32u, n);
@@ -164,13 +169,21 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
             const uint32_t avail = batch_end - batch_next;
             const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
             if (!active && rank < avail) {
-                my_pos = queue_pos(batch_next + rank, nb, R.cap);
+                my_pos = REDO ? R.redo[batch_next + rank] : queue_pos(batch_next + rank, nb, R.cap);
                 const float4 a = R.A[q][my_pos], b = R.B[q][my_pos];
                 if (__float_as_uint(b.w) & RT_ROOT_MISS) {
                     R.hits[my_pos] = make_uint2(RT_NO_HIT, __float_as_uint(INF));
                 } else {
                     trav_setup(S, T, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), R.Tm[q] ? R.Tm[q][my_pos] : 0.0f, 0.001f, INF);
                     active = true;
+                    if (MODE == 3) {
+                        if (T.exact_only) {  // zero / denormal / non-finite direction component: reference traversal only
+                            R.redo[atomicAdd(&R.ctr->n_redo, 1u)] = my_pos;
+                            active = false;
+                        } else {
+                            trav_setup_fast(S, T);
+                        }
+                    }
                 }
             }
             batch_next += min(avail, (uint32_t)__popc(idle));
@@ -188,8 +201,14 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
         const uint32_t n_leaf = __popc(__ballot_sync(FULL, active && (T.cur & RT_REF_LEAF)));
         const bool do_leaf = n_leaf * R.leaf_weight > ((uint32_t)__popc(act_mask) - n_leaf) * 16u;
         if (active) {
-            if (!trav_round<MODE, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos})) {
-                R.hits[my_pos] = make_uint2(T.best, __float_as_uint(T.end));
+            bool more;
+            if constexpr (MODE == 3) more = trav_round_fast<COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc);
+            else more = trav_round<MODE, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
+            if (!more) {
+                if (MODE == 3 && T.best != RT_NO_HIT && ((T.dpos & RT_TIE_BIT) || !ref_visible(S, T.best, T.o, T.d, T.end)))
+                    R.redo[atomicAdd(&R.ctr->n_redo, 1u)] = my_pos;
+                else
+                    R.hits[my_pos] = make_uint2(T.best, __float_as_uint(T.end));
                 active = false;
             }
         }
@@ -220,6 +239,9 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         R.ctr->cursor_extend = 0;
+        R.ctr->redo_total += R.ctr->n_redo;
+        R.ctr->n_redo = 0;
+        R.ctr->cursor_redo = 0;
         R.ctr->rays += n;
         if (R.iter_log) {  // [iter] live paths, [CAP + 2 iter] cumulative node visits (lo/hi), [3 CAP + 2 iter] cumulative prim tests
             R.iter_log[R.iter] = n;
@@ -483,7 +505,19 @@ __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ SceneDev 
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]);
         float3 d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
-        HitRec h = traverse<MODE, false>(S, o, d, S.trace_time, t_min, t_max, stk_ref, stk_tn, blockDim.x, TraceKey{i});
+        HitRec h;
+        bool proven = false;
+        // Ray::new debug_asserts a unit direction (ray.rs:13) and SphereGeometry::hit relies on it (no d.d term): for a caller
+        // ray outside that contract the reference arithmetic is not the geometric intersection, so no true-bound cull applies
+        const float dd = dot3(d, d);
+        if (MODE != 0 && !(fabsf(dd - 1.0f) <= 1e-5f)) {
+            h = traverse<0, false>(S, o, d, S.trace_time, t_min, t_max, stk_ref, stk_tn, blockDim.x, TraceKey{i});
+        } else if constexpr (MODE == 3) {
+            if (S.nodes2) h = traverse_fast(S, o, d, t_min, t_max, stk_ref, stk_tn, blockDim.x, &proven);
+            if (!proven) h = traverse<2, false>(S, o, d, S.trace_time, t_min, t_max, stk_ref, stk_tn, blockDim.x, TraceKey{i});
+        } else {
+            h = traverse<MODE, false>(S, o, d, S.trace_time, t_min, t_max, stk_ref, stk_tn, blockDim.x, TraceKey{i});
+        }
         if (h.ref != RT_NO_HIT) {
             Interaction hi = make_interaction(S, h.ref, h.t, o, d, S.trace_time, true);
             if (hit_id) hit_id[i] = h.ref & RT_REF_ITEM_MASK;

@@ -30,7 +30,7 @@ def product_world(name):
 
 @pytest.fixture(autouse=True)
 def default_options():
-    for k, v in (("traversal", 2), ("count", 0), ("profile", 0)):
+    for k, v in (("traversal", 3), ("count", 0), ("profile", 0)):
         _cabi.set_option(k, v)
     yield
 
@@ -64,7 +64,7 @@ def test_golden_hits_and_replay_image(path):
 
 
 # ---------------------------------------------------------------- Scene::hit parity, all traversal variants
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("name", CONFIGS + ["demo:suzanne", "demo:earth_mapped", "demo:cornell_box", "demo:moving_spheres",
                                             "demo:cornell_box_smoke", "demo:perlin_spheres", "demo:final_scene2"])
 def test_trace_parity_vs_oracle(name, mode, oracle_world):
@@ -103,7 +103,7 @@ def test_trace_parity_random_scenes(seed, oracle):
     tm = 0.37 if f2 else 0.0
     for org, dir in (random_rays(fs, 30000, seed), adversarial_rays(fs, 1500, seed)):
         ref = o.trace(org, dir, time=tm)
-        for mode in (0, 2):
+        for mode in (0, 2, 3):
             _cabi.set_option("traversal", mode)
             r = assert_hits_match(w.hit(org, dir, time=tm), ref)
             assert r["t_bit_mismatch"] == 0 and r["normal_bit_mismatch"] == 0, (mode, r)
@@ -146,7 +146,7 @@ def test_flat_nodes_are_never_entered(oracle):
     w, o = rb.World.from_elements(**sc), oracle.OracleWorld.from_flat(**sc)
     org = np.array([[0.3, 0.3, 0], [5.3, 0.3, 0]], F32); dir = np.array([[0, 0, -1], [0, 0, -1]], F32)
     ref = o.trace(org, dir)
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         _cabi.set_option("traversal", mode)
         assert_hits_match(w.hit(org, dir), ref)
     assert ref["hit_id"][0] == MISS and ref["hit_id"][1] != MISS
@@ -291,6 +291,60 @@ def test_traversal_variants_agree_at_full_size():
     _cabi.set_option("traversal", 0)
     b, sb = rb.render(size, 1, 1, 50, w, seed=11, return_stats=True)
     assert sa["ray_segments"] == sb["ray_segments"] and images_equal_bits(a, b)
+    _cabi.set_option("traversal", 3)
+    c, sc = rb.render(size, 1, 1, 50, w, seed=11, return_stats=True)
+    assert sc["ray_segments"] == sb["ray_segments"] and images_equal_bits(c, b)
+    assert 0 < sc["redo_rays"] < 0.05 * sc["ray_segments"], sc   # a few rays per cent need the reference tree; never zero on 3M rays
+
+
+@pytest.mark.parametrize("name,size", [("config:c1", (600, 400)), ("config:c3", (256, 256)), ("config:c5", (240, 135)), ("demo:suzanne", (200, 150)),
+                                       ("demo:simple_plane", (160, 90)), ("demo:defocus_blur", (300, 200))])
+def test_rebuilt_topology_gives_the_reference_film(name, size):
+    """Row f4: traversal 3 (rebuilt SAH topology + per-ray proof + redo on the reference tree) vs traversal 0 (the reference's
+    own node test on the reference's own tree): same ray count, bit-identical film, on every plain scene family."""
+    w = product_world(name)
+    _cabi.set_option("traversal", 0)
+    a, sa = rb.render(rb.Size2i(*size), 2, 4, 50, w, seed=5, return_stats=True)
+    _cabi.set_option("traversal", 3)
+    b, sb = rb.render(rb.Size2i(*size), 2, 4, 50, w, seed=5, return_stats=True)
+    assert sa["ray_segments"] == sb["ray_segments"] and images_equal_bits(a, b)
+    assert sb["redo_rays"] <= 0.25 * sb["ray_segments"], sb
+
+
+def test_rebuilt_topology_redo_paths(oracle):
+    """The cases the proof must refuse: (a) two elements at exactly the same t (the reference's visit order decides),
+    (b) elements below a zero-thickness node (invisible in the reference), (c) hits on a face of the parent box
+    (axis-aligned triangles), (d) axis-parallel rays (zero direction components)."""
+    sc = random_scene(61, n_spheres=6, n_tris=12, n_rects=0)
+    z = -3.0
+    tri = lambda a, b, c: np.array(list(a) + list(b) + list(c) + [0, 0, 1] * 3 + [0] * 6, F32)
+    tr = np.nonzero(sc["kinds"] == 2)[0]
+    sc["geom"][tr[0]] = tri((0, 0, z), (1, 0, z), (0, 1, z))              # coplanar axis-aligned pair: may form a flat node
+    sc["geom"][tr[1]] = tri((0.1, 0.1, z), (1.1, 0.1, z), (0.1, 1.1, z))
+    sc["geom"][tr[2]] = tri((-2, -2, z - 1), (-1, -2, z - 1), (-2, -1, z - 1))  # axis-aligned single: lies on its parent's face
+    sp = np.nonzero(sc["kinds"] == 0)[0]
+    sc["geom"][sp[0], :4] = [3, 0, -5, 1]
+    sc["geom"][sp[1], :4] = [3, 0, -5, 1]                                  # coincident spheres: exact tie
+    w, o = rb.World.from_elements(**sc), oracle.OracleWorld.from_flat(**sc)
+    fs = o.export()
+    org0, dir0 = random_rays(fs, 20000, 5)
+    aim = np.array([[0.3, 0.3, z], [0.5, 0.4, z], [-1.7, -1.8, z - 1], [3, 0, -5], [3.2, 0.1, -5]], F32)
+    org1 = np.tile(np.array([[0.2, 0.1, 4.0]], F32), (len(aim), 1)); dir1 = aim - org1
+    dir1 = np.concatenate([dir1, (dir1 / np.linalg.norm(dir1, axis=1, keepdims=True)).astype(F32)]); org1 = np.concatenate([org1, org1])
+    # (the un-normalised copies are outside Ray::new's contract: the sphere test has no d.d term, so the reference arithmetic is
+    #  not the geometric hit there; rt_trace must still reproduce it, which it does by using the reference rule alone)
+    org2 = aim + np.array([0, 0, 6], F32); dir2 = np.tile(np.array([[0, 0, -1]], F32), (len(aim), 1))   # axis-parallel
+    org, dir = np.concatenate([org0, org1, org2]), np.concatenate([dir0, dir1, dir2])
+    ref = o.trace(org, dir)
+    for mode in (2, 3):
+        _cabi.set_option("traversal", mode)
+        r = assert_hits_match(w.hit(org, dir), ref)
+        assert r["t_bit_mismatch"] == 0 and r["normal_bit_mismatch"] == 0, (mode, r)
+    _cabi.set_option("traversal", 3)
+    ref_img, st = o.render(64, 48, 6, 20, 2, 9, "replay")
+    img, gst = rb.render(rb.Size2i(64, 48), 2, 6, 20, w, seed=9, return_stats=True)
+    assert gst["ray_segments"] == st["rays"] and images_equal_bits(img, ref_img)
+    assert gst["redo_rays"] > 0
 
 
 def test_lane_count_only_changes_summation_order():
