@@ -227,14 +227,18 @@ def main():
     pinned = torch.empty((size.height, size.width, 3), dtype=torch.float32).pin_memory()
     barrier()
     e2e_ms, e2e_rays = 0.0, 0.0
-    for i in range(max(1, min(args.steps, 3))):
+    e2e_steps = []
+    for i in range(-1, max(1, min(args.steps, 3))):   # i = -1: one untimed warm-up of this code path (first-use allocations)
         t0 = time.perf_counter()
         world.release_device()
         film, st = rdist.render_distributed(world, size, lanes_total, spp_total, MAX_DEPTH, rb.RenderMode.Default, 300 + i,
                                             device=dev, return_stats=True)
         pinned.copy_(film, non_blocking=False)
         torch.cuda.synchronize(dev)
-        e2e_ms += (time.perf_counter() - t0) * 1e3
+        if i < 0:
+            continue
+        e2e_steps.append((time.perf_counter() - t0) * 1e3)
+        e2e_ms += e2e_steps[-1]
         e2e_rays += st["ray_segments"]
     scene = world.device_scene(local_rank)
     t_e = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -284,7 +288,7 @@ def main():
             "fp32": {"kernel": "k_extend", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
                      "nodes_per_ray": nodes_per_ray, "prims_per_ray": prims_per_ray, "flops_per_ray": flops_per_ray,
                      "note": "algorithmic flops (SURVEY 8d: 30 per box test, 41 per primitive test); peak = SMs x 128 lanes x max SM clock, no FMA"},
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": world.upload_bytes(),
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": [round(x, 2) for x in e2e_steps], "h2d_bytes_per_step": world.upload_bytes(),
                     "d2h_bytes_per_step": size.count() * 12, "note": "rt_scene_create (scene hand-off) + render + film read-back to pinned host memory, every step"},
             "clocks": clocks, "gpu_launches": int(sum(s["kernel_launches"] for s in stats)) + args.steps,
         }

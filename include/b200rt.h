@@ -167,7 +167,7 @@ typedef struct RtStats {
     uint64_t node_visits;    /* BVH node fetches (64 B each) — only with rt_set_option("count", 1) */
     uint64_t prim_tests;     /* primitive intersection tests    — only with rt_set_option("count", 1) */
     uint64_t exact_steps;    /* node steps that fell back to true divisions — only with rt_set_option("count", 1) */
-    uint64_t redo_rays;      /* traversal 3: rays the fast topology could not prove, traced again on the reference tree */
+    uint64_t redo_rays;      /* traversal 3: rays the fast topology could not prove, traced again on the reference tree — only with "count" */
 } RtStats;
 
 typedef struct RtScene RtScene;

@@ -29,6 +29,7 @@ namespace {
 thread_local std::string g_err;
 int g_opt_traversal = 3;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path,
                               // 3 = rebuilt topology + per-ray proof, unproven rays on the reference tree with 2 (plain scenes; else 2)
+int g_opt_fast_order = 0;     // experiment: child order of the fast traversal (0 near-first, 1 split-axis sign, 2 near-first, ties by sign)
 int g_opt_rebuild = 1;        // build the second topology at rt_scene_create (0: traversal 3 behaves like 2)
 int g_opt_rebuild_depth_extra = 3;  // depth cap of the rebuilt tree = reference depth + this (the stack lives in shared memory)
 int g_opt_pipes = 1;         // independent wavefront pipelines (streams) per render: one pipeline's extend tail overlaps the other's work
@@ -79,7 +80,6 @@ struct Workspace {
     DevBuf<int32_t> D[2];
     DevBuf<float> Tm[2];
     DevBuf<uint2> hits;
-    DevBuf<uint32_t> redo;
     DevBuf<Counters> ctr;
     DevBuf<float> film;
     static const int MAX_PIPES = 8;
@@ -401,7 +401,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
             nd.q0 = make_float4(bl.mn[0], bl.mn[1], bl.mn[2], bl.mx[0]);
             nd.q1 = make_float4(bl.mx[1], bl.mx[2], br.mn[0], br.mn[1]);
             nd.q2 = make_float4(br.mn[2], br.mx[0], br.mx[1], br.mx[2]);
-            nd.q3 = make_uint4(ref2(F.left[i]), ref2(F.right[i]), 0u, pack_margin(a2[i], c2[i]));
+            nd.q3 = make_uint4(ref2(F.left[i]), ref2(F.right[i]), F.axis[i], pack_margin(a2[i], c2[i]));
             nodes2[i] = nd;
         }
         root2 = ref2(F.root);
@@ -568,7 +568,6 @@ int ensure_workspace(Workspace& sc, size_t slots, size_t npix, bool need_time) {
             sc.Tm[q].release();
         }
         CU(sc.hits.alloc(slots));
-        CU(sc.redo.alloc(slots));
         CU(sc.acc.alloc(slots));
         sc.ws_slots = slots;
     }
@@ -641,6 +640,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     R.ref_only = g_opt_traversal == 0 ? 1u : 0u;
     R.refill_threshold = (uint32_t)std::min(32, std::max(1, g_opt_refill));
     R.leaf_weight = (uint32_t)std::max(1, g_opt_leaf_weight);
+    R.fast_order = (uint32_t)g_opt_fast_order;
 
     // Split the rank's lanes over G independent wavefront pipelines, each on its own stream with its own queues and
     // counters.  A persistent extend launch ends with a tail in which a few very long rays keep a few warps busy; with two
@@ -671,7 +671,6 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
                 pp.R.Tm[q] = sc.has_animation ? ws.Tm[q].p + off : nullptr;
             }
             pp.R.hits = ws.hits.p + off;
-            pp.R.redo = ws.redo.p + off;
             pp.R.ctr = ws.ctr.p + p;
             pp.st = ws.pipe_stream[p];
             pp.R.iter_log = iter_log_path ? ws.iter_log.p + (size_t)p * Workspace::ITER_LOG_CAP * 8 : nullptr;
@@ -686,15 +685,9 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     if (mode == 3 && !sc.nodes2.p) mode = 2;  // no rebuilt topology for this scene (wrapped elements, single element, rebuild off)
     ExtendFn ext = mode == 3 ? (g_opt_count ? k_extend<3, true, 0> : k_extend<3, false, 0>)
                              : pick_extend(mode, g_opt_count != 0, sc.has_volume ? 2 : (sc.has_wrapped ? 1 : 0));
-    ExtendFn ext_redo = g_opt_count ? k_extend<2, true, 0, true> : k_extend<2, false, 0, true>;
     rc = persistent_grid(sc, ext, eblock, esmem, &egrid);
     if (rc) return rc;
-    int rgrid = 0;
-    if (mode == 3) {
-        rc = persistent_grid(sc, ext_redo, eblock, esmem, &rgrid);
-        if (rc) return rc;
-        rgrid = std::max(1, rgrid / 4);  // the redo list is a small fraction of an iteration's rays
-    }
+
     rc = persistent_grid(sc, k_shade, 128, 0, &sgrid);
     if (rc) return rc;
 
@@ -733,7 +726,6 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
             if (pe) CU(cudaEventRecord(pe[0], pp.st));
             pp.R.iter = (uint32_t)std::min<uint64_t>(pp.iters, Workspace::ITER_LOG_CAP - 1);
             ext<<<egrid, eblock, esmem, pp.st>>>(sc.dev, pp.R, pp.q);
-            if (mode == 3) { ext_redo<<<rgrid, eblock, esmem, pp.st>>>(sc.dev, pp.R, pp.q); ++launches; }
             if (pe) CU(cudaEventRecord(pe[1], pp.st));
             k_shade<<<sgrid, 128, 0, pp.st>>>(sc.dev, pp.R, pp.q);
             if (pe) CU(cudaEventRecord(pe[2], pp.st));
@@ -858,6 +850,7 @@ int rt_set_option(const char* key, int64_t value) {
     std::string k(key);
     if (k == "traversal") g_opt_traversal = (int)value;
     else if (k == "rebuild") g_opt_rebuild = (int)value;
+    else if (k == "fast_order") g_opt_fast_order = (int)value;
     else if (k == "rebuild_depth_extra") g_opt_rebuild_depth_extra = (int)value;
     else if (k == "profile") g_opt_profile = (int)value;
     else if (k == "count") g_opt_count = (int)value;

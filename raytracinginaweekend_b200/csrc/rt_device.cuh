@@ -363,6 +363,7 @@ struct HitRec {
 };
 struct TravCount {
     uint32_t nodes, prims, exact;  // node visits (64 B fetches), primitive tests, exact-fallback node steps
+    uint32_t redo;                 // traversal 3: rays restarted on the reference tree
 };
 struct Trav {
     float3 o, d;
@@ -384,10 +385,25 @@ struct Trav {
 // delta / |d_i| in t, so the gap that proves "misses the box padded by eps" is eps * (1/|d_j| + 1/|d_k|) <= eps * mscale
 // with mscale = 2 * max_i |1/d_i| (per ray).  Near-axis-parallel rays therefore (correctly) lose the tight cull:
 // they can slide along a box face within rounding distance of it.
-__device__ __forceinline__ float node_margin(uint32_t packed, float t, float mscale) {
-    float a = __uint_as_float(packed & 0xFFFF0000u), c = __uint_as_float(packed << 16);
-    float at = fabsf(t);
-    return (a + at * (1e-5f + c * at)) * mscale;
+//
+// Where to evaluate eps: an accepted hit at parameter t needs  t - g(t) <= tf  and  t + g(t) >= tn  with g(t) = eps(t) max_i|1/d_i|
+// (every slab interval, padded, must contain t).  g grows with t, so the band must be taken at the LARGEST feasible t, which
+// is near the interval's EXIT tf, not its entry tn: if g' <= 1/2 up to te = tf' + 2 g(tf') (tf' = max(tf, start)), then every
+// feasible t is <= te, hence g(t) <= g(te) and the child can be skipped iff  tn - tf > 2 g(te).  (A ray nearly parallel to a
+// slab has a huge tn for a box it misses; evaluating the quadratic sphere term there would make the band useless.)
+// If g' > 1/2 at te (grazing rays, huge distances) the band is infinite: no tight cull.
+// G2(t) := 2 g(t) = sA + t (sB + sC t)  with sA = A mscale (+ approximation error), sB = 1e-5 mscale, sC = C mscale.
+// Independently of that, every accepted t is < end, so G2(end) is always a valid band once a hit has made end finite.
+__device__ __forceinline__ float guard_band(float sA, float sB, float sC, float tf, float start, float end) {
+    const float tfp = fmaxf(tf, start);
+    const float te = tfp + __fmaf_rn(tfp, __fmaf_rn(sC, tfp, sB), sA);
+    const float mg = __fmaf_rn(te, __fmaf_rn(sC, te, sB), sA);
+    const float at_end = __fmaf_rn(end, __fmaf_rn(sC, end, sB), sA);  // +inf (or NaN from 0 * inf, ignored by fminf) while end = inf
+    return fminf((__fmaf_rn(2.0f * sC, te, sB) <= 1.0f) ? mg : __int_as_float(0x7f800000), at_end);  // NaN compares false: no cull
+}
+__device__ __forceinline__ float node_margin(uint32_t packed, float tf, float start, float end, float mscale) {
+    const float a = __uint_as_float(packed & 0xFFFF0000u), c = __uint_as_float(packed << 16);
+    return guard_band(a * mscale, 1e-5f * mscale, c * mscale, tf, start, end);
 }
 
 // Root box test of BoundingVolumeHierarchy::hit (hittable.rs:472 -> hit_recursive(initial_index)): the reference rule, plus the
@@ -399,7 +415,7 @@ __device__ __forceinline__ bool root_gate(const SceneDev& S, float3 o, float3 d,
     bool pass = r.ref_pass;
     if (!ref_only) {
         const float mscale = 2.0f * fmaxf(fmaxf(fabsf(1.0f / d.x), fabsf(1.0f / d.y)), fabsf(1.0f / d.z));
-        pass = pass && !(r.tn - r.tf > node_margin(S.root_margin, r.tn, mscale));
+        pass = pass && !(r.tn - r.tf > node_margin(S.root_margin, r.tf, start, end, mscale));
     }
     return pass;
 }
@@ -437,6 +453,50 @@ __device__ __forceinline__ void approx_slab(float mnx, float mny, float mnz, flo
     tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), T.end));
 }
 
+// Second-chance tight cull, decisive for rays that run nearly parallel to an axis.  For them the scalar band
+// eps * 2 max|1/d_i| is useless, and the reference's own rule is per-axis independent (Q1): it never intersects the slab
+// intervals, so without a hit yet (end = inf) such a ray walks most of the tree — a handful of these rays set the duration
+// of a whole launch.  Here every axis is padded with ITS OWN eps |1/d_i|: an accepted hit at t satisfies
+// lo_i - eps(t)|1/d_i| <= t <= hi_i + eps(t)|1/d_i| on every axis (the hit point is within eps(t) of the element's true box),
+// and t <= te := min(end, min_i(hi_i' + 2 g_i(hi_i'))) over the axes where g_i = eps |1/d_i| has slope <= 1/2.
+// Returns true when the padded intervals do not intersect; tn_pad = padded entry (a valid pop threshold: t >= tn_pad).
+__device__ __forceinline__ float padded_exit_bound(float h, float i, float a, float c, float start) {
+    const float hp = fmaxf(h, start);
+    const float te = __fmaf_rn(2.0f * i, __fmaf_rn(hp, __fmaf_rn(c, hp, 1e-5f), a), hp);
+    return (i * __fmaf_rn(2.0f * c, te, 1e-5f) <= 0.5f) ? te : __int_as_float(0x7f800000);
+}
+struct PadRay {  // the ray fields padded_cull needs, by value (the function is deliberately not inlined: it is the rare path)
+    float3 inv, oinv;
+    float start, end, oe;
+};
+__device__ __noinline__ float padded_cull_impl(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, PadRay T, uint32_t packed) {
+    const float a = __uint_as_float(packed & 0xFFFF0000u), c = __uint_as_float(packed << 16);
+    const float ax = __fmaf_rn(mnx, T.inv.x, T.oinv.x), bx = __fmaf_rn(mxx, T.inv.x, T.oinv.x);
+    const float ay = __fmaf_rn(mny, T.inv.y, T.oinv.y), by = __fmaf_rn(mxy, T.inv.y, T.oinv.y);
+    const float az = __fmaf_rn(mnz, T.inv.z, T.oinv.z), bz = __fmaf_rn(mxz, T.inv.z, T.oinv.z);
+    const float lx = fminf(ax, bx), hx = fmaxf(ax, bx), ly = fminf(ay, by), hy = fmaxf(ay, by), lz = fminf(az, bz), hz = fmaxf(az, bz);
+    const float ix = fabsf(T.inv.x), iy = fabsf(T.inv.y), iz = fabsf(T.inv.z);
+    float te = T.end;
+    te = fminf(te, padded_exit_bound(hx, ix, a, c, T.start));
+    te = fminf(te, padded_exit_bound(hy, iy, a, c, T.start));
+    te = fminf(te, padded_exit_bound(hz, iz, a, c, T.start));
+    const float eps_e = __fmaf_rn(te, __fmaf_rn(c, te, 1e-5f), a);  // inf / NaN when te = inf: fmaxf / fminf then drop the padded terms
+    // error of an approximate slab distance: T.oe (absolute part, already doubled) + 1e-6 relative (>= 8 ulp)
+    const float px = __fmaf_rn(eps_e, ix, T.oe), py = __fmaf_rn(eps_e, iy, T.oe), pz = __fmaf_rn(eps_e, iz, T.oe);
+    const float nx = lx - __fmaf_rn(RT_BAND, fabsf(lx), px), ny = ly - __fmaf_rn(RT_BAND, fabsf(ly), py), nz = lz - __fmaf_rn(RT_BAND, fabsf(lz), pz);
+    const float fx = hx + __fmaf_rn(RT_BAND, fabsf(hx), px), fy = hy + __fmaf_rn(RT_BAND, fabsf(hy), py), fz = hz + __fmaf_rn(RT_BAND, fabsf(hz), pz);
+    const float tn_pad = fmaxf(fmaxf(nx, ny), fmaxf(nz, T.start));
+    const float tf_pad = fminf(fminf(fx, fy), fminf(fz, T.end));
+    return tn_pad > tf_pad ? __int_as_float(0x7f800000) : tn_pad;  // +inf = culled, else the padded entry
+}
+__device__ __forceinline__ bool padded_cull(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const Trav& T,
+                                            uint32_t packed, float& tn_pad) {
+    PadRay r;
+    r.inv = T.inv; r.oinv = T.oinv; r.start = T.start; r.end = T.end; r.oe = T.oe;
+    tn_pad = padded_cull_impl(mnx, mny, mnz, mxx, mxy, mxz, r, packed);
+    return tn_pad == __int_as_float(0x7f800000);
+}
+
 // One scheduling round of a lane: a node step (if `do_leaf` is false and the lane is at an internal node) or a leaf
 // step (if `do_leaf` is true and the lane is at a leaf), followed by the pops it triggers; lanes in the other state
 // simply wait.  The warp picks `do_leaf` by vote (k_extend), so each phase runs with most lanes enabled instead of
@@ -467,9 +527,21 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
             approx_slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, tnR, tfR);
             // guard band in t (tn >= start >= 0 here): (A + 1e-5 t + C t^2) * mscale, plus the approximation error
             const float sA = __fmaf_rn(__uint_as_float(q3.w & 0xFFFF0000u), T.mscale, T.oe), sC = __uint_as_float(q3.w << 16) * T.mscale;
-            mgL = __fmaf_rn(tnL, __fmaf_rn(sC, tnL, T.sB), sA);
-            mgR = __fmaf_rn(tnR, __fmaf_rn(sC, tnR, T.sB), sA);
-            const bool cullL = tnL - tfL > mgL, cullR = tnR - tfR > mgR;
+            mgL = guard_band(sA, T.sB, sC, tfL, T.start, T.end);
+            mgR = guard_band(sA, T.sB, sC, tfR, T.start, T.end);
+            bool cullL = tnL - tfL > mgL, cullR = tnR - tfR > mgR;
+            // second chance for a child whose carried interval is empty, but by less than the scalar band: the per-axis padded
+            // test (strictly tighter; rare for ordinary rays, the normal case for rays nearly parallel to an axis)
+            if (!cullL && tnL > tfL) {
+                float pn;
+                cullL = padded_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T, q3.w, pn);
+                mgL = tnL - pn;  // a leaf entry is pushed with threshold tn - mg = the padded entry
+            }
+            if (!cullR && tnR > tfR) {
+                float pn;
+                cullR = padded_cull(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, q3.w, pn);
+                mgR = tnR - pn;
+            }
             // carried interval non-empty beyond rounding => the per-axis reference rule passes too
             const bool sureL = leafL || (tfL - tnL > __fmaf_rn(RT_BAND, tfL + tnL, T.oe));
             const bool sureR = leafR || (tfR - tnR > __fmaf_rn(RT_BAND, tfR + tnR, T.oe));
@@ -487,11 +559,11 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
             pL = leafL ? true : sl.ref_pass;
             pR = leafR ? true : sr.ref_pass;
             if (MODE >= 1) {
-                pL = pL && !(sl.tn - sl.tf > node_margin(q3.w, sl.tn, T.mscale));
-                pR = pR && !(sr.tn - sr.tf > node_margin(q3.w, sr.tn, T.mscale));
+                pL = pL && !(sl.tn - sl.tf > node_margin(q3.w, sl.tf, T.start, T.end, T.mscale));
+                pR = pR && !(sr.tn - sr.tf > node_margin(q3.w, sr.tf, T.start, T.end, T.mscale));
             }
             tnL = sl.tn; tnR = sr.tn;
-            if (MODE >= 1) { mgL = node_margin(q3.w, tnL, T.mscale); mgR = node_margin(q3.w, tnR, T.mscale); }
+            if (MODE >= 1) { mgL = node_margin(q3.w, sl.tf, T.start, T.end, T.mscale); mgR = node_margin(q3.w, sr.tf, T.start, T.end, T.mscale); }
         }
         const bool left_first = ((T.dpos >> q3.z) & 1u) != 0u;  // dir[axis_id] > 0, hittable.rs:441-445
         const uint32_t c1 = left_first ? q3.x : q3.y, c2 = left_first ? q3.y : q3.x;
@@ -546,7 +618,8 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
 //   * children are visited near-first (the reference orders by the sign of dir[axis_id]; irrelevant here).
 // The caller accepts the result only if !tie and ref_visible(); everything else is traced again on the reference tree.
 // ------------------------------------------------------------------------------------------------
-#define RT_TIE_BIT 8u  // kept in Trav::dpos (bits 0..2 are unused by the fast traversal)
+#define RT_TIE_BIT 8u  // kept in Trav::dpos next to the direction signs (bits 0..2)
+#define RT_ORDER_SHIFT 5u  // experiment: child-order policy in bits 5..6 of Trav::dpos
 
 template <bool COUNT>
 __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool do_leaf, uint32_t* stk_ref, float* stk_tn,
@@ -579,10 +652,22 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
         approx_slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T, tnL, tfL);
         approx_slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, tnR, tfR);
         const float sA = __fmaf_rn(__uint_as_float(q3.w & 0xFFFF0000u), T.mscale, T.oe), sC = __uint_as_float(q3.w << 16) * T.mscale;
-        const float mgL = __fmaf_rn(tnL, __fmaf_rn(sC, tnL, T.sB), sA);
-        const float mgR = __fmaf_rn(tnR, __fmaf_rn(sC, tnR, T.sB), sA);
-        const bool pL = !(tnL - tfL > mgL), pR = !(tnR - tfR > mgR);
-        const bool left_first = tnL <= tnR;
+        float mgL = guard_band(sA, T.sB, sC, tfL, T.start, T.end);
+        float mgR = guard_band(sA, T.sB, sC, tfR, T.start, T.end);
+        bool pL = !(tnL - tfL > mgL), pR = !(tnR - tfR > mgR);
+        if (pL && tnL > tfL) {  // empty by less than the scalar band: per-axis padded second chance (see padded_cull)
+            float pn;
+            pL = !padded_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T, q3.w, pn);
+            mgL = tnL - pn;
+        }
+        if (pR && tnR > tfR) {
+            float pn;
+            pR = !padded_cull(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, q3.w, pn);
+            mgR = tnR - pn;
+        }
+        const bool sign_first = ((T.dpos >> q3.z) & 1u) != 0u;  // dir[split axis] > 0: the lower-centroid (left) child lies behind
+        const uint32_t policy = (T.dpos >> RT_ORDER_SHIFT) & 3u;
+        const bool left_first = policy == 1u ? sign_first : (policy == 2u ? (tnL < tnR || (tnL == tnR && sign_first)) : tnL <= tnR);
         const uint32_t c1 = left_first ? q3.x : q3.y, c2 = left_first ? q3.y : q3.x;
         const bool p1 = left_first ? pL : pR, p2 = left_first ? pR : pL;
         if (p1 && p2) {
@@ -608,26 +693,32 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
 }
 
 // Can the fast traversal be used for this ray at all?  (finite, non-degenerate direction; see trav_setup)
-__device__ __forceinline__ bool fast_eligible(const SceneDev& S, const Trav& T) { return S.nodes2 != nullptr && !T.exact_only; }
-__device__ __forceinline__ void trav_setup_fast(const SceneDev& S, Trav& T) { T.cur = S.root2; T.dpos = 0u; }
+// Can the fast traversal be used for this ray?  Not for degenerate directions (zero / denormal / non-finite components,
+// trav_setup): the approximate slab arithmetic is not defined for them; the reference tree's exact path is.
+__device__ __forceinline__ bool fast_eligible(const Trav& T) { return !T.exact_only; }
+__device__ __forceinline__ void trav_setup_fast(const SceneDev& S, Trav& T, uint32_t policy = 0u) {
+    T.cur = S.root2;
+    T.dpos = (T.dpos & 7u) | (policy << RT_ORDER_SHIFT);
+}
 
 // Does the reference traversal provably return element `ref` at `t` (given that it is the UNIQUE minimum of all accepted
 // candidates)?  The reference reaches the element iff every ancestor A passes Aabb::hit_cond for the range [start, e) with
 // some e > t.  Per axis that holds when t lies strictly between the two slab distances the reference computes,
-// t0 = rn(rn(A.lo - o) / d) and t1 likewise: sufficient is that p = o + t d lies inside A by more than
-// 2^-22 (|A.lo| + |o| + |p|) on that axis (three roundings of 2^-24 each); we ask for 1e-6 (4x).
-// Ancestor boxes are nested (exact unions), and the margin grows slower than the distance when a face moves outward, so
-// the test against the PARENT's box covers the whole chain.  Flat parents (zero thickness, invisible in the reference,
-// aabb.rs:73) can never pass.  A failure proves nothing: the ray is simply traced on the reference tree.
+// t0 = rn(rn(X - o) / d) for the entry face X (and t1 likewise).  With p = rn(o + rn(t d)) (four roundings of 2^-24 in
+// total between the two sides) a sufficient condition is  p - X > 3.2 * 2^-24 (|X| + |o| + |p|)  = 1.9e-7 (...); we ask for
+// 4e-7 on both faces of every axis.  Ancestor boxes are nested (exact unions) and the margin grows slower
+// than the distance when a face moves outward (c < 1), so the test against the PARENT's box covers the whole chain.  Flat
+// parents (zero thickness: invisible in the reference, aabb.rs:73) can never pass.  A failure proves nothing: the ray is
+// simply traced again on the reference tree.
 __device__ __forceinline__ bool ref_visible(const SceneDev& S, uint32_t ref, float3 o, float3 d, float t) {
     const uint32_t item = ref & RT_REF_ITEM_MASK;
     const float4 lo = __ldg(S.vis_box + 2u * item), hi = __ldg(S.vis_box + 2u * item + 1u);
-    const float c = 1e-6f;
+    const float c = 4e-7f;
     const float px = o.x + t * d.x, py = o.y + t * d.y, pz = o.z + t * d.z;
-    const float mx = c * (fabsf(lo.x) + fabsf(hi.x) + fabsf(o.x) + fabsf(px));
-    const float my = c * (fabsf(lo.y) + fabsf(hi.y) + fabsf(o.y) + fabsf(py));
-    const float mz = c * (fabsf(lo.z) + fabsf(hi.z) + fabsf(o.z) + fabsf(pz));
-    return (px - lo.x > mx) && (hi.x - px > mx) && (py - lo.y > my) && (hi.y - py > my) && (pz - lo.z > mz) && (hi.z - pz > mz);
+    const float sx = fabsf(o.x) + fabsf(px), sy = fabsf(o.y) + fabsf(py), sz = fabsf(o.z) + fabsf(pz);
+    return (px - lo.x > c * (fabsf(lo.x) + sx)) && (hi.x - px > c * (fabsf(hi.x) + sx)) &&
+           (py - lo.y > c * (fabsf(lo.y) + sy)) && (hi.y - py > c * (fabsf(hi.y) + sy)) &&
+           (pz - lo.z > c * (fabsf(lo.z) + sz)) && (hi.z - pz > c * (fabsf(hi.z) + sz));
 }
 
 template <int MODE, bool COUNT, class KEYFN>
@@ -660,7 +751,7 @@ __device__ __forceinline__ HitRec traverse_fast(const SceneDev& S, float3 o, flo
     best.t = end_in;
     *proven = false;
     trav_setup(S, T, o, d, 0.0f, start, end_in);
-    if (T.exact_only) return best;
+    if (!fast_eligible(T)) return best;
     if (!root_gate(S, o, d, start, end_in, false)) { *proven = true; return best; }  // the reference root test itself fails
     trav_setup_fast(S, T);
     while (trav_round_fast<false>(S, T, (T.cur & RT_REF_LEAF) != 0u, stk_ref, stk_tn, stk_stride, nullptr)) {}

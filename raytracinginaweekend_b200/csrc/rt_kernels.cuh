@@ -20,8 +20,7 @@ struct Counters {
     unsigned long long paths;  // camera samples generated so far
     unsigned long long node_visits, prim_tests, exact_steps;  // only maintained by the COUNT kernel variant
     unsigned long long rounds, busy_lanes, tail_rounds, tail_busy_lanes;  // COUNT: warp rounds / busy lanes, overall and after the queue ran dry
-    uint32_t n_redo, cursor_redo;      // row f4: rays of this iteration the fast traversal could not prove -> reference traversal
-    unsigned long long redo_total;
+    unsigned long long redo_total;     // row f4 (COUNT variant): rays the fast traversal could not prove -> reference traversal
 };
 
 struct RenderDev {
@@ -31,7 +30,6 @@ struct RenderDev {
     int32_t* D[2];  // remaining depth
     float* Tm[2];   // Ray::time of the path (camera.rs:185-190); NULL when the scene has no Animation leaf
     uint2* hits;    // (child ref of closest primitive | RT_NO_HIT, bits(t)) per queue position
-    uint32_t* redo; // [cap] queue positions to trace again on the reference tree (traversal MODE 3 only)
     float4* acc;    // [n_local_lanes * npix] running per-lane sums (exclusive owner: the slot's single live path)
     Counters* ctr;
     uint32_t cap;            // queue capacity = number of path slots of THIS pipeline
@@ -40,6 +38,7 @@ struct RenderDev {
     uint32_t pipe, n_pipes;  // rank-local lanes are dealt round-robin to n_pipes independent wavefront pipelines (streams)
     uint32_t refill_threshold;  // extend refills idle lanes when fewer than this many lanes are busy
     uint32_t leaf_weight;       // phase vote: leaf phase runs when n_leaf * leaf_weight > n_node * 16
+    uint32_t fast_order;        // experiment knob (traversal 3 child order)
     uint32_t npix, width, height;
     int32_t max_depth;
     uint32_t n_tasks;        // T' = lanes that got >= 1 sample (split_work_tasks)
@@ -104,6 +103,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
         R.ctr->prim_tests = 0;
         R.ctr->exact_steps = 0;
         R.ctr->rounds = 0; R.ctr->busy_lanes = 0; R.ctr->tail_rounds = 0; R.ctr->tail_busy_lanes = 0;
+        R.ctr->redo_total = 0;
     }
 }
 
@@ -134,20 +134,22 @@ __device__ __forceinline__ uint32_t queue_pos(uint32_t i, uint32_t nb, uint32_t 
 // Closest hit for every live path of queue `q`.  Persistent warps: every lane owns one ray's traversal state and,
 // when fewer than `refill_threshold` lanes are still busy, the idle lanes pull fresh rays with one warp-aggregated
 // atomic — rays differ by 100x in node visits, so waiting for the slowest lane would idle most of the warp.
-// MODE 3 (row f4): fast traversal of the rebuilt topology + proof that the reference returns the same element; unproven rays
-// go to R.redo and a second launch (REDO = true: MODE 2 over that list) traces them on the reference tree.
-template <int MODE, bool COUNT, int FEAT, bool REDO = false>
+// MODE 3 (row f4): fast traversal of the rebuilt topology + proof that the reference returns the same element; a lane whose
+// result is not proven restarts on the reference tree (MODE 2 code) in place, overlapped with the other lanes' work — a
+// separate redo launch would serialise the few longest rays of every iteration into its own tail.
+#define RT_REFMODE_BIT 16u  // Trav::dpos: this lane is (re)tracing on the reference tree
+template <int MODE, bool COUNT, int FEAT>
 __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
     extern __shared__ uint32_t smem[];
     uint32_t* stk_ref = smem + threadIdx.x;
     float* stk_tn = reinterpret_cast<float*>(smem + S.stack_cap * blockDim.x) + threadIdx.x;
-    const uint32_t nb = R.ctr->nb[q], n = REDO ? R.ctr->n_redo : nb + R.ctr->nn[q];
+    const uint32_t nb = R.ctr->nb[q], n = nb + R.ctr->nn[q];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xFFFFFFFFu;
     const float INF = __int_as_float(0x7f800000);
-    if (!REDO && blockIdx.x == 0 && threadIdx.x == 0) { R.ctr->nb[q ^ 1] = 0; R.ctr->nn[q ^ 1] = 0; }  // nobody touches them during extend
+    if (blockIdx.x == 0 && threadIdx.x == 0) { R.ctr->nb[q ^ 1] = 0; R.ctr->nn[q ^ 1] = 0; }  // nobody touches them during extend
     TravCount tc;
-    tc.nodes = 0; tc.prims = 0; tc.exact = 0;
+    tc.nodes = 0; tc.prims = 0; tc.exact = 0; tc.redo = 0;
     Trav T;
     bool active = false, exhausted = false;
     uint32_t my_pos = 0;
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
         if (act_mask != FULL && !(exhausted && batch_next == batch_end) && (uint32_t)__popc(act_mask) < R.refill_threshold) {
             if (batch_next == batch_end) {
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(REDO ? &R.ctr->cursor_redo : &R.ctr->cursor_extend, 32u);
+                if (lane == 0) base = atomicAdd(&R.ctr->cursor_extend, 32u);
                 base = __shfl_sync(FULL, base, 0);
                 batch_next = min(base, n);
                 batch_end = min(base + 32u, n);
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
             const uint32_t avail = batch_end - batch_next;
             const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
             if (!active && rank < avail) {
-                my_pos = REDO ? R.redo[batch_next + rank] : queue_pos(batch_next + rank, nb, R.cap);
+                my_pos = queue_pos(batch_next + rank, nb, R.cap);
                 const float4 a = R.A[q][my_pos], b = R.B[q][my_pos];
                 if (__float_as_uint(b.w) & RT_ROOT_MISS) {
                     R.hits[my_pos] = make_uint2(RT_NO_HIT, __float_as_uint(INF));
@@ -177,12 +179,8 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
                     trav_setup(S, T, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), R.Tm[q] ? R.Tm[q][my_pos] : 0.0f, 0.001f, INF);
                     active = true;
                     if (MODE == 3) {
-                        if (T.exact_only) {  // zero / denormal / non-finite direction component: reference traversal only
-                            R.redo[atomicAdd(&R.ctr->n_redo, 1u)] = my_pos;
-                            active = false;
-                        } else {
-                            trav_setup_fast(S, T);
-                        }
+                        if (!fast_eligible(T)) T.dpos |= RT_REFMODE_BIT;  // degenerate or near-axis-parallel direction: reference tree only
+                        else trav_setup_fast(S, T, R.fast_order);
                     }
                 }
             }
@@ -202,14 +200,23 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
         const bool do_leaf = n_leaf * R.leaf_weight > ((uint32_t)__popc(act_mask) - n_leaf) * 16u;
         if (active) {
             bool more;
-            if constexpr (MODE == 3) more = trav_round_fast<COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc);
-            else more = trav_round<MODE, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
+            if constexpr (MODE == 3) {
+                if (T.dpos & RT_REFMODE_BIT) more = trav_round<2, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
+                else more = trav_round_fast<COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc);
+            } else {
+                more = trav_round<MODE, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
+            }
             if (!more) {
-                if (MODE == 3 && T.best != RT_NO_HIT && ((T.dpos & RT_TIE_BIT) || !ref_visible(S, T.best, T.o, T.d, T.end)))
-                    R.redo[atomicAdd(&R.ctr->n_redo, 1u)] = my_pos;
-                else
+                if (MODE == 3 && !(T.dpos & RT_REFMODE_BIT) && T.best != RT_NO_HIT &&
+                    ((T.dpos & RT_TIE_BIT) || !ref_visible(S, T.best, T.o, T.d, T.end))) {
+                    // not proven: same ray again on the reference tree (the root test already passed in the producer)
+                    T.best = RT_NO_HIT; T.end = INF; T.sp = 0; T.cur = S.root;
+                    T.dpos = (T.d.x > 0.0f ? 1u : 0u) | (T.d.y > 0.0f ? 2u : 0u) | (T.d.z > 0.0f ? 4u : 0u) | RT_REFMODE_BIT;
+                    if (COUNT) tc.redo++;
+                } else {
                     R.hits[my_pos] = make_uint2(T.best, __float_as_uint(T.end));
-                active = false;
+                    active = false;
+                }
             }
         }
         act_mask = __ballot_sync(FULL, active);
@@ -219,11 +226,13 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
             tc.nodes += __shfl_xor_sync(FULL, tc.nodes, off);
             tc.prims += __shfl_xor_sync(FULL, tc.prims, off);
             tc.exact += __shfl_xor_sync(FULL, tc.exact, off);
+            tc.redo += __shfl_xor_sync(FULL, tc.redo, off);
         }
         if (lane == 0) {
             atomicAdd(&R.ctr->node_visits, (unsigned long long)tc.nodes);
             atomicAdd(&R.ctr->prim_tests, (unsigned long long)tc.prims);
             atomicAdd(&R.ctr->exact_steps, (unsigned long long)tc.exact);
+            atomicAdd(&R.ctr->redo_total, (unsigned long long)tc.redo);
             atomicAdd(&R.ctr->rounds, rounds_c); atomicAdd(&R.ctr->busy_lanes, busy_c);
             atomicAdd(&R.ctr->tail_rounds, trounds_c); atomicAdd(&R.ctr->tail_busy_lanes, tbusy_c);
         }
@@ -239,9 +248,6 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         R.ctr->cursor_extend = 0;
-        R.ctr->redo_total += R.ctr->n_redo;
-        R.ctr->n_redo = 0;
-        R.ctr->cursor_redo = 0;
         R.ctr->rays += n;
         if (R.iter_log) {  // [iter] live paths, [CAP + 2 iter] cumulative node visits (lo/hi), [3 CAP + 2 iter] cumulative prim tests
             R.iter_log[R.iter] = n;

@@ -24,6 +24,7 @@ struct Box3 {
 
 struct Tree {
     std::vector<uint32_t> left, right;  // child: 0x80000000 | element, or node index
+    std::vector<uint32_t> axis;         // split axis: the left child holds the lower centroids on it
     std::vector<Box3> box;              // each node's own box (exact union of the element boxes below it)
     uint32_t root = 0;
     uint32_t depth = 0;
@@ -63,7 +64,7 @@ struct Builder {
     }
 
     // returns the split position (lo < mid < hi) after reordering idx[lo, hi)
-    uint32_t split(uint32_t lo, uint32_t hi, uint32_t levels_left) {
+    uint32_t split(uint32_t lo, uint32_t hi, uint32_t levels_left, uint32_t* axis_out) {
         const uint32_t n = hi - lo;
         const uint64_t child_cap = levels_left >= 1 ? (levels_left - 1 >= 63 ? ~0ull : (1ull << (levels_left - 1))) : 1ull;
         float cmin[3], cmax[3];
@@ -92,6 +93,7 @@ struct Builder {
             if (best_axis >= 0) {
                 const int k = best_axis;
                 std::stable_sort(idx.begin() + lo, idx.begin() + hi, [&](uint32_t a, uint32_t b) { return cen[k][a] < cen[k][b]; });
+                *axis_out = (uint32_t)k;
                 return lo + best_pos;
             }
         } else {
@@ -132,7 +134,7 @@ struct Builder {
                     return (uint32_t)b <= best_pos;
                 });
                 const uint32_t mid = (uint32_t)(it - idx.begin());
-                if (mid > lo && mid < hi) return mid;
+                if (mid > lo && mid < hi) { *axis_out = (uint32_t)k; return mid; }
             }
         }
         // no useful plane (coincident centroids, NaNs, or the depth cap binds): median split on the widest centroid axis
@@ -141,6 +143,7 @@ struct Builder {
             if (cmax[a] - cmin[a] > cmax[k] - cmin[k]) k = a;
         const uint32_t mid = lo + n / 2;
         std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](uint32_t a, uint32_t b) { return cen[k][a] < cen[k][b]; });
+        *axis_out = (uint32_t)k;
         return mid;
     }
 
@@ -150,8 +153,11 @@ struct Builder {
         out.left.push_back(0);
         out.right.push_back(0);
         out.box.push_back(empty_box());
+        out.axis.push_back(0);
         out.depth = std::max(out.depth, depth + 1);
-        const uint32_t mid = split(lo, hi, max_depth - depth);
+        uint32_t ax = 0;
+        const uint32_t mid = split(lo, hi, max_depth - depth, &ax);
+        out.axis[me] = ax;
         const uint32_t l = build(lo, mid, depth + 1);
         const uint32_t r = build(mid, hi, depth + 1);
         out.left[me] = l;

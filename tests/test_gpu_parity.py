@@ -294,6 +294,9 @@ def test_traversal_variants_agree_at_full_size():
     _cabi.set_option("traversal", 3)
     c, sc = rb.render(size, 1, 1, 50, w, seed=11, return_stats=True)
     assert sc["ray_segments"] == sb["ray_segments"] and images_equal_bits(c, b)
+    _cabi.set_option("count", 1)      # the counting kernel variant reports how many rays were restarted on the reference tree
+    c, sc = rb.render(size, 1, 1, 50, w, seed=11, return_stats=True)
+    assert sc["ray_segments"] == sb["ray_segments"] and images_equal_bits(c, b)
     assert 0 < sc["redo_rays"] < 0.05 * sc["ray_segments"], sc   # a few rays per cent need the reference tree; never zero on 3M rays
 
 
@@ -308,7 +311,11 @@ def test_rebuilt_topology_gives_the_reference_film(name, size):
     _cabi.set_option("traversal", 3)
     b, sb = rb.render(rb.Size2i(*size), 2, 4, 50, w, seed=5, return_stats=True)
     assert sa["ray_segments"] == sb["ray_segments"] and images_equal_bits(a, b)
+    _cabi.set_option("count", 1)
+    b, sb = rb.render(rb.Size2i(*size), 2, 4, 50, w, seed=5, return_stats=True)
+    assert sa["ray_segments"] == sb["ray_segments"] and images_equal_bits(a, b)
     assert sb["redo_rays"] <= 0.25 * sb["ray_segments"], sb
+    assert sb["node_visits"] > 0
 
 
 def test_rebuilt_topology_redo_paths(oracle):
@@ -341,6 +348,7 @@ def test_rebuilt_topology_redo_paths(oracle):
         r = assert_hits_match(w.hit(org, dir), ref)
         assert r["t_bit_mismatch"] == 0 and r["normal_bit_mismatch"] == 0, (mode, r)
     _cabi.set_option("traversal", 3)
+    _cabi.set_option("count", 1)
     ref_img, st = o.render(64, 48, 6, 20, 2, 9, "replay")
     img, gst = rb.render(rb.Size2i(64, 48), 2, 6, 20, w, seed=9, return_stats=True)
     assert gst["ray_segments"] == st["rays"] and images_equal_bits(img, ref_img)

@@ -67,10 +67,23 @@ def prim_hit(i, o, d, t0, t1):
     return None
 
 # ---------------------------------------------------------------- trees: arrays of (box, left, right) with negative = ~leaf
+EPS = 5.9604645e-8
+leafA = np.zeros(n); leafC = np.zeros(n)
+for i in range(n):
+    maxabs = np.abs(boxes[i]).max()
+    if kinds[i] == 0:
+        leafA[i] = 8 * EPS * (maxabs + 3 * geom[i][3]); leafC[i] = 8 * 3 * EPS / geom[i][3]
+    else:
+        leafA[i] = 8 * EPS * maxabs
+GUARD = os.environ.get("GUARD", "0") == "1"
+SIGN_REF = os.environ.get("SIGN_REF", "0") == "1"
+ref_axis = {}
+
 def ref_tree():
     nodes = []
     for j in range(len(fs.nodes_lra)):
-        l, r, _ = fs.nodes_lra[j]
+        l, r, ax = fs.nodes_lra[j]
+        ref_axis[j] = int(ax)
         enc = lambda c: ~int(c & 0x7FFFFFFF) if c & 0x80000000 else int(c)
         nodes.append((fs.nodes_box[j].astype(np.float64), enc(int(l)), enc(int(r))))
     root = fs.root
@@ -113,10 +126,27 @@ def slab(b, o, inv, t0, t1):
     tn = max(t0, np.nanmax(np.minimum(ta, tb))); tf = min(t1, np.nanmin(np.maximum(ta, tb)))
     return tn, tf
 
-def traverse(tree, o, d, t0=1e-3, t1=np.inf):
+_margin_cache = {}
+def margins(tree):
+    key = id(tree[0])
+    if key in _margin_cache: return _margin_cache[key]
     nodes, root = tree
+    A = [0.0] * len(nodes); C = [0.0] * len(nodes)
+    def rec(c):
+        if c < 0: return leafA[~c], leafC[~c]
+        a1, c1 = rec(nodes[c][1]); a2, c2 = rec(nodes[c][2])
+        A[c], C[c] = max(a1, a2), max(c1, c2)
+        return A[c], C[c]
+    rec(root)
+    _margin_cache[key] = (A, C)
+    return A, C
+
+def traverse(tree, o, d, t0=1e-3, t1=np.inf, sign_order=False):
+    nodes, root = tree
+    mA, mC = margins(tree)
     with np.errstate(divide="ignore"):
         inv = 1.0 / d
+    mscale = 2 * np.abs(inv).max()
     best, bt = -1, t1
     nv = npt = 0
     def box_of(c):
@@ -139,8 +169,12 @@ def traverse(tree, o, d, t0=1e-3, t1=np.inf):
                 tn_c, tf_c = slab(boxes[~ch], o, inv, t0, bt)
             else:
                 tn_c, tf_c = slab(nodes[ch][0], o, inv, t0, bt)
-            if tn_c <= tf_c: kids.append((ch, tn_c))
-        kids.sort(key=lambda x: -x[1])
+            mg = (mA[c] + tn_c * (1e-5 + mC[c] * tn_c)) * mscale if GUARD else 0.0
+            if not (tn_c - tf_c > mg): kids.append((ch, tn_c - mg))
+        if sign_order:
+            if d[ref_axis[c]] > 0: kids = kids[::-1]      # left first => left must be popped last pushed
+        else:
+            kids.sort(key=lambda x: -x[1])
         stack.extend(kids)
     return best, bt, nv, npt
 
@@ -161,7 +195,7 @@ for bounce in range(3):
     stats = {"ref": [0, 0], "sah": [0, 0]}
     mism = 0
     for i in range(len(o)):
-        a = traverse(T_ref, o[i], d[i]); b = traverse(T_sah, o[i], d[i])
+        a = traverse(T_ref, o[i], d[i], sign_order=SIGN_REF); b = traverse(T_sah, o[i], d[i])
         stats["ref"][0] += a[2]; stats["ref"][1] += a[3]; stats["sah"][0] += b[2]; stats["sah"][1] += b[3]
         mism += a[0] != b[0]
         if a[0] >= 0:
