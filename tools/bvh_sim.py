@@ -5,11 +5,11 @@ versus a SAH binary tree over the same elements, for primary and bounce rays of 
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import binding as ob
+import raytracinginaweekend_b200 as rb
 
 name = sys.argv[1] if len(sys.argv) > 1 else "config:c2"
 NR = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
-W = ob.OracleWorld.named(name)
+W = rb.World.named(name)
 fs = W.export()
 n = len(fs.kinds)
 geom = fs.geom.astype(np.float64)
@@ -179,9 +179,12 @@ def traverse(tree, o, d, t0=1e-3, t1=np.inf, sign_order=False):
     return best, bt, nv, npt
 
 rng = np.random.default_rng(0)
-po, pd = W.primary_rays(64, 36)
-sel = rng.choice(len(po), min(NR, len(po)), replace=False)
-po, pd = po[sel].astype(np.float64), pd[sel].astype(np.float64)
+# primary-like rays: from the camera position towards random points of the element boxes
+cam_pos = fs.cam[0:3].astype(np.float64)
+tgt = boxes[rng.integers(0, n, NR)]
+tgt = tgt[:, :3] + rng.uniform(size=(NR, 3)) * (tgt[:, 3:] - tgt[:, :3])
+pd = tgt - cam_pos; pd /= np.linalg.norm(pd, axis=1, keepdims=True)
+po = np.tile(cam_pos, (NR, 1))
 T_ref, T_sah = ref_tree(), sah_tree()
 def sah_cost(tree):
     nodes, root = tree
