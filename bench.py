@@ -268,8 +268,12 @@ def main():
         fp32_ach = rays_rank0 * flops_per_ray / (ext_ms * 1e-3) / 1e12 if ext_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "extend_traffic.json")
+        traffic_src = None
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            # measured DRAM bytes per ray of the captured launch x this run's average rays per launch ("per launch like achieved")
+            traffic = tj["dram_bytes_per_ray"] * rays_rank0 / max(1, n_ext)
+            traffic_src = tj.get("capture")
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -281,7 +285,7 @@ def main():
                        "ray_segments_per_step": total_rays / args.steps,
                        "per_rank_ms_per_step": [float(t.item()) / args.steps for t in per_rank] if n_gpus > 1 else [total_ms / args.steps]},
             "roofline": {"kernel": "k_extend", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                          "bytes_per_ray": EXTEND_BYTES_PER_RAY, "launches": n_ext, "avg_launch_ms": ext_ms / max(1, n_ext),
                          "share_of_step": ext_ms / max(1e-9, sum(step_ms)),
                          "note": "scene (nodes+primitives) is L2-resident, so the kernel is FP32-issue / latency bound: see fp32"},
