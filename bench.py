@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {  # BASELINE.json configs (DESIGN.md "Workload definitions")
     "c1": dict(world="config:c1", width=1200, height=800, spp=10, lanes=10, cpu_sample=(300, 200, 4)),
-    "c2": dict(world="config:c2", width=1920, height=1080, spp=64, lanes=64, cpu_sample=(320, 180, 4)),
+    "c2": dict(world="config:c2", width=1920, height=1080, spp=64, lanes=64, cpu_sample=(640, 360, 4)),
     "c3": dict(world="config:c3", width=1024, height=1024, spp=256, lanes=32, cpu_sample=(256, 256, 16)),
     "c4": dict(world="config:c4", width=3840, height=2160, spp=16, lanes=1, cpu_sample=(240, 135, 2)),
     "c5": dict(world="config:c5", width=3840, height=2160, spp=4096, lanes=8, cpu_sample=(240, 135, 2)),
@@ -92,7 +92,7 @@ class ClockSampler:
 
 def cpu_sample_dims(wl, cores):
     """Bounded CPU sample: every one of the `cores` worker threads gets >= 1 sample per pixel (the reference splits SAMPLES
-    across threads), and the image shrinks so the work stays ~constant (~0.25 M paths)."""
+    across threads), and the image shrinks so the work stays ~constant (C2: ~0.9 M paths, 10-15 s on 16 cores)."""
     w, h, spp = wl["cpu_sample"]
     target = w * h * spp
     spp = max(spp, cores)
@@ -121,7 +121,8 @@ def run_reference(args, wl):
     out = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": wl["world"], "width": wl["width"], "height": wl["height"], "spp": wl["spp"], "max_depth": MAX_DEPTH,
+           "config": {"workload": wl["world"], "width": wl["width"], "height": wl["height"], "spp_per_gpu": wl["spp"],
+                      "spp_total": wl["spp"] * args.gpus, "max_depth": MAX_DEPTH, "sample_lanes_per_gpu": wl["lanes"],
                       "note": "reference arm = CPU restatement of the Rust renderer (rustc unavailable); bounded sample per step"},
            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
