@@ -168,6 +168,8 @@ typedef struct RtStats {
     uint64_t prim_tests;     /* primitive intersection tests    — only with rt_set_option("count", 1) */
     uint64_t exact_steps;    /* node steps that fell back to true divisions — only with rt_set_option("count", 1) */
     uint64_t redo_rays;      /* traversal 3: rays the fast topology could not prove, traced again on the reference tree — only with "count" */
+    uint32_t max_stack;      /* deepest traversal stack use of any ray (entries) — only with "count" */
+    uint32_t stack_capacity; /* entries per thread the launch provided (tree depth + 2): max_stack must never exceed it */
 } RtStats;
 
 typedef struct RtScene RtScene;

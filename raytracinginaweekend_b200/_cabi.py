@@ -69,7 +69,7 @@ class RtStats(C.Structure):
     _fields_ = [("ray_segments", C.c_uint64), ("paths", C.c_uint64), ("iterations", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("render_ms", C.c_double), ("extend_ms", C.c_double),
                 ("shade_ms", C.c_double), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64), ("exact_steps", C.c_uint64),
-                ("redo_rays", C.c_uint64)]
+                ("redo_rays", C.c_uint64), ("max_stack", C.c_uint32), ("stack_capacity", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -814,6 +814,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
         total.rays += pp.final_ctr->rays; total.paths += pp.final_ctr->paths;
         total.node_visits += pp.final_ctr->node_visits; total.prim_tests += pp.final_ctr->prim_tests; total.exact_steps += pp.final_ctr->exact_steps;
         total.redo_total += pp.final_ctr->redo_total;
+        total.max_sp = std::max(total.max_sp, pp.final_ctr->max_sp);
         iters = std::max(iters, pp.iters);
     }
     const Counters* final_ctr = &total;
@@ -829,6 +830,8 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
         stats->prim_tests = final_ctr->prim_tests;
         stats->exact_steps = final_ctr->exact_steps;
         stats->redo_rays = final_ctr->redo_total;
+        stats->max_stack = final_ctr->max_sp;
+        stats->stack_capacity = sc.dev.stack_cap;
     }
     return RT_OK;
 }

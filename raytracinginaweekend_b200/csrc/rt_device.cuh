@@ -364,6 +364,7 @@ struct HitRec {
 struct TravCount {
     uint32_t nodes, prims, exact;  // node visits (64 B fetches), primitive tests, exact-fallback node steps
     uint32_t redo;                 // traversal 3: rays restarted on the reference tree
+    uint32_t max_sp;               // deepest traversal stack use (entries); must stay <= SceneDev::stack_cap
 };
 struct Trav {
     float3 o, d;
@@ -575,6 +576,7 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
             stk_ref[T.sp * stk_stride] = c2;
             stk_tn[T.sp * stk_stride] = tn2;
             ++T.sp;
+            if (COUNT) cnt->max_sp = max(cnt->max_sp, T.sp);
         }
         if (p1) T.cur = c1;
         else if (p2) T.cur = c2;
@@ -674,6 +676,7 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
             stk_ref[T.sp * stk_stride] = c2;
             stk_tn[T.sp * stk_stride] = left_first ? tnR - mgR : tnL - mgL;  // cull threshold of the deferred child
             ++T.sp;
+            if (COUNT) cnt->max_sp = max(cnt->max_sp, T.sp);
         }
         if (p1) T.cur = c1;
         else if (p2) T.cur = c2;

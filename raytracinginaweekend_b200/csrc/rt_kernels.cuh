@@ -21,6 +21,7 @@ struct Counters {
     unsigned long long node_visits, prim_tests, exact_steps;  // only maintained by the COUNT kernel variant
     unsigned long long rounds, busy_lanes, tail_rounds, tail_busy_lanes;  // COUNT: warp rounds / busy lanes, overall and after the queue ran dry
     unsigned long long redo_total;     // row f4 (COUNT variant): rays the fast traversal could not prove -> reference traversal
+    uint32_t max_sp, pad2;             // COUNT variant: deepest traversal stack use of any ray
 };
 
 struct RenderDev {
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
         R.ctr->prim_tests = 0;
         R.ctr->exact_steps = 0;
         R.ctr->rounds = 0; R.ctr->busy_lanes = 0; R.ctr->tail_rounds = 0; R.ctr->tail_busy_lanes = 0;
-        R.ctr->redo_total = 0;
+        R.ctr->redo_total = 0; R.ctr->max_sp = 0;
     }
 }
 
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
     const float INF = __int_as_float(0x7f800000);
     if (blockIdx.x == 0 && threadIdx.x == 0) { R.ctr->nb[q ^ 1] = 0; R.ctr->nn[q ^ 1] = 0; }  // nobody touches them during extend
     TravCount tc;
-    tc.nodes = 0; tc.prims = 0; tc.exact = 0; tc.redo = 0;
+    tc.nodes = 0; tc.prims = 0; tc.exact = 0; tc.redo = 0; tc.max_sp = 0;
     Trav T;
     bool active = false, exhausted = false;
     uint32_t my_pos = 0;
@@ -227,12 +228,14 @@ __global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ Scene
             tc.prims += __shfl_xor_sync(FULL, tc.prims, off);
             tc.exact += __shfl_xor_sync(FULL, tc.exact, off);
             tc.redo += __shfl_xor_sync(FULL, tc.redo, off);
+            tc.max_sp = max(tc.max_sp, __shfl_xor_sync(FULL, tc.max_sp, off));
         }
         if (lane == 0) {
             atomicAdd(&R.ctr->node_visits, (unsigned long long)tc.nodes);
             atomicAdd(&R.ctr->prim_tests, (unsigned long long)tc.prims);
             atomicAdd(&R.ctr->exact_steps, (unsigned long long)tc.exact);
             atomicAdd(&R.ctr->redo_total, (unsigned long long)tc.redo);
+            atomicMax(&R.ctr->max_sp, tc.max_sp);
             atomicAdd(&R.ctr->rounds, rounds_c); atomicAdd(&R.ctr->busy_lanes, busy_c);
             atomicAdd(&R.ctr->tail_rounds, trounds_c); atomicAdd(&R.ctr->tail_busy_lanes, tbusy_c);
         }

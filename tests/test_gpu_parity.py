@@ -316,6 +316,7 @@ def test_rebuilt_topology_gives_the_reference_film(name, size):
     assert sa["ray_segments"] == sb["ray_segments"] and images_equal_bits(a, b)
     assert sb["redo_rays"] <= 0.25 * sb["ray_segments"], sb
     assert sb["node_visits"] > 0
+    assert 0 < sb["max_stack"] <= sb["stack_capacity"], sb      # the shared-memory traversal stack never overflows
 
 
 def test_rebuilt_topology_redo_paths(oracle):
@@ -353,6 +354,16 @@ def test_rebuilt_topology_redo_paths(oracle):
     img, gst = rb.render(rb.Size2i(64, 48), 2, 6, 20, w, seed=9, return_stats=True)
     assert gst["ray_segments"] == st["rays"] and images_equal_bits(img, ref_img)
     assert gst["redo_rays"] > 0
+
+
+@pytest.mark.parametrize("name", ["config:c2", "config:c3", "config:c5", "demo:final_scene2", "demo:cornell_box_smoke", "demo:suzanne"])
+@pytest.mark.parametrize("mode", [0, 2, 3])
+def test_traversal_stack_stays_within_capacity(name, mode):
+    """compute-sanitizer is not available on the GPU pool: the counting kernel variant records the deepest stack use instead."""
+    _cabi.set_option("traversal", mode)
+    _cabi.set_option("count", 1)
+    _, st = rb.render(rb.Size2i(160, 120), 2, 4, 50, product_world(name), seed=13, return_stats=True)
+    assert 0 < st["max_stack"] <= st["stack_capacity"], st
 
 
 def test_lane_count_only_changes_summation_order():
