@@ -30,6 +30,7 @@ thread_local std::string g_err;
 int g_opt_traversal = 3;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path,
                               // 3 = rebuilt topology + per-ray proof, unproven rays on the reference tree with 2 (plain scenes; else 2)
 int g_opt_fast_order = 0;     // experiment: child order of the fast traversal (0 near-first, 1 split-axis sign, 2 near-first, ties by sign)
+int g_opt_presplit = 400;     // reference budget of the rebuilt tree in per cent of the element count (<= 100: no pre-splitting)
 int g_opt_rebuild = 1;        // build the second topology at rt_scene_create (0: traversal 3 behaves like 2)
 int g_opt_rebuild_depth_extra = 3;  // depth cap of the rebuilt tree = reference depth + this (the stack lives in shared memory)
 int g_opt_pipes = 1;         // independent wavefront pipelines (streams) per render: one pipeline's extend tail overlaps the other's work
@@ -378,23 +379,42 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     uint32_t root2 = 0;
     if (!any_wrap && N >= 2 && g_opt_rebuild) {
         std::vector<rt_rebuild::Box3> lb(N);
+        std::vector<float> tri;
+        std::vector<uint8_t> is_tri(N, 0);
         for (uint32_t i = 0; i < N; ++i)
             for (int k = 0; k < 3; ++k) { lb[i].mn[k] = lbox[i].mn[k]; lb[i].mx[k] = lbox[i].mx[k]; }
+        // pre-split sliver triangles into several references (rt_rebuild.hpp); the budget shrinks for very large scenes
+        const double factor = g_opt_presplit <= 100 ? 1.0 : std::min((double)g_opt_presplit / 100.0, N <= 150000u ? 8.0 : (N <= 400000u ? 2.0 : 1.0));
+        if (factor > 1.0) {
+            tri.assign(9 * (size_t)N, 0.0f);
+            for (uint32_t i = 0; i < N; ++i)
+                if (d.items[i].kind == RT_GEO_TRIANGLE) {
+                    is_tri[i] = 1;
+                    for (int k = 0; k < 9; ++k) tri[9 * (size_t)i + k] = d.items[i].geom[k];
+                }
+        }
+        std::vector<rt_rebuild::Ref> refs;
+        rt_rebuild::presplit(lb, tri, is_tri, (size_t)((double)N * factor), refs);
+        std::vector<rt_rebuild::Box3> rbx(refs.size());
+        for (size_t i = 0; i < refs.size(); ++i) rbx[i] = refs[i].box;
         rt_rebuild::Tree F;
-        rt_rebuild::build(lb, depth + (uint32_t)std::max(0, g_opt_rebuild_depth_extra), F);
+        uint32_t extra_levels = 0;
+        while (((size_t)N << extra_levels) < refs.size()) ++extra_levels;
+        rt_rebuild::build(rbx, depth + extra_levels + (uint32_t)std::max(0, g_opt_rebuild_depth_extra), F);
         const uint32_t n2 = (uint32_t)F.left.size();
+        auto item_of = [&](uint32_t leafref) -> uint32_t { return refs[leafref & ~RT_LEAF_BIT].item; };
         std::vector<float> a2(n2, 0.0f), c2(n2, 0.0f);
         for (uint32_t ii = n2; ii-- > 0;) {  // pre-order numbering: children have larger indices
             float a = 0.0f, c = 0.0f;
             for (uint32_t ch : {F.left[ii], F.right[ii]}) {
-                if (ch & RT_LEAF_BIT) { a = std::max(a, leafA[ch & ~RT_LEAF_BIT]); c = std::max(c, leafC[ch & ~RT_LEAF_BIT]); }
+                if (ch & RT_LEAF_BIT) { a = std::max(a, leafA[item_of(ch)]); c = std::max(c, leafC[item_of(ch)]); }
                 else { a = std::max(a, a2[ch]); c = std::max(c, c2[ch]); }
             }
             a2[ii] = a; c2[ii] = c;
         }
         nodes2.resize(n2);
-        auto box2 = [&](uint32_t r) -> rt_rebuild::Box3 { return (r & RT_LEAF_BIT) ? lb[r & ~RT_LEAF_BIT] : F.box[r]; };
-        auto ref2 = [&](uint32_t r) -> uint32_t { return (r & RT_LEAF_BIT) ? ref_of_item(r & ~RT_LEAF_BIT) : r; };
+        auto box2 = [&](uint32_t r) -> rt_rebuild::Box3 { return (r & RT_LEAF_BIT) ? rbx[r & ~RT_LEAF_BIT] : F.box[r]; };
+        auto ref2 = [&](uint32_t r) -> uint32_t { return (r & RT_LEAF_BIT) ? ref_of_item(item_of(r)) : r; };
         for (uint32_t i = 0; i < n2; ++i) {
             const rt_rebuild::Box3 bl = box2(F.left[i]), br = box2(F.right[i]);
             NodeDev nd;
@@ -853,6 +873,7 @@ int rt_set_option(const char* key, int64_t value) {
     std::string k(key);
     if (k == "traversal") g_opt_traversal = (int)value;
     else if (k == "rebuild") g_opt_rebuild = (int)value;
+    else if (k == "presplit") g_opt_presplit = (int)value;
     else if (k == "fast_order") g_opt_fast_order = (int)value;
     else if (k == "rebuild_depth_extra") g_opt_rebuild_depth_extra = (int)value;
     else if (k == "profile") g_opt_profile = (int)value;

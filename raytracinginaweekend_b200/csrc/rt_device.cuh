@@ -638,7 +638,8 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
             float t;
             if (prim_t(kind, reinterpret_cast<const float4*>(S.prims + item), T.o, T.d, T.start, end_closed, t)) {
                 if (have && t == T.end) {
-                    T.dpos |= RT_TIE_BIT;
+                    // the same element can sit in several leaves (pre-split references): seeing it again is not a tie
+                    if (((cur ^ T.best) & RT_REF_ITEM_MASK) != 0u) T.dpos |= RT_TIE_BIT;
                 } else {
                     T.best = cur; T.end = t; T.dpos &= ~RT_TIE_BIT;
                 }

@@ -171,7 +171,109 @@ struct Builder {
 
 }  // namespace detail
 
-// max_depth: number of internal levels allowed (>= ceil(log2 n)).
+// ------------------------------------------------------------------------------------------------
+// Reference pre-splitting.  The reference's OBJ loader fans every polygon around the mesh origin (Q4), so half of a mesh's
+// triangles are long slivers whose boxes all overlap around one point; a tree over such boxes cannot separate them.
+// Because this tree is only an accelerator, an element may appear in several leaves: a triangle's reference is cut at the
+// middle of its box's longest axis (exact polygon clipping in double, boxes rounded outward to float) as long as the two
+// clipped boxes together are < 0.9x the area of the unsplit one, largest boxes first, until `budget` references exist.
+// Every point of the triangle stays inside the box of at least one of its references, which is all the traversal needs.
+// ------------------------------------------------------------------------------------------------
+struct Ref {
+    uint32_t item;
+    Box3 box;
+};
+
+namespace detail {
+struct Poly {
+    int n = 0;
+    double v[12][3];
+};
+inline Poly clip_half(const Poly& in, int axis, double c, double sign) {  // keep sign * (x[axis] - c) >= 0
+    Poly out;
+    for (int i = 0; i < in.n; ++i) {
+        const double* a = in.v[i];
+        const double* b = in.v[(i + 1) % in.n];
+        const double da = sign * (a[axis] - c), db = sign * (b[axis] - c);
+        if (da >= 0.0 && out.n < 12) { for (int k = 0; k < 3; ++k) out.v[out.n][k] = a[k]; ++out.n; }
+        if ((da >= 0.0) != (db >= 0.0) && out.n < 12) {
+            const double t = da / (da - db);
+            for (int k = 0; k < 3; ++k) out.v[out.n][k] = a[k] + t * (b[k] - a[k]);
+            out.v[out.n][axis] = c;
+            ++out.n;
+        }
+    }
+    return out;
+}
+inline float round_down(double v) {
+    float f = (float)v;
+    return (double)f > v ? std::nextafter(f, -INFINITY) : f;
+}
+inline float round_up(double v) {
+    float f = (float)v;
+    return (double)f < v ? std::nextafter(f, INFINITY) : f;
+}
+inline Box3 poly_box(const Poly& p, const Box3& within) {
+    Box3 b = empty_box();
+    for (int i = 0; i < p.n; ++i)
+        for (int k = 0; k < 3; ++k) { b.mn[k] = std::fmin(b.mn[k], round_down(p.v[i][k])); b.mx[k] = std::fmax(b.mx[k], round_up(p.v[i][k])); }
+    for (int k = 0; k < 3; ++k) { b.mn[k] = std::fmax(b.mn[k], within.mn[k]); b.mx[k] = std::fmin(b.mx[k], within.mx[k]); }  // never beyond the element's own box
+    return b;
+}
+}  // namespace detail
+
+// tri: 9 floats (p0, p1, p2) per element, only read where is_tri[i] != 0.
+inline void presplit(const std::vector<Box3>& leaf, const std::vector<float>& tri, const std::vector<uint8_t>& is_tri, size_t budget,
+                     std::vector<Ref>& refs) {
+    using detail::Poly;
+    refs.clear();
+    refs.reserve(std::max(budget, leaf.size()));
+    std::vector<Poly> polys;
+    std::vector<int32_t> poly_of;  // per reference: index into polys or -1
+    std::vector<std::pair<double, uint32_t>> heap;
+    for (uint32_t i = 0; i < leaf.size(); ++i) {
+        refs.push_back(Ref{i, leaf[i]});
+        if (is_tri[i] && budget > leaf.size()) {
+            Poly p;
+            p.n = 3;
+            for (int v = 0; v < 3; ++v)
+                for (int k = 0; k < 3; ++k) p.v[v][k] = tri[9 * (size_t)i + 3 * v + k];
+            poly_of.push_back((int32_t)polys.size());
+            polys.push_back(p);
+            heap.push_back({detail::half_area(leaf[i]), i});
+        } else {
+            poly_of.push_back(-1);
+        }
+    }
+    std::make_heap(heap.begin(), heap.end());
+    while (!heap.empty() && refs.size() < budget) {
+        std::pop_heap(heap.begin(), heap.end());
+        const uint32_t r = heap.back().second;
+        heap.pop_back();
+        const Box3 b = refs[r].box;
+        int ax = 0;
+        for (int k = 1; k < 3; ++k)
+            if (b.mx[k] - b.mn[k] > b.mx[ax] - b.mn[ax]) ax = k;
+        if (!(b.mx[ax] > b.mn[ax])) continue;
+        const double mid = 0.5 * ((double)b.mn[ax] + (double)b.mx[ax]);
+        const Poly& src = polys[poly_of[r]];
+        const Poly lo = detail::clip_half(src, ax, mid, -1.0), hi = detail::clip_half(src, ax, mid, 1.0);
+        if (lo.n < 3 || hi.n < 3) continue;
+        const Box3 bl = detail::poly_box(lo, b), bh = detail::poly_box(hi, b);
+        const double a0 = detail::half_area(b), al = detail::half_area(bl), ah = detail::half_area(bh);
+        if (!(al + ah < 0.9 * a0)) continue;
+        polys[poly_of[r]] = lo;
+        refs[r].box = bl;
+        const uint32_t r2 = (uint32_t)refs.size();
+        refs.push_back(Ref{refs[r].item, bh});
+        poly_of.push_back((int32_t)polys.size());
+        polys.push_back(hi);
+        heap.push_back({al, r}); std::push_heap(heap.begin(), heap.end());
+        heap.push_back({ah, r2}); std::push_heap(heap.begin(), heap.end());
+    }
+}
+
+// max_depth: number of internal levels allowed (>= ceil(log2 n)).  Leaves are indices into `leaf` (boxes of references).
 inline void build(const std::vector<Box3>& leaf, uint32_t max_depth, Tree& out) {
     out = Tree();
     uint32_t need = 0;
