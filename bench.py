@@ -228,14 +228,20 @@ def main():
     pinned = torch.empty((size.height, size.width, 3), dtype=torch.float32).pin_memory()
     barrier()
     e2e_ms, e2e_rays = 0.0, 0.0
-    e2e_steps = []
-    for i in range(-1, max(1, min(args.steps, 3))):   # i = -1: one untimed warm-up of this code path (first-use allocations)
+    e2e_steps, e2e_phases = [], []
+    for i in range(-1, max(1, args.steps)):   # i = -1: one untimed warm-up of this code path (first-use allocations)
         t0 = time.perf_counter()
         world.release_device()
+        t1 = time.perf_counter()
+        scene_e = world.device_scene(local_rank)      # rt_scene_create: pack + rebuild + upload
+        t2 = time.perf_counter()
         film, st = rdist.render_distributed(world, size, lanes_total, spp_total, MAX_DEPTH, rb.RenderMode.Default, 300 + i,
                                             device=dev, return_stats=True)
+        t3 = time.perf_counter()
         pinned.copy_(film, non_blocking=False)
         torch.cuda.synchronize(dev)
+        t4 = time.perf_counter()
+        e2e_phases.append([round((b - a) * 1e3, 2) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, t4))] + [round(st["render_ms"], 2)])
         if i < 0:
             continue
         e2e_steps.append((time.perf_counter() - t0) * 1e3)
@@ -293,8 +299,10 @@ def main():
             "fp32": {"kernel": "k_extend", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
                      "nodes_per_ray": nodes_per_ray, "prims_per_ray": prims_per_ray, "flops_per_ray": flops_per_ray,
                      "note": "algorithmic flops (SURVEY 8d: 30 per box test, 41 per primitive test); peak = SMs x 128 lanes x max SM clock, no FMA"},
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": [round(x, 2) for x in e2e_steps], "h2d_bytes_per_step": world.upload_bytes(),
-                    "d2h_bytes_per_step": size.count() * 12, "note": "rt_scene_create (scene hand-off) + render + film read-back to pinned host memory, every step"},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": [round(x, 2) for x in e2e_steps], "h2d_bytes_per_step": scene.device_bytes(),
+                    "scene_desc_bytes": world.upload_bytes(),
+                    "phases_ms": {"columns": ["release", "scene_create", "render_call", "readback", "render_device"], "steps": e2e_phases[1:]},
+                    "d2h_bytes_per_step": size.count() * 12, "note": "rt_scene_create (scene hand-off incl. building and uploading the packed scene) + render + film read-back to pinned host memory, every step"},
             "clocks": clocks, "gpu_launches": int(sum(s["kernel_launches"] for s in stats)) + args.steps,
         }
         if n_gpus == 1 and not args.no_cpu_baseline:

@@ -219,7 +219,9 @@ int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_o
  * reference traversal provably returns the same element (unique minimum, hit point strictly inside the element's parent
  * box of the reference tree), every other ray is traced again with 2 on the reference tree (RtStats.redo_rays); scenes with
  * wrapped elements or volumes always use 2.  "rebuild": 0 = do not build the second topology at rt_scene_create.
- * "rebuild_depth_extra": depth cap of the rebuilt tree above the reference depth (default 3).
+ * "rebuild_depth_extra": depth cap of the rebuilt tree above the reference depth (default 4).  "presplit": reference budget of
+ * the rebuilt tree in per cent of the element count (default 800; <= 100 = one reference per element): sliver triangles are
+ * cut into several references with tighter boxes (an element may sit in several leaves of the accelerator tree).
  * "count": 1 = maintain node_visits / prim_tests / exact_steps.  "profile": 1 = time extend / shade separately.
  * "refill": busy-lane threshold of the persistent extend warps.  "leaf_weight": phase-vote weight.  "check_every": host
  * polling period (iterations).  "pipes": independent wavefront pipelines (streams) per render (default 1).

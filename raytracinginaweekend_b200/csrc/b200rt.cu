@@ -30,9 +30,9 @@ thread_local std::string g_err;
 int g_opt_traversal = 3;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path,
                               // 3 = rebuilt topology + per-ray proof, unproven rays on the reference tree with 2 (plain scenes; else 2)
 int g_opt_fast_order = 0;     // experiment: child order of the fast traversal (0 near-first, 1 split-axis sign, 2 near-first, ties by sign)
-int g_opt_presplit = 400;     // reference budget of the rebuilt tree in per cent of the element count (<= 100: no pre-splitting)
+int g_opt_presplit = 800;     // reference budget of the rebuilt tree in per cent of the element count (<= 100: no pre-splitting)
 int g_opt_rebuild = 1;        // build the second topology at rt_scene_create (0: traversal 3 behaves like 2)
-int g_opt_rebuild_depth_extra = 3;  // depth cap of the rebuilt tree = reference depth + this (the stack lives in shared memory)
+int g_opt_rebuild_depth_extra = 4;  // depth cap of the rebuilt tree = reference depth + this (the stack lives in shared memory)
 int g_opt_pipes = 1;         // independent wavefront pipelines (streams) per render: one pipeline's extend tail overlaps the other's work
 int g_opt_leaf_weight = 24;   // extend phase vote: leaf phase when n_leaf * w > n_node * 16
 int g_opt_refill = 28;        // extend refills idle lanes when fewer than this many of 32 are busy
@@ -384,7 +384,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
         for (uint32_t i = 0; i < N; ++i)
             for (int k = 0; k < 3; ++k) { lb[i].mn[k] = lbox[i].mn[k]; lb[i].mx[k] = lbox[i].mx[k]; }
         // pre-split sliver triangles into several references (rt_rebuild.hpp); the budget shrinks for very large scenes
-        const double factor = g_opt_presplit <= 100 ? 1.0 : std::min((double)g_opt_presplit / 100.0, N <= 150000u ? 8.0 : (N <= 400000u ? 2.0 : 1.0));
+        const double factor = g_opt_presplit <= 100 ? 1.0 : std::min((double)g_opt_presplit / 100.0, N <= 150000u ? 16.0 : (N <= 2000000u ? 2.0 : 1.0));
         if (factor > 1.0) {
             tri.assign(9 * (size_t)N, 0.0f);
             for (uint32_t i = 0; i < N; ++i)

@@ -13,7 +13,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <atomic>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 namespace rt_rebuild {
@@ -38,7 +40,10 @@ inline Box3 empty_box() {
     return b;
 }
 inline void grow(Box3& b, const Box3& o) {
-    for (int k = 0; k < 3; ++k) { b.mn[k] = std::fmin(b.mn[k], o.mn[k]); b.mx[k] = std::fmax(b.mx[k], o.mx[k]); }
+    for (int k = 0; k < 3; ++k) {  // plain comparisons (std::fmin is a libm call at -O2); NaN boxes are rejected upstream
+        b.mn[k] = o.mn[k] < b.mn[k] ? o.mn[k] : b.mn[k];
+        b.mx[k] = o.mx[k] > b.mx[k] ? o.mx[k] : b.mx[k];
+    }
 }
 inline double half_area(const Box3& b) {
     const double x = std::max(0.0, (double)b.mx[0] - b.mn[0]), y = std::max(0.0, (double)b.mx[1] - b.mn[1]), z = std::max(0.0, (double)b.mx[2] - b.mn[2]);
@@ -48,20 +53,24 @@ inline double half_area(const Box3& b) {
 struct Builder {
     const std::vector<Box3>& leaf;
     Tree& out;
-    std::vector<uint32_t> idx;
-    std::vector<float> cen[3];
+    std::vector<uint32_t> own_idx;
+    std::vector<float> own_cen[3];
+    std::vector<uint32_t>& idx;        // element order (partitioned in place); shared between the builders of one build()
+    const std::vector<float>* cen;     // [3] centroids
     uint32_t max_depth;
     static const int BINS = 32;
     static const uint32_t SWEEP_MAX = 96;
 
-    Builder(const std::vector<Box3>& l, Tree& t, uint32_t md) : leaf(l), out(t), max_depth(md) {
-        idx.resize(leaf.size());
-        std::iota(idx.begin(), idx.end(), 0u);
+    Builder(const std::vector<Box3>& l, Tree& t, uint32_t md) : leaf(l), out(t), idx(own_idx), cen(own_cen), max_depth(md) {
+        own_idx.resize(leaf.size());
+        std::iota(own_idx.begin(), own_idx.end(), 0u);
         for (int k = 0; k < 3; ++k) {
-            cen[k].resize(leaf.size());
-            for (size_t i = 0; i < leaf.size(); ++i) cen[k][i] = 0.5f * leaf[i].mn[k] + 0.5f * leaf[i].mx[k];
+            own_cen[k].resize(leaf.size());
+            for (size_t i = 0; i < leaf.size(); ++i) own_cen[k][i] = 0.5f * leaf[i].mn[k] + 0.5f * leaf[i].mx[k];
         }
     }
+    Builder(const std::vector<Box3>& l, Tree& t, uint32_t md, std::vector<uint32_t>* shared_idx, const std::vector<float>* shared_cen)
+        : leaf(l), out(t), idx(*shared_idx), cen(shared_cen), max_depth(md) {}
 
     // returns the split position (lo < mid < hi) after reordering idx[lo, hi)
     uint32_t split(uint32_t lo, uint32_t hi, uint32_t levels_left, uint32_t* axis_out) {
@@ -70,7 +79,11 @@ struct Builder {
         float cmin[3], cmax[3];
         for (int k = 0; k < 3; ++k) { cmin[k] = INFINITY; cmax[k] = -INFINITY; }
         for (uint32_t i = lo; i < hi; ++i)
-            for (int k = 0; k < 3; ++k) { cmin[k] = std::fmin(cmin[k], cen[k][idx[i]]); cmax[k] = std::fmax(cmax[k], cen[k][idx[i]]); }
+            for (int k = 0; k < 3; ++k) {
+                const float c = cen[k][idx[i]];
+                cmin[k] = c < cmin[k] ? c : cmin[k];
+                cmax[k] = c > cmax[k] ? c : cmax[k];
+            }
         int best_axis = -1;
         uint32_t best_pos = 0;  // sweep: number of elements on the left; bins: last left bin
         double best_cost = INFINITY;
@@ -215,9 +228,13 @@ inline float round_up(double v) {
 }
 inline Box3 poly_box(const Poly& p, const Box3& within) {
     Box3 b = empty_box();
-    for (int i = 0; i < p.n; ++i)
-        for (int k = 0; k < 3; ++k) { b.mn[k] = std::fmin(b.mn[k], round_down(p.v[i][k])); b.mx[k] = std::fmax(b.mx[k], round_up(p.v[i][k])); }
-    for (int k = 0; k < 3; ++k) { b.mn[k] = std::fmax(b.mn[k], within.mn[k]); b.mx[k] = std::fmin(b.mx[k], within.mx[k]); }  // never beyond the element's own box
+    for (int k = 0; k < 3; ++k) {
+        double lo = p.v[0][k], hi = p.v[0][k];
+        for (int i = 1; i < p.n; ++i) { lo = p.v[i][k] < lo ? p.v[i][k] : lo; hi = p.v[i][k] > hi ? p.v[i][k] : hi; }
+        const float flo = round_down(lo), fhi = round_up(hi);
+        b.mn[k] = flo > within.mn[k] ? flo : within.mn[k];  // never beyond the box being split
+        b.mx[k] = fhi < within.mx[k] ? fhi : within.mx[k];
+    }
     return b;
 }
 }  // namespace detail
@@ -230,6 +247,7 @@ inline void presplit(const std::vector<Box3>& leaf, const std::vector<float>& tr
     refs.reserve(std::max(budget, leaf.size()));
     std::vector<Poly> polys;
     std::vector<int32_t> poly_of;  // per reference: index into polys or -1
+    if (budget > leaf.size()) { polys.reserve(budget); poly_of.reserve(budget); }
     std::vector<std::pair<double, uint32_t>> heap;
     for (uint32_t i = 0; i < leaf.size(); ++i) {
         refs.push_back(Ref{i, leaf[i]});
@@ -274,15 +292,91 @@ inline void presplit(const std::vector<Box3>& leaf, const std::vector<float>& tr
 }
 
 // max_depth: number of internal levels allowed (>= ceil(log2 n)).  Leaves are indices into `leaf` (boxes of references).
+// Ranges larger than n / (4 x threads) are split on the calling thread; the subtrees below are built concurrently (they work
+// on disjoint ranges of the index array) and appended, so every child still has a larger index than its parent.
 inline void build(const std::vector<Box3>& leaf, uint32_t max_depth, Tree& out) {
     out = Tree();
     uint32_t need = 0;
     while ((1ull << need) < leaf.size()) ++need;
-    detail::Builder b(leaf, out, std::max(max_depth, need));
-    out.left.reserve(leaf.size());
-    out.right.reserve(leaf.size());
-    out.box.reserve(leaf.size());
-    out.root = b.build(0, (uint32_t)leaf.size(), 0);
+    max_depth = std::max(max_depth, need);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const uint32_t PAR_MIN = (uint32_t)std::max<size_t>(1024, leaf.size() / (4 * (size_t)hw));
+    if (leaf.size() < 4096 || hw < 2) {
+        detail::Builder b(leaf, out, max_depth);
+        out.left.reserve(leaf.size());
+        out.right.reserve(leaf.size());
+        out.box.reserve(leaf.size());
+        out.root = b.build(0, (uint32_t)leaf.size(), 0);
+        return;
+    }
+    const uint32_t TASK_BIT = 0x40000000u;
+    struct Task {
+        uint32_t lo, hi, depth;
+        Tree tree;
+    };
+    std::vector<Task> tasks;
+    detail::Builder top(leaf, out, max_depth);
+    // top part: same recursion, but ranges that reach PAR_LEVELS (or get small) become tasks
+    struct TopRec {
+        detail::Builder& b;
+        std::vector<Task>& tasks;
+        uint32_t par_min, task_bit;
+        uint32_t go(uint32_t lo, uint32_t hi, uint32_t depth) {
+            if (hi - lo == 1) return 0x80000000u | b.idx[lo];
+            if (hi - lo <= par_min) {
+                tasks.push_back(Task{lo, hi, depth, Tree()});
+                return task_bit | (uint32_t)(tasks.size() - 1);
+            }
+            const uint32_t me = (uint32_t)b.out.left.size();
+            b.out.left.push_back(0); b.out.right.push_back(0); b.out.box.push_back(detail::empty_box()); b.out.axis.push_back(0);
+            b.out.depth = std::max(b.out.depth, depth + 1);
+            uint32_t ax = 0;
+            const uint32_t mid = b.split(lo, hi, b.max_depth - depth, &ax);
+            b.out.axis[me] = ax;
+            const uint32_t l = go(lo, mid, depth + 1), r = go(mid, hi, depth + 1);
+            b.out.left[me] = l; b.out.right[me] = r;
+            return me;
+        }
+    } rec{top, tasks, PAR_MIN, TASK_BIT};
+    const uint32_t root = rec.go(0, (uint32_t)leaf.size(), 0);
+    const uint32_t n_top = (uint32_t)out.left.size();
+    // subtrees: each task gets its own Builder view (shared, already partitioned index array; disjoint ranges)
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const size_t t = next.fetch_add(1);
+            if (t >= tasks.size()) return;
+            Task& tk = tasks[t];
+            detail::Builder b(leaf, tk.tree, max_depth, &top.idx, top.cen);
+            tk.tree.root = b.build(tk.lo, tk.hi, tk.depth);
+        }
+    };
+    std::vector<std::thread> pool;
+    const unsigned n_thr = (unsigned)std::min<size_t>(hw, tasks.size());
+    for (unsigned i = 1; i < n_thr; ++i) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    // splice
+    std::vector<uint32_t> task_root(tasks.size());
+    for (size_t t = 0; t < tasks.size(); ++t) {
+        const Tree& tr = tasks[t].tree;
+        const uint32_t off = (uint32_t)out.left.size();
+        auto fix = [&](uint32_t c) { return (c & 0x80000000u) ? c : c + off; };
+        for (size_t i = 0; i < tr.left.size(); ++i) {
+            out.left.push_back(fix(tr.left[i])); out.right.push_back(fix(tr.right[i]));
+            out.axis.push_back(tr.axis[i]); out.box.push_back(tr.box[i]);
+        }
+        task_root[t] = fix(tr.root);
+        out.depth = std::max(out.depth, tr.depth);
+    }
+    for (uint32_t i = n_top; i-- > 0;) {  // patch task references, then the top boxes bottom-up
+        for (uint32_t* c : {&out.left[i], &out.right[i]})
+            if (!(*c & 0x80000000u) && (*c & TASK_BIT)) *c = task_root[*c & ~TASK_BIT];
+        Box3 bx = detail::empty_box();
+        for (uint32_t c : {out.left[i], out.right[i]}) detail::grow(bx, (c & 0x80000000u) ? leaf[c & 0x7FFFFFFFu] : out.box[c]);
+        out.box[i] = bx;
+    }
+    out.root = (!(root & 0x80000000u) && (root & TASK_BIT)) ? task_root[root & ~TASK_BIT] : root;
 }
 
 }  // namespace rt_rebuild

@@ -6,7 +6,7 @@ cfgs = {"c2": ("config:c2", (1920, 1080), 64, 64), "c1": ("config:c1", (1200, 80
         "c3": ("config:c3", (1024, 1024), 32, 64), "suz": ("demo:suzanne", (1600, 1200), 16, 16)}
 for key in (sys.argv[1:] or ["c2"]):
     name, size, T, spp = cfgs[key]
-    for ps, extra in ((100, 3), (200, 3), (400, 3), (400, 5), (800, 4)):
+    for ps, extra in [tuple(int(v) for v in a.split(",")) for a in os.environ.get("PS", "100,3 200,3 400,3 400,5 800,4").split()]:
         _cabi.set_option("presplit", ps); _cabi.set_option("rebuild_depth_extra", extra)
         W = rb.World.named(name)
         t0 = time.time(); rb.render(rb.Size2i(64, 36), 1, 1, 50, W, seed=1); t_create = time.time() - t0
