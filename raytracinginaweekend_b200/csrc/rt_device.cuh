@@ -113,6 +113,18 @@ __device__ __forceinline__ float3 with_length3(float3 a, float len) { return mul
 __device__ __forceinline__ float3 unit3(float3 a) { return with_length3(a, 1.0f); }                      // vec3.rs:203-205
 __device__ __forceinline__ float comp3(float3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
+// 256-bit read-only global load (sm_100: LDG.E.256): a 64 B node / primitive record is two requests instead of four.  The
+// extend kernel's deep-bounce launches are bound by L1TEX request throughput (ncu: 85 %), not by bytes.
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg_record(const void* p, float4& q0, float4& q1, float4& q2, float4& q3) {
+    ldg256(p, q0, q1);
+    ldg256(static_cast<const char*>(p) + 32, q2, q3);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Aabb::hit_cond (src/lib/aabb.rs:65-78) + carried-interval bounds
 // ------------------------------------------------------------------------------------------------
@@ -205,7 +217,7 @@ __device__ __forceinline__ bool triangle_t(const PrimDev& p, float3 o, float3 d,
 __device__ __forceinline__ PrimDev load_prim(const PrimDev* p) {
     const float4* q = reinterpret_cast<const float4*>(p);
     PrimDev r;
-    r.q0 = __ldg(q); r.q1 = __ldg(q + 1); r.q2 = __ldg(q + 2); r.q3 = __ldg(q + 3);
+    ldg_record(q, r.q0, r.q1, r.q2, r.q3);
     return r;
 }
 
@@ -273,7 +285,7 @@ __device__ __forceinline__ bool prim_t(uint32_t kind, const float4* q, float3 o,
     if (kind == 0u) return sphere_t(__ldg(q), o, d, start, end, t);
     if (kind == 2u) {
         PrimDev p;
-        p.q0 = __ldg(q); p.q1 = __ldg(q + 1); p.q2 = __ldg(q + 2); p.q3 = __ldg(q + 3);
+        ldg_record(q, p.q0, p.q1, p.q2, p.q3);
         float w1, w2;
         return triangle_t(p, o, d, start, end, t, w1, w2);
     }
@@ -518,8 +530,9 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
     } else if (!at_leaf) {
         if (COUNT) cnt->nodes++;
         const float4* q = reinterpret_cast<const float4*>(S.nodes + cur);
-        const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-        const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));
+        float4 q0, q1, q2, q3f;
+        ldg_record(q, q0, q1, q2, q3f);
+        const uint4 q3 = make_uint4(__float_as_uint(q3f.x), __float_as_uint(q3f.y), __float_as_uint(q3f.z), __float_as_uint(q3f.w));
         const bool leafL = (q3.x & RT_REF_LEAF) != 0u, leafR = (q3.y & RT_REF_LEAF) != 0u;
         float tnL, tfL, tnR, tfR, mgL = 0.0f, mgR = 0.0f;
         bool pL, pR, need_exact;
@@ -649,8 +662,9 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
     } else if (!at_leaf) {
         if (COUNT) cnt->nodes++;
         const float4* q = reinterpret_cast<const float4*>(S.nodes2 + cur);
-        const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-        const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));
+        float4 q0, q1, q2, q3f;
+        ldg_record(q, q0, q1, q2, q3f);
+        const uint4 q3 = make_uint4(__float_as_uint(q3f.x), __float_as_uint(q3f.y), __float_as_uint(q3f.z), __float_as_uint(q3f.w));
         float tnL, tfL, tnR, tfR;
         approx_slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T, tnL, tfL);
         approx_slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, tnR, tfR);
@@ -812,7 +826,7 @@ __device__ __forceinline__ Interaction make_interaction(const SceneDev& S, uint3
         if (want_uv) sphere_uv(sn, hi.u, hi.v);
     } else if (kind == 2u) {
         PrimDev p;
-        p.q0 = __ldg(q); p.q1 = __ldg(q + 1); p.q2 = __ldg(q + 2); p.q3 = __ldg(q + 3);
+        ldg_record(q, p.q0, p.q1, p.q2, p.q3);
         float3 p0 = f3(p.q0.x, p.q0.y, p.q0.z);
         float3 qq = sub3(pos, p0);
         float w1 = dot3(qq, f3(p.q1.z, p.q1.w, p.q2.x)) / p.q2.y;

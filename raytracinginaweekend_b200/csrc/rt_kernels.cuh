@@ -140,7 +140,7 @@ __device__ __forceinline__ uint32_t queue_pos(uint32_t i, uint32_t nb, uint32_t 
 // separate redo launch would serialise the few longest rays of every iteration into its own tail.
 #define RT_REFMODE_BIT 16u  // Trav::dpos: this lane is (re)tracing on the reference tree
 template <int MODE, bool COUNT, int FEAT>
-__global__ void __launch_bounds__(128, 9) k_extend(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
+__global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
     extern __shared__ uint32_t smem[];
     uint32_t* stk_ref = smem + threadIdx.x;
     float* stk_tn = reinterpret_cast<float*>(smem + S.stack_cap * blockDim.x) + threadIdx.x;
