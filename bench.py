@@ -229,7 +229,7 @@ def main():
     barrier()
     e2e_ms, e2e_rays = 0.0, 0.0
     e2e_steps, e2e_phases = [], []
-    for i in range(-1, max(1, args.steps)):   # i = -1: one untimed warm-up of this code path (first-use allocations)
+    for i in range(-min(3, max(1, args.warmup)), max(1, args.steps)):   # i < 0: untimed warm-up of this code path (like the W steps above)
         t0 = time.perf_counter()
         world.release_device()
         t1 = time.perf_counter()
@@ -301,7 +301,7 @@ def main():
                      "note": "algorithmic flops (SURVEY 8d: 30 per box test, 41 per primitive test); peak = SMs x 128 lanes x max SM clock, no FMA"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": [round(x, 2) for x in e2e_steps], "h2d_bytes_per_step": scene.device_bytes(),
                     "scene_desc_bytes": world.upload_bytes(),
-                    "phases_ms": {"columns": ["release", "scene_create", "render_call", "readback", "render_device"], "steps": e2e_phases[1:]},
+                    "phases_ms": {"columns": ["release", "scene_create", "render_call", "readback", "render_device"], "steps": e2e_phases[-len(e2e_steps):]},
                     "d2h_bytes_per_step": size.count() * 12, "note": "rt_scene_create (scene hand-off incl. building and uploading the packed scene) + render + film read-back to pinned host memory, every step"},
             "clocks": clocks, "gpu_launches": int(sum(s["kernel_launches"] for s in stats)) + args.steps,
         }

@@ -472,9 +472,18 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
 
     // upload
     CU(cudaSetDevice(sc.device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, sc.device));
-    sc.sm_count = prop.multiProcessorCount;
+    {   // one attribute, cached per device (cudaGetDeviceProperties walks every attribute and can take tens of milliseconds)
+        static std::mutex mu;
+        static std::map<int, int> sm_of;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = sm_of.find(sc.device);
+        if (it == sm_of.end()) {
+            int v = 0;
+            CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, sc.device));
+            it = sm_of.emplace(sc.device, v).first;
+        }
+        sc.sm_count = it->second;
+    }
     CU(sc.nodes.alloc(std::max<size_t>(nodes.size(), 1)));
     CU(sc.prims.alloc(N));
     CU(sc.shade.alloc(N));

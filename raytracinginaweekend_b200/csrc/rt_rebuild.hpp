@@ -299,7 +299,7 @@ inline void build(const std::vector<Box3>& leaf, uint32_t max_depth, Tree& out) 
     uint32_t need = 0;
     while ((1ull << need) < leaf.size()) ++need;
     max_depth = std::max(max_depth, need);
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned hw = std::min(std::max(1u, std::thread::hardware_concurrency()), leaf.size() < 100000 ? 8u : 32u);
     const uint32_t PAR_MIN = (uint32_t)std::max<size_t>(1024, leaf.size() / (4 * (size_t)hw));
     if (leaf.size() < 4096 || hw < 2) {
         detail::Builder b(leaf, out, max_depth);
