@@ -29,7 +29,6 @@ namespace {
 thread_local std::string g_err;
 int g_opt_traversal = 3;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path,
                               // 3 = rebuilt topology + per-ray proof, unproven rays on the reference tree with 2 (plain scenes; else 2)
-int g_opt_fast_order = 0;     // experiment: child order of the fast traversal (0 near-first, 1 split-axis sign, 2 near-first, ties by sign)
 int g_opt_presplit = 800;     // reference budget of the rebuilt tree in per cent of the element count (<= 100: no pre-splitting)
 int g_opt_rebuild = 1;        // build the second topology at rt_scene_create (0: traversal 3 behaves like 2)
 int g_opt_rebuild_depth_extra = 4;  // depth cap of the rebuilt tree = reference depth + this (the stack lives in shared memory)
@@ -669,7 +668,6 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     R.ref_only = g_opt_traversal == 0 ? 1u : 0u;
     R.refill_threshold = (uint32_t)std::min(32, std::max(1, g_opt_refill));
     R.leaf_weight = (uint32_t)std::max(1, g_opt_leaf_weight);
-    R.fast_order = (uint32_t)g_opt_fast_order;
 
     // Split the rank's lanes over G independent wavefront pipelines, each on its own stream with its own queues and
     // counters.  A persistent extend launch ends with a tail in which a few very long rays keep a few warps busy; with two
@@ -883,7 +881,6 @@ int rt_set_option(const char* key, int64_t value) {
     if (k == "traversal") g_opt_traversal = (int)value;
     else if (k == "rebuild") g_opt_rebuild = (int)value;
     else if (k == "presplit") g_opt_presplit = (int)value;
-    else if (k == "fast_order") g_opt_fast_order = (int)value;
     else if (k == "rebuild_depth_extra") g_opt_rebuild_depth_extra = (int)value;
     else if (k == "profile") g_opt_profile = (int)value;
     else if (k == "count") g_opt_count = (int)value;

@@ -406,17 +406,20 @@ struct Trav {
 // slab has a huge tn for a box it misses; evaluating the quadratic sphere term there would make the band useless.)
 // If g' > 1/2 at te (grazing rays, huge distances) the band is infinite: no tight cull.
 // G2(t) := 2 g(t) = sA + t (sB + sC t)  with sA = A mscale (+ approximation error), sB = 1e-5 mscale, sC = C mscale.
-// Independently of that, every accepted t is < end, so G2(end) is always a valid band once a hit has made end finite.
-__device__ __forceinline__ float guard_band(float sA, float sB, float sC, float tf, float start, float end) {
+// Independently of that, every accepted t is < end, so G2(end) is always a valid band once a hit has made end finite
+// (band_at_end: the same for both children of a node, computed once).
+__device__ __forceinline__ float band_at_end(float sA, float sB, float sC, float end) {
+    return __fmaf_rn(end, __fmaf_rn(sC, end, sB), sA);  // +inf (or NaN from 0 * inf, ignored by fminf) while end = inf
+}
+__device__ __forceinline__ float guard_band(float sA, float sB, float sC, float tf, float start, float at_end) {
     const float tfp = fmaxf(tf, start);
     const float te = tfp + __fmaf_rn(tfp, __fmaf_rn(sC, tfp, sB), sA);
     const float mg = __fmaf_rn(te, __fmaf_rn(sC, te, sB), sA);
-    const float at_end = __fmaf_rn(end, __fmaf_rn(sC, end, sB), sA);  // +inf (or NaN from 0 * inf, ignored by fminf) while end = inf
     return fminf((__fmaf_rn(2.0f * sC, te, sB) <= 1.0f) ? mg : __int_as_float(0x7f800000), at_end);  // NaN compares false: no cull
 }
 __device__ __forceinline__ float node_margin(uint32_t packed, float tf, float start, float end, float mscale) {
     const float a = __uint_as_float(packed & 0xFFFF0000u), c = __uint_as_float(packed << 16);
-    return guard_band(a * mscale, 1e-5f * mscale, c * mscale, tf, start, end);
+    return guard_band(a * mscale, 1e-5f * mscale, c * mscale, tf, start, band_at_end(a * mscale, 1e-5f * mscale, c * mscale, end));
 }
 
 // Root box test of BoundingVolumeHierarchy::hit (hittable.rs:472 -> hit_recursive(initial_index)): the reference rule, plus the
@@ -541,8 +544,9 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
             approx_slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, tnR, tfR);
             // guard band in t (tn >= start >= 0 here): (A + 1e-5 t + C t^2) * mscale, plus the approximation error
             const float sA = __fmaf_rn(__uint_as_float(q3.w & 0xFFFF0000u), T.mscale, T.oe), sC = __uint_as_float(q3.w << 16) * T.mscale;
-            mgL = guard_band(sA, T.sB, sC, tfL, T.start, T.end);
-            mgR = guard_band(sA, T.sB, sC, tfR, T.start, T.end);
+            const float at_end = band_at_end(sA, T.sB, sC, T.end);
+            mgL = guard_band(sA, T.sB, sC, tfL, T.start, at_end);
+            mgR = guard_band(sA, T.sB, sC, tfR, T.start, at_end);
             bool cullL = tnL - tfL > mgL, cullR = tnR - tfR > mgR;
             // second chance for a child whose carried interval is empty, but by less than the scalar band: the per-axis padded
             // test (strictly tighter; rare for ordinary rays, the normal case for rays nearly parallel to an axis)
@@ -634,7 +638,6 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
 // The caller accepts the result only if !tie and ref_visible(); everything else is traced again on the reference tree.
 // ------------------------------------------------------------------------------------------------
 #define RT_TIE_BIT 8u  // kept in Trav::dpos next to the direction signs (bits 0..2)
-#define RT_ORDER_SHIFT 5u  // experiment: child-order policy in bits 5..6 of Trav::dpos
 
 template <bool COUNT>
 __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool do_leaf, uint32_t* stk_ref, float* stk_tn,
@@ -669,8 +672,9 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
         approx_slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T, tnL, tfL);
         approx_slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, tnR, tfR);
         const float sA = __fmaf_rn(__uint_as_float(q3.w & 0xFFFF0000u), T.mscale, T.oe), sC = __uint_as_float(q3.w << 16) * T.mscale;
-        float mgL = guard_band(sA, T.sB, sC, tfL, T.start, T.end);
-        float mgR = guard_band(sA, T.sB, sC, tfR, T.start, T.end);
+        const float at_end = band_at_end(sA, T.sB, sC, T.end);
+        float mgL = guard_band(sA, T.sB, sC, tfL, T.start, at_end);
+        float mgR = guard_band(sA, T.sB, sC, tfR, T.start, at_end);
         bool pL = !(tnL - tfL > mgL), pR = !(tnR - tfR > mgR);
         if (pL && tnL > tfL) {  // empty by less than the scalar band: per-axis padded second chance (see padded_cull)
             float pn;
@@ -682,9 +686,7 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
             pR = !padded_cull(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, q3.w, pn);
             mgR = tnR - pn;
         }
-        const bool sign_first = ((T.dpos >> q3.z) & 1u) != 0u;  // dir[split axis] > 0: the lower-centroid (left) child lies behind
-        const uint32_t policy = (T.dpos >> RT_ORDER_SHIFT) & 3u;
-        const bool left_first = policy == 1u ? sign_first : (policy == 2u ? (tnL < tnR || (tnL == tnR && sign_first)) : tnL <= tnR);
+        const bool left_first = tnL <= tnR;  // near-first (ordering by the split-axis sign, or as a tie-break, measured within 1 %)
         const uint32_t c1 = left_first ? q3.x : q3.y, c2 = left_first ? q3.y : q3.x;
         const bool p1 = left_first ? pL : pR, p2 = left_first ? pR : pL;
         if (p1 && p2) {
@@ -714,9 +716,9 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
 // Can the fast traversal be used for this ray?  Not for degenerate directions (zero / denormal / non-finite components,
 // trav_setup): the approximate slab arithmetic is not defined for them; the reference tree's exact path is.
 __device__ __forceinline__ bool fast_eligible(const Trav& T) { return !T.exact_only; }
-__device__ __forceinline__ void trav_setup_fast(const SceneDev& S, Trav& T, uint32_t policy = 0u) {
+__device__ __forceinline__ void trav_setup_fast(const SceneDev& S, Trav& T) {
     T.cur = S.root2;
-    T.dpos = (T.dpos & 7u) | (policy << RT_ORDER_SHIFT);
+    T.dpos &= 7u;
 }
 
 // Does the reference traversal provably return element `ref` at `t` (given that it is the UNIQUE minimum of all accepted

@@ -39,7 +39,6 @@ struct RenderDev {
     uint32_t pipe, n_pipes;  // rank-local lanes are dealt round-robin to n_pipes independent wavefront pipelines (streams)
     uint32_t refill_threshold;  // extend refills idle lanes when fewer than this many lanes are busy
     uint32_t leaf_weight;       // phase vote: leaf phase runs when n_leaf * leaf_weight > n_node * 16
-    uint32_t fast_order;        // experiment knob (traversal 3 child order)
     uint32_t npix, width, height;
     int32_t max_depth;
     uint32_t n_tasks;        // T' = lanes that got >= 1 sample (split_work_tasks)
@@ -181,7 +180,7 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
                     active = true;
                     if (MODE == 3) {
                         if (!fast_eligible(T)) T.dpos |= RT_REFMODE_BIT;  // degenerate or near-axis-parallel direction: reference tree only
-                        else trav_setup_fast(S, T, R.fast_order);
+                        else trav_setup_fast(S, T);
                     }
                 }
             }
