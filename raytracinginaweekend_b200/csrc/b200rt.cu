@@ -114,6 +114,7 @@ struct RtScene {
     DevBuf<float4> vis_box;
     uint32_t depth2 = 0;
     bool has_animation = false;
+    bool boxes_are_bounds = true;  // every node box contains its children's boxes (false: MODE 0 only, see pack_scene)
     bool has_wrapped = false, has_volume = false;  // pick the k_extend instantiation (plain / wrappers / wrappers + volumes)
     DevBuf<MaterialDev> materials;
     DevBuf<TextureDev> textures;
@@ -371,12 +372,24 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     }
     sc.depth = depth;
 
+    // The tight cull (MODE >= 1) and the visibility proof of MODE 3 rely on what the reference builder guarantees: a node's box
+    // contains the boxes of its children (it is their union).  A caller-made tree that breaks this is still traversed exactly
+    // as given, but only with the reference's own node rule (MODE 0) and without the rebuilt topology.
+    sc.boxes_are_bounds = true;
+    for (uint32_t i = 0; i < d.n_nodes && sc.boxes_are_bounds; ++i)
+        for (uint32_t ch : {d.nodes[i].left, d.nodes[i].right}) {
+            if ((ch & RT_LEAF_BIT) && d.items[ch & ~RT_LEAF_BIT].wrap_flags) continue;  // Q2 boxes: no tight cull around them anyway
+            const Box cb = child_box(ch);
+            for (int k = 0; k < 3; ++k)
+                if (!(cb.mn[k] >= d.nodes[i].aabb_min[k] && cb.mx[k] <= d.nodes[i].aabb_max[k])) sc.boxes_are_bounds = false;
+        }
+
     // Row f4: second topology (SAH) over the same elements.  Plain scenes only: wrapped elements have boxes that are not
     // true bounds (Q2) and volumes draw random numbers per tested element, so those scenes keep the reference tree alone.
     std::vector<NodeDev> nodes2;
     std::vector<float4> vis_box;
     uint32_t root2 = 0;
-    if (!any_wrap && N >= 2 && g_opt_rebuild) {
+    if (!any_wrap && N >= 2 && g_opt_rebuild && sc.boxes_are_bounds) {
         std::vector<rt_rebuild::Box3> lb(N);
         std::vector<float> tri;
         std::vector<uint8_t> is_tri(N, 0);
@@ -665,7 +678,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     R.sx = 1.0f / (float)(P.width - 1);
     R.sy = 1.0f / (float)(P.height - 1);
     R.mode = P.render_mode;
-    R.ref_only = g_opt_traversal == 0 ? 1u : 0u;
+    R.ref_only = (g_opt_traversal == 0 || !sc.boxes_are_bounds) ? 1u : 0u;
     R.refill_threshold = (uint32_t)std::min(32, std::max(1, g_opt_refill));
     R.leaf_weight = (uint32_t)std::max(1, g_opt_leaf_weight);
 
@@ -709,6 +722,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     const size_t esmem = stack_smem_bytes(sc, eblock);
     int egrid = 0, sgrid = 0;
     int mode = std::min(3, std::max(0, g_opt_traversal));
+    if (!sc.boxes_are_bounds) mode = 0;
     if (mode == 3 && !sc.nodes2.p) mode = 2;  // no rebuilt topology for this scene (wrapped elements, single element, rebuild off)
     ExtendFn ext = mode == 3 ? (g_opt_count ? k_extend<3, true, 0> : k_extend<3, false, 0>)
                              : pick_extend(mode, g_opt_count != 0, sc.has_volume ? 2 : (sc.has_wrapped ? 1 : 0));
@@ -939,7 +953,7 @@ int rt_trace_device(RtScene* scene, const float* d_org, const float* d_dir, uint
     const int block = 128;
     const size_t smem = stack_smem_bytes(*scene, block);
     int grid = 0, rc;
-    const int mode = std::min(3, std::max(0, g_opt_traversal));
+    const int mode = scene->boxes_are_bounds ? std::min(3, std::max(0, g_opt_traversal)) : 0;
     auto trc = mode == 3 ? k_trace<3> : (mode == 2 ? k_trace<2> : (mode == 1 ? k_trace<1> : k_trace<0>));
     rc = persistent_grid(*scene, trc, block, smem, &grid);
     if (rc) return rc;

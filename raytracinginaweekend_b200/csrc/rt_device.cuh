@@ -367,7 +367,7 @@ __device__ __forceinline__ bool leaf_test(const SceneDev& S, uint32_t ref, float
 //     MODE 2: MODE 1 decisions, but evaluated with one reciprocal per ray and multiplies.  Whenever the
 //             approximate values cannot prove the decision (within RT_BAND relative, or the ray has a zero /
 //             denormal direction component) the exact MODE 1 code runs instead, so the visited set is identical.
-// Stack: shared memory, [level][thread] so lanes never bank-conflict.
+// Stack: shared memory, [level][thread] entries of 8 B (child reference, cull threshold): one 64-bit access per push / pop.
 // ------------------------------------------------------------------------------------------------
 struct HitRec {
     uint32_t ref;  // child reference of the closest primitive, RT_NO_HIT if none
@@ -519,7 +519,7 @@ __device__ __forceinline__ bool padded_cull(float mnx, float mny, float mnz, flo
 // interleaving 17-lane node steps with 4-lane leaf tests.  Per-lane visit order is untouched.
 // Returns false when the lane's traversal is finished.
 template <int MODE, bool COUNT, class KEYFN>
-__device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_leaf, uint32_t* stk_ref, float* stk_tn,
+__device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_leaf, uint2* stk,
                                            uint32_t stk_stride, TravCount* cnt, const KEYFN& keyfn) {
     uint32_t cur = T.cur;
     const bool at_leaf = (cur & RT_REF_LEAF) != 0u;
@@ -590,8 +590,7 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
             float tn2 = left_first ? tnR : tnL;
             // leaf entries carry their cull threshold (tn - guard band), internal entries carry tn
             if (c2 & RT_REF_LEAF) tn2 = (MODE >= 1) ? tn2 - (left_first ? mgR : mgL) : -__int_as_float(0x7f800000);
-            stk_ref[T.sp * stk_stride] = c2;
-            stk_tn[T.sp * stk_stride] = tn2;
+            stk[T.sp * stk_stride] = make_uint2(c2, __float_as_uint(tn2));
             ++T.sp;
             if (COUNT) cnt->max_sp = max(cnt->max_sp, T.sp);
         }
@@ -603,8 +602,9 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
         for (;;) {
             if (T.sp == 0) return false;
             --T.sp;
-            cur = stk_ref[T.sp * stk_stride];
-            const float tn = stk_tn[T.sp * stk_stride];
+            const uint2 e = stk[T.sp * stk_stride];
+            cur = e.x;
+            const float tn = __uint_as_float(e.y);
             if (cur & RT_REF_LEAF) {
                 if (T.end < tn) continue;  // tight cull with the shrunken range (never taken in MODE 0: tn = -inf)
                 break;
@@ -640,7 +640,7 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
 #define RT_TIE_BIT 8u  // kept in Trav::dpos next to the direction signs (bits 0..2)
 
 template <bool COUNT>
-__device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool do_leaf, uint32_t* stk_ref, float* stk_tn,
+__device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool do_leaf, uint2* stk,
                                                 uint32_t stk_stride, TravCount* cnt) {
     uint32_t cur = T.cur;
     const bool at_leaf = (cur & RT_REF_LEAF) != 0u;
@@ -672,9 +672,9 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
         approx_slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T, tnL, tfL);
         approx_slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T, tnR, tfR);
         const float sA = __fmaf_rn(__uint_as_float(q3.w & 0xFFFF0000u), T.mscale, T.oe), sC = __uint_as_float(q3.w << 16) * T.mscale;
-        const float at_end = band_at_end(sA, T.sB, sC, T.end);
-        float mgL = guard_band(sA, T.sB, sC, tfL, T.start, at_end);
-        float mgR = guard_band(sA, T.sB, sC, tfR, T.start, at_end);
+        // one band for both children, taken at the later of the two exits (the band grows with t: valid for both, 8 instructions less)
+        const float mgB = guard_band(sA, T.sB, sC, fmaxf(tfL, tfR), T.start, band_at_end(sA, T.sB, sC, T.end));
+        float mgL = mgB, mgR = mgB;
         bool pL = !(tnL - tfL > mgL), pR = !(tnR - tfR > mgR);
         if (pL && tnL > tfL) {  // empty by less than the scalar band: per-axis padded second chance (see padded_cull)
             float pn;
@@ -690,8 +690,7 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
         const uint32_t c1 = left_first ? q3.x : q3.y, c2 = left_first ? q3.y : q3.x;
         const bool p1 = left_first ? pL : pR, p2 = left_first ? pR : pL;
         if (p1 && p2) {
-            stk_ref[T.sp * stk_stride] = c2;
-            stk_tn[T.sp * stk_stride] = left_first ? tnR - mgR : tnL - mgL;  // cull threshold of the deferred child
+            stk[T.sp * stk_stride] = make_uint2(c2, __float_as_uint(left_first ? tnR - mgR : tnL - mgL));  // ref + cull threshold of the deferred child
             ++T.sp;
             if (COUNT) cnt->max_sp = max(cnt->max_sp, T.sp);
         }
@@ -703,8 +702,9 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
         for (;;) {
             if (T.sp == 0) return false;
             --T.sp;
-            cur = stk_ref[T.sp * stk_stride];
-            if (T.end < stk_tn[T.sp * stk_stride]) continue;
+            const uint2 e = stk[T.sp * stk_stride];
+            cur = e.x;
+            if (T.end < __uint_as_float(e.y)) continue;
             break;
         }
         T.cur = cur;
@@ -742,29 +742,28 @@ __device__ __forceinline__ bool ref_visible(const SceneDev& S, uint32_t ref, flo
 }
 
 template <int MODE, bool COUNT, class KEYFN>
-__device__ __forceinline__ bool trav_step(const SceneDev& S, Trav& T, uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride,
+__device__ __forceinline__ bool trav_step(const SceneDev& S, Trav& T, uint2* stk, uint32_t stk_stride,
                                           TravCount* cnt, const KEYFN& keyfn) {
-    return trav_round<MODE, COUNT>(S, T, (T.cur & RT_REF_LEAF) != 0u, stk_ref, stk_tn, stk_stride, cnt, keyfn);
+    return trav_round<MODE, COUNT>(S, T, (T.cur & RT_REF_LEAF) != 0u, stk, stk_stride, cnt, keyfn);
 }
 
 template <int MODE, bool COUNT = false, class KEYFN>
 __device__ __forceinline__ HitRec traverse(const SceneDev& S, float3 o, float3 d, float time, float start, float end_in,
-                                           uint32_t* stk_ref, float* stk_tn, uint32_t stk_stride, const KEYFN& keyfn,
+                                           uint2* stk, uint32_t stk_stride, const KEYFN& keyfn,
                                            TravCount* cnt = nullptr) {
     Trav T;
     HitRec best;
     best.ref = RT_NO_HIT;
     best.t = end_in;
     if (!trav_begin<MODE>(S, T, o, d, time, start, end_in)) return best;
-    while (trav_step<MODE, COUNT>(S, T, stk_ref, stk_tn, stk_stride, cnt, keyfn)) {}
+    while (trav_step<MODE, COUNT>(S, T, stk, stk_stride, cnt, keyfn)) {}
     best.ref = T.best;
     best.t = T.end;
     return best;
 }
 
 // Whole-ray form of the fast path (rt_trace).  *proven = false -> the caller must trace the ray on the reference tree.
-__device__ __forceinline__ HitRec traverse_fast(const SceneDev& S, float3 o, float3 d, float start, float end_in, uint32_t* stk_ref,
-                                                float* stk_tn, uint32_t stk_stride, bool* proven) {
+__device__ __forceinline__ HitRec traverse_fast(const SceneDev& S, float3 o, float3 d, float start, float end_in, uint2* stk, uint32_t stk_stride, bool* proven) {
     Trav T;
     HitRec best;
     best.ref = RT_NO_HIT;
@@ -774,7 +773,7 @@ __device__ __forceinline__ HitRec traverse_fast(const SceneDev& S, float3 o, flo
     if (!fast_eligible(T)) return best;
     if (!root_gate(S, o, d, start, end_in, false)) { *proven = true; return best; }  // the reference root test itself fails
     trav_setup_fast(S, T);
-    while (trav_round_fast<false>(S, T, (T.cur & RT_REF_LEAF) != 0u, stk_ref, stk_tn, stk_stride, nullptr)) {}
+    while (trav_round_fast<false>(S, T, (T.cur & RT_REF_LEAF) != 0u, stk, stk_stride, nullptr)) {}
     best.ref = T.best;
     best.t = T.end;
     *proven = T.best == RT_NO_HIT || (!(T.dpos & RT_TIE_BIT) && ref_visible(S, T.best, o, d, T.end));

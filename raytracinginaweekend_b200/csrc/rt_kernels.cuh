@@ -140,9 +140,8 @@ __device__ __forceinline__ uint32_t queue_pos(uint32_t i, uint32_t nb, uint32_t 
 #define RT_REFMODE_BIT 16u  // Trav::dpos: this lane is (re)tracing on the reference tree
 template <int MODE, bool COUNT, int FEAT>
 __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
-    extern __shared__ uint32_t smem[];
-    uint32_t* stk_ref = smem + threadIdx.x;
-    float* stk_tn = reinterpret_cast<float*>(smem + S.stack_cap * blockDim.x) + threadIdx.x;
+    extern __shared__ uint2 smem[];
+    uint2* stk = reinterpret_cast<uint2*>(smem) + threadIdx.x;
     const uint32_t nb = R.ctr->nb[q], n = nb + R.ctr->nn[q];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -201,10 +200,10 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
         if (active) {
             bool more;
             if constexpr (MODE == 3) {
-                if (T.dpos & RT_REFMODE_BIT) more = trav_round<2, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
-                else more = trav_round_fast<COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc);
+                if (T.dpos & RT_REFMODE_BIT) more = trav_round<2, COUNT>(S, T, do_leaf, stk, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
+                else more = trav_round_fast<COUNT>(S, T, do_leaf, stk, blockDim.x, &tc);
             } else {
-                more = trav_round<MODE, COUNT>(S, T, do_leaf, stk_ref, stk_tn, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
+                more = trav_round<MODE, COUNT>(S, T, do_leaf, stk, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
             }
             if (!more) {
                 if (MODE == 3 && !(T.dpos & RT_REFMODE_BIT) && T.best != RT_NO_HIT &&
@@ -507,9 +506,8 @@ __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ SceneDev 
                                                uint32_t* __restrict__ hit_id, float* __restrict__ t_out,
                                                float* __restrict__ normal, uint8_t* __restrict__ front_face,
                                                float* __restrict__ uv) {
-    extern __shared__ uint32_t smem[];
-    uint32_t* stk_ref = smem + threadIdx.x;
-    float* stk_tn = reinterpret_cast<float*>(smem + S.stack_cap * blockDim.x) + threadIdx.x;
+    extern __shared__ uint2 smem[];
+    uint2* stk = reinterpret_cast<uint2*>(smem) + threadIdx.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]);
         float3 d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
@@ -519,12 +517,12 @@ __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ SceneDev 
         // ray outside that contract the reference arithmetic is not the geometric intersection, so no true-bound cull applies
         const float dd = dot3(d, d);
         if (MODE != 0 && !(fabsf(dd - 1.0f) <= 1e-5f)) {
-            h = traverse<0, false>(S, o, d, S.trace_time, t_min, t_max, stk_ref, stk_tn, blockDim.x, TraceKey{i});
+            h = traverse<0, false>(S, o, d, S.trace_time, t_min, t_max, stk, blockDim.x, TraceKey{i});
         } else if constexpr (MODE == 3) {
-            if (S.nodes2) h = traverse_fast(S, o, d, t_min, t_max, stk_ref, stk_tn, blockDim.x, &proven);
-            if (!proven) h = traverse<2, false>(S, o, d, S.trace_time, t_min, t_max, stk_ref, stk_tn, blockDim.x, TraceKey{i});
+            if (S.nodes2) h = traverse_fast(S, o, d, t_min, t_max, stk, blockDim.x, &proven);
+            if (!proven) h = traverse<2, false>(S, o, d, S.trace_time, t_min, t_max, stk, blockDim.x, TraceKey{i});
         } else {
-            h = traverse<MODE, false>(S, o, d, S.trace_time, t_min, t_max, stk_ref, stk_tn, blockDim.x, TraceKey{i});
+            h = traverse<MODE, false>(S, o, d, S.trace_time, t_min, t_max, stk, blockDim.x, TraceKey{i});
         }
         if (h.ref != RT_NO_HIT) {
             Interaction hi = make_interaction(S, h.ref, h.t, o, d, S.trace_time, true);

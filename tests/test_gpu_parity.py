@@ -366,6 +366,34 @@ def test_traversal_stack_stays_within_capacity(name, mode):
     assert 0 < st["max_stack"] <= st["stack_capacity"], st
 
 
+def test_caller_tree_with_non_bounding_boxes_is_traversed_as_given(oracle):
+    """The C ABI takes the BVH as data.  If a node box does not contain its children (never the case for the reference's own
+    builder) the true-bound culls and the rebuilt topology are not valid: the scene is then traversed with the reference's
+    node rule alone, exactly as given — elements behind the shrunken box become invisible, as they would in the reference."""
+    sc = random_scene(71, n_spheres=30, n_tris=30, n_rects=0)
+    fs = rb.World.from_elements(**sc).export()
+    org, dir = random_rays(fs, 30000, 3)
+    good = _cabi.DeviceScene.from_flat(fs)
+    ref = good.trace(org, dir)
+    import copy
+    bad_fs = copy.deepcopy(fs)
+    k = int(fs.nodes_lra[fs.root, 0]) if not (int(fs.nodes_lra[fs.root, 0]) & 0x80000000) else int(fs.nodes_lra[fs.root, 1])
+    mid = 0.5 * (bad_fs.nodes_box[k, :3] + bad_fs.nodes_box[k, 3:])
+    bad_fs.nodes_box[k, :3] = mid - 0.05; bad_fs.nodes_box[k, 3:] = mid + 0.05      # a child of the root claims a tiny box
+    bad = _cabi.DeviceScene.from_flat(bad_fs)
+    got = {}
+    for mode in (0, 2, 3):
+        _cabi.set_option("traversal", mode)
+        got[mode] = bad.trace(org, dir)
+    for mode in (2, 3):
+        assert np.array_equal(got[mode]["hit_id"], got[0]["hit_id"]) and np.array_equal(got[mode]["t"].view(np.uint32), got[0]["t"].view(np.uint32))
+    assert (got[0]["hit_id"] != ref["hit_id"]).sum() > 100          # the given box is honoured, not recomputed
+    img0 = bad.render(64, 48, 4, 20, 2, 5)[0]
+    _cabi.set_option("traversal", 0)
+    img1 = bad.render(64, 48, 4, 20, 2, 5)[0]
+    assert images_equal_bits(img0, img1)
+
+
 def test_lane_count_only_changes_summation_order():
     """Sample set is keyed by (pixel, global sample index): T lanes vs 1 lane differ only by the merge order (Q12)."""
     w = product_world("config:c3")
