@@ -261,6 +261,16 @@ def main():
         n_ext = sum(s["iterations"] for s in stats)
         rays_rank0 = sum(s["ray_segments"] for s in stats)
         achieved = rays_rank0 * EXTEND_BYTES_PER_RAY / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+        # one extra (untimed) step with a single wavefront pipeline: kernels then run back to back, so per-launch CUDA-event times
+        # are comparable with the (serialised) ncu launch list and extend's share of the step is well defined
+        _cabi.set_option("pipes", 1)
+        pst = scene.render_planes_device(plane.data_ptr(), rank, n_gpus, size.width, size.height, spp_total, MAX_DEPTH, lanes_total,
+                                         200, 0, stream.cuda_stream)
+        _cabi.set_option("pipes", 2)
+        torch.cuda.synchronize(dev)
+        serial = {"pipes": 1, "step_ms": pst["render_ms"], "extend_ms": pst["extend_ms"], "shade_ms": pst["shade_ms"],
+                  "avg_launch_ms": pst["extend_ms"] / max(1, pst["iterations"]), "share_of_step": pst["extend_ms"] / max(1e-9, pst["render_ms"]),
+                  "achieved_gbs": pst["ray_segments"] * EXTEND_BYTES_PER_RAY / (pst["extend_ms"] * 1e-3) / 1e9}
         # one extra (untimed) step with the counting kernel variant: node visits / primitive tests per ray -> FP32 issue roofline
         _cabi.set_option("count", 1)
         cst = scene.render_planes_device(plane.data_ptr(), rank, n_gpus, size.width, size.height, spp_total, MAX_DEPTH, lanes_total,
@@ -294,8 +304,11 @@ def main():
             "roofline": {"kernel": "k_extend", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                          "bytes_per_ray": EXTEND_BYTES_PER_RAY, "launches": n_ext, "avg_launch_ms": ext_ms / max(1, n_ext),
-                         "share_of_step": ext_ms / max(1e-9, sum(step_ms)),
-                         "note": "scene (nodes+primitives) is L2-resident, so the kernel is FP32-issue / latency bound: see fp32"},
+                         "share_of_step": serial["share_of_step"], "serial_probe": serial,
+                         "note": "scene (nodes+primitives) is L2-resident, so the kernel is FP32-issue / latency bound: see fp32. The timed region "
+                                 "runs two wavefront pipelines on separate streams: avg_launch_ms / achieved are per-launch CUDA-event times "
+                                 "under that overlap; serial_probe repeats one step with a single pipeline (kernels back to back), which is "
+                                 "what share_of_step and the ncu launch list describe"},
             "fp32": {"kernel": "k_extend", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
                      "nodes_per_ray": nodes_per_ray, "prims_per_ray": prims_per_ray, "flops_per_ray": flops_per_ray,
                      "note": "algorithmic flops (SURVEY 8d: 30 per box test, 41 per primitive test); peak = SMs x 128 lanes x max SM clock, no FMA"},

@@ -224,7 +224,7 @@ int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_o
  * cut into several references with tighter boxes (an element may sit in several leaves of the accelerator tree).
  * "count": 1 = maintain node_visits / prim_tests / exact_steps.  "profile": 1 = time extend / shade separately.
  * "refill": busy-lane threshold of the persistent extend warps.  "leaf_weight": phase-vote weight.  "check_every": host
- * polling period (iterations).  "pipes": independent wavefront pipelines (streams) per render (default 1).
+ * polling period (iterations).  "pipes": independent wavefront pipelines (streams) per render (default 2: one pipeline's launch tails overlap the other's work; the film is bit-identical for any value).
  * "blocks_per_sm": cap on resident blocks of the persistent kernels.
  * Environment: RT_ITER_LOG=<path> dumps (pipe, iteration, live paths, extend ms, shade ms) of the last render as CSV. */
 int rt_set_option(const char* key, int64_t value);

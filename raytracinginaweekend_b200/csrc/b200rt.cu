@@ -32,7 +32,7 @@ int g_opt_traversal = 3;      // 0 = reference node test only (exact), 1 = + tig
 int g_opt_presplit = 800;     // reference budget of the rebuilt tree in per cent of the element count (<= 100: no pre-splitting)
 int g_opt_rebuild = 1;        // build the second topology at rt_scene_create (0: traversal 3 behaves like 2)
 int g_opt_rebuild_depth_extra = 4;  // depth cap of the rebuilt tree = reference depth + this (the stack lives in shared memory)
-int g_opt_pipes = 1;         // independent wavefront pipelines (streams) per render: one pipeline's extend tail overlaps the other's work
+int g_opt_pipes = 2;         // independent wavefront pipelines (streams) per render: one pipeline's extend tail overlaps the other's work
 int g_opt_leaf_weight = 24;   // extend phase vote: leaf phase when n_leaf * w > n_node * 16
 int g_opt_refill = 28;        // extend refills idle lanes when fewer than this many of 32 are busy
 int g_opt_count = 0;        // 1 = COUNT kernel variant (node visits / primitive tests per ray)

@@ -30,7 +30,7 @@ def product_world(name):
 
 @pytest.fixture(autouse=True)
 def default_options():
-    for k, v in (("traversal", 3), ("count", 0), ("profile", 0)):
+    for k, v in (("traversal", 3), ("count", 0), ("profile", 0), ("pipes", 2)):
         _cabi.set_option(k, v)
     yield
 
@@ -392,6 +392,20 @@ def test_caller_tree_with_non_bounding_boxes_is_traversed_as_given(oracle):
     _cabi.set_option("traversal", 0)
     img1 = bad.render(64, 48, 4, 20, 2, 5)[0]
     assert images_equal_bits(img0, img1)
+
+
+@pytest.mark.parametrize("name,size,T,spp", [("config:c2", (160, 90), 5, 9), ("config:c3", (96, 96), 8, 8), ("demo:final_scene2", (64, 64), 4, 7)])
+def test_overlapped_pipelines_do_not_change_the_film(name, size, T, spp):
+    """rt_set_option("pipes", n): the sample lanes are dealt to n independent wavefront pipelines on separate streams; every lane still
+    accumulates its own plane and k_finalize merges the planes in lane order, so the film is bit-identical for any n."""
+    w = product_world(name)
+    films = []
+    for pipes in (1, 2, 3, 8):
+        _cabi.set_option("pipes", pipes)
+        img, st = rb.render(rb.Size2i(*size), T, spp, 50, w, seed=21, return_stats=True)
+        films.append((img, st["ray_segments"]))
+    for img, rays in films[1:]:
+        assert rays == films[0][1] and images_equal_bits(img, films[0][0])
 
 
 def test_lane_count_only_changes_summation_order():

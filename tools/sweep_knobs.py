@@ -13,9 +13,8 @@ def run(**kw):
         _, st = rb.render(size, 64, 64, 50, W, seed=3, return_stats=True)
         best = min(best, st["render_ms"])
     print(kw, "%.1f ms  %.1f Mrays/s" % (best, st["ray_segments"] / best / 1e3), flush=True)
-for lw, rf in itertools.product((12, 16, 24, 32, 48), (20, 28, 32)):
-    run(pipes=1, leaf_weight=lw, refill=rf)
-run(pipes=2, leaf_weight=24, refill=28)
+for p in (1, 2, 3, 4, 2, 1):
+    run(pipes=p, leaf_weight=24, refill=28)
 run(pipes=1, leaf_weight=24, refill=28, blocks_per_sm=8)
 run(pipes=1, leaf_weight=24, refill=28, blocks_per_sm=0, check_every=4)
 run(pipes=1, leaf_weight=24, refill=28, check_every=16)
