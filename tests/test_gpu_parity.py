@@ -319,6 +319,24 @@ def test_rebuilt_topology_gives_the_reference_film(name, size):
     assert 0 < sb["max_stack"] <= sb["stack_capacity"], sb      # the shared-memory traversal stack never overflows
 
 
+@pytest.mark.parametrize("name,size,T,spp", [("config:c1", (1200, 800), 10, 10), ("config:c3", (1024, 1024), 4, 4), ("config:c5", (3840, 2160), 1, 1),
+                                            ("config:c4", (960, 540), 1, 1)])
+def test_rebuilt_topology_at_baseline_sizes(name, size, T, spp):
+    """Size-independent property at (or near) BASELINE.json's sizes, no CPU in the loop: the default traversal (rebuilt topology,
+    pre-split references, proof + restart) must give the film of the reference's own node rule on the reference's own tree,
+    bit for bit, with the same number of ray segments — millions to tens of millions of rays per case (C4 is run at a quarter
+    of its size: the reference rule alone needs ~100 s for it at 1920x1080)."""
+    w = product_world(name)
+    _cabi.set_option("traversal", 3)
+    a, sa = rb.render(rb.Size2i(*size), T, spp, 50, w, seed=31, return_stats=True)
+    _cabi.set_option("traversal", 0)
+    b, sb = rb.render(rb.Size2i(*size), T, spp, 50, w, seed=31, return_stats=True)
+    assert sa["ray_segments"] == sb["ray_segments"] and sa["ray_segments"] > 1_000_000
+    assert images_equal_bits(a, b)
+    if name in ("config:c4", "config:c5"):
+        _cache.pop(name).close()      # free the large host / device copies
+
+
 def test_rebuilt_topology_redo_paths(oracle):
     """The cases the proof must refuse: (a) two elements at exactly the same t (the reference's visit order decides),
     (b) elements below a zero-thickness node (invisible in the reference), (c) hits on a face of the parent box
