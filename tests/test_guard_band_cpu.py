@@ -146,3 +146,55 @@ def test_accepted_triangle_hits_are_never_culled(seed, oracle):
             n_outside += gap > 0
             assert not sc and not pc, (p0, p1, p2, org[i], d[i], h["t"][i], gap, mg)
     assert n_acc > 5000 and n_outside > 20
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_accepted_rect_and_box_hits_are_never_culled(seed, oracle):
+    """Rects (rect_geometry.rs:33-59, box = the rect padded by 0.01 along its normal) and AxisAlignedBox primitives (aabb.rs:80-167,
+    box = itself): rays aimed at their borders, edges and corners."""
+    rng = np.random.default_rng(300 + seed)
+    n_acc = n_outside = 0
+    for it in range(30):
+        s = 10.0 ** rng.uniform(-1, 3)
+        lo = (rng.normal(size=3) * s).astype(F32)
+        hi = (lo + np.abs(rng.normal(size=3)) * s * 10.0 ** rng.uniform(-2, 0, 3) + F32(1e-3) * F32(s)).astype(F32)
+        n = 1500
+        if it % 2 == 0:
+            plane = int(rng.integers(0, 3))
+            p0, p1, nn = [(0, 1, 2), (0, 2, 1), (1, 2, 0)][plane]
+            dist = lo[nn]
+            W = one_item_world(oracle, 1, [plane, dist, lo[p0], hi[p0], lo[p1], hi[p1]])
+            box = np.zeros(6, F32)
+            box[p0], box[3 + p0], box[p1], box[3 + p1] = lo[p0], hi[p0], lo[p1], hi[p1]
+            box[nn], box[3 + nn] = F32(dist) - F32(0.01), F32(dist) + F32(0.01)
+            target = np.zeros((n, 3))
+            target[:, nn] = float(dist)
+            for ax in (p0, p1):
+                edge = rng.integers(0, 3, n)
+                inside = float(lo[ax]) + rng.uniform(0, 1, n) * float(hi[ax] - lo[ax])
+                border = np.where(edge == 0, float(lo[ax]), float(hi[ax])) * (1 + rng.choice([-1, 1], n) * 10.0 ** rng.uniform(-8, -4, n))
+                target[:, ax] = np.where(edge == 2, inside, border)
+        else:
+            W = one_item_world(oracle, 3, list(lo) + list(hi))
+            box = np.concatenate([lo, hi]).astype(F32)
+            pick = rng.integers(0, 2, (n, 3))
+            corner = np.where(pick == 0, lo.astype(np.float64), hi.astype(np.float64))
+            inside = lo.astype(np.float64) + rng.uniform(0, 1, (n, 3)) * (hi - lo).astype(np.float64)
+            on_face = rng.random((n, 3)) < 0.6
+            target = np.where(on_face, corner * (1 + rng.choice([-1, 1], (n, 3)) * 10.0 ** rng.uniform(-8, -4, (n, 3))), inside)
+        dirs = unit(rng.normal(size=(n, 3)))
+        if it % 3 == 0:
+            k = rng.integers(0, 3)
+            dirs[:, k] *= 10.0 ** rng.uniform(-6, -1, n)
+            dirs = unit(dirs)
+        dist_o = rng.uniform(0.5, 200.0, n) * s
+        org = (target - dirs * dist_o[:, None]).astype(F32)
+        d = unit(target - org.astype(np.float64)).astype(F32)
+        h = W.trace(org, d)
+        A = 8 * EPS * float(np.abs(box).max())
+        for i in np.nonzero(h["hit_id"] != MISS)[0]:
+            sc, pc, gap, mg = band_checks(box, A, 0.0, org[i].astype(np.float64), d[i], float(h["t"][i]))
+            n_acc += 1
+            n_outside += gap > 0
+            assert not sc and not pc, (it, box, org[i], d[i], h["t"][i], gap, mg)
+    assert n_acc > 5000
