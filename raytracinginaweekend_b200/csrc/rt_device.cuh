@@ -364,9 +364,12 @@ __device__ __forceinline__ bool leaf_test(const SceneDev& S, uint32_t ref, float
 //   * MODE 0: the reference rule alone, true divisions (the reference's algorithm, for A/B sweeps);
 //     MODE 1: + tight cull: a child is skipped when the carried slab interval is empty by more than a per-node
 //             guard band (true-bound AABBs cannot contain an accepted hit then), true divisions;
-//     MODE 2: MODE 1 decisions, but evaluated with one reciprocal per ray and multiplies.  Whenever the
-//             approximate values cannot prove the decision (within RT_BAND relative, or the ray has a zero /
-//             denormal direction component) the exact MODE 1 code runs instead, so the visited set is identical.
+//     MODE 2: the same rules evaluated with one reciprocal per ray and multiplies, plus the per-axis padded
+//             second-chance cull (padded_cull).  Whenever the approximate values cannot prove a reference-rule
+//             decision (within RT_BAND relative, or the ray has a zero / denormal direction component) the exact
+//             MODE 1 code runs for that node.  Every extra cull only removes children that cannot contain an accepted
+//             hit, so the RESULT (element, t) is identical in all modes;
+//     MODE 3: trav_round_fast below — a different tree, with a per-ray proof that the reference returns the same element.
 // Stack: shared memory, [level][thread] entries of 8 B (child reference, cull threshold): one 64-bit access per push / pop.
 // ------------------------------------------------------------------------------------------------
 struct HitRec {
