@@ -282,7 +282,8 @@ def main():
         flops_per_ray = NODE_FLOPS * nodes_per_ray + PRIM_FLOPS * prims_per_ray
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         fp32_peak = sms * 128 * sm_mhz * 1e6 / 1e12      # TFLOP/s without FMA (parity code is --fmad=false)
-        fp32_ach = rays_rank0 * flops_per_ray / (ext_ms * 1e-3) / 1e12 if ext_ms > 0 else 0.0
+        # algorithmic flops of one step / the extend time of the single-pipeline probe step (kernels back to back, no overlap)
+        fp32_ach = pst["ray_segments"] * flops_per_ray / (pst["extend_ms"] * 1e-3) / 1e12 if pst["extend_ms"] > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "extend_traffic.json")
         traffic_src = None
