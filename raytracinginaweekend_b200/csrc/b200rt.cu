@@ -898,6 +898,21 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
 
 }  // namespace
 
+// The C ABI never lets a C++ exception (std::bad_alloc from the host-side packing, std::system_error from the builder threads)
+// cross the boundary: the reference panics, this library returns an error code.
+template <class F>
+static int guarded(F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return fail(RT_ENOMEM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(RT_ECUDA, std::string("internal error: ") + e.what());
+    } catch (...) {
+        return fail(RT_ECUDA, "internal error");
+    }
+}
+
 extern "C" {
 
 const char* rt_last_error(void) { return g_err.c_str(); }
@@ -935,7 +950,7 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene) {
     RtScene* sc = new (std::nothrow) RtScene();
     if (!sc) return fail(RT_ENOMEM, "out of host memory");
     sc->device = device;
-    int rc = pack_scene(*desc, *sc);
+    int rc = guarded([&] { return pack_scene(*desc, *sc); });
     if (rc != RT_OK) {
         delete sc;
         return rc;
@@ -1014,12 +1029,12 @@ int rt_trace(RtScene* scene, const float* org, const float* dir, uint64_t n, flo
 int rt_render_planes_device(RtScene* scene, const RtRenderParams* params, uint32_t lane_first, uint32_t lane_stride,
                             float* d_plane_sum, void* cuda_stream, RtStats* out_stats) {
     if (!scene || !params || !d_plane_sum) return fail(RT_EINVAL, "NULL argument");
-    return render_core(*scene, *params, lane_first, lane_stride, d_plane_sum, false, (cudaStream_t)cuda_stream, out_stats);
+    return guarded([&] { return render_core(*scene, *params, lane_first, lane_stride, d_plane_sum, false, (cudaStream_t)cuda_stream, out_stats); });
 }
 
 int rt_render_device(RtScene* scene, const RtRenderParams* params, float* d_out_rgb, void* cuda_stream, RtStats* out_stats) {
     if (!scene || !params || !d_out_rgb) return fail(RT_EINVAL, "NULL argument");
-    return render_core(*scene, *params, 0, 1, d_out_rgb, true, (cudaStream_t)cuda_stream, out_stats);
+    return guarded([&] { return render_core(*scene, *params, 0, 1, d_out_rgb, true, (cudaStream_t)cuda_stream, out_stats); });
 }
 
 int rt_render(RtScene* scene, const RtRenderParams* params, float* out_rgb, RtStats* out_stats) {
@@ -1029,7 +1044,7 @@ int rt_render(RtScene* scene, const RtRenderParams* params, float* out_rgb, RtSt
     const size_t n = (size_t)params->width * params->height * 3;
     DevBuf<float> film;  // 25 MB at 1080p: cheap next to the render; the big buffers live in the per-device workspace
     CU(film.alloc(n));
-    int rc = render_core(*scene, *params, 0, 1, film.p, true, nullptr, out_stats);
+    int rc = guarded([&] { return render_core(*scene, *params, 0, 1, film.p, true, nullptr, out_stats); });
     if (rc) return rc;
     CU(cudaMemcpy(out_rgb, film.p, n * sizeof(float), cudaMemcpyDeviceToHost));
     return RT_OK;
