@@ -218,7 +218,9 @@ int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_o
  * rebuilt (SAH) topology over the same elements finds the closest accepted element, the result is kept only when the
  * reference traversal provably returns the same element (unique minimum, hit point strictly inside the element's parent
  * box of the reference tree), every other ray is traced again with 2 on the reference tree (RtStats.redo_rays); scenes with
- * wrapped elements or volumes always use 2.  "rebuild": 0 = do not build the second topology at rt_scene_create.
+ * fewer than "rebuild_min_items" (32) elements use 2, as does rt_trace on scenes with Animation leaves (the rebuilt tree bounds
+ * moving elements over the camera's shutter interval only).  "rebuild": 0 = do not build the second topology at rt_scene_create;
+ * "rebuild_wrapped": 0 = not for scenes with wrapped elements / volumes.
  * "rebuild_depth_extra": depth cap of the rebuilt tree above the reference depth (default 4).  "presplit": reference budget of
  * the rebuilt tree in per cent of the element count (default 800; <= 100 = one reference per element): sliver triangles are
  * cut into several references with tighter boxes (an element may sit in several leaves of the accelerator tree).

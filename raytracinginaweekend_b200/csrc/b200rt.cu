@@ -30,6 +30,8 @@ thread_local std::string g_err;
 int g_opt_traversal = 3;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path,
                               // 3 = rebuilt topology + per-ray proof, unproven rays on the reference tree with 2 (plain scenes; else 2)
 int g_opt_presplit = 800;     // reference budget of the rebuilt tree in per cent of the element count (<= 100: no pre-splitting)
+int g_opt_rebuild_min_items = 32;  // below this the reference tree is as good (a Cornell box has 8 elements) and nothing has to be proven
+int g_opt_rebuild_wrapped = 1;  // also build it for scenes with wrapped elements / volumes (true world-space bounds)
 int g_opt_rebuild = 1;        // build the second topology at rt_scene_create (0: traversal 3 behaves like 2)
 int g_opt_rebuild_depth_extra = 4;  // depth cap of the rebuilt tree = reference depth + this (the stack lives in shared memory)
 int g_opt_pipes = 2;         // independent wavefront pipelines (streams) per render: one pipeline's extend tail overlaps the other's work
@@ -155,6 +157,33 @@ Box leaf_box(const RtItem& it) {
     return b;
 }
 
+// True world-space bounds of a wrapped element (for the rebuilt tree only; the reference's own box for it is the Q2 box):
+// the local box's corners through Transformation::apply_point (transformations.rs) and, for Animation, translated by
+// velocity * t at both ends of the shutter interval (linear motion: the union of the two end boxes bounds the sweep).
+Box world_box(const RtItem& it, const Box& lb, double t_lo, double t_hi) {
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int c = 0; c < 8; ++c) {
+        double p[3] = {(c & 1) ? lb.mx[0] : lb.mn[0], (c & 2) ? lb.mx[1] : lb.mn[1], (c & 4) ? lb.mx[2] : lb.mn[2]};
+        if (it.wrap_flags & RT_WRAP_TRANSFORMATION) {
+            const double sn = it.transform[3], cs = it.transform[4];
+            const double x = cs * p[0] + sn * p[2], z = -sn * p[0] + cs * p[2];
+            p[0] = x + it.transform[0]; p[1] += it.transform[1]; p[2] = z + it.transform[2];
+        }
+        for (double t : {t_lo, t_hi}) {
+            for (int k = 0; k < 3; ++k) {
+                const double q = p[k] + ((it.wrap_flags & RT_WRAP_ANIMATION) ? (double)it.velocity[k] * t : 0.0);
+                mn[k] = std::min(mn[k], q); mx[k] = std::max(mx[k], q);
+            }
+        }
+    }
+    Box b;
+    for (int k = 0; k < 3; ++k) {
+        b.mn[k] = (float)mn[k]; if ((double)b.mn[k] > mn[k]) b.mn[k] = std::nextafter(b.mn[k], -INFINITY);
+        b.mx[k] = (float)mx[k]; if ((double)b.mx[k] < mx[k]) b.mx[k] = std::nextafter(b.mx[k], INFINITY);
+    }
+    return b;
+}
+
 struct H3 {
     float x, y, z;
 };
@@ -232,7 +261,10 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     // misses the primitive's true AABB by the rounding slack of that test.  m(t) = A + |t| (1e-5 + C |t|) with
     //   triangles / rects: A = 8 eps max|coordinate|            (position = o + t d is rounded at coordinate scale)
     //   spheres          : A = 8 eps (max|coordinate| + 3 r), C = 8 * 3 eps / r   (|disc error| <~ 11 eps |oc|^2)
-    std::vector<float> leafA(N), leafC(N);
+    std::vector<float> leafA(N), leafC(N), fastA(N), fastC(N);
+    std::vector<Box> fbox(N);
+    const double shutter_lo = std::isfinite(d.camera.time_start) && std::isfinite(d.camera.time_end) ? std::min<double>(d.camera.time_start, d.camera.time_end) : 0.0;
+    const double shutter_hi = std::isfinite(d.camera.time_start) && std::isfinite(d.camera.time_end) ? std::max<double>(d.camera.time_start, d.camera.time_end) : 0.0;
     bool any_wrap = false;
     std::vector<WrapDev> wraps(N);
     const float eps = 5.9604645e-8f, safety = 8.0f;
@@ -308,7 +340,16 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
         wraps[i] = w;
         // Q2: the reference does not transform / motion-extend the AABB of a wrapped element, so its box (and every ancestor's)
         // is NOT a true bound: no tight cull there, the reference's weak per-axis rule alone decides (guard band = +inf)
-        if (it.wrap_flags & 3u) { leafA[i] = INFINITY; leafC[i] = 0.0f; }
+        fastA[i] = leafA[i]; fastC[i] = leafC[i]; fbox[i] = lbox[i];
+        if (it.wrap_flags & 3u) {
+            // the rebuilt tree (row f4) bounds the element where it really is; its band adds the rounding of the ray's reverse
+            // transform (rotation + offsets at world / local coordinate scale)
+            fbox[i] = world_box(it, lbox[i], shutter_lo, shutter_hi);
+            float wabs = maxabs;
+            for (int k = 0; k < 3; ++k) wabs = std::max(wabs, std::max(std::fabs(fbox[i].mn[k]), std::fabs(fbox[i].mx[k])));
+            fastA[i] += 16.0f * eps * wabs;
+            leafA[i] = INFINITY; leafC[i] = 0.0f;
+        }
     }
     auto bf16_up = [](float v) -> uint32_t {  // smallest bf16 >= v (v >= 0)
         uint32_t b;
@@ -403,23 +444,24 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
                 if (!(cb.mn[k] >= d.nodes[i].aabb_min[k] && cb.mx[k] <= d.nodes[i].aabb_max[k])) sc.boxes_are_bounds = false;
         }
 
-    // Row f4: second topology (SAH) over the same elements.  Plain scenes only: wrapped elements have boxes that are not
-    // true bounds (Q2) and volumes draw random numbers per tested element, so those scenes keep the reference tree alone.
+    // Row f4: second topology (SAH) over the same elements.  Wrapped elements enter it with their true world-space bounds
+    // (fbox; the reference's own boxes for them are not bounds, Q2); a volume's draw is keyed by the element, so it does not
+    // depend on the tree that reaches it.
     std::vector<NodeDev> nodes2;
     std::vector<float4> vis_box;
     uint32_t root2 = 0;
-    if (!any_wrap && N >= 2 && g_opt_rebuild && sc.boxes_are_bounds) {
+    if (N >= (uint32_t)std::max(2, g_opt_rebuild_min_items) && g_opt_rebuild && sc.boxes_are_bounds && (!any_wrap || g_opt_rebuild_wrapped)) {
         std::vector<rt_rebuild::Box3> lb(N);
         std::vector<float> tri;
         std::vector<uint8_t> is_tri(N, 0);
         for (uint32_t i = 0; i < N; ++i)
-            for (int k = 0; k < 3; ++k) { lb[i].mn[k] = lbox[i].mn[k]; lb[i].mx[k] = lbox[i].mx[k]; }
+            for (int k = 0; k < 3; ++k) { lb[i].mn[k] = fbox[i].mn[k]; lb[i].mx[k] = fbox[i].mx[k]; }
         // pre-split sliver triangles into several references (rt_rebuild.hpp); the budget shrinks for very large scenes
         const double factor = g_opt_presplit <= 100 ? 1.0 : std::min((double)g_opt_presplit / 100.0, N <= 150000u ? 16.0 : (N <= 2000000u ? 2.0 : 1.0));
         if (factor > 1.0) {
             tri.assign(9 * (size_t)N, 0.0f);
             for (uint32_t i = 0; i < N; ++i)
-                if (d.items[i].kind == RT_GEO_TRIANGLE) {
+                if (d.items[i].kind == RT_GEO_TRIANGLE && !d.items[i].wrap_flags) {  // wrapped triangles keep one reference
                     is_tri[i] = 1;
                     for (int k = 0; k < 9; ++k) tri[9 * (size_t)i + k] = d.items[i].geom[k];
                 }
@@ -438,7 +480,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
         for (uint32_t ii = n2; ii-- > 0;) {  // pre-order numbering: children have larger indices
             float a = 0.0f, c = 0.0f;
             for (uint32_t ch : {F.left[ii], F.right[ii]}) {
-                if (ch & RT_LEAF_BIT) { a = std::max(a, leafA[item_of(ch)]); c = std::max(c, leafC[item_of(ch)]); }
+                if (ch & RT_LEAF_BIT) { a = std::max(a, fastA[item_of(ch)]); c = std::max(c, fastC[item_of(ch)]); }
                 else { a = std::max(a, a2[ch]); c = std::max(c, c2[ch]); }
             }
             a2[ii] = a; c2[ii] = c;
@@ -597,6 +639,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     S.shade = sc.shade.p;
     S.own_box = sc.own_box.p;
     S.nodes2 = sc.nodes2.p;
+    S.fast_trace_ok = sc.has_animation ? 0u : 1u;
     S.vis_box = sc.vis_box.p;
     S.wraps = sc.wraps.p;
     S.trace_time = 0.0f;
@@ -743,8 +786,11 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
     int mode = std::min(3, std::max(0, g_opt_traversal));
     if (!sc.boxes_are_bounds) mode = 0;
     if (mode == 3 && !sc.nodes2.p) mode = 2;  // no rebuilt topology for this scene (wrapped elements, single element, rebuild off)
-    ExtendFn ext = mode == 3 ? (g_opt_count ? k_extend<3, true, 0> : k_extend<3, false, 0>)
-                             : pick_extend(mode, g_opt_count != 0, sc.has_volume ? 2 : (sc.has_wrapped ? 1 : 0));
+    const int feat = sc.has_volume ? 2 : (sc.has_wrapped ? 1 : 0);
+    ExtendFn ext = mode == 3 ? (feat == 2 ? (g_opt_count ? k_extend<3, true, 2> : k_extend<3, false, 2>)
+                                          : (feat == 1 ? (g_opt_count ? k_extend<3, true, 1> : k_extend<3, false, 1>)
+                                                       : (g_opt_count ? k_extend<3, true, 0> : k_extend<3, false, 0>)))
+                             : pick_extend(mode, g_opt_count != 0, feat);
     rc = persistent_grid(sc, ext, eblock, esmem, &egrid);
     if (rc) return rc;
 
@@ -928,6 +974,8 @@ int rt_set_option(const char* key, int64_t value) {
     std::string k(key);
     if (k == "traversal") g_opt_traversal = (int)value;
     else if (k == "rebuild") g_opt_rebuild = (int)value;
+    else if (k == "rebuild_wrapped") g_opt_rebuild_wrapped = (int)value;
+    else if (k == "rebuild_min_items") g_opt_rebuild_min_items = (int)value;
     else if (k == "presplit") g_opt_presplit = (int)value;
     else if (k == "rebuild_depth_extra") g_opt_rebuild_depth_extra = (int)value;
     else if (k == "profile") g_opt_profile = (int)value;

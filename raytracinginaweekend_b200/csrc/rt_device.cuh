@@ -90,6 +90,8 @@ struct SceneDev {
     const NodeDev* nodes2;    // same 64 B record; q3.z unused (children are visited near-first)
     uint32_t root2;
     const float4* vis_box;    // [2*n_items] box of the element's parent in the REFERENCE tree (min.xyz,0 | max.xyz,0)
+    uint32_t fast_trace_ok;   // rt_trace may use the rebuilt tree (0 when the scene has Animation leaves: the tree's boxes only
+                              // cover the camera's shutter interval, rt_trace takes any ray time)
     float trace_time;         // Ray::time of rt_trace rays
     CameraDev cam;
     uint32_t bg_is_sky;
@@ -642,9 +644,14 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
 // ------------------------------------------------------------------------------------------------
 #define RT_TIE_BIT 8u  // kept in Trav::dpos next to the direction signs (bits 0..2)
 
-template <bool COUNT>
+// Scenes with wrapped elements / volumes (KEYFN::FEAT >= 1): the rebuilt tree holds the TRUE world-space bounds of a wrapped
+// element (the reference's own box for it is not a bound, Q2), the leaf test applies the wrappers exactly like leaf_test, and a
+// volume's free-flight draw is keyed by the element, so it does not depend on which tree reaches it.  A volume accepts t <= end
+// (hittable.rs:330: `t > end_medium` rejects), i.e. its range is closed by nature: an equal-t volume is flagged as a tie like
+// everything else, and the reference tree decides.
+template <bool COUNT, class KEYFN>
 __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool do_leaf, uint2* stk,
-                                                uint32_t stk_stride, TravCount* cnt) {
+                                                uint32_t stk_stride, TravCount* cnt, const KEYFN& keyfn) {
     uint32_t cur = T.cur;
     const bool at_leaf = (cur & RT_REF_LEAF) != 0u;
     bool need_pop = false;
@@ -654,8 +661,25 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
             const uint32_t kind = (cur >> RT_REF_KIND_SHIFT) & 3u, item = cur & RT_REF_ITEM_MASK;
             const bool have = T.best != RT_NO_HIT;
             const float end_closed = have ? __uint_as_float(__float_as_uint(T.end + 0.0f) + 1u) : T.end;  // next float up (end >= 0, finite)
+            const float4* q = reinterpret_cast<const float4*>(S.prims + item);
             float t;
-            if (prim_t(kind, reinterpret_cast<const float4*>(S.prims + item), T.o, T.d, T.start, end_closed, t)) {
+            bool hit;
+            bool done = false;
+            float3 o = T.o, d = T.d;
+            if constexpr (KEYFN::FEAT >= 1) {
+                if (cur & RT_REF_WRAPPED) {
+                    const WrapDev w = load_wrap(S, item);
+                    wrap_reverse_ray(w, T.time, o, d);
+                    if constexpr (KEYFN::FEAT >= 2) {
+                        if (w.flags & 4u) {
+                            hit = volume_t(kind, q, item, w.neg_inv_density, o, d, T.start, T.end, keyfn, t);
+                            done = true;
+                        }
+                    }
+                }
+            }
+            if (!done) hit = prim_t(kind, q, o, d, T.start, end_closed, t);
+            if (hit) {
                 if (have && t == T.end) {
                     // the same element can sit in several leaves (pre-split references): seeing it again is not a tie
                     if (((cur ^ T.best) & RT_REF_ITEM_MASK) != 0u) T.dpos |= RT_TIE_BIT;
@@ -766,17 +790,19 @@ __device__ __forceinline__ HitRec traverse(const SceneDev& S, float3 o, float3 d
 }
 
 // Whole-ray form of the fast path (rt_trace).  *proven = false -> the caller must trace the ray on the reference tree.
-__device__ __forceinline__ HitRec traverse_fast(const SceneDev& S, float3 o, float3 d, float start, float end_in, uint2* stk, uint32_t stk_stride, bool* proven) {
+template <class KEYFN>
+__device__ __forceinline__ HitRec traverse_fast(const SceneDev& S, float3 o, float3 d, float time, float start, float end_in, uint2* stk,
+                                                uint32_t stk_stride, bool* proven, const KEYFN& keyfn) {
     Trav T;
     HitRec best;
     best.ref = RT_NO_HIT;
     best.t = end_in;
     *proven = false;
-    trav_setup(S, T, o, d, 0.0f, start, end_in);
+    trav_setup(S, T, o, d, time, start, end_in);
     if (!fast_eligible(T)) return best;
     if (!root_gate(S, o, d, start, end_in, false)) { *proven = true; return best; }  // the reference root test itself fails
     trav_setup_fast(S, T);
-    while (trav_round_fast<false>(S, T, (T.cur & RT_REF_LEAF) != 0u, stk, stk_stride, nullptr)) {}
+    while (trav_round_fast<false>(S, T, (T.cur & RT_REF_LEAF) != 0u, stk, stk_stride, nullptr, keyfn)) {}
     best.ref = T.best;
     best.t = T.end;
     *proven = T.best == RT_NO_HIT || (!(T.dpos & RT_TIE_BIT) && ref_visible(S, T.best, o, d, T.end));

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
             bool more;
             if constexpr (MODE == 3) {
                 if (T.dpos & RT_REFMODE_BIT) more = trav_round<2, COUNT>(S, T, do_leaf, stk, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
-                else more = trav_round_fast<COUNT>(S, T, do_leaf, stk, blockDim.x, &tc);
+                else more = trav_round_fast<COUNT>(S, T, do_leaf, stk, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
             } else {
                 more = trav_round<MODE, COUNT>(S, T, do_leaf, stk, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
             }
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ SceneDev 
         if (MODE != 0 && !(fabsf(dd - 1.0f) <= 1e-5f)) {
             h = traverse<0, false>(S, o, d, S.trace_time, t_min, t_max, stk, blockDim.x, TraceKey{i});
         } else if constexpr (MODE == 3) {
-            if (S.nodes2) h = traverse_fast(S, o, d, t_min, t_max, stk, blockDim.x, &proven);
+            if (S.nodes2 && S.fast_trace_ok) h = traverse_fast(S, o, d, S.trace_time, t_min, t_max, stk, blockDim.x, &proven, TraceKey{i});
             if (!proven) h = traverse<2, false>(S, o, d, S.trace_time, t_min, t_max, stk, blockDim.x, TraceKey{i});
         } else {
             h = traverse<MODE, false>(S, o, d, S.trace_time, t_min, t_max, stk, blockDim.x, TraceKey{i});

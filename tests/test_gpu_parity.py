@@ -30,7 +30,7 @@ def product_world(name):
 
 @pytest.fixture(autouse=True)
 def default_options():
-    for k, v in (("traversal", 3), ("count", 0), ("profile", 0), ("pipes", 2)):
+    for k, v in (("traversal", 3), ("count", 0), ("profile", 0), ("pipes", 2), ("rebuild_min_items", 32)):
         _cabi.set_option(k, v)
     yield
 
@@ -424,6 +424,32 @@ def test_overlapped_pipelines_do_not_change_the_film(name, size, T, spp):
         films.append((img, st["ray_segments"]))
     for img, rays in films[1:]:
         assert rays == films[0][1] and images_equal_bits(img, films[0][0])
+
+
+@pytest.mark.parametrize("name,w,h,spp,T", [("demo:cornell_box", 64, 64, 8, 4), ("demo:cornell_box_smoke", 64, 64, 8, 4), ("demo:moving_spheres", 76, 64, 6, 3),
+                                            ("demo:simple_plane", 64, 36, 9, 4)])
+def test_rebuilt_topology_on_tiny_wrapped_scenes(name, w, h, spp, T, oracle_world):
+    """By default scenes below 32 elements keep the reference tree.  Forcing the rebuilt tree on them exercises the wrapped /
+    volume leaf tests of the fast traversal where restarts are most frequent (a rotated box sticks out of its Q2 box)."""
+    _cabi.set_option("rebuild_min_items", 2)
+    world = rb.World.named(name)          # a fresh scene: the option is read by rt_scene_create
+    try:
+        ref, st = oracle_world(name).render(w, h, spp, 50, T, 77, "replay")
+        _cabi.set_option("count", 1)
+        img, gst = rb.render(rb.Size2i(w, h), T, spp, 50, world, rb.RenderMode.Default, seed=77, return_stats=True)
+        assert gst["ray_segments"] == st["rays"] and gst["node_visits"] > 0
+        if name == "demo:moving_spheres":
+            nan = np.isnan(ref) | np.isnan(img)
+            assert np.array_equal(np.isnan(ref), np.isnan(img)) and ((np.abs(ref - img) > 1e-6) & ~nan).any(axis=2).sum() <= 0.002 * w * h + 2
+        else:
+            assert images_equal_bits(img, ref)
+        fs = oracle_world(name).export()
+        org, dir = random_rays(fs, 20000, 5)
+        tm = 0.25 if name == "demo:moving_spheres" else 0.0
+        r = assert_hits_match(world.hit(org, dir, time=tm), oracle_world(name).trace(org, dir, time=tm))
+        assert r["t_bit_mismatch"] == 0 and r["normal_bit_mismatch"] == 0, r
+    finally:
+        world.close()
 
 
 def test_lane_count_only_changes_summation_order():
