@@ -351,6 +351,7 @@ def test_rebuilt_topology_redo_paths(oracle):
     sp = np.nonzero(sc["kinds"] == 0)[0]
     sc["geom"][sp[0], :4] = [3, 0, -5, 1]
     sc["geom"][sp[1], :4] = [3, 0, -5, 1]                                  # coincident spheres: exact tie
+    _cabi.set_option("rebuild_min_items", 2)                               # 18 elements: below the default threshold of the rebuilt tree
     w, o = rb.World.from_elements(**sc), oracle.OracleWorld.from_flat(**sc)
     fs = o.export()
     org0, dir0 = random_rays(fs, 20000, 5)
