@@ -263,8 +263,13 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     //   spheres          : A = 8 eps (max|coordinate| + 3 r), C = 8 * 3 eps / r   (|disc error| <~ 11 eps |oc|^2)
     std::vector<float> leafA(N), leafC(N), fastA(N), fastC(N);
     std::vector<Box> fbox(N);
-    const double shutter_lo = std::isfinite(d.camera.time_start) && std::isfinite(d.camera.time_end) ? std::min<double>(d.camera.time_start, d.camera.time_end) : 0.0;
-    const double shutter_hi = std::isfinite(d.camera.time_start) && std::isfinite(d.camera.time_end) ? std::max<double>(d.camera.time_start, d.camera.time_end) : 0.0;
+    // ray times the camera can produce: U[t0, t1) + dot(shutter_pace, point), point in [0, 1 + 1/(w-1)]^2 (camera.rs:185-190)
+    const bool times_ok = std::isfinite(d.camera.time_start) && std::isfinite(d.camera.time_end) && std::isfinite(d.camera.shutter_pace[0]) &&
+                          std::isfinite(d.camera.shutter_pace[1]);
+    const double pace_lo = 2.0 * (std::min(0.0, (double)d.camera.shutter_pace[0]) + std::min(0.0, (double)d.camera.shutter_pace[1]));
+    const double pace_hi = 2.0 * (std::max(0.0, (double)d.camera.shutter_pace[0]) + std::max(0.0, (double)d.camera.shutter_pace[1]));
+    const double shutter_lo = times_ok ? std::min<double>(d.camera.time_start, d.camera.time_end) + pace_lo : 0.0;
+    const double shutter_hi = times_ok ? std::max<double>(d.camera.time_start, d.camera.time_end) + pace_hi : 0.0;
     bool any_wrap = false;
     std::vector<WrapDev> wraps(N);
     const float eps = 5.9604645e-8f, safety = 8.0f;
@@ -450,7 +455,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     std::vector<NodeDev> nodes2;
     std::vector<float4> vis_box;
     uint32_t root2 = 0;
-    if (N >= (uint32_t)std::max(2, g_opt_rebuild_min_items) && g_opt_rebuild && sc.boxes_are_bounds && (!any_wrap || g_opt_rebuild_wrapped)) {
+    if (N >= (uint32_t)std::max(2, g_opt_rebuild_min_items) && g_opt_rebuild && sc.boxes_are_bounds && (!any_wrap || (g_opt_rebuild_wrapped && times_ok))) {
         std::vector<rt_rebuild::Box3> lb(N);
         std::vector<float> tri;
         std::vector<uint8_t> is_tri(N, 0);
@@ -534,6 +539,8 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     S.cam.lens_radius = c.lens_radius;
     S.cam.time_start = c.time_start;
     S.cam.time_end = c.time_end;
+    S.cam.pace_x = c.shutter_pace[0];
+    S.cam.pace_y = c.shutter_pace[1];
     S.bg_is_sky = d.background_is_sky ? 1u : 0u;
     for (int k = 0; k < 3; ++k) S.bg[k] = d.background_rgb[k];
     S.has_light = d.has_light ? 1u : 0u;

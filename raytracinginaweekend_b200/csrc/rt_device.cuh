@@ -71,6 +71,7 @@ struct CameraDev {
     float3 position, ulc, unit_right, unit_up, scaled_right, scaled_up;
     float lens_radius;
     float time_start, time_end;
+    float pace_x, pace_y;  // Camera::shutter_pace (rolling shutter, camera.rs:190); zero in every builder of the reference
 };
 
 struct SceneDev {

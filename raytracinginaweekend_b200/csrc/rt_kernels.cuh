@@ -67,13 +67,14 @@ __device__ __forceinline__ void generate_path(const SceneDev& S, const RenderDev
     float py = fy + (u01(r.y) * R.sy + 0.0f);
     camera_ray(S.cam, px, py, r, o, d);
     // shutter time (camera.rs:185-190): the next draw of the camera block after the lens disc (draw #2 without a lens,
-    // draw #4 = first output of sub-block 1 with one); shutter_pace is always zero in the reference's builders
+    // draw #4 = first output of sub-block 1 with one)
     time = S.cam.time_start;
     if (S.cam.time_start != S.cam.time_end) {
         uint32_t bits = r.z;
         if (S.cam.lens_radius > 0.0f) bits = philox4x32_10(R.seed0, R.seed1, pixel, s_global, 0u, 1u).x;
         time = S.cam.time_start + u01(bits) * (S.cam.time_end - S.cam.time_start);
     }
+    time = time + (S.cam.pace_x * px + S.cam.pace_y * py);  // + Vec2f::dot(shutter_pace, point), camera.rs:190
 }
 
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R) {

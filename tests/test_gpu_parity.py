@@ -225,6 +225,22 @@ def test_render_volume_only_scene_bit_exact(oracle):
     assert images_equal_bits(img, ref)
 
 
+def test_rolling_shutter_with_moving_elements(oracle):
+    """Camera::shutter_pace (camera.rs:190: time += dot(shutter_pace, point)) is zero in every builder of the reference, but it is
+    part of the Camera the C ABI takes: moving elements must then see per-pixel times, and the rebuilt tree must bound them over
+    the widened interval."""
+    sc = random_scene(52, n_spheres=30, n_tris=20, n_rects=3, n_boxes=6, wrap_fraction=0.6, with_light=True)
+    sc["cam"][19], sc["cam"][20] = 0.2, 0.9
+    sc["cam"][21], sc["cam"][22] = 0.7, -0.4
+    w, o = rb.World.from_elements(**sc), oracle.OracleWorld.from_flat(**sc)
+    for mode in (2, 3):
+        _cabi.set_option("traversal", mode)
+        ref, st = o.render(60, 45, 6, 20, 3, 11, "replay")
+        img, gst = rb.render(rb.Size2i(60, 45), 3, 6, 20, w, seed=11, return_stats=True)
+        assert gst["ray_segments"] == st["rays"], mode
+        assert images_equal_bits(img, ref), mode
+
+
 def test_render_random_scene_with_light_bit_exact(oracle):
     sc = random_scene(21, n_spheres=10, n_tris=24, n_rects=4, with_light=True)
     w, o = rb.World.from_elements(**sc), oracle.OracleWorld.from_flat(**sc)
