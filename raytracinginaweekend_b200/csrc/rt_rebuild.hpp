@@ -247,21 +247,12 @@ inline void presplit(const std::vector<Box3>& leaf, const std::vector<float>& tr
     refs.reserve(std::max(budget, leaf.size()));
     std::vector<Poly> polys;
     std::vector<int32_t> poly_of;  // per reference: index into polys or -1
-    if (budget > leaf.size()) { polys.reserve(budget); poly_of.reserve(budget); }
+    if (budget > leaf.size()) { polys.reserve(2 * (budget - leaf.size())); poly_of.reserve(budget); }
     std::vector<std::pair<double, uint32_t>> heap;
     for (uint32_t i = 0; i < leaf.size(); ++i) {
         refs.push_back(Ref{i, leaf[i]});
-        if (is_tri[i] && budget > leaf.size()) {
-            Poly p;
-            p.n = 3;
-            for (int v = 0; v < 3; ++v)
-                for (int k = 0; k < 3; ++k) p.v[v][k] = tri[9 * (size_t)i + 3 * v + k];
-            poly_of.push_back((int32_t)polys.size());
-            polys.push_back(p);
-            heap.push_back({detail::half_area(leaf[i]), i});
-        } else {
-            poly_of.push_back(-1);
-        }
+        poly_of.push_back(-1);  // the polygon of an unsplit triangle is only materialised when it is first cut
+        if (is_tri[i] && budget > leaf.size()) heap.push_back({detail::half_area(leaf[i]), i});
     }
     std::make_heap(heap.begin(), heap.end());
     while (!heap.empty() && refs.size() < budget) {
@@ -274,7 +265,15 @@ inline void presplit(const std::vector<Box3>& leaf, const std::vector<float>& tr
             if (b.mx[k] - b.mn[k] > b.mx[ax] - b.mn[ax]) ax = k;
         if (!(b.mx[ax] > b.mn[ax])) continue;
         const double mid = 0.5 * ((double)b.mn[ax] + (double)b.mx[ax]);
-        const Poly& src = polys[poly_of[r]];
+        if (poly_of[r] < 0) {
+            Poly p;
+            p.n = 3;
+            for (int v = 0; v < 3; ++v)
+                for (int k = 0; k < 3; ++k) p.v[v][k] = tri[9 * (size_t)refs[r].item + 3 * v + k];
+            poly_of[r] = (int32_t)polys.size();
+            polys.push_back(p);
+        }
+        const Poly src = polys[poly_of[r]];
         const Poly lo = detail::clip_half(src, ax, mid, -1.0), hi = detail::clip_half(src, ax, mid, 1.0);
         if (lo.n < 3 || hi.n < 3) continue;
         const Box3 bl = detail::poly_box(lo, b), bh = detail::poly_box(hi, b);
