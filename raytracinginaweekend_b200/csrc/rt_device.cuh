@@ -396,7 +396,7 @@ struct Trav {
     uint32_t dpos;  // bit i = (d_i > 0): child order (hittable.rs:441)
     bool exact_only;
 };
-#define RT_BAND 1e-6f  // >= 8 ulp: bound on |(x*rcp(d)) - rn(x/d)| is ~1.5 ulp
+#define RT_BAND 1e-6f  // relative band of an approximate slab distance: 4x the bound 4 eps (see trav_setup)
 
 // Guard band of the tight cull.  eps(t) = A + |t| * (1e-5 + C * |t|) is the LATERAL distance (space units) by which a ray
 // may miss a primitive's true AABB and still be accepted by the primitive's single-precision test (A and C are packed
@@ -450,7 +450,9 @@ __device__ __forceinline__ void trav_setup(const SceneDev& S, Trav& T, float3 o,
     T.oinv = f3(-o.x * T.inv.x, -o.y * T.inv.y, -o.z * T.inv.z);
     T.mscale = 2.0f * fmaxf(fmaxf(fabsf(T.inv.x), fabsf(T.inv.y)), fabsf(T.inv.z));  // +inf for axis-parallel rays: no tight cull
     T.sB = 1e-5f * T.mscale;
-    // fma(b, inv, oinv) vs rn((b - o) / d): |err| <= 1.2e-7 |t| + 6e-8 |o_i / d_i|  (inv, oinv and the fma each round once)
+    // fma(b, inv, oinv) vs the reference's rn(rn(b - o) / d): |err| <= 4 eps |t| + eps |o_i / d_i| = 2.4e-7 |t| + 6e-8 |o_i / d_i|
+    // (inv, the fma and the reference's own two roundings act on t; the rounding of oinv acts on o / d).  The bands used are
+    // RT_BAND |t| = 1e-6 |t| and T.oe = 2.4e-7 max_i |o_i / d_i|, i.e. 4x each (tests/test_slab_error_bound.py).
     T.oe = 2.4e-7f * fmaxf(fmaxf(fabsf(T.oinv.x), fabsf(T.oinv.y)), fabsf(T.oinv.z));
     T.dpos = (d.x > 0.0f ? 1u : 0u) | (d.y > 0.0f ? 2u : 0u) | (d.z > 0.0f ? 4u : 0u);
     const float lo = 1e-18f, hi = 1e18f;  // NaN / inf / zero / denormal components, or a negative range start -> exact path only
@@ -617,7 +619,7 @@ __device__ __forceinline__ bool trav_round(const SceneDev& S, Trav& T, bool do_l
             }
             // hit_cond's end-dependent part with the shrunken range: reject iff end <= tn (exact tn)
             if (MODE == 2 && !T.exact_only) {
-                const float e = RT_BAND * fabsf(tn);
+                const float e = __fmaf_rn(RT_BAND, fabsf(tn), T.oe);  // relative + absolute part of the approximation error (trav_setup)
                 if (T.end > tn + e) break;
                 if (T.end < tn - e) continue;
                 const float4 b0 = __ldg(S.own_box + 2u * cur), b1 = __ldg(S.own_box + 2u * cur + 1u);
