@@ -72,7 +72,7 @@ def test_accepted_sphere_hits_are_never_culled(seed, oracle):
         W = one_item_world(oracle, 0, [c[0], c[1], c[2], r])
         n = 1500
         # rays that graze the sphere: aim at points at distance r (1 + delta) from the centre, |delta| from 1e-8 to 1e-3, both signs
-        dist = (rng.uniform(1.5, 200.0, n) * float(r)).astype(np.float64)
+        dist = (10.0 ** rng.uniform(math.log10(1.5), 4.5, n) * float(r)).astype(np.float64)    # 1.5 r .. 30 000 r away
         dirs = unit(rng.normal(size=(n, 3)))
         perp = unit(np.cross(dirs, rng.normal(size=(n, 3))))
         # half of the rays touch the sphere where it touches its box: perp = +-e_k, direction (nearly) perpendicular to e_k
