@@ -107,6 +107,37 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_cabi.RtCamera) == 92 and C.sizeof(_cabi.RtRenderParams) == 40
 
 
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Compile include/b200rt.h as plain C and compare sizeof / offsetof of every struct with the ctypes mirror in _cabi.py."""
+    import subprocess
+    structs = {"RtItem": ["kind", "geom", "wrap_flags", "transform", "velocity", "neg_inv_density"], "RtBvhNode": ["aabb_min", "left", "axis_id"],
+               "RtMaterial": ["texture", "param"], "RtTexture": ["image", "rgb", "inv_frequency", "odd"], "RtImage": ["height", "rgb8"],
+               "RtPerlin": ["perm_x", "perm_z"], "RtCamera": ["upper_left_corner", "scaled_up", "lens_radius", "time_end", "shutter_pace"],
+               "RtSceneDesc": ["items", "nodes", "root", "materials", "textures", "images", "n_perlins", "perlins", "camera", "background_is_sky",
+                               "background_rgb", "has_light", "light_dist", "light_r1"],
+               "RtRenderParams": ["height", "samples_per_pixel", "max_depth", "thread_count", "render_mode", "seed"],
+               "RtStats": ["paths", "kernel_launches", "render_ms", "shade_ms", "exact_steps", "redo_rays", "max_stack", "stack_capacity"]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200rt.h"', 'int main(void) {']
+    for name, fields in structs.items():
+        lines.append(f'  printf("{name} %zu", sizeof({name}));')
+        for f in fields:
+            lines.append(f'  printf(" %zu", offsetof({name}, {f}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    for line in out:
+        parts = line.split()
+        name, vals = parts[0], [int(x) for x in parts[1:]]
+        ct = getattr(_cabi, name)
+        assert C.sizeof(ct) == vals[0], name
+        for f, off in zip(structs[name], vals[1:]):
+            assert getattr(ct, f).offset == off, (name, f)
+
+
 def test_native_libraries_are_in_tree():
     assert os.path.dirname(build.LIB_CUDA) == os.path.join(ROOT, "raytracinginaweekend_b200")
     assert os.path.exists(build.LIB_CUDA) and os.path.exists(build.LIB_HOST)
