@@ -198,3 +198,69 @@ def test_accepted_rect_and_box_hits_are_never_culled(seed, oracle):
             n_outside += gap > 0
             assert not sc and not pc, (it, box, org[i], d[i], h["t"][i], gap, mg)
     assert n_acc > 5000
+
+
+def world_box_py(lbox, flags, off, sn, cs, vel, t_lo, t_hi):
+    """pack_scene's world_box: the local box's corners through Transformation::apply_point, swept over the shutter interval."""
+    pts = []
+    for c in range(8):
+        p = np.array([lbox[3 + 0] if c & 1 else lbox[0], lbox[3 + 1] if c & 2 else lbox[1], lbox[3 + 2] if c & 4 else lbox[2]], np.float64)
+        if flags & 1:
+            p = np.array([cs * p[0] + sn * p[2] + off[0], p[1] + off[1], -sn * p[0] + cs * p[2] + off[2]])
+        for t in (t_lo, t_hi):
+            pts.append(p + (np.asarray(vel, np.float64) * t if flags & 2 else 0.0))
+    pts = np.array(pts)
+    lo, hi = pts.min(0), pts.max(0)
+    return np.concatenate([np.nextafter(lo.astype(F32), F32(-np.inf)), np.nextafter(hi.astype(F32), F32(np.inf))]).astype(F32)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_accepted_hits_on_wrapped_elements_stay_within_their_world_box_band(seed, oracle):
+    """Row f4 on wrapped elements: the rebuilt tree bounds a Transformation / Animation-wrapped element by its world-space box and
+    adds 16 eps (coordinate magnitude) to its band for the rounding of the ray's reverse transform."""
+    rng = np.random.default_rng(700 + seed)
+    n_acc = 0
+    for it in range(24):
+        s = 10.0 ** rng.uniform(-1, 2)
+        kind = [0, 3, 1][it % 3]
+        if kind == 0:
+            r = F32(s * rng.uniform(0.2, 2)); c = (rng.normal(size=3) * s).astype(F32)
+            geom = [c[0], c[1], c[2], r]
+            lbox = np.concatenate([(c - r).astype(F32), (c + r).astype(F32)])
+            A_loc, C_loc = 8 * EPS * (float(np.abs(lbox).max()) + 3 * float(r)), 24 * EPS / float(r)
+        else:
+            lo = (rng.normal(size=3) * s).astype(F32); hi = (lo + np.abs(rng.normal(size=3)) * s + F32(1e-3 * s)).astype(F32)
+            if kind == 3:
+                geom = list(lo) + list(hi); lbox = np.concatenate([lo, hi]).astype(F32)
+            else:
+                geom = [1, lo[1], lo[0], hi[0], lo[2], hi[2]]           # XZ rect at y = lo[1]
+                lbox = np.array([lo[0], lo[1] - F32(0.01), lo[2], hi[0], lo[1] + F32(0.01), hi[2]], F32)
+            A_loc, C_loc = 8 * EPS * float(np.abs(lbox).max()), 0.0
+        flags = int(rng.integers(1, 4))
+        ang = rng.uniform(-math.pi, math.pi)
+        off = (rng.normal(size=3) * s * 3).astype(F32) if flags & 1 else np.zeros(3, F32)
+        sn, cs = (F32(math.sin(ang)), F32(math.cos(ang))) if flags & 1 else (F32(0), F32(1))
+        vel = (rng.normal(size=3) * s).astype(F32) if flags & 2 else np.zeros(3, F32)
+        time = F32(rng.uniform(0.0, 1.0))
+        wrap = np.array([[flags, off[0], off[1], off[2], sn, cs, vel[0], vel[1], vel[2], 0.0]], F32)
+        g = np.zeros((1, 24), F32); g[0, :len(geom)] = geom
+        W = oracle.OracleWorld.from_flat(np.array([kind], np.uint32), np.zeros(1, np.uint32), g, np.array([mat(0, 0)], np.uint32),
+                                         np.array([solid_tex([1, 1, 1])], np.uint32), [], simple_camera(), np.array([0, 1, 1, 1], F32),
+                                         np.zeros(7, F32), wrap=wrap)
+        wbox = world_box_py(lbox, flags, off.astype(np.float64), float(sn), float(cs), vel, 0.0, 1.0)
+        A = A_loc + 16 * EPS * max(float(np.abs(wbox).max()), float(np.abs(lbox).max()))
+        # grazing rays in WORLD space: aim at the surface of the element's world position at `time`
+        n = 1500
+        wb_t = world_box_py(lbox, flags, off.astype(np.float64), float(sn), float(cs), vel, float(time), float(time))
+        centre = 0.5 * (wb_t[:3] + wb_t[3:]).astype(np.float64); half = 0.5 * (wb_t[3:] - wb_t[:3]).astype(np.float64)
+        target = centre + rng.uniform(-1.02, 1.02, (n, 3)) * half
+        dirs = unit(rng.normal(size=(n, 3)))
+        dist = rng.uniform(0.5, 100.0, n) * s
+        org = (target - dirs * dist[:, None]).astype(F32)
+        d = unit(target - org.astype(np.float64)).astype(F32)
+        h = W.trace(org, d, time=float(time))
+        for i in np.nonzero(h["hit_id"] != MISS)[0]:
+            sc, pc, gap, mg = band_checks(wbox, A, C_loc, org[i].astype(np.float64), d[i], float(h["t"][i]))
+            n_acc += 1
+            assert not sc and not pc, (it, kind, flags, wbox, org[i], d[i], h["t"][i], gap, mg)
+    assert n_acc > 3000
