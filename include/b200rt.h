@@ -170,6 +170,11 @@ typedef struct RtStats {
     uint64_t redo_rays;      /* traversal 3: rays the fast topology could not prove, traced again on the reference tree — only with "count" */
     uint32_t max_stack;      /* deepest traversal stack use of any ray (entries) — only with "count" */
     uint32_t stack_capacity; /* entries per thread the launch provided (tree depth + 2): max_stack must never exceed it */
+    uint32_t tracks;         /* paths in flight per pixel the library chose (<= lanes of this rank; "max_slots" / pixels) */
+    uint32_t pipes;          /* wavefront pipelines (streams) used */
+    double merge_ms;         /* rt_render_multi: device time of this GPU's share of the film combine (k_merge_peers + copy-out) */
+    uint64_t warp_rounds, busy_lane_rounds; /* only with "count": scheduling rounds of the extend warps and lanes holding a ray in them */
+    uint64_t rounds_hist[24];/* only with "count": rays by floor(log2(traversal rounds)) — the tail that sets a launch's duration */
 } RtStats;
 
 typedef struct RtScene RtScene;
@@ -203,6 +208,12 @@ int rt_render(RtScene* scene, const RtRenderParams* params, float* out_rgb, RtSt
 int rt_render_device(RtScene* scene, const RtRenderParams* params, float* d_out_rgb, void* cuda_stream,
                      RtStats* out_stats);
 
+/* rt_render_device plus the per-pixel second moment: d_out_sumsq[p] = sum over all samples of (r^2 + g^2 + b^2) (width*height
+ * floats).  With the film (the mean) this gives the per-sample variance the image-RMSE acceptance bound is derived from
+ * (RMSE <= 1.25 sqrt(2 mean(sigma^2) / N)); the reference has no counterpart (rendering.rs:172-179 keeps only the sum). */
+int rt_render_moments_device(RtScene* scene, const RtRenderParams* params, float* d_out_rgb, float* d_out_sumsq, void* cuda_stream,
+                             RtStats* out_stats);
+
 /* Multi-GPU split of render(): this rank renders sample lanes {lane_first, lane_first+lane_stride, ...} < T and
  * writes  sum over its lanes of (lane plane / lane sample count)  into d_plane_sum (width*height*3 floats).
  * After summing d_plane_sum over ranks (NCCL all-reduce), rt_film_scale_device multiplies by 1/T (merge_planes). */
@@ -210,10 +221,25 @@ int rt_render_planes_device(RtScene* scene, const RtRenderParams* params, uint32
                             float* d_plane_sum, void* cuda_stream, RtStats* out_stats);
 int rt_film_scale_device(float* d_rgb, uint64_t n_floats, float multiplier, void* cuda_stream);
 
+/* render() on n_scenes GPUs of one box in ONE blocking call (replaces the worker-thread scope + merge_planes of rendering.rs:161-210,
+ * 239-252 across devices).  scenes[g] = the same RtSceneDesc created on n_scenes different devices.  GPU g renders sample lanes
+ * g, g + n_scenes, ... of the thread_count lanes (one host thread per GPU); the film is combined inside the library by a
+ * fixed-order reduce over NVLink peer memory fused with the finalize step (lane T-1 first, then ascending, x 1/T — merge_planes'
+ * own order), so out_rgb has the SAME BITS for every n_scenes, n_scenes = 1 and rt_render included.  Needs peer access between
+ * the GPUs (RT_EUNSUPPORTED otherwise).  out_stats: NULL or n_scenes entries (per GPU).
+ * rt_render_multi_device leaves the complete film on every GPU instead (d_out_rgb[g] on scenes[g]'s device; the all-gather is
+ * fused into the reduce as peer stores). */
+int rt_render_multi(RtScene* const* scenes, int n_scenes, const RtRenderParams* params, float* out_rgb, RtStats* out_stats);
+int rt_render_multi_device(RtScene* const* scenes, int n_scenes, const RtRenderParams* params, float* const* d_out_rgb, RtStats* out_stats);
+
 /* Color::to_rgb8_gamma2 on device data. */
 int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_out_rgb8, void* cuda_stream);
 
-/* Knobs (process-wide).  "traversal": 0 = reference node test only, true divisions (the reference's algorithm, for A/B
+/* Knobs (process-wide; every rt_scene_create / render call reads ONE consistent snapshot at entry, rt_set_option is
+ * serialised with those reads, so the calls stay re-entrant).  "max_slots": paths in flight per render (default 160 Mi): the
+ * library runs min(lanes, max_slots / pixels) tracks per pixel and feeds the caller's thread_count lanes through them, so the
+ * path-state workspace (120 B per slot) no longer grows with thread_count.  
+ * "traversal": 0 = reference node test only, true divisions (the reference's algorithm, for A/B
  * parity sweeps); 1 = + tight carried-interval cull; 2 = + reciprocal fast path with exact fallback; 3 (default) = a
  * rebuilt (SAH) topology over the same elements finds the closest accepted element, the result is kept only when the
  * reference traversal provably returns the same element (unique minimum, hit point strictly inside the element's parent
@@ -226,7 +252,7 @@ int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_o
  * cut into several references with tighter boxes (an element may sit in several leaves of the accelerator tree).
  * "count": 1 = maintain node_visits / prim_tests / exact_steps.  "profile": 1 = time extend / shade separately.
  * "refill": busy-lane threshold of the persistent extend warps.  "leaf_weight": phase-vote weight.  "check_every": host
- * polling period (iterations).  "pipes": independent wavefront pipelines (streams) per render (default 2: one pipeline's launch tails overlap the other's work; the film is bit-identical for any value).
+ * polling period (iterations).  "pipes": independent wavefront pipelines (streams) per render (default 0 = auto, 2 for >= 64 Mi path slots, else 4: one pipeline's launch tails overlap the other's work; the film is bit-identical for any value).
  * "blocks_per_sm": cap on resident blocks of the persistent kernels.
  * Environment: RT_ITER_LOG=<path> dumps (pipe, iteration, live paths, extend ms, shade ms) of the last render as CSV. */
 int rt_set_option(const char* key, int64_t value);

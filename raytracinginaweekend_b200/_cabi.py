@@ -69,10 +69,13 @@ class RtStats(C.Structure):
     _fields_ = [("ray_segments", C.c_uint64), ("paths", C.c_uint64), ("iterations", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("render_ms", C.c_double), ("extend_ms", C.c_double),
                 ("shade_ms", C.c_double), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64), ("exact_steps", C.c_uint64),
-                ("redo_rays", C.c_uint64), ("max_stack", C.c_uint32), ("stack_capacity", C.c_uint32)]
+                ("redo_rays", C.c_uint64), ("max_stack", C.c_uint32), ("stack_capacity", C.c_uint32),
+                ("tracks", C.c_uint32), ("pipes", C.c_uint32), ("merge_ms", C.c_double), ("warp_rounds", C.c_uint64), ("busy_lane_rounds", C.c_uint64), ("rounds_hist", C.c_uint64 * 24)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["rounds_hist"] = list(self.rounds_hist)
+        return d
 
 
 ITEM_DTYPE = np.dtype([("kind", "<u4"), ("material", "<u4"), ("geom", "<f4", (24,)), ("wrap_flags", "<u4"),
@@ -86,7 +89,7 @@ assert ITEM_DTYPE.itemsize == C.sizeof(RtItem) and NODE_DTYPE.itemsize == C.size
 assert MATERIAL_DTYPE.itemsize == C.sizeof(RtMaterial) and TEXTURE_DTYPE.itemsize == C.sizeof(RtTexture)
 
 EXPORTED = ["rt_last_error", "rt_device_count", "rt_scene_create", "rt_scene_destroy", "rt_scene_device_bytes", "rt_scene_set_ray_time",
-            "rt_trace", "rt_trace_device", "rt_render", "rt_render_device", "rt_render_planes_device",
+            "rt_trace", "rt_trace_device", "rt_render", "rt_render_device", "rt_render_moments_device", "rt_render_planes_device", "rt_render_multi", "rt_render_multi_device",
             "rt_film_scale_device", "rt_to_rgb8_gamma2_device", "rt_set_option"]
 
 _lib = None
@@ -115,8 +118,11 @@ def lib():
         L.rt_trace_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_float] + [C.c_void_p] * 6
         L.rt_render.argtypes = [C.c_void_p, C.POINTER(RtRenderParams), C.c_void_p, C.POINTER(RtStats)]
         L.rt_render_device.argtypes = [C.c_void_p, C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p, C.POINTER(RtStats)]
+        L.rt_render_moments_device.argtypes = [C.c_void_p, C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RtStats)]
         L.rt_render_planes_device.argtypes = [C.c_void_p, C.POINTER(RtRenderParams), C.c_uint32, C.c_uint32, C.c_void_p,
                                               C.c_void_p, C.POINTER(RtStats)]
+        L.rt_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(RtRenderParams), C.c_void_p, C.POINTER(RtStats)]
+        L.rt_render_multi_device.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(RtRenderParams), C.POINTER(C.c_void_p), C.POINTER(RtStats)]
         L.rt_film_scale_device.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p]
         L.rt_to_rgb8_gamma2_device.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.rt_set_option.argtypes = [C.c_char_p, C.c_int64]
@@ -315,6 +321,15 @@ class DeviceScene:
         check(lib().rt_render_device(self.h, C.byref(p), C.c_void_p(d_out_ptr), C.c_void_p(stream), C.byref(st)))
         return st.as_dict()
 
+    def render_moments_device(self, d_out_ptr: int, d_sumsq_ptr: int, width, height, spp, max_depth=50, thread_count=1, seed=1,
+                              render_mode=0, stream: int = 0):
+        """Film + per-pixel sum over samples of (r^2 + g^2 + b^2)."""
+        p = RtRenderParams(width, height, spp, max_depth, thread_count, render_mode, seed)
+        st = RtStats()
+        check(lib().rt_render_moments_device(self.h, C.byref(p), C.c_void_p(d_out_ptr), C.c_void_p(d_sumsq_ptr), C.c_void_p(stream),
+                                             C.byref(st)))
+        return st.as_dict()
+
     def render_planes_device(self, d_out_ptr: int, lane_first, lane_stride, width, height, spp, max_depth=50,
                              thread_count=1, seed=1, render_mode=0, stream: int = 0):
         p = RtRenderParams(width, height, spp, max_depth, thread_count, render_mode, seed)
@@ -322,3 +337,14 @@ class DeviceScene:
         check(lib().rt_render_planes_device(self.h, C.byref(p), lane_first, lane_stride, C.c_void_p(d_out_ptr),
                                             C.c_void_p(stream), C.byref(st)))
         return st.as_dict()
+
+
+def render_multi(scenes, width, height, spp, max_depth=50, thread_count=1, seed=1, render_mode=0):
+    """rt_render_multi: one blocking call over len(scenes) GPUs (DeviceScene objects on different devices); host film + per-GPU stats."""
+    n = len(scenes)
+    p = RtRenderParams(width, height, spp, max_depth, thread_count, render_mode, seed)
+    hs = (C.c_void_p * n)(*[C.cast(s.h, C.c_void_p).value for s in scenes])
+    out = np.zeros((height, width, 3), np.float32)
+    st = (RtStats * n)()
+    check(lib().rt_render_multi(hs, n, C.byref(p), _p(out), st))
+    return out, [s.as_dict() for s in st]

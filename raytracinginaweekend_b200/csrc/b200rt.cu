@@ -16,6 +16,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200rt.h"
@@ -27,6 +28,9 @@ using namespace rt;
 namespace {
 
 thread_local std::string g_err;
+// Knobs (rt_set_option).  Writers and readers go through g_opt_mu; rt_scene_create and every render take ONE snapshot at entry
+// (Options), so a concurrent rt_set_option never changes a call half-way.
+std::mutex g_opt_mu;
 int g_opt_traversal = 3;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path,
                               // 3 = rebuilt topology + per-ray proof, unproven rays on the reference tree with 2 (plain scenes; else 2)
 int g_opt_presplit = 800;     // reference budget of the rebuilt tree in per cent of the element count (<= 100: no pre-splitting)
@@ -34,13 +38,27 @@ int g_opt_rebuild_min_items = 32;  // below this the reference tree is as good (
 int g_opt_rebuild_wrapped = 1;  // also build it for scenes with wrapped elements / volumes (true world-space bounds)
 int g_opt_rebuild = 1;        // build the second topology at rt_scene_create (0: traversal 3 behaves like 2)
 int g_opt_rebuild_depth_extra = 4;  // depth cap of the rebuilt tree = reference depth + this (the stack lives in shared memory)
-int g_opt_pipes = 2;         // independent wavefront pipelines (streams) per render: one pipeline's extend tail overlaps the other's work
+int g_opt_pipes = 0;         // independent wavefront pipelines (streams) per render: one pipeline's extend tail overlaps the others' work.
+                              // 0 = auto: 2 for renders with >= 64 Mi path slots (throughput-bound), 4 below (launch-tail-bound)
 int g_opt_leaf_weight = 24;   // extend phase vote: leaf phase when n_leaf * w > n_node * 16
 int g_opt_refill = 28;        // extend refills idle lanes when fewer than this many of 32 are busy
 int g_opt_count = 0;        // 1 = COUNT kernel variant (node visits / primitive tests per ray)
 int g_opt_profile = 0;        // 1 = time every extend / shade launch with CUDA events on the launching stream (no extra syncs)
 int g_opt_check_every = 8;    // host polls the live-path count every N iterations
 int g_opt_blocks_per_sm = 0;  // 0 = from occupancy query
+int64_t g_opt_max_slots = 160ll << 20;  // path slots in flight per render (bounds the workspace: 120 B per slot, 19 GB at most); tracks per pixel = max_slots / pixels
+
+struct Options {
+    int traversal, presplit, rebuild_min_items, rebuild_wrapped, rebuild, rebuild_depth_extra, pipes, leaf_weight, refill, count, profile,
+        check_every, blocks_per_sm;
+    int64_t max_slots;
+};
+Options options_snapshot() {
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    return Options{g_opt_traversal, g_opt_presplit, g_opt_rebuild_min_items, g_opt_rebuild_wrapped, g_opt_rebuild, g_opt_rebuild_depth_extra,
+                   g_opt_pipes, g_opt_leaf_weight, g_opt_refill, g_opt_count, g_opt_profile, g_opt_check_every, g_opt_blocks_per_sm,
+                   g_opt_max_slots};
+}
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -59,9 +77,15 @@ struct DevBuf {
     size_t n = 0;
     cudaError_t alloc(size_t count) {
         release();
-        n = count;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc(&p, count * sizeof(T));
+        const cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();  // clear the sticky-looking last error: the next call must not report this OOM again
+            return e;
+        }
+        n = count;
+        return cudaSuccess;
     }
     void release() {
         if (p) cudaFree(p);
@@ -79,16 +103,18 @@ struct DevBuf {
 struct Workspace {
     std::mutex mu;
     DevBuf<float4> A[2], B[2], C[2], acc;
-    DevBuf<int32_t> D[2];
+    DevBuf<int2> D[2];
     DevBuf<float> Tm[2];
     DevBuf<uint2> hits;
     DevBuf<Counters> ctr;
-    DevBuf<float> film;
+    size_t ws_slots2 = 0;            // slots the second queue set (A[1]..D[1]) is sized for
+    DevBuf<float> film, sumsq;
     static const int MAX_PIPES = 8;
     Counters* h_ctr = nullptr;  // pinned, MAX_PIPES x 2 entries (double-buffered poll per pipeline)
     cudaEvent_t poll_event[MAX_PIPES][2] = {};
     cudaStream_t pipe_stream[MAX_PIPES] = {};
     cudaEvent_t fork_event = nullptr, join_event[MAX_PIPES] = {};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // render brackets (created once: no per-call create / destroy to leak on error paths)
     std::vector<cudaEvent_t> prof_events[MAX_PIPES];
     DevBuf<uint32_t> iter_log;  // [MAX_PIPES][ITER_LOG_CAP], only with RT_ITER_LOG set
     static const int ITER_LOG_CAP = 16384;
@@ -217,7 +243,7 @@ inline float u2f(uint32_t u) {
     return f;
 }
 
-int pack_scene(const RtSceneDesc& d, RtScene& sc) {
+int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     const uint32_t N = d.n_items;
     if (N == 0) return fail(RT_EINVAL, "scene has no items (the reference BVH builder recurses forever on an empty list)");
     if (N > RT_REF_ITEM_MASK) return fail(RT_EINVAL, "too many items");
@@ -238,6 +264,21 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
         if (t.kind == RT_TEX_CHECKER && (t.even >= d.n_textures || t.odd >= d.n_textures)) return fail(RT_EINVAL, "checker texture child out of range");
         if (t.kind == RT_TEX_IMAGE && (t.image >= d.n_images || !d.images[t.image].rgb8 || d.images[t.image].width == 0 || d.images[t.image].height == 0))
             return fail(RT_EINVAL, "image texture refers to a missing image");
+    }
+    // a checker must resolve to a non-checker texture within 8 levels whichever way it branches (the device walks at most 8)
+    for (uint32_t i = 0; i < d.n_textures; ++i) {
+        if (d.textures[i].kind != RT_TEX_CHECKER) continue;
+        std::vector<uint32_t> level{i};
+        bool ok = false;
+        for (int depth = 0; depth < 8 && !ok; ++depth) {
+            std::vector<uint32_t> next;
+            for (uint32_t t : level)
+                for (uint32_t c : {d.textures[t].even, d.textures[t].odd})
+                    if (d.textures[c].kind == RT_TEX_CHECKER && std::find(next.begin(), next.end(), c) == next.end()) next.push_back(c);
+            ok = next.empty();
+            level.swap(next);
+        }
+        if (!ok) return fail(RT_EINVAL, "checker texture nesting deeper than 8 levels (or cyclic)");
     }
     auto ref_of_item = [&](uint32_t item) {
         return RT_REF_LEAF | (d.items[item].kind << RT_REF_KIND_SHIFT) | (d.items[item].wrap_flags ? RT_REF_WRAPPED : 0u) | item;
@@ -455,14 +496,14 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
     std::vector<NodeDev> nodes2;
     std::vector<float4> vis_box;
     uint32_t root2 = 0;
-    if (N >= (uint32_t)std::max(2, g_opt_rebuild_min_items) && g_opt_rebuild && sc.boxes_are_bounds && (!any_wrap || (g_opt_rebuild_wrapped && times_ok))) {
+    if (N >= (uint32_t)std::max(2, O.rebuild_min_items) && O.rebuild && sc.boxes_are_bounds && (!any_wrap || (O.rebuild_wrapped && times_ok))) {
         std::vector<rt_rebuild::Box3> lb(N);
         std::vector<float> tri;
         std::vector<uint8_t> is_tri(N, 0);
         for (uint32_t i = 0; i < N; ++i)
             for (int k = 0; k < 3; ++k) { lb[i].mn[k] = fbox[i].mn[k]; lb[i].mx[k] = fbox[i].mx[k]; }
         // pre-split sliver triangles into several references (rt_rebuild.hpp); the budget shrinks for very large scenes
-        const double factor = g_opt_presplit <= 100 ? 1.0 : std::min((double)g_opt_presplit / 100.0, N <= 150000u ? 16.0 : (N <= 2000000u ? 2.0 : 1.0));
+        const double factor = O.presplit <= 100 ? 1.0 : std::min((double)O.presplit / 100.0, N <= 150000u ? 16.0 : (N <= 2000000u ? 2.0 : 1.0));
         if (factor > 1.0) {
             tri.assign(9 * (size_t)N, 0.0f);
             for (uint32_t i = 0; i < N; ++i)
@@ -478,7 +519,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
         rt_rebuild::Tree F;
         uint32_t extra_levels = 0;
         while (((size_t)N << extra_levels) < refs.size()) ++extra_levels;
-        rt_rebuild::build(rbx, depth + extra_levels + (uint32_t)std::max(0, g_opt_rebuild_depth_extra), F);
+        rt_rebuild::build(rbx, depth + extra_levels + (uint32_t)std::max(0, O.rebuild_depth_extra), F);
         const uint32_t n2 = (uint32_t)F.left.size();
         auto item_of = [&](uint32_t leafref) -> uint32_t { return refs[leafref & ~RT_LEAF_BIT].item; };
         std::vector<float> a2(n2, 0.0f), c2(n2, 0.0f);
@@ -658,32 +699,48 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc) {
 size_t stack_smem_bytes(const RtScene& sc, int block) { return (size_t)sc.dev.stack_cap * block * 8; }
 
 template <class K>
-int persistent_grid(const RtScene& sc, K kernel, int block, size_t smem, int* out_grid) {
+int persistent_grid(const RtScene& sc, K kernel, int block, size_t smem, int* out_grid, int blocks_per_sm_cap = 0) {
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
     if (per_sm < 1) return fail(RT_ECUDA, "kernel does not fit on an SM (BVH too deep for the shared-memory stack)");
-    if (g_opt_blocks_per_sm > 0) per_sm = std::min(per_sm, g_opt_blocks_per_sm);
+    if (blocks_per_sm_cap > 0) per_sm = std::min(per_sm, blocks_per_sm_cap);
     *out_grid = per_sm * sc.sm_count;
     return RT_OK;
 }
 
-int ensure_workspace(Workspace& sc, size_t slots, size_t npix, bool need_time) {
+// Grows the per-device workspace.  On any allocation failure every queue buffer is released and the sizes reset, so a later
+// (smaller) render never runs on a half-allocated workspace.
+void release_workspace_queues(Workspace& w) {
+    for (int q = 0; q < 2; ++q) { w.A[q].release(); w.B[q].release(); w.C[q].release(); w.D[q].release(); w.Tm[q].release(); }
+    w.hits.release();
+    w.acc.release();
+    w.ws_slots = 0;
+    w.ws_slots2 = 0;
+}
+int ensure_workspace(Workspace& sc, size_t slots, size_t acc_elems, size_t npix, bool need_time, bool two_queues) {
+    cudaError_t e = cudaSuccess;
+    auto grow = [&](auto& buf, size_t count) {
+        if (e == cudaSuccess && buf.n < count) e = buf.alloc(count);
+    };
     if (sc.ws_slots < slots) {
-        for (int q = 0; q < 2; ++q) {
-            CU(sc.A[q].alloc(slots));
-            CU(sc.B[q].alloc(slots));
-            CU(sc.C[q].alloc(slots));
-            CU(sc.D[q].alloc(slots));
-            sc.Tm[q].release();
-        }
-        CU(sc.hits.alloc(slots));
-        CU(sc.acc.alloc(slots));
-        sc.ws_slots = slots;
+        grow(sc.A[0], slots); grow(sc.B[0], slots); grow(sc.C[0], slots); grow(sc.D[0], slots);
+        grow(sc.hits, slots);
+        sc.Tm[0].release();
+        if (e == cudaSuccess) sc.ws_slots = slots;
     }
-    if (need_time && sc.Tm[0].n < sc.ws_slots) {
-        CU(sc.Tm[0].alloc(sc.ws_slots));
-        CU(sc.Tm[1].alloc(sc.ws_slots));
+    if (two_queues && sc.ws_slots2 < slots) {  // the wavefront loop ping-pongs between two queue sets
+        grow(sc.A[1], slots); grow(sc.B[1], slots); grow(sc.C[1], slots); grow(sc.D[1], slots);
+        sc.Tm[1].release();
+        if (e == cudaSuccess) sc.ws_slots2 = slots;
+    }
+    grow(sc.acc, acc_elems);
+    if (need_time) { grow(sc.Tm[0], sc.ws_slots); if (two_queues) grow(sc.Tm[1], sc.ws_slots2); }
+    grow(sc.film, npix * 3);
+    grow(sc.sumsq, npix);
+    if (e != cudaSuccess) {
+        release_workspace_queues(sc);
+        return fail(e == cudaErrorMemoryAllocation ? RT_ENOMEM : RT_ECUDA, std::string("render workspace: ") + cudaGetErrorString(e));
     }
     if (!sc.ctr.p) CU(sc.ctr.alloc(Workspace::MAX_PIPES));
     if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, Workspace::MAX_PIPES * 2 * sizeof(Counters)));
@@ -695,7 +752,6 @@ int ensure_workspace(Workspace& sc, size_t slots, size_t npix, bool need_time) {
             for (int b = 0; b < 2; ++b) CU(cudaEventCreate(&sc.poll_event[p][b]));
         }
     }
-    if (sc.film.n < npix * 3) CU(sc.film.alloc(npix * 3));
     return RT_OK;
 }
 
@@ -710,54 +766,98 @@ static ExtendFn pick_extend(int mode, bool count, int feat) {
     return feat == 2 ? pick_extend_feat<2>(mode, count) : (feat == 1 ? pick_extend_feat<1>(mode, count) : pick_extend_feat<0>(mode, count));
 }
 
-int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint32_t lane_stride, float* d_out, bool apply_scale,
-                cudaStream_t stream, RtStats* stats) {
+// What one rank renders: validated parameters + the lane / track split.
+struct RenderPlan {
+    RenderDev R{};       // rank-level description (k_finalize and the multi-GPU reduce use it as is)
+    uint64_t n_tasks = 0;
+    uint32_t n_local = 0;  // lanes this rank owns (0: it contributes nothing)
+    uint32_t n_tracks = 0; // paths in flight per pixel
+    size_t npix = 0, slots = 0, acc_elems = 0;
+};
+
+int make_plan(const RtScene& sc, const Options& O, const RtRenderParams& P, uint32_t lane_first, uint32_t lane_stride, RenderPlan& pl) {
     if (P.width < 2 || P.height < 2) return fail(RT_EINVAL, "image must be at least 2x2 (reference divides by width-1 / height-1)");
     if (P.samples_per_pixel == 0) return fail(RT_EINVAL, "samples_per_pixel must be >= 1");
     if (P.thread_count == 0) return fail(RT_EINVAL, "thread_count must be >= 1");
     if (P.render_mode > RT_MODE_NORMALS) return fail(RT_EINVAL, "unknown render mode");
     if (lane_stride == 0) return fail(RT_EINVAL, "lane_stride must be >= 1");
     const uint64_t T = P.thread_count;
-    const uint64_t n_tasks = std::min<uint64_t>(T, P.samples_per_pixel);
+    pl.n_tasks = std::min<uint64_t>(T, P.samples_per_pixel);
     if (P.samples_per_pixel / T + 1 > 0x7FFFFFFFull) return fail(RT_EINVAL, "too many samples per lane");
-    const size_t npix = (size_t)P.width * P.height;
-    CU(cudaSetDevice(sc.device));
-    if (lane_first >= n_tasks) {  // this rank owns no lane: contributes zeros
-        CU(cudaMemsetAsync(d_out, 0, npix * 3 * sizeof(float), stream));
-        if (stats) std::memset(stats, 0, sizeof(*stats));
-        return RT_OK;
+    pl.npix = (size_t)P.width * P.height;
+    if (pl.npix > 0x7FFFFFFFull) return fail(RT_EINVAL, "image too large");
+    pl.n_local = lane_first >= pl.n_tasks ? 0u : (uint32_t)((pl.n_tasks - lane_first + lane_stride - 1) / lane_stride);
+    // Tracks: the library, not the caller's thread_count, decides how many paths are in flight.  Each pixel gets J tracks
+    // (J * pixels <= max_slots); track j renders the rank's lanes j, j + J, ... one after the other, so the path-state
+    // workspace is bounded while every lane still owns its plane (merge_planes needs all T of them: 16 B x T x pixels).
+    if (pl.n_local) {
+        const uint64_t budget = (uint64_t)std::max<int64_t>(O.max_slots, 1);
+        uint32_t J = (uint32_t)std::min<uint64_t>(pl.n_local, std::max<uint64_t>(1, budget / pl.npix));
+        const uint32_t rounds = (pl.n_local + J - 1) / J;
+        J = (pl.n_local + rounds - 1) / rounds;  // same number of rounds, evenly filled tracks
+        pl.n_tracks = J;
+        pl.slots = (size_t)J * pl.npix;
+        if (pl.slots > 0xFFFFFFF0ull) return fail(RT_EINVAL, "width*height*tracks exceeds 2^32 path slots (lower max_slots)");
+        pl.acc_elems = (size_t)pl.n_local * pl.npix;
     }
-    const uint32_t n_local = (uint32_t)((n_tasks - lane_first + lane_stride - 1) / lane_stride);
-    const size_t slots = (size_t)n_local * npix;
-    if (slots > 0xFFFFFFF0ull) return fail(RT_EINVAL, "width*height*lanes exceeds 2^32 path slots");
-    Workspace& ws = workspace_of(sc.device);
-    std::lock_guard<std::mutex> ws_lock(ws.mu);
-    int rc = ensure_workspace(ws, slots, npix, sc.has_animation);
-    if (rc) return rc;
-
-    RenderDev R{};   // rank-level description (k_finalize uses it as is)
-    R.acc = ws.acc.p;
-    R.npix = (uint32_t)npix; R.width = (uint32_t)P.width; R.height = (uint32_t)P.height;
+    RenderDev& R = pl.R;
+    R.npix = (uint32_t)pl.npix; R.width = (uint32_t)P.width; R.height = (uint32_t)P.height;
     R.max_depth = P.max_depth;
-    R.n_tasks = (uint32_t)n_tasks;
-    R.lane_first = lane_first; R.lane_stride = lane_stride; R.n_local_lanes = n_local;
+    R.n_tasks = (uint32_t)pl.n_tasks;
+    R.lane_first = lane_first; R.lane_stride = lane_stride; R.n_local_lanes = pl.n_local;
+    R.n_tracks = pl.n_tracks;
     R.spp_whole = (uint32_t)(P.samples_per_pixel / T);
     R.spp_rem = (uint32_t)(P.samples_per_pixel % T);
     R.seed0 = (uint32_t)P.seed; R.seed1 = (uint32_t)(P.seed >> 32);
     R.sx = 1.0f / (float)(P.width - 1);
     R.sy = 1.0f / (float)(P.height - 1);
     R.mode = P.render_mode;
-    R.ref_only = (g_opt_traversal == 0 || !sc.boxes_are_bounds) ? 1u : 0u;
-    R.refill_threshold = (uint32_t)std::min(32, std::max(1, g_opt_refill));
-    R.leaf_weight = (uint32_t)std::max(1, g_opt_leaf_weight);
+    R.ref_only = (O.traversal == 0 || !sc.boxes_are_bounds) ? 1u : 0u;
+    R.refill_threshold = (uint32_t)std::min(32, std::max(1, O.refill));
+    R.leaf_weight = (uint32_t)std::max(1, O.leaf_weight);
+    return RT_OK;
+}
 
-    // Split the rank's lanes over G independent wavefront pipelines, each on its own stream with its own queues and
+// The wavefront loop of one rank.  The caller holds ws.mu.  Leaves the per-lane sums in ws.acc (pl.R.acc); with `finalize` also
+// writes the film (unscaled unless apply_scale) into d_out and, if d_sumsq, the per-pixel sum of squared samples.
+// On any error every pipeline stream is drained before returning, so the shared workspace is never reused under running kernels.
+int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, float* d_out, bool apply_scale, float* d_sumsq,
+                  bool finalize, cudaStream_t stream, RtStats* stats) {
+    const size_t npix = pl.npix;
+    CU(cudaSetDevice(sc.device));
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (pl.n_local == 0) {  // this rank owns no lane: contributes zeros
+        if (finalize) {
+            CU(cudaMemsetAsync(d_out, 0, npix * 3 * sizeof(float), stream));
+            if (d_sumsq) CU(cudaMemsetAsync(d_sumsq, 0, npix * sizeof(float), stream));
+        }
+        return RT_OK;
+    }
+    int rc = ensure_workspace(ws, pl.slots, pl.acc_elems, npix, sc.has_animation, true);
+    if (rc) return rc;
+    if (!ws.ev0) {
+        CU(cudaEventCreate(&ws.ev0));
+        CU(cudaEventCreate(&ws.ev1));
+    }
+    RenderDev& R = pl.R;
+    R.acc = ws.acc.p;
+    const uint32_t J = pl.n_tracks;
+
+    int mode = std::min(3, std::max(0, O.traversal));
+    if (!sc.boxes_are_bounds) mode = 0;
+    if (mode == 3 && !sc.nodes2.p) mode = 2;  // no rebuilt topology for this scene (wrapped elements, single element, rebuild off)
+    const int feat = sc.has_volume ? 2 : (sc.has_wrapped ? 1 : 0);
+    const int eblock = 128;
+    const size_t esmem = stack_smem_bytes(sc, eblock);
+
+    // Split the rank's tracks over G independent wavefront pipelines, each on its own stream with its own queues and
     // counters.  A persistent extend launch ends with a tail in which a few very long rays keep a few warps busy; with two
     // pipelines in flight the other pipeline's blocks backfill the SMs during that tail (and during shade / launch gaps).
     const char* iter_log_path = std::getenv("RT_ITER_LOG");  // debug: dump (pipe, iteration, live paths, extend ms, shade ms)
     if (iter_log_path && !ws.iter_log.p) CU(ws.iter_log.alloc((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP * 8));
     std::vector<std::array<float, 2>> iter_ms[Workspace::MAX_PIPES];
-    const int G = (int)std::min<uint32_t>((uint32_t)std::max(1, std::min(g_opt_pipes, (int)Workspace::MAX_PIPES)), n_local);
+    const int want_pipes = O.pipes > 0 ? O.pipes : (pl.slots >= ((size_t)64 << 20) ? 2 : 4);
+    const int G = (int)std::min<uint32_t>((uint32_t)std::max(1, std::min(want_pipes, (int)Workspace::MAX_PIPES)), J);
     struct Pipe {
         RenderDev R;
         cudaStream_t st;
@@ -771,10 +871,10 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
         size_t off = 0;
         for (int p = 0; p < G; ++p) {
             Pipe& pp = pipes[p];
-            const uint32_t lanes_p = (n_local - (uint32_t)p + (uint32_t)G - 1u) / (uint32_t)G;
+            const uint32_t tracks_p = (J - (uint32_t)p + (uint32_t)G - 1u) / (uint32_t)G;
             pp.R = R;
             pp.R.pipe = (uint32_t)p; pp.R.n_pipes = (uint32_t)G;
-            pp.R.cap = (uint32_t)((size_t)lanes_p * npix);
+            pp.R.cap = (uint32_t)((size_t)tracks_p * npix);
             for (int q = 0; q < 2; ++q) {
                 pp.R.A[q] = ws.A[q].p + off; pp.R.B[q] = ws.B[q].p + off; pp.R.C[q] = ws.C[q].p + off; pp.R.D[q] = ws.D[q].p + off;
                 pp.R.Tm[q] = sc.has_animation ? ws.Tm[q].p + off : nullptr;
@@ -786,32 +886,32 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
             off += pp.R.cap;
         }
     }
+    // error exits: drain the pipeline streams so the workspace is quiescent when ws.mu is released
+    struct Drain {
+        std::vector<Pipe>& pipes;
+        bool armed = true;
+        ~Drain() {
+            if (!armed) return;
+            for (Pipe& pp : pipes) cudaStreamSynchronize(pp.st);
+            cudaGetLastError();
+        }
+    } drain{pipes};
 
-    const int eblock = 128;
-    const size_t esmem = stack_smem_bytes(sc, eblock);
     int egrid = 0, sgrid = 0;
-    int mode = std::min(3, std::max(0, g_opt_traversal));
-    if (!sc.boxes_are_bounds) mode = 0;
-    if (mode == 3 && !sc.nodes2.p) mode = 2;  // no rebuilt topology for this scene (wrapped elements, single element, rebuild off)
-    const int feat = sc.has_volume ? 2 : (sc.has_wrapped ? 1 : 0);
-    ExtendFn ext = mode == 3 ? (feat == 2 ? (g_opt_count ? k_extend<3, true, 2> : k_extend<3, false, 2>)
-                                          : (feat == 1 ? (g_opt_count ? k_extend<3, true, 1> : k_extend<3, false, 1>)
-                                                       : (g_opt_count ? k_extend<3, true, 0> : k_extend<3, false, 0>)))
-                             : pick_extend(mode, g_opt_count != 0, feat);
-    rc = persistent_grid(sc, ext, eblock, esmem, &egrid);
+    ExtendFn ext = mode == 3 ? (feat == 2 ? (O.count ? k_extend<3, true, 2> : k_extend<3, false, 2>)
+                                          : (feat == 1 ? (O.count ? k_extend<3, true, 1> : k_extend<3, false, 1>)
+                                                       : (O.count ? k_extend<3, true, 0> : k_extend<3, false, 0>)))
+                             : pick_extend(mode, O.count != 0, feat);
+    rc = persistent_grid(sc, ext, eblock, esmem, &egrid, O.blocks_per_sm);
+    if (rc) return rc;
+    rc = persistent_grid(sc, k_shade, 128, 0, &sgrid, O.blocks_per_sm);
     if (rc) return rc;
 
-    rc = persistent_grid(sc, k_shade, 128, 0, &sgrid);
-    if (rc) return rc;
-
-    cudaEvent_t ev0, ev1;
-    CU(cudaEventCreate(&ev0));
-    CU(cudaEventCreate(&ev1));
     uint64_t launches = 0;
     double extend_ms = 0.0, shade_ms = 0.0;
-    const int chunk = g_opt_check_every;
+    const int chunk = std::max(1, O.check_every);
     // per-launch timing without extra synchronisation: 3 events per iteration, read back after the chunk's poll
-    if (g_opt_profile) {
+    if (O.profile) {
         for (int p = 0; p < G; ++p)
             while (ws.prof_events[p].size() < (size_t)(2 * 3 * chunk)) {
                 cudaEvent_t e;
@@ -819,8 +919,10 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
                 ws.prof_events[p].push_back(e);
             }
     }
-    CU(cudaEventRecord(ev0, stream));
+    CU(cudaEventRecord(ws.ev0, stream));
+    CU(cudaMemsetAsync(ws.acc.p, 0, pl.acc_elems * sizeof(float4), stream));  // every lane plane starts at zero
     CU(cudaEventRecord(ws.fork_event, stream));
+    ++launches;
     for (int p = 0; p < G; ++p) {
         Pipe& pp = pipes[p];
         CU(cudaStreamWaitEvent(pp.st, ws.fork_event, 0));
@@ -828,14 +930,15 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
         k_generate<<<ggrid, 256, 0, pp.st>>>(sc.dev, pp.R);
         ++launches;
     }
-    const uint64_t max_iters = (uint64_t)(R.spp_whole + 1u) * (uint64_t)std::max(P.max_depth, 1) + 4 + 2 * (uint64_t)chunk;
+    // a track renders ceil(n_local / J) lanes, each up to spp_whole + 1 samples of at most max_depth segments
+    const uint64_t max_iters = (uint64_t)((pl.n_local + J - 1) / J) * (uint64_t)(R.spp_whole + 1u) * (uint64_t)std::max(R.max_depth, 1) + 4 + 2 * (uint64_t)chunk;
     // The host never knows the live-path count of the iteration it is launching: kernels read it from device memory
     // (grids are persistent, sized by the SM count).  Every `chunk` iterations the counters are copied to pinned memory;
     // the host keeps one chunk in flight per pipeline while it waits for the previous chunk's copy.
     auto enqueue_chunk = [&](int p, int buf) -> int {
         Pipe& pp = pipes[p];
         for (int it = 0; it < chunk; ++it) {
-            cudaEvent_t* pe = g_opt_profile ? &ws.prof_events[p][(size_t)(buf * chunk + it) * 3] : nullptr;
+            cudaEvent_t* pe = O.profile ? &ws.prof_events[p][(size_t)(buf * chunk + it) * 3] : nullptr;
             if (pe) CU(cudaEventRecord(pe[0], pp.st));
             pp.R.iter = (uint32_t)std::min<uint64_t>(pp.iters, Workspace::ITER_LOG_CAP - 1);
             ext<<<egrid, eblock, esmem, pp.st>>>(sc.dev, pp.R, pp.q);
@@ -852,7 +955,7 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
         return RT_OK;
     };
     auto harvest = [&](int p, int buf) -> int {
-        if (!g_opt_profile) return RT_OK;
+        if (!O.profile) return RT_OK;
         for (int it = 0; it < chunk; ++it) {
             cudaEvent_t* pe = &ws.prof_events[p][(size_t)(buf * chunk + it) * 3];
             float a = 0.0f, b2 = 0.0f;
@@ -894,17 +997,17 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
             if (pp.iters > max_iters) return fail(RT_ECUDA, "wavefront loop did not terminate");
         }
     }
-    {
+    if (finalize) {
         int fgrid = (int)std::min<size_t>((npix + 255) / 256, (size_t)sc.sm_count * 8);
-        k_finalize<<<fgrid, 256, 0, stream>>>(R, d_out, 1.0f / (float)n_tasks, apply_scale ? 1 : 0);
+        k_finalize<<<fgrid, 256, 0, stream>>>(R, d_out, 1.0f / (float)pl.n_tasks, apply_scale ? 1 : 0, d_sumsq);
         ++launches;
     }
-    CU(cudaEventRecord(ev1, stream));
-    CU(cudaEventSynchronize(ev1));
+    CU(cudaEventRecord(ws.ev1, stream));
+    CU(cudaEventSynchronize(ws.ev1));
     CU(cudaGetLastError());
+    drain.armed = false;
     float ms = 0.0f;
-    CU(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    CU(cudaEventElapsedTime(&ms, ws.ev0, ws.ev1));
     if (iter_log_path) {
         std::vector<uint32_t> lg((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP * 8);
         CU(cudaMemcpy(lg.data(), ws.iter_log.p, lg.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -927,26 +1030,42 @@ int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint3
         total.rays += pp.final_ctr->rays; total.paths += pp.final_ctr->paths;
         total.node_visits += pp.final_ctr->node_visits; total.prim_tests += pp.final_ctr->prim_tests; total.exact_steps += pp.final_ctr->exact_steps;
         total.redo_total += pp.final_ctr->redo_total;
+        total.rounds += pp.final_ctr->rounds; total.busy_lanes += pp.final_ctr->busy_lanes;
         total.max_sp = std::max(total.max_sp, pp.final_ctr->max_sp);
+        for (int h = 0; h < 24; ++h) total.hist[h] += pp.final_ctr->hist[h];
         iters = std::max(iters, pp.iters);
     }
-    const Counters* final_ctr = &total;
     if (stats) {
-        stats->ray_segments = final_ctr->rays;
-        stats->paths = final_ctr->paths;
+        stats->ray_segments = total.rays;
+        stats->paths = total.paths;
         stats->iterations = iters;
         stats->kernel_launches = launches;
         stats->render_ms = ms;
         stats->extend_ms = extend_ms;
         stats->shade_ms = shade_ms;
-        stats->node_visits = final_ctr->node_visits;
-        stats->prim_tests = final_ctr->prim_tests;
-        stats->exact_steps = final_ctr->exact_steps;
-        stats->redo_rays = final_ctr->redo_total;
-        stats->max_stack = final_ctr->max_sp;
+        stats->node_visits = total.node_visits;
+        stats->prim_tests = total.prim_tests;
+        stats->exact_steps = total.exact_steps;
+        stats->redo_rays = total.redo_total;
+        stats->max_stack = total.max_sp;
         stats->stack_capacity = sc.dev.stack_cap;
+        stats->tracks = J;
+        stats->pipes = (uint32_t)G;
+        stats->warp_rounds = total.rounds; stats->busy_lane_rounds = total.busy_lanes;
+        for (int h = 0; h < 24; ++h) stats->rounds_hist[h] = total.hist[h];
     }
     return RT_OK;
+}
+
+int render_core(RtScene& sc, const RtRenderParams& P, uint32_t lane_first, uint32_t lane_stride, float* d_out, bool apply_scale,
+                float* d_sumsq, cudaStream_t stream, RtStats* stats) {
+    const Options O = options_snapshot();
+    RenderPlan pl;
+    int rc = make_plan(sc, O, P, lane_first, lane_stride, pl);
+    if (rc) return rc;
+    Workspace& ws = workspace_of(sc.device);
+    std::lock_guard<std::mutex> ws_lock(ws.mu);
+    return render_locked(sc, ws, O, pl, d_out, apply_scale, d_sumsq, true, stream, stats);
 }
 
 }  // namespace
@@ -979,6 +1098,7 @@ int rt_device_count(int* out_count) {
 int rt_set_option(const char* key, int64_t value) {
     if (!key) return fail(RT_EINVAL, "key is NULL");
     std::string k(key);
+    std::lock_guard<std::mutex> lk(g_opt_mu);
     if (k == "traversal") g_opt_traversal = (int)value;
     else if (k == "rebuild") g_opt_rebuild = (int)value;
     else if (k == "rebuild_wrapped") g_opt_rebuild_wrapped = (int)value;
@@ -992,6 +1112,7 @@ int rt_set_option(const char* key, int64_t value) {
     else if (k == "pipes") g_opt_pipes = (int)value;
     else if (k == "check_every") g_opt_check_every = std::max<int>(1, (int)value);
     else if (k == "blocks_per_sm") g_opt_blocks_per_sm = (int)value;
+    else if (k == "max_slots") g_opt_max_slots = std::max<int64_t>(1, value);
     else return fail(RT_EINVAL, "unknown option " + k);
     return RT_OK;
 }
@@ -1005,7 +1126,8 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene) {
     RtScene* sc = new (std::nothrow) RtScene();
     if (!sc) return fail(RT_ENOMEM, "out of host memory");
     sc->device = device;
-    int rc = guarded([&] { return pack_scene(*desc, *sc); });
+    const Options O = options_snapshot();
+    int rc = guarded([&] { return pack_scene(*desc, *sc, O); });
     if (rc != RT_OK) {
         delete sc;
         return rc;
@@ -1042,7 +1164,7 @@ int rt_trace_device(RtScene* scene, const float* d_org, const float* d_dir, uint
     const int block = 128;
     const size_t smem = stack_smem_bytes(*scene, block);
     int grid = 0, rc;
-    const int mode = scene->boxes_are_bounds ? std::min(3, std::max(0, g_opt_traversal)) : 0;
+    const int mode = scene->boxes_are_bounds ? std::min(3, std::max(0, options_snapshot().traversal)) : 0;
     auto trc = mode == 3 ? k_trace<3> : (mode == 2 ? k_trace<2> : (mode == 1 ? k_trace<1> : k_trace<0>));
     rc = persistent_grid(*scene, trc, block, smem, &grid);
     if (rc) return rc;
@@ -1084,25 +1206,159 @@ int rt_trace(RtScene* scene, const float* org, const float* dir, uint64_t n, flo
 int rt_render_planes_device(RtScene* scene, const RtRenderParams* params, uint32_t lane_first, uint32_t lane_stride,
                             float* d_plane_sum, void* cuda_stream, RtStats* out_stats) {
     if (!scene || !params || !d_plane_sum) return fail(RT_EINVAL, "NULL argument");
-    return guarded([&] { return render_core(*scene, *params, lane_first, lane_stride, d_plane_sum, false, (cudaStream_t)cuda_stream, out_stats); });
+    return guarded([&] { return render_core(*scene, *params, lane_first, lane_stride, d_plane_sum, false, nullptr, (cudaStream_t)cuda_stream, out_stats); });
 }
 
 int rt_render_device(RtScene* scene, const RtRenderParams* params, float* d_out_rgb, void* cuda_stream, RtStats* out_stats) {
     if (!scene || !params || !d_out_rgb) return fail(RT_EINVAL, "NULL argument");
-    return guarded([&] { return render_core(*scene, *params, 0, 1, d_out_rgb, true, (cudaStream_t)cuda_stream, out_stats); });
+    return guarded([&] { return render_core(*scene, *params, 0, 1, d_out_rgb, true, nullptr, (cudaStream_t)cuda_stream, out_stats); });
+}
+
+int rt_render_moments_device(RtScene* scene, const RtRenderParams* params, float* d_out_rgb, float* d_out_sumsq, void* cuda_stream,
+                             RtStats* out_stats) {
+    if (!scene || !params || !d_out_rgb || !d_out_sumsq) return fail(RT_EINVAL, "NULL argument");
+    return guarded([&] { return render_core(*scene, *params, 0, 1, d_out_rgb, true, d_out_sumsq, (cudaStream_t)cuda_stream, out_stats); });
 }
 
 int rt_render(RtScene* scene, const RtRenderParams* params, float* out_rgb, RtStats* out_stats) {
     if (!scene || !params || !out_rgb) return fail(RT_EINVAL, "NULL argument");
     if (params->width < 2 || params->height < 2) return fail(RT_EINVAL, "image must be at least 2x2");
     CU(cudaSetDevice(scene->device));
-    const size_t n = (size_t)params->width * params->height * 3;
-    DevBuf<float> film;  // 25 MB at 1080p: cheap next to the render; the big buffers live in the per-device workspace
-    CU(film.alloc(n));
-    int rc = guarded([&] { return render_core(*scene, *params, 0, 1, film.p, true, nullptr, out_stats); });
-    if (rc) return rc;
-    CU(cudaMemcpy(out_rgb, film.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return guarded([&]() -> int {
+        const size_t n = (size_t)params->width * params->height * 3;
+        const Options O = options_snapshot();
+        RenderPlan pl;
+        int rc = make_plan(*scene, O, *params, 0, 1, pl);
+        if (rc) return rc;
+        Workspace& ws = workspace_of(scene->device);
+        std::lock_guard<std::mutex> ws_lock(ws.mu);
+        if (ws.film.n < n) {  // the film lives in the per-device workspace: no cudaMalloc / cudaFree per call
+            if (ws.film.alloc(n) != cudaSuccess) return fail(RT_ENOMEM, "film buffer");
+        }
+        rc = render_locked(*scene, ws, O, pl, ws.film.p, true, nullptr, true, nullptr, out_stats);
+        if (rc) return rc;
+        CU(cudaMemcpy(out_rgb, ws.film.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+        return RT_OK;
+    });
+}
+
+// render() on several GPUs of one box from ONE call.  The reference splits the SAMPLES over its worker threads and
+// averages their planes (rendering.rs:161-210, 222-252); here the T lanes are dealt round-robin to the GPUs (lane id % n == g), one
+// host thread drives each GPU, and the film combine is k_merge_peers: a fixed-order reduce over NVLink peer memory fused with
+// finalize, so the returned film has the same bits for every n (including n = 1 and rt_render).
+static int enable_peers(const std::vector<int>& devs) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, bool> done;
+    std::lock_guard<std::mutex> lk(mu);
+    for (int a : devs)
+        for (int b : devs) {
+            if (a == b || done.count({a, b})) continue;
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, a, b));
+            if (!can) return fail(RT_EUNSUPPORTED, "rt_render_multi needs peer access between the GPUs (NVLink / NVSwitch)");
+            CU(cudaSetDevice(a));
+            cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) return fail(RT_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            done[{a, b}] = true;
+        }
     return RT_OK;
+}
+
+static int render_multi_impl(RtScene* const* scenes, int n, const RtRenderParams& P, float* out_rgb, float* const* d_out_rgb, RtStats* out_stats) {
+    if (n < 1 || n > RT_MAX_GPUS) return fail(RT_EINVAL, "n_scenes must be 1..16");
+    std::vector<int> devs(n);
+    for (int g = 0; g < n; ++g) {
+        if (!scenes[g]) return fail(RT_EINVAL, "scene is NULL");
+        devs[g] = scenes[g]->device;
+        for (int h = 0; h < g; ++h)
+            if (devs[h] == devs[g]) return fail(RT_EINVAL, "rt_render_multi: every scene must live on a different GPU");
+    }
+    const Options O = options_snapshot();
+    std::vector<RenderPlan> plans(n);
+    for (int g = 0; g < n; ++g) {
+        int rc = make_plan(*scenes[g], O, P, (uint32_t)g, (uint32_t)n, plans[g]);
+        if (rc) return rc;
+    }
+    int rc = enable_peers(devs);
+    if (rc) return rc;
+    // lock every involved workspace (ascending device order: no deadlock with a concurrent rt_render_multi) until the merge is done
+    std::vector<int> order(n);
+    for (int g = 0; g < n; ++g) order[g] = g;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return devs[a] < devs[b]; });
+    std::vector<Workspace*> wss(n);
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (int g : order) {
+        wss[g] = &workspace_of(devs[g]);
+        locks.emplace_back(wss[g]->mu);
+    }
+    const size_t npix = plans[0].npix;
+    std::vector<int> rcs(n, RT_OK);
+    std::vector<std::string> errs(n);
+    std::vector<RtStats> stats(n);
+    auto run_all = [&](auto&& fn) {
+        std::vector<std::thread> th;
+        for (int g = 1; g < n; ++g) th.emplace_back([&, g] { rcs[g] = guarded([&] { return fn(g); }); errs[g] = g_err; });
+        rcs[0] = guarded([&] { return fn(0); });
+        errs[0] = g_err;
+        for (auto& t : th) t.join();
+        for (int g = 0; g < n; ++g)
+            if (rcs[g]) return fail(rcs[g], "GPU " + std::to_string(devs[g]) + ": " + errs[g]);
+        return (int)RT_OK;
+    };
+    // phase 1: every GPU renders its lanes into its own workspace (per-lane sums stay in HBM)
+    rc = run_all([&](int g) -> int {
+        int r = render_locked(*scenes[g], *wss[g], O, plans[g], nullptr, false, nullptr, false, nullptr, &stats[g]);
+        if (r) return r;
+        if (wss[g]->film.n < npix * 3 && wss[g]->film.alloc(npix * 3) != cudaSuccess) return fail(RT_ENOMEM, "film buffer");
+        return RT_OK;
+    });
+    if (rc) return rc;
+    // phase 2: GPU g merges pixel slice g from all ranks' lane sums (peer loads) and stores it (host copy, or peer stores into every film)
+    PeerPlanes PP{};
+    PP.n_ranks = (uint32_t)n;
+    for (int g = 0; g < n; ++g) PP.acc[g] = plans[g].n_local ? wss[g]->acc.p : nullptr;
+    std::vector<float> merge_ms(n, 0.0f);
+    rc = run_all([&](int g) -> int {
+        CU(cudaSetDevice(devs[g]));
+        Workspace& ws = *wss[g];
+        const uint32_t p0 = (uint32_t)(npix * (size_t)g / n), p1 = (uint32_t)(npix * (size_t)(g + 1) / n);
+        PeerPlanes pp = PP;
+        if (d_out_rgb) { pp.n_out = (uint32_t)n; for (int h = 0; h < n; ++h) pp.out[h] = d_out_rgb[h]; }
+        else { pp.n_out = 1; pp.out[0] = ws.film.p; }
+        cudaStream_t st = ws.pipe_stream[0];
+        CU(cudaEventRecord(ws.ev0, st));
+        if (p1 > p0) {
+            const int grid = (int)std::min<size_t>(((size_t)(p1 - p0) + 255) / 256, (size_t)scenes[g]->sm_count * 8);
+            k_merge_peers<<<grid, 256, 0, st>>>(pp, plans[g].R, p0, p1, 1.0f / (float)plans[g].n_tasks);
+            CU(cudaGetLastError());
+            if (out_rgb) CU(cudaMemcpyAsync(out_rgb + 3 * (size_t)p0, ws.film.p + 3 * (size_t)p0, (size_t)(p1 - p0) * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaEventRecord(ws.ev1, st));
+        CU(cudaEventSynchronize(ws.ev1));
+        CU(cudaEventElapsedTime(&merge_ms[g], ws.ev0, ws.ev1));
+        return RT_OK;
+    });
+    if (rc) return rc;
+    if (out_stats)
+        for (int g = 0; g < n; ++g) {
+            out_stats[g] = stats[g];
+            out_stats[g].merge_ms = merge_ms[g];
+            out_stats[g].kernel_launches += 1;
+        }
+    return RT_OK;
+}
+
+int rt_render_multi(RtScene* const* scenes, int n_scenes, const RtRenderParams* params, float* out_rgb, RtStats* out_stats) {
+    if (!scenes || !params || !out_rgb) return fail(RT_EINVAL, "NULL argument");
+    return guarded([&] { return render_multi_impl(scenes, n_scenes, *params, out_rgb, nullptr, out_stats); });
+}
+
+int rt_render_multi_device(RtScene* const* scenes, int n_scenes, const RtRenderParams* params, float* const* d_out_rgb, RtStats* out_stats) {
+    if (!scenes || !params || !d_out_rgb) return fail(RT_EINVAL, "NULL argument");
+    for (int g = 0; g < n_scenes; ++g)
+        if (!d_out_rgb[g]) return fail(RT_EINVAL, "NULL film pointer");
+    return guarded([&] { return render_multi_impl(scenes, n_scenes, *params, nullptr, d_out_rgb, out_stats); });
 }
 
 int rt_film_scale_device(float* d_rgb, uint64_t n_floats, float multiplier, void* cuda_stream) {

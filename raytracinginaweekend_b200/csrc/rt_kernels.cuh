@@ -22,18 +22,22 @@ struct Counters {
     unsigned long long rounds, busy_lanes, tail_rounds, tail_busy_lanes;  // COUNT: warp rounds / busy lanes, overall and after the queue ran dry
     unsigned long long redo_total;     // row f4 (COUNT variant): rays the fast traversal could not prove -> reference traversal
     uint32_t max_sp, pad2;             // COUNT variant: deepest traversal stack use of any ray
+    unsigned long long hist[24];       // COUNT variant: rays by floor(log2(rounds the ray took)) — the per-launch tail
 };
 
 struct RenderDev {
-    float4* A[2];   // origin.xyz, bits(slot)            slot = local_lane * npix + pixel
+    float4* A[2];   // origin.xyz, bits(slot)            slot = track * npix + pixel
     float4* B[2];   // direction.xyz, bits(sample k within the lane)
     float4* C[2];   // throughput.rgb, primary direction.y (Q6)
-    int32_t* D[2];  // remaining depth
+    int2* D[2];     // remaining depth, local lane m the path belongs to
     float* Tm[2];   // Ray::time of the path (camera.rs:185-190); NULL when the scene has no Animation leaf
     uint2* hits;    // (child ref of closest primitive | RT_NO_HIT, bits(t)) per queue position
-    float4* acc;    // [n_local_lanes * npix] running per-lane sums (exclusive owner: the slot's single live path)
+    float4* acc;    // [n_local_lanes * npix] running per-lane sums (rgb) + sum of r^2+g^2+b^2 per sample (w);
+                    // exclusive owner: the single live path of the track that currently renders that lane
     Counters* ctr;
     uint32_t cap;            // queue capacity = number of path slots of THIS pipeline
+    uint32_t n_tracks;       // paths in flight per pixel on this rank: track j renders local lanes j, j + n_tracks, ... one after
+                             // the other (a lane's samples stay sequential, so every per-lane sum keeps the reference's order)
     uint32_t* iter_log;      // optional [max_iters]: live paths of each iteration (debug / per-launch accounting)
     uint32_t iter;           // iteration index of this launch (only used with iter_log)
     uint32_t pipe, n_pipes;  // rank-local lanes are dealt round-robin to n_pipes independent wavefront pipelines (streams)
@@ -78,11 +82,11 @@ __device__ __forceinline__ void generate_path(const SceneDev& S, const RenderDev
 }
 
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R) {
-    const uint32_t n_slots = R.cap;  // this pipeline's lanes: rank-local lane = pipe + n_pipes * m
+    const uint32_t n_slots = R.cap;  // this pipeline's tracks: track = pipe + n_pipes * i; a track starts with local lane m = track
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_slots; j += gridDim.x * blockDim.x) {
-        const uint32_t pixel = j % R.npix, local_lane = R.pipe + R.n_pipes * (j / R.npix);
-        const uint32_t slot = local_lane * R.npix + pixel;  // accumulator index, unique across pipelines
-        const uint32_t lane_id = R.lane_first + local_lane * R.lane_stride;
+        const uint32_t pixel = j % R.npix, track = R.pipe + R.n_pipes * (j / R.npix);
+        const uint32_t slot = track * R.npix + pixel;  // unique across pipelines
+        const uint32_t lane_id = R.lane_first + track * R.lane_stride;
         float3 o, d;
         float time;
         generate_path(S, R, pixel, lane_id, 0u, o, d, time);
@@ -91,8 +95,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
         const uint32_t miss = root_gate(S, o, d, 0.001f, __int_as_float(0x7f800000), R.ref_only != 0u) ? 0u : RT_ROOT_MISS;
         R.B[0][j] = make_float4(d.x, d.y, d.z, __uint_as_float(miss));
         R.C[0][j] = make_float4(1.0f, 1.0f, 1.0f, d.y);
-        R.D[0][j] = R.max_depth;
-        R.acc[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        R.D[0][j] = make_int2(R.max_depth, (int)track);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         R.ctr->nb[0] = n_slots; R.ctr->nn[0] = 0;
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
         R.ctr->exact_steps = 0;
         R.ctr->rounds = 0; R.ctr->busy_lanes = 0; R.ctr->tail_rounds = 0; R.ctr->tail_busy_lanes = 0;
         R.ctr->redo_total = 0; R.ctr->max_sp = 0;
+        for (int h = 0; h < 24; ++h) R.ctr->hist[h] = 0;
     }
 }
 
@@ -116,10 +120,10 @@ struct ExtendKey {
     int q;
     uint32_t pos;
     __device__ __forceinline__ VolKey operator()() const {
-        const uint32_t slot = __float_as_uint(R->A[q][pos].w), k = __float_as_uint(R->B[q][pos].w) & ~RT_ROOT_MISS;
-        const int32_t depth = R->D[q][pos];
-        const uint32_t pixel = slot % R->npix, lane_id = R->lane_first + (slot / R->npix) * R->lane_stride;
-        return VolKey{R->seed0, R->seed1, pixel, k * R->n_tasks + lane_id, 1u + (uint32_t)(R->max_depth - depth)};
+        const uint32_t slot = __float_as_uint(__ldcg(&R->A[q][pos].w)), k = __float_as_uint(__ldcg(&R->B[q][pos].w)) & ~RT_ROOT_MISS;
+        const int2 dm = __ldcg(&R->D[q][pos]);
+        const uint32_t pixel = slot % R->npix, lane_id = R->lane_first + (uint32_t)dm.y * R->lane_stride;
+        return VolKey{R->seed0, R->seed1, pixel, k * R->n_tasks + lane_id, 1u + (uint32_t)(R->max_depth - dm.x)};
     }
 };
 // rt_trace: keyed by the ray index, seed 0, block 0
@@ -156,6 +160,7 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
     uint32_t batch_next = 0, batch_end = 0;  // warp-uniform: ray indices [batch_next, batch_end) already claimed by this warp
     uint32_t act_mask = 0;                   // warp-uniform ballot of `active`
     unsigned long long rounds_c = 0, busy_c = 0, trounds_c = 0, tbusy_c = 0;
+    uint32_t my_rounds = 0;  // COUNT: scheduling rounds this lane's current ray has been active for
     for (;;) {
         // refill: idle lanes take rays from the warp's claimed batch (one atomic per 32 rays)
         if (act_mask != FULL && !(exhausted && batch_next == batch_end) && (uint32_t)__popc(act_mask) < R.refill_threshold) {
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
                 } else {
                     trav_setup(S, T, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), R.Tm[q] ? R.Tm[q][my_pos] : 0.0f, 0.001f, INF);
                     active = true;
+                    if (COUNT) my_rounds = 0;
                     if (MODE == 3) {
                         if (!fast_eligible(T)) T.dpos |= RT_REFMODE_BIT;  // degenerate or near-axis-parallel direction: reference tree only
                         else trav_setup_fast(S, T);
@@ -200,6 +206,7 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
         const bool do_leaf = n_leaf * R.leaf_weight > ((uint32_t)__popc(act_mask) - n_leaf) * 16u;
         if (active) {
             bool more;
+            if (COUNT) ++my_rounds;
             if constexpr (MODE == 3) {
                 if (T.dpos & RT_REFMODE_BIT) more = trav_round<2, COUNT>(S, T, do_leaf, stk, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
                 else more = trav_round_fast<COUNT>(S, T, do_leaf, stk, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
@@ -216,6 +223,7 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
                 } else {
                     R.hits[my_pos] = make_uint2(T.best, __float_as_uint(T.end));
                     active = false;
+                    if (COUNT) atomicAdd(&R.ctr->hist[min(23, 31 - __clz(max(my_rounds, 1u)))], 1ull);
                 }
             }
         }
@@ -239,6 +247,200 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
             atomicAdd(&R.ctr->tail_rounds, trounds_c); atomicAdd(&R.ctr->tail_busy_lanes, tbusy_c);
         }
     }
+}
+
+// One bounce of ray_color (rendering.rs:25-68) for ONE path whose closest hit is `h`, including the accumulation of a terminated
+// sample and the regeneration of the slot's next sample (next sample of the lane, then the track's next lane).  Shared by the
+// wavefront k_shade and the persistent k_path.  Returns RT_PATH_* flags.
+#define RT_PATH_LIVE 1u      // P holds a path to trace next (continuing or fresh)
+#define RT_PATH_FRESH 2u     // ... and it is a new camera path
+#define RT_PATH_FINISHED 4u  // the slot has rendered its last sample (not live)
+struct PathIO {
+    float3 o, d, thr;
+    float dy0, time;
+    uint32_t slot, k, m;
+    int32_t depth;
+};
+__device__ __forceinline__ uint32_t shade_path(const SceneDev& S, const RenderDev& R, PathIO& P, const uint2 h) {
+    float3 o = P.o, d = P.d, thr = P.thr;
+    float dy0 = P.dy0, time = P.time;
+    const uint32_t slot = P.slot;
+    uint32_t k = P.k, m = P.m;
+    int32_t depth = P.depth;
+    bool live = false, fresh = false;
+    uint32_t new_paths = 0;
+    const uint32_t pixel = slot % R.npix;
+    uint32_t lane_id = R.lane_first + m * R.lane_stride;
+    const float t = __uint_as_float(h.y);
+    float3 radiance = f3(0.0f, 0.0f, 0.0f);
+    bool terminated = true;
+    // background_color.rs:9-19, sampled with the PRIMARY ray (Q6)
+    float3 bgc;
+    if (S.bg_is_sky) {
+        float tt = 0.5f * (dy0 + 1.0f);
+        float omt = 1.0f - tt;
+        bgc = f3(1.0f * omt + 0.5f * tt, 1.0f * omt + 0.7f * tt, 1.0f * omt + 1.0f * tt);
+    } else {
+        bgc = f3(S.bg[0], S.bg[1], S.bg[2]);
+    }
+    if (R.mode == 1u) {  // RenderMode::Normals (rendering.rs:108-116)
+        if (h.x != RT_NO_HIT) {
+            Interaction hi = make_interaction(S, h.x, t, o, d, time, false);
+            radiance = f3((hi.normal.x + 1.0f) * 0.5f, (hi.normal.y + 1.0f) * 0.5f, (hi.normal.z + 1.0f) * 0.5f);
+        } else {
+            radiance = bgc;
+        }
+    } else if (h.x == RT_NO_HIT) {
+        radiance = f3(0.0f + thr.x * bgc.x, 0.0f + thr.y * bgc.y, 0.0f + thr.z * bgc.z);  // rendering.rs:66-68
+    } else if (depth <= 1) {
+        radiance = f3(0.0f, 0.0f, 0.0f);  // Q7, rendering.rs:26-27
+    } else {
+        Interaction hi = make_interaction(S, h.x, t, o, d, time, false);
+        const MaterialDev m = S.materials[hi.material];
+        const uint32_t s_global = k * R.n_tasks + lane_id;
+        const uint4 rnd = philox4x32_10(R.seed0, R.seed1, pixel, s_global, 1u + (uint32_t)(R.max_depth - depth), 0u);
+        float3 att = f3(1.0f, 1.0f, 1.0f), ndir = f3(0, 0, 1);
+        float prob = 1.0f;
+        bool scattered = false;
+        float3 emitted = f3(0.0f, 0.0f, 0.0f);
+        // texture coordinates are only needed by image textures: sphere uv costs acos+atan2
+        float tu = hi.u, tv = hi.v;
+        if (m.kind != 2u && ((h.x >> RT_REF_KIND_SHIFT) & 3u) == 0u && texture_needs_uv(S, m.texture)) {
+            const Interaction hu = make_interaction(S, h.x, t, o, d, time, true);  // sphere uv costs acos + atan2: only on demand
+            tu = hu.u; tv = hu.v;
+        }
+        if (m.kind == 0u) {  // Lambert, material.rs:59-63 + rendering.rs:35-51
+            att = texture_sample(S, m.texture, tu, tv, hi.position);
+            const float3 nrm = hi.normal;
+            const float PI = 3.14159265358979323846f;
+            float pdf;
+            if (S.has_light) {  // sample_final_scattering_distribution, rendering.rs:73-86
+                int p0, p1, pn;
+                rect_axes(S.light_plane, p0, p1, pn);
+                if (u01(rnd.x) < 0.5f) {  // gen_bool(0.5) -> RectGeometry::generate, rect_geometry.rs:60-67
+                    float e0 = S.light_r0lo + u01(rnd.y) * (S.light_r0hi - S.light_r0lo);
+                    float e1 = S.light_r1lo + u01(rnd.z) * (S.light_r1hi - S.light_r1lo);
+                    float ex = p0 == 0 ? e0 : (p1 == 0 ? e1 : S.light_dist);
+                    float ey = p0 == 1 ? e0 : (p1 == 1 ? e1 : S.light_dist);
+                    float ez = p0 == 2 ? e0 : (p1 == 2 ? e1 : S.light_dist);
+                    ndir = unit3(sub3(f3(ex, ey, ez), hi.position));
+                } else {
+                    float3 sph = sample_unit_sphere(u01(rnd.y), u01(rnd.z));
+                    float3 v = add3(nrm, sph);
+                    float l2 = dot3(v, v);
+                    ndir = l2 > 1e-8f ? div3(v, sqrtf(l2)) : nrm;  // unit_or_else, vec3.rs:223-230
+                }
+                // RectGeometry::value, rect_geometry.rs:68-85
+                float lv = 0.0f, lt;
+                if (rect_t(S.light_plane, S.light_dist, S.light_r0lo, S.light_r0hi, S.light_r1lo, S.light_r1hi,
+                           hi.position, ndir, 0.001f, __int_as_float(0x7f800000), lt)) {
+                    float area = (S.light_r0hi - S.light_r0lo) * (S.light_r1hi - S.light_r1lo);
+                    float cosine = fabsf(comp3(ndir, pn));
+                    lv = (lt * lt) / (cosine * area);
+                }
+                pdf = 0.5f * lv + 0.5f * (fmaxf(dot3(nrm, ndir), 0.0f) / PI);
+            } else {
+                float3 sph = sample_unit_sphere(u01(rnd.x), u01(rnd.y));
+                float3 v = add3(nrm, sph);
+                float l2 = dot3(v, v);
+                ndir = l2 > 1e-8f ? div3(v, sqrtf(l2)) : nrm;
+                pdf = fmaxf(dot3(nrm, ndir), 0.0f) / PI;
+            }
+            float scattering_pdf = fmaxf(dot3(nrm, ndir), 0.0f) / PI;  // material.rs:123-127
+            prob = scattering_pdf / pdf;                                // Q9: 0/0 -> NaN
+            scattered = true;
+        } else if (m.kind == 1u) {  // Metal, material.rs:65-79
+            float3 fuzz_dir = f3(0.0f, 0.0f, 0.0f);
+            if (m.param > 0.0f) {
+                float3 sph = sample_unit_sphere(u01(rnd.x), u01(rnd.y));
+                fuzz_dir = mul3(mul3(sph, cbrt_unit(u01(rnd.z))), m.param);
+            }
+            float3 refl = sub3(d, mul3(hi.normal, 2.0f * dot3(d, hi.normal)));  // reflect, vec3.rs:232-234
+            float3 dir = add3(refl, fuzz_dir);
+            if (dot3(dir, hi.normal) > 0.0f) {
+                ndir = unit3(dir);
+                att = texture_sample(S, m.texture, tu, tv, hi.position);
+                scattered = true;
+            }
+        } else if (m.kind == 2u) {  // Dielectric, material.rs:80-105
+            float ratio = hi.front_face ? 1.0f / m.param : m.param;
+            float cos_theta = fminf(dot3(neg3(d), hi.normal), 1.0f);
+            float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+            bool cannot_refract = ratio * sin_theta > 1.0f;
+            bool do_reflect = cannot_refract;
+            if (!do_reflect) {
+                float r0 = (1.0f - ratio) / (1.0f + ratio);
+                float rs = r0 * r0;
+                float x = 1.0f - cos_theta;
+                float x2 = x * x;
+                float x4 = x2 * x2;
+                float refl = rs + (1.0f - rs) * (x * x4);  // powi(5)
+                do_reflect = refl > u01(rnd.x);
+            }
+            float3 dir;
+            if (do_reflect) {
+                dir = sub3(d, mul3(hi.normal, 2.0f * dot3(d, hi.normal)));
+            } else {  // refract, vec3.rs:235-240
+                float ct = fminf(dot3(neg3(d), hi.normal), 1.0f);
+                float3 perp = mul3(add3(d, mul3(hi.normal, ct)), ratio);
+                float3 par = mul3(hi.normal, -sqrtf(fabsf(1.0f - dot3(perp, perp))));
+                dir = add3(perp, par);
+            }
+            ndir = unit3(dir);
+            scattered = true;
+        } else if (m.kind == 4u) {  // Isotropic (volume phase function), material.rs:106-111: Mirror(UnitSphere), not normalised
+            ndir = sample_unit_sphere(u01(rnd.x), u01(rnd.y));
+            att = texture_sample(S, m.texture, tu, tv, hi.position);
+            scattered = true;
+        } else {  // DiffuseLight: never scatters, emits from both faces (Q14), material.rs:132-137
+            emitted = texture_sample(S, m.texture, tu, tv, hi.position);
+        }
+        if (scattered) {
+            // rendering.rs:54-61.  accum_emitted stays 0 unless the throughput is non-finite, in which case
+            // it turns NaN; folding that into the throughput (inf -> NaN) keeps every outcome identical.
+            float3 nt = f3((thr.x * att.x) * prob, (thr.y * att.y) * prob, (thr.z * att.z) * prob);
+            const float qnan = __int_as_float(0x7fc00000);
+            if (isinf(thr.x)) nt.x = qnan;
+            if (isinf(thr.y)) nt.y = qnan;
+            if (isinf(thr.z)) nt.z = qnan;
+            thr = nt;
+            o = hi.position;
+            d = ndir;
+            depth -= 1;
+            terminated = false;
+            live = true;
+        } else {
+            radiance = f3(0.0f + thr.x * emitted.x, 0.0f + thr.y * emitted.y, 0.0f + thr.z * emitted.z);  // :62-64
+        }
+    }
+    if (terminated) {
+        float4* ap = R.acc + ((size_t)m * R.npix + pixel);
+        float4 s = __ldcg(ap);  // sequential per-pixel sum in sample order (rendering.rs:172-178); L2 access: a slot is shaded by different SMs over time
+        s.x += radiance.x; s.y += radiance.y; s.z += radiance.z;
+        s.w += radiance.x * radiance.x + radiance.y * radiance.y + radiance.z * radiance.z;  // second moment (RMSE bound)
+        __stcg(ap, s);
+        // regenerate in place: next sample of this (pixel, lane), then the track's next lane
+        bool more = true;
+        if (k + 1u < lane_samples(R, lane_id)) {
+            k += 1u;
+        } else {
+            m += R.n_tracks; k = 0u;
+            lane_id = R.lane_first + m * R.lane_stride;
+            more = m < R.n_local_lanes;
+        }
+        if (more) {
+            generate_path(S, R, pixel, lane_id, k, o, d, time);
+            thr = f3(1.0f, 1.0f, 1.0f);
+            dy0 = d.y;
+            depth = R.max_depth;
+            live = true;
+            fresh = true;
+            new_paths += 1u;
+        }
+    }
+    P.o = o; P.d = d; P.thr = thr; P.dy0 = dy0; P.time = time; P.k = k; P.m = m; P.depth = depth;
+    (void)new_paths;
+    return (live ? RT_PATH_LIVE : 0u) | (fresh ? RT_PATH_FRESH : 0u) | ((terminated && !live) ? RT_PATH_FINISHED : 0u);
 }
 
 // One bounce of ray_color for every live path of queue `q`; survivors (and regenerated paths) are compacted
@@ -268,176 +470,24 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
         bool live = false, fresh = false;
         float3 o = f3(0, 0, 0), d = f3(0, 0, 1), thr = f3(1, 1, 1);
         float dy0 = 0.0f, time = 0.0f;
-        uint32_t slot = 0, k = 0;
+        uint32_t slot = 0, k = 0, m = 0;
         int32_t depth = 0;
         if (i < n) {
             float4 a = R.A[q][ipos], b = R.B[q][ipos], c = R.C[q][ipos];
-            depth = R.D[q][ipos];
+            const int2 dm = R.D[q][ipos];
+            depth = dm.x; m = (uint32_t)dm.y;
             time = R.Tm[q] ? R.Tm[q][ipos] : 0.0f;
             uint2 h = R.hits[ipos];
             o = f3(a.x, a.y, a.z); d = f3(b.x, b.y, b.z); thr = f3(c.x, c.y, c.z);
             dy0 = c.w;
             slot = __float_as_uint(a.w);
             k = __float_as_uint(b.w) & ~RT_ROOT_MISS;
-            const uint32_t pixel = slot % R.npix, local_lane = slot / R.npix;
-            const uint32_t lane_id = R.lane_first + local_lane * R.lane_stride;
-            const float t = __uint_as_float(h.y);
-            float3 radiance = f3(0.0f, 0.0f, 0.0f);
-            bool terminated = true;
-            // background_color.rs:9-19, sampled with the PRIMARY ray (Q6)
-            float3 bgc;
-            if (S.bg_is_sky) {
-                float tt = 0.5f * (dy0 + 1.0f);
-                float omt = 1.0f - tt;
-                bgc = f3(1.0f * omt + 0.5f * tt, 1.0f * omt + 0.7f * tt, 1.0f * omt + 1.0f * tt);
-            } else {
-                bgc = f3(S.bg[0], S.bg[1], S.bg[2]);
-            }
-            if (R.mode == 1u) {  // RenderMode::Normals (rendering.rs:108-116)
-                if (h.x != RT_NO_HIT) {
-                    Interaction hi = make_interaction(S, h.x, t, o, d, time, false);
-                    radiance = f3((hi.normal.x + 1.0f) * 0.5f, (hi.normal.y + 1.0f) * 0.5f, (hi.normal.z + 1.0f) * 0.5f);
-                } else {
-                    radiance = bgc;
-                }
-            } else if (h.x == RT_NO_HIT) {
-                radiance = f3(0.0f + thr.x * bgc.x, 0.0f + thr.y * bgc.y, 0.0f + thr.z * bgc.z);  // rendering.rs:66-68
-            } else if (depth <= 1) {
-                radiance = f3(0.0f, 0.0f, 0.0f);  // Q7, rendering.rs:26-27
-            } else {
-                Interaction hi = make_interaction(S, h.x, t, o, d, time, false);
-                const MaterialDev m = S.materials[hi.material];
-                const uint32_t s_global = k * R.n_tasks + lane_id;
-                const uint4 rnd = philox4x32_10(R.seed0, R.seed1, pixel, s_global, 1u + (uint32_t)(R.max_depth - depth), 0u);
-                float3 att = f3(1.0f, 1.0f, 1.0f), ndir = f3(0, 0, 1);
-                float prob = 1.0f;
-                bool scattered = false;
-                float3 emitted = f3(0.0f, 0.0f, 0.0f);
-                // texture coordinates are only needed by image textures: sphere uv costs acos+atan2
-                float tu = hi.u, tv = hi.v;
-                if (m.kind != 2u && ((h.x >> RT_REF_KIND_SHIFT) & 3u) == 0u && texture_needs_uv(S, m.texture)) {
-                    const Interaction hu = make_interaction(S, h.x, t, o, d, time, true);  // sphere uv costs acos + atan2: only on demand
-                    tu = hu.u; tv = hu.v;
-                }
-                if (m.kind == 0u) {  // Lambert, material.rs:59-63 + rendering.rs:35-51
-                    att = texture_sample(S, m.texture, tu, tv, hi.position);
-                    const float3 nrm = hi.normal;
-                    const float PI = 3.14159265358979323846f;
-                    float pdf;
-                    if (S.has_light) {  // sample_final_scattering_distribution, rendering.rs:73-86
-                        int p0, p1, pn;
-                        rect_axes(S.light_plane, p0, p1, pn);
-                        if (u01(rnd.x) < 0.5f) {  // gen_bool(0.5) -> RectGeometry::generate, rect_geometry.rs:60-67
-                            float e0 = S.light_r0lo + u01(rnd.y) * (S.light_r0hi - S.light_r0lo);
-                            float e1 = S.light_r1lo + u01(rnd.z) * (S.light_r1hi - S.light_r1lo);
-                            float ex = p0 == 0 ? e0 : (p1 == 0 ? e1 : S.light_dist);
-                            float ey = p0 == 1 ? e0 : (p1 == 1 ? e1 : S.light_dist);
-                            float ez = p0 == 2 ? e0 : (p1 == 2 ? e1 : S.light_dist);
-                            ndir = unit3(sub3(f3(ex, ey, ez), hi.position));
-                        } else {
-                            float3 sph = sample_unit_sphere(u01(rnd.y), u01(rnd.z));
-                            float3 v = add3(nrm, sph);
-                            float l2 = dot3(v, v);
-                            ndir = l2 > 1e-8f ? div3(v, sqrtf(l2)) : nrm;  // unit_or_else, vec3.rs:223-230
-                        }
-                        // RectGeometry::value, rect_geometry.rs:68-85
-                        float lv = 0.0f, lt;
-                        if (rect_t(S.light_plane, S.light_dist, S.light_r0lo, S.light_r0hi, S.light_r1lo, S.light_r1hi,
-                                   hi.position, ndir, 0.001f, __int_as_float(0x7f800000), lt)) {
-                            float area = (S.light_r0hi - S.light_r0lo) * (S.light_r1hi - S.light_r1lo);
-                            float cosine = fabsf(comp3(ndir, pn));
-                            lv = (lt * lt) / (cosine * area);
-                        }
-                        pdf = 0.5f * lv + 0.5f * (fmaxf(dot3(nrm, ndir), 0.0f) / PI);
-                    } else {
-                        float3 sph = sample_unit_sphere(u01(rnd.x), u01(rnd.y));
-                        float3 v = add3(nrm, sph);
-                        float l2 = dot3(v, v);
-                        ndir = l2 > 1e-8f ? div3(v, sqrtf(l2)) : nrm;
-                        pdf = fmaxf(dot3(nrm, ndir), 0.0f) / PI;
-                    }
-                    float scattering_pdf = fmaxf(dot3(nrm, ndir), 0.0f) / PI;  // material.rs:123-127
-                    prob = scattering_pdf / pdf;                                // Q9: 0/0 -> NaN
-                    scattered = true;
-                } else if (m.kind == 1u) {  // Metal, material.rs:65-79
-                    float3 fuzz_dir = f3(0.0f, 0.0f, 0.0f);
-                    if (m.param > 0.0f) {
-                        float3 sph = sample_unit_sphere(u01(rnd.x), u01(rnd.y));
-                        fuzz_dir = mul3(mul3(sph, cbrt_unit(u01(rnd.z))), m.param);
-                    }
-                    float3 refl = sub3(d, mul3(hi.normal, 2.0f * dot3(d, hi.normal)));  // reflect, vec3.rs:232-234
-                    float3 dir = add3(refl, fuzz_dir);
-                    if (dot3(dir, hi.normal) > 0.0f) {
-                        ndir = unit3(dir);
-                        att = texture_sample(S, m.texture, tu, tv, hi.position);
-                        scattered = true;
-                    }
-                } else if (m.kind == 2u) {  // Dielectric, material.rs:80-105
-                    float ratio = hi.front_face ? 1.0f / m.param : m.param;
-                    float cos_theta = fminf(dot3(neg3(d), hi.normal), 1.0f);
-                    float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
-                    bool cannot_refract = ratio * sin_theta > 1.0f;
-                    bool do_reflect = cannot_refract;
-                    if (!do_reflect) {
-                        float r0 = (1.0f - ratio) / (1.0f + ratio);
-                        float rs = r0 * r0;
-                        float x = 1.0f - cos_theta;
-                        float x2 = x * x;
-                        float x4 = x2 * x2;
-                        float refl = rs + (1.0f - rs) * (x * x4);  // powi(5)
-                        do_reflect = refl > u01(rnd.x);
-                    }
-                    float3 dir;
-                    if (do_reflect) {
-                        dir = sub3(d, mul3(hi.normal, 2.0f * dot3(d, hi.normal)));
-                    } else {  // refract, vec3.rs:235-240
-                        float ct = fminf(dot3(neg3(d), hi.normal), 1.0f);
-                        float3 perp = mul3(add3(d, mul3(hi.normal, ct)), ratio);
-                        float3 par = mul3(hi.normal, -sqrtf(fabsf(1.0f - dot3(perp, perp))));
-                        dir = add3(perp, par);
-                    }
-                    ndir = unit3(dir);
-                    scattered = true;
-                } else if (m.kind == 4u) {  // Isotropic (volume phase function), material.rs:106-111: Mirror(UnitSphere), not normalised
-                    ndir = sample_unit_sphere(u01(rnd.x), u01(rnd.y));
-                    att = texture_sample(S, m.texture, tu, tv, hi.position);
-                    scattered = true;
-                } else {  // DiffuseLight: never scatters, emits from both faces (Q14), material.rs:132-137
-                    emitted = texture_sample(S, m.texture, tu, tv, hi.position);
-                }
-                if (scattered) {
-                    // rendering.rs:54-61.  accum_emitted stays 0 unless the throughput is non-finite, in which case
-                    // it turns NaN; folding that into the throughput (inf -> NaN) keeps every outcome identical.
-                    float3 nt = f3((thr.x * att.x) * prob, (thr.y * att.y) * prob, (thr.z * att.z) * prob);
-                    const float qnan = __int_as_float(0x7fc00000);
-                    if (isinf(thr.x)) nt.x = qnan;
-                    if (isinf(thr.y)) nt.y = qnan;
-                    if (isinf(thr.z)) nt.z = qnan;
-                    thr = nt;
-                    o = hi.position;
-                    d = ndir;
-                    depth -= 1;
-                    terminated = false;
-                    live = true;
-                } else {
-                    radiance = f3(0.0f + thr.x * emitted.x, 0.0f + thr.y * emitted.y, 0.0f + thr.z * emitted.z);  // :62-64
-                }
-            }
-            if (terminated) {
-                float4 s = R.acc[slot];  // sequential per-pixel sum in sample order (rendering.rs:172-178)
-                s.x += radiance.x; s.y += radiance.y; s.z += radiance.z;
-                R.acc[slot] = s;
-                if (k + 1u < lane_samples(R, lane_id)) {  // regenerate in place: next sample of this (pixel, lane)
-                    k += 1u;
-                    generate_path(S, R, pixel, lane_id, k, o, d, time);
-                    thr = f3(1.0f, 1.0f, 1.0f);
-                    dy0 = d.y;
-                    depth = R.max_depth;
-                    live = true;
-                    fresh = true;
-                    new_paths += 1u;
-                }
-            }
+            PathIO P;
+            P.o = o; P.d = d; P.thr = thr; P.dy0 = dy0; P.time = time; P.slot = slot; P.k = k; P.m = m; P.depth = depth;
+            const uint32_t fl = shade_path(S, R, P, h);
+            o = P.o; d = P.d; thr = P.thr; dy0 = P.dy0; time = P.time; k = P.k; m = P.m; depth = P.depth;
+            live = (fl & RT_PATH_LIVE) != 0u; fresh = (fl & RT_PATH_FRESH) != 0u;
+            if (fresh) new_paths += 1u;
         }
         // warp-ballot compaction into the other queue: continuing paths from the bottom, fresh camera paths from the
         // top, so warps of the next extend hold either coherent primary rays or bounce rays, not a mix
@@ -458,7 +508,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
                 R.A[q ^ 1][pos] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
                 R.B[q ^ 1][pos] = make_float4(d.x, d.y, d.z, __uint_as_float(k | miss));
                 R.C[q ^ 1][pos] = make_float4(thr.x, thr.y, thr.z, dy0);
-                R.D[q ^ 1][pos] = depth;
+                R.D[q ^ 1][pos] = make_int2(depth, (int)m);
                 if (R.Tm[q ^ 1]) R.Tm[q ^ 1][pos] = time;
             }
         }
@@ -468,11 +518,13 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev 
     if (lane == 0 && new_paths) atomicAdd(&R.ctr->paths, (unsigned long long)new_paths);
 }
 
+
 // film[p] = sum over this rank's lanes, in merge_planes order (last plane first), of lane_sum / lane_samples; times `scale`.
 __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ RenderDev R, float* __restrict__ out_rgb, float scale,
-                                                  int apply_scale) {
+                                                  int apply_scale, float* __restrict__ out_sumsq) {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < R.npix; p += gridDim.x * blockDim.x) {
         float3 sum = f3(0, 0, 0);
+        float sq = 0.0f;
         bool first = true;
         // order: lane T'-1 (if local), then ascending
         for (uint32_t step = 0; step <= R.n_local_lanes; ++step) {
@@ -492,11 +544,43 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ Render
             float3 plane = f3(a.x / ns, a.y / ns, a.z / ns);  // `.sum::<Color>() / real_samples as f32`
             if (first) { sum = plane; first = false; }
             else sum = add3(sum, plane);
+            sq += a.w;
         }
+        if (out_sumsq) out_sumsq[p] = sq;
         if (apply_scale) sum = mul3(sum, scale);
         out_rgb[3ull * p + 0] = sum.x;
         out_rgb[3ull * p + 1] = sum.y;
         out_rgb[3ull * p + 2] = sum.z;
+    }
+}
+
+// Multi-GPU film combine fused with finalize (rt_render_multi): every rank holds the per-lane sums of ITS lanes (lane id % n_ranks
+// == rank, local index id / n_ranks) in its own HBM; the GPU that owns a pixel slice reads all T' lane sums of those pixels —
+// its own from HBM, the others through NVLink peer loads — and folds them in merge_planes order (last plane first, then
+// ascending; rendering.rs:239-252) with the same arithmetic as k_finalize, so the film is bit-identical for ANY number of GPUs.
+// The result is stored to every output pointer (own film, or all peers' films = the all-gather fused in as peer stores).
+#define RT_MAX_GPUS 16
+struct PeerPlanes {
+    const float4* acc[RT_MAX_GPUS];  // acc[r]: rank r's lane sums, [lanes of r][npix]
+    float* out[RT_MAX_GPUS];         // films to store the merged slice into (width*height*3 floats each)
+    uint32_t n_ranks, n_out;
+};
+__global__ void __launch_bounds__(256) k_merge_peers(const __grid_constant__ PeerPlanes PP, const __grid_constant__ RenderDev R, uint32_t p_begin,
+                                                     uint32_t p_end, float scale) {
+    for (uint32_t p = p_begin + blockIdx.x * blockDim.x + threadIdx.x; p < p_end; p += gridDim.x * blockDim.x) {
+        float3 sum = f3(0, 0, 0);
+        for (uint32_t step = 0; step < R.n_tasks; ++step) {
+            const uint32_t id = step == 0 ? R.n_tasks - 1u : step - 1u;  // lane T'-1 first, then 0 .. T'-2
+            const float ns = (float)lane_samples(R, id);
+            const float4 a = PP.acc[id % PP.n_ranks][(size_t)(id / PP.n_ranks) * R.npix + p];
+            const float3 plane = f3(a.x / ns, a.y / ns, a.z / ns);
+            sum = step == 0 ? plane : add3(sum, plane);
+        }
+        sum = mul3(sum, scale);
+        for (uint32_t o = 0; o < PP.n_out; ++o) {
+            float* out = PP.out[o];
+            out[3ull * p + 0] = sum.x; out[3ull * p + 1] = sum.y; out[3ull * p + 2] = sum.z;
+        }
     }
 }
 

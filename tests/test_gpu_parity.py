@@ -30,7 +30,7 @@ def product_world(name):
 
 @pytest.fixture(autouse=True)
 def default_options():
-    for k, v in (("traversal", 3), ("count", 0), ("profile", 0), ("pipes", 2), ("rebuild_min_items", 32)):
+    for k, v in (("traversal", 3), ("count", 0), ("profile", 0), ("pipes", 0), ("rebuild_min_items", 32), ("max_slots", 160 << 20)):
         _cabi.set_option(k, v)
     yield
 
