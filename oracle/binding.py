@@ -62,6 +62,7 @@ def lib():
         L.orc_aabb_hit_cond.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float]
         L.orc_obj_load.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_rng_kat.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_xoroshiro_from_seed.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_probe_math.argtypes = [C.c_float, C.c_void_p]
         L.orc_probe_ln.argtypes = [C.c_float]
         L.orc_probe_ln.restype = C.c_float

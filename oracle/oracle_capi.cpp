@@ -431,6 +431,10 @@ void orc_rng_kat(uint64_t* u64_out, float* f32_out) {  // first draws of the sce
     TRng r2 = scene_rng();
     for (int i = 0; i < 4; ++i) f32_out[i] = r2.gen_f32();
 }
+void orc_xoroshiro_from_seed(const uint8_t* seed16, uint64_t* out, int n) {  // Xoroshiro128PlusPlus::from_seed + next_u64
+    TRng r = TRng::from_seed_bytes(seed16);
+    for (int i = 0; i < n; ++i) out[i] = r.next_u64();
+}
 void orc_probe_math(float u, float* out3) {  // sincos_2pi / cbrt_unit of the REPLAY samplers
     sincos_2pi(u, &out3[0], &out3[1]);
     out3[2] = cbrt_unit(u);

@@ -4,8 +4,9 @@ The reference gives every worker thread the WHOLE image at spp/T samples and the
 (`split_work_tasks`, `merge_planes`).  Here the T sample lanes are dealt round-robin to the ranks
 (lane id % world_size == rank); each rank's hand-written CUDA path renders its lanes and leaves
    sum over its lanes of (lane sum / lane samples)
-on its GPU; the film is then combined with ONE collective — an NCCL all-reduce(SUM) over NVLink — and scaled
-by 1/T.  The Philox streams are keyed by (pixel, global sample index), so the sample set does not depend
+on its GPU; the film is then combined with ONE collective — an NCCL all-reduce over NVLink whose reduction is a
+pre-multiplied sum, i.e. the 1/T of merge_planes is folded into the collective (`combine_film`).  (Single-process callers
+use rt_render_multi instead: a fixed-order peer-memory reduce fused with finalize, bit-identical for any GPU count.)  The Philox streams are keyed by (pixel, global sample index), so the sample set does not depend
 on the number of ranks.
 """
 from __future__ import annotations
@@ -34,6 +35,20 @@ def lane_samples(thread_count: int, samples_per_pixel: int, lane_id: int) -> int
     return samples_per_pixel // thread_count + (1 if lane_id < samples_per_pixel % thread_count else 0)
 
 
+def combine_film(plane, mult: float, world_size: int, group=None):
+    """The film combine of the multi-process path: ONE NCCL all-reduce whose reduction is a pre-multiplied sum, so the `x 1/T` of
+    merge_planes (rendering.rs:239-252) is folded into the collective (ncclRedOpCreatePreMulSum) — no extra pass over the film.
+    With one rank the library's own scale kernel runs (rt_film_scale_device).  CUDA tensors only: the product path has no CPU code."""
+    import torch.distributed as dist
+    from . import _cabi
+    import torch
+    if world_size > 1:
+        dist.all_reduce(plane, op=dist._make_nccl_premul_sum(float(mult)), group=group)
+    else:
+        _cabi.check(_cabi.lib().rt_film_scale_device(plane.data_ptr(), plane.numel(), float(mult), torch.cuda.current_stream(plane.device).cuda_stream))
+    return plane
+
+
 def render_distributed(world: Optional[World], image_size: Size2i, thread_count: int, samples_per_pixel: int, max_depth: int,
                        render_mode: RenderMode = RenderMode.Default, seed: int = 0x5EED, *, group=None, device=None,
                        plane_fn: Optional[Callable] = None, return_stats: bool = False):
@@ -60,8 +75,11 @@ def render_distributed(world: Optional[World], image_size: Size2i, thread_count:
                                            samples_per_pixel, max_depth, thread_count, seed, int(render_mode), stream)
     else:
         plane = plane_fn(lane_first, lane_stride)
-    if world_size > 1:
-        dist.all_reduce(plane, op=dist.ReduceOp.SUM, group=group)  # the film combine: one collective per render
     mult = np.float32(1.0) / np.float32(n_tasks(thread_count, samples_per_pixel))  # merge_planes multiplier, rendering.rs:240
-    plane.mul_(float(mult))
+    if plane_fn is None:
+        combine_film(plane, float(mult), world_size, group)  # the film combine: one collective per render, scale folded in
+    else:  # tests (CPU tensors, gloo): the same two steps spelled out
+        if world_size > 1:
+            dist.all_reduce(plane, op=dist.ReduceOp.SUM, group=group)
+        plane = plane * float(mult)
     return (plane, stats) if return_stats else plane

@@ -187,6 +187,20 @@ def test_scene_rng_matches_published_xoroshiro128pp(oracle):
     assert [float(x) for x in f] == [((e & 0xFFFFFFFF) >> 8) * 2.0 ** -24 for e in exp]
 
 
+def test_xoroshiro128pp_reference_vector_of_the_crate(oracle):
+    """Oracle pin (iii): the known-answer vector of rand_xoshiro 0.6.0's own unit test (src/xoroshiro128plusplus.rs, `reference`:
+    from_seed([1,0,0,0,0,0,0,0, 2,0,0,0,0,0,0,0]), values "produced with the reference implementation
+    http://xoshiro.di.unimi.it/xoroshiro128plusplus.c") — quoted from the crate, which is not vendored under /root/reference."""
+    expected = [393217, 669327710093319, 1732421326133921491, 11394790081659126983, 9555452776773192676, 3586421180005889563,
+                1691397964866707553, 10735626796753111697, 15216282715349408991, 14247243556711267923]
+    seed = np.array([1, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0], np.uint8)
+    out = np.zeros(10, np.uint64)
+    oracle.lib().orc_xoroshiro_from_seed(oracle._p(seed), oracle._p(out), 10)
+    assert [int(x) for x in out] == expected
+    g = _xoroshiro128pp(1, 2)
+    assert [next(g) for _ in range(10)] == expected
+
+
 def test_philox_known_answers(oracle):
     # Random123 kat_vectors, philox4x32 with 10 rounds
     kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
