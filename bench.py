@@ -93,6 +93,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+            self.proc.wait()
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -472,6 +473,12 @@ def main():
         if n == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(out), flush=True)
+    # leave the device clean: no kernels in flight, the library's workspaces (up to 19 GB) and the flush buffer released
+    from raytracinginaweekend_b200 import _cabi
+    B.torch.cuda.synchronize(B.dev)
+    _cabi.shutdown()
+    B.flush = None
+    B.torch.cuda.empty_cache()
     if n > 1:
         B.dist.barrier()
         B.dist.destroy_process_group()

@@ -257,6 +257,10 @@ int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_o
  * Environment: RT_ITER_LOG=<path> dumps (pipe, iteration, live paths, extend ms, shade ms) of the last render as CSV. */
 int rt_set_option(const char* key, int64_t value);
 
+/* Frees the per-device render workspaces (path-state queues, per-lane accumulators, streams, events) that the library keeps
+ * between renders.  Optional; call it only when no render is in flight.  The next render allocates them again. */
+int rt_shutdown(void);
+
 #ifdef __cplusplus
 }
 #endif

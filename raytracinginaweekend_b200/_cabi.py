@@ -90,7 +90,7 @@ assert MATERIAL_DTYPE.itemsize == C.sizeof(RtMaterial) and TEXTURE_DTYPE.itemsiz
 
 EXPORTED = ["rt_last_error", "rt_device_count", "rt_scene_create", "rt_scene_destroy", "rt_scene_device_bytes", "rt_scene_set_ray_time",
             "rt_trace", "rt_trace_device", "rt_render", "rt_render_device", "rt_render_moments_device", "rt_render_planes_device", "rt_render_multi", "rt_render_multi_device",
-            "rt_film_scale_device", "rt_to_rgb8_gamma2_device", "rt_set_option"]
+            "rt_film_scale_device", "rt_to_rgb8_gamma2_device", "rt_set_option", "rt_shutdown"]
 
 _lib = None
 
@@ -141,6 +141,12 @@ def _p(a):
 
 def set_option(key: str, value: int):
     check(lib().rt_set_option(key.encode(), int(value)))
+
+
+def shutdown():
+    """Release the library's per-device render workspaces (rt_shutdown)."""
+    if _lib is not None:
+        check(_lib.rt_shutdown())
 
 
 def device_count() -> int:

@@ -1361,6 +1361,35 @@ int rt_render_multi_device(RtScene* const* scenes, int n_scenes, const RtRenderP
     return guarded([&] { return render_multi_impl(scenes, n_scenes, *params, nullptr, d_out_rgb, out_stats); });
 }
 
+// Releases every per-device render workspace (queues, accumulators, streams, events).  Optional: a process may simply exit; a
+// long-lived caller (or a benchmark that wants a clean device before it returns) calls this when no render is in flight.
+int rt_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    for (auto& kv : g_ws) {
+        Workspace* w = kv.second;
+        if (!w) continue;
+        std::lock_guard<std::mutex> wl(w->mu);
+        if (cudaSetDevice(kv.first) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaDeviceSynchronize();
+        release_workspace_queues(*w);
+        w->ctr.release(); w->film.release(); w->sumsq.release(); w->iter_log.release();
+        if (w->h_ctr) { cudaFreeHost(w->h_ctr); w->h_ctr = nullptr; }
+        for (int p = 0; p < Workspace::MAX_PIPES; ++p) {
+            if (w->pipe_stream[p]) { cudaStreamDestroy(w->pipe_stream[p]); w->pipe_stream[p] = nullptr; }
+            if (w->join_event[p]) { cudaEventDestroy(w->join_event[p]); w->join_event[p] = nullptr; }
+            for (int b = 0; b < 2; ++b)
+                if (w->poll_event[p][b]) { cudaEventDestroy(w->poll_event[p][b]); w->poll_event[p][b] = nullptr; }
+            for (cudaEvent_t e : w->prof_events[p]) cudaEventDestroy(e);
+            w->prof_events[p].clear();
+        }
+        if (w->fork_event) { cudaEventDestroy(w->fork_event); w->fork_event = nullptr; }
+        if (w->ev0) { cudaEventDestroy(w->ev0); w->ev0 = nullptr; }
+        if (w->ev1) { cudaEventDestroy(w->ev1); w->ev1 = nullptr; }
+        cudaGetLastError();
+    }
+    return RT_OK;
+}
+
 int rt_film_scale_device(float* d_rgb, uint64_t n_floats, float multiplier, void* cuda_stream) {
     if (!d_rgb) return fail(RT_EINVAL, "NULL argument");
     if (n_floats == 0) return RT_OK;

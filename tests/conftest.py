@@ -52,3 +52,11 @@ def oracle_world(oracle):
             _worlds[name] = oracle.OracleWorld.named(name)
         return _worlds[name]
     return get
+
+
+@pytest.fixture(scope="session", autouse=True)
+def release_gpu_workspaces_at_the_end():
+    yield
+    if have_gpu():
+        from raytracinginaweekend_b200 import _cabi
+        _cabi.shutdown()

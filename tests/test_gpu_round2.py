@@ -102,7 +102,8 @@ def mc_gate(gpu, sumsq, ref, n):
     bound = 1.25 * math.sqrt(2.0 * mean_var / n)
     bias = [abs(float((gpu[..., c][ok].astype(np.float64) - ref[..., c][ok]).mean())) for c in range(3)]
     bias_bound = 4.0 * math.sqrt(2.0 * mean_var / (n * ok.sum()))
-    return dict(rmse=rmse, bound=bound, bias=bias, bias_bound=bias_bound, iou=iou, nan_union=int(union), mean_var=mean_var)
+    return dict(rmse=rmse, bound=bound, bias=bias, bias_bound=bias_bound, iou=iou, nan_union=int(union), mean_var=mean_var,
+                nan_gpu=int(nan_g.sum()), nan_ref=int(nan_r.sum()))
 
 
 @pytest.mark.parametrize("name,w,h,spp,T", [("config:c1", 120, 80, 10, 10), ("config:c2", 96, 54, 64, 16), ("config:c3", 64, 64, 256, 16)])
@@ -115,10 +116,11 @@ def test_image_rmse_gate_vs_faithful_reference_render(name, w, h, spp, T, oracle
     g = mc_gate(gpu, sumsq, ref, spp)
     assert g["rmse"] <= g["bound"], g
     assert max(g["bias"]) <= g["bias_bound"] + 1e-4, g
-    # Q9 NaN pixels are themselves random events (a sample whose Lambert draw lands below a non-unit normal): the masks of two
-    # independent renders overlap only statistically, so the IoU criterion applies where the NaN probability per pixel is high
-    if g["nan_union"] > 0.2 * w * h:
-        assert g["iou"] >= 0.5, g
+    # Q9: a NaN pixel is itself a random event (ONE sample whose Lambert draw lands below a non-unit normal poisons the pixel), so
+    # the NaN masks of two independent renders agree only statistically: what must agree is the NaN RATE (SURVEY's 99 % IoU holds
+    # for REPLAY renders, where the masks are identical — test_nan_pixels_match)
+    n_g, n_r = g["nan_gpu"], g["nan_ref"]
+    assert abs(n_g - n_r) <= 4.0 * math.sqrt(max(n_g + n_r, 1)) + 2, g
 
 
 def test_rmse_falls_by_four_with_sixteen_times_the_samples(oracle_world):
