@@ -115,6 +115,7 @@ d0 = tgt - cam; d0 /= np.linalg.norm(d0, axis=1, keepdims=True)
 gen = (np.tile(cam, (NR, 1)), d0)
 for bounce in range(4):
     o, d = gen
+    if len(o) == 0: break
     s0 = [0, 0]; s1 = [0, 0]; no, nd = [], []; mism = 0
     for i in range(len(o)):
         a = traverse(T0, boxes, list(range(n)), o[i], d[i]); b = traverse(T1, rboxes, ritem, o[i], d[i])
