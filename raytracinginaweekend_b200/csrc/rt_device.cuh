@@ -983,6 +983,26 @@ __device__ __forceinline__ void camera_ray(const CameraDev& C, float px, float p
     d = unit3(sub3(sub3(add3(C.ulc, mul3(C.scaled_right, px)), mul3(C.scaled_up, py)), offset));
 }
 
+// f32::sin for the procedural textures (texture.rs:32, 50).  CUDA's sinf carries a Payne-Hanek slow path (|x| > 105 615) that works
+// on a local-memory array: never executed for scene-scale arguments, but ~500 LDL / STL instructions in every kernel that samples a
+// texture.  This version reduces the argument in double precision (two-term Cody-Waite with fused multiply-adds: exact to ~1e-16
+// for |x| < 1e15), evaluates the quadrant's polynomial in double and rounds once: within 1 ulp of the correctly rounded value that
+// glibc (the oracle, and Rust's std on Linux) returns — the same tolerance the tests already grant device sinf.
+__device__ __forceinline__ float sin_f32(float x) {
+    const double xd = (double)x;
+    const double k = rint(xd * 0.63661977236758134308);  // nearest multiple of pi/2
+    double r = fma(-k, 1.57079632679489655800e+00, xd);
+    r = fma(-k, 6.12323399573676603587e-17, r);
+    const long long q = __double2ll_rn(k);
+    const double r2 = r * r;
+    const double sn = r * fma(r2, fma(r2, fma(r2, fma(r2, fma(r2, fma(r2, 1.6059043836821613e-10, -2.5052108385441720e-08), 2.7557319223985893e-06),
+                                                                 -1.9841269841269841e-04), 8.3333333333333333e-03), -1.6666666666666666e-01), 1.0);
+    const double cs = fma(r2, fma(r2, fma(r2, fma(r2, fma(r2, fma(r2, fma(r2, -1.1470745597729725e-11, 2.0876756987868100e-09), -2.7557319223985888e-07),
+                                                                 2.4801587301587302e-05), -1.3888888888888889e-03), 4.1666666666666664e-02), -0.5), 1.0);
+    const double v = (q & 1) ? cs : sn;
+    return (float)((q & 2) ? -v : v);  // NaN / inf arguments: r is NaN, so is the result (as f32::sin)
+}
+
 // Texture::sample (src/lib/texture.rs:23-43)
 __device__ __forceinline__ uint32_t sat_u32(float v) {  // Rust `as u32` (saturating, NaN -> 0)
     if (!(v == v)) return 0u;
@@ -1032,12 +1052,12 @@ __device__ __forceinline__ float3 texture_sample(const SceneDev& S, uint32_t tex
     TextureDev t = S.textures[tex];
     for (int depth = 0; depth < 8 && t.kind == 2u; ++depth) {  // Checker (texture.rs:26-35): pick even / odd by the sign of the sine product
         const float sx = position.x * t.inv_frequency, sy = position.y * t.inv_frequency, sz = position.z * t.inv_frequency;
-        const float sines = sinf(sx) * sinf(sy) * sinf(sz);
+        const float sines = sin_f32(sx) * sin_f32(sy) * sin_f32(sz);
         t = S.textures[sines < 0.0f ? t.even : t.odd];
     }
     if (t.kind == 0u) return f3(t.r, t.g, t.b);
     if (t.kind == 3u) {  // Marble (texture.rs:44-51): 0.5 * (1 + sin(scale * z + 10 * turbulence(p, 7, 0.5)))
-        const float v = 0.5f * (1.0f + sinf(position.z * t.inv_frequency + 10.0f * perlin_turbulence(t, position, 7, 0.5f)));
+        const float v = 0.5f * (1.0f + sin_f32(position.z * t.inv_frequency + 10.0f * perlin_turbulence(t, position, 7, 0.5f)));
         return f3(v, v, v);
     }
     uint32_t pu = min(sat_u32(u * (float)t.width), t.width - 1u);

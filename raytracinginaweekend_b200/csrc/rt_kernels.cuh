@@ -445,7 +445,7 @@ __device__ __forceinline__ uint32_t shade_path(const SceneDev& S, const RenderDe
 
 // One bounce of ray_color for every live path of queue `q`; survivors (and regenerated paths) are compacted
 // into queue q^1 with one warp-aggregated atomic per warp.
-__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
+__global__ void __launch_bounds__(128, 6) k_shade(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
     const uint32_t nb = R.ctr->nb[q], n = nb + R.ctr->nn[q];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
