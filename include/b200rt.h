@@ -38,7 +38,7 @@ extern "C" {
 #define RT_EINVAL (-1)  /* malformed scene / arguments                        */
 #define RT_ECUDA (-2)   /* CUDA runtime error (no device, launch failure ...) */
 #define RT_ENOMEM (-3)  /* host or device allocation failed                   */
-#define RT_EUNSUPPORTED (-4) /* scene element outside the hot-path scope (reserved: every finish() output is supported) */
+#define RT_EUNSUPPORTED (-4) /* not supported here: rt_render_multi without peer access between the GPUs.  (Scenes: every NodeRef::finish output has a flat form; Group / nested BVH / unbounded items are rejected by the flattener on the caller side) */
 
 #define RT_LEAF_BIT 0x80000000u /* BVH child reference: RT_LEAF_BIT | item index  (reference: usize::MAX - index) */
 #define RT_MISS 0xFFFFFFFFu     /* hit id of a ray that hit nothing                */

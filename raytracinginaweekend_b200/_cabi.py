@@ -14,6 +14,7 @@ from . import build as _build
 
 RT_LEAF_BIT = 0x80000000
 RT_MISS = 0xFFFFFFFF
+RT_EINVAL_PY = -1
 
 
 class RtItem(C.Structure):
@@ -266,13 +267,27 @@ class DeviceScene:
         del keepalive  # rt_scene_create copies everything
 
     @classmethod
-    def borrowed(cls, handle, device: int = 0) -> "DeviceScene":
-        """Wrap an RtScene* owned by someone else (the host mirror's World)."""
+    def borrowed(cls, handle, device: int = 0, owner=None, generation: int = 0) -> "DeviceScene":
+        """Wrap an RtScene* owned by someone else (the host mirror's World).  The wrapper keeps its owner alive and refuses to
+        touch the handle once the owner has released or replaced its device copy (`owner._scene_generation` moves on)."""
         self = cls.__new__(cls)
-        self.h = handle
+        self._h = handle
         self.device = device
         self.owned = False
+        self._owner = owner
+        self._generation = generation
         return self
+
+    @property
+    def h(self):
+        owner = getattr(self, "_owner", None)
+        if owner is not None and owner._scene_generation != self._generation:
+            raise B200RTError(RT_EINVAL_PY, "stale scene handle: the World released or re-created its device scene")
+        return self._h
+
+    @h.setter
+    def h(self, value):
+        self._h = value
 
     @classmethod
     def from_flat(cls, fs, device: int = 0) -> "DeviceScene":
@@ -282,10 +297,10 @@ class DeviceScene:
         return cls(desc, device, keep)
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "_h", None):
             if getattr(self, "owned", True):
-                lib().rt_scene_destroy(self.h)
-            self.h = None
+                lib().rt_scene_destroy(self._h)
+            self._h = None
 
     def __del__(self):
         try:

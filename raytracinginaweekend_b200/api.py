@@ -129,6 +129,8 @@ class World:
         if not handle:
             raise RuntimeError("rtiaw host: " + host_lib().rtw_last_error().decode(errors="replace"))
         self.h = C.c_void_p(handle)
+        self._scene_generation = 0  # bumped whenever the device scene is released / re-created: borrowed wrappers check it
+        self._scene_device = None
         info = np.zeros(11, np.uint64)
         _check(host_lib().rtw_world_info(self.h, _p(info)))
         self.info = info
@@ -168,6 +170,7 @@ class World:
 
     def close(self):
         if getattr(self, "h", None):
+            self._scene_generation += 1
             host_lib().rtw_world_destroy(self.h)
             self.h = None
 
@@ -211,12 +214,17 @@ class World:
 
     def device_scene(self, device: int = 0) -> "_cabi.DeviceScene":
         """RtScene* owned by this world (uploaded on first use)."""
+        if self._scene_device is not None and self._scene_device != device:
+            self._scene_generation += 1  # the host mirror keeps ONE device copy: asking for another device replaces it
         h = C.c_void_p()
         _check(host_lib().rtw_world_device(self.h, device, C.byref(h)))
-        return _cabi.DeviceScene.borrowed(h, device)
+        self._scene_device = device
+        return _cabi.DeviceScene.borrowed(h, device, owner=self, generation=self._scene_generation)
 
     def release_device(self):
         """Drop the device copy; the next render / hit uploads the scene again."""
+        self._scene_generation += 1
+        self._scene_device = None
         _check(host_lib().rtw_world_release_device(self.h))
 
     def upload_bytes(self) -> int:
@@ -225,13 +233,17 @@ class World:
         return b.value
 
     def hit(self, org, dir, t_range=(0.001, float("inf")), device: int = 0, time: float = 0.0):
-        self.device_scene(device).set_ray_time(time)
+        scene = self.device_scene(device)
+        scene.set_ray_time(time)
         org = np.ascontiguousarray(org, np.float32).reshape(-1, 3)
         dir = np.ascontiguousarray(dir, np.float32).reshape(-1, 3)
         n = org.shape[0]
         hit, t = np.zeros(n, np.uint32), np.zeros(n, np.float32)
         nrm, ff, uv = np.zeros((n, 3), np.float32), np.zeros(n, np.uint8), np.zeros((n, 2), np.float32)
-        _check(host_lib().rtw_hit(self.h, n, _p(org), _p(dir), t_range[0], t_range[1], device, _p(hit), _p(t), _p(nrm), _p(ff), _p(uv)))
+        try:
+            _check(host_lib().rtw_hit(self.h, n, _p(org), _p(dir), t_range[0], t_range[1], device, _p(hit), _p(t), _p(nrm), _p(ff), _p(uv)))
+        finally:
+            scene.set_ray_time(0.0)  # Ray::time belongs to this batch only: do not leave it set on the shared scene
         return dict(hit_id=hit, t=t, normal=nrm, front_face=ff, uv=uv)
 
 
@@ -240,6 +252,9 @@ def render(image_size: Size2i, thread_count: int, samples_per_pixel: int, max_de
     """render() of src/lib/rendering.rs:121-128: returns [height, width, 3] linear-RGB float32, row 0 = top."""
     out = np.zeros((image_size.height, image_size.width, 3), np.float32)
     st = _cabi.RtStats()
+    if world._scene_device is not None and world._scene_device != device:
+        world._scene_generation += 1  # the World re-creates its device scene on the other GPU: earlier borrowed handles die
+    world._scene_device = device
     _check(host_lib().rtw_render(world.h, image_size.width, image_size.height, thread_count, samples_per_pixel, max_depth,
                                  int(render_mode), seed, device, _p(out), C.byref(st)))
     return (out, st.as_dict()) if return_stats else out

@@ -9,6 +9,8 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -244,6 +246,15 @@ inline float u2f(uint32_t u) {
 }
 
 int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
+    // RT_PACK_LOG=1: phase times of the scene hand-off on stderr (host packing, accelerator build, upload)
+    const bool pack_log = std::getenv("RT_PACK_LOG") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!pack_log) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[rt_scene_create] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     const uint32_t N = d.n_items;
     if (N == 0) return fail(RT_EINVAL, "scene has no items (the reference BVH builder recurses forever on an empty list)");
     if (N > RT_REF_ITEM_MASK) return fail(RT_EINVAL, "too many items");
@@ -314,26 +325,30 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     bool any_wrap = false;
     std::vector<WrapDev> wraps(N);
     const float eps = 5.9604645e-8f, safety = 8.0f;
-    for (uint32_t i = 0; i < N; ++i) {
+    std::atomic<bool> flag_wrap{false}, flag_anim{false}, flag_vol{false};
+    std::atomic<const char*> first_error{nullptr};
+    rt_rebuild::parallel_for(N, 16384, [&](size_t i_lo, size_t i_hi) {
+        const char* item_error = nullptr;
+        auto one = [&](uint32_t i) {
         const RtItem& it = d.items[i];
-        if (it.kind > RT_GEO_BOX) return fail(RT_EINVAL, "unknown geometry kind");
-        if (it.wrap_flags & ~7u) return fail(RT_EINVAL, "unknown wrapper flag");
-        any_wrap = any_wrap || it.wrap_flags != 0u;
-        sc.has_animation = sc.has_animation || (it.wrap_flags & RT_WRAP_ANIMATION) != 0u;
-        sc.has_wrapped = sc.has_wrapped || it.wrap_flags != 0u;
-        sc.has_volume = sc.has_volume || (it.wrap_flags & RT_WRAP_VOLUME) != 0u;
-        if (it.material >= d.n_materials) return fail(RT_EINVAL, "item material index out of range");
+        if (it.kind > RT_GEO_BOX) { item_error = "unknown geometry kind"; return; }
+        if (it.wrap_flags & ~7u) { item_error = "unknown wrapper flag"; return; }
+        if (it.wrap_flags != 0u) flag_wrap.store(true, std::memory_order_relaxed);
+        if (it.wrap_flags & RT_WRAP_ANIMATION) flag_anim.store(true, std::memory_order_relaxed);
+        
+        if (it.wrap_flags & RT_WRAP_VOLUME) flag_vol.store(true, std::memory_order_relaxed);
+        if (it.material >= d.n_materials) { item_error = "item material index out of range"; return; }
         const float* g = it.geom;
         PrimDev p;
         p.q0 = p.q1 = p.q2 = p.q3 = make_float4(0, 0, 0, 0);
         ShadeDev s;
         s.q0 = s.q1 = s.q2 = s.q3 = make_float4(0, 0, 0, 0);
         if (it.kind == RT_GEO_SPHERE) {
-            if (!(g[3] >= 0.0f)) return fail(RT_EINVAL, "sphere radius must be >= 0 (sphere_geometry.rs:13)");
+            if (!(g[3] >= 0.0f)) { item_error = "sphere radius must be >= 0 (sphere_geometry.rs:13)"; return; }
             p.q0 = make_float4(g[0], g[1], g[2], g[3]);
         } else if (it.kind == RT_GEO_RECT) {
             uint32_t plane = (uint32_t)g[0];
-            if (plane > RT_RECT_YZ) return fail(RT_EINVAL, "rect plane out of range");
+            if (plane > RT_RECT_YZ) { item_error = "rect plane out of range"; return; }
             p.q0 = make_float4(g[1], g[2], g[3], g[4]);
             p.q1 = make_float4(g[5], u2f(plane), 0.0f, 0.0f);
         } else if (it.kind == RT_GEO_BOX) {
@@ -396,7 +411,16 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
             fastA[i] += 16.0f * eps * wabs;
             leafA[i] = INFINITY; leafC[i] = 0.0f;
         }
-    }
+        };
+        for (size_t i = i_lo; i < i_hi && !item_error; ++i) one((uint32_t)i);
+        if (item_error) { const char* expect = nullptr; first_error.compare_exchange_strong(expect, item_error); }
+    });
+    if (first_error.load()) return fail(RT_EINVAL, first_error.load());
+    any_wrap = flag_wrap.load();
+    sc.has_animation = flag_anim.load();
+    sc.has_wrapped = any_wrap;
+    sc.has_volume = flag_vol.load();
+    lap("validate + pack items");
     auto bf16_up = [](float v) -> uint32_t {  // smallest bf16 >= v (v >= 0)
         uint32_t b;
         std::memcpy(&b, &v, 4);
@@ -443,20 +467,26 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         for (int k = 0; k < 3; ++k) { b.mn[k] = d.nodes[r].aabb_min[k]; b.mx[k] = d.nodes[r].aabb_max[k]; }
         return b;
     };
-    for (uint32_t i = 0; i < d.n_nodes; ++i) {
-        const RtBvhNode& n = d.nodes[i];
-        uint32_t l, r;
-        if (!conv_ref(n.left, &l) || !conv_ref(n.right, &r)) return fail(RT_EINVAL, "BVH child reference out of range");
-        if (n.axis_id > 2) return fail(RT_EINVAL, "BVH axis_id out of range");
-        Box bl = child_box(n.left), br = child_box(n.right);
-        NodeDev nd;
-        nd.q0 = make_float4(bl.mn[0], bl.mn[1], bl.mn[2], bl.mx[0]);
-        nd.q1 = make_float4(bl.mx[1], bl.mx[2], br.mn[0], br.mn[1]);
-        nd.q2 = make_float4(br.mn[2], br.mx[0], br.mx[1], br.mx[2]);
-        nd.q3 = make_uint4(l, r, n.axis_id, pack_margin(nodeA[i], nodeC[i]));
-        nodes[i] = nd;
-        own_box[2 * i] = make_float4(n.aabb_min[0], n.aabb_min[1], n.aabb_min[2], 0.0f);
-        own_box[2 * i + 1] = make_float4(n.aabb_max[0], n.aabb_max[1], n.aabb_max[2], 0.0f);
+    {
+        std::atomic<const char*> node_error{nullptr};
+        rt_rebuild::parallel_for(d.n_nodes, 32768, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                const RtBvhNode& n = d.nodes[i];
+                uint32_t l, r;
+                if (!conv_ref(n.left, &l) || !conv_ref(n.right, &r)) { node_error.store("BVH child reference out of range"); return; }
+                if (n.axis_id > 2) { node_error.store("BVH axis_id out of range"); return; }
+                Box bl = child_box(n.left), br = child_box(n.right);
+                NodeDev nd;
+                nd.q0 = make_float4(bl.mn[0], bl.mn[1], bl.mn[2], bl.mx[0]);
+                nd.q1 = make_float4(bl.mx[1], bl.mx[2], br.mn[0], br.mn[1]);
+                nd.q2 = make_float4(br.mn[2], br.mx[0], br.mx[1], br.mx[2]);
+                nd.q3 = make_uint4(l, r, n.axis_id, pack_margin(nodeA[i], nodeC[i]));
+                nodes[i] = nd;
+                own_box[2 * i] = make_float4(n.aabb_min[0], n.aabb_min[1], n.aabb_min[2], 0.0f);
+                own_box[2 * i + 1] = make_float4(n.aabb_max[0], n.aabb_max[1], n.aabb_max[2], 0.0f);
+            }
+        });
+        if (node_error.load()) return fail(RT_EINVAL, node_error.load());
     }
     // depth of the tree (iterative DFS; also rejects cycles by bounding the visit count)
     uint32_t root;
@@ -490,6 +520,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
                 if (!(cb.mn[k] >= d.nodes[i].aabb_min[k] && cb.mx[k] <= d.nodes[i].aabb_max[k])) sc.boxes_are_bounds = false;
         }
 
+    lap("reference nodes + depth");
     // Row f4: second topology (SAH) over the same elements.  Wrapped elements enter it with their true world-space bounds
     // (fbox; the reference's own boxes for them are not bounds, Q2); a volume's draw is keyed by the element, so it does not
     // depend on the tree that reaches it.
@@ -514,12 +545,14 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         }
         std::vector<rt_rebuild::Ref> refs;
         rt_rebuild::presplit(lb, tri, is_tri, (size_t)((double)N * factor), refs);
+        lap("pre-split references");
         std::vector<rt_rebuild::Box3> rbx(refs.size());
         for (size_t i = 0; i < refs.size(); ++i) rbx[i] = refs[i].box;
         rt_rebuild::Tree F;
         uint32_t extra_levels = 0;
         while (((size_t)N << extra_levels) < refs.size()) ++extra_levels;
         rt_rebuild::build(rbx, depth + extra_levels + (uint32_t)std::max(0, O.rebuild_depth_extra), F);
+        lap("SAH build");
         const uint32_t n2 = (uint32_t)F.left.size();
         auto item_of = [&](uint32_t leafref) -> uint32_t { return refs[leafref & ~RT_LEAF_BIT].item; };
         std::vector<float> a2(n2, 0.0f), c2(n2, 0.0f);
@@ -534,15 +567,17 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         nodes2.resize(n2);
         auto box2 = [&](uint32_t r) -> rt_rebuild::Box3 { return (r & RT_LEAF_BIT) ? rbx[r & ~RT_LEAF_BIT] : F.box[r]; };
         auto ref2 = [&](uint32_t r) -> uint32_t { return (r & RT_LEAF_BIT) ? ref_of_item(item_of(r)) : r; };
-        for (uint32_t i = 0; i < n2; ++i) {
-            const rt_rebuild::Box3 bl = box2(F.left[i]), br = box2(F.right[i]);
-            NodeDev nd;
-            nd.q0 = make_float4(bl.mn[0], bl.mn[1], bl.mn[2], bl.mx[0]);
-            nd.q1 = make_float4(bl.mx[1], bl.mx[2], br.mn[0], br.mn[1]);
-            nd.q2 = make_float4(br.mn[2], br.mx[0], br.mx[1], br.mx[2]);
-            nd.q3 = make_uint4(ref2(F.left[i]), ref2(F.right[i]), F.axis[i], pack_margin(a2[i], c2[i]));
-            nodes2[i] = nd;
-        }
+        rt_rebuild::parallel_for(n2, 32768, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                const rt_rebuild::Box3 bl = box2(F.left[i]), br = box2(F.right[i]);
+                NodeDev nd;
+                nd.q0 = make_float4(bl.mn[0], bl.mn[1], bl.mn[2], bl.mx[0]);
+                nd.q1 = make_float4(bl.mx[1], bl.mx[2], br.mn[0], br.mn[1]);
+                nd.q2 = make_float4(br.mn[2], br.mx[0], br.mx[1], br.mx[2]);
+                nd.q3 = make_uint4(ref2(F.left[i]), ref2(F.right[i]), F.axis[i], pack_margin(a2[i], c2[i]));
+                nodes2[i] = nd;
+            }
+        });
         root2 = ref2(F.root);
         sc.depth2 = F.depth;
         // the reference parent's box of every element: the visibility proof of a fast-path hit (ref_visible)
@@ -556,6 +591,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
                 }
     }
 
+    lap("pack accelerator nodes");
     SceneDev& S = sc.dev;
     std::memset(&S, 0, sizeof(S));
     S.root = root;
@@ -693,6 +729,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     S.trace_time = 0.0f;
     S.materials = sc.materials.p;
     S.textures = sc.textures.p;
+    lap("upload");
     return RT_OK;
 }
 

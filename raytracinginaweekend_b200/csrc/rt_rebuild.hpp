@@ -14,11 +14,24 @@
 #include <cmath>
 #include <cstdint>
 #include <atomic>
+#include <mutex>
 #include <numeric>
 #include <thread>
 #include <vector>
 
 namespace rt_rebuild {
+
+// Static chunking over hardware threads; fn(begin, end) works on disjoint index ranges, so results do not depend on the thread count.
+template <class F>
+inline void parallel_for(size_t n, size_t min_chunk, F&& fn) {
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t parts = std::max<size_t>(1, std::min(hw, n / std::max<size_t>(1, min_chunk)));
+    if (parts <= 1) { fn((size_t)0, n); return; }
+    std::vector<std::thread> pool;
+    for (size_t p = 1; p < parts; ++p) pool.emplace_back([&, p] { fn(n * p / parts, n * (p + 1) / parts); });
+    fn((size_t)0, n / parts);
+    for (auto& t : pool) t.join();
+}
 
 struct Box3 {
     float mn[3], mx[3];
@@ -60,14 +73,16 @@ struct Builder {
     uint32_t max_depth;
     static const int BINS = 32;
     static const uint32_t SWEEP_MAX = 96;
+    static const uint32_t PAR_SPLIT_MIN = 1u << 18;
 
     Builder(const std::vector<Box3>& l, Tree& t, uint32_t md) : leaf(l), out(t), idx(own_idx), cen(own_cen), max_depth(md) {
         own_idx.resize(leaf.size());
         std::iota(own_idx.begin(), own_idx.end(), 0u);
-        for (int k = 0; k < 3; ++k) {
-            own_cen[k].resize(leaf.size());
-            for (size_t i = 0; i < leaf.size(); ++i) own_cen[k][i] = 0.5f * leaf[i].mn[k] + 0.5f * leaf[i].mx[k];
-        }
+        for (int k = 0; k < 3; ++k) own_cen[k].resize(leaf.size());
+        parallel_for(leaf.size(), 65536, [&](size_t a, size_t b) {
+            for (size_t i = a; i < b; ++i)
+                for (int k = 0; k < 3; ++k) own_cen[k][i] = 0.5f * leaf[i].mn[k] + 0.5f * leaf[i].mx[k];
+        });
     }
     Builder(const std::vector<Box3>& l, Tree& t, uint32_t md, std::vector<uint32_t>* shared_idx, const std::vector<float>* shared_cen)
         : leaf(l), out(t), idx(*shared_idx), cen(shared_cen), max_depth(md) {}
@@ -78,12 +93,28 @@ struct Builder {
         const uint64_t child_cap = levels_left >= 1 ? (levels_left - 1 >= 63 ? ~0ull : (1ull << (levels_left - 1))) : 1ull;
         float cmin[3], cmax[3];
         for (int k = 0; k < 3; ++k) { cmin[k] = INFINITY; cmax[k] = -INFINITY; }
-        for (uint32_t i = lo; i < hi; ++i)
-            for (int k = 0; k < 3; ++k) {
-                const float c = cen[k][idx[i]];
-                cmin[k] = c < cmin[k] ? c : cmin[k];
-                cmax[k] = c > cmax[k] ? c : cmax[k];
-            }
+        const bool big = n >= PAR_SPLIT_MIN;  // the first few levels of a large build: scan and bin on all cores
+        if (big) {
+            std::mutex mu;
+            parallel_for(n, 65536, [&](size_t a, size_t b) {
+                float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+                for (size_t i = lo + a; i < lo + b; ++i)
+                    for (int k = 0; k < 3; ++k) {
+                        const float c = cen[k][idx[i]];
+                        mn[k] = c < mn[k] ? c : mn[k];
+                        mx[k] = c > mx[k] ? c : mx[k];
+                    }
+                std::lock_guard<std::mutex> lk(mu);
+                for (int k = 0; k < 3; ++k) { cmin[k] = std::min(cmin[k], mn[k]); cmax[k] = std::max(cmax[k], mx[k]); }
+            });
+        } else {
+            for (uint32_t i = lo; i < hi; ++i)
+                for (int k = 0; k < 3; ++k) {
+                    const float c = cen[k][idx[i]];
+                    cmin[k] = c < cmin[k] ? c : cmin[k];
+                    cmax[k] = c > cmax[k] ? c : cmax[k];
+                }
+        }
         int best_axis = -1;
         uint32_t best_pos = 0;  // sweep: number of elements on the left; bins: last left bin
         double best_cost = INFINITY;
@@ -116,6 +147,22 @@ struct Builder {
                 Box3 bb[BINS];
                 uint32_t cnt[BINS];
                 for (int b = 0; b < BINS; ++b) { bb[b] = empty_box(); cnt[b] = 0; }
+                if (big) {  // per-thread bins, merged (box union and counts are order-independent: same result as the serial loop)
+                    std::mutex mu;
+                    parallel_for(n, 65536, [&](size_t a, size_t e) {
+                        Box3 lb[BINS];
+                        uint32_t lc[BINS];
+                        for (int b = 0; b < BINS; ++b) { lb[b] = empty_box(); lc[b] = 0; }
+                        for (size_t i = lo + a; i < lo + e; ++i) {
+                            int b = (int)((cen[k][idx[i]] - cmin[k]) * scale);
+                            b = std::min(BINS - 1, std::max(0, b));
+                            grow(lb[b], leaf[idx[i]]);
+                            ++lc[b];
+                        }
+                        std::lock_guard<std::mutex> lk(mu);
+                        for (int b = 0; b < BINS; ++b) { if (lc[b]) grow(bb[b], lb[b]); cnt[b] += lc[b]; }
+                    });
+                } else
                 for (uint32_t i = lo; i < hi; ++i) {
                     int b = (int)((cen[k][idx[i]] - cmin[k]) * scale);
                     b = std::min(BINS - 1, std::max(0, b));
@@ -240,53 +287,96 @@ inline Box3 poly_box(const Poly& p, const Box3& within) {
 }  // namespace detail
 
 // tri: 9 floats (p0, p1, p2) per element, only read where is_tri[i] != 0.
+// Largest boxes first, in ROUNDS: each round cuts every candidate whose box area is at least tau, in parallel, and feeds the
+// pieces back as candidates; tau halves when nothing that large is left.  A piece is always smaller than the reference it came
+// from (accepted cuts shrink the summed area to < 0.9x), so this visits the references in the order of a sequential "pop the
+// largest" loop up to a factor 2 in area, and the budget ends on the largest candidates of the last round.  A reference carries no polygon: its piece of the triangle is re-derived on demand by
+// clipping the triangle against the reference's REGION (the axis-aligned cell its cuts have carved out: 48 B instead of a
+// 300 B polygon — the sequential polygon-copying version was memory-bound at ~0.9 s for the 10^6 triangles of C4).
+// Deterministic for any thread count.
 inline void presplit(const std::vector<Box3>& leaf, const std::vector<float>& tri, const std::vector<uint8_t>& is_tri, size_t budget,
                      std::vector<Ref>& refs) {
     using detail::Poly;
     refs.clear();
     refs.reserve(std::max(budget, leaf.size()));
-    std::vector<Poly> polys;
-    std::vector<int32_t> poly_of;  // per reference: index into polys or -1
-    if (budget > leaf.size()) { polys.reserve(2 * (budget - leaf.size())); poly_of.reserve(budget); }
-    std::vector<std::pair<double, uint32_t>> heap;
-    for (uint32_t i = 0; i < leaf.size(); ++i) {
-        refs.push_back(Ref{i, leaf[i]});
-        poly_of.push_back(-1);  // the polygon of an unsplit triangle is only materialised when it is first cut
-        if (is_tri[i] && budget > leaf.size()) heap.push_back({detail::half_area(leaf[i]), i});
-    }
-    std::make_heap(heap.begin(), heap.end());
-    while (!heap.empty() && refs.size() < budget) {
-        std::pop_heap(heap.begin(), heap.end());
-        const uint32_t r = heap.back().second;
-        heap.pop_back();
-        const Box3 b = refs[r].box;
-        int ax = 0;
-        for (int k = 1; k < 3; ++k)
-            if (b.mx[k] - b.mn[k] > b.mx[ax] - b.mn[ax]) ax = k;
-        if (!(b.mx[ax] > b.mn[ax])) continue;
-        const double mid = 0.5 * ((double)b.mn[ax] + (double)b.mx[ax]);
-        if (poly_of[r] < 0) {
-            Poly p;
-            p.n = 3;
-            for (int v = 0; v < 3; ++v)
-                for (int k = 0; k < 3; ++k) p.v[v][k] = tri[9 * (size_t)refs[r].item + 3 * v + k];
-            poly_of[r] = (int32_t)polys.size();
-            polys.push_back(p);
+    for (uint32_t i = 0; i < leaf.size(); ++i) refs.push_back(Ref{i, leaf[i]});
+    if (budget <= leaf.size()) return;
+    struct Region { double lo[3], hi[3]; };
+    std::vector<Region> region;
+    region.reserve(budget);
+    region.resize(leaf.size(), Region{{-INFINITY, -INFINITY, -INFINITY}, {INFINITY, INFINITY, INFINITY}});
+    struct Cand { double area; uint32_t ref; };
+    std::vector<Cand> cand;
+    for (uint32_t i = 0; i < leaf.size(); ++i)
+        if (is_tri[i]) cand.push_back({detail::half_area(leaf[i]), i});
+    struct Cut { Box3 bl, bh; double mid; int ax; bool ok; };
+    std::vector<Cut> cuts;
+    double tau = 0.0;  // area threshold of the current round: everything at least this large is cut now
+    for (const Cand& c : cand) tau = std::max(tau, c.area);
+    tau *= 0.5;
+    while (!cand.empty() && refs.size() < budget && tau > 0.0) {
+        const size_t room = budget - refs.size();
+        // candidates of this round at the END of the array (they are consumed, their pieces appended: no copying of the rest)
+        auto first_big = std::partition(cand.begin(), cand.end(), [&](const Cand& c) { return c.area < tau; });
+        size_t k = (size_t)(cand.end() - first_big);
+        if (k == 0) { tau *= 0.5; continue; }
+        if (k > room) {  // the budget ends inside this round: the `room` largest of them (ties by reference index: deterministic)
+            auto larger = [](const Cand& a, const Cand& b) { return a.area > b.area || (a.area == b.area && a.ref < b.ref); };
+            std::nth_element(first_big, first_big + room, cand.end(), larger);
+            cand.resize((size_t)(first_big - cand.begin()) + room);
+            k = room;
         }
-        const Poly src = polys[poly_of[r]];
-        const Poly lo = detail::clip_half(src, ax, mid, -1.0), hi = detail::clip_half(src, ax, mid, 1.0);
-        if (lo.n < 3 || hi.n < 3) continue;
-        const Box3 bl = detail::poly_box(lo, b), bh = detail::poly_box(hi, b);
-        const double a0 = detail::half_area(b), al = detail::half_area(bl), ah = detail::half_area(bh);
-        if (!(al + ah < 0.9 * a0)) continue;
-        polys[poly_of[r]] = lo;
-        refs[r].box = bl;
-        const uint32_t r2 = (uint32_t)refs.size();
-        refs.push_back(Ref{refs[r].item, bh});
-        poly_of.push_back((int32_t)polys.size());
-        polys.push_back(hi);
-        heap.push_back({al, r}); std::push_heap(heap.begin(), heap.end());
-        heap.push_back({ah, r2}); std::push_heap(heap.begin(), heap.end());
+        const size_t base = cand.size() - k;
+        cuts.resize(k);
+        parallel_for(k, 2048, [&](size_t lo_i, size_t hi_i) {
+            for (size_t c = lo_i; c < hi_i; ++c) {
+                Cut& cu = cuts[c];
+                cu.ok = false;
+                const uint32_t r = cand[base + c].ref;
+                const Box3 b = refs[r].box;
+                int ax = 0;
+                for (int q = 1; q < 3; ++q)
+                    if (b.mx[q] - b.mn[q] > b.mx[ax] - b.mn[ax]) ax = q;
+                if (!(b.mx[ax] > b.mn[ax])) continue;
+                const double mid = 0.5 * ((double)b.mn[ax] + (double)b.mx[ax]);
+                // this reference's piece of the triangle = triangle clipped against its region
+                Poly src;
+                src.n = 3;
+                for (int v = 0; v < 3; ++v)
+                    for (int q = 0; q < 3; ++q) src.v[v][q] = tri[9 * (size_t)refs[r].item + 3 * v + q];
+                const Region& rg = region[r];
+                for (int q = 0; q < 3 && src.n >= 3; ++q) {
+                    if (rg.lo[q] > -INFINITY) src = detail::clip_half(src, q, rg.lo[q], 1.0);
+                    if (rg.hi[q] < INFINITY && src.n >= 3) src = detail::clip_half(src, q, rg.hi[q], -1.0);
+                }
+                if (src.n < 3) continue;
+                const Poly lo = detail::clip_half(src, ax, mid, -1.0), hi = detail::clip_half(src, ax, mid, 1.0);
+                if (lo.n < 3 || hi.n < 3) continue;
+                cu.bl = detail::poly_box(lo, b);
+                cu.bh = detail::poly_box(hi, b);
+                const double a0 = detail::half_area(b), al = detail::half_area(cu.bl), ah = detail::half_area(cu.bh);
+                cu.ok = al + ah < 0.9 * a0;
+                cu.mid = mid; cu.ax = ax;
+            }
+        });
+        // apply in batch order (sequential, cheap): the low half replaces the reference, the high half is appended; both pieces
+        // are smaller than the reference they came from and become candidates again
+        std::vector<uint32_t> batch(k);
+        for (size_t c = 0; c < k; ++c) batch[c] = cand[base + c].ref;
+        cand.resize(base);
+        for (size_t c = 0; c < k; ++c) {
+            if (!cuts[c].ok || refs.size() >= budget) continue;
+            const uint32_t r = batch[c];
+            refs[r].box = cuts[c].bl;
+            const uint32_t r2 = (uint32_t)refs.size();
+            refs.push_back(Ref{refs[r].item, cuts[c].bh});
+            Region hi_region = region[r];
+            region[r].hi[cuts[c].ax] = cuts[c].mid;
+            hi_region.lo[cuts[c].ax] = cuts[c].mid;
+            region.push_back(hi_region);
+            cand.push_back({detail::half_area(cuts[c].bl), r});
+            cand.push_back({detail::half_area(cuts[c].bh), r2});
+        }
     }
 }
 

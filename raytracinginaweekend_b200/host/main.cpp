@@ -5,8 +5,10 @@
 // Same positional arguments, same height rule (`(width as f32 * camera.aspect_ratio()) as i32`, main.rs:38-41), same
 // gamma-2 quantisation (Color::to_rgb8_gamma2, color.rs:43-48).  `thread_count` = available_parallelism in the reference
 // (main.rs:19); here it is the number of sample lanes in flight per pixel (env RTIAW_LANES, default 16).
+// The reference seeds its render RNG from OS entropy (rendering.rs:160); so does this CLI unless RTIAW_SEED is set (tests).
 // Assets are looked up under $RTIAW_ASSETS (default ./assets); worlds with an image texture read <assets>/earthmap.ppm
-// (P6; `python -m raytracinginaweekend_b200.tools_earth_ppm` writes it from earthmap.jpg — JPEG decode is caller-side).
+// (P6; `python -m raytracinginaweekend_b200.tools_earth_ppm` writes it from earthmap.jpg — JPEG decode is caller-side, the
+// reference delegates it to the `image` crate, world_builder.rs:19-31).  Without that file those worlds fail with a clear message.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -99,12 +101,18 @@ int main(int argc, char** argv) {
         a.cube_obj = assets_dir + "/cube.obj";
         std::vector<uint8_t> earth;
         if (read_ppm(assets_dir + "/earthmap.ppm", a.earth_w, a.earth_h, earth)) a.earth_rgb8 = earth.data();
+        const bool needs_earth = world_name == "demo:earth_mapped" || world_name == "demo:final_scene2" || world_name == "config:c3";
+        if (needs_earth && !a.earth_rgb8)
+            throw std::runtime_error("world " + world_name + " needs the earth map: " + assets_dir + "/earthmap.ppm is missing "
+                                     "(write it with: python -m raytracinginaweekend_b200.tools_earth_ppm)");
         NamedWorld nw = create_world(world_name, a);
         const Size2i size{image_width, (int32_t)((float)image_width * nw.world->camera.aspect_ratio())};
         std::fprintf(stderr, "Start rendering...\n");
         RtStats st{};
         const auto t0 = std::chrono::steady_clock::now();
-        std::vector<Color> px = render(size, thread_count, spp, max_depth, *nw.world, RenderMode::Default, /*seed=*/std::chrono::system_clock::now().time_since_epoch().count(), &st);
+        const char* sd = std::getenv("RTIAW_SEED");
+        const uint64_t seed = sd ? (uint64_t)std::strtoull(sd, nullptr, 10) : (uint64_t)std::chrono::system_clock::now().time_since_epoch().count();
+        std::vector<Color> px = render(size, thread_count, spp, max_depth, *nw.world, RenderMode::Default, seed, &st);
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::fprintf(stderr, "Rendering done in %f seconds (%.1f Mrays/s on the device)\n", secs, st.ray_segments / (st.render_ms * 1e3));
         std::fprintf(stderr, "Saving image...\n");

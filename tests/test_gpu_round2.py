@@ -2,6 +2,8 @@
 device-side gamma, full-size MODE 3 == MODE 0 films.  Everything goes through the C ABI; the oracle is only the checker."""
 import ctypes as C
 import math
+import os
+import sys
 
 import numpy as np
 import pytest
@@ -225,3 +227,63 @@ def test_c4_full_size_film_mode3_equals_reference_tree():
         _cabi.set_option("traversal", mode)
         small[mode] = rb.render(rb.Size2i(480, 270), 1, 1, 50, w, seed=13)
     assert images_equal_bits(small[3], small[0])
+
+
+# ---------------------------------------------------------------- the reference CLI (src/app/main.rs) over the B200 path
+def _png_rgb(path):
+    import struct
+    import zlib
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w, h = 8, b"", 0, 0
+    while pos < len(raw):
+        n, typ = struct.unpack(">I4s", raw[pos:pos + 8])
+        data = raw[pos + 8:pos + 8 + n]
+        assert zlib.crc32(typ + data) == struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])[0]
+        if typ == b"IHDR":
+            w, h, depth, ctype = struct.unpack(">IIBB", data[:10])
+            assert (depth, ctype) == (8, 2)
+        if typ == b"IDAT":
+            idat += data
+        pos += 12 + n
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 3 * w)
+    assert (rows[:, 0] == 0).all()
+    return rows[:, 1:].reshape(h, w, 3)
+
+
+@pytest.mark.parametrize("name", ["demo:final_scene1", "demo:suzanne", "demo:earth_mapped"])
+def test_cli_writes_the_gamma2_png_of_the_render(name, oracle_world, oracle, tmp_path):
+    """rtiaw_app <out> <width> <spp> <depth> <world> (main.rs:10-64): positional arguments, height = (width * aspect) as i32
+    (main.rs:38-41), render(), Color::to_rgb8_gamma2 (color.rs:43-48), 8-bit RGB PNG.  With RTIAW_SEED the image is the oracle's."""
+    import subprocess
+    from raytracinginaweekend_b200 import build as _build
+    exe = _build.build_app()
+    assets = tmp_path / "assets"
+    assets.mkdir()
+    for f in ("suzanne.obj", "cube.obj"):
+        os.symlink(os.path.join(_build.ROOT, "assets", f), assets / f)
+    env = dict(os.environ, RTIAW_SEED="7", RTIAW_LANES="2", RTIAW_ASSETS=str(assets))
+    out = tmp_path / "out.png"
+    if name == "demo:earth_mapped":   # first without the earth map: a clear error, not a crash
+        r = subprocess.run([exe, str(out), "64", "2", "10", name], env=env, capture_output=True, text=True)
+        assert r.returncode == 1 and "earthmap.ppm" in r.stderr
+        subprocess.check_call([sys.executable, "-m", "raytracinginaweekend_b200.tools_earth_ppm", str(assets / "earthmap.ppm")], cwd=_build.ROOT)
+    r = subprocess.run([exe, str(out), "96", "4", "50", name], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Rendering done in" in r.stderr and "Saving image..." in r.stderr          # the reference's progress lines (rendering.rs:216, main.rs:52)
+    img = _png_rgb(out)
+    fs = product_world(name).export()
+    aspect = np.float32(np.linalg.norm(fs.cam[15:18].astype(np.float32))) / np.float32(np.linalg.norm(fs.cam[12:15].astype(np.float32)))
+    assert img.shape[1] == 96 and abs(img.shape[0] - int(np.float32(96) * aspect)) <= 1
+    ref, _ = oracle_world(name).render(96, img.shape[0], 4, 50, 2, 7, "replay")
+    exp = oracle.to_rgb8_gamma2(ref)
+    assert (img != exp).any(axis=2).mean() <= (0.003 if name == "demo:earth_mapped" else 0.0)   # texel-border pixels of the image texture
+
+
+def test_cli_argument_errors():
+    import subprocess
+    from raytracinginaweekend_b200 import build as _build
+    exe = _build.build_app()
+    assert subprocess.run([exe, "x.png", "64"], capture_output=True).returncode != 0                       # main.rs indexes args[1..5]: panics
+    r = subprocess.run([exe, "/tmp/x.png", "64", "1", "5", "demo:no_such_world"], capture_output=True, text=True)
+    assert r.returncode != 0 and "error" in r.stderr                                                        # main.rs:36 `_ => panic!()`
