@@ -26,7 +26,7 @@ struct Counters {
 };
 
 struct RenderDev {
-    float4* A[2];   // origin.xyz, bits(slot)            slot = track * npix + pixel
+    float4* A[2];   // origin.xyz, bits(pixel)           (the lane it renders is D.y; with it the accumulator = acc[lane][pixel])
     float4* B[2];   // direction.xyz, bits(sample k within the lane)
     float4* C[2];   // throughput.rgb, primary direction.y (Q6)
     int2* D[2];     // remaining depth, local lane m the path belongs to
@@ -85,13 +85,12 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
     const uint32_t n_slots = R.cap;  // this pipeline's tracks: track = pipe + n_pipes * i; a track starts with local lane m = track
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_slots; j += gridDim.x * blockDim.x) {
         const uint32_t pixel = j % R.npix, track = R.pipe + R.n_pipes * (j / R.npix);
-        const uint32_t slot = track * R.npix + pixel;  // unique across pipelines
         const uint32_t lane_id = R.lane_first + track * R.lane_stride;
         float3 o, d;
         float time;
         generate_path(S, R, pixel, lane_id, 0u, o, d, time);
         if (R.Tm[0]) R.Tm[0][j] = time;
-        R.A[0][j] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
+        R.A[0][j] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
         const uint32_t miss = root_gate(S, o, d, 0.001f, __int_as_float(0x7f800000), R.ref_only != 0u) ? 0u : RT_ROOT_MISS;
         R.B[0][j] = make_float4(d.x, d.y, d.z, __uint_as_float(miss));
         R.C[0][j] = make_float4(1.0f, 1.0f, 1.0f, d.y);
@@ -120,9 +119,9 @@ struct ExtendKey {
     int q;
     uint32_t pos;
     __device__ __forceinline__ VolKey operator()() const {
-        const uint32_t slot = __float_as_uint(__ldcg(&R->A[q][pos].w)), k = __float_as_uint(__ldcg(&R->B[q][pos].w)) & ~RT_ROOT_MISS;
+        const uint32_t pixel = __float_as_uint(__ldcg(&R->A[q][pos].w)), k = __float_as_uint(__ldcg(&R->B[q][pos].w)) & ~RT_ROOT_MISS;
         const int2 dm = __ldcg(&R->D[q][pos]);
-        const uint32_t pixel = slot % R->npix, lane_id = R->lane_first + (uint32_t)dm.y * R->lane_stride;
+        const uint32_t lane_id = R->lane_first + (uint32_t)dm.y * R->lane_stride;
         return VolKey{R->seed0, R->seed1, pixel, k * R->n_tasks + lane_id, 1u + (uint32_t)(R->max_depth - dm.x)};
     }
 };
@@ -269,7 +268,7 @@ __device__ __forceinline__ uint32_t shade_path(const SceneDev& S, const RenderDe
     int32_t depth = P.depth;
     bool live = false, fresh = false;
     uint32_t new_paths = 0;
-    const uint32_t pixel = slot % R.npix;
+    const uint32_t pixel = slot;  // the path carries its pixel (an integer modulo here was 4 % of the shade kernel's instructions and 13 % of its stalls)
     uint32_t lane_id = R.lane_first + m * R.lane_stride;
     const float t = __uint_as_float(h.y);
     float3 radiance = f3(0.0f, 0.0f, 0.0f);
@@ -415,7 +414,7 @@ __device__ __forceinline__ uint32_t shade_path(const SceneDev& S, const RenderDe
     }
     if (terminated) {
         float4* ap = R.acc + ((size_t)m * R.npix + pixel);
-        float4 s = __ldcg(ap);  // sequential per-pixel sum in sample order (rendering.rs:172-178); L2 access: a slot is shaded by different SMs over time
+        float4 s = __ldcg(ap);  // sequential per-pixel sum in sample order (rendering.rs:172-178); streamed through L2, never reused from L1
         s.x += radiance.x; s.y += radiance.y; s.z += radiance.z;
         s.w += radiance.x * radiance.x + radiance.y * radiance.y + radiance.z * radiance.z;  // second moment (RMSE bound)
         __stcg(ap, s);
