@@ -272,7 +272,7 @@ class Bench:
                 "avg_launch_ms": p["extend_ms"] / max(1, p["iterations"]), "share_of_step": p["extend_ms"] / max(1e-9, p["render_ms"]),
                 "nodes_per_ray": npr, "prims_per_ray": ppr, "flops_per_ray": flops, "bytes_per_ray": bytes_per_ray, "scene_in_l2": in_l2,
                 "fp32_tflops": fp32, "fp32_frac": fp32 / self.fp32_peak, "hbm_gbs": hbm, "hbm_frac": hbm / self.hbm_peak,
-                "lanes_holding_a_ray": lanes, "tracks": int(p["tracks"]), "rays": int(rays)}
+                "lanes_holding_a_ray": lanes, "slots": int(p["slots"]), "rays": int(rays)}
 
     def roofline(self, pr, config="c2"):
         """The JSON `roofline` object from a probe: the BINDING roof first (FP32 issue when the scene lives in L2, HBM otherwise)."""
@@ -390,7 +390,7 @@ class Bench:
         pr = self.probes(scene, plane, wl["width"], wl["height"], spp_total, lanes_total, scene_bytes)
         e2e = (self.e2e_host if n == 1 else self.e2e_dist)(world, wl, spp_total, lanes_total, e2e_steps)
         out = {"workload": wl["world"], "width": wl["width"], "height": wl["height"], "spp_per_gpu": wl["spp"], "spp_total": spp_total,
-               "sample_lanes_per_gpu": wl["lanes"], "tracks_per_pixel": pr["tracks"], "value": r["value"], "unit": "Mrays/s", "ms_per_step": r["ms_per_step"],
+               "sample_lanes_per_gpu": wl["lanes"], "path_slots": pr["slots"], "value": r["value"], "unit": "Mrays/s", "ms_per_step": r["ms_per_step"],
                "steps": steps, "ray_segments_per_step": r["rays_per_step"], "e2e": e2e, "roofline": self.roofline(pr, name),
                "scene_device_bytes": scene_bytes, "world_build_s": round(t1 - t0, 3), "scene_create_s": round(t2 - t1, 3)}
         for k in ("spp_note",):
@@ -471,9 +471,9 @@ def main():
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wl["world"], "width": wl["width"], "height": wl["height"], "spp_per_gpu": wl["spp"],
-                       "spp_total": wl["spp"] * n, "max_depth": MAX_DEPTH, "sample_lanes_per_gpu": wl["lanes"], "tracks_per_pixel": head["tracks_per_pixel"],
+                       "spp_total": wl["spp"] * n, "max_depth": MAX_DEPTH, "sample_lanes_per_gpu": wl["lanes"], "path_slots": head["path_slots"],
                        "parallelism": f"sample-lane sharding x{n}, NCCL all-reduce (pre-multiplied sum) of the film",
-                       "l2": "256 MB flush between steps; path-state working set %.1f GB > L2" % (head["tracks_per_pixel"] * wl["width"] * wl["height"] * 120 / 1e9),
+                       "l2": "256 MB flush between steps; path-state working set %.1f GB > L2" % (head["path_slots"] * 120 / 1e9),
                        "ray_segments_per_step": head["ray_segments_per_step"],
                        "per_rank_ms_per_step": [float(t.item()) / args.steps for t in per_rank] if n > 1 else [head["ms_per_step"]]},
             "roofline": head["roofline"], "e2e": head["e2e"], "clocks": clocks, "gpu_launches": int(B.launches),

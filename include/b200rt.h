@@ -170,9 +170,9 @@ typedef struct RtStats {
     uint64_t redo_rays;      /* traversal 3: rays the fast topology could not prove, traced again on the reference tree — only with "count" */
     uint32_t max_stack;      /* deepest traversal stack use of any ray (entries) — only with "count" */
     uint32_t stack_capacity; /* entries per thread the launch provided (tree depth + 2): max_stack must never exceed it */
-    uint32_t tracks;         /* paths in flight per pixel the library chose (<= lanes of this rank; "max_slots" / pixels) */
+    uint32_t slots;          /* path slots in flight the library chose: min("max_slots", lanes of this rank x pixels) */
     uint32_t pipes;          /* wavefront pipelines (streams) used */
-    double merge_ms;         /* rt_render_multi: device time of this GPU's share of the film combine (k_merge_peers + copy-out) */
+    double merge_ms;         /* rt_render_multi: device time of this GPU's share of the film combine (k_merge_peers) */
     uint64_t warp_rounds, busy_lane_rounds; /* only with "count": scheduling rounds of the extend warps and lanes holding a ray in them */
     uint64_t rounds_hist[24];/* only with "count": rays by floor(log2(traversal rounds)) — the tail that sets a launch's duration */
 } RtStats;

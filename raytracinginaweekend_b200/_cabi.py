@@ -71,7 +71,7 @@ class RtStats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("render_ms", C.c_double), ("extend_ms", C.c_double),
                 ("shade_ms", C.c_double), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64), ("exact_steps", C.c_uint64),
                 ("redo_rays", C.c_uint64), ("max_stack", C.c_uint32), ("stack_capacity", C.c_uint32),
-                ("tracks", C.c_uint32), ("pipes", C.c_uint32), ("merge_ms", C.c_double), ("warp_rounds", C.c_uint64), ("busy_lane_rounds", C.c_uint64), ("rounds_hist", C.c_uint64 * 24)]
+                ("slots", C.c_uint32), ("pipes", C.c_uint32), ("merge_ms", C.c_double), ("warp_rounds", C.c_uint64), ("busy_lane_rounds", C.c_uint64), ("rounds_hist", C.c_uint64 * 24)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

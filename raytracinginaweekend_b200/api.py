@@ -250,7 +250,7 @@ class World:
 def render(image_size: Size2i, thread_count: int, samples_per_pixel: int, max_depth: int, world: World,
            render_mode: RenderMode = RenderMode.Default, seed: int = 0x5EED, device: int = 0, return_stats: bool = False):
     """render() of src/lib/rendering.rs:121-128: returns [height, width, 3] linear-RGB float32, row 0 = top."""
-    out = np.zeros((image_size.height, image_size.width, 3), np.float32)
+    out = np.empty((image_size.height, image_size.width, 3), np.float32)
     st = _cabi.RtStats()
     if world._scene_device is not None and world._scene_device != device:
         world._scene_generation += 1  # the World re-creates its device scene on the other GPU: earlier borrowed handles die

@@ -44,21 +44,22 @@ int g_opt_pipes = 0;         // independent wavefront pipelines (streams) per re
                               // 0 = auto: 2 for renders with >= 64 Mi path slots (throughput-bound), 4 below (launch-tail-bound)
 int g_opt_leaf_weight = 24;   // extend phase vote: leaf phase when n_leaf * w > n_node * 16
 int g_opt_refill = 28;        // extend refills idle lanes when fewer than this many of 32 are busy
+int g_opt_debug_skip_redo = 0;  // measurement only: keep unproven fast-path results (films are then NOT the reference's)
 int g_opt_count = 0;        // 1 = COUNT kernel variant (node visits / primitive tests per ray)
 int g_opt_profile = 0;        // 1 = time every extend / shade launch with CUDA events on the launching stream (no extra syncs)
 int g_opt_check_every = 8;    // host polls the live-path count every N iterations
 int g_opt_blocks_per_sm = 0;  // 0 = from occupancy query
-int64_t g_opt_max_slots = 160ll << 20;  // path slots in flight per render (bounds the workspace: 120 B per slot, 19 GB at most); tracks per pixel = max_slots / pixels
+int64_t g_opt_max_slots = 160ll << 20;  // path slots in flight per render (bounds the workspace: 120 B per slot)
 
 struct Options {
     int traversal, presplit, rebuild_min_items, rebuild_wrapped, rebuild, rebuild_depth_extra, pipes, leaf_weight, refill, count, profile,
-        check_every, blocks_per_sm;
+        check_every, blocks_per_sm, debug_skip_redo;
     int64_t max_slots;
 };
 Options options_snapshot() {
     std::lock_guard<std::mutex> lk(g_opt_mu);
     return Options{g_opt_traversal, g_opt_presplit, g_opt_rebuild_min_items, g_opt_rebuild_wrapped, g_opt_rebuild, g_opt_rebuild_depth_extra,
-                   g_opt_pipes, g_opt_leaf_weight, g_opt_refill, g_opt_count, g_opt_profile, g_opt_check_every, g_opt_blocks_per_sm,
+                   g_opt_pipes, g_opt_leaf_weight, g_opt_refill, g_opt_count, g_opt_profile, g_opt_check_every, g_opt_blocks_per_sm, g_opt_debug_skip_redo,
                    g_opt_max_slots};
 }
 
@@ -119,8 +120,14 @@ struct Workspace {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // render brackets (created once: no per-call create / destroy to leak on error paths)
     std::vector<cudaEvent_t> prof_events[MAX_PIPES];
     DevBuf<uint32_t> iter_log;  // [MAX_PIPES][ITER_LOG_CAP], only with RT_ITER_LOG set
+    DevBuf<float> long_rays;    // 4096 x 8 floats, only with RT_LONG_RAYS set (debug: the rays that set a launch's tail)
     static const int ITER_LOG_CAP = 16384;
     size_t ws_slots = 0;
+    // film download into a caller's pageable buffer: two pinned staging chunks, DMA of chunk i+1 overlapped with the host copy of chunk i
+    static const size_t STAGE_BYTES = (size_t)4 << 20;
+    char* h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_event[2] = {};
+    cudaStream_t copy_stream = nullptr;
 };
 static std::mutex g_ws_mu;
 static std::map<int, Workspace*> g_ws;  // never freed: lives as long as the process (the CUDA context may already be gone at exit)
@@ -142,6 +149,7 @@ struct RtScene {
     DevBuf<WrapDev> wraps;
     DevBuf<NodeDev> nodes2;    // row f4: rebuilt topology (plain scenes only)
     DevBuf<float4> vis_box;
+    DevBuf<uint32_t> visit_rank;
     uint32_t depth2 = 0;
     bool has_animation = false;
     bool boxes_are_bounds = true;  // every node box contains its children's boxes (false: MODE 0 only, see pack_scene)
@@ -482,11 +490,15 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
                 nd.q2 = make_float4(br.mn[2], br.mx[0], br.mx[1], br.mx[2]);
                 nd.q3 = make_uint4(l, r, n.axis_id, pack_margin(nodeA[i], nodeC[i]));
                 nodes[i] = nd;
-                own_box[2 * i] = make_float4(n.aabb_min[0], n.aabb_min[1], n.aabb_min[2], 0.0f);
+                // .w of the first half: the node's parent in the reference tree (ref_reaches_exact walks the chain); filled below
+                own_box[2 * i] = make_float4(n.aabb_min[0], n.aabb_min[1], n.aabb_min[2], u2f(0xFFFFFFFFu));
                 own_box[2 * i + 1] = make_float4(n.aabb_max[0], n.aabb_max[1], n.aabb_max[2], 0.0f);
             }
         });
         if (node_error.load()) return fail(RT_EINVAL, node_error.load());
+        for (uint32_t i = 0; i < d.n_nodes; ++i)  // parent links (every child reference was range-checked above)
+            for (uint32_t ch : {d.nodes[i].left, d.nodes[i].right})
+                if (!(ch & RT_LEAF_BIT)) own_box[2 * (size_t)ch].w = u2f(i);
     }
     // depth of the tree (iterative DFS; also rejects cycles by bounding the visit count)
     uint32_t root;
@@ -586,11 +598,33 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
             for (uint32_t ch : {d.nodes[i].left, d.nodes[i].right})
                 if (ch & RT_LEAF_BIT) {
                     const uint32_t item = ch & ~RT_LEAF_BIT;
-                    vis_box[2 * (size_t)item] = make_float4(d.nodes[i].aabb_min[0], d.nodes[i].aabb_min[1], d.nodes[i].aabb_min[2], 0.0f);
+                    vis_box[2 * (size_t)item] = make_float4(d.nodes[i].aabb_min[0], d.nodes[i].aabb_min[1], d.nodes[i].aabb_min[2], u2f(i));  // .w: the parent node
                     vis_box[2 * (size_t)item + 1] = make_float4(d.nodes[i].aabb_max[0], d.nodes[i].aabb_max[1], d.nodes[i].aabb_max[2], 0.0f);
                 }
     }
 
+    // Equal-t ties on the fast path (plain scenes): the reference returns the element its ordered DFS visits first, and that order
+    // depends only on the signs of the ray direction (hittable.rs:441-445) — one leaf order per octant, 8 x n_items ranks.
+    std::vector<uint32_t> visit_rank;
+    if (!nodes2.empty() && !any_wrap && !(root & RT_REF_LEAF)) {
+        visit_rank.assign(8 * (size_t)N, 0u);
+        rt_rebuild::parallel_for(8, 1, [&](size_t o_lo, size_t o_hi) {
+            std::vector<uint32_t> st;
+            for (size_t oct = o_lo; oct < o_hi; ++oct) {
+                uint32_t next = 0;
+                st.clear();
+                st.push_back(root);
+                while (!st.empty()) {
+                    const uint32_t r = st.back();
+                    st.pop_back();
+                    if (r & RT_REF_LEAF) { visit_rank[oct * N + (r & RT_REF_ITEM_MASK)] = next++; continue; }
+                    const bool left_first = ((oct >> nodes[r].q3.z) & 1u) != 0u;
+                    st.push_back(left_first ? nodes[r].q3.y : nodes[r].q3.x);  // visited second
+                    st.push_back(left_first ? nodes[r].q3.x : nodes[r].q3.y);
+                }
+            }
+        });
+    }
     lap("pack accelerator nodes");
     SceneDev& S = sc.dev;
     std::memset(&S, 0, sizeof(S));
@@ -662,6 +696,11 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         CU(cudaMemcpy(sc.vis_box.p, vis_box.data(), vis_box.size() * sizeof(float4), cudaMemcpyHostToDevice));
         sc.device_bytes += nodes2.size() * sizeof(NodeDev) + vis_box.size() * sizeof(float4);
     }
+    if (!visit_rank.empty()) {
+        CU(sc.visit_rank.alloc(visit_rank.size()));
+        CU(cudaMemcpy(sc.visit_rank.p, visit_rank.data(), visit_rank.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        sc.device_bytes += visit_rank.size() * sizeof(uint32_t);
+    }
 
     std::vector<const uint8_t*> img_dev(d.n_images, nullptr);
     for (uint32_t i = 0; i < d.n_images; ++i) {
@@ -724,6 +763,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     S.own_box = sc.own_box.p;
     S.nodes2 = sc.nodes2.p;
     S.fast_trace_ok = sc.has_animation ? 0u : 1u;
+    S.visit_rank = sc.visit_rank.p;
     S.vis_box = sc.vis_box.p;
     S.wraps = sc.wraps.p;
     S.trace_time = 0.0f;
@@ -808,8 +848,7 @@ struct RenderPlan {
     RenderDev R{};       // rank-level description (k_finalize and the multi-GPU reduce use it as is)
     uint64_t n_tasks = 0;
     uint32_t n_local = 0;  // lanes this rank owns (0: it contributes nothing)
-    uint32_t n_tracks = 0; // paths in flight per pixel
-    size_t npix = 0, slots = 0, acc_elems = 0;
+    size_t npix = 0, slots = 0, acc_elems = 0;  // slots: paths in flight on this rank (all pipelines)
 };
 
 int make_plan(const RtScene& sc, const Options& O, const RtRenderParams& P, uint32_t lane_first, uint32_t lane_stride, RenderPlan& pl) {
@@ -820,21 +859,19 @@ int make_plan(const RtScene& sc, const Options& O, const RtRenderParams& P, uint
     if (lane_stride == 0) return fail(RT_EINVAL, "lane_stride must be >= 1");
     const uint64_t T = P.thread_count;
     pl.n_tasks = std::min<uint64_t>(T, P.samples_per_pixel);
-    if (P.samples_per_pixel / T + 1 > 0x7FFFFFFFull) return fail(RT_EINVAL, "too many samples per lane");
+    if (P.samples_per_pixel / T + 1 > 0x3FFFFFFFull) return fail(RT_EINVAL, "too many samples per lane (2^30 at most)");
     pl.npix = (size_t)P.width * P.height;
     if (pl.npix > 0x7FFFFFFFull) return fail(RT_EINVAL, "image too large");
     pl.n_local = lane_first >= pl.n_tasks ? 0u : (uint32_t)((pl.n_tasks - lane_first + lane_stride - 1) / lane_stride);
-    // Tracks: the library, not the caller's thread_count, decides how many paths are in flight.  Each pixel gets J tracks
-    // (J * pixels <= max_slots); track j renders the rank's lanes j, j + J, ... one after the other, so the path-state
-    // workspace is bounded while every lane still owns its plane (merge_planes needs all T of them: 16 B x T x pixels).
+    // The library, not the caller's thread_count, decides how many paths are in flight: at most max_slots path slots, fed from
+    // the rank's chains (one chain = all samples of one (lane, pixel), rendered in order by one slot; a slot whose chain has
+    // ended takes the next one).  The path-state workspace is bounded while every lane still owns its plane (merge_planes
+    // needs all T of them: 16 B x T x pixels).
     if (pl.n_local) {
         const uint64_t budget = (uint64_t)std::max<int64_t>(O.max_slots, 1);
-        uint32_t J = (uint32_t)std::min<uint64_t>(pl.n_local, std::max<uint64_t>(1, budget / pl.npix));
-        const uint32_t rounds = (pl.n_local + J - 1) / J;
-        J = (pl.n_local + rounds - 1) / rounds;  // same number of rounds, evenly filled tracks
-        pl.n_tracks = J;
-        pl.slots = (size_t)J * pl.npix;
-        if (pl.slots > 0xFFFFFFF0ull) return fail(RT_EINVAL, "width*height*tracks exceeds 2^32 path slots (lower max_slots)");
+        const uint64_t chains = (uint64_t)pl.n_local * pl.npix;
+        pl.slots = (size_t)std::min<uint64_t>(chains, std::max<uint64_t>(budget, 4 * Workspace::MAX_PIPES));  // >= 1 slot for every pipeline
+        if (pl.slots > 0xFFFFFFF0ull) return fail(RT_EINVAL, "more than 2^32 path slots (lower max_slots)");
         pl.acc_elems = (size_t)pl.n_local * pl.npix;
     }
     RenderDev& R = pl.R;
@@ -842,7 +879,6 @@ int make_plan(const RtScene& sc, const Options& O, const RtRenderParams& P, uint
     R.max_depth = P.max_depth;
     R.n_tasks = (uint32_t)pl.n_tasks;
     R.lane_first = lane_first; R.lane_stride = lane_stride; R.n_local_lanes = pl.n_local;
-    R.n_tracks = pl.n_tracks;
     R.spp_whole = (uint32_t)(P.samples_per_pixel / T);
     R.spp_rem = (uint32_t)(P.samples_per_pixel % T);
     R.seed0 = (uint32_t)P.seed; R.seed1 = (uint32_t)(P.seed >> 32);
@@ -850,6 +886,7 @@ int make_plan(const RtScene& sc, const Options& O, const RtRenderParams& P, uint
     R.sy = 1.0f / (float)(P.height - 1);
     R.mode = P.render_mode;
     R.ref_only = (O.traversal == 0 || !sc.boxes_are_bounds) ? 1u : 0u;
+    R.debug_skip_redo = O.debug_skip_redo ? 1u : 0u;
     R.refill_threshold = (uint32_t)std::min(32, std::max(1, O.refill));
     R.leaf_weight = (uint32_t)std::max(1, O.leaf_weight);
     return RT_OK;
@@ -878,8 +915,6 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
     }
     RenderDev& R = pl.R;
     R.acc = ws.acc.p;
-    const uint32_t J = pl.n_tracks;
-
     int mode = std::min(3, std::max(0, O.traversal));
     if (!sc.boxes_are_bounds) mode = 0;
     if (mode == 3 && !sc.nodes2.p) mode = 2;  // no rebuilt topology for this scene (wrapped elements, single element, rebuild off)
@@ -887,14 +922,19 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
     const int eblock = 128;
     const size_t esmem = stack_smem_bytes(sc, eblock);
 
-    // Split the rank's tracks over G independent wavefront pipelines, each on its own stream with its own queues and
+    // Split the rank's lanes over G independent wavefront pipelines, each on its own stream with its own queues and
     // counters.  A persistent extend launch ends with a tail in which a few very long rays keep a few warps busy; with two
     // pipelines in flight the other pipeline's blocks backfill the SMs during that tail (and during shade / launch gaps).
     const char* iter_log_path = std::getenv("RT_ITER_LOG");  // debug: dump (pipe, iteration, live paths, extend ms, shade ms)
     if (iter_log_path && !ws.iter_log.p) CU(ws.iter_log.alloc((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP * 8));
+    const char* long_rays_path = O.count ? std::getenv("RT_LONG_RAYS") : nullptr;  // debug: dump the rays that took >= 4096 traversal rounds
+    if (long_rays_path) {
+        if (!ws.long_rays.p) CU(ws.long_rays.alloc(4096 * 8));
+        CU(cudaMemsetAsync(ws.long_rays.p, 0, 4096 * 8 * sizeof(float), stream));
+    }
     std::vector<std::array<float, 2>> iter_ms[Workspace::MAX_PIPES];
-    const int want_pipes = O.pipes > 0 ? O.pipes : (pl.slots >= ((size_t)64 << 20) ? 2 : 4);
-    const int G = (int)std::min<uint32_t>((uint32_t)std::max(1, std::min(want_pipes, (int)Workspace::MAX_PIPES)), J);
+    const int want_pipes = O.pipes > 0 ? O.pipes : (pl.slots >= ((size_t)64 << 20) ? 3 : 4);  // measured on C1..C5 (profiles/README.md)
+    const int G = (int)std::min<uint32_t>((uint32_t)std::max(1, std::min(want_pipes, (int)Workspace::MAX_PIPES)), pl.n_local);
     struct Pipe {
         RenderDev R;
         cudaStream_t st;
@@ -908,10 +948,12 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
         size_t off = 0;
         for (int p = 0; p < G; ++p) {
             Pipe& pp = pipes[p];
-            const uint32_t tracks_p = (J - (uint32_t)p + (uint32_t)G - 1u) / (uint32_t)G;
+            // pipeline p renders the rank's local lanes p, p + G, ...: its chains, and its share of the slots
+            const uint32_t lanes_p = (pl.n_local - (uint32_t)p + (uint32_t)G - 1u) / (uint32_t)G;
             pp.R = R;
             pp.R.pipe = (uint32_t)p; pp.R.n_pipes = (uint32_t)G;
-            pp.R.cap = (uint32_t)((size_t)tracks_p * npix);
+            pp.R.n_chains = (unsigned long long)lanes_p * npix;
+            pp.R.cap = (uint32_t)std::min<uint64_t>(pp.R.n_chains, std::max<uint64_t>(1, (uint64_t)pl.slots * lanes_p / pl.n_local));
             for (int q = 0; q < 2; ++q) {
                 pp.R.A[q] = ws.A[q].p + off; pp.R.B[q] = ws.B[q].p + off; pp.R.C[q] = ws.C[q].p + off; pp.R.D[q] = ws.D[q].p + off;
                 pp.R.Tm[q] = sc.has_animation ? ws.Tm[q].p + off : nullptr;
@@ -920,6 +962,7 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
             pp.R.ctr = ws.ctr.p + p;
             pp.st = ws.pipe_stream[p];
             pp.R.iter_log = iter_log_path ? ws.iter_log.p + (size_t)p * Workspace::ITER_LOG_CAP * 8 : nullptr;
+            pp.R.long_rays = long_rays_path ? ws.long_rays.p : nullptr;
             off += pp.R.cap;
         }
     }
@@ -967,8 +1010,12 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
         k_generate<<<ggrid, 256, 0, pp.st>>>(sc.dev, pp.R);
         ++launches;
     }
-    // a track renders ceil(n_local / J) lanes, each up to spp_whole + 1 samples of at most max_depth segments
-    const uint64_t max_iters = (uint64_t)((pl.n_local + J - 1) / J) * (uint64_t)(R.spp_whole + 1u) * (uint64_t)std::max(R.max_depth, 1) + 4 + 2 * (uint64_t)chunk;
+    // a chain takes at most (spp_whole + 1) samples x max_depth segments (x 2: k_shade may send a segment back once, to be traced again
+    // on the reference tree); while chains are left every slot advances one every iteration
+    uint64_t max_iters = 0;
+    for (const Pipe& pp : pipes)
+        max_iters = std::max<uint64_t>(max_iters, ((pp.R.n_chains + pp.R.cap - 1) / pp.R.cap + 1) * (uint64_t)(R.spp_whole + 1u) * 2ull * (uint64_t)std::max(R.max_depth, 1));
+    max_iters += 4 + 2 * (uint64_t)chunk;
     // The host never knows the live-path count of the iteration it is launching: kernels read it from device memory
     // (grids are persistent, sized by the SM count).  Every `chunk` iterations the counters are copied to pinned memory;
     // the host keeps one chunk in flight per pipeline while it waits for the previous chunk's copy.
@@ -1045,6 +1092,20 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
     drain.armed = false;
     float ms = 0.0f;
     CU(cudaEventElapsedTime(&ms, ws.ev0, ws.ev1));
+    if (long_rays_path) {
+        std::vector<float> lr(4096 * 8);
+        CU(cudaMemcpy(lr.data(), ws.long_rays.p, lr.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        uint32_t cnt;
+        std::memcpy(&cnt, lr.data(), 4);
+        if (FILE* f = std::fopen(long_rays_path, "w")) {
+            std::fprintf(f, "ox,oy,oz,dx,dy,dz,rounds,on_reference_tree\n");
+            for (uint32_t i = 0; i < std::min(cnt, 4095u); ++i) {
+                const float* r = &lr[8 * (i + 1)];
+                std::fprintf(f, "%.9g,%.9g,%.9g,%.9g,%.9g,%.9g,%.0f,%.0f\n", r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+            }
+            std::fclose(f);
+        }
+    }
     if (iter_log_path) {
         std::vector<uint32_t> lg((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP * 8);
         CU(cudaMemcpy(lg.data(), ws.iter_log.p, lg.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -1067,11 +1128,17 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
         total.rays += pp.final_ctr->rays; total.paths += pp.final_ctr->paths;
         total.node_visits += pp.final_ctr->node_visits; total.prim_tests += pp.final_ctr->prim_tests; total.exact_steps += pp.final_ctr->exact_steps;
         total.redo_total += pp.final_ctr->redo_total;
+        total.ref_rounds += pp.final_ctr->ref_rounds; total.ref_lanes += pp.final_ctr->ref_lanes;
+        total.tail_rounds += pp.final_ctr->tail_rounds; total.tail_busy_lanes += pp.final_ctr->tail_busy_lanes;
         total.rounds += pp.final_ctr->rounds; total.busy_lanes += pp.final_ctr->busy_lanes;
         total.max_sp = std::max(total.max_sp, pp.final_ctr->max_sp);
         for (int h = 0; h < 24; ++h) total.hist[h] += pp.final_ctr->hist[h];
         iters = std::max(iters, pp.iters);
     }
+    if (O.count && std::getenv("RT_TAIL_LOG"))
+        std::fprintf(stderr, "[rt_render] warp rounds %llu (lanes holding a ray %.2f), after the queue ran dry %llu (%.2f lanes), with >= 1 lane on the reference tree %llu (%.2f such lanes), redo rays %llu of %llu\n",
+                     total.rounds, total.rounds ? (double)total.busy_lanes / total.rounds : 0.0, total.tail_rounds, total.tail_rounds ? (double)total.tail_busy_lanes / total.tail_rounds : 0.0,
+                     total.ref_rounds, total.ref_rounds ? (double)total.ref_lanes / total.ref_rounds : 0.0, total.redo_total, total.rays);
     if (stats) {
         stats->ray_segments = total.rays;
         stats->paths = total.paths;
@@ -1086,7 +1153,7 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
         stats->redo_rays = total.redo_total;
         stats->max_stack = total.max_sp;
         stats->stack_capacity = sc.dev.stack_cap;
-        stats->tracks = J;
+        stats->slots = (uint32_t)pl.slots;
         stats->pipes = (uint32_t)G;
         stats->warp_rounds = total.rounds; stats->busy_lane_rounds = total.busy_lanes;
         for (int h = 0; h < 24; ++h) stats->rounds_hist[h] = total.hist[h];
@@ -1122,6 +1189,34 @@ static int guarded(F&& body) {
     }
 }
 
+// Device -> pageable host copy through the workspace's pinned staging chunks (the caller holds ws.mu and has synchronised the
+// producer of `d_src`).  A plain cudaMemcpy into pageable memory ran at 1.5 GB/s here (16 ms for a 1920x1080 film, 64 ms at 4K).
+static int download_staged(Workspace& ws, void* dst, const void* d_src, size_t bytes) {
+    if (!ws.h_stage[0]) {
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaMallocHost(&ws.h_stage[b], Workspace::STAGE_BYTES));
+            CU(cudaEventCreateWithFlags(&ws.stage_event[b], cudaEventDisableTiming));
+        }
+        CU(cudaStreamCreateWithFlags(&ws.copy_stream, cudaStreamNonBlocking));
+    }
+    const size_t C = Workspace::STAGE_BYTES;
+    const size_t n_chunks = (bytes + C - 1) / C;
+    auto issue = [&](size_t i) -> int {
+        const size_t off = i * C, len = std::min(C, bytes - off);
+        CU(cudaMemcpyAsync(ws.h_stage[i & 1], static_cast<const char*>(d_src) + off, len, cudaMemcpyDeviceToHost, ws.copy_stream));
+        CU(cudaEventRecord(ws.stage_event[i & 1], ws.copy_stream));
+        return RT_OK;
+    };
+    if (n_chunks) { int rc = issue(0); if (rc) return rc; }
+    for (size_t i = 0; i < n_chunks; ++i) {
+        if (i + 1 < n_chunks) { int rc = issue(i + 1); if (rc) { cudaStreamSynchronize(ws.copy_stream); return rc; } }
+        CU(cudaEventSynchronize(ws.stage_event[i & 1]));
+        const size_t off = i * C, len = std::min(C, bytes - off);
+        std::memcpy(static_cast<char*>(dst) + off, ws.h_stage[i & 1], len);
+    }
+    return RT_OK;
+}
+
 extern "C" {
 
 const char* rt_last_error(void) { return g_err.c_str(); }
@@ -1144,6 +1239,7 @@ int rt_set_option(const char* key, int64_t value) {
     else if (k == "rebuild_depth_extra") g_opt_rebuild_depth_extra = (int)value;
     else if (k == "profile") g_opt_profile = (int)value;
     else if (k == "count") g_opt_count = (int)value;
+    else if (k == "debug_skip_redo") g_opt_debug_skip_redo = (int)value;
     else if (k == "refill") g_opt_refill = (int)value;
     else if (k == "leaf_weight") g_opt_leaf_weight = (int)value;
     else if (k == "pipes") g_opt_pipes = (int)value;
@@ -1157,9 +1253,13 @@ int rt_set_option(const char* key, int64_t value) {
 int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene) {
     if (!desc || !out_scene) return fail(RT_EINVAL, "NULL argument");
     *out_scene = nullptr;
-    int count = 0;
-    CU(cudaGetDeviceCount(&count));
-    if (device < 0 || device >= count) return fail(RT_ECUDA, "CUDA device ordinal out of range (no CPU fallback exists)");
+    // RT_PACK_DRYRUN (profiling of the host phases on a box without a GPU, together with RT_PACK_LOG): the device check is skipped
+    // and the call fails at the upload instead
+    if (!std::getenv("RT_PACK_DRYRUN")) {
+        int count = 0;
+        CU(cudaGetDeviceCount(&count));
+        if (device < 0 || device >= count) return fail(RT_ECUDA, "CUDA device ordinal out of range (no CPU fallback exists)");
+    }
     RtScene* sc = new (std::nothrow) RtScene();
     if (!sc) return fail(RT_ENOMEM, "out of host memory");
     sc->device = device;
@@ -1274,8 +1374,7 @@ int rt_render(RtScene* scene, const RtRenderParams* params, float* out_rgb, RtSt
         }
         rc = render_locked(*scene, ws, O, pl, ws.film.p, true, nullptr, true, nullptr, out_stats);
         if (rc) return rc;
-        CU(cudaMemcpy(out_rgb, ws.film.p, n * sizeof(float), cudaMemcpyDeviceToHost));
-        return RT_OK;
+        return download_staged(ws, out_rgb, ws.film.p, n * sizeof(float));  // render_locked has synchronised the render
     });
 }
 
@@ -1369,10 +1468,13 @@ static int render_multi_impl(RtScene* const* scenes, int n, const RtRenderParams
             const int grid = (int)std::min<size_t>(((size_t)(p1 - p0) + 255) / 256, (size_t)scenes[g]->sm_count * 8);
             k_merge_peers<<<grid, 256, 0, st>>>(pp, plans[g].R, p0, p1, 1.0f / (float)plans[g].n_tasks);
             CU(cudaGetLastError());
-            if (out_rgb) CU(cudaMemcpyAsync(out_rgb + 3 * (size_t)p0, ws.film.p + 3 * (size_t)p0, (size_t)(p1 - p0) * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
         CU(cudaEventRecord(ws.ev1, st));
         CU(cudaEventSynchronize(ws.ev1));
+        if (out_rgb && p1 > p0) {  // every GPU downloads its own slice through its own pinned staging chunks, in parallel
+            int r = download_staged(ws, out_rgb + 3 * (size_t)p0, ws.film.p + 3 * (size_t)p0, (size_t)(p1 - p0) * 3 * sizeof(float));
+            if (r) return r;
+        }
         CU(cudaEventElapsedTime(&merge_ms[g], ws.ev0, ws.ev1));
         return RT_OK;
     });
@@ -1409,8 +1511,13 @@ int rt_shutdown(void) {
         if (cudaSetDevice(kv.first) != cudaSuccess) { cudaGetLastError(); continue; }
         cudaDeviceSynchronize();
         release_workspace_queues(*w);
-        w->ctr.release(); w->film.release(); w->sumsq.release(); w->iter_log.release();
+        w->ctr.release(); w->film.release(); w->sumsq.release(); w->iter_log.release(); w->long_rays.release();
         if (w->h_ctr) { cudaFreeHost(w->h_ctr); w->h_ctr = nullptr; }
+        for (int b = 0; b < 2; ++b) {
+            if (w->h_stage[b]) { cudaFreeHost(w->h_stage[b]); w->h_stage[b] = nullptr; }
+            if (w->stage_event[b]) { cudaEventDestroy(w->stage_event[b]); w->stage_event[b] = nullptr; }
+        }
+        if (w->copy_stream) { cudaStreamDestroy(w->copy_stream); w->copy_stream = nullptr; }
         for (int p = 0; p < Workspace::MAX_PIPES; ++p) {
             if (w->pipe_stream[p]) { cudaStreamDestroy(w->pipe_stream[p]); w->pipe_stream[p] = nullptr; }
             if (w->join_event[p]) { cudaEventDestroy(w->join_event[p]); w->join_event[p] = nullptr; }

@@ -85,14 +85,17 @@ struct SceneDev {
     float root_min[3], root_max[3];
     uint32_t stack_cap;       // traversal stack entries per thread
     uint32_t root_margin;     // guard band of the root box test (packed like NodeDev.q3.w)
-    const float4* own_box;    // [2*n_nodes] each node's own AABB (min.xyz,0 | max.xyz,0): only read on exact-tie pops
+    const float4* own_box;    // [2*n_nodes] each node's own AABB (min.xyz, bits(parent node | 0xFFFFFFFF for the root) | max.xyz, 0): read on
+                              // exact-tie pops and by the ancestor walks (ref_reaches_exact, ref_first_visited)
     const WrapDev* wraps;     // [n_items] or NULL when no item is wrapped
     // Row f4 (rt_rebuild.hpp): the rebuilt topology over the same elements; NULL when the scene has wrapped elements
     const NodeDev* nodes2;    // same 64 B record; q3.z unused (children are visited near-first)
     uint32_t root2;
-    const float4* vis_box;    // [2*n_items] box of the element's parent in the REFERENCE tree (min.xyz,0 | max.xyz,0)
+    const float4* vis_box;    // [2*n_items] box of the element's parent in the REFERENCE tree (min.xyz, bits(parent node) | max.xyz, 0)
     uint32_t fast_trace_ok;   // rt_trace may use the rebuilt tree (0 when the scene has Animation leaves: the tree's boxes only
                               // cover the camera's shutter interval, rt_trace takes any ray time)
+    const uint32_t* visit_rank;  // [8][n_items] position of each element in the reference's ordered DFS for the 8 direction-sign octants
+                              // (bit i = d_i > 0), or NULL: equal-t ties between elements are then resolved on the reference tree
     float trace_time;         // Ray::time of rt_trace rays
     CameraDev cam;
     uint32_t bg_is_sky;
@@ -491,7 +494,7 @@ __device__ __forceinline__ float padded_exit_bound(float h, float i, float a, fl
 }
 struct PadRay {  // the ray fields padded_cull needs, by value (the function is deliberately not inlined: it is the rare path)
     float3 inv, oinv;
-    float start, end, oe;
+    float start, end;
 };
 __device__ __noinline__ float padded_cull_impl(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, PadRay T, uint32_t packed) {
     const float a = __uint_as_float(packed & 0xFFFF0000u), c = __uint_as_float(packed << 16);
@@ -505,8 +508,12 @@ __device__ __noinline__ float padded_cull_impl(float mnx, float mny, float mnz, 
     te = fminf(te, padded_exit_bound(hy, iy, a, c, T.start));
     te = fminf(te, padded_exit_bound(hz, iz, a, c, T.start));
     const float eps_e = __fmaf_rn(te, __fmaf_rn(c, te, 1e-5f), a);  // inf / NaN when te = inf: fmaxf / fminf then drop the padded terms
-    // error of an approximate slab distance: T.oe (absolute part, already doubled) + 1e-6 relative (>= 8 ulp)
-    const float px = __fmaf_rn(eps_e, ix, T.oe), py = __fmaf_rn(eps_e, iy, T.oe), pz = __fmaf_rn(eps_e, iz, T.oe);
+    // error of an approximate slab distance ON ITS OWN AXIS: absolute part 2.4e-7 |o_i / d_i| (4x the bound eps |o_i / d_i|, trav_setup)
+    // + 1e-6 relative (>= 8 ulp).  The scalar T.oe (the max over the axes) would pad every axis with the error of the worst one: for a
+    // ray nearly parallel to an axis (|d_y| ~ 1e-8: |o_y / d_y| ~ 1e8, T.oe ~ 50) the x and z intervals would grow by +-50 in t and
+    // the ray would walk every box that straddles its plane — 30 000 - 47 000 rounds, a whole launch waiting for one ray.
+    const float oex = 2.4e-7f * fabsf(T.oinv.x), oey = 2.4e-7f * fabsf(T.oinv.y), oez = 2.4e-7f * fabsf(T.oinv.z);
+    const float px = __fmaf_rn(eps_e, ix, oex), py = __fmaf_rn(eps_e, iy, oey), pz = __fmaf_rn(eps_e, iz, oez);
     const float nx = lx - __fmaf_rn(RT_BAND, fabsf(lx), px), ny = ly - __fmaf_rn(RT_BAND, fabsf(ly), py), nz = lz - __fmaf_rn(RT_BAND, fabsf(lz), pz);
     const float fx = hx + __fmaf_rn(RT_BAND, fabsf(hx), px), fy = hy + __fmaf_rn(RT_BAND, fabsf(hy), py), fz = hz + __fmaf_rn(RT_BAND, fabsf(hz), pz);
     const float tn_pad = fmaxf(fmaxf(nx, ny), fmaxf(nz, T.start));
@@ -516,7 +523,7 @@ __device__ __noinline__ float padded_cull_impl(float mnx, float mny, float mnz, 
 __device__ __forceinline__ bool padded_cull(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const Trav& T,
                                             uint32_t packed, float& tn_pad) {
     PadRay r;
-    r.inv = T.inv; r.oinv = T.oinv; r.start = T.start; r.end = T.end; r.oe = T.oe;
+    r.inv = T.inv; r.oinv = T.oinv; r.start = T.start; r.end = T.end;
     tn_pad = padded_cull_impl(mnx, mny, mnz, mxx, mxy, mxz, r, packed);
     return tn_pad == __int_as_float(0x7f800000);
 }
@@ -685,7 +692,21 @@ __device__ __forceinline__ bool trav_round_fast(const SceneDev& S, Trav& T, bool
             if (hit) {
                 if (have && t == T.end) {
                     // the same element can sit in several leaves (pre-split references): seeing it again is not a tie
-                    if (((cur ^ T.best) & RT_REF_ITEM_MASK) != 0u) T.dpos |= RT_TIE_BIT;
+                    if (((cur ^ T.best) & RT_REF_ITEM_MASK) != 0u) {
+                        // Two elements accept exactly the same t (coplanar overlapping triangles: the Q4 fan of an OBJ mesh puts
+                        // hundreds of them into the mesh's symmetry plane).  The reference keeps the one it visits FIRST (the later
+                        // one fails t < end), and its visit order for this ray is fixed by the tree and the signs of the direction
+                        // alone: every node visits the side dir[axis_id] > 0 picks first (hittable.rs:441-445).  S.visit_rank holds
+                        // each element's position in that order for the 8 sign octants, so plain scenes resolve the tie right here
+                        // with two loads; with wrapped elements / volumes (a volume accepts t <= end, so a LATER equal-t volume
+                        // wins) the ray is flagged and traced again on the reference tree.
+                        if (KEYFN::FEAT == 0 && S.visit_rank) {
+                            const uint32_t* rk = S.visit_rank + (size_t)(T.dpos & 7u) * S.n_items;
+                            if (__ldg(rk + (cur & RT_REF_ITEM_MASK)) < __ldg(rk + (T.best & RT_REF_ITEM_MASK))) T.best = cur;
+                        } else {
+                            T.dpos |= RT_TIE_BIT;
+                        }
+                    }
                 } else {
                     T.best = cur; T.end = t; T.dpos &= ~RT_TIE_BIT;
                 }
@@ -771,6 +792,33 @@ __device__ __forceinline__ bool ref_visible(const SceneDev& S, uint32_t ref, flo
            (pz - lo.z > c * (fabsf(lo.z) + sz)) && (hi.z - pz > c * (fabsf(hi.z) + sz));
 }
 
+// The exact form of the same proof, for the few hits (~5e-4 of the rays) the margins above cannot decide: walk the element's
+// ancestors in the reference tree and evaluate, with the reference's own arithmetic (slab_axis: true IEEE divisions), whether
+// t0_i <= t < t1_i on every axis of every ancestor box.  Given that t is the unique minimum over all elements, the reference's
+// range end e is > t whenever it reaches an ancestor (e is inf or another element's accepted t), so min(t1_i, e) > t >=
+// max(t0_i, start): Aabb::hit_cond (aabb.rs:65-78) passes for the whole chain, the element is reached and tested with a range
+// that contains t, and it wins.  ~20 levels x 6 divisions instead of a second traversal on the reference tree (~300 rounds that
+// the whole warp has to step through).  NaN (0/0) compares false: not proven.  A failure proves nothing: the ray is traced again.
+__device__ __noinline__ bool ref_reaches_exact(const SceneDev& S, uint32_t ref, float3 o, float3 d, float t) {
+    uint32_t node = __float_as_uint(__ldg(S.vis_box + 2u * (ref & RT_REF_ITEM_MASK)).w);
+    for (uint32_t level = 0; level < 8192u; ++level) {
+        if (node == 0xFFFFFFFFu) return true;  // walked past the root
+        const float4 lo = __ldg(S.own_box + 2u * node), hi = __ldg(S.own_box + 2u * node + 1u);
+        float t0, t1;
+        slab_axis(lo.x, hi.x, o.x, d.x, t0, t1);
+        if (!(t0 <= t && t < t1)) return false;
+        slab_axis(lo.y, hi.y, o.y, d.y, t0, t1);
+        if (!(t0 <= t && t < t1)) return false;
+        slab_axis(lo.z, hi.z, o.z, d.z, t0, t1);
+        if (!(t0 <= t && t < t1)) return false;
+        node = __float_as_uint(lo.w);
+    }
+    return false;
+}
+__device__ __forceinline__ bool ref_proven(const SceneDev& S, uint32_t ref, float3 o, float3 d, float t) {
+    return ref_visible(S, ref, o, d, t) || ref_reaches_exact(S, ref, o, d, t);
+}
+
 template <int MODE, bool COUNT, class KEYFN>
 __device__ __forceinline__ bool trav_step(const SceneDev& S, Trav& T, uint2* stk, uint32_t stk_stride,
                                           TravCount* cnt, const KEYFN& keyfn) {
@@ -808,7 +856,7 @@ __device__ __forceinline__ HitRec traverse_fast(const SceneDev& S, float3 o, flo
     while (trav_round_fast<false>(S, T, (T.cur & RT_REF_LEAF) != 0u, stk, stk_stride, nullptr, keyfn)) {}
     best.ref = T.best;
     best.t = T.end;
-    *proven = T.best == RT_NO_HIT || (!(T.dpos & RT_TIE_BIT) && ref_visible(S, T.best, o, d, T.end));
+    *proven = T.best == RT_NO_HIT || (!(T.dpos & RT_TIE_BIT) && ref_proven(S, T.best, o, d, T.end));
     return best;
 }
 

@@ -16,10 +16,12 @@ struct Counters {
     uint32_t nn[2];         // live regenerated (primary) paths in queue 0 / 1: positions cap-1 .. cap-nn (descending)
     uint32_t cursor_extend; // dynamic work fetch
     uint32_t pad;
+    unsigned long long next_chain;  // next (lane, pixel) chain of this pipeline to hand to a slot whose chain has ended
     unsigned long long rays;   // closest-hit queries so far
     unsigned long long paths;  // camera samples generated so far
     unsigned long long node_visits, prim_tests, exact_steps;  // only maintained by the COUNT kernel variant
     unsigned long long rounds, busy_lanes, tail_rounds, tail_busy_lanes;  // COUNT: warp rounds / busy lanes, overall and after the queue ran dry
+    unsigned long long ref_rounds, ref_lanes;  // COUNT: warp rounds in which >= 1 lane traced on the reference tree, and those lanes
     unsigned long long redo_total;     // row f4 (COUNT variant): rays the fast traversal could not prove -> reference traversal
     uint32_t max_sp, pad2;             // COUNT variant: deepest traversal stack use of any ray
     unsigned long long hist[24];       // COUNT variant: rays by floor(log2(rounds the ray took)) — the per-launch tail
@@ -36,9 +38,13 @@ struct RenderDev {
                     // exclusive owner: the single live path of the track that currently renders that lane
     Counters* ctr;
     uint32_t cap;            // queue capacity = number of path slots of THIS pipeline
-    uint32_t n_tracks;       // paths in flight per pixel on this rank: track j renders local lanes j, j + n_tracks, ... one after
-                             // the other (a lane's samples stay sequential, so every per-lane sum keeps the reference's order)
+    unsigned long long n_chains;  // chains of this pipeline.  A chain = all samples of one (lane, pixel), rendered one after the other by
+                             // ONE slot (so every per-lane sum keeps the reference's order); chain c = (pixel c % npix, the pipeline's
+                             // (c / npix)-th lane).  A slot whose chain has ended takes the next chain from Counters::next_chain, so
+                             // every wavefront stays full until the chains run out, whatever the paths' lengths.
     uint32_t* iter_log;      // optional [max_iters]: live paths of each iteration (debug / per-launch accounting)
+    float* long_rays;        // optional (COUNT + RT_LONG_RAYS): [0] = count (as u32 bits), then 8 floats per ray that took >= 4096 rounds:
+                             // origin, direction, rounds, flags (1 = finished on the reference tree)
     uint32_t iter;           // iteration index of this launch (only used with iter_log)
     uint32_t pipe, n_pipes;  // rank-local lanes are dealt round-robin to n_pipes independent wavefront pipelines (streams)
     uint32_t refill_threshold;  // extend refills idle lanes when fewer than this many lanes are busy
@@ -51,10 +57,13 @@ struct RenderDev {
     uint32_t seed0, seed1;
     float sx, sy;            // 1/(w-1), 1/(h-1)   (size2i.rs:21-22; also the jitter scale, rendering.rs:132-138)
     uint32_t mode;
+    uint32_t debug_skip_redo;  // measurement only (rt_set_option("debug_skip_redo")): unproven fast-path results are kept — NOT the reference's result
     uint32_t ref_only;       // traversal MODE 0: the root gate must not apply the tight cull either
 };
 
 #define RT_ROOT_MISS 0x80000000u  // top bit of the per-path sample index: the ray fails the BVH root test (producer-side)
+#define RT_FORCE_REF 0x40000000u  // next bit: trace this segment on the reference tree (k_shade could not prove the fast-path hit)
+#define RT_K_MASK 0x3FFFFFFFu     // the sample index itself (make_plan caps the samples per lane at 2^30)
 
 __device__ __forceinline__ uint32_t lane_samples(const RenderDev& R, uint32_t lane_id) {
     return R.spp_whole + (lane_id < R.spp_rem ? 1u : 0u);
@@ -82,7 +91,7 @@ __device__ __forceinline__ void generate_path(const SceneDev& S, const RenderDev
 }
 
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R) {
-    const uint32_t n_slots = R.cap;  // this pipeline's tracks: track = pipe + n_pipes * i; a track starts with local lane m = track
+    const uint32_t n_slots = R.cap;  // slot j starts with chain j: pixel j % npix of the pipeline's (j / npix)-th lane (local lane m = pipe + n_pipes * that)
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_slots; j += gridDim.x * blockDim.x) {
         const uint32_t pixel = j % R.npix, track = R.pipe + R.n_pipes * (j / R.npix);
         const uint32_t lane_id = R.lane_first + track * R.lane_stride;
@@ -100,13 +109,14 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
         R.ctr->nb[0] = n_slots; R.ctr->nn[0] = 0;
         R.ctr->nb[1] = 0; R.ctr->nn[1] = 0;
         R.ctr->cursor_extend = 0;
+        R.ctr->next_chain = n_slots;
         R.ctr->rays = 0;
         R.ctr->paths = n_slots;
         R.ctr->node_visits = 0;
         R.ctr->prim_tests = 0;
         R.ctr->exact_steps = 0;
         R.ctr->rounds = 0; R.ctr->busy_lanes = 0; R.ctr->tail_rounds = 0; R.ctr->tail_busy_lanes = 0;
-        R.ctr->redo_total = 0; R.ctr->max_sp = 0;
+        R.ctr->redo_total = 0; R.ctr->max_sp = 0; R.ctr->ref_rounds = 0; R.ctr->ref_lanes = 0;
         for (int h = 0; h < 24; ++h) R.ctr->hist[h] = 0;
     }
 }
@@ -119,7 +129,7 @@ struct ExtendKey {
     int q;
     uint32_t pos;
     __device__ __forceinline__ VolKey operator()() const {
-        const uint32_t pixel = __float_as_uint(__ldcg(&R->A[q][pos].w)), k = __float_as_uint(__ldcg(&R->B[q][pos].w)) & ~RT_ROOT_MISS;
+        const uint32_t pixel = __float_as_uint(__ldcg(&R->A[q][pos].w)), k = __float_as_uint(__ldcg(&R->B[q][pos].w)) & RT_K_MASK;
         const int2 dm = __ldcg(&R->D[q][pos]);
         const uint32_t lane_id = R->lane_first + (uint32_t)dm.y * R->lane_stride;
         return VolKey{R->seed0, R->seed1, pixel, k * R->n_tasks + lane_id, 1u + (uint32_t)(R->max_depth - dm.x)};
@@ -158,7 +168,7 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
     uint32_t my_pos = 0;
     uint32_t batch_next = 0, batch_end = 0;  // warp-uniform: ray indices [batch_next, batch_end) already claimed by this warp
     uint32_t act_mask = 0;                   // warp-uniform ballot of `active`
-    unsigned long long rounds_c = 0, busy_c = 0, trounds_c = 0, tbusy_c = 0;
+    unsigned long long rounds_c = 0, busy_c = 0, trounds_c = 0, tbusy_c = 0, rrounds_c = 0, rlanes_c = 0;
     uint32_t my_rounds = 0;  // COUNT: scheduling rounds this lane's current ray has been active for
     for (;;) {
         // refill: idle lanes take rays from the warp's claimed batch (one atomic per 32 rays)
@@ -184,7 +194,8 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
                     active = true;
                     if (COUNT) my_rounds = 0;
                     if (MODE == 3) {
-                        if (!fast_eligible(T)) T.dpos |= RT_REFMODE_BIT;  // degenerate or near-axis-parallel direction: reference tree only
+                        // degenerate direction, or k_shade sent the segment back (fast-path hit not provable): reference tree only
+                        if (!fast_eligible(T) || (__float_as_uint(b.w) & RT_FORCE_REF)) T.dpos |= RT_REFMODE_BIT;
                         else trav_setup_fast(S, T);
                     }
                 }
@@ -195,6 +206,10 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
         if (act_mask == 0u) {
             if (exhausted && batch_next == batch_end) break;
             continue;
+        }
+        if (COUNT && MODE == 3) {
+            const uint32_t rm = __ballot_sync(FULL, active && (T.dpos & RT_REFMODE_BIT));
+            if (rm) { rrounds_c += 1u; rlanes_c += __popc(rm); }
         }
         if (COUNT && lane == 0) {
             rounds_c += 1u; busy_c += __popc(act_mask);
@@ -213,16 +228,29 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
                 more = trav_round<MODE, COUNT>(S, T, do_leaf, stk, blockDim.x, &tc, ExtendKey<FEAT>{&R, q, my_pos});
             }
             if (!more) {
-                if (MODE == 3 && !(T.dpos & RT_REFMODE_BIT) && T.best != RT_NO_HIT &&
-                    ((T.dpos & RT_TIE_BIT) || !ref_visible(S, T.best, T.o, T.d, T.end))) {
-                    // not proven: same ray again on the reference tree (the root test already passed in the producer)
+                if (MODE == 3 && !(T.dpos & RT_REFMODE_BIT) && T.best != RT_NO_HIT && (T.dpos & RT_TIE_BIT) && !R.debug_skip_redo) {
+                    // an equal-t tie the fast path could not resolve (scenes with wrapped elements / volumes): same ray again on the
+                    // reference tree, in place (the root test already passed in the producer)
                     T.best = RT_NO_HIT; T.end = INF; T.sp = 0; T.cur = S.root;
                     T.dpos = (T.d.x > 0.0f ? 1u : 0u) | (T.d.y > 0.0f ? 2u : 0u) | (T.d.z > 0.0f ? 4u : 0u) | RT_REFMODE_BIT;
                     if (COUNT) tc.redo++;
                 } else {
-                    R.hits[my_pos] = make_uint2(T.best, __float_as_uint(T.end));
+                    // A fast-path hit still has to be PROVEN to be the reference's result (ref_proven).  That proof runs in k_shade, where
+                    // all 32 lanes hold a hit, instead of here with the one or two lanes that finish in a given round (it was 5.5 % of
+                    // this kernel's instructions at 1.2 active lanes): the hit is stored without its leaf bit = "unverified".
+                    uint32_t out_ref = T.best;
+                    if (MODE == 3 && !(T.dpos & RT_REFMODE_BIT) && T.best != RT_NO_HIT && !R.debug_skip_redo) out_ref &= ~RT_REF_LEAF;
+                    R.hits[my_pos] = make_uint2(out_ref, __float_as_uint(T.end));
                     active = false;
                     if (COUNT) atomicAdd(&R.ctr->hist[min(23, 31 - __clz(max(my_rounds, 1u)))], 1ull);
+                    if (COUNT && R.long_rays && my_rounds >= 4096u) {
+                        const uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(R.long_rays), 1u);
+                        if (slot < 4095u) {
+                            float* lr = R.long_rays + 8u * (slot + 1u);
+                            lr[0] = T.o.x; lr[1] = T.o.y; lr[2] = T.o.z; lr[3] = T.d.x; lr[4] = T.d.y; lr[5] = T.d.z;
+                            lr[6] = (float)my_rounds; lr[7] = (MODE == 3 && (T.dpos & RT_REFMODE_BIT)) ? 1.0f : 0.0f;
+                        }
+                    }
                 }
             }
         }
@@ -244,32 +272,26 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
             atomicMax(&R.ctr->max_sp, tc.max_sp);
             atomicAdd(&R.ctr->rounds, rounds_c); atomicAdd(&R.ctr->busy_lanes, busy_c);
             atomicAdd(&R.ctr->tail_rounds, trounds_c); atomicAdd(&R.ctr->tail_busy_lanes, tbusy_c);
+            atomicAdd(&R.ctr->ref_rounds, rrounds_c); atomicAdd(&R.ctr->ref_lanes, rlanes_c);
         }
     }
 }
 
 // One bounce of ray_color (rendering.rs:25-68) for ONE path whose closest hit is `h`, including the accumulation of a terminated
-// sample and the regeneration of the slot's next sample (next sample of the lane, then the track's next lane).  Shared by the
-// wavefront k_shade and the persistent k_path.  Returns RT_PATH_* flags.
-#define RT_PATH_LIVE 1u      // P holds a path to trace next (continuing or fresh)
-#define RT_PATH_FRESH 2u     // ... and it is a new camera path
-#define RT_PATH_FINISHED 4u  // the slot has rendered its last sample (not live)
+// sample.  Returns true when the path continues (P then holds the scattered ray), false when the sample has ended.
 struct PathIO {
     float3 o, d, thr;
     float dy0, time;
-    uint32_t slot, k, m;
+    uint32_t pixel, k, m;
     int32_t depth;
 };
-__device__ __forceinline__ uint32_t shade_path(const SceneDev& S, const RenderDev& R, PathIO& P, const uint2 h) {
+__device__ __forceinline__ bool shade_path(const SceneDev& S, const RenderDev& R, PathIO& P, const uint2 h) {
     float3 o = P.o, d = P.d, thr = P.thr;
-    float dy0 = P.dy0, time = P.time;
-    const uint32_t slot = P.slot;
-    uint32_t k = P.k, m = P.m;
+    const float dy0 = P.dy0, time = P.time;
+    const uint32_t k = P.k, m = P.m;
     int32_t depth = P.depth;
-    bool live = false, fresh = false;
-    uint32_t new_paths = 0;
-    const uint32_t pixel = slot;  // the path carries its pixel (an integer modulo here was 4 % of the shade kernel's instructions and 13 % of its stalls)
-    uint32_t lane_id = R.lane_first + m * R.lane_stride;
+    const uint32_t pixel = P.pixel;  // the path carries its pixel (an integer modulo here was 4 % of the shade kernel's instructions and 13 % of its stalls)
+    const uint32_t lane_id = R.lane_first + m * R.lane_stride;
     const float t = __uint_as_float(h.y);
     float3 radiance = f3(0.0f, 0.0f, 0.0f);
     bool terminated = true;
@@ -407,7 +429,6 @@ __device__ __forceinline__ uint32_t shade_path(const SceneDev& S, const RenderDe
             d = ndir;
             depth -= 1;
             terminated = false;
-            live = true;
         } else {
             radiance = f3(0.0f + thr.x * emitted.x, 0.0f + thr.y * emitted.y, 0.0f + thr.z * emitted.z);  // :62-64
         }
@@ -418,28 +439,9 @@ __device__ __forceinline__ uint32_t shade_path(const SceneDev& S, const RenderDe
         s.x += radiance.x; s.y += radiance.y; s.z += radiance.z;
         s.w += radiance.x * radiance.x + radiance.y * radiance.y + radiance.z * radiance.z;  // second moment (RMSE bound)
         __stcg(ap, s);
-        // regenerate in place: next sample of this (pixel, lane), then the track's next lane
-        bool more = true;
-        if (k + 1u < lane_samples(R, lane_id)) {
-            k += 1u;
-        } else {
-            m += R.n_tracks; k = 0u;
-            lane_id = R.lane_first + m * R.lane_stride;
-            more = m < R.n_local_lanes;
-        }
-        if (more) {
-            generate_path(S, R, pixel, lane_id, k, o, d, time);
-            thr = f3(1.0f, 1.0f, 1.0f);
-            dy0 = d.y;
-            depth = R.max_depth;
-            live = true;
-            fresh = true;
-            new_paths += 1u;
-        }
     }
-    P.o = o; P.d = d; P.thr = thr; P.dy0 = dy0; P.time = time; P.k = k; P.m = m; P.depth = depth;
-    (void)new_paths;
-    return (live ? RT_PATH_LIVE : 0u) | (fresh ? RT_PATH_FRESH : 0u) | ((terminated && !live) ? RT_PATH_FINISHED : 0u);
+    P.o = o; P.d = d; P.thr = thr; P.depth = depth;
+    return !terminated;
 }
 
 // One bounce of ray_color for every live path of queue `q`; survivors (and regenerated paths) are compacted
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(128, 6) k_shade(const __grid_constant__ SceneD
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         R.ctr->cursor_extend = 0;
-        R.ctr->rays += n;
+        atomicAdd(&R.ctr->rays, (unsigned long long)n);
         if (R.iter_log) {  // [iter] live paths, [CAP + 2 iter] cumulative node visits (lo/hi), [3 CAP + 2 iter] cumulative prim tests
             R.iter_log[R.iter] = n;
             R.iter_log[16384u + R.iter] = (uint32_t)(R.ctr->node_visits >> 6);
@@ -466,27 +468,69 @@ __global__ void __launch_bounds__(128, 6) k_shade(const __grid_constant__ SceneD
     for (uint32_t base = warp_global * 32u; base < n; base += n_warps * 32u) {
         const uint32_t i = base + lane;
         const uint32_t ipos = queue_pos(i, nb, R.cap);
-        bool live = false, fresh = false;
-        float3 o = f3(0, 0, 0), d = f3(0, 0, 1), thr = f3(1, 1, 1);
-        float dy0 = 0.0f, time = 0.0f;
-        uint32_t slot = 0, k = 0, m = 0;
-        int32_t depth = 0;
+        bool live = false, fresh = false, ended = false, again = false;
+        PathIO P;
+        P.o = f3(0, 0, 0); P.d = f3(0, 0, 1); P.thr = f3(1, 1, 1);
+        P.dy0 = 0.0f; P.time = 0.0f; P.pixel = 0; P.k = 0; P.m = 0; P.depth = 0;
         if (i < n) {
-            float4 a = R.A[q][ipos], b = R.B[q][ipos], c = R.C[q][ipos];
+            const float4 a = R.A[q][ipos], b = R.B[q][ipos], c = R.C[q][ipos];
             const int2 dm = R.D[q][ipos];
-            depth = dm.x; m = (uint32_t)dm.y;
-            time = R.Tm[q] ? R.Tm[q][ipos] : 0.0f;
-            uint2 h = R.hits[ipos];
-            o = f3(a.x, a.y, a.z); d = f3(b.x, b.y, b.z); thr = f3(c.x, c.y, c.z);
-            dy0 = c.w;
-            slot = __float_as_uint(a.w);
-            k = __float_as_uint(b.w) & ~RT_ROOT_MISS;
-            PathIO P;
-            P.o = o; P.d = d; P.thr = thr; P.dy0 = dy0; P.time = time; P.slot = slot; P.k = k; P.m = m; P.depth = depth;
-            const uint32_t fl = shade_path(S, R, P, h);
-            o = P.o; d = P.d; thr = P.thr; dy0 = P.dy0; time = P.time; k = P.k; m = P.m; depth = P.depth;
-            live = (fl & RT_PATH_LIVE) != 0u; fresh = (fl & RT_PATH_FRESH) != 0u;
-            if (fresh) new_paths += 1u;
+            const uint2 h = R.hits[ipos];
+            P.depth = dm.x; P.m = (uint32_t)dm.y;
+            P.time = R.Tm[q] ? R.Tm[q][ipos] : 0.0f;
+            P.o = f3(a.x, a.y, a.z); P.d = f3(b.x, b.y, b.z); P.thr = f3(c.x, c.y, c.z);
+            P.dy0 = c.w;
+            P.pixel = __float_as_uint(a.w);
+            P.k = __float_as_uint(b.w) & RT_K_MASK;
+            uint2 hv = h;
+            if (hv.x != RT_NO_HIT && !(hv.x & RT_REF_LEAF)) {  // unverified fast-path hit (k_extend): prove it here, with the whole warp at work
+                hv.x |= RT_REF_LEAF;
+                if (!ref_proven(S, hv.x, P.o, P.d, __uint_as_float(hv.y))) again = true;
+            }
+            if (!again) {
+                live = shade_path(S, R, P, hv);
+                ended = !live;
+            } else {
+                // not provable (~1e-5 of the rays): the path goes back into the queue unchanged and this segment is traced again, on
+                // the reference tree; it is the same ray segment, so it is not counted twice
+                live = true;
+                atomicAdd(&R.ctr->rays, ~0ull);
+                atomicAdd(&R.ctr->redo_total, 1ull);
+            }
+        }
+        // A sample has ended: the slot renders the next sample of its chain, or, when the chain is complete, takes the next
+        // chain of the pipeline (one warp-aggregated atomic) — the wavefront stays full while chains are left.
+        const bool chain_done = ended && !(P.k + 1u < lane_samples(R, R.lane_first + P.m * R.lane_stride));
+        const uint32_t mchain = __ballot_sync(0xFFFFFFFFu, chain_done);
+        if (mchain) {
+            unsigned long long cbase = 0;
+            if (lane == 0) cbase = atomicAdd(&R.ctr->next_chain, (unsigned long long)__popc(mchain));
+            cbase = __shfl_sync(0xFFFFFFFFu, cbase, 0);
+            if (chain_done) {
+                const unsigned long long cid = cbase + __popc(mchain & ((1u << lane) - 1u));
+                if (cid < R.n_chains) {
+                    uint32_t lane_index;
+                    if (R.n_chains <= 0xFFFFFFFFull) {  // the usual case: 32-bit division
+                        lane_index = (uint32_t)cid / R.npix;
+                        P.pixel = (uint32_t)cid - lane_index * R.npix;
+                    } else {
+                        lane_index = (uint32_t)(cid / R.npix);
+                        P.pixel = (uint32_t)(cid - (unsigned long long)lane_index * R.npix);
+                    }
+                    P.m = R.pipe + R.n_pipes * lane_index;
+                    P.k = 0u;
+                    fresh = true;
+                }
+            }
+        }
+        if (ended && !chain_done) { P.k += 1u; fresh = true; }
+        if (fresh) {
+            generate_path(S, R, P.pixel, R.lane_first + P.m * R.lane_stride, P.k, P.o, P.d, P.time);
+            P.thr = f3(1.0f, 1.0f, 1.0f);
+            P.dy0 = P.d.y;
+            P.depth = R.max_depth;
+            live = true;
+            new_paths += 1u;
         }
         // warp-ballot compaction into the other queue: continuing paths from the bottom, fresh camera paths from the
         // top, so warps of the next extend hold either coherent primary rays or bounce rays, not a mix
@@ -501,14 +545,14 @@ __global__ void __launch_bounds__(128, 6) k_shade(const __grid_constant__ SceneD
             bc = __shfl_sync(0xFFFFFFFFu, bc, 0);
             bn = __shfl_sync(0xFFFFFFFFu, bn, 0);
             if (live) {
-                const uint32_t miss = root_gate(S, o, d, 0.001f, __int_as_float(0x7f800000), R.ref_only != 0u) ? 0u : RT_ROOT_MISS;
+                const uint32_t miss = root_gate(S, P.o, P.d, 0.001f, __int_as_float(0x7f800000), R.ref_only != 0u) ? 0u : RT_ROOT_MISS;
                 const uint32_t below = (1u << lane) - 1u;
                 const uint32_t pos = fresh ? R.cap - 1u - (bn + __popc(mnew & below)) : bc + __popc(mcont & below);
-                R.A[q ^ 1][pos] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
-                R.B[q ^ 1][pos] = make_float4(d.x, d.y, d.z, __uint_as_float(k | miss));
-                R.C[q ^ 1][pos] = make_float4(thr.x, thr.y, thr.z, dy0);
-                R.D[q ^ 1][pos] = make_int2(depth, (int)m);
-                if (R.Tm[q ^ 1]) R.Tm[q ^ 1][pos] = time;
+                R.A[q ^ 1][pos] = make_float4(P.o.x, P.o.y, P.o.z, __uint_as_float(P.pixel));
+                R.B[q ^ 1][pos] = make_float4(P.d.x, P.d.y, P.d.z, __uint_as_float(P.k | miss | (again ? RT_FORCE_REF : 0u)));
+                R.C[q ^ 1][pos] = make_float4(P.thr.x, P.thr.y, P.thr.z, P.dy0);
+                R.D[q ^ 1][pos] = make_int2(P.depth, (int)P.m);
+                if (R.Tm[q ^ 1]) R.Tm[q ^ 1][pos] = P.time;
             }
         }
     }

@@ -583,9 +583,9 @@ private:
 // render() — src/lib/rendering.rs:121-128.  Same arguments and result layout (W*H linear-RGB colours, row 0 = top);
 // `thread_count` keeps its role in the sample split (split_work_tasks, :222-237) and becomes the number of sample
 // lanes in flight per pixel on the GPU.  `seed` replaces the reference's OS-entropy seeding (:160).
-inline std::vector<Color> render(Size2i image_size, size_t thread_count, size_t samples_per_pixel, int32_t max_depth,
-                                 const World& world, RenderMode render_mode, uint64_t seed = 0x5EEDull, RtStats* stats = nullptr,
-                                 int device_ordinal = 0) {
+// render_into: the same call writing into a caller-owned buffer of image_size.count() colours (no allocation, no extra copy).
+inline void render_into(Size2i image_size, size_t thread_count, size_t samples_per_pixel, int32_t max_depth, const World& world,
+                        RenderMode render_mode, Color* out, uint64_t seed = 0x5EEDull, RtStats* stats = nullptr, int device_ordinal = 0) {
     RtRenderParams p{};
     p.width = image_size.width; p.height = image_size.height;
     p.samples_per_pixel = samples_per_pixel;
@@ -593,9 +593,14 @@ inline std::vector<Color> render(Size2i image_size, size_t thread_count, size_t 
     p.thread_count = (uint32_t)thread_count;
     p.render_mode = (uint32_t)render_mode;
     p.seed = seed;
-    std::vector<Color> out(image_size.count());
     static_assert(sizeof(Color) == 12, "Color must be 3 packed floats");
-    if (rt_render(world.device(device_ordinal), &p, reinterpret_cast<float*>(out.data()), stats) != RT_OK) throw_rt("rt_render");
+    if (rt_render(world.device(device_ordinal), &p, reinterpret_cast<float*>(out), stats) != RT_OK) throw_rt("rt_render");
+}
+inline std::vector<Color> render(Size2i image_size, size_t thread_count, size_t samples_per_pixel, int32_t max_depth,
+                                 const World& world, RenderMode render_mode, uint64_t seed = 0x5EEDull, RtStats* stats = nullptr,
+                                 int device_ordinal = 0) {
+    std::vector<Color> out(image_size.count());
+    render_into(image_size, thread_count, samples_per_pixel, max_depth, world, render_mode, out.data(), seed, stats, device_ordinal);
     return out;
 }
 

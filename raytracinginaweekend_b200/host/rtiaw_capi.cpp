@@ -204,8 +204,7 @@ int rtw_world_upload_bytes(const RtwWorld* w, uint64_t* out_bytes) {
 int rtw_render(RtwWorld* w, int32_t width, int32_t height, uint64_t thread_count, uint64_t spp, int32_t max_depth, uint32_t render_mode,
                uint64_t seed, int device, float* out_rgb, RtStats* out_stats) {
     return guard([&] {
-        std::vector<Color> px = render(Size2i{width, height}, thread_count, spp, max_depth, *w->world, (RenderMode)render_mode, seed, out_stats, device);
-        std::memcpy(out_rgb, px.data(), px.size() * sizeof(Color));
+        render_into(Size2i{width, height}, thread_count, spp, max_depth, *w->world, (RenderMode)render_mode, reinterpret_cast<Color*>(out_rgb), seed, out_stats, device);
     });
 }
 

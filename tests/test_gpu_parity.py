@@ -313,7 +313,8 @@ def test_traversal_variants_agree_at_full_size():
     _cabi.set_option("count", 1)      # the counting kernel variant reports how many rays were restarted on the reference tree
     c, sc = rb.render(size, 1, 1, 50, w, seed=11, return_stats=True)
     assert sc["ray_segments"] == sb["ray_segments"] and images_equal_bits(c, b)
-    assert 0 < sc["redo_rays"] < 0.05 * sc["ray_segments"], sc   # a few rays per cent need the reference tree; never zero on 3M rays
+    # rays restarted on the reference tree: only what neither the exact ancestor walk nor the visit-rank tie rule can decide
+    assert sc["redo_rays"] < 1e-4 * sc["ray_segments"], sc
 
 
 @pytest.mark.parametrize("name,size", [("config:c1", (600, 400)), ("config:c3", (256, 256)), ("config:c5", (240, 135)), ("demo:suzanne", (200, 150)),

@@ -17,6 +17,6 @@ for name in which:
                 _, st = rb.render(rb.Size2i(w, h), T, spp, 50, W, seed=3, return_stats=True)
                 if best is None or st["render_ms"] < best["render_ms"]:
                     best = st
-            print(json.dumps({"config": name, "max_slots_Mi": slots_m, "pipes": pipes, "tracks": best["tracks"], "Mrays_s": round(best["ray_segments"] / best["render_ms"] / 1e3, 1),
+            print(json.dumps({"config": name, "max_slots_Mi": slots_m, "pipes": pipes, "slots": best["slots"], "Mrays_s": round(best["ray_segments"] / best["render_ms"] / 1e3, 1),
                               "render_ms": round(best["render_ms"], 2), "iters": best["iterations"]}), flush=True)
     W.close()
