@@ -44,6 +44,7 @@ int g_opt_pipes = 0;         // independent wavefront pipelines (streams) per re
                               // 0 = auto: 2 for renders with >= 64 Mi path slots (throughput-bound), 4 below (launch-tail-bound)
 int g_opt_leaf_weight = 24;   // extend phase vote: leaf phase when n_leaf * w > n_node * 16
 int g_opt_refill = 28;        // extend refills idle lanes when fewer than this many of 32 are busy
+int g_opt_tail_budget = 64;   // rounds an extend warp keeps going after it can no longer refill, before it parks its rays (0 = never)
 int g_opt_debug_skip_redo = 0;  // measurement only: keep unproven fast-path results (films are then NOT the reference's)
 int g_opt_count = 0;        // 1 = COUNT kernel variant (node visits / primitive tests per ray)
 int g_opt_profile = 0;        // 1 = time every extend / shade launch with CUDA events on the launching stream (no extra syncs)
@@ -53,13 +54,13 @@ int64_t g_opt_max_slots = 160ll << 20;  // path slots in flight per render (boun
 
 struct Options {
     int traversal, presplit, rebuild_min_items, rebuild_wrapped, rebuild, rebuild_depth_extra, pipes, leaf_weight, refill, count, profile,
-        check_every, blocks_per_sm, debug_skip_redo;
+        check_every, blocks_per_sm, debug_skip_redo, tail_budget;
     int64_t max_slots;
 };
 Options options_snapshot() {
     std::lock_guard<std::mutex> lk(g_opt_mu);
     return Options{g_opt_traversal, g_opt_presplit, g_opt_rebuild_min_items, g_opt_rebuild_wrapped, g_opt_rebuild, g_opt_rebuild_depth_extra,
-                   g_opt_pipes, g_opt_leaf_weight, g_opt_refill, g_opt_count, g_opt_profile, g_opt_check_every, g_opt_blocks_per_sm, g_opt_debug_skip_redo,
+                   g_opt_pipes, g_opt_leaf_weight, g_opt_refill, g_opt_count, g_opt_profile, g_opt_check_every, g_opt_blocks_per_sm, g_opt_debug_skip_redo, g_opt_tail_budget,
                    g_opt_max_slots};
 }
 
@@ -117,9 +118,12 @@ struct Workspace {
     cudaEvent_t poll_event[MAX_PIPES][2] = {};
     cudaStream_t pipe_stream[MAX_PIPES] = {};
     cudaEvent_t fork_event = nullptr, join_event[MAX_PIPES] = {};
+    cudaStream_t resume_stream[MAX_PIPES] = {};  // RESUME launches of k_extend (parked traversals), beside the queue launch of the same pipeline
+    cudaEvent_t resume_fork[MAX_PIPES] = {}, resume_join[MAX_PIPES] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // render brackets (created once: no per-call create / destroy to leak on error paths)
     std::vector<cudaEvent_t> prof_events[MAX_PIPES];
     DevBuf<uint32_t> iter_log;  // [MAX_PIPES][ITER_LOG_CAP], only with RT_ITER_LOG set
+    DevBuf<uint2> susp;         // suspend pools of all pipelines: [pipe][2][susp_cap][4 + stack_cap]
     DevBuf<float> long_rays;    // 4096 x 8 floats, only with RT_LONG_RAYS set (debug: the rays that set a launch's tail)
     static const int ITER_LOG_CAP = 16384;
     size_t ws_slots = 0;
@@ -825,6 +829,11 @@ int ensure_workspace(Workspace& sc, size_t slots, size_t acc_elems, size_t npix,
         CU(cudaEventCreateWithFlags(&sc.fork_event, cudaEventDisableTiming));
         for (int p = 0; p < Workspace::MAX_PIPES; ++p) {
             CU(cudaStreamCreateWithFlags(&sc.pipe_stream[p], cudaStreamNonBlocking));
+            int prio_lo = 0, prio_hi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CU(cudaStreamCreateWithPriority(&sc.resume_stream[p], cudaStreamNonBlocking, prio_hi));
+            CU(cudaEventCreateWithFlags(&sc.resume_fork[p], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&sc.resume_join[p], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&sc.join_event[p], cudaEventDisableTiming));
             for (int b = 0; b < 2; ++b) CU(cudaEventCreate(&sc.poll_event[p][b]));
         }
@@ -834,13 +843,14 @@ int ensure_workspace(Workspace& sc, size_t slots, size_t acc_elems, size_t npix,
 
 // The wavefront loop.  Writes the (unscaled unless apply_scale) film into d_out.
 using ExtendFn = void (*)(SceneDev, RenderDev, int);
-template <int FEAT>
+template <int FEAT, bool RESUME>
 static ExtendFn pick_extend_feat(int mode, bool count) {
-    return count ? (mode == 2 ? k_extend<2, true, FEAT> : (mode == 1 ? k_extend<1, true, FEAT> : k_extend<0, true, FEAT>))
-                 : (mode == 2 ? k_extend<2, false, FEAT> : (mode == 1 ? k_extend<1, false, FEAT> : k_extend<0, false, FEAT>));
+    return count ? (mode == 3 ? k_extend<3, true, FEAT, RESUME> : (mode == 2 ? k_extend<2, true, FEAT, RESUME> : (mode == 1 ? k_extend<1, true, FEAT, RESUME> : k_extend<0, true, FEAT, RESUME>)))
+                 : (mode == 3 ? k_extend<3, false, FEAT, RESUME> : (mode == 2 ? k_extend<2, false, FEAT, RESUME> : (mode == 1 ? k_extend<1, false, FEAT, RESUME> : k_extend<0, false, FEAT, RESUME>)));
 }
+template <bool RESUME>
 static ExtendFn pick_extend(int mode, bool count, int feat) {
-    return feat == 2 ? pick_extend_feat<2>(mode, count) : (feat == 1 ? pick_extend_feat<1>(mode, count) : pick_extend_feat<0>(mode, count));
+    return feat == 2 ? pick_extend_feat<2, RESUME>(mode, count) : (feat == 1 ? pick_extend_feat<1, RESUME>(mode, count) : pick_extend_feat<0, RESUME>(mode, count));
 }
 
 // What one rank renders: validated parameters + the lane / track split.
@@ -859,7 +869,7 @@ int make_plan(const RtScene& sc, const Options& O, const RtRenderParams& P, uint
     if (lane_stride == 0) return fail(RT_EINVAL, "lane_stride must be >= 1");
     const uint64_t T = P.thread_count;
     pl.n_tasks = std::min<uint64_t>(T, P.samples_per_pixel);
-    if (P.samples_per_pixel / T + 1 > 0x3FFFFFFFull) return fail(RT_EINVAL, "too many samples per lane (2^30 at most)");
+    if (P.samples_per_pixel / T + 1 > 0x1FFFFFFFull) return fail(RT_EINVAL, "too many samples per lane (2^29 at most)");
     pl.npix = (size_t)P.width * P.height;
     if (pl.npix > 0x7FFFFFFFull) return fail(RT_EINVAL, "image too large");
     pl.n_local = lane_first >= pl.n_tasks ? 0u : (uint32_t)((pl.n_tasks - lane_first + lane_stride - 1) / lane_stride);
@@ -871,7 +881,7 @@ int make_plan(const RtScene& sc, const Options& O, const RtRenderParams& P, uint
         const uint64_t budget = (uint64_t)std::max<int64_t>(O.max_slots, 1);
         const uint64_t chains = (uint64_t)pl.n_local * pl.npix;
         pl.slots = (size_t)std::min<uint64_t>(chains, std::max<uint64_t>(budget, 4 * Workspace::MAX_PIPES));  // >= 1 slot for every pipeline
-        if (pl.slots > 0xFFFFFFF0ull) return fail(RT_EINVAL, "more than 2^32 path slots (lower max_slots)");
+        if (pl.slots > 0x7FFFFFF0ull) return fail(RT_EINVAL, "more than 2^31 path slots (lower max_slots)");
         pl.acc_elems = (size_t)pl.n_local * pl.npix;
     }
     RenderDev& R = pl.R;
@@ -887,6 +897,7 @@ int make_plan(const RtScene& sc, const Options& O, const RtRenderParams& P, uint
     R.mode = P.render_mode;
     R.ref_only = (O.traversal == 0 || !sc.boxes_are_bounds) ? 1u : 0u;
     R.debug_skip_redo = O.debug_skip_redo ? 1u : 0u;
+    R.tail_budget = (uint32_t)std::max(0, O.tail_budget);
     R.refill_threshold = (uint32_t)std::min(32, std::max(1, O.refill));
     R.leaf_weight = (uint32_t)std::max(1, O.leaf_weight);
     return RT_OK;
@@ -926,7 +937,7 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
     // counters.  A persistent extend launch ends with a tail in which a few very long rays keep a few warps busy; with two
     // pipelines in flight the other pipeline's blocks backfill the SMs during that tail (and during shade / launch gaps).
     const char* iter_log_path = std::getenv("RT_ITER_LOG");  // debug: dump (pipe, iteration, live paths, extend ms, shade ms)
-    if (iter_log_path && !ws.iter_log.p) CU(ws.iter_log.alloc((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP * 8));
+    if (iter_log_path && !ws.iter_log.p) CU(ws.iter_log.alloc((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP * 9));
     const char* long_rays_path = O.count ? std::getenv("RT_LONG_RAYS") : nullptr;  // debug: dump the rays that took >= 4096 traversal rounds
     if (long_rays_path) {
         if (!ws.long_rays.p) CU(ws.long_rays.alloc(4096 * 8));
@@ -944,6 +955,13 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
         const Counters* final_ctr = nullptr;
     };
     std::vector<Pipe> pipes(G);
+    // suspend pools (RenderDev::susp): two per pipeline, 1/64 of its slots (1 Ki .. 64 Ki entries) of 4 + stack_cap 8-byte words each
+    const uint32_t susp_stride = 4u + sc.dev.stack_cap;
+    const uint32_t susp_cap = R.tail_budget ? (uint32_t)std::min<size_t>(65536, std::max<size_t>(1024, pl.slots / (size_t)G / 64)) : 0u;
+    if (susp_cap) {
+        const size_t need = (size_t)G * 2 * susp_cap * susp_stride;
+        if (ws.susp.n < need && ws.susp.alloc(need) != cudaSuccess) { cudaGetLastError(); return fail(RT_ENOMEM, "suspend pool"); }
+    }
     {
         size_t off = 0;
         for (int p = 0; p < G; ++p) {
@@ -959,9 +977,11 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
                 pp.R.Tm[q] = sc.has_animation ? ws.Tm[q].p + off : nullptr;
             }
             pp.R.hits = ws.hits.p + off;
+            pp.R.susp_cap = susp_cap; pp.R.susp_stride = susp_stride;
+            for (int b = 0; b < 2; ++b) pp.R.susp[b] = susp_cap ? ws.susp.p + ((size_t)p * 2 + b) * susp_cap * susp_stride : nullptr;
             pp.R.ctr = ws.ctr.p + p;
             pp.st = ws.pipe_stream[p];
-            pp.R.iter_log = iter_log_path ? ws.iter_log.p + (size_t)p * Workspace::ITER_LOG_CAP * 8 : nullptr;
+            pp.R.iter_log = iter_log_path ? ws.iter_log.p + (size_t)p * Workspace::ITER_LOG_CAP * 9 : nullptr;
             pp.R.long_rays = long_rays_path ? ws.long_rays.p : nullptr;
             off += pp.R.cap;
         }
@@ -973,19 +993,26 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
         ~Drain() {
             if (!armed) return;
             for (Pipe& pp : pipes) cudaStreamSynchronize(pp.st);
+            cudaDeviceSynchronize();  // RESUME launches run on their own streams
             cudaGetLastError();
         }
     } drain{pipes};
 
     int egrid = 0, sgrid = 0;
-    ExtendFn ext = mode == 3 ? (feat == 2 ? (O.count ? k_extend<3, true, 2> : k_extend<3, false, 2>)
-                                          : (feat == 1 ? (O.count ? k_extend<3, true, 1> : k_extend<3, false, 1>)
-                                                       : (O.count ? k_extend<3, true, 0> : k_extend<3, false, 0>)))
-                             : pick_extend(mode, O.count != 0, feat);
+    ExtendFn ext = pick_extend<false>(mode, O.count != 0, feat);
+    ExtendFn ext_resume = pick_extend<true>(mode, O.count != 0, feat);  // the same kernel over the parked traversals (RenderDev::susp)
     rc = persistent_grid(sc, ext, eblock, esmem, &egrid, O.blocks_per_sm);
     if (rc) return rc;
     rc = persistent_grid(sc, k_shade, 128, 0, &sgrid, O.blocks_per_sm);
     if (rc) return rc;
+    int rgrid = 0;  // RESUME launch: one warp per 32 pool entries
+    if (susp_cap) {
+        int unused = 0;
+        rc = persistent_grid(sc, ext_resume, eblock, esmem, &unused, 0);  // sets the shared-memory attribute, checks that it fits
+        if (rc) return rc;
+        rgrid = (int)((susp_cap + 127u) / 128u);
+    }
+    for (Pipe& pp : pipes) pp.R.extend_warps = (uint32_t)egrid * (uint32_t)(eblock / 32);
 
     uint64_t launches = 0;
     double extend_ms = 0.0, shade_ms = 0.0;
@@ -1015,7 +1042,7 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
     uint64_t max_iters = 0;
     for (const Pipe& pp : pipes)
         max_iters = std::max<uint64_t>(max_iters, ((pp.R.n_chains + pp.R.cap - 1) / pp.R.cap + 1) * (uint64_t)(R.spp_whole + 1u) * 2ull * (uint64_t)std::max(R.max_depth, 1));
-    max_iters += 4 + 2 * (uint64_t)chunk;
+    max_iters = max_iters * 64 + 65536 + 2 * (uint64_t)chunk;  // parked traversals (tail_budget) stretch a segment over several iterations; a hang guard, not a tight bound
     // The host never knows the live-path count of the iteration it is launching: kernels read it from device memory
     // (grids are persistent, sized by the SM count).  Every `chunk` iterations the counters are copied to pinned memory;
     // the host keeps one chunk in flight per pipeline while it waits for the previous chunk's copy.
@@ -1025,8 +1052,16 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
             cudaEvent_t* pe = O.profile ? &ws.prof_events[p][(size_t)(buf * chunk + it) * 3] : nullptr;
             if (pe) CU(cudaEventRecord(pe[0], pp.st));
             pp.R.iter = (uint32_t)std::min<uint64_t>(pp.iters, Workspace::ITER_LOG_CAP - 1);
+            if (rgrid) {  // the parked traversals of the previous iteration resume beside the queue launch, on their own (high-priority) stream
+                CU(cudaEventRecord(ws.resume_fork[p], pp.st));
+                CU(cudaStreamWaitEvent(ws.resume_stream[p], ws.resume_fork[p], 0));
+                ext_resume<<<rgrid, eblock, esmem, ws.resume_stream[p]>>>(sc.dev, pp.R, pp.q);
+                CU(cudaEventRecord(ws.resume_join[p], ws.resume_stream[p]));
+                ++launches;
+            }
             ext<<<egrid, eblock, esmem, pp.st>>>(sc.dev, pp.R, pp.q);
             if (pe) CU(cudaEventRecord(pe[1], pp.st));
+            if (rgrid) CU(cudaStreamWaitEvent(pp.st, ws.resume_join[p], 0));
             k_shade<<<sgrid, 128, 0, pp.st>>>(sc.dev, pp.R, pp.q);
             if (pe) CU(cudaEventRecord(pe[2], pp.st));
             launches += 2;
@@ -1107,17 +1142,18 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
         }
     }
     if (iter_log_path) {
-        std::vector<uint32_t> lg((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP * 8);
+        std::vector<uint32_t> lg((size_t)Workspace::MAX_PIPES * Workspace::ITER_LOG_CAP * 9);
         CU(cudaMemcpy(lg.data(), ws.iter_log.p, lg.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         if (FILE* f = std::fopen(iter_log_path, "w")) {
-            std::fprintf(f, "pipe,iter,rays,extend_ms,shade_ms,cum_nodes_div64,cum_prims_div64,cum_rounds_div16,cum_busy_div256,cum_trounds_div16,cum_tbusy_div256\n");
+            std::fprintf(f, "pipe,iter,rays,extend_ms,shade_ms,cum_nodes_div64,cum_prims_div64,cum_rounds_div16,cum_busy_div256,cum_trounds_div16,cum_tbusy_div256,parked,budget\n");
             for (int p = 0; p < G; ++p)
                 for (size_t i = 0; i < pipes[p].iters && i < (size_t)Workspace::ITER_LOG_CAP; ++i) {
-                    const uint32_t* L = &lg[(size_t)p * Workspace::ITER_LOG_CAP * 8];
-                    std::fprintf(f, "%d,%zu,%u,%.4f,%.4f,%u,%u,%u,%u,%u,%u\n", p, i, L[i],
+                    const uint32_t* L = &lg[(size_t)p * Workspace::ITER_LOG_CAP * 9];
+                    std::fprintf(f, "%d,%zu,%u,%.4f,%.4f,%u,%u,%u,%u,%u,%u,%u,%u\n", p, i, L[i],
                                  i < iter_ms[p].size() ? iter_ms[p][i][0] : -1.0f, i < iter_ms[p].size() ? iter_ms[p][i][1] : -1.0f,
                                  L[Workspace::ITER_LOG_CAP + i], L[2 * Workspace::ITER_LOG_CAP + i], L[4 * Workspace::ITER_LOG_CAP + i],
-                                 L[5 * Workspace::ITER_LOG_CAP + i], L[6 * Workspace::ITER_LOG_CAP + i], L[7 * Workspace::ITER_LOG_CAP + i]);
+                                 L[5 * Workspace::ITER_LOG_CAP + i], L[6 * Workspace::ITER_LOG_CAP + i], L[7 * Workspace::ITER_LOG_CAP + i],
+                                 L[3 * Workspace::ITER_LOG_CAP + i], L[8 * Workspace::ITER_LOG_CAP + i]);
                 }
             std::fclose(f);
         }
@@ -1240,6 +1276,7 @@ int rt_set_option(const char* key, int64_t value) {
     else if (k == "profile") g_opt_profile = (int)value;
     else if (k == "count") g_opt_count = (int)value;
     else if (k == "debug_skip_redo") g_opt_debug_skip_redo = (int)value;
+    else if (k == "tail_budget") g_opt_tail_budget = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
     else if (k == "refill") g_opt_refill = (int)value;
     else if (k == "leaf_weight") g_opt_leaf_weight = (int)value;
     else if (k == "pipes") g_opt_pipes = (int)value;
@@ -1511,7 +1548,7 @@ int rt_shutdown(void) {
         if (cudaSetDevice(kv.first) != cudaSuccess) { cudaGetLastError(); continue; }
         cudaDeviceSynchronize();
         release_workspace_queues(*w);
-        w->ctr.release(); w->film.release(); w->sumsq.release(); w->iter_log.release(); w->long_rays.release();
+        w->ctr.release(); w->film.release(); w->sumsq.release(); w->iter_log.release(); w->long_rays.release(); w->susp.release();
         if (w->h_ctr) { cudaFreeHost(w->h_ctr); w->h_ctr = nullptr; }
         for (int b = 0; b < 2; ++b) {
             if (w->h_stage[b]) { cudaFreeHost(w->h_stage[b]); w->h_stage[b] = nullptr; }
@@ -1520,6 +1557,9 @@ int rt_shutdown(void) {
         if (w->copy_stream) { cudaStreamDestroy(w->copy_stream); w->copy_stream = nullptr; }
         for (int p = 0; p < Workspace::MAX_PIPES; ++p) {
             if (w->pipe_stream[p]) { cudaStreamDestroy(w->pipe_stream[p]); w->pipe_stream[p] = nullptr; }
+            if (w->resume_stream[p]) { cudaStreamDestroy(w->resume_stream[p]); w->resume_stream[p] = nullptr; }
+            if (w->resume_fork[p]) { cudaEventDestroy(w->resume_fork[p]); w->resume_fork[p] = nullptr; }
+            if (w->resume_join[p]) { cudaEventDestroy(w->resume_join[p]); w->resume_join[p] = nullptr; }
             if (w->join_event[p]) { cudaEventDestroy(w->join_event[p]); w->join_event[p] = nullptr; }
             for (int b = 0; b < 2; ++b)
                 if (w->poll_event[p][b]) { cudaEventDestroy(w->poll_event[p][b]); w->poll_event[p][b] = nullptr; }

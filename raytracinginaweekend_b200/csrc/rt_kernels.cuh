@@ -17,6 +17,12 @@ struct Counters {
     uint32_t cursor_extend; // dynamic work fetch
     uint32_t pad;
     unsigned long long next_chain;  // next (lane, pixel) chain of this pipeline to hand to a slot whose chain has ended
+    uint32_t n_susp[2];     // suspended traversals waiting in pool 0 / 1 (may over-count: readers clamp to RenderDev::susp_cap)
+    uint32_t budget;        // rounds a warp may run after it can no longer refill before it parks its rays (adapted by k_shade)
+    uint32_t boost;         // log2 of the factor on top of that budget while too large a share of the rays gets parked
+    unsigned long long tail_acc;  // this iteration's queue launch: (warps that ran after they could no longer refill) << 40 | (sum of those rounds)
+    uint32_t pad4;
+    uint32_t main_warps_left;  // warps of the queue launch of k_extend that have not finished yet (set by k_shade / k_generate)
     unsigned long long rays;   // closest-hit queries so far
     unsigned long long paths;  // camera samples generated so far
     unsigned long long node_visits, prim_tests, exact_steps;  // only maintained by the COUNT kernel variant
@@ -47,6 +53,16 @@ struct RenderDev {
                              // origin, direction, rounds, flags (1 = finished on the reference tree)
     uint32_t iter;           // iteration index of this launch (only used with iter_log)
     uint32_t pipe, n_pipes;  // rank-local lanes are dealt round-robin to n_pipes independent wavefront pipelines (streams)
+    // Suspended traversals.  A launch cannot end before its longest ray has; a handful of rays per frame take 10^3 - 10^4 rounds (a
+    // sphere 1800 units away whose test has lost its digits to cancellation accepts hits metres off, so nothing near it can be
+    // culled; hundreds of coplanar fan triangles) and the whole GPU waits for them, every iteration.  Once a warp can no longer
+    // refill, it gives its rays `tail_budget` more rounds and then parks what is still running: (cursor, stack, best hit) go to
+    // pool q^1, the hit slot says RT_SUSPENDED, k_shade puts the path back into the queue untouched and links the pool entry to its
+    // new position, and the next extend resumes the parked traversals FIRST, so they run alongside a whole launch of ordinary rays.
+    uint2* susp[2];             // pools: entry = 4 header words-pairs (pos, cur | sp, best | end, dpos | -, -) + stack_cap stack entries
+    uint32_t susp_cap, susp_stride;  // entries per pool, uint2 per entry
+    uint32_t tail_budget;       // rounds a warp keeps going after it can no longer refill (0 = never suspend)
+    uint32_t extend_warps;      // warps of the queue launch of k_extend (Counters::main_warps_left starts from it every iteration)
     uint32_t refill_threshold;  // extend refills idle lanes when fewer than this many lanes are busy
     uint32_t leaf_weight;       // phase vote: leaf phase runs when n_leaf * leaf_weight > n_node * 16
     uint32_t npix, width, height;
@@ -63,7 +79,10 @@ struct RenderDev {
 
 #define RT_ROOT_MISS 0x80000000u  // top bit of the per-path sample index: the ray fails the BVH root test (producer-side)
 #define RT_FORCE_REF 0x40000000u  // next bit: trace this segment on the reference tree (k_shade could not prove the fast-path hit)
-#define RT_K_MASK 0x3FFFFFFFu     // the sample index itself (make_plan caps the samples per lane at 2^30)
+#define RT_RESUME 0x20000000u     // next bit: this segment's traversal is parked in the suspend pool (the queue entry itself is skipped)
+#define RT_K_MASK 0x1FFFFFFFu     // the sample index itself (make_plan caps the samples per lane at 2^29)
+#define RT_TAIL_BASE 0x80000000u  // k_extend: batch_next == batch_end >= this = rounds since the warp could no longer refill (+ this)
+#define RT_SUSPENDED 0xFFFFFFFEu  // hits[pos].x: traversal parked, hits[pos].y = pool entry
 
 __device__ __forceinline__ uint32_t lane_samples(const RenderDev& R, uint32_t lane_id) {
     return R.spp_whole + (lane_id < R.spp_rem ? 1u : 0u);
@@ -110,6 +129,10 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
         R.ctr->nb[1] = 0; R.ctr->nn[1] = 0;
         R.ctr->cursor_extend = 0;
         R.ctr->next_chain = n_slots;
+        R.ctr->n_susp[0] = 0; R.ctr->n_susp[1] = 0;
+        R.ctr->budget = 1u << 24;  // the first launch measures; budgets follow from the tails seen (k_shade)
+        R.ctr->boost = 0; R.ctr->tail_acc = 0ull;
+        R.ctr->main_warps_left = R.extend_warps;
         R.ctr->rays = 0;
         R.ctr->paths = n_slots;
         R.ctr->node_visits = 0;
@@ -152,15 +175,33 @@ __device__ __forceinline__ uint32_t queue_pos(uint32_t i, uint32_t nb, uint32_t 
 // result is not proven restarts on the reference tree (MODE 2 code) in place, overlapped with the other lanes' work — a
 // separate redo launch would serialise the few longest rays of every iteration into its own tail.
 #define RT_REFMODE_BIT 16u  // Trav::dpos: this lane is (re)tracing on the reference tree
-template <int MODE, bool COUNT, int FEAT>
+// Parked traversals (RenderDev::susp): deliberately not inlined — the rare path must not cost the traversal loop registers.
+__device__ __noinline__ void park_lane(uint2* e, const uint2* stk, uint32_t stk_stride, uint32_t pos, uint32_t cur, uint32_t sp, uint32_t best,
+                                       float end, uint32_t dpos) {
+    __stcg(e, make_uint2(pos, cur));  // .x is rewritten by k_shade with the path's position in the next queue
+    __stcg(e + 1, make_uint2(sp, best));
+    __stcg(e + 2, make_uint2(__float_as_uint(end), dpos));
+    for (uint32_t i = 0; i < sp; ++i) __stcg(e + 4 + i, stk[i * stk_stride]);
+}
+__device__ __noinline__ void unpark_lane(const uint2* e, uint2* stk, uint32_t stk_stride, uint32_t& cur, uint32_t& sp, uint32_t& best, float& end,
+                                         uint32_t& dpos) {
+    const uint2 h0 = __ldcg(e), h1 = __ldcg(e + 1), h2 = __ldcg(e + 2);
+    cur = h0.y; sp = h1.x; best = h1.y; end = __uint_as_float(h2.x); dpos = h2.y;
+    for (uint32_t i = 0; i < h1.x; ++i) stk[i * stk_stride] = __ldcg(e + 4 + i);
+}
+template <int MODE, bool COUNT, int FEAT, bool RESUME>
 __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
     extern __shared__ uint2 smem[];
     uint2* stk = reinterpret_cast<uint2*>(smem) + threadIdx.x;
-    const uint32_t nb = R.ctr->nb[q], n = nb + R.ctr->nn[q];
+    // RESUME = false: the queue.  RESUME = true (a second, small launch that runs beside it on its own stream): the traversals parked by
+    // the previous extend (pool q); warp w owns entries 32 w .. 32 w + 31, so every entry has a lane without any cursor.
+    const uint32_t nb = R.ctr->nb[q];
+    const uint32_t n = RESUME ? min(R.ctr->n_susp[q], R.susp_cap) : nb + R.ctr->nn[q];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xFFFFFFFFu;
     const float INF = __int_as_float(0x7f800000);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { R.ctr->nb[q ^ 1] = 0; R.ctr->nn[q ^ 1] = 0; }  // nobody touches them during extend
+    if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) { R.ctr->nb[q ^ 1] = 0; R.ctr->nn[q ^ 1] = 0; }  // nobody touches them during extend
+    uint32_t resume_rounds = 0;  // RESUME only
     TravCount tc;
     tc.nodes = 0; tc.prims = 0; tc.exact = 0; tc.redo = 0; tc.max_sp = 0;
     Trav T;
@@ -170,30 +211,48 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
     uint32_t act_mask = 0;                   // warp-uniform ballot of `active`
     unsigned long long rounds_c = 0, busy_c = 0, trounds_c = 0, tbusy_c = 0, rrounds_c = 0, rlanes_c = 0;
     uint32_t my_rounds = 0;  // COUNT: scheduling rounds this lane's current ray has been active for
+    for (;;) {  // (outer loop: only taken again when the suspend pool is full)
     for (;;) {
         // refill: idle lanes take rays from the warp's claimed batch (one atomic per 32 rays)
         if (act_mask != FULL && !(exhausted && batch_next == batch_end) && (uint32_t)__popc(act_mask) < R.refill_threshold) {
             if (batch_next == batch_end) {
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&R.ctr->cursor_extend, 32u);
-                base = __shfl_sync(FULL, base, 0);
+                if (RESUME) {
+                    base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u;
+                    exhausted = true;  // this warp's one and only batch
+                } else {
+                    if (lane == 0) base = atomicAdd(&R.ctr->cursor_extend, 32u);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (base + 32u >= n) exhausted = true;
+                }
                 batch_next = min(base, n);
                 batch_end = min(base + 32u, n);
-                if (base + 32u >= n) exhausted = true;
             }
             const uint32_t idle = ~act_mask;
             const uint32_t avail = batch_end - batch_next;
             const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
             if (!active && rank < avail) {
-                my_pos = queue_pos(batch_next + rank, nb, R.cap);
+                const uint2* pe = nullptr;
+                if (RESUME) {  // a parked traversal takes its ray from its (relinked) queue position, cursor and stack from the pool
+                    pe = R.susp[q] + (size_t)(batch_next + rank) * R.susp_stride;
+                    my_pos = __ldcg(pe).x;
+                } else {
+                    my_pos = queue_pos(batch_next + rank, nb, R.cap);
+                }
                 const float4 a = R.A[q][my_pos], b = R.B[q][my_pos];
-                if (__float_as_uint(b.w) & RT_ROOT_MISS) {
-                    R.hits[my_pos] = make_uint2(RT_NO_HIT, __float_as_uint(INF));
+                if (!RESUME && (__float_as_uint(b.w) & (RT_ROOT_MISS | RT_RESUME))) {
+                    // RT_RESUME: parked, the RESUME launch finishes this segment; otherwise the ray fails the root test
+                    if (!(__float_as_uint(b.w) & RT_RESUME)) R.hits[my_pos] = make_uint2(RT_NO_HIT, __float_as_uint(INF));
                 } else {
                     trav_setup(S, T, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), R.Tm[q] ? R.Tm[q][my_pos] : 0.0f, 0.001f, INF);
                     active = true;
                     if (COUNT) my_rounds = 0;
-                    if (MODE == 3) {
+                    if (RESUME) {
+                        uint32_t u_cur, u_sp, u_best, u_dpos;  // temporaries: T itself must never have its address taken
+                        float u_end;
+                        unpark_lane(pe, stk, blockDim.x, u_cur, u_sp, u_best, u_end, u_dpos);
+                        T.cur = u_cur; T.sp = u_sp; T.best = u_best; T.end = u_end; T.dpos = u_dpos;
+                    } else if (MODE == 3) {
                         // degenerate direction, or k_shade sent the segment back (fast-path hit not provable): reference tree only
                         if (!fast_eligible(T) || (__float_as_uint(b.w) & RT_FORCE_REF)) T.dpos |= RT_REFMODE_BIT;
                         else trav_setup_fast(S, T);
@@ -255,6 +314,40 @@ __global__ void __launch_bounds__(128, 8) k_extend(const __grid_constant__ Scene
             }
         }
         act_mask = __ballot_sync(FULL, active);
+        // Leave with rays still running (they are parked below) once the warp has had its budget of rounds without being able to
+        // refill.  The round count lives in batch_next == batch_end, which have no other use once nothing is left to claim.
+        if (!RESUME) {
+            if (R.tail_budget != 0u && exhausted && batch_next == batch_end && act_mask != 0u) {
+                if (batch_end < RT_TAIL_BASE) batch_end = RT_TAIL_BASE;
+                batch_next = ++batch_end;
+                if ((batch_end & 63u) == 0u && batch_end - RT_TAIL_BASE > __ldcg(&R.ctr->budget)) break;
+            }
+        } else {
+            // a resumed traversal runs while the queue launch beside it does, and at least `budget` rounds
+            if (act_mask != 0u && ((++resume_rounds) & 63u) == 0u && resume_rounds > __ldcg(&R.ctr->budget) && __ldcg(&R.ctr->main_warps_left) == 0u) break;
+        }
+    }
+    if (act_mask == 0u) break;
+    {
+        // park (RenderDev::susp): cursor, best hit and stack go to pool q^1; k_shade relinks the entry to the path's next position
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&R.ctr->n_susp[q ^ 1], (uint32_t)__popc(act_mask));
+        base = __shfl_sync(FULL, base, 0);
+        const uint32_t idx = base + __popc(act_mask & ((1u << lane) - 1u));
+        if (active && idx < R.susp_cap) {
+            park_lane(R.susp[q ^ 1] + (size_t)idx * R.susp_stride, stk, blockDim.x, my_pos, T.cur, T.sp, T.best, T.end, T.dpos);
+            R.hits[my_pos] = make_uint2(RT_SUSPENDED, idx);
+            active = false;
+        }
+        act_mask = __ballot_sync(FULL, active);
+        if (act_mask == 0u) break;
+        // pool full (1 Ki .. 64 Ki entries per pipeline): whoever could not be parked gets another budget
+        if (RESUME) resume_rounds = 0u; else batch_next = batch_end = RT_TAIL_BASE + 1u;
+    }
+    }
+    if (!RESUME && lane == 0) {
+        atomicSub(&R.ctr->main_warps_left, 1u);  // the RESUME launch beside this one parks its rays when all are gone
+        if (batch_end >= RT_TAIL_BASE) atomicAdd(&R.ctr->tail_acc, (1ull << 40) | (unsigned long long)(batch_end - RT_TAIL_BASE));  // -> next budget
     }
     if (COUNT) {
         for (int off = 16; off > 0; off >>= 1) {
@@ -453,6 +546,23 @@ __global__ void __launch_bounds__(128, 6) k_shade(const __grid_constant__ SceneD
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         R.ctr->cursor_extend = 0;
+        R.ctr->n_susp[q] = 0;  // pool q has been consumed by the extend that just ran; the NEXT extend fills it again
+        // The budget for the NEXT launch: 4 x the mean number of rounds a warp of this launch ran after it could no longer refill (at
+        // least the caller's floor).  An ordinary tail is left alone — parking costs the path an iteration — and only the rays far
+        // beyond it are parked: the distant-sphere and coplanar-fan rays that take 10^3 - 10^4 rounds.  A launch that consists of long
+        // rays only (traversal 0: 0.4 N nodes per ray) has a long mean tail and parks nothing.  Safety net: while more than 0.4 % of
+        // an iteration's rays still get parked, the budget doubles on top of that.
+        const uint32_t parked = min(R.ctr->n_susp[q ^ 1], R.susp_cap);
+        const unsigned long long acc = R.ctr->tail_acc;
+        const uint32_t tail_warps = (uint32_t)(acc >> 40);
+        const uint32_t mean_tail = tail_warps ? (uint32_t)((acc & ((1ull << 40) - 1ull)) / tail_warps) : 0u;
+        uint32_t boost = R.ctr->boost;
+        if ((unsigned long long)parked * 256ull > n) boost = min(boost + 1u, 16u);
+        else if (boost) boost -= 1u;
+        const uint32_t bud = (uint32_t)min((unsigned long long)max(R.tail_budget, 4u * mean_tail) << boost, 1ull << 24);
+        R.ctr->budget = bud; R.ctr->boost = boost; R.ctr->tail_acc = 0ull;
+        R.ctr->main_warps_left = R.extend_warps;
+        if (R.iter_log) { R.iter_log[3u * 16384u + R.iter] = parked; R.iter_log[8u * 16384u + R.iter] = bud; }
         atomicAdd(&R.ctr->rays, (unsigned long long)n);
         if (R.iter_log) {  // [iter] live paths, [CAP + 2 iter] cumulative node visits (lo/hi), [3 CAP + 2 iter] cumulative prim tests
             R.iter_log[R.iter] = n;
@@ -468,7 +578,8 @@ __global__ void __launch_bounds__(128, 6) k_shade(const __grid_constant__ SceneD
     for (uint32_t base = warp_global * 32u; base < n; base += n_warps * 32u) {
         const uint32_t i = base + lane;
         const uint32_t ipos = queue_pos(i, nb, R.cap);
-        bool live = false, fresh = false, ended = false, again = false;
+        bool live = false, fresh = false, ended = false, again = false, parked = false;
+        uint32_t pool_entry = 0;
         PathIO P;
         P.o = f3(0, 0, 0); P.d = f3(0, 0, 1); P.thr = f3(1, 1, 1);
         P.dy0 = 0.0f; P.time = 0.0f; P.pixel = 0; P.k = 0; P.m = 0; P.depth = 0;
@@ -483,13 +594,19 @@ __global__ void __launch_bounds__(128, 6) k_shade(const __grid_constant__ SceneD
             P.pixel = __float_as_uint(a.w);
             P.k = __float_as_uint(b.w) & RT_K_MASK;
             uint2 hv = h;
-            if (hv.x != RT_NO_HIT && !(hv.x & RT_REF_LEAF)) {  // unverified fast-path hit (k_extend): prove it here, with the whole warp at work
+            pool_entry = hv.y;
+            if (hv.x == RT_SUSPENDED) {  // traversal parked by k_extend: the path waits, untouched, for the next extend to finish the segment
+                again = true; parked = true;
+                atomicAdd(&R.ctr->rays, ~0ull);
+            } else if (hv.x != RT_NO_HIT && !(hv.x & RT_REF_LEAF)) {  // unverified fast-path hit (k_extend): prove it here, with the whole warp at work
                 hv.x |= RT_REF_LEAF;
                 if (!ref_proven(S, hv.x, P.o, P.d, __uint_as_float(hv.y))) again = true;
             }
             if (!again) {
                 live = shade_path(S, R, P, hv);
                 ended = !live;
+            } else if (parked) {
+                live = true;
             } else {
                 // not provable (~1e-5 of the rays): the path goes back into the queue unchanged and this segment is traced again, on
                 // the reference tree; it is the same ray segment, so it is not counted twice
@@ -545,11 +662,14 @@ __global__ void __launch_bounds__(128, 6) k_shade(const __grid_constant__ SceneD
             bc = __shfl_sync(0xFFFFFFFFu, bc, 0);
             bn = __shfl_sync(0xFFFFFFFFu, bn, 0);
             if (live) {
-                const uint32_t miss = root_gate(S, P.o, P.d, 0.001f, __int_as_float(0x7f800000), R.ref_only != 0u) ? 0u : RT_ROOT_MISS;
+                // a path that goes back for the same segment (parked / to be traced again) has passed the root test before
+                const uint32_t miss = again ? (parked ? RT_RESUME : RT_FORCE_REF)
+                                            : (root_gate(S, P.o, P.d, 0.001f, __int_as_float(0x7f800000), R.ref_only != 0u) ? 0u : RT_ROOT_MISS);
                 const uint32_t below = (1u << lane) - 1u;
                 const uint32_t pos = fresh ? R.cap - 1u - (bn + __popc(mnew & below)) : bc + __popc(mcont & below);
                 R.A[q ^ 1][pos] = make_float4(P.o.x, P.o.y, P.o.z, __uint_as_float(P.pixel));
-                R.B[q ^ 1][pos] = make_float4(P.d.x, P.d.y, P.d.z, __uint_as_float(P.k | miss | (again ? RT_FORCE_REF : 0u)));
+                R.B[q ^ 1][pos] = make_float4(P.d.x, P.d.y, P.d.z, __uint_as_float(P.k | miss));
+                if (parked) R.susp[q ^ 1][(size_t)pool_entry * R.susp_stride].x = pos;  // link the parked traversal to the path's new position
                 R.C[q ^ 1][pos] = make_float4(P.thr.x, P.thr.y, P.thr.z, P.dy0);
                 R.D[q ^ 1][pos] = make_int2(P.depth, (int)P.m);
                 if (R.Tm[q ^ 1]) R.Tm[q ^ 1][pos] = P.time;

@@ -1,7 +1,7 @@
 """Render time of the BASELINE configs at the library's defaults and for a few pipeline counts, the restart (redo) rate with "count",
 and optionally a per-launch log of one single-pipeline render (RT_ITER_LOG + "profile", COUNT off so the times are the product's)."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.environ.get("PKG_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # PKG_ROOT: an A/B build of the package
 import numpy as np
 import raytracinginaweekend_b200 as rb
 from raytracinginaweekend_b200 import _cabi
@@ -36,7 +36,7 @@ for name in which:
     os.environ.pop("RT_LONG_RAYS", None)
     if iterlog_dir:
         _cabi.set_option("pipes", 1); _cabi.set_option("profile", 1)
-        os.environ["RT_ITER_LOG"] = os.path.join(iterlog_dir, "r2b_iterp1_%s.csv" % name)
+        os.environ["RT_ITER_LOG"] = os.path.join(iterlog_dir, "r2b_iterp1_%s%s.csv" % (name, "".join("_%s%s" % kv for kv in extra.items())))
         rb.render(rb.Size2i(w, h), T, spp, 50, W, seed=3)
         del os.environ["RT_ITER_LOG"]
         _cabi.set_option("profile", 0); _cabi.set_option("pipes", 0)
