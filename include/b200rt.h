@@ -236,14 +236,18 @@ int rt_render_multi_device(RtScene* const* scenes, int n_scenes, const RtRenderP
 int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_out_rgb8, void* cuda_stream);
 
 /* Knobs (process-wide; every rt_scene_create / render call reads ONE consistent snapshot at entry, rt_set_option is
- * serialised with those reads, so the calls stay re-entrant).  "max_slots": paths in flight per render (default 160 Mi): the
- * library runs min(lanes, max_slots / pixels) tracks per pixel and feeds the caller's thread_count lanes through them, so the
- * path-state workspace (120 B per slot) no longer grows with thread_count.  
+ * serialised with those reads, so the calls stay re-entrant).  "max_slots": path slots in flight per render (default 160 Mi).
+ * The render's work is thread_count x pixels CHAINS (all samples of one lane at one pixel, rendered in order by one slot, so every
+ * per-lane sum keeps the reference's order); a slot whose chain has ended takes the next chain, so the wavefronts stay full and the
+ * path-state workspace (120 B per slot) does not grow with thread_count.  The film is bit-identical for any value.
  * "traversal": 0 = reference node test only, true divisions (the reference's algorithm, for A/B
  * parity sweeps); 1 = + tight carried-interval cull; 2 = + reciprocal fast path with exact fallback; 3 (default) = a
  * rebuilt (SAH) topology over the same elements finds the closest accepted element, the result is kept only when the
- * reference traversal provably returns the same element (unique minimum, hit point strictly inside the element's parent
- * box of the reference tree), every other ray is traced again with 2 on the reference tree (RtStats.redo_rays); scenes with
+ * reference traversal provably returns the same element: the hit point lies strictly inside the element's parent box of the
+ * reference tree (margin test), or — evaluated with the reference's own divisions — inside every ancestor box (exact walk); two
+ * elements that accept exactly the same t are ordered by the reference's visit rank for the ray's direction octant (plain scenes).
+ * The proof runs in the shade kernel; what it cannot decide goes through the queue again and is traced with 2 on the reference
+ * tree (RtStats.redo_rays; ~1e-5 of the rays); scenes with
  * fewer than "rebuild_min_items" (32) elements use 2, as does rt_trace on scenes with Animation leaves (the rebuilt tree bounds
  * moving elements over the camera's shutter interval only).  "rebuild": 0 = do not build the second topology at rt_scene_create;
  * "rebuild_wrapped": 0 = not for scenes with wrapped elements / volumes.
@@ -252,9 +256,16 @@ int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_o
  * cut into several references with tighter boxes (an element may sit in several leaves of the accelerator tree).
  * "count": 1 = maintain node_visits / prim_tests / exact_steps.  "profile": 1 = time extend / shade separately.
  * "refill": busy-lane threshold of the persistent extend warps.  "leaf_weight": phase-vote weight.  "check_every": host
- * polling period (iterations).  "pipes": independent wavefront pipelines (streams) per render (default 0 = auto, 2 for >= 64 Mi path slots, else 4: one pipeline's launch tails overlap the other's work; the film is bit-identical for any value).
+ * polling period (iterations).  "pipes": independent wavefront pipelines (streams) per render (default 0 = auto, 3 for >= 64 Mi path slots, else 4: one
+ * pipeline's launch tails overlap the others' work; the film is bit-identical for any value).  "tail_budget": parked traversals —
+ * an extend warp that can no longer refill gives its rays max(this floor, 4 x the previous launch's mean tail) more rounds, then
+ * parks what is still running (cursor + stack + best hit); the path waits one iteration and a second, small launch of the extend
+ * kernel finishes the segment beside the next queue launch (default 64; 0 = never park; -n = exactly n rounds, for tests).
  * "blocks_per_sm": cap on resident blocks of the persistent kernels.
- * Environment: RT_ITER_LOG=<path> dumps (pipe, iteration, live paths, extend ms, shade ms) of the last render as CSV. */
+ * Environment: RT_ITER_LOG=<path> dumps (pipe, iteration, live paths, extend ms, shade ms, counters, parked, budget) of the last
+ * render as CSV; RT_LONG_RAYS=<path> (with "count") the rays that took >= 4096 traversal rounds; RT_TAIL_LOG=1 (with "count") the
+ * share of warp rounds after the queue ran dry / with a lane on the reference tree; RT_PACK_LOG=1 the phase times of
+ * rt_scene_create. */
 int rt_set_option(const char* key, int64_t value);
 
 /* Frees the per-device render workspaces (path-state queues, per-lane accumulators, streams, events) that the library keeps

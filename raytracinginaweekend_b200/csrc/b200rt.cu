@@ -897,7 +897,8 @@ int make_plan(const RtScene& sc, const Options& O, const RtRenderParams& P, uint
     R.mode = P.render_mode;
     R.ref_only = (O.traversal == 0 || !sc.boxes_are_bounds) ? 1u : 0u;
     R.debug_skip_redo = O.debug_skip_redo ? 1u : 0u;
-    R.tail_budget = (uint32_t)std::max(0, O.tail_budget);
+    R.tail_budget = (uint32_t)std::abs(O.tail_budget);   // < 0: fixed budget of that many rounds (no adaptation)
+    R.tail_fixed = O.tail_budget < 0 ? 1u : 0u;
     R.refill_threshold = (uint32_t)std::min(32, std::max(1, O.refill));
     R.leaf_weight = (uint32_t)std::max(1, O.leaf_weight);
     return RT_OK;
@@ -1276,7 +1277,7 @@ int rt_set_option(const char* key, int64_t value) {
     else if (k == "profile") g_opt_profile = (int)value;
     else if (k == "count") g_opt_count = (int)value;
     else if (k == "debug_skip_redo") g_opt_debug_skip_redo = (int)value;
-    else if (k == "tail_budget") g_opt_tail_budget = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
+    else if (k == "tail_budget") g_opt_tail_budget = (int)std::max<int64_t>(-(1 << 24), std::min<int64_t>(value, 1 << 24));
     else if (k == "refill") g_opt_refill = (int)value;
     else if (k == "leaf_weight") g_opt_leaf_weight = (int)value;
     else if (k == "pipes") g_opt_pipes = (int)value;

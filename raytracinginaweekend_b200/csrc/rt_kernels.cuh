@@ -62,6 +62,7 @@ struct RenderDev {
     uint2* susp[2];             // pools: entry = 4 header words-pairs (pos, cur | sp, best | end, dpos | -, -) + stack_cap stack entries
     uint32_t susp_cap, susp_stride;  // entries per pool, uint2 per entry
     uint32_t tail_budget;       // rounds a warp keeps going after it can no longer refill (0 = never suspend)
+    uint32_t tail_fixed;        // 1: the budget is tail_budget itself, not adapted (rt_set_option("tail_budget", -n): tests that force parking)
     uint32_t extend_warps;      // warps of the queue launch of k_extend (Counters::main_warps_left starts from it every iteration)
     uint32_t refill_threshold;  // extend refills idle lanes when fewer than this many lanes are busy
     uint32_t leaf_weight;       // phase vote: leaf phase runs when n_leaf * leaf_weight > n_node * 16
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneD
         R.ctr->cursor_extend = 0;
         R.ctr->next_chain = n_slots;
         R.ctr->n_susp[0] = 0; R.ctr->n_susp[1] = 0;
-        R.ctr->budget = 1u << 24;  // the first launch measures; budgets follow from the tails seen (k_shade)
+        R.ctr->budget = R.tail_fixed ? R.tail_budget : 1u << 24;  // the first launch measures; budgets follow from the tails seen (k_shade)
         R.ctr->boost = 0; R.ctr->tail_acc = 0ull;
         R.ctr->main_warps_left = R.extend_warps;
         R.ctr->rays = 0;
@@ -559,7 +560,8 @@ __global__ void __launch_bounds__(128, 6) k_shade(const __grid_constant__ SceneD
         uint32_t boost = R.ctr->boost;
         if ((unsigned long long)parked * 256ull > n) boost = min(boost + 1u, 16u);
         else if (boost) boost -= 1u;
-        const uint32_t bud = (uint32_t)min((unsigned long long)max(R.tail_budget, 4u * mean_tail) << boost, 1ull << 24);
+        const uint32_t bud = R.tail_fixed ? R.tail_budget  // tests: park after exactly this many rounds, whatever the tails look like
+                                          : (uint32_t)min((unsigned long long)max(R.tail_budget, 4u * mean_tail) << boost, 1ull << 24);
         R.ctr->budget = bud; R.ctr->boost = boost; R.ctr->tail_acc = 0ull;
         R.ctr->main_warps_left = R.extend_warps;
         if (R.iter_log) { R.iter_log[3u * 16384u + R.iter] = parked; R.iter_log[8u * 16384u + R.iter] = bud; }

@@ -24,10 +24,10 @@ def product_world(name):
 
 @pytest.fixture(autouse=True)
 def default_options():
-    for k, v in (("traversal", 3), ("count", 0), ("profile", 0), ("pipes", 0), ("rebuild_min_items", 32), ("max_slots", 160 << 20)):
+    for k, v in (("traversal", 3), ("count", 0), ("profile", 0), ("pipes", 0), ("rebuild_min_items", 32), ("max_slots", 160 << 20), ("tail_budget", 64)):
         _cabi.set_option(k, v)
     yield
-    _cabi.set_option("max_slots", 160 << 20)
+    _cabi.set_option("max_slots", 160 << 20); _cabi.set_option("tail_budget", 64); _cabi.set_option("traversal", 3)
 
 
 # ---------------------------------------------------------------- path slots: in-flight paths are the library's choice, not thread_count's
@@ -288,3 +288,37 @@ def test_cli_argument_errors():
     assert subprocess.run([exe, "x.png", "64"], capture_output=True).returncode != 0                       # main.rs indexes args[1..5]: panics
     r = subprocess.run([exe, "/tmp/x.png", "64", "1", "5", "demo:no_such_world"], capture_output=True, text=True)
     assert r.returncode != 0 and "error" in r.stderr                                                        # main.rs:36 `_ => panic!()`
+
+
+# ---------------------------------------------------------------- parked traversals (tail_budget): forced parking never changes a film
+@pytest.mark.parametrize("name,w,h,spp,T", [("config:c2", 320, 180, 8, 8), ("config:c5", 240, 135, 4, 4), ("config:c1", 300, 200, 6, 3),
+                                            ("demo:cornell_box_smoke", 64, 64, 8, 4), ("demo:moving_spheres", 96, 64, 6, 3)])
+def test_parked_traversals_do_not_change_the_film(name, w, h, spp, T):
+    """An extend warp that can no longer refill parks its running rays (cursor, stack, best hit -> suspend pool) and a second launch of
+    the extend kernel resumes them next iteration.  With a FIXED budget of 64 rounds nearly every launch parks rays (some of them
+    several times, in both traversal trees, with volumes and moving elements in the scene); the film must keep every bit."""
+    world = product_world(name)
+    films, stats = [], []
+    for budget in (0, -64, -128, 64):
+        _cabi.set_option("tail_budget", budget)
+        img, st = rb.render(rb.Size2i(w, h), T, spp, 50, world, seed=21, return_stats=True)
+        films.append(img); stats.append(st)
+    _cabi.set_option("tail_budget", 64)
+    for f, st in zip(films[1:], stats[1:]):
+        assert images_equal_bits(films[0], f)
+        assert st["ray_segments"] == stats[0]["ray_segments"] and st["paths"] == stats[0]["paths"]
+    if name in ("config:c2", "config:c5"):   # long rays exist there: parked paths wait an iteration, so the fixed small budget shows
+        assert stats[1]["iterations"] > stats[0]["iterations"]
+
+
+def test_parked_traversals_with_the_reference_rule_alone():
+    """traversal 0 (the reference's node rule, ~0.4 N node visits per ray): every ray is long.  The adaptive budget must not thrash
+    (a long mean tail parks nothing) and a forced budget must still terminate with the same film."""
+    world = product_world("config:c5")
+    _cabi.set_option("traversal", 0)
+    a, sa = rb.render(rb.Size2i(96, 54), 2, 2, 50, world, seed=4, return_stats=True)
+    _cabi.set_option("tail_budget", -256)
+    b, sb = rb.render(rb.Size2i(96, 54), 2, 2, 50, world, seed=4, return_stats=True)
+    _cabi.set_option("tail_budget", 64); _cabi.set_option("traversal", 3)
+    assert images_equal_bits(a, b) and sa["ray_segments"] == sb["ray_segments"]
+    assert sa["iterations"] <= 64 + 16, sa
