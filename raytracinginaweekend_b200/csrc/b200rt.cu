@@ -1037,7 +1037,8 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
     ExtendFn ext_resume = pick_extend<true>(mode, O.count != 0, feat);  // the same kernel over the parked traversals (RenderDev::susp)
     rc = persistent_grid(sc, ext, eblock, esmem, &egrid, O.blocks_per_sm);
     if (rc) return rc;
-    rc = persistent_grid(sc, k_shade, 128, 0, &sgrid, O.blocks_per_sm);
+    void (*shade)(SceneDev, RenderDev, int) = mode == 3 ? k_shade<true> : k_shade<false>;
+    rc = persistent_grid(sc, shade, 128, 0, &sgrid, O.blocks_per_sm);
     if (rc) return rc;
     int rgrid = 0;  // RESUME launch: one warp per 32 pool entries
     if (susp_cap) {
@@ -1096,7 +1097,7 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
             ext<<<egrid, eblock, esmem, pp.st>>>(sc.dev, pp.R, pp.q);
             if (pe) CU(cudaEventRecord(pe[1], pp.st));
             if (rgrid) CU(cudaStreamWaitEvent(pp.st, ws.resume_join[p], 0));
-            k_shade<<<sgrid, 128, 0, pp.st>>>(sc.dev, pp.R, pp.q);
+            shade<<<sgrid, 128, 0, pp.st>>>(sc.dev, pp.R, pp.q);
             if (pe) CU(cudaEventRecord(pe[2], pp.st));
             launches += 2;
             ++pp.iters;

@@ -540,6 +540,7 @@ __device__ __forceinline__ bool shade_path(const SceneDev& S, const RenderDev& R
 
 // One bounce of ray_color for every live path of queue `q`; survivors (and regenerated paths) are compacted
 // into queue q^1 with one warp-aggregated atomic per warp.
+template <bool PROOF>  // PROOF: the extend launches run traversal 3, so hits may arrive unverified (scenes that keep the reference tree never do)
 __global__ void __launch_bounds__(128, 6) k_shade(const __grid_constant__ SceneDev S, const __grid_constant__ RenderDev R, int q) {
     const uint32_t nb = R.ctr->nb[q], n = nb + R.ctr->nn[q];
     const uint32_t lane = threadIdx.x & 31u;
@@ -600,7 +601,7 @@ __global__ void __launch_bounds__(128, 6) k_shade(const __grid_constant__ SceneD
             if (hv.x == RT_SUSPENDED) {  // traversal parked by k_extend: the path waits, untouched, for the next extend to finish the segment
                 again = true; parked = true;
                 atomicAdd(&R.ctr->rays, ~0ull);
-            } else if (hv.x != RT_NO_HIT && !(hv.x & RT_REF_LEAF)) {  // unverified fast-path hit (k_extend): prove it here, with the whole warp at work
+            } else if (PROOF && hv.x != RT_NO_HIT && !(hv.x & RT_REF_LEAF)) {  // unverified fast-path hit (k_extend): prove it here, with the whole warp at work
                 hv.x |= RT_REF_LEAF;
                 if (!ref_proven(S, hv.x, P.o, P.d, __uint_as_float(hv.y))) again = true;
             }
