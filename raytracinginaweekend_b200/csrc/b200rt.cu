@@ -45,6 +45,8 @@ int g_opt_pipes = 0;         // independent wavefront pipelines (streams) per re
 int g_opt_leaf_weight = 24;   // extend phase vote: leaf phase when n_leaf * w > n_node * 16
 int g_opt_refill = 28;        // extend refills idle lanes when fewer than this many of 32 are busy
 int g_opt_tail_budget = 64;   // rounds an extend warp keeps going after it can no longer refill, before it parks its rays (0 = never)
+int g_opt_carveout = 75;        // cudaFuncAttributePreferredSharedMemoryCarveout of the extend kernel in per cent (-1 = driver default): the stacks get
+                                // 171 KB of the SM's 228 KB, the rest stays L1 for node / primitive records (C4 +4.8 %, C2 unchanged; profiles/README.md)
 int g_opt_debug_skip_redo = 0;  // measurement only: keep unproven fast-path results (films are then NOT the reference's)
 int g_opt_count = 0;        // 1 = COUNT kernel variant (node visits / primitive tests per ray)
 int g_opt_profile = 0;        // 1 = time every extend / shade launch with CUDA events on the launching stream (no extra syncs)
@@ -54,13 +56,13 @@ int64_t g_opt_max_slots = 160ll << 20;  // path slots in flight per render (boun
 
 struct Options {
     int traversal, presplit, rebuild_min_items, rebuild_wrapped, rebuild, rebuild_depth_extra, pipes, leaf_weight, refill, count, profile,
-        check_every, blocks_per_sm, debug_skip_redo, tail_budget;
+        check_every, blocks_per_sm, debug_skip_redo, tail_budget, carveout;
     int64_t max_slots;
 };
 Options options_snapshot() {
     std::lock_guard<std::mutex> lk(g_opt_mu);
     return Options{g_opt_traversal, g_opt_presplit, g_opt_rebuild_min_items, g_opt_rebuild_wrapped, g_opt_rebuild, g_opt_rebuild_depth_extra,
-                   g_opt_pipes, g_opt_leaf_weight, g_opt_refill, g_opt_count, g_opt_profile, g_opt_check_every, g_opt_blocks_per_sm, g_opt_debug_skip_redo, g_opt_tail_budget,
+                   g_opt_pipes, g_opt_leaf_weight, g_opt_refill, g_opt_count, g_opt_profile, g_opt_check_every, g_opt_blocks_per_sm, g_opt_debug_skip_redo, g_opt_tail_budget, g_opt_carveout,
                    g_opt_max_slots};
 }
 
@@ -978,7 +980,7 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
         CU(cudaMemsetAsync(ws.long_rays.p, 0, 4096 * 8 * sizeof(float), stream));
     }
     std::vector<std::array<float, 2>> iter_ms[Workspace::MAX_PIPES];
-    const int want_pipes = O.pipes > 0 ? O.pipes : (pl.slots >= ((size_t)64 << 20) ? 3 : 4);  // measured on C1..C5 (profiles/README.md)
+    const int want_pipes = O.pipes > 0 ? O.pipes : (pl.slots >= ((size_t)64 << 20) ? 2 : 4);  // measured on C1..C5 (profiles/README.md)
     const int G = (int)std::min<uint32_t>((uint32_t)std::max(1, std::min(want_pipes, (int)Workspace::MAX_PIPES)), pl.n_local);
     struct Pipe {
         RenderDev R;
@@ -1035,6 +1037,7 @@ int render_locked(RtScene& sc, Workspace& ws, const Options& O, RenderPlan& pl, 
     int egrid = 0, sgrid = 0;
     ExtendFn ext = pick_extend<false>(mode, O.count != 0, feat);
     ExtendFn ext_resume = pick_extend<true>(mode, O.count != 0, feat);  // the same kernel over the parked traversals (RenderDev::susp)
+    CU(cudaFuncSetAttribute(ext, cudaFuncAttributePreferredSharedMemoryCarveout, O.carveout >= 0 ? std::min(100, O.carveout) : (int)cudaSharedmemCarveoutDefault));
     rc = persistent_grid(sc, ext, eblock, esmem, &egrid, O.blocks_per_sm);
     if (rc) return rc;
     void (*shade)(SceneDev, RenderDev, int) = mode == 3 ? k_shade<true> : k_shade<false>;
@@ -1308,6 +1311,7 @@ int rt_set_option(const char* key, int64_t value) {
     else if (k == "profile") g_opt_profile = (int)value;
     else if (k == "count") g_opt_count = (int)value;
     else if (k == "debug_skip_redo") g_opt_debug_skip_redo = (int)value;
+    else if (k == "carveout") g_opt_carveout = (int)value;
     else if (k == "tail_budget") g_opt_tail_budget = (int)std::max<int64_t>(-(1 << 24), std::min<int64_t>(value, 1 << 24));
     else if (k == "refill") g_opt_refill = (int)value;
     else if (k == "leaf_weight") g_opt_leaf_weight = (int)value;
