@@ -560,14 +560,19 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     // The tight cull (MODE >= 1) and the visibility proof of MODE 3 rely on what the reference builder guarantees: a node's box
     // contains the boxes of its children (it is their union).  A caller-made tree that breaks this is still traversed exactly
     // as given, but only with the reference's own node rule (MODE 0) and without the rebuilt topology.
-    sc.boxes_are_bounds = true;
-    for (uint32_t i = 0; i < d.n_nodes && sc.boxes_are_bounds; ++i)
-        for (uint32_t ch : {d.nodes[i].left, d.nodes[i].right}) {
-            if ((ch & RT_LEAF_BIT) && d.items[ch & ~RT_LEAF_BIT].wrap_flags) continue;  // Q2 boxes: no tight cull around them anyway
-            const Box cb = child_box(ch);
-            for (int k = 0; k < 3; ++k)
-                if (!(cb.mn[k] >= d.nodes[i].aabb_min[k] && cb.mx[k] <= d.nodes[i].aabb_max[k])) sc.boxes_are_bounds = false;
-        }
+    {
+        std::atomic<bool> bounds_ok{true};
+        rt_rebuild::parallel_for(d.n_nodes, 65536, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi && bounds_ok.load(std::memory_order_relaxed); ++i)
+                for (uint32_t ch : {d.nodes[i].left, d.nodes[i].right}) {
+                    if ((ch & RT_LEAF_BIT) && d.items[ch & ~RT_LEAF_BIT].wrap_flags) continue;  // Q2 boxes: no tight cull around them anyway
+                    const Box cb = child_box(ch);
+                    for (int k = 0; k < 3; ++k)
+                        if (!(cb.mn[k] >= d.nodes[i].aabb_min[k] && cb.mx[k] <= d.nodes[i].aabb_max[k])) bounds_ok.store(false, std::memory_order_relaxed);
+                }
+        });
+        sc.boxes_are_bounds = bounds_ok.load();
+    }
 
     lap("reference nodes + depth");
     // Row f4: second topology (SAH) over the same elements.  Wrapped elements enter it with their true world-space bounds
@@ -580,23 +585,29 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         std::vector<rt_rebuild::Box3> lb(N);
         std::vector<float> tri;
         std::vector<uint8_t> is_tri(N, 0);
-        for (uint32_t i = 0; i < N; ++i)
-            for (int k = 0; k < 3; ++k) { lb[i].mn[k] = fbox[i].mn[k]; lb[i].mx[k] = fbox[i].mx[k]; }
+        rt_rebuild::parallel_for(N, 65536, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i)
+                for (int k = 0; k < 3; ++k) { lb[i].mn[k] = fbox[i].mn[k]; lb[i].mx[k] = fbox[i].mx[k]; }
+        });
         // pre-split sliver triangles into several references (rt_rebuild.hpp); the budget shrinks for very large scenes
         const double factor = O.presplit <= 100 ? 1.0 : std::min((double)O.presplit / 100.0, N <= 150000u ? 16.0 : (N <= 2000000u ? 2.0 : 1.0));
         if (factor > 1.0) {
-            tri.assign(9 * (size_t)N, 0.0f);
-            for (uint32_t i = 0; i < N; ++i)
-                if (d.items[i].kind == RT_GEO_TRIANGLE && !d.items[i].wrap_flags) {  // wrapped triangles keep one reference
-                    is_tri[i] = 1;
-                    for (int k = 0; k < 9; ++k) tri[9 * (size_t)i + k] = d.items[i].geom[k];
+            tri.resize(9 * (size_t)N);
+            rt_rebuild::parallel_for(N, 65536, [&](size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; ++i) {
+                    const bool t = d.items[i].kind == RT_GEO_TRIANGLE && !d.items[i].wrap_flags;  // wrapped triangles keep one reference
+                    is_tri[i] = t ? 1 : 0;
+                    for (int k = 0; k < 9; ++k) tri[9 * i + k] = t ? d.items[i].geom[k] : 0.0f;
                 }
+            });
         }
         std::vector<rt_rebuild::Ref> refs;
         rt_rebuild::presplit(lb, tri, is_tri, (size_t)((double)N * factor), refs);
         lap("pre-split references");
         std::vector<rt_rebuild::Box3> rbx(refs.size());
-        for (size_t i = 0; i < refs.size(); ++i) rbx[i] = refs[i].box;
+        rt_rebuild::parallel_for(refs.size(), 65536, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) rbx[i] = refs[i].box;
+        });
         rt_rebuild::Tree F;
         uint32_t extra_levels = 0;
         while (((size_t)N << extra_levels) < refs.size()) ++extra_levels;
@@ -644,17 +655,26 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     // depends only on the signs of the ray direction (hittable.rs:441-445) — one leaf order per octant, 8 x n_items ranks.
     std::vector<uint32_t> visit_rank;
     if (!nodes2.empty() && !any_wrap && !(root & RT_REF_LEAF)) {
-        visit_rank.assign(8 * (size_t)N, 0u);
-        rt_rebuild::parallel_for(8, 1, [&](size_t o_lo, size_t o_hi) {
+        visit_rank.resize(8 * (size_t)N);
+        // octants 0..3 by an ordered DFS each; the complementary octant (7 - o) flips the child order at EVERY node, i.e. visits the
+        // leaves in exactly the reverse order: rank = N - 1 - rank
+        rt_rebuild::parallel_for(4, 1, [&](size_t o_lo, size_t o_hi) {
             std::vector<uint32_t> st;
             for (size_t oct = o_lo; oct < o_hi; ++oct) {
                 uint32_t next = 0;
                 st.clear();
                 st.push_back(root);
+                uint32_t* fwd = visit_rank.data() + oct * N;
+                uint32_t* rev = visit_rank.data() + (7 - oct) * N;
                 while (!st.empty()) {
                     const uint32_t r = st.back();
                     st.pop_back();
-                    if (r & RT_REF_LEAF) { visit_rank[oct * N + (r & RT_REF_ITEM_MASK)] = next++; continue; }
+                    if (r & RT_REF_LEAF) {
+                        const uint32_t item = r & RT_REF_ITEM_MASK;
+                        fwd[item] = next; rev[item] = N - 1u - next;
+                        ++next;
+                        continue;
+                    }
                     const bool left_first = ((oct >> nodes[r].q3.z) & 1u) != 0u;
                     st.push_back(left_first ? nodes[r].q3.y : nodes[r].q3.x);  // visited second
                     st.push_back(left_first ? nodes[r].q3.x : nodes[r].q3.y);

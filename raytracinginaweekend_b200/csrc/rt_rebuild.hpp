@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdint>
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <numeric>
 #include <thread>
@@ -405,29 +406,58 @@ inline void build(const std::vector<Box3>& leaf, uint32_t max_depth, Tree& out) 
     };
     std::vector<Task> tasks;
     detail::Builder top(leaf, out, max_depth);
-    // top part: same recursion, but ranges that reach PAR_LEVELS (or get small) become tasks
-    struct TopRec {
+    // Top part, phase 1: only the SPLITS of the ranges above PAR_MIN, fork-join (the two halves of a split work on disjoint ranges of
+    // the index array, so they run on two threads down to FORK_LEVELS; a split of >= 2^18 references also bins on all cores).
+    // The result of a split depends on its range alone, so the tree is the same for any thread count.
+    struct TopNode {
+        uint32_t lo = 0, hi = 0, depth = 0, mid = 0, axis = 0;
+        bool task = false;
+        std::unique_ptr<TopNode> l, r;
+    };
+    const uint32_t FORK_LEVELS = hw >= 16 ? 4u : (hw >= 4 ? 3u : (hw >= 2 ? 1u : 0u));
+    struct Splitter {
+        detail::Builder& b;
+        uint32_t par_min, fork_levels;
+        void go(TopNode* nd) {
+            if (nd->hi - nd->lo == 1) return;
+            if (nd->hi - nd->lo <= par_min) { nd->task = true; return; }
+            nd->mid = b.split(nd->lo, nd->hi, b.max_depth - nd->depth, &nd->axis);
+            nd->l.reset(new TopNode); nd->r.reset(new TopNode);
+            nd->l->lo = nd->lo; nd->l->hi = nd->mid; nd->r->lo = nd->mid; nd->r->hi = nd->hi;
+            nd->l->depth = nd->r->depth = nd->depth + 1;
+            if (nd->depth < fork_levels && nd->l->hi - nd->l->lo > par_min && nd->r->hi - nd->r->lo > par_min) {
+                std::thread other([&] { go(nd->l.get()); });
+                go(nd->r.get());
+                other.join();
+            } else {
+                go(nd->l.get());
+                go(nd->r.get());
+            }
+        }
+    } splitter{top, PAR_MIN, FORK_LEVELS};
+    TopNode top_root;
+    top_root.lo = 0; top_root.hi = (uint32_t)leaf.size(); top_root.depth = 0;
+    splitter.go(&top_root);
+    // phase 2: number the top nodes in pre-order and collect the subtree tasks left to right (sequential, a few hundred nodes)
+    struct Numberer {
         detail::Builder& b;
         std::vector<Task>& tasks;
-        uint32_t par_min, task_bit;
-        uint32_t go(uint32_t lo, uint32_t hi, uint32_t depth) {
-            if (hi - lo == 1) return 0x80000000u | b.idx[lo];
-            if (hi - lo <= par_min) {
-                tasks.push_back(Task{lo, hi, depth, Tree()});
+        uint32_t task_bit;
+        uint32_t go(const TopNode* nd) {
+            if (nd->hi - nd->lo == 1) return 0x80000000u | b.idx[nd->lo];
+            if (nd->task) {
+                tasks.push_back(Task{nd->lo, nd->hi, nd->depth, Tree()});
                 return task_bit | (uint32_t)(tasks.size() - 1);
             }
             const uint32_t me = (uint32_t)b.out.left.size();
-            b.out.left.push_back(0); b.out.right.push_back(0); b.out.box.push_back(detail::empty_box()); b.out.axis.push_back(0);
-            b.out.depth = std::max(b.out.depth, depth + 1);
-            uint32_t ax = 0;
-            const uint32_t mid = b.split(lo, hi, b.max_depth - depth, &ax);
-            b.out.axis[me] = ax;
-            const uint32_t l = go(lo, mid, depth + 1), r = go(mid, hi, depth + 1);
+            b.out.left.push_back(0); b.out.right.push_back(0); b.out.box.push_back(detail::empty_box()); b.out.axis.push_back(nd->axis);
+            b.out.depth = std::max(b.out.depth, nd->depth + 1);
+            const uint32_t l = go(nd->l.get()), r = go(nd->r.get());
             b.out.left[me] = l; b.out.right[me] = r;
             return me;
         }
-    } rec{top, tasks, PAR_MIN, TASK_BIT};
-    const uint32_t root = rec.go(0, (uint32_t)leaf.size(), 0);
+    } numberer{top, tasks, TASK_BIT};
+    const uint32_t root = numberer.go(&top_root);
     const uint32_t n_top = (uint32_t)out.left.size();
     // subtrees: each task gets its own Builder view (shared, already partitioned index array; disjoint ranges)
     std::atomic<size_t> next{0};
@@ -445,19 +475,26 @@ inline void build(const std::vector<Box3>& leaf, uint32_t max_depth, Tree& out) 
     for (unsigned i = 1; i < n_thr; ++i) pool.emplace_back(worker);
     worker();
     for (auto& th : pool) th.join();
-    // splice
-    std::vector<uint32_t> task_root(tasks.size());
-    for (size_t t = 0; t < tasks.size(); ++t) {
-        const Tree& tr = tasks[t].tree;
-        const uint32_t off = (uint32_t)out.left.size();
-        auto fix = [&](uint32_t c) { return (c & 0x80000000u) ? c : c + off; };
-        for (size_t i = 0; i < tr.left.size(); ++i) {
-            out.left.push_back(fix(tr.left[i])); out.right.push_back(fix(tr.right[i]));
-            out.axis.push_back(tr.axis[i]); out.box.push_back(tr.box[i]);
-        }
-        task_root[t] = fix(tr.root);
-        out.depth = std::max(out.depth, tr.depth);
+    // splice: offsets by prefix sum, then every task copies its nodes into place (parallel over tasks)
+    std::vector<uint32_t> task_root(tasks.size()), task_off(tasks.size());
+    {
+        uint32_t off = n_top;
+        for (size_t t = 0; t < tasks.size(); ++t) { task_off[t] = off; off += (uint32_t)tasks[t].tree.left.size(); }
+        out.left.resize(off); out.right.resize(off); out.axis.resize(off); out.box.resize(off);
     }
+    parallel_for(tasks.size(), 1, [&](size_t t_lo, size_t t_hi) {
+        for (size_t t = t_lo; t < t_hi; ++t) {
+            const Tree& tr = tasks[t].tree;
+            const uint32_t off = task_off[t];
+            auto fix = [&](uint32_t c) { return (c & 0x80000000u) ? c : c + off; };
+            for (size_t i = 0; i < tr.left.size(); ++i) {
+                out.left[off + i] = fix(tr.left[i]); out.right[off + i] = fix(tr.right[i]);
+                out.axis[off + i] = tr.axis[i]; out.box[off + i] = tr.box[i];
+            }
+            task_root[t] = fix(tr.root);
+        }
+    });
+    for (size_t t = 0; t < tasks.size(); ++t) out.depth = std::max(out.depth, tasks[t].tree.depth);
     for (uint32_t i = n_top; i-- > 0;) {  // patch task references, then the top boxes bottom-up
         for (uint32_t* c : {&out.left[i], &out.right[i]})
             if (!(*c & 0x80000000u) && (*c & TASK_BIT)) *c = task_root[*c & ~TASK_BIT];
