@@ -424,8 +424,9 @@ class Bench:
                "lanes_total": STRONG["lanes_total"], "lanes_per_gpu": STRONG["lanes_total"] // self.world_size, "scaling": "strong", "value": r["value"], "unit": "Mrays/s",
                "ms_per_step": r["ms_per_step"], "steps": steps, "ray_segments_per_step": r["rays_per_step"],
                "rank0_render_ms": e0.elapsed_time(e1), "rank0_combine_ms": e1.elapsed_time(e2), "rank0_iterations": int(st["iterations"]),
-               "note": "total work fixed, per-GPU work = 1/N: what limits it is the per-render fixed cost (~50 wavefront iterations whose duration is set by "
-                       "their slowest ray, whatever the ray count) — the film all-reduce is < 1 ms"}
+               "note": "total work fixed, per-GPU work = 1/N: what limits it is the per-render fixed cost (the >= 50 wavefront iterations of a depth-50 path, "
+                       "whose duration stops shrinking with the ray count; round 2 parks the rays that outlast a launch's ordinary tail instead of "
+                       "waiting for them, DESIGN 9.2) — the film all-reduce is < 1 ms"}
         world.close()
         return out
 
