@@ -42,7 +42,7 @@ def _sources(d: str, exts: tuple[str, ...]) -> list[str]:
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
-    srcs = _sources(CSRC, (".cu", ".cuh")) + [os.path.join(ROOT, "include", "b200rt.h")]
+    srcs = _sources(CSRC, (".cu", ".cuh", ".hpp")) + [os.path.join(ROOT, "include", "b200rt.h")]
     if force or _stale(LIB_CUDA, srcs):
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_CUDA, os.path.join(CSRC, "b200rt.cu")]
         subprocess.check_call(cmd)

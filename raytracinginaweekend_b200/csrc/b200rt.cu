@@ -11,6 +11,9 @@
 #include <array>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -290,6 +293,67 @@ int upload_staged(int device, void* d_dst, const void* src, size_t bytes) {
     return RT_OK;
 }
 
+// A helper thread of pack_scene that is always joined when it goes out of scope (early returns, exceptions of the packing code).
+struct ScopedThread {
+    std::thread t;
+    std::string error;  // set by the body (exceptions included)
+    template <class F>
+    void start(F&& body) {
+        t = std::thread([this, body]() {
+            try { body(error); } catch (const std::exception& e) { error = e.what(); } catch (...) { error = "unknown exception"; }
+        });
+    }
+    void join() { if (t.joinable()) t.join(); }
+    ~ScopedThread() { join(); }
+};
+// Host -> device copies of the scene arrays on a thread of their own, in the order they are posted, so that the upload of what is
+// already packed (primitives, shading records, the reference tree) runs beside the accelerator build.  The staging chunks of a
+// device's workspace serve one copy at a time, so every large scene upload goes through this one thread.
+struct Uploader {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<int()>> jobs;
+    bool closing = false;
+    int rc = RT_OK;
+    std::string error;
+    double busy_ms = 0.0;
+    std::thread t;
+    void start() {
+        t = std::thread([this] {
+            for (;;) {
+                std::function<int()> job;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return closing || !jobs.empty(); });
+                    if (jobs.empty()) return;
+                    job = std::move(jobs.front());
+                    jobs.pop_front();
+                }
+                if (rc != RT_OK) continue;  // after a failure the remaining jobs are dropped
+                const auto t0 = std::chrono::steady_clock::now();
+                int r;
+                try { r = job(); } catch (const std::exception& e) { r = fail(RT_ENOMEM, e.what()); } catch (...) { r = fail(RT_EINVAL, "unknown exception"); }
+                busy_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                if (r != RT_OK) { rc = r; error = g_err; }  // g_err is thread-local: carried to the caller by finish()
+            }
+        });
+    }
+    void post(std::function<int()> job) {
+        { std::lock_guard<std::mutex> lk(mu); jobs.push_back(std::move(job)); }
+        cv.notify_one();
+    }
+    void stop() {  // waits for everything posted
+        { std::lock_guard<std::mutex> lk(mu); closing = true; }
+        cv.notify_one();
+        if (t.joinable()) t.join();
+    }
+    int finish() {  // ... and reports the first failure on the calling thread
+        stop();
+        return rc == RT_OK ? RT_OK : fail(rc, error);
+    }
+    ~Uploader() { stop(); }  // early return of the packing code: its own error stays the reported one
+};
+
 int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     // RT_PACK_LOG=1: phase times of the scene hand-off on stderr (host packing, accelerator build, upload)
     const bool pack_log = std::getenv("RT_PACK_LOG") != nullptr;
@@ -351,15 +415,19 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         return true;
     };
 
-    std::vector<PrimDev> prims(N);
-    std::vector<ShadeDev> shade(N);
-    std::vector<Box> lbox(N);
+    // uninitialised buffers: first touch (page faults included) happens in the parallel loops that fill them
+    using rt_rebuild::Buffer;
+    Buffer<PrimDev> prims;
+    Buffer<ShadeDev> shade;
+    Buffer<Box> lbox;
+    prims.resize_discard(N); shade.resize_discard(N); lbox.resize_discard(N);
     // Guard band of the tight cull (DESIGN.md "Tight node test"): a primitive test can report a hit for a ray that
     // misses the primitive's true AABB by the rounding slack of that test.  m(t) = A + |t| (1e-5 + C |t|) with
     //   triangles / rects: A = 8 eps max|coordinate|            (position = o + t d is rounded at coordinate scale)
     //   spheres          : A = 8 eps (max|coordinate| + 3 r), C = 8 * 3 eps / r   (|disc error| <~ 11 eps |oc|^2)
-    std::vector<float> leafA(N), leafC(N), fastA(N), fastC(N);
-    std::vector<Box> fbox(N);
+    Buffer<float> leafA, leafC, fastA, fastC;
+    Buffer<Box> fbox;
+    leafA.resize_discard(N); leafC.resize_discard(N); fastA.resize_discard(N); fastC.resize_discard(N); fbox.resize_discard(N);
     // ray times the camera can produce: U[t0, t1) + dot(shutter_pace, point), point in [0, 1 + 1/(w-1)]^2 (camera.rs:185-190)
     const bool times_ok = std::isfinite(d.camera.time_start) && std::isfinite(d.camera.time_end) && std::isfinite(d.camera.shutter_pace[0]) &&
                           std::isfinite(d.camera.shutter_pace[1]);
@@ -368,7 +436,8 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     const double shutter_lo = times_ok ? std::min<double>(d.camera.time_start, d.camera.time_end) + pace_lo : 0.0;
     const double shutter_hi = times_ok ? std::max<double>(d.camera.time_start, d.camera.time_end) + pace_hi : 0.0;
     bool any_wrap = false;
-    std::vector<WrapDev> wraps(N);
+    Buffer<WrapDev> wraps;
+    wraps.resize_discard(N);
     const float eps = 5.9604645e-8f, safety = 8.0f;
     std::atomic<bool> flag_wrap{false}, flag_anim{false}, flag_vol{false};
     std::atomic<const char*> first_error{nullptr};
@@ -473,10 +542,76 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         return b >> 16;
     };
     auto pack_margin = [&](float a, float c) -> uint32_t { return (bf16_up(a) << 16) | bf16_up(c); };
-    // subtree maxima, bottom-up (children always have larger indices than their parent in the pre-order numbering;
-    // verified below, otherwise fall back to the global maximum)
-    std::vector<float> nodeA(d.n_nodes, 0.0f), nodeC(d.n_nodes, 0.0f);
+
+    // every child reference of the caller's tree, range-checked once (the passes below, several of them on helper threads, index with them)
     {
+        std::atomic<const char*> node_error{nullptr};
+        rt_rebuild::parallel_for(d.n_nodes, 65536, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                uint32_t tmp;
+                if (!conv_ref(d.nodes[i].left, &tmp) || !conv_ref(d.nodes[i].right, &tmp)) { node_error.store("BVH child reference out of range"); return; }
+                if (d.nodes[i].axis_id > 2) { node_error.store("BVH axis_id out of range"); return; }
+            }
+        });
+        if (node_error.load()) return fail(RT_EINVAL, node_error.load());
+    }
+    uint32_t root;
+    if (!conv_ref(d.root, &root)) return fail(RT_EINVAL, "root reference out of range");
+
+    // everything the helper threads write (declared before them: they are joined before these buffers go away)
+    Buffer<NodeDev> nodes;
+    Buffer<float4> own_box;
+    Buffer<float> nodeA, nodeC;
+    nodes.resize_discard(d.n_nodes); own_box.resize_discard(2 * (size_t)d.n_nodes); nodeA.resize_discard(d.n_nodes); nodeC.resize_discard(d.n_nodes);
+    Buffer<NodeDev> nodes2;
+    Buffer<float4> vis_box;
+    Buffer<uint32_t> visit_rank;
+    double ms_ref_nodes = 0.0, ms_vis = 0.0, ms_ranks = 0.0;
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+
+    // Uploads start now, beside the rest of the packing: primitives and shading records first.
+#define UP(dst, src, bytes) do { int rc_up_ = upload_staged(sc.device, (dst), (src), (bytes)); if (rc_up_) return rc_up_; } while (0)
+    Uploader up;
+    up.start();
+    up.post([&]() -> int {
+        CU(cudaSetDevice(sc.device));
+        {   // one attribute, cached per device (cudaGetDeviceProperties walks every attribute and can take tens of milliseconds)
+            static std::mutex mu;
+            static std::map<int, int> sm_of;
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = sm_of.find(sc.device);
+            if (it == sm_of.end()) {
+                int v = 0;
+                CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, sc.device));
+                it = sm_of.emplace(sc.device, v).first;
+            }
+            sc.sm_count = it->second;
+        }
+        CU(sc.prims.alloc(N));
+        CU(sc.shade.alloc(N));
+        if (any_wrap) {
+            CU(sc.wraps.alloc(N));
+            UP(sc.wraps.p, wraps.data(), N * sizeof(WrapDev));
+            sc.device_bytes += (uint64_t)N * sizeof(WrapDev);
+        }
+        UP(sc.prims.p, prims.data(), N * sizeof(PrimDev));
+        UP(sc.shade.p, shade.data(), N * sizeof(ShadeDev));
+        sc.device_bytes += (uint64_t)N * (sizeof(PrimDev) + sizeof(ShadeDev));
+        return RT_OK;
+    });
+
+    auto child_box = [&](uint32_t r) -> Box {
+        if (r & RT_LEAF_BIT) return lbox[r & ~RT_LEAF_BIT];
+        Box b;
+        for (int k = 0; k < 3; ++k) { b.mn[k] = d.nodes[r].aabb_min[k]; b.mx[k] = d.nodes[r].aabb_max[k]; }
+        return b;
+    };
+    // Helper 1: the reference tree's device records.  Subtree maxima of the guard band bottom-up (children always have larger
+    // indices than their parent in the pre-order numbering; verified, otherwise fall back to the global maximum), the 64-byte
+    // node records, each node's own box and its parent link; then the upload of both arrays is posted.
+    ScopedThread h_ref;
+    h_ref.start([&](std::string&) {
+        const auto t0 = std::chrono::steady_clock::now();
         bool preorder = true;
         for (uint32_t i = 0; i < d.n_nodes && preorder; ++i)
             for (uint32_t c : {d.nodes[i].left, d.nodes[i].right})
@@ -485,14 +620,8 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
             for (uint32_t ii = d.n_nodes; ii-- > 0;) {
                 float a = 0.0f, c = 0.0f;
                 for (uint32_t ch : {d.nodes[ii].left, d.nodes[ii].right}) {
-                    if (ch & RT_LEAF_BIT) {
-                        uint32_t item = ch & ~RT_LEAF_BIT;
-                        if (item >= N) return fail(RT_EINVAL, "BVH child reference out of range");
-                        a = std::max(a, leafA[item]); c = std::max(c, leafC[item]);
-                    } else {
-                        if (ch >= d.n_nodes) return fail(RT_EINVAL, "BVH child reference out of range");
-                        a = std::max(a, nodeA[ch]); c = std::max(c, nodeC[ch]);
-                    }
+                    if (ch & RT_LEAF_BIT) { const uint32_t item = ch & ~RT_LEAF_BIT; a = std::max(a, leafA[item]); c = std::max(c, leafC[item]); }
+                    else { a = std::max(a, nodeA[ch]); c = std::max(c, nodeC[ch]); }
                 }
                 nodeA[ii] = a; nodeC[ii] = c;
             }
@@ -502,24 +631,11 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
             std::fill(nodeA.begin(), nodeA.end(), a);
             std::fill(nodeC.begin(), nodeC.end(), c);
         }
-    }
-
-    std::vector<NodeDev> nodes(d.n_nodes);
-    std::vector<float4> own_box(2 * (size_t)d.n_nodes);
-    auto child_box = [&](uint32_t r) -> Box {
-        if (r & RT_LEAF_BIT) return lbox[r & ~RT_LEAF_BIT];
-        Box b;
-        for (int k = 0; k < 3; ++k) { b.mn[k] = d.nodes[r].aabb_min[k]; b.mx[k] = d.nodes[r].aabb_max[k]; }
-        return b;
-    };
-    {
-        std::atomic<const char*> node_error{nullptr};
         rt_rebuild::parallel_for(d.n_nodes, 32768, [&](size_t lo, size_t hi) {
             for (size_t i = lo; i < hi; ++i) {
                 const RtBvhNode& n = d.nodes[i];
-                uint32_t l, r;
-                if (!conv_ref(n.left, &l) || !conv_ref(n.right, &r)) { node_error.store("BVH child reference out of range"); return; }
-                if (n.axis_id > 2) { node_error.store("BVH axis_id out of range"); return; }
+                uint32_t l = 0, r = 0;
+                conv_ref(n.left, &l); conv_ref(n.right, &r);  // range-checked above
                 Box bl = child_box(n.left), br = child_box(n.right);
                 NodeDev nd;
                 nd.q0 = make_float4(bl.mn[0], bl.mn[1], bl.mn[2], bl.mx[0]);
@@ -532,14 +648,21 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
                 own_box[2 * i + 1] = make_float4(n.aabb_max[0], n.aabb_max[1], n.aabb_max[2], 0.0f);
             }
         });
-        if (node_error.load()) return fail(RT_EINVAL, node_error.load());
-        for (uint32_t i = 0; i < d.n_nodes; ++i)  // parent links (every child reference was range-checked above)
+        for (uint32_t i = 0; i < d.n_nodes; ++i)  // parent links
             for (uint32_t ch : {d.nodes[i].left, d.nodes[i].right})
                 if (!(ch & RT_LEAF_BIT)) own_box[2 * (size_t)ch].w = u2f(i);
-    }
+        ms_ref_nodes = ms_since(t0);
+        up.post([&]() -> int {
+            CU(sc.nodes.alloc(std::max<size_t>(nodes.size(), 1)));
+            CU(sc.own_box.alloc(std::max<size_t>(own_box.size(), 2)));
+            if (!nodes.empty()) UP(sc.nodes.p, nodes.data(), nodes.size() * sizeof(NodeDev));
+            if (!nodes.empty()) UP(sc.own_box.p, own_box.data(), own_box.size() * sizeof(float4));
+            sc.device_bytes += nodes.size() * (sizeof(NodeDev) + 2 * sizeof(float4));
+            return RT_OK;
+        });
+    });
+
     // depth of the tree (iterative DFS; also rejects cycles by bounding the visit count)
-    uint32_t root;
-    if (!conv_ref(d.root, &root)) return fail(RT_EINVAL, "root reference out of range");
     uint32_t depth = 0;
     if (!(root & RT_REF_LEAF)) {
         std::vector<std::pair<uint32_t, uint32_t>> st;
@@ -550,9 +673,8 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
             st.pop_back();
             if (++visited > (size_t)d.n_nodes) return fail(RT_EINVAL, "BVH is not a tree");
             depth = std::max(depth, dep);
-            uint32_t ch[2] = {nodes[nd].q3.x, nodes[nd].q3.y};
-            for (uint32_t c : ch)
-                if (!(c & RT_REF_LEAF)) st.push_back({c, dep + 1});
+            for (uint32_t c : {d.nodes[nd].left, d.nodes[nd].right})
+                if (!(c & RT_LEAF_BIT)) st.push_back({c, dep + 1});
         }
     }
     sc.depth = depth;
@@ -573,18 +695,74 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         });
         sc.boxes_are_bounds = bounds_ok.load();
     }
+    lap("tree depth + bounds check");
 
-    lap("reference nodes + depth");
     // Row f4: second topology (SAH) over the same elements.  Wrapped elements enter it with their true world-space bounds
     // (fbox; the reference's own boxes for them are not bounds, Q2); a volume's draw is keyed by the element, so it does not
     // depend on the tree that reaches it.
-    std::vector<NodeDev> nodes2;
-    std::vector<float4> vis_box;
     uint32_t root2 = 0;
-    if (N >= (uint32_t)std::max(2, O.rebuild_min_items) && O.rebuild && sc.boxes_are_bounds && (!any_wrap || (O.rebuild_wrapped && times_ok))) {
-        std::vector<rt_rebuild::Box3> lb(N);
-        std::vector<float> tri;
-        std::vector<uint8_t> is_tri(N, 0);
+    const bool rebuild = N >= (uint32_t)std::max(2, O.rebuild_min_items) && O.rebuild && sc.boxes_are_bounds && (!any_wrap || (O.rebuild_wrapped && times_ok));
+    const bool want_ranks = rebuild && !any_wrap && !(root & RT_REF_LEAF);
+    // Helper 2: the reference parent's box of every element — the visibility proof of a fast-path hit (ref_visible).
+    // Helper 3: equal-t ties on the fast path (plain scenes): the reference returns the element its ordered DFS visits first, and
+    // that order depends only on the signs of the ray direction (hittable.rs:441-445) — one leaf order per octant, 8 x n_items ranks.
+    ScopedThread h_vis, h_ranks;
+    if (rebuild) {
+        vis_box.resize_discard(2 * (size_t)N);
+        h_vis.start([&](std::string&) {
+            const auto t0 = std::chrono::steady_clock::now();
+            rt_rebuild::parallel_for(vis_box.size(), 1 << 18, [&](size_t lo, size_t hi) { std::fill(vis_box.data() + lo, vis_box.data() + hi, make_float4(0, 0, 0, 0)); });
+            rt_rebuild::parallel_for(d.n_nodes, 65536, [&](size_t lo, size_t hi) {  // every element has one parent: the writes do not collide
+                for (size_t i = lo; i < hi; ++i)
+                    for (uint32_t ch : {d.nodes[i].left, d.nodes[i].right})
+                        if (ch & RT_LEAF_BIT) {
+                            const uint32_t item = ch & ~RT_LEAF_BIT;
+                            vis_box[2 * (size_t)item] = make_float4(d.nodes[i].aabb_min[0], d.nodes[i].aabb_min[1], d.nodes[i].aabb_min[2], u2f((uint32_t)i));  // .w: the parent node
+                            vis_box[2 * (size_t)item + 1] = make_float4(d.nodes[i].aabb_max[0], d.nodes[i].aabb_max[1], d.nodes[i].aabb_max[2], 0.0f);
+                        }
+            });
+            ms_vis = ms_since(t0);
+        });
+    }
+    if (want_ranks) {
+        visit_rank.resize_discard(8 * (size_t)N);
+        h_ranks.start([&](std::string&) {
+            const auto t0 = std::chrono::steady_clock::now();
+            rt_rebuild::parallel_for(visit_rank.size(), 1 << 20, [&](size_t lo, size_t hi) { std::fill(visit_rank.data() + lo, visit_rank.data() + hi, 0u); });
+            // octants 0..3 by an ordered DFS each; the complementary octant (7 - o) flips the child order at EVERY node, i.e. visits the
+            // leaves in exactly the reverse order: rank = N - 1 - rank
+            rt_rebuild::parallel_for(4, 1, [&](size_t o_lo, size_t o_hi) {
+                std::vector<uint32_t> st;
+                for (size_t oct = o_lo; oct < o_hi; ++oct) {
+                    uint32_t next = 0;
+                    st.clear();
+                    st.push_back(d.root);
+                    uint32_t* fwd = visit_rank.data() + oct * N;
+                    uint32_t* rev = visit_rank.data() + (7 - oct) * N;
+                    while (!st.empty()) {
+                        const uint32_t r = st.back();
+                        st.pop_back();
+                        if (r & RT_LEAF_BIT) {
+                            const uint32_t item = r & ~RT_LEAF_BIT;
+                            fwd[item] = next; rev[item] = N - 1u - next;
+                            ++next;
+                            continue;
+                        }
+                        const RtBvhNode& n = d.nodes[r];
+                        const bool left_first = ((oct >> n.axis_id) & 1u) != 0u;
+                        st.push_back(left_first ? n.right : n.left);  // visited second
+                        st.push_back(left_first ? n.left : n.right);
+                    }
+                }
+            });
+            ms_ranks = ms_since(t0);
+        });
+    }
+    if (rebuild) {
+        Buffer<rt_rebuild::Box3> lb;
+        lb.resize_discard(N);
+        Buffer<float> tri;
+        Buffer<uint8_t> is_tri;
         rt_rebuild::parallel_for(N, 65536, [&](size_t lo, size_t hi) {
             for (size_t i = lo; i < hi; ++i)
                 for (int k = 0; k < 3; ++k) { lb[i].mn[k] = fbox[i].mn[k]; lb[i].mx[k] = fbox[i].mx[k]; }
@@ -592,7 +770,8 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         // pre-split sliver triangles into several references (rt_rebuild.hpp); the budget shrinks for very large scenes
         const double factor = O.presplit <= 100 ? 1.0 : std::min((double)O.presplit / 100.0, N <= 150000u ? 16.0 : (N <= 2000000u ? 2.0 : 1.0));
         if (factor > 1.0) {
-            tri.resize(9 * (size_t)N);
+            tri.resize_discard(9 * (size_t)N);
+            is_tri.resize_discard(N);
             rt_rebuild::parallel_for(N, 65536, [&](size_t lo, size_t hi) {
                 for (size_t i = lo; i < hi; ++i) {
                     const bool t = d.items[i].kind == RT_GEO_TRIANGLE && !d.items[i].wrap_flags;  // wrapped triangles keep one reference
@@ -601,31 +780,19 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
                 }
             });
         }
-        std::vector<rt_rebuild::Ref> refs;
-        rt_rebuild::presplit(lb, tri, is_tri, (size_t)((double)N * factor), refs);
+        Buffer<rt_rebuild::Ref> refs;
+        rt_rebuild::presplit(lb.data(), N, tri.data(), is_tri.data(), (size_t)((double)N * factor), refs);
         lap("pre-split references");
-        std::vector<rt_rebuild::Box3> rbx(refs.size());
-        rt_rebuild::parallel_for(refs.size(), 65536, [&](size_t lo, size_t hi) {
-            for (size_t i = lo; i < hi; ++i) rbx[i] = refs[i].box;
-        });
         rt_rebuild::Tree F;
         uint32_t extra_levels = 0;
         while (((size_t)N << extra_levels) < refs.size()) ++extra_levels;
-        rt_rebuild::build(rbx, depth + extra_levels + (uint32_t)std::max(0, O.rebuild_depth_extra), F);
+        // the builder also collects, bottom-up, each node's maxima of the two guard-band coefficients of the elements below it
+        rt_rebuild::build(refs, fastA.data(), fastC.data(), depth + extra_levels + (uint32_t)std::max(0, O.rebuild_depth_extra), F);
         lap("SAH build");
         const uint32_t n2 = (uint32_t)F.left.size();
         auto item_of = [&](uint32_t leafref) -> uint32_t { return refs[leafref & ~RT_LEAF_BIT].item; };
-        std::vector<float> a2(n2, 0.0f), c2(n2, 0.0f);
-        for (uint32_t ii = n2; ii-- > 0;) {  // pre-order numbering: children have larger indices
-            float a = 0.0f, c = 0.0f;
-            for (uint32_t ch : {F.left[ii], F.right[ii]}) {
-                if (ch & RT_LEAF_BIT) { a = std::max(a, fastA[item_of(ch)]); c = std::max(c, fastC[item_of(ch)]); }
-                else { a = std::max(a, a2[ch]); c = std::max(c, c2[ch]); }
-            }
-            a2[ii] = a; c2[ii] = c;
-        }
-        nodes2.resize(n2);
-        auto box2 = [&](uint32_t r) -> rt_rebuild::Box3 { return (r & RT_LEAF_BIT) ? rbx[r & ~RT_LEAF_BIT] : F.box[r]; };
+        nodes2.resize_discard(n2);
+        auto box2 = [&](uint32_t r) -> rt_rebuild::Box3 { return (r & RT_LEAF_BIT) ? refs[r & ~RT_LEAF_BIT].box : F.box[r]; };
         auto ref2 = [&](uint32_t r) -> uint32_t { return (r & RT_LEAF_BIT) ? ref_of_item(item_of(r)) : r; };
         rt_rebuild::parallel_for(n2, 32768, [&](size_t lo, size_t hi) {
             for (size_t i = lo; i < hi; ++i) {
@@ -634,55 +801,46 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
                 nd.q0 = make_float4(bl.mn[0], bl.mn[1], bl.mn[2], bl.mx[0]);
                 nd.q1 = make_float4(bl.mx[1], bl.mx[2], br.mn[0], br.mn[1]);
                 nd.q2 = make_float4(br.mn[2], br.mx[0], br.mx[1], br.mx[2]);
-                nd.q3 = make_uint4(ref2(F.left[i]), ref2(F.right[i]), F.axis[i], pack_margin(a2[i], c2[i]));
+                nd.q3 = make_uint4(ref2(F.left[i]), ref2(F.right[i]), F.axis[i], pack_margin(F.band_a[i], F.band_c[i]));
                 nodes2[i] = nd;
             }
         });
         root2 = ref2(F.root);
         sc.depth2 = F.depth;
-        // the reference parent's box of every element: the visibility proof of a fast-path hit (ref_visible)
-        vis_box.assign(2 * (size_t)N, make_float4(0, 0, 0, 0));
-        for (uint32_t i = 0; i < d.n_nodes; ++i)
-            for (uint32_t ch : {d.nodes[i].left, d.nodes[i].right})
-                if (ch & RT_LEAF_BIT) {
-                    const uint32_t item = ch & ~RT_LEAF_BIT;
-                    vis_box[2 * (size_t)item] = make_float4(d.nodes[i].aabb_min[0], d.nodes[i].aabb_min[1], d.nodes[i].aabb_min[2], u2f(i));  // .w: the parent node
-                    vis_box[2 * (size_t)item + 1] = make_float4(d.nodes[i].aabb_max[0], d.nodes[i].aabb_max[1], d.nodes[i].aabb_max[2], 0.0f);
-                }
+        if (!nodes2.empty())
+            up.post([&]() -> int {
+                CU(sc.nodes2.alloc(nodes2.size()));
+                UP(sc.nodes2.p, nodes2.data(), nodes2.size() * sizeof(NodeDev));
+                sc.device_bytes += nodes2.size() * sizeof(NodeDev);
+                return RT_OK;
+            });
+        lap("pack accelerator nodes");
     }
-
-    // Equal-t ties on the fast path (plain scenes): the reference returns the element its ordered DFS visits first, and that order
-    // depends only on the signs of the ray direction (hittable.rs:441-445) — one leaf order per octant, 8 x n_items ranks.
-    std::vector<uint32_t> visit_rank;
-    if (!nodes2.empty() && !any_wrap && !(root & RT_REF_LEAF)) {
-        visit_rank.resize(8 * (size_t)N);
-        // octants 0..3 by an ordered DFS each; the complementary octant (7 - o) flips the child order at EVERY node, i.e. visits the
-        // leaves in exactly the reverse order: rank = N - 1 - rank
-        rt_rebuild::parallel_for(4, 1, [&](size_t o_lo, size_t o_hi) {
-            std::vector<uint32_t> st;
-            for (size_t oct = o_lo; oct < o_hi; ++oct) {
-                uint32_t next = 0;
-                st.clear();
-                st.push_back(root);
-                uint32_t* fwd = visit_rank.data() + oct * N;
-                uint32_t* rev = visit_rank.data() + (7 - oct) * N;
-                while (!st.empty()) {
-                    const uint32_t r = st.back();
-                    st.pop_back();
-                    if (r & RT_REF_LEAF) {
-                        const uint32_t item = r & RT_REF_ITEM_MASK;
-                        fwd[item] = next; rev[item] = N - 1u - next;
-                        ++next;
-                        continue;
-                    }
-                    const bool left_first = ((oct >> nodes[r].q3.z) & 1u) != 0u;
-                    st.push_back(left_first ? nodes[r].q3.y : nodes[r].q3.x);  // visited second
-                    st.push_back(left_first ? nodes[r].q3.x : nodes[r].q3.y);
-                }
+    h_ref.join();
+    h_vis.join();
+    h_ranks.join();
+    for (const std::string* e : {&h_ref.error, &h_vis.error, &h_ranks.error})
+        if (!e->empty()) return fail(RT_ENOMEM, "scene packing: " + *e);
+    if (rebuild && !nodes2.empty())
+        up.post([&]() -> int {
+            CU(sc.vis_box.alloc(vis_box.size()));
+            UP(sc.vis_box.p, vis_box.data(), vis_box.size() * sizeof(float4));
+            sc.device_bytes += vis_box.size() * sizeof(float4);
+            if (want_ranks) {
+                CU(sc.visit_rank.alloc(visit_rank.size()));
+                UP(sc.visit_rank.p, visit_rank.data(), visit_rank.size() * sizeof(uint32_t));
+                sc.device_bytes += visit_rank.size() * sizeof(uint32_t);
             }
+            return RT_OK;
         });
+    {
+        const int rc_up = up.finish();
+        lap("helpers + uploads (tail)");
+        if (pack_log)
+            std::fprintf(stderr, "[rt_scene_create]   beside the build: reference nodes %.1f ms, parent boxes %.1f ms, visit ranks %.1f ms, uploads %.1f ms\n",
+                         ms_ref_nodes, ms_vis, ms_ranks, up.busy_ms);
+        if (rc_up != RT_OK) return rc_up;
     }
-    lap("pack accelerator nodes");
     SceneDev& S = sc.dev;
     std::memset(&S, 0, sizeof(S));
     S.root = root;
@@ -718,47 +876,8 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     S.light_r0lo = d.light_r0[0]; S.light_r0hi = d.light_r0[1];
     S.light_r1lo = d.light_r1[0]; S.light_r1hi = d.light_r1[1];
 
-    // upload
-#define UP(dst, src, bytes) do { int rc_up_ = upload_staged(sc.device, (dst), (src), (bytes)); if (rc_up_) return rc_up_; } while (0)
+    // the large arrays are on the device already (Uploader above); the small tables follow from this thread
     CU(cudaSetDevice(sc.device));
-    {   // one attribute, cached per device (cudaGetDeviceProperties walks every attribute and can take tens of milliseconds)
-        static std::mutex mu;
-        static std::map<int, int> sm_of;
-        std::lock_guard<std::mutex> lk(mu);
-        auto it = sm_of.find(sc.device);
-        if (it == sm_of.end()) {
-            int v = 0;
-            CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, sc.device));
-            it = sm_of.emplace(sc.device, v).first;
-        }
-        sc.sm_count = it->second;
-    }
-    CU(sc.nodes.alloc(std::max<size_t>(nodes.size(), 1)));
-    CU(sc.prims.alloc(N));
-    CU(sc.shade.alloc(N));
-    CU(sc.own_box.alloc(std::max<size_t>(own_box.size(), 2)));
-    if (any_wrap) {
-        CU(sc.wraps.alloc(N));
-        UP(sc.wraps.p, wraps.data(), N * sizeof(WrapDev));
-        sc.device_bytes += (uint64_t)N * sizeof(WrapDev);
-    }
-    if (!nodes.empty()) UP(sc.nodes.p, nodes.data(), nodes.size() * sizeof(NodeDev));
-    if (!nodes.empty()) UP(sc.own_box.p, own_box.data(), own_box.size() * sizeof(float4));
-    UP(sc.prims.p, prims.data(), N * sizeof(PrimDev));
-    UP(sc.shade.p, shade.data(), N * sizeof(ShadeDev));
-    sc.device_bytes += nodes.size() * (sizeof(NodeDev) + 2 * sizeof(float4)) + (uint64_t)N * (sizeof(PrimDev) + sizeof(ShadeDev));
-    if (!nodes2.empty()) {
-        CU(sc.nodes2.alloc(nodes2.size()));
-        CU(sc.vis_box.alloc(vis_box.size()));
-        UP(sc.nodes2.p, nodes2.data(), nodes2.size() * sizeof(NodeDev));
-        UP(sc.vis_box.p, vis_box.data(), vis_box.size() * sizeof(float4));
-        sc.device_bytes += nodes2.size() * sizeof(NodeDev) + vis_box.size() * sizeof(float4);
-    }
-    if (!visit_rank.empty()) {
-        CU(sc.visit_rank.alloc(visit_rank.size()));
-        UP(sc.visit_rank.p, visit_rank.data(), visit_rank.size() * sizeof(uint32_t));
-        sc.device_bytes += visit_rank.size() * sizeof(uint32_t);
-    }
 
     std::vector<const uint8_t*> img_dev(d.n_images, nullptr);
     for (uint32_t i = 0; i < d.n_images; ++i) {
@@ -1357,7 +1476,11 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene) {
     if (!sc) return fail(RT_ENOMEM, "out of host memory");
     sc->device = device;
     const Options O = options_snapshot();
+    const auto t_create = std::chrono::steady_clock::now();
     int rc = guarded([&] { return pack_scene(*desc, *sc, O); });
+    if (std::getenv("RT_PACK_LOG"))
+        std::fprintf(stderr, "[rt_scene_create] total (with the release of the host buffers) %8.1f ms\n",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_create).count());
     if (rc != RT_OK) {
         delete sc;
         return rc;

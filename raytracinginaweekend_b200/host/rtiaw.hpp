@@ -18,6 +18,7 @@
 #include <numeric>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "b200rt.h"
@@ -481,12 +482,22 @@ public:
     World& operator=(const World&) = delete;
 
     // Flatten into the C-ABI description (pointers stay valid while *this and `items_scratch` live).
-    RtSceneDesc describe(std::vector<RtItem>& items_scratch, std::vector<RtImage>& images_scratch, std::vector<RtPerlin>& perlins_scratch) const {
+    // Uninitialised item records, written on all cores (every field of every record is set below): the flat form of 10^6 elements
+    // is 140 MB, and this step is part of every scene hand-off.
+    struct ItemArray {
+        std::unique_ptr<RtItem[]> p;
+        size_t n = 0;
+    };
+    RtSceneDesc describe(ItemArray& items_scratch, std::vector<RtImage>& images_scratch, std::vector<RtPerlin>& perlins_scratch) const {
         const Scene& sc = *hittable;
-        items_scratch.resize(sc.elements.size());
-        for (size_t i = 0; i < sc.elements.size(); ++i) {
+        const size_t n_items = sc.elements.size();
+        items_scratch.p.reset(new RtItem[n_items]);
+        items_scratch.n = n_items;
+        RtItem* const items_out = items_scratch.p.get();
+        auto fill = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
             const SurfaceGeometry& e = sc.elements[i];
-            RtItem& it = items_scratch[i];
+            RtItem& it = items_out[i];
             e.geometry.write(it);
             it.material = e.material;
             it.wrap_flags = (e.has_transformation ? (uint32_t)RT_WRAP_TRANSFORMATION : 0u) | (e.has_animation ? (uint32_t)RT_WRAP_ANIMATION : 0u) |
@@ -496,6 +507,14 @@ public:
             it.transform[3] = e.transformation.y_sine; it.transform[4] = e.transformation.y_cosine;
             it.velocity[0] = e.velocity.x; it.velocity[1] = e.velocity.y; it.velocity[2] = e.velocity.z;
         }
+        };
+        {
+            const size_t parts = std::max<size_t>(1, std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), n_items / 32768));
+            std::vector<std::thread> pool;
+            for (size_t q = 1; q < parts; ++q) pool.emplace_back([&, q] { fill(n_items * q / parts, n_items * (q + 1) / parts); });
+            fill(0, n_items / parts);
+            for (auto& t : pool) t.join();
+        }
         images_scratch.clear();
         for (const ImageData& im : tables->images) images_scratch.push_back(RtImage{im.width, im.height, im.rgb8.data()});
         perlins_scratch.clear();
@@ -503,8 +522,8 @@ public:
         RtSceneDesc d{};
         d.n_perlins = (uint32_t)perlins_scratch.size();
         d.perlins = perlins_scratch.data();
-        d.n_items = (uint32_t)items_scratch.size();
-        d.items = items_scratch.data();
+        d.n_items = (uint32_t)items_scratch.n;
+        d.items = items_scratch.p.get();
         d.n_nodes = (uint32_t)sc.bvh.nodes.size();
         d.nodes = sc.bvh.nodes.data();
         d.root = sc.bvh.initial_index;
@@ -540,7 +559,7 @@ public:
     RtScene* device(int device_ordinal = 0) const {
         if (dev_ && dev_ordinal_ == device_ordinal) return dev_;
         release_device();
-        std::vector<RtItem> items;
+        ItemArray items;
         std::vector<RtImage> images;
         std::vector<RtPerlin> perlins;
         RtSceneDesc d = describe(items, images, perlins);

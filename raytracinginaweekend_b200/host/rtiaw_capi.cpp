@@ -153,7 +153,7 @@ int rtw_world_export(const RtwWorld* w, RtItem* items, RtBvhNode* nodes, RtMater
                      uint32_t* image_wh, float* cam, float* bg, float* light) {
     return guard([&] {
         const World& W = *w->world;
-        std::vector<RtItem> it;
+        World::ItemArray it;
         std::vector<RtImage> im;
         std::vector<RtPerlin> pn;
         RtSceneDesc d = W.describe(it, im, pn);

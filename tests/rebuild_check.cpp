@@ -49,7 +49,7 @@ int main(int argc, char** argv) {
             for (int k = 0; k < 3; ++k) { const float c = 10.0f * U(rng); leaf[i].mn[k] = c - r; leaf[i].mx[k] = c + r; }
         }
     }
-    std::vector<Ref> refs;
+    Buffer<Ref> refs;
     presplit(leaf, tri, is_tri, (size_t)((double)n * factor), refs);
     CHECK(refs.size() >= n && refs.size() <= std::max(n, (size_t)((double)n * factor)), "reference count %zu", refs.size());
     std::vector<std::vector<uint32_t>> of(n);
