@@ -14,6 +14,7 @@
 #include <condition_variable>
 #include <deque>
 #include <functional>
+#include <future>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -133,7 +134,7 @@ struct Workspace {
     static const int ITER_LOG_CAP = 16384;
     size_t ws_slots = 0;
     // film download into a caller's pageable buffer: two pinned staging chunks, DMA of chunk i+1 overlapped with the host copy of chunk i
-    static const size_t STAGE_BYTES = (size_t)4 << 20;
+    static const size_t STAGE_BYTES = (size_t)16 << 20;
     char* h_stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_event[2] = {};
     cudaStream_t copy_stream = nullptr;
@@ -262,6 +263,17 @@ inline float u2f(uint32_t u) {
     return f;
 }
 
+// Pageable <-> pinned copies of a staging chunk on up to four threads: one core copies at 5-6 GB/s, less than a quarter of what the DMA
+// engine moves, so a single-threaded copy was what a 100 MB film download or a 128 MB node upload waited for.
+static void copy_mt(void* dst, const void* src, size_t len) {
+    const size_t parts = std::min<size_t>(4, len >> 21);
+    if (parts < 2) { std::memcpy(dst, src, len); return; }
+    std::thread th[3];
+    for (size_t p = 1; p < parts; ++p)
+        th[p - 1] = std::thread([=] { std::memcpy(static_cast<char*>(dst) + len * p / parts, static_cast<const char*>(src) + len * p / parts, len * (p + 1) / parts - len * p / parts); });
+    std::memcpy(dst, src, len / parts);
+    for (size_t p = 1; p < parts; ++p) th[p - 1].join();
+}
 // Pinned staging chunks of a device's workspace (created on first use; the caller holds ws.mu).
 int ensure_staging(Workspace& ws) {
     if (ws.h_stage[0]) return RT_OK;
@@ -285,7 +297,7 @@ int upload_staged(int device, void* d_dst, const void* src, size_t bytes) {
     for (size_t i = 0; i < n_chunks; ++i) {
         const size_t off = i * C, len = std::min(C, bytes - off);
         if (i >= 2) CU(cudaEventSynchronize(ws.stage_event[i & 1]));  // the DMA that last read this chunk has finished
-        std::memcpy(ws.h_stage[i & 1], static_cast<const char*>(src) + off, len);
+        copy_mt(ws.h_stage[i & 1], static_cast<const char*>(src) + off, len);
         CU(cudaMemcpyAsync(static_cast<char*>(d_dst) + off, ws.h_stage[i & 1], len, cudaMemcpyHostToDevice, ws.copy_stream));
         CU(cudaEventRecord(ws.stage_event[i & 1], ws.copy_stream));
     }
@@ -662,22 +674,33 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         });
     });
 
-    // depth of the tree (iterative DFS; also rejects cycles by bounding the visit count)
+    // Helper 0: depth of the tree (iterative DFS; also rejects cycles by bounding the visit count).  Sequential, and only the
+    // accelerator build needs the number: it runs beside the pre-split.  The visit-rank walks below wait for its verdict first
+    // (they would not terminate on a cyclic graph).
     uint32_t depth = 0;
-    if (!(root & RT_REF_LEAF)) {
-        std::vector<std::pair<uint32_t, uint32_t>> st;
-        st.push_back({root, 1u});
-        size_t visited = 0;
-        while (!st.empty()) {
-            auto [nd, dep] = st.back();
-            st.pop_back();
-            if (++visited > (size_t)d.n_nodes) return fail(RT_EINVAL, "BVH is not a tree");
-            depth = std::max(depth, dep);
-            for (uint32_t c : {d.nodes[nd].left, d.nodes[nd].right})
-                if (!(c & RT_LEAF_BIT)) st.push_back({c, dep + 1});
-        }
-    }
-    sc.depth = depth;
+    std::promise<bool> depth_promise;
+    std::shared_future<bool> tree_ok = depth_promise.get_future().share();
+    ScopedThread h_depth;
+    h_depth.start([&](std::string& err) {
+        bool ok = false;
+        try {
+            ok = true;
+            if (!(root & RT_REF_LEAF)) {
+                std::vector<std::pair<uint32_t, uint32_t>> st;
+                st.push_back({root, 1u});
+                size_t visited = 0;
+                while (!st.empty() && ok) {
+                    auto [nd, dep] = st.back();
+                    st.pop_back();
+                    if (++visited > (size_t)d.n_nodes) { ok = false; break; }
+                    depth = std::max(depth, dep);
+                    for (uint32_t c : {d.nodes[nd].left, d.nodes[nd].right})
+                        if (!(c & RT_LEAF_BIT)) st.push_back({c, dep + 1});
+                }
+            }
+        } catch (const std::exception& e) { err = e.what(); ok = false; }
+        depth_promise.set_value(ok);
+    });
 
     // The tight cull (MODE >= 1) and the visibility proof of MODE 3 rely on what the reference builder guarantees: a node's box
     // contains the boxes of its children (it is their union).  A caller-made tree that breaks this is still traversed exactly
@@ -695,7 +718,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         });
         sc.boxes_are_bounds = bounds_ok.load();
     }
-    lap("tree depth + bounds check");
+    lap("bounds check");
 
     // Row f4: second topology (SAH) over the same elements.  Wrapped elements enter it with their true world-space bounds
     // (fbox; the reference's own boxes for them are not bounds, Q2); a volume's draw is keyed by the element, so it does not
@@ -722,11 +745,18 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
                         }
             });
             ms_vis = ms_since(t0);
+            up.post([&]() -> int {
+                CU(sc.vis_box.alloc(vis_box.size()));
+                UP(sc.vis_box.p, vis_box.data(), vis_box.size() * sizeof(float4));
+                sc.device_bytes += vis_box.size() * sizeof(float4);
+                return RT_OK;
+            });
         });
     }
     if (want_ranks) {
         visit_rank.resize_discard(8 * (size_t)N);
         h_ranks.start([&](std::string&) {
+            if (!tree_ok.get()) return;
             const auto t0 = std::chrono::steady_clock::now();
             rt_rebuild::parallel_for(visit_rank.size(), 1 << 20, [&](size_t lo, size_t hi) { std::fill(visit_rank.data() + lo, visit_rank.data() + hi, 0u); });
             // octants 0..3 by an ordered DFS each; the complementary octant (7 - o) flips the child order at EVERY node, i.e. visits the
@@ -756,6 +786,12 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
                 }
             });
             ms_ranks = ms_since(t0);
+            up.post([&]() -> int {
+                CU(sc.visit_rank.alloc(visit_rank.size()));
+                UP(sc.visit_rank.p, visit_rank.data(), visit_rank.size() * sizeof(uint32_t));
+                sc.device_bytes += visit_rank.size() * sizeof(uint32_t);
+                return RT_OK;
+            });
         });
     }
     if (rebuild) {
@@ -783,6 +819,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         Buffer<rt_rebuild::Ref> refs;
         rt_rebuild::presplit(lb.data(), N, tri.data(), is_tri.data(), (size_t)((double)N * factor), refs);
         lap("pre-split references");
+        if (!tree_ok.get()) return fail(RT_EINVAL, h_depth.error.empty() ? "BVH is not a tree" : "scene packing: " + h_depth.error);
         rt_rebuild::Tree F;
         uint32_t extra_levels = 0;
         while (((size_t)N << extra_levels) < refs.size()) ++extra_levels;
@@ -794,45 +831,35 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         nodes2.resize_discard(n2);
         auto box2 = [&](uint32_t r) -> rt_rebuild::Box3 { return (r & RT_LEAF_BIT) ? refs[r & ~RT_LEAF_BIT].box : F.box[r]; };
         auto ref2 = [&](uint32_t r) -> uint32_t { return (r & RT_LEAF_BIT) ? ref_of_item(item_of(r)) : r; };
-        rt_rebuild::parallel_for(n2, 32768, [&](size_t lo, size_t hi) {
-            for (size_t i = lo; i < hi; ++i) {
-                const rt_rebuild::Box3 bl = box2(F.left[i]), br = box2(F.right[i]);
-                NodeDev nd;
-                nd.q0 = make_float4(bl.mn[0], bl.mn[1], bl.mn[2], bl.mx[0]);
-                nd.q1 = make_float4(bl.mx[1], bl.mx[2], br.mn[0], br.mn[1]);
-                nd.q2 = make_float4(br.mn[2], br.mx[0], br.mx[1], br.mx[2]);
-                nd.q3 = make_uint4(ref2(F.left[i]), ref2(F.right[i]), F.axis[i], pack_margin(F.band_a[i], F.band_c[i]));
-                nodes2[i] = nd;
-            }
-        });
+        // packed and uploaded in slices: the copy of one slice runs while the next is being packed
+        if (n2) up.post([&]() -> int { CU(sc.nodes2.alloc(nodes2.size())); sc.device_bytes += nodes2.size() * sizeof(NodeDev); return RT_OK; });
+        const size_t SLICE = (size_t)1 << 19;  // 32 MB of node records
+        for (size_t s0 = 0; s0 < n2; s0 += SLICE) {
+            const size_t s1 = std::min<size_t>(n2, s0 + SLICE);
+            rt_rebuild::parallel_for(s1 - s0, 32768, [&](size_t lo, size_t hi) {
+                for (size_t i = s0 + lo; i < s0 + hi; ++i) {
+                    const rt_rebuild::Box3 bl = box2(F.left[i]), br = box2(F.right[i]);
+                    NodeDev nd;
+                    nd.q0 = make_float4(bl.mn[0], bl.mn[1], bl.mn[2], bl.mx[0]);
+                    nd.q1 = make_float4(bl.mx[1], bl.mx[2], br.mn[0], br.mn[1]);
+                    nd.q2 = make_float4(br.mn[2], br.mx[0], br.mx[1], br.mx[2]);
+                    nd.q3 = make_uint4(ref2(F.left[i]), ref2(F.right[i]), F.axis[i], pack_margin(F.band_a[i], F.band_c[i]));
+                    nodes2[i] = nd;
+                }
+            });
+            up.post([&, s0, s1]() -> int { UP(sc.nodes2.p + s0, nodes2.data() + s0, (s1 - s0) * sizeof(NodeDev)); return RT_OK; });
+        }
         root2 = ref2(F.root);
         sc.depth2 = F.depth;
-        if (!nodes2.empty())
-            up.post([&]() -> int {
-                CU(sc.nodes2.alloc(nodes2.size()));
-                UP(sc.nodes2.p, nodes2.data(), nodes2.size() * sizeof(NodeDev));
-                sc.device_bytes += nodes2.size() * sizeof(NodeDev);
-                return RT_OK;
-            });
         lap("pack accelerator nodes");
     }
+    if (!tree_ok.get()) return fail(RT_EINVAL, h_depth.error.empty() ? "BVH is not a tree" : "scene packing: " + h_depth.error);
+    sc.depth = depth;
     h_ref.join();
     h_vis.join();
     h_ranks.join();
     for (const std::string* e : {&h_ref.error, &h_vis.error, &h_ranks.error})
         if (!e->empty()) return fail(RT_ENOMEM, "scene packing: " + *e);
-    if (rebuild && !nodes2.empty())
-        up.post([&]() -> int {
-            CU(sc.vis_box.alloc(vis_box.size()));
-            UP(sc.vis_box.p, vis_box.data(), vis_box.size() * sizeof(float4));
-            sc.device_bytes += vis_box.size() * sizeof(float4);
-            if (want_ranks) {
-                CU(sc.visit_rank.alloc(visit_rank.size()));
-                UP(sc.visit_rank.p, visit_rank.data(), visit_rank.size() * sizeof(uint32_t));
-                sc.device_bytes += visit_rank.size() * sizeof(uint32_t);
-            }
-            return RT_OK;
-        });
     {
         const int rc_up = up.finish();
         lap("helpers + uploads (tail)");
@@ -1422,7 +1449,7 @@ static int download_staged(Workspace& ws, void* dst, const void* d_src, size_t b
         if (i + 1 < n_chunks) { int rc = issue(i + 1); if (rc) { cudaStreamSynchronize(ws.copy_stream); return rc; } }
         CU(cudaEventSynchronize(ws.stage_event[i & 1]));
         const size_t off = i * C, len = std::min(C, bytes - off);
-        std::memcpy(static_cast<char*>(dst) + off, ws.h_stage[i & 1], len);
+        copy_mt(static_cast<char*>(dst) + off, ws.h_stage[i & 1], len);
     }
     return RT_OK;
 }

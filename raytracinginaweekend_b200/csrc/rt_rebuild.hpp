@@ -15,6 +15,9 @@
 #include <cstdint>
 #include <cstring>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <numeric>
@@ -23,16 +26,86 @@
 
 namespace rt_rebuild {
 
+// Worker threads shared by every parallel_for of the process (created on first use).  Starting a thread costs 20-30 us; the scene
+// hand-off of C5 issues ~100 parallel loops (24 pre-split rounds among them), which on 16 cores was a fifth of its run time.
+// Calls may come from several threads at once and from inside a chunk: a caller runs its own first chunk, then helps with
+// whatever is queued until its own chunks are done, so nobody ever waits on a thread that waits on it.
+class Pool {
+  public:
+    struct Job {
+        const std::function<void(size_t, size_t)>* fn;
+        size_t a, b;
+        std::atomic<size_t>* pending;
+    };
+    static Pool& get() {
+        static Pool p;
+        return p;
+    }
+    size_t threads() const { return workers_.size() + 1; }
+    void run(size_t n, size_t parts, const std::function<void(size_t, size_t)>& fn) {
+        std::atomic<size_t> pending{parts - 1};
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (size_t p = 1; p < parts; ++p) q_.push_back(Job{&fn, n * p / parts, n * (p + 1) / parts, &pending});
+        }
+        cv_.notify_all();
+        fn((size_t)0, n / parts);
+        while (pending.load(std::memory_order_acquire) != 0) {
+            Job j;
+            if (pop(j)) exec(j);
+            else std::this_thread::yield();
+        }
+    }
+
+  private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Job> q_;
+    std::vector<std::thread> workers_;
+    bool stop_ = false;
+    Pool() {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        for (unsigned i = 1; i < hw; ++i)
+            workers_.emplace_back([this] {
+                for (;;) {
+                    Job j;
+                    {
+                        std::unique_lock<std::mutex> lk(mu_);
+                        cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                        if (q_.empty()) return;
+                        j = q_.front();
+                        q_.pop_front();
+                    }
+                    exec(j);
+                }
+            });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    bool pop(Job& j) {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (q_.empty()) return false;
+        j = q_.front();
+        q_.pop_front();
+        return true;
+    }
+    static void exec(const Job& j) {
+        (*j.fn)(j.a, j.b);
+        j.pending->fetch_sub(1, std::memory_order_release);
+    }
+};
+
 // Static chunking over hardware threads; fn(begin, end) works on disjoint index ranges, so results do not depend on the thread count.
 template <class F>
 inline void parallel_for(size_t n, size_t min_chunk, F&& fn) {
     const size_t hw = std::max(1u, std::thread::hardware_concurrency());
     const size_t parts = std::max<size_t>(1, std::min(hw, n / std::max<size_t>(1, min_chunk)));
     if (parts <= 1) { fn((size_t)0, n); return; }
-    std::vector<std::thread> pool;
-    for (size_t p = 1; p < parts; ++p) pool.emplace_back([&, p] { fn(n * p / parts, n * (p + 1) / parts); });
-    fn((size_t)0, n / parts);
-    for (auto& t : pool) t.join();
+    const std::function<void(size_t, size_t)> f = [&fn](size_t a, size_t b) { fn(a, b); };
+    Pool::get().run(n, parts, f);
 }
 
 struct Box3 {
@@ -421,8 +494,10 @@ inline Box3 poly_box(const Poly& p, const Box3& within) {
 inline void presplit(const Box3* leaf, size_t n0, const float* tri, const uint8_t* is_tri, size_t budget, Buffer<Ref>& refs) {
     using detail::Poly;
     refs.resize_discard(std::max(budget, n0));  // sized once; `n_refs` of them are live
+    Buffer<double> area;  // scratch: box areas computed in the parallel loops, consumed by the sequential bucket fills
+    area.resize_discard(std::max(n0, budget > n0 ? 2 * (budget - n0) : (size_t)0));
     parallel_for(n0, 65536, [&](size_t a, size_t b) {
-        for (size_t i = a; i < b; ++i) refs[i] = Ref{(uint32_t)i, leaf[i]};
+        for (size_t i = a; i < b; ++i) { refs[i] = Ref{(uint32_t)i, leaf[i]}; area[i] = detail::half_area(leaf[i]); }
     });
     size_t n_refs = n0;
     if (budget <= n0) { refs.n = n0; return; }
@@ -435,7 +510,7 @@ inline void presplit(const Box3* leaf, size_t n0, const float* tri, const uint8_
     struct Cand { double area; uint32_t ref; };
     double tau0 = 0.0;
     for (uint32_t i = 0; i < n0; ++i)
-        if (is_tri[i]) tau0 = std::max(tau0, detail::half_area(leaf[i]));
+        if (is_tri[i]) tau0 = std::max(tau0, area[i]);
     tau0 *= 0.5;
     if (!(tau0 > 0.0) || !std::isfinite(tau0)) { refs.n = n0; return; }
     // bucket j holds the candidates with tau0 / 2^j <= area < tau0 / 2^(j-1)  (bucket 0: everything >= tau0)
@@ -456,9 +531,10 @@ inline void presplit(const Box3* leaf, size_t n0, const float* tri, const uint8_
         if (j >= 0) buckets[(size_t)j].push_back(c);
     };
     for (uint32_t i = 0; i < n0; ++i)
-        if (is_tri[i]) put(Cand{detail::half_area(leaf[i]), i});
+        if (is_tri[i]) put(Cand{area[i], i});
     struct Cut { Box3 bl, bh; double mid; int ax; bool ok; };
     Buffer<Cut> cuts;
+    Buffer<int> piece_bucket;  // of the two pieces of cut c: computed in the parallel loop, the sequential queueing only appends
     std::vector<Cand> cur;
     std::vector<uint32_t> slot;
     for (size_t j = 0; j < buckets.size() && n_refs < budget;) {
@@ -508,6 +584,7 @@ inline void presplit(const Box3* leaf, size_t n0, const float* tri, const uint8_
         // apply: the low half replaces the reference, the high half goes to a new reference at n_refs + (accepted cuts before it);
         // both pieces are smaller than the reference they came from and become candidates again
         slot.resize(k);
+        piece_bucket.resize_discard(2 * k);
         uint32_t n_ok = 0;
         for (size_t c = 0; c < k; ++c) { slot[c] = n_ok; n_ok += cuts[c].ok ? 1u : 0u; }
         const size_t base = n_refs;
@@ -521,13 +598,18 @@ inline void presplit(const Box3* leaf, size_t n0, const float* tri, const uint8_
                 region[r].hi[cuts[c].ax] = cuts[c].mid;
                 hi_region.lo[cuts[c].ax] = cuts[c].mid;
                 region[r2] = hi_region;
+                area[2 * c] = detail::half_area(cuts[c].bl);
+                area[2 * c + 1] = detail::half_area(cuts[c].bh);
+                piece_bucket[2 * c] = bucket_of(area[2 * c]);
+                piece_bucket[2 * c + 1] = bucket_of(area[2 * c + 1]);
             }
         });
         n_refs += n_ok;
+        if (n_refs >= budget) break;  // nothing will be cut any more: the pieces of this round need not be queued
         for (size_t c = 0; c < k; ++c) {
             if (!cuts[c].ok) continue;
-            put(Cand{detail::half_area(cuts[c].bl), cur[c].ref});
-            put(Cand{detail::half_area(cuts[c].bh), (uint32_t)(base + slot[c])});
+            if (piece_bucket[2 * c] >= 0) buckets[(size_t)piece_bucket[2 * c]].push_back(Cand{area[2 * c], cur[c].ref});
+            if (piece_bucket[2 * c + 1] >= 0) buckets[(size_t)piece_bucket[2 * c + 1]].push_back(Cand{area[2 * c + 1], (uint32_t)(base + slot[c])});
         }
     }
     refs.n = n_refs;
