@@ -309,11 +309,13 @@ int upload_staged(int device, void* d_dst, const void* src, size_t bytes) {
 struct ScopedThread {
     std::thread t;
     std::string error;  // set by the body (exceptions included)
+    bool inline_mode = false;  // small scenes: the body runs on the calling thread (starting and waking threads costs more than the work)
     template <class F>
     void start(F&& body) {
-        t = std::thread([this, body]() {
+        auto run = [this, body]() {
             try { body(error); } catch (const std::exception& e) { error = e.what(); } catch (...) { error = "unknown exception"; }
-        });
+        };
+        if (inline_mode) run(); else t = std::thread(run);
     }
     void join() { if (t.joinable()) t.join(); }
     ~ScopedThread() { join(); }
@@ -330,7 +332,17 @@ struct Uploader {
     std::string error;
     double busy_ms = 0.0;
     std::thread t;
+    bool inline_mode = false;  // small scenes: every job runs inside post()
+    void run_job(std::function<int()>& job) {
+        if (rc != RT_OK) return;  // after a failure the remaining jobs are dropped
+        const auto t0 = std::chrono::steady_clock::now();
+        int r;
+        try { r = job(); } catch (const std::exception& e) { r = fail(RT_ENOMEM, e.what()); } catch (...) { r = fail(RT_EINVAL, "unknown exception"); }
+        busy_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (r != RT_OK) { rc = r; error = g_err; }  // g_err is thread-local: carried to the caller by finish()
+    }
     void start() {
+        if (inline_mode) return;
         t = std::thread([this] {
             for (;;) {
                 std::function<int()> job;
@@ -341,16 +353,12 @@ struct Uploader {
                     job = std::move(jobs.front());
                     jobs.pop_front();
                 }
-                if (rc != RT_OK) continue;  // after a failure the remaining jobs are dropped
-                const auto t0 = std::chrono::steady_clock::now();
-                int r;
-                try { r = job(); } catch (const std::exception& e) { r = fail(RT_ENOMEM, e.what()); } catch (...) { r = fail(RT_EINVAL, "unknown exception"); }
-                busy_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-                if (r != RT_OK) { rc = r; error = g_err; }  // g_err is thread-local: carried to the caller by finish()
+                run_job(job);
             }
         });
     }
     void post(std::function<int()> job) {
+        if (inline_mode) { std::lock_guard<std::mutex> lk(mu); run_job(job); return; }
         { std::lock_guard<std::mutex> lk(mu); jobs.push_back(std::move(job)); }
         cv.notify_one();
     }
@@ -583,7 +591,9 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
 
     // Uploads start now, beside the rest of the packing: primitives and shading records first.
 #define UP(dst, src, bytes) do { int rc_up_ = upload_staged(sc.device, (dst), (src), (bytes)); if (rc_up_) return rc_up_; } while (0)
+    const bool threaded = N >= 16384u;  // below: everything on this thread, in the same order
     Uploader up;
+    up.inline_mode = !threaded;
     up.start();
     up.post([&]() -> int {
         CU(cudaSetDevice(sc.device));
@@ -622,6 +632,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     // indices than their parent in the pre-order numbering; verified, otherwise fall back to the global maximum), the 64-byte
     // node records, each node's own box and its parent link; then the upload of both arrays is posted.
     ScopedThread h_ref;
+    h_ref.inline_mode = !threaded;
     h_ref.start([&](std::string&) {
         const auto t0 = std::chrono::steady_clock::now();
         bool preorder = true;
@@ -681,6 +692,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     std::promise<bool> depth_promise;
     std::shared_future<bool> tree_ok = depth_promise.get_future().share();
     ScopedThread h_depth;
+    h_depth.inline_mode = !threaded;
     h_depth.start([&](std::string& err) {
         bool ok = false;
         try {
@@ -730,6 +742,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     // Helper 3: equal-t ties on the fast path (plain scenes): the reference returns the element its ordered DFS visits first, and
     // that order depends only on the signs of the ray direction (hittable.rs:441-445) — one leaf order per octant, 8 x n_items ranks.
     ScopedThread h_vis, h_ranks;
+    h_vis.inline_mode = h_ranks.inline_mode = !threaded;
     if (rebuild) {
         vis_box.resize_discard(2 * (size_t)N);
         h_vis.start([&](std::string&) {

@@ -20,6 +20,8 @@ def checker(tmp_path_factory):
     (9000, 8, 4, 3, 1),        # above the threaded-build threshold, tight depth cap on a sliver nest
     (300, 9, 8, 4, 2),         # coincident centroids: median fallback
     (20000, 10, 1, 1, 0),      # no pre-splitting, threaded build, cap one level above the minimum
+    (300000, 11, 2, 3, 0),     # 600 000 references: splits of >= 2^18 references scan, bin and partition on all cores (worker pool)
+    (600000, 12, 2, 2, 1),     # sliver nests at that size: bucketed pre-split rounds with the budget ending inside a round
 ])
 def test_builder_invariants(checker, n, seed, factor, extra, mode):
     r = subprocess.run([checker, str(n), str(seed), str(factor), str(extra), str(mode)], capture_output=True, text=True, timeout=300)
