@@ -254,6 +254,8 @@ int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_o
  * "rebuild_depth_extra": depth cap of the rebuilt tree above the reference depth (default 4).  "presplit": reference budget of
  * the rebuilt tree in per cent of the element count (default 800; <= 100 = one reference per element): sliver triangles are
  * cut into several references with tighter boxes (an element may sit in several leaves of the accelerator tree).
+ * "presplit_device": 1 (default) = that cutting runs on the device for scenes of >= 16 Ki elements, 0 = on the host cores (same
+ * set of references either way).
  * "count": 1 = maintain node_visits / prim_tests / exact_steps.  "profile": 1 = time extend / shade separately.
  * "refill": busy-lane threshold of the persistent extend warps.  "leaf_weight": phase-vote weight.  "check_every": host
  * polling period (iterations).  "pipes": independent wavefront pipelines (streams) per render (default 0 = auto, 3 for >= 64 Mi path slots, else 4: one
@@ -267,6 +269,14 @@ int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_o
  * share of warp rounds after the queue ran dry / with a lane on the reference tree; RT_PACK_LOG=1 the phase times of
  * rt_scene_create. */
 int rt_set_option(const char* key, int64_t value);
+
+/* Test aid for row f4's pre-split (rt_rebuild.hpp / rt_presplit.cuh), the step of rt_scene_create that cuts sliver triangles into
+ * several references for the accelerator tree (the reference has no counterpart: its tree, hittable.rs:382-427, holds every
+ * element once).  boxes6: n x (min xyz, max xyz); tri9: n x (p0, p1, p2), read where is_tri != 0; budget: references allowed.
+ * device < 0: the host implementation; otherwise the device one on that GPU.  out_items / out_boxes6: room for max(budget, n)
+ * references; *out_n: how many were made.  Both implementations produce the same SET of references (their order differs). */
+int rt_presplit_refs(const float* boxes6, const float* tri9, const uint8_t* is_tri, uint32_t n, uint64_t budget, int device,
+                     uint32_t* out_items, float* out_boxes6, uint64_t* out_n);
 
 /* Frees the per-device render workspaces (path-state queues, per-lane accumulators, streams, events) that the library keeps
  * between renders.  Optional; call it only when no render is in flight.  The next render allocates them again. */

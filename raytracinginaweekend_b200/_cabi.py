@@ -91,7 +91,7 @@ assert MATERIAL_DTYPE.itemsize == C.sizeof(RtMaterial) and TEXTURE_DTYPE.itemsiz
 
 EXPORTED = ["rt_last_error", "rt_device_count", "rt_scene_create", "rt_scene_destroy", "rt_scene_device_bytes", "rt_scene_set_ray_time",
             "rt_trace", "rt_trace_device", "rt_render", "rt_render_device", "rt_render_moments_device", "rt_render_planes_device", "rt_render_multi", "rt_render_multi_device",
-            "rt_film_scale_device", "rt_to_rgb8_gamma2_device", "rt_set_option", "rt_shutdown"]
+            "rt_film_scale_device", "rt_to_rgb8_gamma2_device", "rt_set_option", "rt_presplit_refs", "rt_shutdown"]
 
 _lib = None
 
@@ -138,6 +138,21 @@ def check(rc: int):
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def presplit_refs(boxes6, tri9, is_tri, budget: int, device: int = -1):
+    """rt_presplit_refs (test aid): the references row f4's pre-split makes of n elements; device < 0 = the host implementation."""
+    boxes6 = np.ascontiguousarray(boxes6, dtype=np.float32); tri9 = np.ascontiguousarray(tri9, dtype=np.float32)
+    is_tri = np.ascontiguousarray(is_tri, dtype=np.uint8)
+    n = boxes6.shape[0]
+    cap = max(int(budget), n)
+    items = np.empty(cap, dtype=np.uint32); boxes = np.empty((cap, 6), dtype=np.float32)
+    out_n = C.c_uint64(0)
+    L = lib()
+    L.rt_presplit_refs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    check(L.rt_presplit_refs(boxes6.ctypes.data, tri9.ctypes.data, is_tri.ctypes.data, n, int(budget), int(device), items.ctypes.data,
+                             boxes.ctypes.data, C.byref(out_n)))
+    return items[:out_n.value].copy(), boxes[:out_n.value].copy()
 
 
 def set_option(key: str, value: int):

@@ -28,6 +28,7 @@
 #include "../../include/b200rt.h"
 #include "rt_kernels.cuh"
 #include "rt_rebuild.hpp"
+#include "rt_presplit.cuh"
 
 using namespace rt;
 
@@ -40,6 +41,7 @@ std::mutex g_opt_mu;
 int g_opt_traversal = 3;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path,
                               // 3 = rebuilt topology + per-ray proof, unproven rays on the reference tree with 2 (plain scenes; else 2)
 int g_opt_presplit = 800;     // reference budget of the rebuilt tree in per cent of the element count (<= 100: no pre-splitting)
+int g_opt_presplit_device = 1;  // pre-split on the device (rt_presplit.cuh) for scenes of >= 16 Ki elements; 0 = on the host cores
 int g_opt_rebuild_min_items = 32;  // below this the reference tree is as good (a Cornell box has 8 elements) and nothing has to be proven
 int g_opt_rebuild_wrapped = 1;  // also build it for scenes with wrapped elements / volumes (true world-space bounds)
 int g_opt_rebuild = 1;        // build the second topology at rt_scene_create (0: traversal 3 behaves like 2)
@@ -62,12 +64,13 @@ struct Options {
     int traversal, presplit, rebuild_min_items, rebuild_wrapped, rebuild, rebuild_depth_extra, pipes, leaf_weight, refill, count, profile,
         check_every, blocks_per_sm, debug_skip_redo, tail_budget, carveout;
     int64_t max_slots;
+    int presplit_device;
 };
 Options options_snapshot() {
     std::lock_guard<std::mutex> lk(g_opt_mu);
     return Options{g_opt_traversal, g_opt_presplit, g_opt_rebuild_min_items, g_opt_rebuild_wrapped, g_opt_rebuild, g_opt_rebuild_depth_extra,
                    g_opt_pipes, g_opt_leaf_weight, g_opt_refill, g_opt_count, g_opt_profile, g_opt_check_every, g_opt_blocks_per_sm, g_opt_debug_skip_redo, g_opt_tail_budget, g_opt_carveout,
-                   g_opt_max_slots};
+                   g_opt_max_slots, g_opt_presplit_device};
 }
 
 int fail(int code, const std::string& msg) {
@@ -302,6 +305,30 @@ int upload_staged(int device, void* d_dst, const void* src, size_t bytes) {
         CU(cudaEventRecord(ws.stage_event[i & 1], ws.copy_stream));
     }
     CU(cudaStreamSynchronize(ws.copy_stream));
+    return RT_OK;
+}
+
+// Device -> pageable host through the pinned chunks (the caller holds ws.mu): the DMA of chunk i+1 overlaps the host copy of chunk i.
+static int download_staged(Workspace& ws, void* dst, const void* d_src, size_t bytes) {
+    {
+        int rc = ensure_staging(ws);
+        if (rc) return rc;
+    }
+    const size_t C = Workspace::STAGE_BYTES;
+    const size_t n_chunks = (bytes + C - 1) / C;
+    auto issue = [&](size_t i) -> int {
+        const size_t off = i * C, len = std::min(C, bytes - off);
+        CU(cudaMemcpyAsync(ws.h_stage[i & 1], static_cast<const char*>(d_src) + off, len, cudaMemcpyDeviceToHost, ws.copy_stream));
+        CU(cudaEventRecord(ws.stage_event[i & 1], ws.copy_stream));
+        return RT_OK;
+    };
+    if (n_chunks) { int rc = issue(0); if (rc) return rc; }
+    for (size_t i = 0; i < n_chunks; ++i) {
+        if (i + 1 < n_chunks) { int rc = issue(i + 1); if (rc) { cudaStreamSynchronize(ws.copy_stream); return rc; } }
+        CU(cudaEventSynchronize(ws.stage_event[i & 1]));
+        const size_t off = i * C, len = std::min(C, bytes - off);
+        copy_mt(static_cast<char*>(dst) + off, ws.h_stage[i & 1], len);
+    }
     return RT_OK;
 }
 
@@ -609,18 +636,23 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
             }
             sc.sm_count = it->second;
         }
-        CU(sc.prims.alloc(N));
-        CU(sc.shade.alloc(N));
-        if (any_wrap) {
-            CU(sc.wraps.alloc(N));
-            UP(sc.wraps.p, wraps.data(), N * sizeof(WrapDev));
-            sc.device_bytes += (uint64_t)N * sizeof(WrapDev);
-        }
-        UP(sc.prims.p, prims.data(), N * sizeof(PrimDev));
-        UP(sc.shade.p, shade.data(), N * sizeof(ShadeDev));
-        sc.device_bytes += (uint64_t)N * (sizeof(PrimDev) + sizeof(ShadeDev));
         return RT_OK;
     });
+    auto post_item_uploads = [&]() {  // primitives and shading records (after the inputs of a device pre-split, which the build waits for)
+        up.post([&]() -> int {
+            CU(sc.prims.alloc(N));
+            CU(sc.shade.alloc(N));
+            if (any_wrap) {
+                CU(sc.wraps.alloc(N));
+                UP(sc.wraps.p, wraps.data(), N * sizeof(WrapDev));
+                sc.device_bytes += (uint64_t)N * sizeof(WrapDev);
+            }
+            UP(sc.prims.p, prims.data(), N * sizeof(PrimDev));
+            UP(sc.shade.p, shade.data(), N * sizeof(ShadeDev));
+            sc.device_bytes += (uint64_t)N * (sizeof(PrimDev) + sizeof(ShadeDev));
+            return RT_OK;
+        });
+    };
 
     auto child_box = [&](uint32_t r) -> Box {
         if (r & RT_LEAF_BIT) return lbox[r & ~RT_LEAF_BIT];
@@ -830,8 +862,57 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
             });
         }
         Buffer<rt_rebuild::Ref> refs;
-        rt_rebuild::presplit(lb.data(), N, tri.data(), is_tri.data(), (size_t)((double)N * factor), refs);
-        lap("pre-split references");
+        const size_t budget = (size_t)((double)N * factor);
+        const bool on_device = factor > 1.0 && budget > N && O.presplit_device && threaded && !std::getenv("RT_PACK_DRYRUN");
+        if (on_device) {
+            // rt_presplit.cuh: the elements' boxes and triangles go up first, the references come back for the builder
+            DevBuf<rt_rebuild::Box3> d_lb;
+            DevBuf<float> d_tri;
+            DevBuf<uint8_t> d_is;
+            DevBuf<rt_rebuild::Ref> d_refs;
+            struct Signal {  // set when the job ends, whichever way
+                std::promise<int>& p;
+                int rc = RT_ECUDA;
+                ~Signal() { p.set_value(rc); }
+            };
+            std::promise<int> in_done;
+            std::future<int> in_rc = in_done.get_future();
+            up.post([&]() -> int {
+                Signal sig{in_done};
+                CU(d_lb.alloc(N)); CU(d_tri.alloc(9 * (size_t)N)); CU(d_is.alloc(N)); CU(d_refs.alloc(budget));
+                UP(d_lb.p, lb.data(), (size_t)N * sizeof(rt_rebuild::Box3));
+                UP(d_tri.p, tri.data(), 9 * (size_t)N * sizeof(float));
+                UP(d_is.p, is_tri.data(), N);
+                sig.rc = RT_OK;
+                return RT_OK;
+            });
+            post_item_uploads();
+            const bool in_ok = in_rc.get() == RT_OK;
+            CU(cudaSetDevice(sc.device));  // (this thread frees the DevBufs above when the block ends)
+            if (!in_ok) return up.finish();
+            cudaStream_t st = nullptr;
+            CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            size_t n_refs = 0;
+            const cudaError_t e = rt_presplit::run(d_lb.p, d_tri.p, d_is.p, N, budget, d_refs.p, &n_refs, st);
+            cudaStreamDestroy(st);
+            if (e != cudaSuccess) return fail(RT_ECUDA, std::string("device pre-split: ") + cudaGetErrorString(e));
+            refs.resize_discard(n_refs);
+            std::promise<int> out_done;
+            std::future<int> out_rc = out_done.get_future();
+            up.post([&]() -> int {
+                Signal sig{out_done};
+                Workspace& ws = workspace_of(sc.device);
+                std::lock_guard<std::mutex> lk(ws.mu);
+                const int rc = download_staged(ws, refs.data(), d_refs.p, n_refs * sizeof(rt_rebuild::Ref));
+                sig.rc = rc;
+                return rc;
+            });
+            if (out_rc.get() != RT_OK) return up.finish();
+        } else {
+            post_item_uploads();
+            rt_rebuild::presplit(lb.data(), N, tri.data(), is_tri.data(), budget, refs);
+        }
+        lap(on_device ? "pre-split references (device)" : "pre-split references");
         if (!tree_ok.get()) return fail(RT_EINVAL, h_depth.error.empty() ? "BVH is not a tree" : "scene packing: " + h_depth.error);
         rt_rebuild::Tree F;
         uint32_t extra_levels = 0;
@@ -868,6 +949,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
     }
     if (!tree_ok.get()) return fail(RT_EINVAL, h_depth.error.empty() ? "BVH is not a tree" : "scene packing: " + h_depth.error);
     sc.depth = depth;
+    if (!rebuild) post_item_uploads();
     h_ref.join();
     h_vis.join();
     h_ranks.join();
@@ -1444,29 +1526,6 @@ static int guarded(F&& body) {
 
 // Device -> pageable host copy through the workspace's pinned staging chunks (the caller holds ws.mu and has synchronised the
 // producer of `d_src`).  A plain cudaMemcpy into pageable memory ran at 1.5 GB/s here (16 ms for a 1920x1080 film, 64 ms at 4K).
-static int download_staged(Workspace& ws, void* dst, const void* d_src, size_t bytes) {
-    {
-        int rc = ensure_staging(ws);
-        if (rc) return rc;
-    }
-    const size_t C = Workspace::STAGE_BYTES;
-    const size_t n_chunks = (bytes + C - 1) / C;
-    auto issue = [&](size_t i) -> int {
-        const size_t off = i * C, len = std::min(C, bytes - off);
-        CU(cudaMemcpyAsync(ws.h_stage[i & 1], static_cast<const char*>(d_src) + off, len, cudaMemcpyDeviceToHost, ws.copy_stream));
-        CU(cudaEventRecord(ws.stage_event[i & 1], ws.copy_stream));
-        return RT_OK;
-    };
-    if (n_chunks) { int rc = issue(0); if (rc) return rc; }
-    for (size_t i = 0; i < n_chunks; ++i) {
-        if (i + 1 < n_chunks) { int rc = issue(i + 1); if (rc) { cudaStreamSynchronize(ws.copy_stream); return rc; } }
-        CU(cudaEventSynchronize(ws.stage_event[i & 1]));
-        const size_t off = i * C, len = std::min(C, bytes - off);
-        copy_mt(static_cast<char*>(dst) + off, ws.h_stage[i & 1], len);
-    }
-    return RT_OK;
-}
-
 extern "C" {
 
 const char* rt_last_error(void) { return g_err.c_str(); }
@@ -1475,6 +1534,44 @@ int rt_device_count(int* out_count) {
     if (!out_count) return fail(RT_EINVAL, "out_count is NULL");
     CU(cudaGetDeviceCount(out_count));
     return RT_OK;
+}
+
+int rt_presplit_refs(const float* boxes6, const float* tri9, const uint8_t* is_tri, uint32_t n, uint64_t budget, int device,
+                     uint32_t* out_items, float* out_boxes6, uint64_t* out_n) {
+    if (!boxes6 || !tri9 || !is_tri || !out_items || !out_boxes6 || !out_n) return fail(RT_EINVAL, "NULL argument");
+    return guarded([&]() -> int {
+        static_assert(sizeof(rt_rebuild::Box3) == 24 && sizeof(rt_rebuild::Ref) == 28, "reference layout");
+        const rt_rebuild::Box3* leaf = reinterpret_cast<const rt_rebuild::Box3*>(boxes6);
+        rt_rebuild::Buffer<rt_rebuild::Ref> refs;
+        if (device < 0) {
+            rt_rebuild::presplit(leaf, n, tri9, is_tri, (size_t)budget, refs);
+        } else {
+            CU(cudaSetDevice(device));
+            const size_t cap = std::max<size_t>((size_t)budget, n);
+            DevBuf<rt_rebuild::Box3> d_lb;
+            DevBuf<float> d_tri;
+            DevBuf<uint8_t> d_is;
+            DevBuf<rt_rebuild::Ref> d_refs;
+            CU(d_lb.alloc(n)); CU(d_tri.alloc(9 * (size_t)n)); CU(d_is.alloc(n)); CU(d_refs.alloc(cap));
+            CU(cudaMemcpy(d_lb.p, leaf, (size_t)n * 24, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(d_tri.p, tri9, (size_t)n * 36, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(d_is.p, is_tri, n, cudaMemcpyHostToDevice));
+            cudaStream_t st = nullptr;
+            CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            size_t n_refs = 0;
+            const cudaError_t e = rt_presplit::run(d_lb.p, d_tri.p, d_is.p, n, (size_t)budget, d_refs.p, &n_refs, st);
+            cudaStreamDestroy(st);
+            if (e != cudaSuccess) return fail(RT_ECUDA, std::string("device pre-split: ") + cudaGetErrorString(e));
+            refs.resize_discard(n_refs);
+            CU(cudaMemcpy(refs.data(), d_refs.p, n_refs * sizeof(rt_rebuild::Ref), cudaMemcpyDeviceToHost));
+        }
+        for (size_t i = 0; i < refs.size(); ++i) {
+            out_items[i] = refs[i].item;
+            std::memcpy(out_boxes6 + 6 * i, &refs[i].box, 24);
+        }
+        *out_n = refs.size();
+        return RT_OK;
+    });
 }
 
 int rt_set_option(const char* key, int64_t value) {
@@ -1486,6 +1583,7 @@ int rt_set_option(const char* key, int64_t value) {
     else if (k == "rebuild_wrapped") g_opt_rebuild_wrapped = (int)value;
     else if (k == "rebuild_min_items") g_opt_rebuild_min_items = (int)value;
     else if (k == "presplit") g_opt_presplit = (int)value;
+    else if (k == "presplit_device") g_opt_presplit_device = (int)value;
     else if (k == "rebuild_depth_extra") g_opt_rebuild_depth_extra = (int)value;
     else if (k == "profile") g_opt_profile = (int)value;
     else if (k == "count") g_opt_count = (int)value;

@@ -24,6 +24,13 @@
 #include <thread>
 #include <vector>
 
+#include <math.h>
+#ifdef __CUDACC__
+#define RT_HD __host__ __device__
+#else
+#define RT_HD
+#endif
+
 namespace rt_rebuild {
 
 // Worker threads shared by every parallel_for of the process (created on first use).  Starting a thread costs 20-30 us; the scene
@@ -159,7 +166,7 @@ struct LeafSrc {
 
 namespace detail {
 
-inline Box3 empty_box() {
+RT_HD inline Box3 empty_box() {
     Box3 b;
     for (int k = 0; k < 3; ++k) { b.mn[k] = INFINITY; b.mx[k] = -INFINITY; }
     return b;
@@ -170,8 +177,9 @@ inline void grow(Box3& b, const Box3& o) {
         b.mx[k] = o.mx[k] > b.mx[k] ? o.mx[k] : b.mx[k];
     }
 }
-inline double half_area(const Box3& b) {
-    const double x = std::max(0.0, (double)b.mx[0] - b.mn[0]), y = std::max(0.0, (double)b.mx[1] - b.mn[1]), z = std::max(0.0, (double)b.mx[2] - b.mn[2]);
+RT_HD inline double half_area(const Box3& b) {
+    double x = (double)b.mx[0] - b.mn[0], y = (double)b.mx[1] - b.mn[1], z = (double)b.mx[2] - b.mn[2];
+    x = 0.0 < x ? x : 0.0; y = 0.0 < y ? y : 0.0; z = 0.0 < z ? z : 0.0;  // std::max(0.0, .) without the host-only call (device code uses this too)
     return x * y + y * z + z * x;
 }
 
@@ -444,8 +452,8 @@ struct Poly {
     int n = 0;
     double v[12][3];
 };
-inline Poly clip_half(const Poly& in, int axis, double c, double sign) {  // keep sign * (x[axis] - c) >= 0
-    Poly out;
+RT_HD inline void clip_half(const Poly& in, int axis, double c, double sign, Poly& out) {  // keep sign * (x[axis] - c) >= 0
+    out.n = 0;
     for (int i = 0; i < in.n; ++i) {
         const double* a = in.v[i];
         const double* b = in.v[(i + 1) % in.n];
@@ -458,17 +466,16 @@ inline Poly clip_half(const Poly& in, int axis, double c, double sign) {  // kee
             ++out.n;
         }
     }
-    return out;
 }
-inline float round_down(double v) {
+RT_HD inline float round_down(double v) {
     float f = (float)v;
-    return (double)f > v ? std::nextafter(f, -INFINITY) : f;
+    return (double)f > v ? nextafterf(f, -INFINITY) : f;
 }
-inline float round_up(double v) {
+RT_HD inline float round_up(double v) {
     float f = (float)v;
-    return (double)f < v ? std::nextafter(f, INFINITY) : f;
+    return (double)f < v ? nextafterf(f, INFINITY) : f;
 }
-inline Box3 poly_box(const Poly& p, const Box3& within) {
+RT_HD inline Box3 poly_box(const Poly& p, const Box3& within) {
     Box3 b = empty_box();
     for (int k = 0; k < 3; ++k) {
         double lo = p.v[0][k], hi = p.v[0][k];
@@ -481,6 +488,52 @@ inline Box3 poly_box(const Poly& p, const Box3& within) {
 }
 }  // namespace detail
 
+// The cell a reference's cuts have carved out of space (its piece of the triangle = the triangle clipped against it).
+struct Region {
+    double lo[3], hi[3];
+};
+struct Cut {
+    Box3 bl, bh;  // boxes of the low / high piece
+    double mid;
+    int ax;
+    bool ok;
+};
+// One attempted cut of a reference (box b, region rg) of the triangle tri9 at the middle of the box's longest axis.  The ONE
+// implementation, compiled for the host loop below and for the device kernel (rt_presplit.cuh): double arithmetic without
+// contraction on both sides (-ffp-contract=off / --fmad=false), so both produce the same boxes bit for bit.
+RT_HD inline void compute_cut(const Box3& b, const float* tri9, const Region& rg, Cut& cu) {
+    using detail::Poly;
+    cu.ok = false;
+    cu.mid = 0.0;
+    cu.ax = 0;
+    int ax = 0;
+    for (int q = 1; q < 3; ++q)
+        if (b.mx[q] - b.mn[q] > b.mx[ax] - b.mn[ax]) ax = q;
+    if (!(b.mx[ax] > b.mn[ax])) return;
+    const double mid = 0.5 * ((double)b.mn[ax] + (double)b.mx[ax]);
+    Poly p0, p1;
+    p0.n = 3;
+    for (int v = 0; v < 3; ++v)
+        for (int q = 0; q < 3; ++q) p0.v[v][q] = tri9[3 * v + q];
+    Poly* src = &p0;
+    Poly* dst = &p1;
+    for (int q = 0; q < 3 && src->n >= 3; ++q) {
+        if (rg.lo[q] > -INFINITY) { detail::clip_half(*src, q, rg.lo[q], 1.0, *dst); Poly* t = src; src = dst; dst = t; }
+        if (rg.hi[q] < INFINITY && src->n >= 3) { detail::clip_half(*src, q, rg.hi[q], -1.0, *dst); Poly* t = src; src = dst; dst = t; }
+    }
+    if (src->n < 3) return;
+    Poly lo;
+    detail::clip_half(*src, ax, mid, -1.0, lo);
+    detail::clip_half(*src, ax, mid, 1.0, *dst);
+    if (lo.n < 3 || dst->n < 3) return;
+    cu.bl = detail::poly_box(lo, b);
+    cu.bh = detail::poly_box(*dst, b);
+    const double a0 = detail::half_area(b), al = detail::half_area(cu.bl), ah = detail::half_area(cu.bh);
+    cu.ok = al + ah < 0.9 * a0;
+    cu.mid = mid;
+    cu.ax = ax;
+}
+
 // tri: 9 floats (p0, p1, p2) per element, only read where is_tri[i] != 0.
 // Largest boxes first, in ROUNDS: each round cuts every candidate whose box area is at least tau, in parallel, and feeds the
 // pieces back as candidates; tau halves when nothing that large is left.  A piece is always smaller than the reference it came
@@ -492,7 +545,6 @@ inline Box3 poly_box(const Poly& p, const Box3& within) {
 // by clipping the triangle against the reference's REGION (the axis-aligned cell its cuts have carved out: 48 B instead of a
 // 300 B polygon).  Deterministic for any thread count.
 inline void presplit(const Box3* leaf, size_t n0, const float* tri, const uint8_t* is_tri, size_t budget, Buffer<Ref>& refs) {
-    using detail::Poly;
     refs.resize_discard(std::max(budget, n0));  // sized once; `n_refs` of them are live
     Buffer<double> area;  // scratch: box areas computed in the parallel loops, consumed by the sequential bucket fills
     area.resize_discard(std::max(n0, budget > n0 ? 2 * (budget - n0) : (size_t)0));
@@ -501,7 +553,6 @@ inline void presplit(const Box3* leaf, size_t n0, const float* tri, const uint8_
     });
     size_t n_refs = n0;
     if (budget <= n0) { refs.n = n0; return; }
-    struct Region { double lo[3], hi[3]; };
     Buffer<Region> region;
     region.resize_discard(budget);
     parallel_for(n0, 65536, [&](size_t a, size_t b) {
@@ -532,7 +583,6 @@ inline void presplit(const Box3* leaf, size_t n0, const float* tri, const uint8_
     };
     for (uint32_t i = 0; i < n0; ++i)
         if (is_tri[i]) put(Cand{area[i], i});
-    struct Cut { Box3 bl, bh; double mid; int ax; bool ok; };
     Buffer<Cut> cuts;
     Buffer<int> piece_bucket;  // of the two pieces of cut c: computed in the parallel loop, the sequential queueing only appends
     std::vector<Cand> cur;
@@ -552,33 +602,8 @@ inline void presplit(const Box3* leaf, size_t n0, const float* tri, const uint8_
         cuts.resize_discard(k);
         parallel_for(k, 2048, [&](size_t lo_i, size_t hi_i) {
             for (size_t c = lo_i; c < hi_i; ++c) {
-                Cut& cu = cuts[c];
-                cu.ok = false;
                 const uint32_t r = cur[c].ref;
-                const Box3 b = refs[r].box;
-                int ax = 0;
-                for (int q = 1; q < 3; ++q)
-                    if (b.mx[q] - b.mn[q] > b.mx[ax] - b.mn[ax]) ax = q;
-                if (!(b.mx[ax] > b.mn[ax])) continue;
-                const double mid = 0.5 * ((double)b.mn[ax] + (double)b.mx[ax]);
-                // this reference's piece of the triangle = triangle clipped against its region
-                Poly src;
-                src.n = 3;
-                for (int v = 0; v < 3; ++v)
-                    for (int q = 0; q < 3; ++q) src.v[v][q] = tri[9 * (size_t)refs[r].item + 3 * v + q];
-                const Region& rg = region[r];
-                for (int q = 0; q < 3 && src.n >= 3; ++q) {
-                    if (rg.lo[q] > -INFINITY) src = detail::clip_half(src, q, rg.lo[q], 1.0);
-                    if (rg.hi[q] < INFINITY && src.n >= 3) src = detail::clip_half(src, q, rg.hi[q], -1.0);
-                }
-                if (src.n < 3) continue;
-                const Poly lo = detail::clip_half(src, ax, mid, -1.0), hi = detail::clip_half(src, ax, mid, 1.0);
-                if (lo.n < 3 || hi.n < 3) continue;
-                cu.bl = detail::poly_box(lo, b);
-                cu.bh = detail::poly_box(hi, b);
-                const double a0 = detail::half_area(b), al = detail::half_area(cu.bl), ah = detail::half_area(cu.bh);
-                cu.ok = al + ah < 0.9 * a0;
-                cu.mid = mid; cu.ax = ax;
+                compute_cut(refs[r].box, tri + 9 * (size_t)refs[r].item, region[r], cuts[c]);
             }
         });
         // apply: the low half replaces the reference, the high half goes to a new reference at n_refs + (accepted cuts before it);
