@@ -187,6 +187,12 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene);
 void rt_scene_destroy(RtScene* scene);
 /* Device bytes held by the packed scene (nodes, primitives, shading records, tables, images). */
 int rt_scene_device_bytes(const RtScene* scene, uint64_t* out_bytes);
+/* Test aid for row f4: the accelerator tree of the scene as the kernels read it.  *out_n = its node count (0: the scene has
+ * none: fewer than "rebuild_min_items" elements, or rebuilding is off), *out_root = the root reference, *out_depth = its depth.
+ * out_nodes64 (may be NULL): room for cap_nodes 64-byte records = 16 words each: the left child's box (min xyz, max xyz), the
+ * right child's box, then left reference, right reference, split axis, packed guard band.  A reference is a node index, or has
+ * bit 31 set and the element index in its low 28 bits. */
+int rt_scene_accelerator_nodes(const RtScene* scene, void* out_nodes64, uint64_t cap_nodes, uint64_t* out_n, uint32_t* out_root, uint32_t* out_depth);
 
 /* Closest hit for n caller rays (host buffers).  Volumes draw one random number per tested volume element inside the traversal
  * (the reference passes an rng into Scene::hit for this): rt_trace keys that draw by (ray index, element index), seed 0.  org/dir: n*3 floats; outputs: hit_id n, t n, normal n*3,
@@ -255,7 +261,9 @@ int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_o
  * the rebuilt tree in per cent of the element count (default 800; <= 100 = one reference per element): sliver triangles are
  * cut into several references with tighter boxes (an element may sit in several leaves of the accelerator tree).
  * "presplit_device": 1 (default) = that cutting runs on the device for scenes of >= 16 Ki elements, 0 = on the host cores (same
- * set of references either way).
+ * set of references either way).  "build_device": 1 (default) = after a device pre-split the accelerator tree is built on the device too
+ * (rt_sahbuild.cuh: nothing comes back to the host), 0 = by the host builder.  "presplit_large": the budget (per cent) for scenes
+ * above 150 000 elements (default 200).
  * "count": 1 = maintain node_visits / prim_tests / exact_steps.  "profile": 1 = time extend / shade separately.
  * "refill": busy-lane threshold of the persistent extend warps.  "leaf_weight": phase-vote weight.  "check_every": host
  * polling period (iterations).  "pipes": independent wavefront pipelines (streams) per render (default 0 = auto, 3 for >= 64 Mi path slots, else 4: one

@@ -91,7 +91,7 @@ assert MATERIAL_DTYPE.itemsize == C.sizeof(RtMaterial) and TEXTURE_DTYPE.itemsiz
 
 EXPORTED = ["rt_last_error", "rt_device_count", "rt_scene_create", "rt_scene_destroy", "rt_scene_device_bytes", "rt_scene_set_ray_time",
             "rt_trace", "rt_trace_device", "rt_render", "rt_render_device", "rt_render_moments_device", "rt_render_planes_device", "rt_render_multi", "rt_render_multi_device",
-            "rt_film_scale_device", "rt_to_rgb8_gamma2_device", "rt_set_option", "rt_presplit_refs", "rt_shutdown"]
+            "rt_film_scale_device", "rt_to_rgb8_gamma2_device", "rt_set_option", "rt_presplit_refs", "rt_scene_accelerator_nodes", "rt_shutdown"]
 
 _lib = None
 
@@ -327,6 +327,17 @@ class DeviceScene:
         b = C.c_uint64(0)
         check(lib().rt_scene_device_bytes(self.h, C.byref(b)))
         return b.value
+
+    def accelerator_nodes(self):
+        """rt_scene_accelerator_nodes (test aid): (nodes as a (n, 16) uint32 array, root reference, depth) of the accelerator tree."""
+        L = lib()
+        L.rt_scene_accelerator_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        n, root, depth = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+        check(L.rt_scene_accelerator_nodes(self.h, None, 0, C.byref(n), C.byref(root), C.byref(depth)))
+        nodes = np.empty((n.value, 16), dtype=np.uint32)
+        if n.value:
+            check(L.rt_scene_accelerator_nodes(self.h, nodes.ctypes.data, n.value, C.byref(n), C.byref(root), C.byref(depth)))
+        return nodes, root.value, depth.value
 
     def set_ray_time(self, time: float):
         check(lib().rt_scene_set_ray_time(self.h, float(time)))

@@ -29,6 +29,7 @@
 #include "rt_kernels.cuh"
 #include "rt_rebuild.hpp"
 #include "rt_presplit.cuh"
+#include "rt_sahbuild.cuh"
 
 using namespace rt;
 
@@ -41,6 +42,8 @@ std::mutex g_opt_mu;
 int g_opt_traversal = 3;      // 0 = reference node test only (exact), 1 = + tight cull (exact), 2 = + reciprocal fast path,
                               // 3 = rebuilt topology + per-ray proof, unproven rays on the reference tree with 2 (plain scenes; else 2)
 int g_opt_presplit = 800;     // reference budget of the rebuilt tree in per cent of the element count (<= 100: no pre-splitting)
+int g_opt_presplit_large = 200;  // the same budget for scenes above 150 000 elements (capped: the accelerator tree of C4 is already > L2)
+int g_opt_build_device = 1;     // after a device pre-split, also build the accelerator tree there (rt_sahbuild.cuh): nothing comes back to the host
 int g_opt_presplit_device = 1;  // pre-split on the device (rt_presplit.cuh) for scenes of >= 16 Ki elements; 0 = on the host cores
 int g_opt_rebuild_min_items = 32;  // below this the reference tree is as good (a Cornell box has 8 elements) and nothing has to be proven
 int g_opt_rebuild_wrapped = 1;  // also build it for scenes with wrapped elements / volumes (true world-space bounds)
@@ -64,13 +67,13 @@ struct Options {
     int traversal, presplit, rebuild_min_items, rebuild_wrapped, rebuild, rebuild_depth_extra, pipes, leaf_weight, refill, count, profile,
         check_every, blocks_per_sm, debug_skip_redo, tail_budget, carveout;
     int64_t max_slots;
-    int presplit_device;
+    int presplit_device, presplit_large, build_device;
 };
 Options options_snapshot() {
     std::lock_guard<std::mutex> lk(g_opt_mu);
     return Options{g_opt_traversal, g_opt_presplit, g_opt_rebuild_min_items, g_opt_rebuild_wrapped, g_opt_rebuild, g_opt_rebuild_depth_extra,
                    g_opt_pipes, g_opt_leaf_weight, g_opt_refill, g_opt_count, g_opt_profile, g_opt_check_every, g_opt_blocks_per_sm, g_opt_debug_skip_redo, g_opt_tail_budget, g_opt_carveout,
-                   g_opt_max_slots, g_opt_presplit_device};
+                   g_opt_max_slots, g_opt_presplit_device, g_opt_presplit_large, g_opt_build_device};
 }
 
 int fail(int code, const std::string& msg) {
@@ -849,7 +852,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
                 for (int k = 0; k < 3; ++k) { lb[i].mn[k] = fbox[i].mn[k]; lb[i].mx[k] = fbox[i].mx[k]; }
         });
         // pre-split sliver triangles into several references (rt_rebuild.hpp); the budget shrinks for very large scenes
-        const double factor = O.presplit <= 100 ? 1.0 : std::min((double)O.presplit / 100.0, N <= 150000u ? 16.0 : (N <= 2000000u ? 2.0 : 1.0));
+        const double factor = O.presplit <= 100 ? 1.0 : std::min((double)O.presplit / 100.0, N <= 150000u ? 16.0 : (N <= 2000000u ? (double)O.presplit_large / 100.0 : 1.0));
         if (factor > 1.0) {
             tri.resize_discard(9 * (size_t)N);
             is_tri.resize_discard(N);
@@ -864,12 +867,22 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         Buffer<rt_rebuild::Ref> refs;
         const size_t budget = (size_t)((double)N * factor);
         const bool on_device = factor > 1.0 && budget > N && O.presplit_device && threaded && !std::getenv("RT_PACK_DRYRUN");
+        const bool build_on_device = on_device && O.build_device;
+        bool built = false;
+        const uint32_t depth_extra = (uint32_t)std::max(0, O.rebuild_depth_extra);
         if (on_device) {
-            // rt_presplit.cuh: the elements' boxes and triangles go up first, the references come back for the builder
+            // rt_presplit.cuh: the elements' boxes and triangles go up first; the references come back for the host builder, or stay
+            // for the device one (rt_sahbuild.cuh), which also needs the per-element band coefficients and leaf references
             DevBuf<rt_rebuild::Box3> d_lb;
-            DevBuf<float> d_tri;
+            DevBuf<float> d_tri, d_a, d_c;
             DevBuf<uint8_t> d_is;
+            DevBuf<uint32_t> d_iref;
             DevBuf<rt_rebuild::Ref> d_refs;
+            Buffer<uint32_t> iref;
+            if (build_on_device) {
+                iref.resize_discard(N);
+                rt_rebuild::parallel_for(N, 65536, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) iref[i] = ref_of_item((uint32_t)i); });
+            }
             struct Signal {  // set when the job ends, whichever way
                 std::promise<int>& p;
                 int rc = RT_ECUDA;
@@ -883,6 +896,12 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
                 UP(d_lb.p, lb.data(), (size_t)N * sizeof(rt_rebuild::Box3));
                 UP(d_tri.p, tri.data(), 9 * (size_t)N * sizeof(float));
                 UP(d_is.p, is_tri.data(), N);
+                if (build_on_device) {
+                    CU(d_a.alloc(N)); CU(d_c.alloc(N)); CU(d_iref.alloc(N));
+                    UP(d_a.p, fastA.data(), (size_t)N * 4);
+                    UP(d_c.p, fastC.data(), (size_t)N * 4);
+                    UP(d_iref.p, iref.data(), (size_t)N * 4);
+                }
                 sig.rc = RT_OK;
                 return RT_OK;
             });
@@ -893,32 +912,51 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
             cudaStream_t st = nullptr;
             CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
             size_t n_refs = 0;
-            const cudaError_t e = rt_presplit::run(d_lb.p, d_tri.p, d_is.p, N, budget, d_refs.p, &n_refs, st);
-            cudaStreamDestroy(st);
-            if (e != cudaSuccess) return fail(RT_ECUDA, std::string("device pre-split: ") + cudaGetErrorString(e));
-            refs.resize_discard(n_refs);
-            std::promise<int> out_done;
-            std::future<int> out_rc = out_done.get_future();
-            up.post([&]() -> int {
-                Signal sig{out_done};
-                Workspace& ws = workspace_of(sc.device);
-                std::lock_guard<std::mutex> lk(ws.mu);
-                const int rc = download_staged(ws, refs.data(), d_refs.p, n_refs * sizeof(rt_rebuild::Ref));
-                sig.rc = rc;
-                return rc;
-            });
-            if (out_rc.get() != RT_OK) return up.finish();
+            cudaError_t e = rt_presplit::run(d_lb.p, d_tri.p, d_is.p, N, budget, d_refs.p, &n_refs, st);
+            if (e != cudaSuccess) { cudaStreamDestroy(st); return fail(RT_ECUDA, std::string("device pre-split: ") + cudaGetErrorString(e)); }
+            lap("pre-split references (device)");
+            if (build_on_device && n_refs > rt_sahbuild::SMALL) {
+                if (!tree_ok.get()) { cudaStreamDestroy(st); return fail(RT_EINVAL, h_depth.error.empty() ? "BVH is not a tree" : "scene packing: " + h_depth.error); }
+                uint32_t extra_levels = 0;
+                while (((size_t)N << extra_levels) < n_refs) ++extra_levels;
+                if (sc.nodes2.alloc(n_refs - 1) != cudaSuccess) { cudaStreamDestroy(st); return fail(RT_ENOMEM, "out of device memory (accelerator tree)"); }
+                rt_sahbuild::Result res;
+                e = rt_sahbuild::run(d_refs.p, (uint32_t)n_refs, d_a.p, d_c.p, d_iref.p, depth + extra_levels + depth_extra, sc.nodes2.p, &res, st);
+                cudaStreamDestroy(st);
+                if (e != cudaSuccess) return fail(RT_ECUDA, std::string("device accelerator build: ") + cudaGetErrorString(e));
+                sc.device_bytes += (uint64_t)(n_refs - 1) * sizeof(NodeDev);
+                root2 = res.root;
+                sc.depth2 = res.depth;
+                built = true;
+                lap("SAH build (device)");
+            } else {
+                cudaStreamDestroy(st);
+                refs.resize_discard(n_refs);
+                std::promise<int> out_done;
+                std::future<int> out_rc = out_done.get_future();
+                up.post([&]() -> int {
+                    Signal sig{out_done};
+                    Workspace& ws = workspace_of(sc.device);
+                    std::lock_guard<std::mutex> lk(ws.mu);
+                    const int rc = download_staged(ws, refs.data(), d_refs.p, n_refs * sizeof(rt_rebuild::Ref));
+                    sig.rc = rc;
+                    return rc;
+                });
+                if (out_rc.get() != RT_OK) return up.finish();
+                lap("references back to the host");
+            }
         } else {
             post_item_uploads();
             rt_rebuild::presplit(lb.data(), N, tri.data(), is_tri.data(), budget, refs);
+            lap("pre-split references");
         }
-        lap(on_device ? "pre-split references (device)" : "pre-split references");
+        if (!built) {
         if (!tree_ok.get()) return fail(RT_EINVAL, h_depth.error.empty() ? "BVH is not a tree" : "scene packing: " + h_depth.error);
         rt_rebuild::Tree F;
         uint32_t extra_levels = 0;
         while (((size_t)N << extra_levels) < refs.size()) ++extra_levels;
         // the builder also collects, bottom-up, each node's maxima of the two guard-band coefficients of the elements below it
-        rt_rebuild::build(refs, fastA.data(), fastC.data(), depth + extra_levels + (uint32_t)std::max(0, O.rebuild_depth_extra), F);
+        rt_rebuild::build(refs, fastA.data(), fastC.data(), depth + extra_levels + depth_extra, F);
         lap("SAH build");
         const uint32_t n2 = (uint32_t)F.left.size();
         auto item_of = [&](uint32_t leafref) -> uint32_t { return refs[leafref & ~RT_LEAF_BIT].item; };
@@ -946,6 +984,8 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         root2 = ref2(F.root);
         sc.depth2 = F.depth;
         lap("pack accelerator nodes");
+        }
+
     }
     if (!tree_ok.get()) return fail(RT_EINVAL, h_depth.error.empty() ? "BVH is not a tree" : "scene packing: " + h_depth.error);
     sc.depth = depth;
@@ -1584,6 +1624,8 @@ int rt_set_option(const char* key, int64_t value) {
     else if (k == "rebuild_min_items") g_opt_rebuild_min_items = (int)value;
     else if (k == "presplit") g_opt_presplit = (int)value;
     else if (k == "presplit_device") g_opt_presplit_device = (int)value;
+    else if (k == "build_device") g_opt_build_device = (int)value;
+    else if (k == "presplit_large") g_opt_presplit_large = (int)std::max<int64_t>(100, std::min<int64_t>(value, 1600));
     else if (k == "rebuild_depth_extra") g_opt_rebuild_depth_extra = (int)value;
     else if (k == "profile") g_opt_profile = (int)value;
     else if (k == "count") g_opt_count = (int)value;
@@ -1642,6 +1684,17 @@ int rt_scene_set_ray_time(RtScene* scene, float time) {
 int rt_scene_device_bytes(const RtScene* scene, uint64_t* out_bytes) {
     if (!scene || !out_bytes) return fail(RT_EINVAL, "NULL argument");
     *out_bytes = scene->device_bytes;
+    return RT_OK;
+}
+
+int rt_scene_accelerator_nodes(const RtScene* scene, void* out_nodes64, uint64_t cap_nodes, uint64_t* out_n, uint32_t* out_root, uint32_t* out_depth) {
+    if (!scene || !out_n || !out_root || !out_depth) return fail(RT_EINVAL, "NULL argument");
+    *out_n = scene->nodes2.n;
+    *out_root = scene->dev.root2;
+    *out_depth = scene->depth2;
+    if (!out_nodes64 || cap_nodes < scene->nodes2.n || scene->nodes2.n == 0) return RT_OK;
+    CU(cudaSetDevice(scene->device));
+    CU(cudaMemcpy(out_nodes64, scene->nodes2.p, scene->nodes2.n * sizeof(NodeDev), cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 

@@ -24,7 +24,8 @@ def product_world(name):
 
 @pytest.fixture(autouse=True)
 def default_options():
-    for k, v in (("traversal", 3), ("count", 0), ("profile", 0), ("pipes", 0), ("rebuild_min_items", 32), ("max_slots", 160 << 20), ("tail_budget", 64)):
+    for k, v in (("traversal", 3), ("count", 0), ("profile", 0), ("pipes", 0), ("rebuild_min_items", 32), ("max_slots", 160 << 20), ("tail_budget", 64),
+                 ("presplit_device", 1), ("build_device", 1)):
         _cabi.set_option(k, v)
     yield
     _cabi.set_option("max_slots", 160 << 20); _cabi.set_option("tail_budget", 64); _cabi.set_option("traversal", 3)
@@ -380,3 +381,65 @@ def test_device_presplit_scene_renders_the_same_film():
     _cabi.set_option("presplit_device", 1)
     assert images_equal_bits(films[0], films[1])
     assert sizes[0] == sizes[1]          # same number of references -> same accelerator tree size
+
+
+# ---------------------------------------------------------------- row f4: the accelerator tree built on the device
+def _check_accelerator(nodes, root, depth, n_items):
+    """Structure of an accelerator tree as the kernels read it: a binary tree in which every node is reached once, children have larger
+    indices than their parent (pre-order), every element sits in a leaf, and the box a parent holds for an internal child is the union
+    of the two boxes that child holds for its own children."""
+    n = len(nodes)
+    assert n >= 1 and not (root & 0x80000000) and root == 0
+    f = nodes.view(np.float32)
+    left, right = nodes[:, 12], nodes[:, 13]
+    lbox, rbox = f[:, 0:6], f[:, 6:12]
+    seen = np.zeros(n, bool)
+    items = np.zeros(n_items, bool)
+    level = np.array([root], dtype=np.int64)
+    d = 0
+    while len(level):
+        d += 1
+        assert not seen[level].any()
+        seen[level] = True
+        nxt = []
+        for child, box in ((left[level], lbox[level]), (right[level], rbox[level])):
+            leaf = (child & 0x80000000) != 0
+            it = child[leaf] & 0x0FFFFFFF
+            assert (it < n_items).all()
+            items[it] = True
+            ci = child[~leaf].astype(np.int64)
+            assert (ci > level[~leaf]).all() and (ci < n).all()
+            union = np.concatenate([np.minimum(lbox[ci][:, 0:3], rbox[ci][:, 0:3]), np.maximum(lbox[ci][:, 3:6], rbox[ci][:, 3:6])], axis=1)
+            assert np.array_equal(union, box[~leaf])
+            nxt.append(ci)
+        level = np.concatenate(nxt)
+    assert seen.all() and items.all()
+    assert d == depth
+
+
+@pytest.mark.parametrize("dev", [1, 0])
+def test_accelerator_tree_structure(dev):
+    _cabi.set_option("build_device", dev)
+    W = rb.World.named("config:c5")
+    sc = W.device_scene(0)
+    nodes, root, depth = sc.accelerator_nodes()
+    n_items = len(W.export().kinds)
+    assert len(nodes) >= n_items - 1
+    _check_accelerator(nodes, root, depth, n_items)
+    W.close()
+
+
+def test_device_built_tree_renders_the_same_film_with_the_same_work():
+    size, spp, T = rb.Size2i(320, 180), 4, 4
+    out = []
+    for dev in (1, 0):
+        _cabi.set_option("build_device", dev)
+        W = rb.World.named("config:c5")
+        _cabi.set_option("count", 1)
+        film, st = rb.render(size, T, spp, 50, W, seed=5, device=0, return_stats=True)
+        _cabi.set_option("count", 0)
+        out.append((film, st["node_visits"] / st["ray_segments"], st["prim_tests"] / st["ray_segments"], W.device_scene(0).device_bytes()))
+        W.close()
+    assert images_equal_bits(out[0][0], out[1][0])
+    assert out[0][3] == out[1][3]
+    assert out[0][1] < 1.03 * out[1][1] and out[0][2] < 1.03 * out[1][2], out     # the device builder's tree is as good as the host builder's
