@@ -263,7 +263,8 @@ int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_o
  * "presplit_device": 1 (default) = that cutting runs on the device for scenes of >= 16 Ki elements, 0 = on the host cores (same
  * set of references either way).  "build_device": 1 (default) = after a device pre-split the accelerator tree is built on the device too
  * (rt_sahbuild.cuh: nothing comes back to the host), 0 = by the host builder.  "presplit_large": the budget (per cent) for scenes
- * above 150 000 elements (default 200).
+ * above 150 000 elements (default 200).  "device_cache_mb": device memory of destroyed scenes (and of the hand-off's scratch) kept per GPU for the
+ * next rt_scene_create, in MB (default 2048; 0 = every release is a cudaFree; rt_shutdown gives everything back).
  * "count": 1 = maintain node_visits / prim_tests / exact_steps.  "profile": 1 = time extend / shade separately.
  * "refill": busy-lane threshold of the persistent extend warps.  "leaf_weight": phase-vote weight.  "check_every": host
  * polling period (iterations).  "pipes": independent wavefront pipelines (streams) per render (default 0 = auto, 3 for >= 64 Mi path slots, else 4: one

@@ -28,6 +28,17 @@
 #include "../../include/b200rt.h"
 #include "rt_kernels.cuh"
 #include "rt_rebuild.hpp"
+
+// Device memory of scenes and of the scene hand-off's scratch goes through a small per-device cache of freed blocks (defined below):
+// cudaMalloc / cudaFree go to the kernel-mode driver and serialise with everything else that does; inside bench.py's later configs
+// single calls were seen to take 0.1 - 1.3 s each (profiles/README.md, round 2 late).  A caller that hands scenes over again and
+// again (a shim's render() does, every call) re-uses the blocks of the scene it has just destroyed.
+namespace rt_devcache {
+cudaError_t alloc(void** out, size_t bytes);
+void release(void* p);
+void trim(int device);  // -1: every device
+}  // namespace rt_devcache
+
 #include "rt_presplit.cuh"
 #include "rt_sahbuild.cuh"
 
@@ -43,6 +54,7 @@ int g_opt_traversal = 3;      // 0 = reference node test only (exact), 1 = + tig
                               // 3 = rebuilt topology + per-ray proof, unproven rays on the reference tree with 2 (plain scenes; else 2)
 int g_opt_presplit = 800;     // reference budget of the rebuilt tree in per cent of the element count (<= 100: no pre-splitting)
 int g_opt_presplit_large = 200;  // the same budget for scenes above 150 000 elements (capped: the accelerator tree of C4 is already > L2)
+int64_t g_opt_device_cache_mb = 2048;  // freed device blocks kept per GPU for the next scene (0: every release is a cudaFree)
 int g_opt_build_device = 1;     // after a device pre-split, also build the accelerator tree there (rt_sahbuild.cuh): nothing comes back to the host
 int g_opt_presplit_device = 1;  // pre-split on the device (rt_presplit.cuh) for scenes of >= 16 Ki elements; 0 = on the host cores
 int g_opt_rebuild_min_items = 32;  // below this the reference tree is as good (a Cornell box has 8 elements) and nothing has to be proven
@@ -87,6 +99,96 @@ int fail(int code, const std::string& msg) {
             return fail(RT_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
     } while (0)
 
+}  // namespace
+namespace rt_devcache {
+struct Block {
+    void* p;
+    size_t bytes;
+    int device;
+};
+static std::mutex g_mu;
+static std::map<void*, Block> g_live;          // blocks handed out
+static std::vector<Block> g_free;              // blocks kept for re-use, oldest first
+static size_t g_cached[64] = {0};              // bytes kept per device
+cudaError_t alloc(void** out, size_t bytes) {
+    *out = nullptr;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    bytes = (bytes + 511) & ~(size_t)511;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        size_t best = g_free.size();
+        for (size_t i = 0; i < g_free.size(); ++i)  // smallest kept block that fits without wasting more than a quarter
+            if (g_free[i].device == dev && g_free[i].bytes >= bytes && g_free[i].bytes <= bytes + bytes / 4 + ((size_t)1 << 20) &&
+                (best == g_free.size() || g_free[i].bytes < g_free[best].bytes))
+                best = i;
+        if (best != g_free.size()) {
+            const Block b = g_free[best];
+            g_free.erase(g_free.begin() + (long)best);
+            if (dev >= 0 && dev < 64) g_cached[dev] -= b.bytes;
+            g_live[b.p] = b;
+            *out = b.p;
+            return cudaSuccess;
+        }
+    }
+    void* p = nullptr;
+    e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {  // out of memory with blocks still kept: give them back and try once more
+        cudaGetLastError();
+        trim(dev);
+        e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_live[p] = Block{p, bytes, dev};
+    *out = p;
+    return cudaSuccess;
+}
+void release(void* p) {
+    if (!p) return;
+    std::vector<void*> to_free;
+    {
+        int64_t cap_mb;
+        { std::lock_guard<std::mutex> ol(g_opt_mu); cap_mb = g_opt_device_cache_mb; }
+        const size_t cap = (size_t)cap_mb << 20;
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_live.find(p);
+        if (it == g_live.end()) { to_free.push_back(p); }
+        else {
+            const Block b = it->second;
+            g_live.erase(it);
+            if (b.bytes > cap || b.device < 0 || b.device >= 64) to_free.push_back(p);  // e.g. the 19 GB path queues: never kept
+            else {
+                g_free.push_back(b);
+                g_cached[b.device] += b.bytes;
+                for (size_t i = 0; g_cached[b.device] > cap && i < g_free.size();) {  // over the cap: the oldest go first
+                    if (g_free[i].device != b.device) { ++i; continue; }
+                    to_free.push_back(g_free[i].p);
+                    g_cached[b.device] -= g_free[i].bytes;
+                    g_free.erase(g_free.begin() + (long)i);
+                }
+            }
+        }
+    }
+    for (void* q : to_free) cudaFree(q);  // (a pointer is valid on any current device)
+}
+void trim(int device) {
+    std::vector<void*> to_free;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (size_t i = 0; i < g_free.size();) {
+            if (device >= 0 && g_free[i].device != device) { ++i; continue; }
+            to_free.push_back(g_free[i].p);
+            if (g_free[i].device >= 0 && g_free[i].device < 64) g_cached[g_free[i].device] -= g_free[i].bytes;
+            g_free.erase(g_free.begin() + (long)i);
+        }
+    }
+    for (void* q : to_free) cudaFree(q);
+}
+}  // namespace rt_devcache
+namespace {
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -94,7 +196,7 @@ struct DevBuf {
     cudaError_t alloc(size_t count) {
         release();
         if (count == 0) return cudaSuccess;
-        const cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        const cudaError_t e = rt_devcache::alloc(reinterpret_cast<void**>(&p), count * sizeof(T));
         if (e != cudaSuccess) {
             p = nullptr;
             cudaGetLastError();  // clear the sticky-looking last error: the next call must not report this OOM again
@@ -104,7 +206,7 @@ struct DevBuf {
         return cudaSuccess;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) rt_devcache::release(p);
         p = nullptr;
         n = 0;
     }
@@ -847,9 +949,15 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         lb.resize_discard(N);
         Buffer<float> tri;
         Buffer<uint8_t> is_tri;
+        std::atomic<bool> finite_boxes{true};  // the device builders order floats by their bits: anything else stays on the host path
         rt_rebuild::parallel_for(N, 65536, [&](size_t lo, size_t hi) {
+            bool fin = true;
             for (size_t i = lo; i < hi; ++i)
-                for (int k = 0; k < 3; ++k) { lb[i].mn[k] = fbox[i].mn[k]; lb[i].mx[k] = fbox[i].mx[k]; }
+                for (int k = 0; k < 3; ++k) {
+                    lb[i].mn[k] = fbox[i].mn[k]; lb[i].mx[k] = fbox[i].mx[k];
+                    fin = fin && std::isfinite(lb[i].mn[k]) && std::isfinite(lb[i].mx[k]);
+                }
+            if (!fin) finite_boxes.store(false, std::memory_order_relaxed);
         });
         // pre-split sliver triangles into several references (rt_rebuild.hpp); the budget shrinks for very large scenes
         const double factor = O.presplit <= 100 ? 1.0 : std::min((double)O.presplit / 100.0, N <= 150000u ? 16.0 : (N <= 2000000u ? (double)O.presplit_large / 100.0 : 1.0));
@@ -866,7 +974,7 @@ int pack_scene(const RtSceneDesc& d, RtScene& sc, const Options& O) {
         }
         Buffer<rt_rebuild::Ref> refs;
         const size_t budget = (size_t)((double)N * factor);
-        const bool on_device = factor > 1.0 && budget > N && O.presplit_device && threaded && !std::getenv("RT_PACK_DRYRUN");
+        const bool on_device = factor > 1.0 && budget > N && O.presplit_device && threaded && finite_boxes.load() && !std::getenv("RT_PACK_DRYRUN");
         const bool build_on_device = on_device && O.build_device;
         bool built = false;
         const uint32_t depth_extra = (uint32_t)std::max(0, O.rebuild_depth_extra);
@@ -1625,6 +1733,7 @@ int rt_set_option(const char* key, int64_t value) {
     else if (k == "presplit") g_opt_presplit = (int)value;
     else if (k == "presplit_device") g_opt_presplit_device = (int)value;
     else if (k == "build_device") g_opt_build_device = (int)value;
+    else if (k == "device_cache_mb") { g_opt_device_cache_mb = std::max<int64_t>(0, value); }
     else if (k == "presplit_large") g_opt_presplit_large = (int)std::max<int64_t>(100, std::min<int64_t>(value, 1600));
     else if (k == "rebuild_depth_extra") g_opt_rebuild_depth_extra = (int)value;
     else if (k == "profile") g_opt_profile = (int)value;
@@ -1672,7 +1781,14 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene) {
 void rt_scene_destroy(RtScene* scene) {
     if (!scene) return;
     cudaSetDevice(scene->device);
+    const bool log = std::getenv("RT_PACK_LOG") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (log) cudaDeviceSynchronize();  // (logging only: separates "the device was still busy" from the cost of the frees)
+    const auto t1 = std::chrono::steady_clock::now();
     delete scene;
+    if (log)
+        std::fprintf(stderr, "[rt_scene_destroy] device busy for %8.1f ms, frees %8.1f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
 }
 
 int rt_scene_set_ray_time(RtScene* scene, float time) {
@@ -1910,6 +2026,7 @@ int rt_render_multi_device(RtScene* const* scenes, int n_scenes, const RtRenderP
 // Releases every per-device render workspace (queues, accumulators, streams, events).  Optional: a process may simply exit; a
 // long-lived caller (or a benchmark that wants a clean device before it returns) calls this when no render is in flight.
 int rt_shutdown(void) {
+    rt_devcache::trim(-1);
     std::lock_guard<std::mutex> lk(g_ws_mu);
     for (auto& kv : g_ws) {
         Workspace* w = kv.second;

@@ -21,6 +21,11 @@
 
 #include "rt_rebuild.hpp"
 
+namespace rt_devcache {  // b200rt.cu: device blocks re-used from scene to scene
+cudaError_t alloc(void** out, size_t bytes);
+void release(void* p);
+}
+
 namespace rt_presplit {
 
 using rt_rebuild::Box3;
@@ -158,7 +163,7 @@ __global__ void k_apply(const uint32_t* __restrict__ cand, uint32_t n_cand, cons
 // references; *n_refs_out: how many were made.  Synchronous (a few dozen tiny read-backs steer the rounds).
 inline cudaError_t run(const Box3* d_leaf, const float* d_tri, const uint8_t* d_is_tri, uint32_t n0, size_t budget, Ref* d_refs, size_t* n_refs_out,
                        cudaStream_t st) {
-#define PS_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { if (base) cudaFree(base); return e_; } } while (0)
+#define PS_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { if (base) rt_devcache::release(base); return e_; } } while (0)
     char* base = nullptr;
     *n_refs_out = n0;
     if (n0 == 0) return cudaSuccess;
@@ -170,7 +175,7 @@ inline cudaError_t run(const Box3* d_leaf, const float* d_tri, const uint8_t* d_
     auto take = [&](size_t bytes) { const size_t o = off; off += align(bytes); return o; };
     const size_t o_region = take(B * sizeof(Region)), o_cand0 = take(B * 4), o_cand1 = take(B * 4), o_code = take(B * 8), o_pos = take(B * 8),
                  o_area = take(B * 8), o_big = take(B), o_cuts = take(B * sizeof(Cut)), o_ctr = take(sizeof(Counters)), o_scan = take(scan_bytes);
-    PS_CU(cudaMalloc(&base, off));
+    PS_CU(rt_devcache::alloc(reinterpret_cast<void**>(&base), off));
     Region* region = reinterpret_cast<Region*>(base + o_region);
     uint32_t* cand[2] = {reinterpret_cast<uint32_t*>(base + o_cand0), reinterpret_cast<uint32_t*>(base + o_cand1)};
     unsigned long long* code = reinterpret_cast<unsigned long long*>(base + o_code);
@@ -276,7 +281,7 @@ inline cudaError_t run(const Box3* d_leaf, const float* d_tri, const uint8_t* d_
                          n_rounds, n_descents, n_selections, n_refs);
     }
     PS_CU(cudaStreamSynchronize(st));
-    cudaFree(base);
+    rt_devcache::release(base);
     *n_refs_out = n_refs;
     return cudaSuccess;
 #undef PS_CU

@@ -445,7 +445,7 @@ struct Result {
 // (device).  d_nodes: room for n - 1 records.  Synchronous (one small read-back per level sizes the next level's launches).
 inline cudaError_t run(const Ref* d_refs, uint32_t n, const float* d_item_a, const float* d_item_c, const uint32_t* d_item_ref, uint32_t max_depth,
                        NodeDev* d_nodes, Result* out, cudaStream_t st) {
-#define SB_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { if (base) cudaFree(base); return e_; } } while (0)
+#define SB_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { if (base) rt_devcache::release(base); return e_; } } while (0)
     char* base = nullptr;
     if (n <= SMALL) return cudaErrorInvalidValue;
     uint32_t need = 0;
@@ -461,7 +461,7 @@ inline cudaError_t run(const Ref* d_refs, uint32_t n, const float* d_item_a, con
                  o_pos = take((size_t)n * 8), o_act0 = take(cap * sizeof(Active)), o_act1 = take(cap * sizeof(Active)), o_split = take(cap * sizeof(Split)),
                  o_bins = take(cap * sizeof(NodeBins)), o_scr = take(cap * 12 * 4), o_small = take(((size_t)n / 2 + 2) * sizeof(uint4)),
                  o_done = take((size_t)n * sizeof(Active)), o_cnt = take(sizeof(Counts)), o_scan = take(scan_bytes);
-    SB_CU(cudaMalloc(&base, off));
+    SB_CU(rt_devcache::alloc(reinterpret_cast<void**>(&base), off));
     uint32_t* idx[2] = {reinterpret_cast<uint32_t*>(base + o_idx0), reinterpret_cast<uint32_t*>(base + o_idx1)};
     uint32_t* nod[2] = {reinterpret_cast<uint32_t*>(base + o_nod0), reinterpret_cast<uint32_t*>(base + o_nod1)};
     unsigned long long* flag = reinterpret_cast<unsigned long long*>(base + o_flag);
@@ -502,7 +502,7 @@ inline cudaError_t run(const Ref* d_refs, uint32_t n, const float* d_item_a, con
         SB_CU(cudaStreamSynchronize(st));
         n_active = h.n_next;
         cur ^= 1;
-        if (++levels > 200 || n_active > cap) { cudaFree(base); return cudaErrorUnknown; }
+        if (++levels > 200 || n_active > cap) { rt_devcache::release(base); return cudaErrorUnknown; }
     }
     if (h.n_small) k_small<<<(h.n_small + 3u) / 4u, 128, 0, st>>>(small, h.n_small, idx[cur], d_refs, d_item_a, d_item_c, d_item_ref, d_nodes, cnt, max_depth);
     if (h.n_done) k_fix_leaves<<<grid(h.n_done), TB, 0, st>>>(done, h.n_done, idx[cur], d_refs, d_item_ref, d_nodes);
@@ -511,7 +511,7 @@ inline cudaError_t run(const Ref* d_refs, uint32_t n, const float* d_item_a, con
     SB_CU(cudaStreamSynchronize(st));
     if (std::getenv("RT_PACK_LOG"))
         std::fprintf(stderr, "[rt_scene_create]   device SAH build: %d levels above %u references, %u warp-built subtrees, depth %u\n", levels, SMALL, h.n_small, h.depth);
-    cudaFree(base);
+    rt_devcache::release(base);
     out->n_nodes = n - 1u;
     out->depth = h.depth;
     out->root = 0u;

@@ -11,6 +11,9 @@
 // file:line citations refer to the reference repo.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -562,7 +565,10 @@ public:
         ItemArray items;
         std::vector<RtImage> images;
         std::vector<RtPerlin> perlins;
+        const auto t_describe = std::chrono::steady_clock::now();
         RtSceneDesc d = describe(items, images, perlins);
+        if (std::getenv("RT_PACK_LOG"))
+            std::fprintf(stderr, "[host mirror] flat form of the scene %8.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_describe).count());
         if (rt_scene_create(&d, device_ordinal, &dev_) != RT_OK) throw_rt("rt_scene_create");
         dev_ordinal_ = device_ordinal;
         return dev_;
