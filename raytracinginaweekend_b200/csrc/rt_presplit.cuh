@@ -9,6 +9,7 @@
 //
 // 10^6 triangles -> 2 * 10^6 references: 125 ms on 16 host cores, ~10 ms here (12 rounds of four small kernels + one scan each).
 #pragma once
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -103,6 +104,16 @@ __global__ void k_big_gather(const uint32_t* __restrict__ cand, uint32_t n_cand,
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n_cand && big[c]) out[pos[c]] = BigCand{area[c], cand[c], c};
 }
+// Selection of that round on the device: order the large candidates by (area descending, reference index ascending) with two stable
+// radix sorts — by reference index first, then by area — and drop everything after the first `room`.
+__global__ void k_sel_keys_ref(const BigCand* __restrict__ sel, uint32_t n, uint32_t* key, uint32_t* val) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { key[i] = sel[i].ref; val[i] = i; }
+}
+__global__ void k_sel_keys_area(const BigCand* __restrict__ sel, const uint32_t* __restrict__ perm, uint32_t n, unsigned long long* key, uint32_t* val) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const BigCand b = sel[perm[i]]; key[i] = (unsigned long long)__double_as_longlong(b.area); val[i] = b.c; }
+}
 __global__ void k_mark_dropped(const uint32_t* __restrict__ dropped, uint32_t n, uint8_t* big) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) big[dropped[i]] = 2;
@@ -169,12 +180,17 @@ inline cudaError_t run(const Box3* d_leaf, const float* d_tri, const uint8_t* d_
     if (n0 == 0) return cudaSuccess;
     const size_t B = std::max<size_t>(budget, n0);
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    size_t scan_bytes = 0;
+    size_t scan_bytes = 0, sort_bytes = 0, sort_bytes2 = 0;
     PS_CU(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)B, st));
+    PS_CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)B, 0, 32, st));
+    PS_CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_bytes2, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr,
+                                                    (uint32_t*)nullptr, (int)B, 0, 64, st));
+    sort_bytes = std::max(sort_bytes, sort_bytes2);
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += align(bytes); return o; };
     const size_t o_region = take(B * sizeof(Region)), o_cand0 = take(B * 4), o_cand1 = take(B * 4), o_code = take(B * 8), o_pos = take(B * 8),
-                 o_area = take(B * 8), o_big = take(B), o_cuts = take(B * sizeof(Cut)), o_ctr = take(sizeof(Counters)), o_scan = take(scan_bytes);
+                 o_area = take(B * 8), o_big = take(B), o_cuts = take(B * sizeof(Cut)), o_ctr = take(sizeof(Counters)), o_scan = take(scan_bytes),
+                 o_sort = take(sort_bytes), o_k32 = take(B * 4), o_k32b = take(B * 4), o_v32 = take(B * 4), o_v32b = take(B * 4), o_k64 = take(B * 8);
     PS_CU(rt_devcache::alloc(reinterpret_cast<void**>(&base), off));
     Region* region = reinterpret_cast<Region*>(base + o_region);
     uint32_t* cand[2] = {reinterpret_cast<uint32_t*>(base + o_cand0), reinterpret_cast<uint32_t*>(base + o_cand1)};
@@ -185,6 +201,12 @@ inline cudaError_t run(const Box3* d_leaf, const float* d_tri, const uint8_t* d_
     Cut* cuts = reinterpret_cast<Cut*>(base + o_cuts);
     Counters* ctr = reinterpret_cast<Counters*>(base + o_ctr);
     void* scan_tmp = base + o_scan;
+    void* sort_tmp = base + o_sort;
+    uint32_t* k32 = reinterpret_cast<uint32_t*>(base + o_k32);
+    uint32_t* k32b = reinterpret_cast<uint32_t*>(base + o_k32b);
+    uint32_t* v32 = reinterpret_cast<uint32_t*>(base + o_v32);
+    uint32_t* v32b = reinterpret_cast<uint32_t*>(base + o_v32b);
+    unsigned long long* k64 = reinterpret_cast<unsigned long long*>(base + o_k64);
     const int TB = 128;
     auto grid = [&](size_t n) { return (unsigned)((n + TB - 1) / TB); };
     auto totals = [&](uint32_t n, unsigned long long* out) -> cudaError_t {  // sum of code[0, n) from the exclusive scan
@@ -250,18 +272,14 @@ inline cudaError_t run(const Box3* d_leaf, const float* d_tri, const uint8_t* d_
                 PS_CU(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, code, pos, (int)n_cand, st));
                 k_big_gather<<<grid(n_cand), TB, 0, st>>>(cand[cur], n_cand, big, area, pos, d_sel);
                 PS_CU(cudaGetLastError());
-                std::vector<BigCand> sel(nb);
-                PS_CU(cudaMemcpyAsync(sel.data(), d_sel, (size_t)nb * sizeof(BigCand), cudaMemcpyDeviceToHost, st));
-                PS_CU(cudaStreamSynchronize(st));
-                auto larger = [](const BigCand& a, const BigCand& b) { return a.area > b.area || (a.area == b.area && a.ref < b.ref); };
-                std::nth_element(sel.begin(), sel.begin() + room, sel.end(), larger);
-                std::vector<uint32_t> dropped(nb - room);
-                for (size_t i = room; i < nb; ++i) dropped[i - room] = sel[i].c;
-                uint32_t* d_dropped = reinterpret_cast<uint32_t*>(pos);  // (free again until the scan after k_cut)
-                PS_CU(cudaMemcpyAsync(d_dropped, dropped.data(), dropped.size() * 4, cudaMemcpyHostToDevice, st));
-                k_mark_dropped<<<grid(dropped.size()), TB, 0, st>>>(d_dropped, (uint32_t)dropped.size(), big);
+                k_sel_keys_ref<<<grid(nb), TB, 0, st>>>(d_sel, nb, k32, v32);
                 PS_CU(cudaGetLastError());
-                PS_CU(cudaStreamSynchronize(st));  // `dropped` goes out of scope
+                PS_CU(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, k32, k32b, v32, v32b, (int)nb, 0, 32, st));
+                k_sel_keys_area<<<grid(nb), TB, 0, st>>>(d_sel, v32b, nb, k64, v32);
+                PS_CU(cudaGetLastError());
+                PS_CU(cub::DeviceRadixSort::SortPairsDescending(sort_tmp, sort_bytes, k64, code /* keys out: free until k_cut */, v32, v32b, (int)nb, 0, 64, st));
+                k_mark_dropped<<<grid(nb - room), TB, 0, st>>>(v32b + room, (uint32_t)(nb - room), big);
+                PS_CU(cudaGetLastError());
             }
             k_cut<<<grid(n_cand), TB, 0, st>>>(cand[cur], n_cand, big, d_refs, region, d_tri, cuts, code);
             PS_CU(cudaGetLastError());

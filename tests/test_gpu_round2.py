@@ -443,3 +443,18 @@ def test_device_built_tree_renders_the_same_film_with_the_same_work():
     assert images_equal_bits(out[0][0], out[1][0])
     assert out[0][3] == out[1][3]
     assert out[0][1] < 1.03 * out[1][1] and out[0][2] < 1.03 * out[1][2], out     # the device builder's tree is as good as the host builder's
+
+
+def test_device_block_cache_off_and_on_render_the_same():
+    """Scene memory taken from the per-GPU list of freed blocks ("device_cache_mb") or from cudaMalloc every time: nothing observable changes."""
+    size, spp, T = rb.Size2i(96, 64), 4, 4
+    films = []
+    for mb in (0, 2048, 2048, 0):
+        _cabi.set_option("device_cache_mb", mb)
+        for name in ("config:c1", "config:c5"):
+            W = rb.World.named(name)
+            films.append(rb.render(size, T, spp, 50, W, seed=11, device=0))
+            W.close()
+    _cabi.set_option("device_cache_mb", 2048)
+    for i in (2, 4, 6):
+        assert images_equal_bits(films[0], films[i]) and images_equal_bits(films[1], films[i + 1])
