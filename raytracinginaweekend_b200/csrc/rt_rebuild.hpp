@@ -600,7 +600,7 @@ inline void presplit(const Box3* leaf, size_t n0, const float* tri, const uint8_
             k = room;
         }
         cuts.resize_discard(k);
-        parallel_for(k, 2048, [&](size_t lo_i, size_t hi_i) {
+        parallel_for(k, 192, [&](size_t lo_i, size_t hi_i) {  // (a cut costs ~0.3 us: rounds of a few hundred candidates already pay for the pool)
             for (size_t c = lo_i; c < hi_i; ++c) {
                 const uint32_t r = cur[c].ref;
                 compute_cut(refs[r].box, tri + 9 * (size_t)refs[r].item, region[r], cuts[c]);
@@ -729,11 +729,8 @@ inline void build(const LeafSrc& leaf, uint32_t max_depth, Tree& out) {
         while (seen < deepest && !depth_max.compare_exchange_weak(seen, deepest)) {}
     };
     {
-        std::vector<std::thread> pool;
-        const unsigned n_thr = (unsigned)std::min<size_t>(hw, tasks.size());
-        for (unsigned i = 1; i < n_thr; ++i) pool.emplace_back(worker);
-        worker();
-        for (auto& th : pool) th.join();
+        const size_t n_thr = std::min<size_t>(hw, tasks.size());
+        parallel_for(n_thr, 1, [&](size_t a, size_t b) { for (size_t i = a; i < b; ++i) worker(); });  // the shared pool's threads pull tasks
     }
     out.depth = depth_max.load();
     auto ref_of = [&](const TopNode* c) -> uint32_t { return c->hi - c->lo == 1 ? (0x80000000u | top.recs[c->lo].id) : c->me; };
