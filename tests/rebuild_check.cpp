@@ -19,6 +19,33 @@ int main(int argc, char** argv) {
     std::mt19937 rng((unsigned)std::atoi(argv[2]));
     const double factor = std::atof(argv[3]);
     const int extra = std::atoi(argv[4]), mode = std::atoi(argv[5]);
+    if (mode == 3) {
+        // The worker pool behind every parallel loop (rt_rebuild::Pool): loops issued from several threads at once, each with a loop nested
+        // inside its chunks (the scene hand-off does both: helper threads beside the builder, whose big splits loop again).  A caller runs
+        // its first chunk and then helps with whatever is queued, so this must neither deadlock nor lose a chunk.
+        std::atomic<uint64_t> total{0};
+        std::vector<std::thread> callers;
+        for (int t = 0; t < 6; ++t)
+            callers.emplace_back([&, t] {
+                for (int rep = 0; rep < 8; ++rep)
+                    parallel_for(n, 64, [&](size_t a, size_t b) {
+                        uint64_t local = 0;
+                        parallel_for(b - a, 16, [&](size_t c, size_t d) {
+                            uint64_t s = 0;
+                            for (size_t i = a + c; i < a + d; ++i) s += i % 7 + (uint64_t)t;
+                            total.fetch_add(s);
+                        });
+                        (void)local;
+                    });
+            });
+        for (auto& th : callers) th.join();
+        uint64_t expect = 0;
+        for (int t = 0; t < 6; ++t)
+            for (size_t i = 0; i < n; ++i) expect += 8 * (i % 7 + (uint64_t)t);
+        CHECK(total.load() == expect, "pool lost or repeated work: %llu vs %llu", (unsigned long long)total.load(), (unsigned long long)expect);
+        std::printf("%s pool n=%zu\n", fails ? "FAILED" : "OK", n);
+        return fails ? 1 : 0;
+    }
     std::uniform_real_distribution<float> U(-1.0f, 1.0f);
     std::vector<Box3> leaf(n);
     std::vector<float> tri(9 * n, 0.0f);

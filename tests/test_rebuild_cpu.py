@@ -22,6 +22,7 @@ def checker(tmp_path_factory):
     (20000, 10, 1, 1, 0),      # no pre-splitting, threaded build, cap one level above the minimum
     (300000, 11, 2, 3, 0),     # 600 000 references: splits of >= 2^18 references scan, bin and partition on all cores (worker pool)
     (600000, 12, 2, 2, 1),     # sliver nests at that size: bucketed pre-split rounds with the budget ending inside a round
+    (3000, 13, 1, 0, 3),       # the shared worker pool: concurrent callers with nested loops (no deadlock, no lost chunk)
 ])
 def test_builder_invariants(checker, n, seed, factor, extra, mode):
     r = subprocess.run([checker, str(n), str(seed), str(factor), str(extra), str(mode)], capture_output=True, text=True, timeout=300)
