@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -57,10 +58,11 @@ class Pool {
         }
         cv_.notify_all();
         fn((size_t)0, n / parts);
-        while (pending.load(std::memory_order_acquire) != 0) {
+        for (int idle = 0; pending.load(std::memory_order_acquire) != 0;) {
             Job j;
-            if (pop(j)) exec(j);
-            else std::this_thread::yield();
+            if (pop(j)) { exec(j); idle = 0; }
+            else if (++idle < 256) std::this_thread::yield();
+            else std::this_thread::sleep_for(std::chrono::microseconds(50));  // a long chunk elsewhere: stop burning a core the workers could use
         }
     }
 

@@ -25,9 +25,9 @@ int main(int argc, char** argv) {
         // its first chunk and then helps with whatever is queued, so this must neither deadlock nor lose a chunk.
         std::atomic<uint64_t> total{0};
         std::vector<std::thread> callers;
-        for (int t = 0; t < 6; ++t)
+        for (int t = 0; t < 3; ++t)
             callers.emplace_back([&, t] {
-                for (int rep = 0; rep < 8; ++rep)
+                for (int rep = 0; rep < 4; ++rep)
                     parallel_for(n, 64, [&](size_t a, size_t b) {
                         uint64_t local = 0;
                         parallel_for(b - a, 16, [&](size_t c, size_t d) {
@@ -40,8 +40,8 @@ int main(int argc, char** argv) {
             });
         for (auto& th : callers) th.join();
         uint64_t expect = 0;
-        for (int t = 0; t < 6; ++t)
-            for (size_t i = 0; i < n; ++i) expect += 8 * (i % 7 + (uint64_t)t);
+        for (int t = 0; t < 3; ++t)
+            for (size_t i = 0; i < n; ++i) expect += 4 * (i % 7 + (uint64_t)t);
         CHECK(total.load() == expect, "pool lost or repeated work: %llu vs %llu", (unsigned long long)total.load(), (unsigned long long)expect);
         std::printf("%s pool n=%zu\n", fails ? "FAILED" : "OK", n);
         return fails ? 1 : 0;
