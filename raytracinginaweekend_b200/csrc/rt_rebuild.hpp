@@ -45,6 +45,7 @@ class Pool {
         size_t a, b;
         std::atomic<size_t>* pending;
     };
+    static constexpr unsigned MAX_THREADS = 32;  // these loops are memory-bound well before that; several processes per box (one per GPU) share the cores
     static Pool& get() {
         static Pool p;
         return p;
@@ -56,7 +57,10 @@ class Pool {
             std::lock_guard<std::mutex> lk(mu_);
             for (size_t p = 1; p < parts; ++p) q_.push_back(Job{&fn, n * p / parts, n * (p + 1) / parts, &pending});
         }
-        cv_.notify_all();
+        // wake as many workers as there are chunks to take, not all of them: on a 128-core box a round of four chunks would otherwise
+        // send 127 threads through the queue's mutex to find it empty
+        if (parts - 1 >= workers_.size()) cv_.notify_all();
+        else for (size_t p = 1; p < parts; ++p) cv_.notify_one();
         fn((size_t)0, n / parts);
         for (int idle = 0; pending.load(std::memory_order_acquire) != 0;) {
             Job j;
@@ -73,7 +77,7 @@ class Pool {
     std::vector<std::thread> workers_;
     bool stop_ = false;
     Pool() {
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned hw = std::min(MAX_THREADS, std::max(1u, std::thread::hardware_concurrency()));
         for (unsigned i = 1; i < hw; ++i)
             workers_.emplace_back([this] {
                 for (;;) {
@@ -110,7 +114,7 @@ class Pool {
 // Static chunking over hardware threads; fn(begin, end) works on disjoint index ranges, so results do not depend on the thread count.
 template <class F>
 inline void parallel_for(size_t n, size_t min_chunk, F&& fn) {
-    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t hw = std::min(Pool::MAX_THREADS, std::max(1u, std::thread::hardware_concurrency()));
     const size_t parts = std::max<size_t>(1, std::min(hw, n / std::max<size_t>(1, min_chunk)));
     if (parts <= 1) { fn((size_t)0, n); return; }
     const std::function<void(size_t, size_t)> f = [&fn](size_t a, size_t b) { fn(a, b); };
