@@ -1783,7 +1783,9 @@ void rt_scene_destroy(RtScene* scene) {
     cudaSetDevice(scene->device);
     const bool log = std::getenv("RT_PACK_LOG") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
-    if (log) cudaDeviceSynchronize();  // (logging only: separates "the device was still busy" from the cost of the frees)
+    // The scene's blocks go back to the block cache, not to cudaFree (which would wait for the device by itself): work a caller has
+    // queued against this scene (rt_trace_device / rt_render*_device on its own stream) must be over before another scene gets them.
+    cudaDeviceSynchronize();
     const auto t1 = std::chrono::steady_clock::now();
     delete scene;
     if (log)
