@@ -272,7 +272,9 @@ int rt_to_rgb8_gamma2_device(const float* d_rgb, uint64_t n_pixels, uint8_t* d_o
  * an extend warp that can no longer refill gives its rays max(this floor, 4 x the previous launch's mean tail) more rounds, then
  * parks what is still running (cursor + stack + best hit); the path waits one iteration and a second, small launch of the extend
  * kernel finishes the segment beside the next queue launch (default 64; 0 = never park; -n = exactly n rounds, for tests).
- * "blocks_per_sm": cap on resident blocks of the persistent kernels.
+ * "blocks_per_sm": cap on resident blocks of the persistent kernels.  "carveout": preferred shared-memory carve-out of the extend kernel in
+ * per cent (default 75: 171 KB of the SM's 228 KB for the traversal stacks, the rest stays L1; -1 = driver default).
+ * "debug_skip_redo": 1 = measurement only, keeps fast-path hits that were not proven (films are then NOT the reference's).
  * Environment: RT_ITER_LOG=<path> dumps (pipe, iteration, live paths, extend ms, shade ms, counters, parked, budget) of the last
  * render as CSV; RT_LONG_RAYS=<path> (with "count") the rays that took >= 4096 traversal rounds; RT_TAIL_LOG=1 (with "count") the
  * share of warp rounds after the queue ran dry / with a lane on the reference tree; RT_PACK_LOG=1 the phase times of

@@ -182,3 +182,14 @@ def test_lane_partition():
     assert sorted(sum(lanes, [])) == list(range(8))
     assert [dist.lane_samples(4, 10, i) for i in range(4)] == [3, 3, 2, 2]
     assert dist.lane_partition(2, 64, 3, 4)[2] == 0      # more ranks than lanes: this rank owns nothing
+
+
+def test_every_option_key_is_documented_in_the_header():
+    """rt_set_option keys accepted by the library (csrc/b200rt.cu) all appear, quoted, in include/b200rt.h's option list."""
+    import re
+    src = open(os.path.join(ROOT, "raytracinginaweekend_b200", "csrc", "b200rt.cu")).read()
+    hdr = open(os.path.join(ROOT, "include", "b200rt.h")).read()
+    keys = set(re.findall(r'k == "([a-z_]+)"', src))
+    assert len(keys) >= 20
+    missing = sorted(k for k in keys if '"%s"' % k not in hdr)
+    assert not missing, missing
